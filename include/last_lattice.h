@@ -1,0 +1,200 @@
+/*
+ * last_lattice.h -- C ABI of the B200 (sm_100a) lattice kernels.
+ *
+ * This is the drop-in boundary for the hot path of theadamsabra/last_torch:
+ * the semiring forward/backward recursion over the frames x context-states
+ * recognition lattice.  The reference has no FFI of its own (it is pure
+ * Python); each entry point below replaces the reference Python function that
+ * is cited beside it (file:line under /root/reference/last_torch/), and is what
+ * a ctypes binding inside the reference would call.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to dense row-major fp32 / int32 arrays
+ *     owned by the caller; nothing is allocated or freed by the library;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *   - every function returns LT_OK (0) or an error code; the message is
+ *     available from lt_last_error() (thread-local, so the autograd thread
+ *     and the main thread do not race);
+ *   - there is no global mutable state: calls are re-entrant.
+ *
+ * Shapes:  B utterances, T frames, V = vocab_size, n = context_size,
+ *   C = sum_{i<=n} V^i context states (FullNGram, contexts.py:181-182),
+ *   k = max_expansions (>= 1) for FrameLabelDependent, or LT_FRAME_DEPENDENT.
+ *   blank   [B,T,C]     lexical [B,T,C,V]   (weight_fns.py:66-75)
+ */
+#ifndef LAST_LATTICE_H_
+#define LAST_LATTICE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_OK 0
+#define LT_ERR_INVALID_ARGUMENT 1
+#define LT_ERR_CUDA 2
+#define LT_ERR_UNSUPPORTED 3
+
+/* semirings.py:143-173 (Real), :184-305 (Log), :308-401 (MaxTropical) */
+#define LT_REAL 0
+#define LT_LOG 1
+#define LT_MAXTROPICAL 2
+
+/* alignments.py:266-329 FrameDependent; any k >= 1 selects
+ * FrameLabelDependent(max_expansions=k), alignments.py:331-432 */
+#define LT_FRAME_DEPENDENT (-1)
+
+/* flags for lt_lattice_forward / lt_lattice_backward */
+#define LT_FLAG_FORCE_GENERIC 1u     /* never take the TMA/cluster fast path   */
+#define LT_FLAG_CLUSTER_SHIFT 8      /* bits 8..11: force cluster size (1,2,4,8) */
+
+int lt_version(void);
+const char* lt_last_error(void);
+/* Number of SMs, compute capability of the current device. */
+int lt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: RecognitionLattice._forward (lattices.py:379-496, loop :856-892) ----
+ * One persistent CTA cluster per utterance keeps alpha on chip for all T
+ * frames.  alpha_{t+1} = alignment.forward(alpha_t, blank_t, lexical_t)
+ * (alignments.py:294-297 / :370-376) with FullNGram.forward_reduce
+ * (contexts.py:207-230); frames t >= num_frames[b] leave alpha unchanged
+ * (lattices.py:460-461).
+ *   alpha_init  [B,C] or NULL (NULL: one-hot semiring-one at the start state,
+ *               lattices.py:801-807)
+ *   dist        [B]      (+)_c alpha_T[c]                  (lattices.py:496)
+ *   alphas      [B,T,C]  alpha_0 .. alpha_{T-1}, or NULL
+ *   alpha_final [B,C]    alpha_T, or NULL
+ *   levels      [B,T,k,C] FrameLabelDependent only: the k intermediate
+ *               `last` vectors of alignments.py:372-375 (needed by the
+ *               backward kernel); NULL otherwise
+ *   backptr     [B,T,max(k,1),C] int16, MaxTropical only or NULL: arg-max
+ *               source row-block of each forward_reduce (semirings.py:380-386);
+ *               for FrameDependent -1 means "blank arc won" (semirings.py:363)
+ *   termptr     [B,T,C] uint8, MaxTropical + FrameLabelDependent only: number
+ *               of lexical expansions taken (first arg-max, alignments.py:376)
+ */
+int lt_lattice_forward(int semiring, int vocab_size, int context_size,
+                       int max_expansions, const float* blank,
+                       const float* lexical, const int32_t* num_frames, int B,
+                       int T, const float* alpha_init, float* dist,
+                       float* alphas, float* alpha_final, float* levels,
+                       int16_t* backptr, uint8_t* termptr, unsigned flags,
+                       void* stream);
+
+/* ---- K2: backward (beta) recursion + arc posteriors as weight gradients ----
+ * Intent of RecognitionLattice._backward (lattices.py:686-799) with
+ * alignment.backward (alignments.py:300-318 / :378-418) and
+ * FullNGram.backward_broadcast (contexts.py:232-256); replaces autograd through
+ * the unrolled loop.  semiring is LT_LOG (marginals * grad_dist) or LT_REAL.
+ *   grad_blank [B,T,C], grad_lexical [B,T,C,V]: fully overwritten (padding
+ *   frames get zeros, lattices.py:775-779).
+ *   beta_final [B,C] or NULL: beta_0 (for diagnostics / chunked use).
+ */
+int lt_lattice_backward(int semiring, int vocab_size, int context_size,
+                        int max_expansions, const float* blank,
+                        const float* lexical, const int32_t* num_frames, int B,
+                        int T, const float* alphas, const float* levels,
+                        const float* dist, const float* grad_dist,
+                        float* grad_blank, float* grad_lexical,
+                        float* beta_final, unsigned flags, void* stream);
+
+/* ---- K5: Viterbi back-trace (replaces the vjp trick of lattices.py:221-247) ----
+ *   alpha_final [B,C] from the MaxTropical forward.
+ *   labels      [B,T,max(k,0)+1] int32: TRUE 1-based lexical labels, 0 = blank
+ *               / not taken (the reference reports y-1)
+ *   path_states [B,T+1] int32 or NULL: context state before each frame
+ *   grad_blank / grad_lexical: NULL, or PRE-ZEROED dense buffers that receive
+ *               grad_dist[b] (or 1 if grad_dist is NULL) on the arcs of the path
+ *               (semirings.py:366-369, :389-398).
+ */
+int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
+                         const int16_t* backptr, const uint8_t* termptr,
+                         const float* alpha_final, const int32_t* num_frames,
+                         int B, int T, int32_t* labels, int32_t* path_states,
+                         const float* grad_dist, float* grad_blank,
+                         float* grad_lexical, void* stream);
+
+/* ---- K3: numerator on the T x (U+1) label lattice (lattices.py:250-377) ----
+ * gather: weight_step_scan + gather_weight (lattices.py:300-342, :830-845)
+ *   states [B,U1] int32 = walk_states(labels) (contexts.py:109-146)
+ *   next_labels [B,U1] int32 in [1,V] (labels ++ [1], label 0 read as 1)
+ *   -> blank_w, lexical_w [B,T,U1]
+ * scatter_add: its transpose, grad_dense[b,t,states[u],(label-1)] += scale*g
+ */
+int lt_string_gather(int vocab_size, int num_states, const float* blank,
+                     const float* lexical, const int32_t* states,
+                     const int32_t* next_labels, int B, int T, int U1,
+                     float* blank_w, float* lexical_w, void* stream);
+int lt_string_scatter_add(int vocab_size, int num_states,
+                          const float* grad_blank_w, const float* grad_lexical_w,
+                          const int32_t* states, const int32_t* next_labels,
+                          int B, int T, int U1, float scale, float* grad_blank,
+                          float* grad_lexical, void* stream);
+/* shortest_distance_step_scan (lattices.py:347-377) with
+ * alignment.string_forward (alignments.py:327-329 / :427-432).
+ *   dist [B] = alpha_T[num_labels[b]] (semiring zero if num_labels > U)
+ *   alphas [B,T,U1] or NULL; backptr [B,T,U1] uint8 (MaxTropical) or NULL. */
+int lt_string_forward(int semiring, int max_expansions, const float* blank_w,
+                      const float* lexical_w, const int32_t* num_frames,
+                      const int32_t* num_labels, int B, int T, int U1,
+                      float* dist, float* alphas, uint8_t* backptr,
+                      void* stream);
+int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
+                       const float* lexical_w, const int32_t* num_frames,
+                       const int32_t* num_labels, int B, int T, int U1,
+                       const float* alphas, const uint8_t* backptr,
+                       const float* dist, const float* grad_dist,
+                       float* grad_blank_w, float* grad_lexical_w,
+                       void* stream);
+
+/* ---- semiring (+) on arbitrary tensors (semirings.py:202-220, :330-348) ----
+ * plus: elementwise on n elements (inputs already broadcast & contiguous).
+ * sum: a viewed as [outer, reduce, inner] -> out [outer, inner];
+ *      argmax [outer, inner] int32 (MaxTropical, may be NULL otherwise).
+ * backward kernels implement the "safe gradient" rules (semirings.py:222-241)
+ * and the tie rules a>=b / first arg-max (semirings.py:363, :382).
+ */
+int lt_semiring_plus_forward(int semiring, const float* a, const float* b,
+                             float* out, int64_t n, void* stream);
+int lt_semiring_plus_backward(int semiring, const float* a, const float* b,
+                              const float* grad_out, float* grad_a,
+                              float* grad_b, int64_t n, void* stream);
+int lt_semiring_sum_forward(int semiring, const float* a, int64_t outer,
+                            int64_t reduce, int64_t inner, float* out,
+                            int32_t* argmax, void* stream);
+int lt_semiring_sum_backward(int semiring, const float* a, const float* out,
+                             const int32_t* argmax, const float* grad_out,
+                             int64_t outer, int64_t reduce, int64_t inner,
+                             float* grad_a, void* stream);
+
+/* ---- K4: JointWeightFn (weight_fns.py:194-227) -------------------------------
+ * joint = tanh(cache @ w_ctx^T + frames @ w_frame^T)   [N, C, H]
+ * blank = joint @ w_blank + b_blank                     [N, C]
+ * lexical = joint @ w_vocab^T + b_vocab                 [N, C, V]
+ * N = number of frames (B*T for the whole-utterance call the lattice makes).
+ * proj_ctx [C,H] and proj_frame [N,H] are the two small input projections
+ * (computed by the caller; they are O(C*E*H + N*D*H) and not on the hot path).
+ * The vocabulary projection runs on tcgen05 tensor cores with a 3-way bf16
+ * split of both operands (fp32-accurate).
+ */
+int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
+                     const float* w_blank, float b_blank, const float* w_vocab,
+                     const float* b_vocab, int64_t N, int C, int H, int V,
+                     float* blank, float* lexical, void* stream);
+/* Gradients w.r.t. the joint pre-activation, reduced to the two projections:
+ *   grad_proj_ctx [C,H] (+= over N), grad_proj_frame [N,H] (+= over C),
+ *   grad_w_blank [H], grad_b_blank [1], grad_w_vocab [V,H], grad_b_vocab [V].
+ * All outputs must be pre-zeroed; they are accumulated with atomics. */
+int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
+                      const float* w_blank, const float* w_vocab,
+                      const float* grad_blank, const float* grad_lexical,
+                      int64_t N, int C, int H, int V, float* grad_proj_ctx,
+                      float* grad_proj_frame, float* grad_w_blank,
+                      float* grad_b_blank, float* grad_w_vocab,
+                      float* grad_b_vocab, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* LAST_LATTICE_H_ */

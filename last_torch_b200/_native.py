@@ -1,0 +1,121 @@
+"""ctypes binding of the C ABI in include/last_lattice.h.
+
+The shared library is built in-tree by `__graft_entry__.build()` (nvcc,
+sm_100a) as last_torch_b200/_C/liblast_lattice.so.  There is NO fallback: if
+the library is missing, or an op is handed a tensor that is not a contiguous
+fp32/int32 CUDA tensor, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_C', 'liblast_lattice.so')
+
+REAL, LOG, MAXTROPICAL = 0, 1, 2
+FRAME_DEPENDENT = -1
+FLAG_FORCE_GENERIC = 1
+FLAG_CLUSTER_SHIFT = 8
+
+_c_int = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_ptr = ctypes.c_void_p
+_c_float = ctypes.c_float
+_c_uint = ctypes.c_uint
+
+# name -> argtypes; every symbol declared in include/last_lattice.h.
+SIGNATURES = {
+    'lt_version': [],
+    'lt_last_error': [],
+    'lt_device_info': [_ptr, _ptr, _ptr],
+    'lt_lattice_forward': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
+    'lt_lattice_backward': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                            _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
+    'lt_viterbi_backtrace': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int,
+                             _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_string_gather': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                         _ptr, _ptr, _ptr],
+    'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                              _c_float, _ptr, _ptr, _ptr],
+    'lt_string_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                          _ptr, _ptr, _ptr, _ptr],
+    'lt_string_backward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_semiring_plus_forward': [_c_int, _ptr, _ptr, _ptr, _c_i64, _ptr],
+    'lt_semiring_plus_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _ptr],
+    'lt_semiring_sum_forward': [_c_int, _ptr, _c_i64, _c_i64, _c_i64, _ptr, _ptr, _ptr],
+    'lt_semiring_sum_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_i64, _c_i64, _ptr,
+                                 _ptr],
+    'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
+                         _ptr, _ptr, _ptr],
+    'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
+                          _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+  pass
+
+
+def lib():
+  """Loads liblast_lattice.so (once).  Raises loudly if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  with _lock:
+    if _lib is not None:
+      return _lib
+    if not os.path.exists(LIB_PATH):
+      raise NativeLibraryError(
+          f'{LIB_PATH} not found: build the CUDA extension first '
+          '(python -c "import __graft_entry__ as g; g.build()"). '
+          'last_torch_b200 has no CPU or eager fallback.')
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+      fn = getattr(handle, name)     # AttributeError if a symbol is missing
+      fn.argtypes = argtypes
+      fn.restype = ctypes.c_char_p if name == 'lt_last_error' else _c_int
+    _lib = handle
+  return _lib
+
+
+def check(rc: int, what: str) -> None:
+  if rc == 0:
+    return
+  msg = lib().lt_last_error()
+  msg = msg.decode('utf-8', 'replace') if msg else ''
+  if rc == 1:
+    raise ValueError(f'{what}: {msg}')
+  raise RuntimeError(f'{what} failed (status {rc}): {msg}')
+
+
+def ptr(t):
+  """Device pointer of a tensor (None -> NULL)."""
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+  """Validates that `t` is something the kernels can read: CUDA, `dtype`,
+  contiguous.  Never copies to or computes on the CPU."""
+  if not isinstance(t, torch.Tensor):
+    raise TypeError(f'{name} must be a torch.Tensor, got {type(t)}')
+  if not t.is_cuda:
+    raise RuntimeError(
+        f'{name} lives on {t.device}; last_torch_b200 runs on CUDA (sm_100a) only and has '
+        'no CPU fallback')
+  if t.dtype != dtype:
+    raise TypeError(f'{name} must have dtype {dtype}, got {t.dtype}')
+  return t.contiguous()

@@ -1,0 +1,254 @@
+// extern "C" entry points declared in include/last_lattice.h: argument
+// validation, geometry, kernel-path dispatch and error reporting.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "params.cuh"
+
+namespace lt {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return LT_ERR_CUDA;
+}
+
+static int device_sm_count(int* out) {
+  int dev = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return LT_OK;
+}
+
+static int check_arch() {
+  int dev = 0, major = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("last_lattice kernels are built for sm_100a (B200) only; current device has "
+              "compute capability major %d", major);
+    return LT_ERR_UNSUPPORTED;
+  }
+  return LT_OK;
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" {
+
+int lt_version(void) { return 100; }
+
+const char* lt_last_error(void) { return g_error; }
+
+int lt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  if (sm_count) LT_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) LT_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) LT_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return LT_OK;
+}
+
+static int check_common(const char* fn, int semiring, int V, int n, int k, int B, int T, NGram* g) {
+  LT_CHECK_ARG(semiring == LT_REAL || semiring == LT_LOG || semiring == LT_MAXTROPICAL,
+               "%s: unknown semiring %d", fn, semiring);
+  LT_CHECK_ARG(V > 0, "%s: vocab_size should be > 0, but got vocab_size=%d", fn, V);
+  LT_CHECK_ARG(n >= 0, "%s: context_size should be >= 0, but got context_size=%d", fn, n);
+  LT_CHECK_ARG(k == LT_FRAME_DEPENDENT || (k >= 1 && k <= 254),
+               "%s: max_expansions must be LT_FRAME_DEPENDENT or in [1, 254], got %d", fn, k);
+  LT_CHECK_ARG(B >= 0 && T >= 0, "%s: negative batch (%d) or frame count (%d)", fn, B, T);
+  LT_CHECK_ARG(make_ngram(V, n, g), "%s: FullNGram(vocab_size=%d, context_size=%d) has too many states",
+               fn, V, n);
+  LT_CHECK_ARG(V + 1 <= 32767, "%s: vocab_size %d exceeds the int16 back-pointer range", fn, V);
+  return LT_OK;
+}
+
+int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_expansions,
+                       const float* blank, const float* lexical, const int32_t* num_frames, int B,
+                       int T, const float* alpha_init, float* dist, float* alphas,
+                       float* alpha_final, float* levels, int16_t* backptr, uint8_t* termptr,
+                       unsigned flags, void* stream) {
+  NGram g;
+  int rc = check_common("lt_lattice_forward", semiring, vocab_size, context_size, max_expansions, B, T, &g);
+  if (rc) return rc;
+  LT_CHECK_ARG(dist && num_frames, "lt_lattice_forward: dist and num_frames must not be NULL");
+  LT_CHECK_ARG(T == 0 || (blank && lexical), "lt_lattice_forward: blank/lexical must not be NULL");
+  if (B == 0) return LT_OK;
+  if ((rc = check_arch())) return rc;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  FwdParams p = {};
+  p.g = g; p.k = max_expansions; p.B = B; p.T = T;
+  p.blank = blank; p.lexical = lexical; p.num_frames = num_frames; p.alpha_init = alpha_init;
+  p.dist = dist; p.alphas = alphas; p.alpha_final = alpha_final;
+  p.levels = max_expansions >= 1 ? levels : nullptr;
+  p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
+  p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
+  return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,
+                                        (cudaStream_t)stream);
+}
+
+int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_expansions,
+                        const float* blank, const float* lexical, const int32_t* num_frames, int B,
+                        int T, const float* alphas, const float* levels, const float* dist,
+                        const float* grad_dist, float* grad_blank, float* grad_lexical,
+                        float* beta_final, unsigned flags, void* stream) {
+  NGram g;
+  int rc = check_common("lt_lattice_backward", semiring, vocab_size, context_size, max_expansions, B, T, &g);
+  if (rc) return rc;
+  LT_CHECK_ARG(semiring != LT_MAXTROPICAL,
+               "lt_lattice_backward: MaxTropical gradients come from lt_viterbi_backtrace");
+  LT_CHECK_ARG(num_frames && dist, "lt_lattice_backward: num_frames and dist must not be NULL");
+  LT_CHECK_ARG(T == 0 || (blank && lexical && alphas && grad_blank && grad_lexical),
+               "lt_lattice_backward: blank/lexical/alphas/grad buffers must not be NULL");
+  LT_CHECK_ARG(max_expansions < 1 || levels || T == 0,
+               "lt_lattice_backward: FrameLabelDependent needs the `levels` buffer of the forward");
+  if (B == 0 || T == 0) return LT_OK;
+  if ((rc = check_arch())) return rc;
+  int sms = 0;
+  if ((rc = device_sm_count(&sms))) return rc;
+  BwdParams p = {};
+  p.g = g; p.k = max_expansions; p.B = B; p.T = T;
+  p.blank = blank; p.lexical = lexical; p.num_frames = num_frames;
+  p.alphas = alphas; p.levels = levels; p.dist = dist; p.grad_dist = grad_dist;
+  p.grad_blank = grad_blank; p.grad_lexical = grad_lexical; p.beta_final = beta_final;
+  return lattice_backward_generic_launch(semiring, g, max_expansions, p, flags, sms,
+                                         (cudaStream_t)stream);
+}
+
+int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
+                         const int16_t* backptr, const uint8_t* termptr, const float* alpha_final,
+                         const int32_t* num_frames, int B, int T, int32_t* labels,
+                         int32_t* path_states, const float* grad_dist, float* grad_blank,
+                         float* grad_lexical, void* stream) {
+  NGram g;
+  int rc = check_common("lt_viterbi_backtrace", LT_MAXTROPICAL, vocab_size, context_size,
+                        max_expansions, B, T, &g);
+  if (rc) return rc;
+  LT_CHECK_ARG(alpha_final && num_frames && labels,
+               "lt_viterbi_backtrace: alpha_final, num_frames and labels must not be NULL");
+  LT_CHECK_ARG(T == 0 || backptr, "lt_viterbi_backtrace: backptr must not be NULL");
+  LT_CHECK_ARG(max_expansions < 1 || termptr || T == 0,
+               "lt_viterbi_backtrace: FrameLabelDependent needs termptr");
+  if (B == 0) return LT_OK;
+  if ((rc = check_arch())) return rc;
+  VitParams p = {};
+  p.g = g; p.k = max_expansions; p.B = B; p.T = T;
+  p.backptr = backptr; p.termptr = termptr; p.alpha_final = alpha_final;
+  p.num_frames = num_frames; p.labels = labels; p.path_states = path_states;
+  p.grad_dist = grad_dist; p.grad_blank = grad_blank; p.grad_lexical = grad_lexical;
+  return viterbi_launch(p, (cudaStream_t)stream);
+}
+
+int lt_string_gather(int vocab_size, int num_states, const float* blank, const float* lexical,
+                     const int32_t* states, const int32_t* next_labels, int B, int T, int U1,
+                     float* blank_w, float* lexical_w, void* stream) {
+  LT_CHECK_ARG(vocab_size > 0 && num_states > 0 && B >= 0 && T >= 0 && U1 >= 1,
+               "lt_string_gather: bad sizes V=%d C=%d B=%d T=%d U1=%d", vocab_size, num_states, B, T, U1);
+  if (B == 0 || T == 0) return LT_OK;
+  LT_CHECK_ARG(blank && lexical && states && next_labels && blank_w && lexical_w,
+               "lt_string_gather: NULL pointer");
+  return string_gather_launch(vocab_size, num_states, blank, lexical, states, next_labels, B, T,
+                              U1, blank_w, lexical_w, (cudaStream_t)stream);
+}
+
+int lt_string_scatter_add(int vocab_size, int num_states, const float* grad_blank_w,
+                          const float* grad_lexical_w, const int32_t* states,
+                          const int32_t* next_labels, int B, int T, int U1, float scale,
+                          float* grad_blank, float* grad_lexical, void* stream) {
+  LT_CHECK_ARG(vocab_size > 0 && num_states > 0 && B >= 0 && T >= 0 && U1 >= 1,
+               "lt_string_scatter_add: bad sizes V=%d C=%d B=%d T=%d U1=%d", vocab_size, num_states, B, T, U1);
+  if (B == 0 || T == 0) return LT_OK;
+  LT_CHECK_ARG(grad_blank_w && grad_lexical_w && states && next_labels && grad_blank && grad_lexical,
+               "lt_string_scatter_add: NULL pointer");
+  return string_scatter_launch(vocab_size, num_states, grad_blank_w, grad_lexical_w, states,
+                               next_labels, B, T, U1, scale, grad_blank, grad_lexical,
+                               (cudaStream_t)stream);
+}
+
+static int check_string(const char* fn, int semiring, int k, int B, int T, int U1) {
+  LT_CHECK_ARG(semiring == LT_REAL || semiring == LT_LOG || semiring == LT_MAXTROPICAL,
+               "%s: unknown semiring %d", fn, semiring);
+  LT_CHECK_ARG(k == LT_FRAME_DEPENDENT || (k >= 1 && k <= 254),
+               "%s: max_expansions must be LT_FRAME_DEPENDENT or in [1, 254], got %d", fn, k);
+  LT_CHECK_ARG(B >= 0 && T >= 0 && U1 >= 1, "%s: bad sizes B=%d T=%d U1=%d", fn, B, T, U1);
+  return LT_OK;
+}
+
+int lt_string_forward(int semiring, int max_expansions, const float* blank_w,
+                      const float* lexical_w, const int32_t* num_frames,
+                      const int32_t* num_labels, int B, int T, int U1, float* dist, float* alphas,
+                      uint8_t* backptr, void* stream) {
+  int rc = check_string("lt_string_forward", semiring, max_expansions, B, T, U1);
+  if (rc) return rc;
+  LT_CHECK_ARG(num_frames && num_labels && dist, "lt_string_forward: NULL pointer");
+  LT_CHECK_ARG(T == 0 || (blank_w && lexical_w), "lt_string_forward: NULL weights");
+  StrParams p = {};
+  p.k = max_expansions; p.B = B; p.T = T; p.U1 = U1;
+  p.blank_w = blank_w; p.lexical_w = lexical_w; p.num_frames = num_frames;
+  p.num_labels = num_labels; p.dist = dist; p.alphas = alphas;
+  p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
+  return string_forward_launch(semiring, p, (cudaStream_t)stream);
+}
+
+int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
+                       const float* lexical_w, const int32_t* num_frames,
+                       const int32_t* num_labels, int B, int T, int U1, const float* alphas,
+                       const uint8_t* backptr, const float* dist, const float* grad_dist,
+                       float* grad_blank_w, float* grad_lexical_w, void* stream) {
+  int rc = check_string("lt_string_backward", semiring, max_expansions, B, T, U1);
+  if (rc) return rc;
+  if (B == 0 || T == 0) return LT_OK;
+  LT_CHECK_ARG(num_frames && num_labels && dist && grad_blank_w && grad_lexical_w && blank_w && lexical_w,
+               "lt_string_backward: NULL pointer");
+  LT_CHECK_ARG(semiring == LT_MAXTROPICAL ? backptr != nullptr : alphas != nullptr,
+               "lt_string_backward: needs alphas (Real/Log) or backptr (MaxTropical) from the forward");
+  StrParams p = {};
+  p.k = max_expansions; p.B = B; p.T = T; p.U1 = U1;
+  p.blank_w = blank_w; p.lexical_w = lexical_w; p.num_frames = num_frames;
+  p.num_labels = num_labels; p.alphas_in = alphas; p.backptr_in = backptr; p.dist_in = dist;
+  p.grad_dist = grad_dist; p.grad_blank_w = grad_blank_w; p.grad_lexical_w = grad_lexical_w;
+  return string_backward_launch(semiring, p, (cudaStream_t)stream);
+}
+
+int lt_semiring_plus_forward(int semiring, const float* a, const float* b, float* out, int64_t n,
+                             void* stream) {
+  LT_CHECK_ARG(n >= 0 && (n == 0 || (a && b && out)), "lt_semiring_plus_forward: bad arguments");
+  return semiring_plus_forward_launch(semiring, a, b, out, n, (cudaStream_t)stream);
+}
+
+int lt_semiring_plus_backward(int semiring, const float* a, const float* b, const float* grad_out,
+                              float* grad_a, float* grad_b, int64_t n, void* stream) {
+  LT_CHECK_ARG(n >= 0 && (n == 0 || (a && b && grad_out && grad_a && grad_b)),
+               "lt_semiring_plus_backward: bad arguments");
+  return semiring_plus_backward_launch(semiring, a, b, grad_out, grad_a, grad_b, n,
+                                       (cudaStream_t)stream);
+}
+
+int lt_semiring_sum_forward(int semiring, const float* a, int64_t outer, int64_t reduce,
+                            int64_t inner, float* out, int32_t* argmax, void* stream) {
+  LT_CHECK_ARG(outer >= 0 && reduce >= 0 && inner >= 0, "lt_semiring_sum_forward: negative extent");
+  return semiring_sum_forward_launch(semiring, a, outer, reduce, inner, out, argmax,
+                                     (cudaStream_t)stream);
+}
+
+int lt_semiring_sum_backward(int semiring, const float* a, const float* out, const int32_t* argmax,
+                             const float* grad_out, int64_t outer, int64_t reduce, int64_t inner,
+                             float* grad_a, void* stream) {
+  LT_CHECK_ARG(outer >= 0 && reduce >= 0 && inner >= 0, "lt_semiring_sum_backward: negative extent");
+  return semiring_sum_backward_launch(semiring, a, out, argmax, grad_out, outer, reduce, inner,
+                                      grad_a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

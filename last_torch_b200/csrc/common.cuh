@@ -1,0 +1,236 @@
+// Shared device/host helpers for the lattice kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/last_lattice.h"
+
+namespace lt {
+
+// ---------------------------------------------------------------------------
+// Error reporting (thread-local: autograd calls backward from its own thread).
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define LT_CHECK_ARG(cond, ...)                    \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::lt::set_error(__VA_ARGS__);                \
+      return LT_ERR_INVALID_ARGUMENT;              \
+    }                                              \
+  } while (0)
+
+#define LT_CUDA(call)                                        \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return ::lt::cuda_fail(e__, #call); \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// FullNGram geometry (contexts.py:181-230), computed once on the host.
+//   states 0 .. A-1      : "ascending" n-grams of order < n
+//   states A .. C-1      : the N = V^n full-order n-grams
+//   rows p < Alow        : their V arcs lead to ascending states; arc (p,y)
+//                          (flat index p*V+y) is the ONLY arc into state off+flat
+//   rows p >= Alow       : flat tail index j = (p-Alow)*V + y leads to state
+//                          A + (j mod N); every full-order state has K arcs,
+//                          at tail offsets (q-A) + kk*N, kk = 0..K-1
+// ---------------------------------------------------------------------------
+struct NGram {
+  int V, n, C;
+  int A;        // sum_{i<n} V^i
+  int Alow;     // sum_{i<n-1} V^i
+  int N;        // V^n
+  int K;        // (C - Alow) * V / N  (= V+1 for n>=1, V for n==0)
+  int off;      // 1 if n > 0 else 0
+  int pstride;  // source-state stride between consecutive kk: N / V (0 if n==0)
+};
+
+inline bool make_ngram(int V, int n, NGram* g) {
+  if (V <= 0 || n < 0) return false;
+  long long C = 0, pw = 1, A = 0, Alow = 0;
+  for (int i = 0; i <= n; ++i) {
+    if (i < n) A += pw;
+    if (i < n - 1) Alow += pw;
+    C += pw;
+    if (i < n) pw *= V;
+    if (C > (1ll << 28)) return false;
+  }
+  g->V = V; g->n = n; g->C = (int)C; g->A = (int)A; g->Alow = (int)Alow;
+  g->N = (int)pw;
+  g->K = (int)((C - Alow) * V / pw);
+  g->off = n > 0 ? 1 : 0;
+  g->pstride = n > 0 ? (int)(pw / V) : 0;
+  return true;
+}
+
+// dest state of arc (p, y0) with y0 zero-based: contexts.py:190-205.
+__host__ __device__ inline int ngram_next(const NGram& g, int p, int y0) {
+  if (p < g.Alow) return g.off + p * g.V + y0;
+  return g.A + ((p - g.Alow) * g.V + y0) % g.N;
+}
+
+// ---------------------------------------------------------------------------
+// Semiring scalar algebra.
+// ---------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
+__device__ __forceinline__ bool is_finite(float x) { return fabsf(x) <= 3.402823466e38f; }
+
+// Accurate-enough exp/log on the SFU (ex2.approx / lg2.approx have ~1-2 ulp
+// relative error on their normal range; far inside the 1e-5 parity budget).
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
+__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
+
+template <int SR> struct Sr;
+
+template <> struct Sr<LT_REAL> {
+  __device__ static float zero() { return 0.f; }
+  __device__ static float one() { return 1.f; }
+  __device__ static float times(float a, float b) { return a * b; }
+  __device__ static float plus(float a, float b) { return a + b; }
+};
+
+// semirings.py:247-255: c = max(a,b); non-finite c is replaced by 0.
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+  float c = fmaxf(a, b);
+  float cs = is_finite(c) ? c : 0.f;
+  float z = fast_exp(a - cs) + fast_exp(b - cs);
+  return cs + fast_log(z);
+}
+
+template <> struct Sr<LT_LOG> {
+  __device__ static float zero() { return neg_inf(); }
+  __device__ static float one() { return 0.f; }
+  __device__ static float times(float a, float b) { return a + b; }
+  __device__ static float plus(float a, float b) { return log_add_exp(a, b); }
+};
+
+template <> struct Sr<LT_MAXTROPICAL> {
+  __device__ static float zero() { return neg_inf(); }
+  __device__ static float one() { return 0.f; }
+  __device__ static float times(float a, float b) { return a + b; }
+  __device__ static float plus(float a, float b) { return fmaxf(a, b); }
+};
+
+// Running (+)-accumulator.  Log keeps (m, s) with value = msafe(m) + log(s),
+// msafe(m) = m if finite else 0 (semirings.py:281-285); MaxTropical keeps the
+// max and the FIRST arg-max (semirings.py:382); Real keeps the sum.
+template <int SR> struct Acc;
+
+template <> struct Acc<LT_REAL> {
+  float s;
+  __device__ void init() { s = 0.f; }
+  __device__ void add(float x, int) { s += x; }
+  __device__ void merge(const Acc& o) { s += o.s; }
+  __device__ float value() const { return s; }
+  __device__ int arg() const { return 0; }
+};
+
+__device__ __forceinline__ float msafe(float m) { return is_finite(m) ? m : 0.f; }
+
+template <> struct Acc<LT_LOG> {
+  float m, s;
+  __device__ void init() { m = neg_inf(); s = 0.f; }
+  // add one term (2 ex2 worst case; chunked callers use add_chunk instead)
+  __device__ void add(float x, int) {
+    float mn = fmaxf(m, x);
+    float ms = msafe(mn);
+    float sc = (m == neg_inf()) ? 0.f : fast_exp(msafe(m) - ms);
+    s = s * sc + fast_exp(x - ms);
+    m = mn;
+  }
+  // add a chunk with precomputed max `cm`: one rescale for the whole chunk.
+  template <int N> __device__ void add_chunk(const float (&x)[N], float cm) {
+    float mn = fmaxf(m, cm);
+    float ms = msafe(mn);
+    float sc = (m == neg_inf()) ? 0.f : fast_exp(msafe(m) - ms);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc += fast_exp(x[i] - ms);
+    s = s * sc + acc;
+    m = mn;
+  }
+  __device__ void merge(const Acc& o) {
+    float mn = fmaxf(m, o.m);
+    float ms = msafe(mn);
+    float sa = (m == neg_inf()) ? 0.f : fast_exp(msafe(m) - ms);
+    float sb = (o.m == neg_inf()) ? 0.f : fast_exp(msafe(o.m) - ms);
+    s = s * sa + o.s * sb;
+    m = mn;
+  }
+  __device__ float value() const { return msafe(m) + fast_log(s); }
+  __device__ int arg() const { return 0; }
+};
+
+template <> struct Acc<LT_MAXTROPICAL> {
+  float m; int a;
+  __device__ void init() { m = neg_inf(); a = 0; }
+  // callers feed candidates in ASCENDING index order, so strict '>' keeps the
+  // first arg-max (torch.argmax semantics, semirings.py:382).
+  __device__ void add(float x, int idx) { if (x > m) { m = x; a = idx; } }
+  __device__ void merge(const Acc& o) {
+    if (o.m > m || (o.m == m && o.a < a)) { m = o.m; a = o.a; }
+  }
+  __device__ float value() const { return m; }
+  __device__ int arg() const { return a; }
+};
+
+// ---------------------------------------------------------------------------
+// Thread-block cluster helpers (raw PTX; cluster size 1 is legal too).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// Address of the same shared-memory variable in CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t map_shared_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+
+// Streaming (read-once) global loads: keep them out of L1.
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace lt

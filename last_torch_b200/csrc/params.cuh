@@ -1,0 +1,103 @@
+// Kernel parameter blocks and launcher prototypes shared by capi.cu and the
+// kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace lt {
+
+struct FwdParams {
+  NGram g;
+  int k;            // max_expansions, or -1 for FrameDependent
+  int B, T;
+  int dslice;       // destination states per CTA
+  int ppad;         // capacity of the partial buffers (entries)
+  const float* blank;
+  const float* lexical;
+  const int32_t* num_frames;
+  const float* alpha_init;
+  float* dist;
+  float* alphas;
+  float* alpha_final;
+  float* levels;
+  int16_t* backptr;
+  uint8_t* termptr;
+};
+
+struct BwdParams {
+  NGram g;
+  int k;            // max_expansions, or -1 for FrameDependent
+  int B, T;
+  int dslice;
+  int lpr;          // lanes per row (power of two <= 32)
+  const float* blank;
+  const float* lexical;
+  const int32_t* num_frames;
+  const float* alphas;
+  const float* levels;
+  const float* dist;
+  const float* grad_dist;
+  float* grad_blank;
+  float* grad_lexical;
+  float* beta_final;
+};
+
+struct StrParams {
+  int k;       // max_expansions or -1
+  int B, T, U1;
+  const float* blank_w;
+  const float* lexical_w;
+  const int32_t* num_frames;
+  const int32_t* num_labels;
+  float* dist;
+  float* alphas;
+  uint8_t* backptr;
+  // backward only
+  const float* alphas_in;
+  const uint8_t* backptr_in;
+  const float* dist_in;
+  const float* grad_dist;
+  float* grad_blank_w;
+  float* grad_lexical_w;
+};
+
+struct VitParams {
+  NGram g;
+  int k;    // -1 FrameDependent
+  int B, T;
+  int frames_per_chunk;   // 0: read back-pointers straight from global memory
+  const int16_t* backptr;
+  const uint8_t* termptr;
+  const float* alpha_final;
+  const int32_t* num_frames;
+  int32_t* labels;
+  int32_t* path_states;
+  const float* grad_dist;
+  float* grad_blank;
+  float* grad_lexical;
+};
+
+int lattice_forward_generic_launch(int semiring, const NGram& g, int k, const FwdParams& base,
+                                   unsigned flags, int sm_count, cudaStream_t stream);
+int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const BwdParams& base,
+                                    unsigned flags, int sm_count, cudaStream_t stream);
+int viterbi_launch(const VitParams& base, cudaStream_t stream);
+int string_gather_launch(int V, int C, const float* blank, const float* lexical,
+                         const int32_t* states, const int32_t* labels, int B, int T, int U1,
+                         float* blank_w, float* lexical_w, cudaStream_t stream);
+int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
+                          const int32_t* states, const int32_t* labels, int B, int T, int U1,
+                          float scale, float* gblank, float* glex, cudaStream_t stream);
+int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);
+int string_backward_launch(int semiring, const StrParams& p, cudaStream_t stream);
+int semiring_plus_forward_launch(int sr, const float* a, const float* b, float* out, int64_t n,
+                                 cudaStream_t stream);
+int semiring_plus_backward_launch(int sr, const float* a, const float* b, const float* g,
+                                  float* ga, float* gb, int64_t n, cudaStream_t stream);
+int semiring_sum_forward_launch(int sr, const float* a, int64_t outer, int64_t R, int64_t inner,
+                                float* out, int32_t* argmax, cudaStream_t stream);
+int semiring_sum_backward_launch(int sr, const float* a, const float* out, const int32_t* argmax,
+                                 const float* g, int64_t outer, int64_t R, int64_t inner,
+                                 float* ga, cudaStream_t stream);
+int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);
+
+}  // namespace lt

@@ -1,0 +1,308 @@
+// K3: numerator lattice = recognition lattice intersected with the reference
+// label string (RecognitionLattice._string_forward,
+// /root/reference/last_torch/lattices.py:250-377).
+//
+//  * string_gather / string_scatter_add: weight_step_scan + gather_weight
+//    (lattices.py:300-342, :830-845) and its transpose.
+//  * string_forward: shortest_distance_step_scan (lattices.py:347-377) with
+//    alignment.string_forward (alignments.py:327-329 / :427-432).
+//  * string_backward: chain forward-backward giving d numerator / d weights
+//    (the reference relies on autograd here, broken as shipped: SURVEY D1/D2).
+//
+// The chain has only U+1 states, so one CTA per utterance with one thread per
+// chain state; alpha/beta live in shared memory for all T frames.
+#include "common.cuh"
+#include "params.cuh"
+
+namespace lt {
+
+// ------------------------------------------------------------------ gather --
+__global__ void string_gather_kernel(int V, int C, const float* __restrict__ blank,
+                                     const float* __restrict__ lexical,
+                                     const int32_t* __restrict__ states,
+                                     const int32_t* __restrict__ labels, int T, int U1,
+                                     float* __restrict__ blank_w, float* __restrict__ lexical_w) {
+  const size_t bt = blockIdx.x;           // b * T + t
+  const int b = (int)(bt / T);
+  const float* bl = blank + bt * C;
+  const float* lx = lexical + bt * (size_t)C * V;
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+    const int s = states[(size_t)b * U1 + u];
+    const int y = labels[(size_t)b * U1 + u] - 1;
+    blank_w[bt * U1 + u] = bl[s];
+    lexical_w[bt * U1 + u] = lx[(size_t)s * V + y];
+  }
+}
+
+__global__ void string_scatter_kernel(int V, int C, const float* __restrict__ gbw,
+                                      const float* __restrict__ glw,
+                                      const int32_t* __restrict__ states,
+                                      const int32_t* __restrict__ labels, int T, int U1,
+                                      float scale, float* __restrict__ gblank,
+                                      float* __restrict__ glex) {
+  const size_t bt = blockIdx.x;
+  const int b = (int)(bt / T);
+  float* bl = gblank + bt * C;
+  float* lx = glex + bt * (size_t)C * V;
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+    const int s = states[(size_t)b * U1 + u];
+    const int y = labels[(size_t)b * U1 + u] - 1;
+    const float a = gbw[bt * U1 + u], c = glw[bt * U1 + u];
+    if (a != 0.f) atomicAdd(bl + s, scale * a);
+    if (c != 0.f) atomicAdd(lx + (size_t)s * V + y, scale * c);
+  }
+}
+
+// ------------------------------------------------------------------ forward --
+
+// last_i[u] = alpha[u-i] (x) lex[u-i] (x) ... (x) lex[u-1], associated in the
+// reference's order (alignments.py:429-430); semiring zero if u < i.
+template <int SR>
+__device__ __forceinline__ float chain_last(const float* alpha, const float* lx, int u, int i) {
+  using S = Sr<SR>;
+  if (u < i) return S::zero();
+  float v = alpha[u - i];
+  for (int j = i; j >= 1; --j) v = S::times(v, lx[u - j]);
+  return v;
+}
+
+template <int SR, bool FLD>
+__global__ void string_forward_kernel(const StrParams p) {
+  using S = Sr<SR>;
+  extern __shared__ float smem[];
+  const int b = blockIdx.x, U1 = p.U1;
+  float* a0 = smem;
+  float* a1 = smem + U1;
+  int nf = max(0, min(p.num_frames[b], p.T));
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) a0[u] = (u == 0) ? S::one() : S::zero();
+  __syncthreads();
+  float* cur = a0; float* nxt = a1;
+  for (int t = 0; t < p.T; ++t) {
+    const size_t off = ((size_t)b * p.T + t) * U1;
+    if (p.alphas)
+      for (int u = threadIdx.x; u < U1; u += blockDim.x) p.alphas[off + u] = cur[u];
+    if (t >= nf) continue;       // uniform per block
+    const float* bl = p.blank_w + off;
+    const float* lx = p.lexical_w + off;
+    for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+      if constexpr (!FLD) {
+        const float a = S::times(cur[u], bl[u]);
+        const float l = (u > 0) ? S::times(cur[u - 1], lx[u - 1]) : S::zero();
+        if constexpr (SR == LT_MAXTROPICAL) {
+          const bool tb = a >= l;
+          nxt[u] = tb ? a : l;
+          if (p.backptr) p.backptr[off + u] = tb ? 0 : 1;
+        } else {
+          nxt[u] = S::plus(a, l);
+        }
+      } else {
+        Acc<SR> acc; acc.init();
+        const float bu = bl[u];
+        for (int i = 0; i <= p.k; ++i)
+          acc.add(S::times(chain_last<SR>(cur, lx, u, i), bu), i);
+        nxt[u] = acc.value();
+        if constexpr (SR == LT_MAXTROPICAL) { if (p.backptr) p.backptr[off + u] = (uint8_t)acc.arg(); }
+      }
+    }
+    __syncthreads();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (threadIdx.x == 0) {
+    const int nl = p.num_labels[b];
+    p.dist[b] = (nl >= 0 && nl < U1) ? cur[nl] : S::zero();   // lattices.py:375-377
+  }
+}
+
+// ----------------------------------------------------------------- backward --
+template <int SR, bool FLD>
+__global__ void string_backward_kernel(const StrParams p) {
+  using S = Sr<SR>;
+  extern __shared__ float smem[];
+  const int b = blockIdx.x, U1 = p.U1;
+  float* b0 = smem;
+  float* b1 = smem + U1;
+  float* n0 = smem + 2 * U1;    // FLD level buffers
+  float* n1 = smem + 3 * U1;
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  const int nl = p.num_labels[b];
+  const float z = p.dist_in[b];
+  const float g = p.grad_dist ? p.grad_dist[b] : 1.f;
+  const bool reachable = (nl >= 0 && nl < U1) &&
+                         (SR == LT_REAL ? true : is_finite(z));
+  const size_t base = (size_t)b * p.T * U1;
+  // zero everything first (padding frames, unreachable utterances, MaxTropical)
+  const int t_zero_from = (reachable && SR != LT_MAXTROPICAL) ? nf : 0;
+  for (size_t i = (size_t)t_zero_from * U1 + threadIdx.x; i < (size_t)p.T * U1; i += blockDim.x) {
+    p.grad_blank_w[base + i] = 0.f;
+    p.grad_lexical_w[base + i] = 0.f;
+  }
+  if (!reachable) return;
+
+  if constexpr (SR == LT_MAXTROPICAL) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int u = nl;
+      for (int t = nf - 1; t >= 0; --t) {
+        const size_t off = base + (size_t)t * U1;
+        const int i = p.backptr_in[off + u];
+        p.grad_blank_w[off + u] += g;
+        for (int j = 1; j <= i; ++j) p.grad_lexical_w[off + u - j] += g;
+        u -= i;
+      }
+    }
+    return;
+  } else {
+    for (int u = threadIdx.x; u < U1; u += blockDim.x) b0[u] = (u == nl) ? S::one() : S::zero();
+    __syncthreads();
+    float* beta = b0; float* nxt = b1;
+    for (int t = nf - 1; t >= 0; --t) {
+      const size_t off = base + (size_t)t * U1;
+      const float* bl = p.blank_w + off;
+      const float* lx = p.lexical_w + off;
+      const float* al = p.alphas_in + off;
+      if constexpr (!FLD) {
+        for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+          const float bn = (u + 1 < U1) ? beta[u + 1] : S::zero();
+          const float bb = S::times(bl[u], beta[u]);
+          const float lb = S::times(lx[u], bn);
+          if constexpr (SR == LT_LOG) {
+            p.grad_blank_w[off + u] = g * fast_exp(al[u] + bb - z);
+            p.grad_lexical_w[off + u] = g * fast_exp(al[u] + lb - z);
+          } else {
+            p.grad_blank_w[off + u] = g * al[u] * beta[u];
+            p.grad_lexical_w[off + u] = g * al[u] * bn;
+          }
+          nxt[u] = S::plus(bb, lb);
+        }
+        __syncthreads();
+      } else {
+        const int k = p.k;
+        float* nb = n0; float* out = n1;
+        for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+          const float bb = S::times(bl[u], beta[u]);
+          nb[u] = bb;
+          float acc = 0.f;
+          for (int i = 0; i <= k; ++i) {
+            const float li = chain_last<SR>(al, lx, u, i);
+            if constexpr (SR == LT_LOG) acc += fast_exp(li + bb - z);
+            else acc += li;
+          }
+          if constexpr (SR == LT_LOG) p.grad_blank_w[off + u] = g * acc;
+          else p.grad_blank_w[off + u] = g * acc * beta[u];
+        }
+        __syncthreads();
+        for (int j = k - 1; j >= 0; --j) {
+          for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+            const float bn = (u + 1 < U1) ? nb[u + 1] : S::zero();
+            const float lb = S::times(lx[u], bn);
+            const float lj = chain_last<SR>(al, lx, u, j);
+            float gv;
+            if constexpr (SR == LT_LOG) gv = g * fast_exp(lj + lb - z);
+            else gv = g * lj * bn;
+            if (j == k - 1) p.grad_lexical_w[off + u] = gv;
+            else p.grad_lexical_w[off + u] += gv;
+            out[u] = S::plus(S::times(bl[u], beta[u]), lb);
+          }
+          __syncthreads();
+          float* tmp = nb; nb = out; out = tmp;
+        }
+        for (int u = threadIdx.x; u < U1; u += blockDim.x) nxt[u] = nb[u];
+        __syncthreads();
+      }
+      float* tmp = beta; beta = nxt; nxt = tmp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------- launch --
+static int block_for(int U1) {
+  int b = 32;
+  while (b < U1 && b < 1024) b *= 2;
+  return b;
+}
+
+int string_gather_launch(int V, int C, const float* blank, const float* lexical,
+                         const int32_t* states, const int32_t* labels, int B, int T, int U1,
+                         float* blank_w, float* lexical_w, cudaStream_t stream) {
+  if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
+  string_gather_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
+      V, C, blank, lexical, states, labels, T, U1, blank_w, lexical_w);
+  LT_CUDA(cudaGetLastError());
+  return LT_OK;
+}
+
+int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
+                          const int32_t* states, const int32_t* labels, int B, int T, int U1,
+                          float scale, float* gblank, float* glex, cudaStream_t stream) {
+  if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
+  string_scatter_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
+      V, C, gbw, glw, states, labels, T, U1, scale, gblank, glex);
+  LT_CUDA(cudaGetLastError());
+  return LT_OK;
+}
+
+template <int SR>
+static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
+  const int block = block_for(p.U1);
+  const size_t smem = sizeof(float) * 2 * p.U1;
+  if (p.k >= 1) {
+    LT_CUDA(cudaFuncSetAttribute(string_forward_kernel<SR, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    string_forward_kernel<SR, true><<<p.B, block, smem, stream>>>(p);
+  } else {
+    LT_CUDA(cudaFuncSetAttribute(string_forward_kernel<SR, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    string_forward_kernel<SR, false><<<p.B, block, smem, stream>>>(p);
+  }
+  LT_CUDA(cudaGetLastError());
+  return LT_OK;
+}
+
+template <int SR>
+static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
+  const int block = block_for(p.U1);
+  const size_t smem = sizeof(float) * 4 * p.U1;
+  if (p.k >= 1) {
+    LT_CUDA(cudaFuncSetAttribute(string_backward_kernel<SR, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    string_backward_kernel<SR, true><<<p.B, block, smem, stream>>>(p);
+  } else {
+    LT_CUDA(cudaFuncSetAttribute(string_backward_kernel<SR, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    string_backward_kernel<SR, false><<<p.B, block, smem, stream>>>(p);
+  }
+  LT_CUDA(cudaGetLastError());
+  return LT_OK;
+}
+
+int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream) {
+  if (p.B == 0) return LT_OK;
+  if ((size_t)p.U1 * 4 * sizeof(float) > 200 * 1024) {
+    set_error("lt_string_forward: U+1 = %d label states do not fit in shared memory", p.U1);
+    return LT_ERR_UNSUPPORTED;
+  }
+  switch (semiring) {
+    case LT_REAL: return string_fwd_sr<LT_REAL>(p, stream);
+    case LT_LOG: return string_fwd_sr<LT_LOG>(p, stream);
+    case LT_MAXTROPICAL: return string_fwd_sr<LT_MAXTROPICAL>(p, stream);
+  }
+  set_error("lt_string_forward: unknown semiring %d", semiring);
+  return LT_ERR_INVALID_ARGUMENT;
+}
+
+int string_backward_launch(int semiring, const StrParams& p, cudaStream_t stream) {
+  if (p.B == 0) return LT_OK;
+  if ((size_t)p.U1 * 4 * sizeof(float) > 200 * 1024) {
+    set_error("lt_string_backward: U+1 = %d label states do not fit in shared memory", p.U1);
+    return LT_ERR_UNSUPPORTED;
+  }
+  switch (semiring) {
+    case LT_REAL: return string_bwd_sr<LT_REAL>(p, stream);
+    case LT_LOG: return string_bwd_sr<LT_LOG>(p, stream);
+    case LT_MAXTROPICAL: return string_bwd_sr<LT_MAXTROPICAL>(p, stream);
+  }
+  set_error("lt_string_backward: unknown semiring %d", semiring);
+  return LT_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace lt

@@ -1,0 +1,72 @@
+"""JointWeightFn over all frames (weight_fns.py:194-227), whole-utterance form.
+
+The two small input projections ([C,E]x[E,H] and [N,D]x[D,H]) are library
+GEMMs; the hot part -- tanh of the [N,C,H] joint and its projection to
+[N,C,1+V] -- goes through the C ABI (lt_joint_forward / lt_joint_backward).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+
+class _JointProjection(torch.autograd.Function):
+  """(blank [N,C], lexical [N,C,V]) from proj_ctx [C,H], proj_frame [N,H]."""
+
+  @staticmethod
+  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab):
+    proj_ctx = N.require_cuda(proj_ctx, 'proj_ctx')
+    proj_frame = N.require_cuda(proj_frame, 'proj_frame')
+    w_blank = N.require_cuda(w_blank.reshape(-1), 'w_blank')
+    w_vocab = N.require_cuda(w_vocab, 'w_vocab')
+    b_vocab = N.require_cuda(b_vocab, 'b_vocab')
+    n, h = proj_frame.shape
+    c = proj_ctx.shape[0]
+    v = w_vocab.shape[0]
+    dev = proj_frame.device
+    blank = torch.empty([n, c], dtype=torch.float32, device=dev)
+    lexical = torch.empty([n, c, v], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_joint_forward(
+          N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), float(b_blank), N.ptr(w_vocab),
+          N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.stream_ptr(dev)),
+          'lt_joint_forward')
+    ctx.save_for_backward(proj_ctx, proj_frame, w_blank, w_vocab)
+    return blank, lexical
+
+  @staticmethod
+  def backward(ctx, g_blank, g_lexical):
+    proj_ctx, proj_frame, w_blank, w_vocab = ctx.saved_tensors
+    n, h = proj_frame.shape
+    c = proj_ctx.shape[0]
+    v = w_vocab.shape[0]
+    dev = proj_frame.device
+    g_blank = N.require_cuda(g_blank, 'grad_blank')
+    g_lexical = N.require_cuda(g_lexical, 'grad_lexical')
+    g_pc = torch.zeros_like(proj_ctx)
+    g_pf = torch.zeros_like(proj_frame)
+    g_wb = torch.zeros_like(w_blank)
+    g_bb = torch.zeros([1], dtype=torch.float32, device=dev)
+    g_wv = torch.zeros_like(w_vocab)
+    g_bv = torch.zeros([v], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_joint_backward(
+          N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(w_vocab), N.ptr(g_blank),
+          N.ptr(g_lexical), n, c, h, v, N.ptr(g_pc), N.ptr(g_pf), N.ptr(g_wb), N.ptr(g_bb),
+          N.ptr(g_wv), N.ptr(g_bv), N.stream_ptr(dev)), 'lt_joint_backward')
+    return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv
+
+
+def joint_all_frames(fn, cache, frames):
+  """fn: weight_fns.JointWeightFn; cache [C,E]; frames [batch..., T, D]."""
+  batch_shape = frames.shape[:-1]
+  proj_ctx = fn.context_projection(cache)                                   # [C,H]
+  proj_frame = fn.blank_projection(frames.reshape(-1, frames.shape[-1]))    # [N,H]
+  blank, lexical = _JointProjection.apply(
+      proj_ctx, proj_frame, fn.joint_projection_to_blank.weight,
+      fn.joint_projection_to_blank.bias.reshape(()), fn.joint_projection_to_vocab.weight,
+      fn.joint_projection_to_vocab.bias)
+  c, v = proj_ctx.shape[0], fn.vocab_size
+  return blank.reshape(*batch_shape, c), lexical.reshape(*batch_shape, c, v)

@@ -1,0 +1,225 @@
+"""Recognition lattice (drop-in for last_torch.RecognitionLattice).
+
+Same constructor and methods as the reference
+(/root/reference/last_torch/lattices.py:35-799): forward (the GNAT loss),
+shortest_path, build_cache and the unit-tested privates _forward,
+_string_forward, _forward_backward.  What changed underneath:
+
+  * the weight function is evaluated ONCE over all frames
+    (WeightFn.all_frames) instead of once per Python loop iteration;
+  * the T-frame semiring recursion (lattices.py:436-462, :856-892) is a single
+    persistent CUDA kernel (ops.LatticeForward / K1);
+  * gradients come from a hand-written backward (beta) recursion that writes
+    arc posteriors as the weight gradient (K2) -- the reference's
+    _forward_backward has no working backward;
+  * shortest_path follows back-pointers (K5) instead of differentiating through
+    the unrolled loop, and reports the true 1-based labels.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Callable, Sequence
+from typing import Generic, Optional, TypeVar
+
+import torch
+from torch import nn
+
+from . import _native as N
+from . import alignments
+from . import contexts
+from . import ops
+from . import semirings
+from . import weight_fns
+
+T = TypeVar('T')
+
+
+class RecognitionLattice(nn.Module, Generic[T]):
+  """Recognition lattice in the GNAT formulation: context dependency x
+  alignment lattice x weight function (lattices.py:35-116)."""
+
+  def __init__(self, context: contexts.ContextDependency,
+               alignment: alignments.TimeSyncAlignmentLattice,
+               weight_fn_cacher_factory: Callable[[contexts.ContextDependency],
+                                                  weight_fns.WeightFnCacher[T]],
+               weight_fn_factory: Callable[[contexts.ContextDependency],
+                                           weight_fns.WeightFn[T]]):
+    super().__init__()
+    self.context = context
+    self.alignment = alignment
+    self.weight_fn_cacher_factory = weight_fn_cacher_factory
+    self.weight_fn_factory = weight_fn_factory
+    self.weight_fn_cacher = self.weight_fn_cacher_factory(self.context)
+    self.weight_fn = self.weight_fn_factory(self.context)
+    # kernel dispatch options (see include/last_lattice.h); 0 = automatic
+    self.kernel_flags = 0
+
+  def build_cache(self) -> T:
+    """Builds the weight function cache (lattices.py:118-129)."""
+    return self.weight_fn_cacher()
+
+  # -- helpers ---------------------------------------------------------------
+
+  def _geometry(self):
+    """(V, n, k) for the kernels; raises for anything they do not implement."""
+    if not isinstance(self.context, contexts.FullNGram):
+      raise NotImplementedError(
+          'the lattice kernels implement contexts.FullNGram only; got '
+          f'{type(self.context).__name__} (no fallback path exists)')
+    if not isinstance(self.alignment, alignments.TimeSyncAlignmentLattice):
+      raise NotImplementedError(f'unsupported alignment {type(self.alignment).__name__}')
+    return (self.context.vocab_size, self.context.context_size,
+            self.alignment.kernel_max_expansions())
+
+  @staticmethod
+  def _check_frames(frames, num_frames):
+    batch_dims = tuple(num_frames.shape)
+    if tuple(frames.shape[:-2]) != batch_dims:
+      raise ValueError('frames and num_frames have different batch_dims: '
+                       f'{tuple(frames.shape[:-2])} vs {batch_dims}')
+    return batch_dims
+
+  @staticmethod
+  def _check_labels(labels, num_labels, batch_dims):
+    if tuple(labels.shape[:-1]) != batch_dims:
+      raise ValueError('labels and num_frames have different batch_dims: '
+                       f'{tuple(labels.shape[:-1])} vs {batch_dims}')
+    if tuple(num_labels.shape) != batch_dims:
+      raise ValueError('num_labels and num_frames have different batch_dims: '
+                       f'{tuple(num_labels.shape)} vs {batch_dims}')
+
+  def _arc_weights(self, cache, frames, batch_dims):
+    """Dense arc weights of all frames, flattened to one batch axis:
+    blank [B,T,C], lexical [B,T,C,V] (fp32, contiguous, CUDA)."""
+    blank, lexical = self.weight_fn.all_frames(cache, frames)
+    c, v = self.context.shape()
+    t = frames.shape[-2]
+    blank = blank.reshape(-1, t, c)
+    lexical = lexical.reshape(-1, t, c, v)
+    if not blank.is_cuda:
+      raise RuntimeError(
+          f'arc weights live on {blank.device}; last_torch_b200 runs on CUDA (sm_100a) only '
+          'and has no CPU fallback -- move frames / weight function to a CUDA device')
+    if blank.dtype != torch.float32 or lexical.dtype != torch.float32:
+      raise TypeError('the lattice kernels compute in float32; weight function returned '
+                      f'{blank.dtype} / {lexical.dtype}')
+    return blank.contiguous(), lexical.contiguous()
+
+  def _string_indices(self, labels, device):
+    """context states along the label string and the label leaving each of
+    them (lattices.py:336-338; label 0 is read as label 1, :314-315)."""
+    labels = labels.reshape(-1, labels.shape[-1]).to(device=device, dtype=torch.int64)
+    states = self.context.walk_states(labels)
+    next_labels = torch.cat([labels, torch.ones_like(labels[:, :1])], dim=-1)
+    next_labels = torch.where(next_labels - 1 < 0, torch.ones_like(next_labels), next_labels)
+    return states.to(torch.int32).contiguous(), next_labels.to(torch.int32).contiguous()
+
+  # -- public API --------------------------------------------------------------
+
+  def forward(self, frames: torch.Tensor, num_frames: torch.Tensor, labels: torch.Tensor,
+              num_labels: torch.Tensor, cache: Optional[T] = None) -> torch.Tensor:
+    """Negative sequence log-probability, [batch_dims...] (lattices.py:131-183)."""
+    batch_dims = self._check_frames(frames, num_frames)
+    self._check_labels(labels, num_labels, batch_dims)
+    if cache is None:
+      cache = self.weight_fn_cacher()
+    if isinstance(self.weight_fn, weight_fns.LocallyNormalizedWeightFn):
+      return -self._string_forward(cache=cache, frames=frames, num_frames=num_frames,
+                                   labels=labels, num_labels=num_labels,
+                                   semiring=semirings.Log)
+    v, n, k = self._geometry()
+    blank, lexical = self._arc_weights(cache, frames, batch_dims)
+    dev = blank.device
+    states, next_labels = self._string_indices(labels, dev)
+    loss, _, _, _ = ops.LatticeLoss.apply(
+        blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
+        ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags)
+    return loss.reshape(batch_dims)
+
+  def shortest_path(self, frames: torch.Tensor, num_frames: torch.Tensor,
+                    cache: Optional[T] = None):
+    """Highest scoring path (lattices.py:185-247).
+
+    Returns (alignment_labels [batch_dims..., T * num_alignment_states],
+    num_alignment_labels [batch_dims...], path_weights [batch_dims...]).
+    Labels are the TRUE labels: 0 = blank, 1..vocab_size lexical.
+    """
+    batch_dims = self._check_frames(frames, num_frames)
+    if cache is None:
+      cache = self.weight_fn_cacher()
+    v, n, k = self._geometry()
+    with torch.no_grad():
+      blank, lexical = self._arc_weights(cache, frames, batch_dims)
+      dev = blank.device
+      labels, _, path_weights = ops.viterbi_path(
+          blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), v, n, k, self.kernel_flags)
+    num_alignment_states = self.alignment.num_states()
+    alignment_labels = labels.to(torch.int64).reshape(*batch_dims, -1)
+    num_alignment_labels = num_alignment_states * num_frames.to(dev)
+    return alignment_labels, num_alignment_labels, path_weights.reshape(batch_dims)
+
+  # -- "private" methods that the reference's tests call directly -------------------
+
+  def _string_forward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor,
+                      labels: torch.Tensor, num_labels: torch.Tensor,
+                      semiring: semirings.Semiring[torch.Tensor]) -> torch.Tensor:
+    """Shortest distance on the lattice intersected with the label string
+    (lattices.py:250-377)."""
+    batch_dims = self._check_frames(frames, num_frames)
+    self._check_labels(labels, num_labels, batch_dims)
+    sr = semirings.kernel_id(semiring)
+    v, n, k = self._geometry()
+    blank, lexical = self._arc_weights(cache, frames, batch_dims)
+    dev = blank.device
+    states, next_labels = self._string_indices(labels, dev)
+    dist = ops.StringForward.apply(
+        blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
+        ops._as_i32(num_labels.reshape(-1), dev), sr, v, k)
+    return dist.reshape(batch_dims)
+
+  def _forward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor,
+               semiring: semirings.Semiring[torch.Tensor],
+               blank_mask: Optional[Sequence[torch.Tensor]] = None,
+               lexical_mask: Optional[Sequence[torch.Tensor]] = None):
+    """Shortest distance on the recognition lattice (lattices.py:379-496).
+
+    Returns (shortest_distance [batch_dims...],
+             alpha_0_to_T_minus_1 [batch_dims..., T, num_context_states]).
+    Zero-valued masks may be passed to differentiate w.r.t. arc weights
+    (lattices.py:390-396); they are added to the dense weights.
+    """
+    batch_dims = self._check_frames(frames, num_frames)
+    num_align = self.alignment.num_states()
+    if blank_mask is not None and len(blank_mask) != num_align:
+      raise ValueError('The length of blank_mask should be equal to '
+                       f'{num_align} (the number of alignment states), '
+                       f'but is {len(blank_mask)}')
+    if lexical_mask is not None and len(lexical_mask) != num_align:
+      raise ValueError('The length of lexical_mask should be equal to '
+                       f'{num_align} (the number of alignment states), '
+                       f'but is {len(lexical_mask)}')
+    sr = semirings.kernel_id(semiring)
+    v, n, k = self._geometry()
+    blank, lexical = self._arc_weights(cache, frames, batch_dims)
+    c = blank.shape[-1]
+    t = blank.shape[1]
+    if blank_mask is not None or lexical_mask is not None:
+      if num_align != 1:
+        raise NotImplementedError(
+            'per-alignment-state masks are only supported for FrameDependent: the kernels '
+            'use alignment-state-invariant weights (lattices.py:447-449)')
+      if blank_mask is not None:
+        blank = blank + torch.broadcast_to(blank_mask[0], (*batch_dims, t, c)).reshape(-1, t, c)
+      if lexical_mask is not None:
+        lexical = lexical + torch.broadcast_to(
+            lexical_mask[0], (*batch_dims, t, c, v)).reshape(-1, t, c, v)
+    dev = blank.device
+    dist, alphas = ops.LatticeForward.apply(
+        blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), sr, v, n, k, self.kernel_flags)
+    return dist.reshape(batch_dims), alphas.reshape(*batch_dims, t, c)
+
+  def _forward_backward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor):
+    """Log-semiring shortest distance whose gradient is computed by the
+    backward algorithm (lattices.py:498-642).  Returns (log_z, alphas)."""
+    return self._forward(cache=cache, frames=frames, num_frames=num_frames,
+                         semiring=semirings.Log)

@@ -1,0 +1,315 @@
+"""torch.autograd.Function wrappers over the C ABI (include/last_lattice.h).
+
+torch is used for device memory, streams and the autograd graph only; every
+arithmetic step below is a hand-written sm_100a kernel.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+_SR_ID = {'Real': N.REAL, 'Log': N.LOG, 'MaxTropical': N.MAXTROPICAL}
+
+
+def _as_i32(x: torch.Tensor, device) -> torch.Tensor:
+  """Index tensors may arrive as float (tests/lattices_test.py:49-51)."""
+  return x.to(device=device, dtype=torch.int32).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# semiring (+) on arbitrary tensors
+# ---------------------------------------------------------------------------
+
+class SemiringPlus(torch.autograd.Function):
+  """Log / MaxTropical `plus` (semirings.py:202-204, :330-332) with the
+  gradients of semirings.py:264-269 (safe) and :360-369 (a >= b)."""
+
+  @staticmethod
+  def forward(ctx, a, b, sr):
+    a, b = torch.broadcast_tensors(a, b)
+    a = N.require_cuda(a, 'a')
+    b = N.require_cuda(b, 'b')
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+      N.check(N.lib().lt_semiring_plus_forward(sr, N.ptr(a), N.ptr(b), N.ptr(out), a.numel(),
+                                               N.stream_ptr(a.device)), 'semiring plus')
+    ctx.save_for_backward(a, b)
+    ctx.sr = sr
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    a, b = ctx.saved_tensors
+    g = N.require_cuda(g, 'grad')
+    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    with torch.cuda.device(a.device):
+      N.check(N.lib().lt_semiring_plus_backward(ctx.sr, N.ptr(a), N.ptr(b), N.ptr(g), N.ptr(ga),
+                                                N.ptr(gb), a.numel(), N.stream_ptr(a.device)),
+              'semiring plus backward')
+    return ga, gb, None
+
+
+class SemiringSum(torch.autograd.Function):
+  """Log / MaxTropical `sum` along one axis (semirings.py:211-220, :339-348)
+  with the gradients of :296-300 (safe) and :389-398 (first arg-max)."""
+
+  @staticmethod
+  def forward(ctx, a, dim, sr):
+    a = N.require_cuda(a, 'a')
+    dim = dim % a.ndim
+    outer = 1
+    for s in a.shape[:dim]:
+      outer *= s
+    inner = 1
+    for s in a.shape[dim + 1:]:
+      inner *= s
+    red = a.shape[dim]
+    out_shape = a.shape[:dim] + a.shape[dim + 1:]
+    out = torch.empty(out_shape, dtype=a.dtype, device=a.device)
+    argmax = (torch.empty(out_shape, dtype=torch.int32, device=a.device)
+              if sr == N.MAXTROPICAL else None)
+    with torch.cuda.device(a.device):
+      N.check(N.lib().lt_semiring_sum_forward(sr, N.ptr(a), outer, red, inner, N.ptr(out),
+                                              N.ptr(argmax), N.stream_ptr(a.device)),
+              'semiring sum')
+    ctx.save_for_backward(a, out, argmax)
+    ctx.geom = (sr, outer, red, inner)
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    a, out, argmax = ctx.saved_tensors
+    sr, outer, red, inner = ctx.geom
+    g = N.require_cuda(g, 'grad')
+    ga = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+      N.check(N.lib().lt_semiring_sum_backward(sr, N.ptr(a), N.ptr(out), N.ptr(argmax), N.ptr(g),
+                                               outer, red, inner, N.ptr(ga),
+                                               N.stream_ptr(a.device)), 'semiring sum backward')
+    return ga, None, None
+
+
+# ---------------------------------------------------------------------------
+# K1 / K2 / K5: recognition-lattice forward with gradients
+# ---------------------------------------------------------------------------
+
+def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_levels,
+                         want_backptr, alpha_init=None):
+  B, T, C = blank.shape
+  dev = blank.device
+  dist = torch.empty([B], dtype=torch.float32, device=dev)
+  alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev)
+  alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)
+  fld = k >= 1
+  levels = (torch.empty([B, T, k, C], dtype=torch.float32, device=dev)
+            if (fld and want_levels) else None)
+  backptr = termptr = None
+  if want_backptr and sr == N.MAXTROPICAL:
+    backptr = torch.empty([B, T, max(k, 1), C], dtype=torch.int16, device=dev)
+    if fld:
+      termptr = torch.empty([B, T, C], dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_lattice_forward(
+        sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alpha_init),
+        N.ptr(dist), N.ptr(alphas), N.ptr(alpha_final), N.ptr(levels), N.ptr(backptr),
+        N.ptr(termptr), flags, N.stream_ptr(dev)), 'lt_lattice_forward')
+  return dist, alphas, alpha_final, levels, backptr, termptr
+
+
+def _check_weights(blank, lexical, V, C):
+  blank = N.require_cuda(blank, 'blank')
+  lexical = N.require_cuda(lexical, 'lexical')
+  if blank.ndim != 3 or lexical.ndim != 4:
+    raise ValueError(f'blank must be [B,T,C] and lexical [B,T,C,V]; got {tuple(blank.shape)} '
+                     f'and {tuple(lexical.shape)}')
+  if blank.shape[-1] != C or tuple(lexical.shape) != (*blank.shape, V):
+    raise ValueError(f'weights do not match the context shape ({C}, {V}): blank '
+                     f'{tuple(blank.shape)}, lexical {tuple(lexical.shape)}')
+  return blank, lexical
+
+
+class LatticeForward(torch.autograd.Function):
+  """(dist, alphas) = RecognitionLattice._forward on dense weights
+  (lattices.py:379-496).  Gradients flow through `dist` only: Log / Real use
+  the beta-recursion kernel, MaxTropical the Viterbi back-trace."""
+
+  @staticmethod
+  def forward(ctx, blank, lexical, num_frames, sr, V, n, k, flags):
+    C = blank.shape[-1]
+    blank, lexical = _check_weights(blank, lexical, V, C)
+    need_grad = any(ctx.needs_input_grad[:2])
+    dist, alphas, alpha_final, levels, backptr, termptr = _lattice_forward_raw(
+        sr, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
+        want_backptr=need_grad)
+    ctx.geom = (sr, V, n, k, flags)
+    ctx.save_for_backward(blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr,
+                          termptr)
+    ctx.mark_non_differentiable(alphas)
+    return dist, alphas
+
+  @staticmethod
+  def backward(ctx, g_dist, _g_alphas):
+    sr, V, n, k, flags = ctx.geom
+    blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr, termptr = \
+        ctx.saved_tensors
+    B, T, C = blank.shape
+    dev = blank.device
+    g_dist = N.require_cuda(g_dist, 'grad_dist')
+    with torch.cuda.device(dev):
+      if sr == N.MAXTROPICAL:
+        gb = torch.zeros_like(blank)
+        gl = torch.zeros_like(lexical)
+        labels = torch.empty([B, T, max(k, 0) + 1], dtype=torch.int32, device=dev)
+        N.check(N.lib().lt_viterbi_backtrace(
+            V, n, k, N.ptr(backptr), N.ptr(termptr), N.ptr(alpha_final), N.ptr(num_frames), B, T,
+            N.ptr(labels), None, N.ptr(g_dist), N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)),
+            'lt_viterbi_backtrace')
+      else:
+        gb = torch.empty_like(blank)
+        gl = torch.empty_like(lexical)
+        N.check(N.lib().lt_lattice_backward(
+            sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+            N.ptr(levels), N.ptr(dist), N.ptr(g_dist), N.ptr(gb), N.ptr(gl), None, flags,
+            N.stream_ptr(dev)), 'lt_lattice_backward')
+    return gb, gl, None, None, None, None, None, None
+
+
+def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
+  """MaxTropical forward + back-trace; returns (labels [B,T,k+1] int32 with true
+  1-based labels, path_states [B,T+1], path_weights [B])."""
+  C = blank.shape[-1]
+  blank, lexical = _check_weights(blank.detach(), lexical.detach(), V, C)
+  B, T, _ = blank.shape
+  dev = blank.device
+  dist, _, alpha_final, _, backptr, termptr = _lattice_forward_raw(
+      N.MAXTROPICAL, V, n, k, blank, lexical, num_frames, flags, want_levels=False,
+      want_backptr=True)
+  labels = torch.empty([B, T, max(k, 0) + 1], dtype=torch.int32, device=dev)
+  states = torch.empty([B, T + 1], dtype=torch.int32, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_viterbi_backtrace(
+        V, n, k, N.ptr(backptr), N.ptr(termptr), N.ptr(alpha_final), N.ptr(num_frames), B, T,
+        N.ptr(labels), N.ptr(states), None, None, None, N.stream_ptr(dev)),
+        'lt_viterbi_backtrace')
+  return labels, states, dist
+
+
+# ---------------------------------------------------------------------------
+# K3: numerator on the label lattice
+# ---------------------------------------------------------------------------
+
+def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels,
+                        need_grad):
+  B, T, _ = blank.shape
+  U1 = states.shape[-1]
+  dev = blank.device
+  bw = torch.empty([B, T, U1], dtype=torch.float32, device=dev)
+  lw = torch.empty([B, T, U1], dtype=torch.float32, device=dev)
+  dist = torch.empty([B], dtype=torch.float32, device=dev)
+  alphas = (torch.empty([B, T, U1], dtype=torch.float32, device=dev)
+            if need_grad and sr != N.MAXTROPICAL else None)
+  backptr = (torch.empty([B, T, U1], dtype=torch.uint8, device=dev)
+             if need_grad and sr == N.MAXTROPICAL else None)
+  with torch.cuda.device(dev):
+    L = N.lib()
+    N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
+                               N.ptr(next_labels), B, T, U1, N.ptr(bw), N.ptr(lw),
+                               N.stream_ptr(dev)), 'lt_string_gather')
+    N.check(L.lt_string_forward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels),
+                                B, T, U1, N.ptr(dist), N.ptr(alphas), N.ptr(backptr),
+                                N.stream_ptr(dev)), 'lt_string_forward')
+  return dist, bw, lw, alphas, backptr
+
+
+def _string_backward_into(sr, k, V, C, bw, lw, num_frames, num_labels, alphas, backptr, dist,
+                          g_dist, states, next_labels, scale, gb, gl):
+  """Numerator posteriors scattered (x scale) into the dense gradient buffers."""
+  B, T, U1 = bw.shape
+  dev = bw.device
+  gbw = torch.empty_like(bw)
+  glw = torch.empty_like(lw)
+  with torch.cuda.device(dev):
+    L = N.lib()
+    N.check(L.lt_string_backward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames),
+                                 N.ptr(num_labels), B, T, U1, N.ptr(alphas), N.ptr(backptr),
+                                 N.ptr(dist), N.ptr(g_dist), N.ptr(gbw), N.ptr(glw),
+                                 N.stream_ptr(dev)), 'lt_string_backward')
+    N.check(L.lt_string_scatter_add(V, C, N.ptr(gbw), N.ptr(glw), N.ptr(states),
+                                    N.ptr(next_labels), B, T, U1, float(scale), N.ptr(gb),
+                                    N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
+
+
+class StringForward(torch.autograd.Function):
+  """RecognitionLattice._string_forward on dense weights (lattices.py:250-377)."""
+
+  @staticmethod
+  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, sr, V, k):
+    C = blank.shape[-1]
+    blank, lexical = _check_weights(blank, lexical, V, C)
+    need_grad = any(ctx.needs_input_grad[:2])
+    dist, bw, lw, alphas, backptr = _string_forward_raw(
+        sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad)
+    ctx.geom = (sr, V, C, k, tuple(blank.shape))
+    ctx.save_for_backward(bw, lw, num_frames, num_labels, alphas, backptr, dist, states,
+                          next_labels)
+    return dist
+
+  @staticmethod
+  def backward(ctx, g_dist):
+    sr, V, C, k, shape = ctx.geom
+    bw, lw, num_frames, num_labels, alphas, backptr, dist, states, next_labels = ctx.saved_tensors
+    g_dist = N.require_cuda(g_dist, 'grad_dist')
+    gb = torch.zeros(shape, dtype=torch.float32, device=bw.device)
+    gl = torch.zeros((*shape, V), dtype=torch.float32, device=bw.device)
+    _string_backward_into(sr, k, V, C, bw, lw, num_frames, num_labels, alphas, backptr, dist,
+                          g_dist, states, next_labels, 1.0, gb, gl)
+    return gb, gl, None, None, None, None, None, None, None
+
+
+class LatticeLoss(torch.autograd.Function):
+  """loss = logZ - numerator (lattices.py:131-183) as ONE autograd node.
+
+  Forward: K1 (Log) over the dense lattice + K3 over the label lattice.
+  Backward: K2 writes g * (arc posteriors) straight into the weight-gradient
+  buffers, then the numerator posteriors are scattered in with scale -1.
+  """
+
+  @staticmethod
+  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags):
+    C = blank.shape[-1]
+    blank, lexical = _check_weights(blank, lexical, V, C)
+    need_grad = any(ctx.needs_input_grad[:2])
+    log_z, alphas, _, levels, _, _ = _lattice_forward_raw(
+        N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
+        want_backptr=False)
+    num, bw, lw, s_alphas, _ = _string_forward_raw(
+        N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad)
+    ctx.geom = (V, n, k, flags)
+    ctx.save_for_backward(blank, lexical, num_frames, log_z, alphas, levels, bw, lw, num_labels,
+                          s_alphas, num, states, next_labels)
+    ctx.mark_non_differentiable(alphas)
+    return log_z - num, log_z, num, alphas
+
+  @staticmethod
+  def backward(ctx, g_loss, g_logz, g_num, _g_alphas):
+    V, n, k, flags = ctx.geom
+    (blank, lexical, num_frames, log_z, alphas, levels, bw, lw, num_labels, s_alphas, num, states,
+     next_labels) = ctx.saved_tensors
+    B, T, C = blank.shape
+    dev = blank.device
+    g_den = g_loss if g_logz is None else g_loss + g_logz
+    g_numr = -g_loss if g_num is None else g_num - g_loss
+    g_den = N.require_cuda(g_den, 'grad')
+    g_numr = N.require_cuda(g_numr, 'grad')
+    gb = torch.empty_like(blank)
+    gl = torch.empty_like(lexical)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_lattice_backward(
+          N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+          N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None, flags,
+          N.stream_ptr(dev)), 'lt_lattice_backward')
+    _string_backward_into(N.LOG, k, V, C, bw, lw, num_frames, num_labels, s_alphas, None, num,
+                          g_numr, states, next_labels, 1.0, gb, gl)
+    return gb, gl, None, None, None, None, None, None, None, None

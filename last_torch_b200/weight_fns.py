@@ -1,0 +1,212 @@
+"""Weight functions (drop-in for last_torch.weight_fns).
+
+Same class names and constructor arguments as the reference
+(/root/reference/last_torch/weight_fns.py).  Differences that are deliberate
+fixes of reference defects (documented in DESIGN.md):
+
+  * JointWeightFn owns its four projections as registered parameters (created
+    on the first call, when the embedding / feature sizes are known) instead
+    of building fresh random nn.Linear layers on every call.
+  * SharedEmbCacher returns the [num_context_states, embedding_size] table.
+
+Every WeightFn additionally exposes `all_frames(cache, frames)`, which
+evaluates the arc weights of ALL T frames in one call; RecognitionLattice uses
+it to materialise `blank [B,T,C]` / `lexical [B,T,C,V]` once and hands them to
+the persistent lattice kernels (a WeightFn is frame-independent by contract,
+weight_fns.py:57-82).
+"""
+
+from __future__ import annotations
+
+import abc
+from typing import Callable, Generic, Optional, TypeVar
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+T = TypeVar('T')
+
+
+class WeightFn(nn.Module, Generic[T], abc.ABC):
+  """Interface (weight_fns.py:42-83)."""
+
+  @abc.abstractmethod
+  def forward(self, cache: T, frame: torch.Tensor,
+              state: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """frame [batch_dims..., feature_size] -> (blank [..., C], lexical [..., C, V]),
+    or ([...], [..., V]) for the given `state`."""
+    raise NotImplementedError
+
+  def all_frames(self, cache: T, frames: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """frames [batch_dims..., T, feature_size] ->
+    (blank [batch_dims..., T, C], lexical [batch_dims..., T, C, V]).
+
+    Default: one `forward` call per frame (always valid); subclasses override
+    it with a single batched evaluation.
+    """
+    outs = [self(cache, frames[..., t, :]) for t in range(frames.shape[-2])]
+    nb = frames.ndim - 2
+    return (torch.stack([o[0] for o in outs], dim=nb),
+            torch.stack([o[1] for o in outs], dim=nb))
+
+
+class WeightFnCacher(nn.Module, Generic[T], abc.ABC):
+  """Interface (weight_fns.py:86-96)."""
+
+  @abc.abstractmethod
+  def forward(self) -> T:
+    """Builds the cached data."""
+
+
+def hat_normalize(blank: torch.Tensor, lexical: torch.Tensor):
+  """HAT local normalisation (weight_fns.py:99-117)."""
+  z = F.softplus(blank)
+  return blank - z, F.log_softmax(lexical, dim=-1) - z.unsqueeze(-1)
+
+
+def log_softmax_normalize(blank: torch.Tensor, lexical: torch.Tensor):
+  """Joint log-softmax over blank ++ lexical (weight_fns.py:120-136)."""
+  all_weights = F.log_softmax(torch.cat([blank.unsqueeze(-1), lexical], dim=-1), dim=-1)
+  return all_weights[..., 0], all_weights[..., 1:]
+
+
+class LocallyNormalizedWeightFn(WeightFn[T]):
+  """Wrapper that makes any weight function locally normalised
+  (weight_fns.py:139-171); RecognitionLattice.forward then skips the
+  denominator (lattices.py:178-179)."""
+
+  def __init__(self, weight_fn: WeightFn[T],
+               normalize: Callable[[torch.Tensor, torch.Tensor],
+                                   tuple[torch.Tensor, torch.Tensor]] = hat_normalize,
+               *args, **kwargs) -> None:
+    super().__init__(*args, **kwargs)
+    self.weight_fn = weight_fn
+    self.normalize = normalize
+
+  def forward(self, cache, frame, state=None):
+    return self.normalize(*self.weight_fn(cache, frame, state))
+
+  def all_frames(self, cache, frames):
+    return self.normalize(*self.weight_fn.all_frames(cache, frames))
+
+
+class JointWeightFn(WeightFn[torch.Tensor]):
+  r"""tanh(W_c emb[c] + W_f frame) -> Linear(H, 1), Linear(H, V)
+  (weight_fns.py:174-227).
+
+  Works with any cacher that yields a [num_context_states, embedding_size]
+  table.  Parameters (names follow the local variables of the reference body):
+    context_projection   Linear(E, H, bias=False)   weight_fns.py:208-209
+    blank_projection     Linear(D, H, bias=False)   weight_fns.py:210-211 (projects the frame)
+    joint_projection_to_blank  Linear(H, 1)         weight_fns.py:220
+    joint_projection_to_vocab  Linear(H, V)         weight_fns.py:221
+  """
+
+  def __init__(self, vocab_size: int, hidden_size: int, device: Optional[str] = 'cpu',
+               *args, embedding_size: Optional[int] = None, feature_size: Optional[int] = None,
+               **kwargs) -> None:
+    super().__init__(*args, **kwargs)
+    self.vocab_size = vocab_size
+    self.hidden_size = hidden_size
+    self.device = device
+    self.context_projection: Optional[nn.Linear] = None
+    self.blank_projection: Optional[nn.Linear] = None
+    self.joint_projection_to_blank: Optional[nn.Linear] = None
+    self.joint_projection_to_vocab: Optional[nn.Linear] = None
+    if embedding_size is not None and feature_size is not None:
+      self._materialize(embedding_size, feature_size, torch.device(device or 'cpu'))
+
+  def _materialize(self, embedding_size: int, feature_size: int, device) -> None:
+    h, v = self.hidden_size, self.vocab_size
+    self.context_projection = nn.Linear(embedding_size, h, bias=False, device=device)
+    self.blank_projection = nn.Linear(feature_size, h, bias=False, device=device)
+    self.joint_projection_to_blank = nn.Linear(h, 1, device=device)
+    self.joint_projection_to_vocab = nn.Linear(h, v, device=device)
+
+  def _ensure(self, cache: torch.Tensor, frame: torch.Tensor) -> None:
+    if self.context_projection is None:
+      self._materialize(cache.shape[-1], frame.shape[-1], frame.device)
+
+  def forward(self, cache, frame, state=None):
+    self._ensure(cache, frame)
+    context_embeddings = cache
+    if state is None:
+      frame = frame.unsqueeze(-2)                      # [..., 1, D]
+    else:
+      context_embeddings = torch.index_select(context_embeddings, 0, state.reshape(-1).long())
+      context_embeddings = context_embeddings.reshape(*state.shape, -1)
+    joint = torch.tanh(self.context_projection(context_embeddings) +
+                       self.blank_projection(frame))
+    blank = self.joint_projection_to_blank(joint).squeeze(-1)
+    lexical = self.joint_projection_to_vocab(joint)
+    return blank, lexical
+
+  def all_frames(self, cache, frames):
+    self._ensure(cache, frames)
+    from . import joint as joint_ops   # CUDA (tcgen05) vocabulary projection
+    return joint_ops.joint_all_frames(self, cache, frames)
+
+
+class SharedEmbCacher(WeightFnCacher[torch.Tensor]):
+  """A trainable, independent context embedding table (weight_fns.py:230-242);
+  returns the [num_context_states, embedding_size] tensor JointWeightFn expects."""
+
+  def __init__(self, num_context_states: int, embedding_size: int,
+               device: Optional[str] = None, *args, **kwargs):
+    super().__init__(*args, **kwargs)
+    self.num_context_states = num_context_states
+    self.embedding_size = embedding_size
+    self.device = device if device else 'cpu'
+    self.embedding = nn.Embedding(num_context_states, embedding_size, device=self.device)
+
+  def forward(self) -> torch.Tensor:
+    return self.embedding.weight
+
+
+class NullCacher(WeightFnCacher[type(None)]):
+  """Returns None; used with TableWeightFn (weight_fns.py:297-304)."""
+
+  def forward(self) -> None:
+    return None
+
+
+class TableWeightFn(WeightFn[type(None)]):
+  """Looks arc weights up in a fixed table, for tests (weight_fns.py:307-342).
+
+  table: [batch_dims..., input_vocab_size, num_context_states, 1 + vocab_size];
+  frame[..., 0] is cast to an integer "input label"; table[..., 0] holds the
+  blank weights, table[..., 1:] the lexical weights.
+  """
+
+  def __init__(self, table: torch.Tensor, *args, **kwargs) -> None:
+    super().__init__(*args, **kwargs)
+    self.table = table
+
+  def forward(self, cache, frame, state=None):
+    del cache
+    *batch_dims, input_vocab_size, num_context_states, _ = self.table.shape
+    if tuple(frame.shape[:-1]) != tuple(batch_dims):
+      raise ValueError(f'frame should have batch_dims={tuple(batch_dims)} but '
+                       f'got ({tuple(frame.shape[:-1])})')
+    index = frame[..., 0].to(torch.int64)
+    table = self.table.float()
+    idx = index.reshape(*index.shape, 1, 1, 1).expand(*index.shape, 1, *table.shape[-2:])
+    weights = torch.gather(table, len(batch_dims), idx).squeeze(len(batch_dims))
+    if state is not None:
+      state = torch.broadcast_to(state, tuple(batch_dims)).to(torch.int64)
+      sidx = state.reshape(*state.shape, 1, 1).expand(*state.shape, 1, weights.shape[-1])
+      weights = torch.gather(weights, len(batch_dims), sidx).squeeze(len(batch_dims))
+    return weights[..., 0], weights[..., 1:]
+
+  def all_frames(self, cache, frames):
+    del cache
+    *batch_dims, input_vocab_size, num_context_states, width = self.table.shape
+    if tuple(frames.shape[:-2]) != tuple(batch_dims):
+      raise ValueError(f'frame should have batch_dims={tuple(batch_dims)} but '
+                       f'got ({tuple(frames.shape[:-2])})')
+    index = frames[..., 0].to(torch.int64)                       # [batch..., T]
+    table = self.table.float()
+    idx = index.reshape(*index.shape, 1, 1).expand(*index.shape, num_context_states, width)
+    weights = torch.gather(table, len(batch_dims), idx)          # [batch..., T, C, 1+V]
+    return weights[..., 0].contiguous(), weights[..., 1:].contiguous()

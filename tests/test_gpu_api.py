@@ -1,0 +1,332 @@
+"""GPU tests of the public API surface: semirings, contexts, alignments,
+weight functions and RecognitionLattice, written to read like the reference's
+own tests (file:line cited) plus the golden fixtures produced by the reference.
+"""
+import os
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, golden_files
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _cuda_default_device():
+  prev = torch.get_default_device()
+  torch.set_default_device('cuda')
+  yield
+  torch.set_default_device(prev)
+
+
+def _lt():
+  import last_torch_b200 as last_torch
+  return last_torch
+
+
+def T(x):
+  return torch.tensor(x, dtype=torch.float32)
+
+
+# ---- semirings (tests/semirings_test.py) -----------------------------------
+
+@pytest.mark.parametrize('name', ['Real', 'Log', 'MaxTropical'])
+def test_zero_and_one(name):
+  # tests/semirings_test.py:25-63
+  semiring = getattr(_lt().semirings, name)
+  one, zero = semiring.ones([3]), semiring.zeros([3])
+  xs = T([1., 2., 3.])
+  for args in [(one, xs), (xs, one)]:
+    npt.assert_array_equal(semiring.times(*args).cpu(), xs.cpu())
+    npt.assert_array_equal(semiring.prod(torch.stack(args), dim=0).cpu(), xs.cpu())
+  for a, b, exp in [('ones', 'zeros', 'zeros'), ('zeros', 'ones', 'zeros'),
+                    ('ones', 'ones', 'ones'), ('zeros', 'zeros', 'zeros')]:
+    npt.assert_array_equal(
+        semiring.times(getattr(semiring, a)((1, 2)), getattr(semiring, b)((3, 1))).cpu(),
+        getattr(semiring, exp)((3, 2)).cpu())
+  for a, b, exp in [('ones', 'zeros', 'ones'), ('zeros', 'ones', 'ones'),
+                    ('zeros', 'zeros', 'zeros')]:
+    npt.assert_array_equal(
+        semiring.plus(getattr(semiring, a)((1, 2)), getattr(semiring, b)((3, 1))).cpu(),
+        getattr(semiring, exp)((3, 2)).cpu())
+  npt.assert_array_equal(semiring.sum(torch.zeros([3, 0]), dim=0).cpu(), np.zeros([0]))
+  npt.assert_array_equal(semiring.sum(torch.zeros([3, 0]), dim=1).cpu(), zero.cpu())
+  npt.assert_array_equal(semiring.prod(torch.zeros([3, 0]), dim=1).cpu(), one.cpu())
+
+
+def test_log_basics_and_grads():
+  # tests/semirings_test.py:194-204
+  log = _lt().semirings.Log
+  npt.assert_allclose(log.plus(T([2]), T([3])).cpu(), 3.31326169, rtol=1e-6)
+  npt.assert_allclose(log.sum(T([2, 3]), dim=0).cpu(), 3.31326169, rtol=1e-6)
+  # gradients: the intent documented at semirings.py:222-241
+  a = T([[1., 2., -float('inf')], [0., 2., -float('inf')]]).requires_grad_()
+  y = log.plus(a[0], a[1])
+  (g,) = torch.autograd.grad(y.sum(), a)
+  e = torch.softmax(torch.tensor([[1., 0.], [2., 2.]]), dim=-1).T
+  npt.assert_allclose(g.cpu()[:, :2], e.cpu(), rtol=1e-6)
+  npt.assert_array_equal(g.cpu()[:, 2], [0, 0])         # all -inf: zero gradient, no NaN
+  a = torch.randn([2, 3, 4, 5]).requires_grad_()
+  for dim in range(-4, 4):
+    y = log.sum(a, dim=dim)
+    npt.assert_allclose(y.detach().cpu(), torch.logsumexp(a.detach(), dim=dim).cpu(), rtol=1e-5,
+                        atol=1e-6)
+    (g,) = torch.autograd.grad(y.sum(), a)
+    npt.assert_allclose(g.cpu(), torch.softmax(a.detach(), dim=dim).cpu(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', ['Log', 'MaxTropical'])
+def test_sum_axis_errors_and_zero_sized(name):
+  # tests/semirings_test.py:148-189
+  semiring = getattr(_lt().semirings, name)
+  xs = torch.arange(2 * 3 * 4 * 5, dtype=torch.float32).reshape([2, 3, 4, 5])
+  assert semiring.sum(xs, dim=1).shape == (2, 4, 5)
+  assert semiring.sum(xs, dim=-1).shape == (2, 3, 4)
+  with pytest.raises(ValueError, match='Invalid reduction axis'):
+    semiring.sum(xs, dim=4)
+  with pytest.raises(ValueError, match='Invalid reduction axis'):
+    semiring.sum(xs, dim=-5)
+  with pytest.raises(ValueError, match='Only int axis'):
+    semiring.sum(xs, dim=None)
+  z = torch.zeros([0, 2])
+  npt.assert_array_equal(semiring.sum(z, dim=0).cpu(), semiring.zeros([2]).cpu())
+  assert semiring.sum(z, dim=1).shape == (0,)
+
+
+def test_maxtropical_tie_gradients():
+  # tests/semirings_test.py:226-247
+  mt = _lt().semirings.MaxTropical
+  a = T([[1., 2., 3.], [0., 2., 4.]]).requires_grad_()
+  (g,) = torch.autograd.grad(mt.plus(a[0], a[1]).sum(), a)
+  npt.assert_array_equal(g.cpu(), [[1, 1, 0], [0, 0, 1]])
+  (g,) = torch.autograd.grad(mt.sum(a, dim=0).sum(), a)
+  npt.assert_array_equal(g.cpu(), [[1, 1, 0], [0, 0, 1]])
+  at = T([[1., 2., 3.], [0., 2., 4.]]).requires_grad_()
+  (g,) = torch.autograd.grad(mt.sum(at.T, dim=-1).sum(), at)
+  npt.assert_array_equal(g.cpu(), [[1, 1, 0], [0, 0, 1]])
+
+
+def test_cartesian_and_expectation():
+  # tests/semirings_test.py:305-388 (op-level composition)
+  s = _lt().semirings
+  cart = s.Cartesian(s.Real, s.MaxTropical)
+  a = (T([2.]), T([3.]))
+  b = (T([4.]), T([5.]))
+  x, y = cart.plus(a, b)
+  npt.assert_array_equal(x.cpu(), [6]); npt.assert_array_equal(y.cpu(), [5])
+  x, y = cart.times(a, b)
+  npt.assert_array_equal(x.cpu(), [8]); npt.assert_array_equal(y.cpu(), [8])
+  x, y = cart.sum((T([1., 2.]), T([1., 2.])), 0)
+  npt.assert_array_equal(x.cpu(), 3); npt.assert_array_equal(y.cpu(), 2)
+  # entropy via the expectation semiring (tests/semirings_test.py:305-324)
+  probs = T([0.25, 0.25, 0.5])
+  w = torch.log(probs)
+  ent = s.LogLogExpectation.sum(s.LogLogExpectation.weighted(w, torch.log(-w)), 0)
+  npt.assert_allclose(torch.exp(ent[1]).cpu(), float(-(probs * torch.log(probs)).sum()), rtol=1e-5)
+
+
+# ---- contexts / alignments (golden per-frame ops from the reference) ----------
+
+@pytest.mark.parametrize('fname', golden_files('frameops_'))
+def test_frame_ops_golden(fname):
+  lt = _lt()
+  g = np.load(os.path.join(GOLDEN_DIR, fname))
+  k = int(g['k'])
+  context = lt.contexts.FullNGram(int(g['vocab']), int(g['context_size']))
+  alignment = (lt.alignments.FrameDependent() if k < 0 else
+               lt.alignments.FrameLabelDependent(max_expansions=k))
+  n = alignment.num_states()
+  alpha, blank, lexical, beta, log_z = (T(g[x]) for x in ['alpha', 'blank', 'lexical', 'beta',
+                                                          'log_z'])
+  for name in ['Real', 'Log', 'MaxTropical']:
+    semiring = getattr(lt.semirings, name)
+    npt.assert_allclose(
+        alignment.forward(alpha, [blank] * n, [lexical] * n, context, semiring).cpu(),
+        g[f'{name}_forward'], rtol=1e-5, atol=1e-6)
+    npt.assert_allclose(
+        alignment.string_forward(T(g['salpha']), [T(g['sblank'])] * n, [T(g['slex'])] * n,
+                                 semiring).cpu(),
+        g[f'{name}_string_forward'], rtol=1e-5, atol=1e-6)
+    npt.assert_allclose(context.forward_reduce(lexical, semiring).cpu(),
+                        g[f'{name}_forward_reduce'], rtol=1e-5, atol=1e-6)
+  nb, bm, lm = alignment.backward(alpha, [blank] * n, [lexical] * n, beta, log_z, context)
+  npt.assert_allclose(nb.cpu(), g['backward_next_beta'], rtol=1e-5, atol=1e-6)
+  npt.assert_allclose(torch.stack(bm).sum(0).cpu(), g['backward_blank_marginal'], rtol=1e-5,
+                      atol=1e-7)
+  npt.assert_allclose(torch.stack(lm).sum(0).cpu(), g['backward_lexical_marginal'], rtol=1e-5,
+                      atol=1e-7)
+  npt.assert_array_equal(context.backward_broadcast(beta).cpu(), g['backward_broadcast'])
+  npt.assert_array_equal(context.next_state_table().cpu(), g['next_state_table'])
+
+
+def test_alignment_arity_errors():
+  # tests/alignments_test.py:77-91
+  lt = _lt()
+  context = lt.contexts.FullNGram(2, 1)
+  al = lt.alignments.FrameDependent()
+  a, b, l = torch.rand([3]), torch.rand([3]), torch.rand([3, 2])
+  with pytest.raises(ValueError, match='blank should be'):
+    al.forward(a, [b, b], [l], context, lt.semirings.Real)
+  with pytest.raises(ValueError, match='lexical should be'):
+    al.forward(a, [b], [l, l], context, lt.semirings.Real)
+
+
+# ---- JointWeightFn (golden from the reference body with injected weights) ------
+
+@pytest.mark.parametrize('fname', golden_files('joint_'))
+def test_joint_golden(fname):
+  lt = _lt()
+  g = np.load(os.path.join(GOLDEN_DIR, fname))
+  v = int(g['vocab'])
+  h, e = g['w_ctx'].shape
+  d = g['w_frame'].shape[1]
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=e,
+                                   feature_size=d)
+  with torch.no_grad():
+    fn.context_projection.weight.copy_(T(g['w_ctx']))
+    fn.blank_projection.weight.copy_(T(g['w_frame']))
+    fn.joint_projection_to_blank.weight.copy_(T(g['w_blank'])[None])
+    fn.joint_projection_to_blank.bias.copy_(T(g['b_blank']).reshape(1))
+    fn.joint_projection_to_vocab.weight.copy_(T(g['w_vocab']))
+    fn.joint_projection_to_vocab.bias.copy_(T(g['b_vocab']))
+  cache, frame = T(g['cache']), T(g['frame'])
+  blank, lexical = fn(cache, frame)
+  npt.assert_allclose(blank.detach().cpu(), g['blank'], rtol=1e-5, atol=1e-6)
+  npt.assert_allclose(lexical.detach().cpu(), g['lexical'], rtol=1e-5, atol=1e-6)
+  sb, sl = fn(cache, frame, torch.tensor(g['state']))
+  npt.assert_allclose(sb.detach().cpu(), g['state_blank'], rtol=1e-5, atol=1e-6)
+  npt.assert_allclose(sl.detach().cpu(), g['state_lexical'], rtol=1e-5, atol=1e-6)
+  # the whole-utterance kernel path gives the same numbers (and gradients)
+  frames = frame[:, None, :].expand(-1, 3, -1).contiguous()
+  kb, kl = fn.all_frames(cache, frames)
+  npt.assert_allclose(kb[:, 0].detach().cpu(), g['blank'], rtol=1e-5, atol=2e-6)
+  npt.assert_allclose(kl[:, 1].detach().cpu(), g['lexical'], rtol=1e-5, atol=2e-6)
+  params = list(fn.parameters())
+  cache_r = cache.clone().requires_grad_()
+  frames_r = frames.clone().requires_grad_()
+  wb = torch.randn_like(kb); wl = torch.randn_like(kl)
+  kb, kl = fn.all_frames(cache_r, frames_r)
+  got = torch.autograd.grad((kb * wb).sum() + (kl * wl).sum(), params + [cache_r, frames_r])
+  rb, rl = fn(cache_r, frames_r.reshape(-1, d))
+  rb, rl = rb.reshape(kb.shape), rl.reshape(kl.shape)
+  ref = torch.autograd.grad((rb * wb).sum() + (rl * wl).sum(), params + [cache_r, frames_r])
+  for a, b in zip(got, ref):
+    npt.assert_allclose(a.cpu(), b.cpu(), rtol=2e-4, atol=2e-5)
+
+
+# ---- RecognitionLattice API (tests/lattices_test.py) ---------------------------
+
+def _joint_lattice(vocab_size, context_size, alignment):
+  lt = _lt()
+  context = lt.contexts.FullNGram(vocab_size=vocab_size, context_size=context_size)
+  return lt.RecognitionLattice(
+      context=context, alignment=alignment,
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=16, device='cuda'))
+
+
+def test_call_joint_weight_fn():
+  # tests/lattices_test.py:39-89
+  lt = _lt()
+  lattice = _joint_lattice(2, 1, lt.alignments.FrameDependent())
+  frames = torch.rand([4, 6, 8])
+  num_frames = T([6, 3, 2, 1])
+  labels = T([[1, 1, 1, 1], [2, 2, 2, 2], [1, 2, 1, 2], [2, 1, 2, 1]])
+  num_labels = T([4, 3, 1, 2])
+  loss = lattice(frames=frames, num_frames=num_frames, labels=labels, num_labels=num_labels)
+  npt.assert_array_equal(torch.isfinite(loss).cpu(), [True, True, True, False])
+  # padded inputs give the SAME loss (the reference can only check rtol=2 because its
+  # weights are re-randomised on every call)
+  padded = lattice(frames=torch.nn.functional.pad(frames, (0, 0, 0, 1, 0, 0)),
+                   num_frames=num_frames,
+                   labels=torch.nn.functional.pad(labels, (0, 2, 0, 0)), num_labels=num_labels)
+  npt.assert_allclose(padded.detach().cpu()[:3], loss.detach().cpu()[:3], rtol=1e-6)
+  with pytest.raises(ValueError, match='frames and num_frames have different batch_dims'):
+    lattice(frames=frames[:1], num_frames=num_frames, labels=labels, num_labels=num_labels)
+  with pytest.raises(ValueError, match='labels and num_frames have different batch_dims'):
+    lattice(frames=frames, num_frames=num_frames, labels=labels[:1], num_labels=num_labels)
+  with pytest.raises(ValueError, match='num_labels and num_frames have different batch_dims'):
+    lattice(frames=frames, num_frames=num_frames, labels=labels, num_labels=num_labels[:1])
+  # gradients reach every parameter of the weight function and the cacher
+  loss[:3].sum().backward()
+  grads = [p.grad for p in lattice.parameters()]
+  assert len(grads) == 6 and all(g is not None and torch.isfinite(g).all() for g in grads)
+  assert all(float(g.abs().sum()) > 0 for g in grads)
+
+
+def test_shortest_path_api():
+  # tests/lattices_test.py:91-127 and :151-176
+  lt = _lt()
+  frames = torch.rand([4, 6, 8])
+  lattice = _joint_lattice(2, 1, lt.alignments.FrameDependent())
+  nf = T([6, 3, 2, 0])
+  labels, num, weights = lattice.shortest_path(frames, nf)
+  npt.assert_array_equal(num.cpu(), [6, 3, 2, 0])
+  is_padding = (torch.arange(6)[None, :] >= nf[:, None])
+  assert bool((labels[is_padding] == 0).all())
+  assert bool(((labels >= 0) & (labels <= 2)).all())
+  npt.assert_array_equal(torch.isfinite(weights).cpu(), [True] * 4)
+  npt.assert_array_equal((weights == 0).cpu(), [False, False, False, True])
+  lattice = _joint_lattice(2, 1, lt.alignments.FrameLabelDependent(max_expansions=2))
+  nf = T([6, 3, 2, 1])
+  labels, num, weights = lattice.shortest_path(frames, nf)
+  npt.assert_array_equal(num.cpu(), (3 * nf).cpu())
+  npt.assert_array_equal(labels.reshape([4, 6, 3])[..., -1].cpu(), np.zeros([4, 6]))
+  loss = lattice(frames=frames, num_frames=nf,
+                 labels=T([[1, 1, 1, 1], [2, 2, 2, 2], [1, 2, 1, 2], [2, 1, 2, 1]]),
+                 num_labels=T([4, 3, 4, 3]))
+  npt.assert_array_equal(torch.isfinite(loss).cpu(), [True, True, True, False])
+
+
+def test_frame_dependent_known_answer():
+  # tests/lattices_test.py:181-288 (TableWeightFn golden)
+  lt = _lt()
+  b, t, v, c = 3, 2, 2, 3
+  frames = torch.arange(t)[None, :, None].expand(b, t, 1).float()
+  num_frames = T([2, 1, 0])
+  table = 1 + torch.arange(b * t * c * (1 + v)).reshape([b, t, c, 1 + v]).float()
+  table = table * T([[-1, 1], [1, -1], [1, 1]])[:, :, None, None]
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=v, context_size=1),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_factory=lambda _: lt.weight_fns.TableWeightFn(table),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+  lse = lambda xs: float(torch.logsumexp(T(xs), 0))
+  den = lse([-1 + 10, -1 + 11, -1 + 12, -2 + 13, -2 + 14, -2 + 15, -3 + 16, -3 + 17, -3 + 18])
+  for name, expected in [('MaxTropical', [15, 21, 0]), ('Real', [-33 - 84 - 153, 60, 1]),
+                         ('Log', [den, lse([19, 20, 21]), 0.])]:
+    got = lattice._forward(cache=None, frames=frames, num_frames=num_frames,
+                           semiring=getattr(lt.semirings, name))[0]
+    npt.assert_allclose(got.cpu(), expected, rtol=1e-6)
+  labels_out, num_out, weights = lattice.shortest_path(frames=frames, num_frames=num_frames,
+                                                       cache=None)
+  npt.assert_array_equal(num_out.cpu(), num_frames.cpu())
+  npt.assert_allclose(weights.cpu(), [15, 21, 0])
+  # true labels; the reference prints [[1,1],[0,0],[0,0]] because of SURVEY D4/D5
+  npt.assert_array_equal(labels_out.cpu(), [[2, 2], [2, 0], [0, 0]])
+  labels = T([[1, 2, 0], [2, 1, 0], [1, 2, 0]])
+  num_labels = T([1, 1, 0])
+  for name, expected in [('MaxTropical', [11, 21, 0]), ('Real', [-11 - 26, 21, 1]),
+                         ('Log', [lse([10, 11]), 21, 0])]:
+    semiring = getattr(lt.semirings, name)
+    got = lattice._string_forward(cache=None, frames=frames, num_frames=num_frames, labels=labels,
+                                  num_labels=num_labels, semiring=semiring)
+    npt.assert_allclose(got.cpu(), expected, rtol=1e-6)
+    got = lattice._string_forward(cache=None, frames=frames, num_frames=num_frames, labels=labels,
+                                  num_labels=T([3, 2, 1]), semiring=semiring)
+    npt.assert_array_equal(got.cpu(), semiring.zeros([3]).cpu())
+  loss = lattice(frames=frames, num_frames=num_frames, labels=labels, num_labels=num_labels,
+                 cache=None)
+  npt.assert_allclose(loss.cpu(), [den - lse([10, 11]), lse([19, 20, 21]) - 21., 0.], rtol=1e-6,
+                      atol=1e-6)
+
+
+def test_no_cpu_fallback():
+  lt = _lt()
+  with pytest.raises(RuntimeError, match='no CPU fallback'):
+    lt.semirings.Log.plus(torch.zeros([2], device='cpu'), torch.zeros([2], device='cpu'))

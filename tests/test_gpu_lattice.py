@@ -1,0 +1,326 @@
+"""GPU parity tests of the lattice kernels (through the C ABI / public API)
+against the golden fixtures produced by the reference and against the numpy
+oracle.  Tolerances: fp32 Log/Real values and gradients 1e-5 relative to the
+magnitude of the quantity (rtol 1e-5 on O(1) values, with an atol that covers
+fp32 cancellation in alpha + w + beta - logZ); MaxTropical distances 1e-6;
+Viterbi one-hot gradients / labels bit-exact.
+"""
+import os
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, golden_files
+from oracle import lattice_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SR = ['Real', 'Log', 'MaxTropical']
+CLUSTER_FLAGS = [0, 1 << 8, 2 << 8, 4 << 8]
+
+
+def _lt():
+  import last_torch_b200 as last_torch
+  return last_torch
+
+
+def make_lattice(vocab, ctx, k, table, flags=0):
+  lt = _lt()
+  alignment = (lt.alignments.FrameDependent() if k < 0 else
+               lt.alignments.FrameLabelDependent(max_expansions=k))
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=vocab, context_size=ctx),
+      alignment=alignment,
+      weight_fn_factory=lambda _: lt.weight_fns.TableWeightFn(table),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+  lattice.kernel_flags = flags
+  return lattice
+
+
+def frames_for(b, t):
+  return torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None].expand(b, t, 1)
+
+
+def cuda(x, dtype=torch.float32):
+  return torch.as_tensor(np.asarray(x), device='cuda').to(dtype)
+
+
+@pytest.mark.parametrize('flags', CLUSTER_FLAGS)
+@pytest.mark.parametrize('fname', golden_files('lattice_'))
+def test_lattice_golden(fname, flags):
+  lt = _lt()
+  g = np.load(os.path.join(GOLDEN_DIR, fname))
+  vocab, ctx, k = int(g['vocab']), int(g['context_size']), int(g['k'])
+  b, t = g['table'].shape[:2]
+  frames = frames_for(b, t)
+  nf, lab, nl = cuda(g['num_frames']), cuda(g['labels']), cuda(g['num_labels'])
+  for name in SR:
+    semiring = getattr(lt.semirings, name)
+    tab = g['Real_table'] if name == 'Real' else g['table']
+    table = cuda(tab).requires_grad_()
+    lattice = make_lattice(vocab, ctx, k, table, flags)
+    dist, alphas = lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=semiring)
+    npt.assert_allclose(dist.detach().cpu(), g[f'{name}_dist'], rtol=2e-5, atol=1e-6,
+                        err_msg=f'{name} dist')
+    npt.assert_allclose(alphas.detach().cpu(), g[f'{name}_alphas'], rtol=2e-5, atol=2e-5,
+                        err_msg=f'{name} alphas')
+    (gd,) = torch.autograd.grad(dist.sum(), table)
+    if name == 'MaxTropical':
+      npt.assert_array_equal(gd.cpu(), g[f'{name}_dist_grad'])
+    else:
+      npt.assert_allclose(gd.cpu(), g[f'{name}_dist_grad'], rtol=2e-4, atol=2e-6,
+                          err_msg=f'{name} dist grad')
+    table = cuda(tab).requires_grad_()
+    lattice = make_lattice(vocab, ctx, k, table, flags)
+    sd = lattice._string_forward(cache=None, frames=frames, num_frames=nf, labels=lab,
+                                 num_labels=nl, semiring=semiring)
+    npt.assert_allclose(sd.detach().cpu(), g[f'{name}_string'], rtol=2e-5, atol=1e-6,
+                        err_msg=f'{name} string')
+    reach = torch.isfinite(sd) if name != 'Real' else sd != 0
+    if bool(reach.any()):
+      (gs,) = torch.autograd.grad(torch.where(reach, sd, torch.zeros_like(sd)).sum(), table)
+      if name == 'MaxTropical':
+        npt.assert_array_equal(gs.cpu(), g[f'{name}_string_grad'])
+      else:
+        npt.assert_allclose(gs.cpu(), g[f'{name}_string_grad'], rtol=2e-4, atol=2e-6,
+                            err_msg=f'{name} string grad')
+  # loss value + gradient (= denominator marginals - numerator marginals)
+  table = cuda(g['table']).requires_grad_()
+  lattice = make_lattice(vocab, ctx, k, table, flags)
+  loss = lattice(frames=frames, num_frames=nf, labels=lab, num_labels=nl, cache=None)
+  npt.assert_allclose(loss.detach().cpu(), g['loss'], rtol=2e-5, atol=2e-5)
+  fin = torch.isfinite(loss)
+  (gt,) = torch.autograd.grad(torch.where(fin, loss, torch.zeros_like(loss)).sum(), table)
+  expect = g['Log_dist_grad'] - g['Log_string_grad']
+  fin_np = fin.cpu().numpy()
+  npt.assert_allclose(gt.cpu().numpy()[fin_np], expect[fin_np], rtol=2e-4, atol=4e-6)
+  # Viterbi labels agree with the oracle's true labels; weights with the reference
+  labels, num_labels, weights = lattice.shortest_path(frames=frames, num_frames=nf, cache=None)
+  kk, fd = (0, True) if k < 0 else (k, False)
+  blank, lex = np.ascontiguousarray(g['table'][..., 0]), np.ascontiguousarray(g['table'][..., 1:])
+  o_dist, _, _, o_labels = O.viterbi(blank, lex, g['num_frames'], O.FullNGram(vocab, ctx), kk, fd)
+  npt.assert_allclose(weights.cpu(), g['MaxTropical_dist'], rtol=1e-6)
+  npt.assert_array_equal(labels.cpu(), o_labels)
+  npt.assert_array_equal(num_labels.cpu(), (kk + 1) * g['num_frames'])
+
+
+def _random_case(seed, b, t, vocab, ctx, k, u, scale=1.0, ragged=True):
+  rng = np.random.RandomState(seed)
+  c = sum(vocab**i for i in range(ctx + 1))
+  table = (rng.randn(b, t, c, 1 + vocab) * scale).astype(np.float32)
+  nf = rng.randint(t // 2, t + 1, size=b) if ragged else np.full(b, t)
+  nf[0] = t
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  per_frame = 1 if k < 0 else k
+  nl = np.minimum(rng.randint(0, u + 1, size=b), nf * per_frame)
+  return table, nf, labels, nl
+
+
+ORACLE_CASES = [
+    # seed, B, T, V, n, k, U, scale
+    (1, 4, 50, 16, 1, -1, 12, 1.0),      # BASELINE.json configs[0]
+    (2, 3, 24, 8, 2, -1, 10, 1.0),
+    (3, 2, 16, 64, 1, -1, 8, 2.0),
+    (4, 3, 12, 6, 2, 2, 10, 1.0),        # FrameLabelDependent(2), trigram states
+    (5, 2, 10, 5, 1, 3, 9, 1.0),
+    (6, 2, 12, 256, 1, -1, 8, 1.0),      # configs[1] width (C=257, V=256), short T
+    (7, 2, 8, 7, 0, -1, 5, 1.0),         # unigram: single context state
+    (8, 2, 6, 64, 2, 2, 6, 1.0),         # configs[2] width (C=4161), FLD(2)
+    (9, 5, 40, 33, 1, -1, 11, 4.0),      # odd vocab (no 16-byte alignment), wide range
+]
+
+
+@pytest.mark.parametrize('flags', [0, 1 << 8, 4 << 8, 8 << 8])
+@pytest.mark.parametrize('case', ORACLE_CASES)
+def test_loss_and_grads_vs_oracle(case, flags):
+  seed, b, t, vocab, ctx, k, u, scale = case
+  table_np, nf, labels, nl = _random_case(seed, b, t, vocab, ctx, k, u, scale)
+  kk, fd = (0, True) if k < 0 else (k, False)
+  octx = O.FullNGram(vocab, ctx)
+  tab64 = table_np.astype(np.float64)
+  blank, lex = np.ascontiguousarray(tab64[..., 0]), np.ascontiguousarray(tab64[..., 1:])
+  o_loss, o_gb, o_gl = O.lattice_loss_and_grads(blank, lex, nf, labels, nl, octx, kk, fd)
+  table = cuda(table_np).requires_grad_()
+  lattice = make_lattice(vocab, ctx, k, table, flags)
+  loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                 num_labels=cuda(nl), cache=None)
+  fin = np.isfinite(o_loss)
+  npt.assert_array_equal(torch.isfinite(loss).cpu().numpy(), fin)
+  # loss: 1e-5 relative (fp32 kernel vs fp64 oracle)
+  npt.assert_allclose(loss.detach().cpu().numpy()[fin], o_loss[fin], rtol=1e-5, atol=1e-5)
+  (gt,) = torch.autograd.grad(
+      torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum(), table)
+  gt = gt.cpu().numpy()
+  # gradients are posteriors in [0, 1]; fp32 rounding of alpha+w+beta-logZ at |alpha| ~ 1e2
+  # bounds the achievable accuracy at ~1e-5 of the value; atol covers tiny posteriors.
+  npt.assert_allclose(gt[fin][..., 0], o_gb[fin], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(gt[fin][..., 1:], o_gl[fin], rtol=1e-4, atol=1e-5)
+  if fd:
+    # free invariant: denominator marginals of each frame sum to one
+    dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                               semiring=_lt().semirings.Log)
+    (gd,) = torch.autograd.grad(dist.sum(), table)
+    npt.assert_allclose(gd.sum((1, 2, 3)).cpu(), nf, rtol=1e-4)
+
+
+@pytest.mark.parametrize('case', ORACLE_CASES)
+def test_forward_all_semirings_vs_oracle(case):
+  lt = _lt()
+  seed, b, t, vocab, ctx, k, u, scale = case
+  table_np, nf, labels, nl = _random_case(seed + 100, b, t, vocab, ctx, k, u, scale)
+  kk, fd = (0, True) if k < 0 else (k, False)
+  octx = O.FullNGram(vocab, ctx)
+  for name, sr in [('Log', O.LOG), ('MaxTropical', O.MAXTROPICAL), ('Real', O.REAL)]:
+    tab = table_np
+    if name == 'Real':
+      tab = (np.exp(np.clip(table_np, -40, 5) * 0.25) / (1 + vocab)).astype(np.float32)
+    tab64 = tab.astype(np.float64)
+    blank, lex = np.ascontiguousarray(tab64[..., 0]), np.ascontiguousarray(tab64[..., 1:])
+    o_dist, o_alphas = O.lattice_forward(blank, lex, nf, octx, sr, kk, fd)
+    o_sd = O.lattice_string_forward(blank, lex, nf, labels, nl, octx, sr, kk, fd)
+    table = cuda(tab)
+    lattice = make_lattice(vocab, ctx, k, table)
+    dist, alphas = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                                    semiring=getattr(lt.semirings, name))
+    sd = lattice._string_forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                                 labels=cuda(labels), num_labels=cuda(nl),
+                                 semiring=getattr(lt.semirings, name))
+    tol = dict(rtol=1e-6, atol=1e-5) if name == 'MaxTropical' else dict(rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(dist.cpu(), o_dist, err_msg=name, **tol)
+    npt.assert_allclose(sd.cpu(), o_sd, err_msg=name, **tol)
+    a = alphas.cpu().numpy()
+    if name == 'Real':
+      npt.assert_allclose(a, o_alphas, rtol=2e-5, atol=1e-30, err_msg=name)
+    else:
+      fin = np.isfinite(o_alphas)
+      npt.assert_array_equal(np.isfinite(a), fin)
+      npt.assert_allclose(a[fin], o_alphas[fin], rtol=1e-5, atol=2e-4, err_msg=name)
+
+
+@pytest.mark.parametrize('case', ORACLE_CASES)
+def test_viterbi_vs_oracle(case):
+  seed, b, t, vocab, ctx, k, u, scale = case
+  table_np, nf, _, _ = _random_case(seed + 200, b, t, vocab, ctx, k, u, scale)
+  kk, fd = (0, True) if k < 0 else (k, False)
+  blank, lex = np.ascontiguousarray(table_np[..., 0]), np.ascontiguousarray(table_np[..., 1:])
+  o_dist, o_gb, o_gl, o_labels = O.viterbi(blank, lex, nf, O.FullNGram(vocab, ctx), kk, fd)
+  table = cuda(table_np).requires_grad_()
+  lattice = make_lattice(vocab, ctx, k, table)
+  dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                             semiring=_lt().semirings.MaxTropical)
+  npt.assert_allclose(dist.detach().cpu(), o_dist, rtol=1e-6)
+  (gd,) = torch.autograd.grad(dist.sum(), table)
+  # random continuous weights: the maximum is unique, so the path is bit-exact
+  npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
+  npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+  labels, _, weights = lattice.shortest_path(frames=frames_for(b, t), num_frames=cuda(nf),
+                                             cache=None)
+  npt.assert_array_equal(labels.cpu(), o_labels)
+  npt.assert_allclose(weights.cpu(), o_dist, rtol=1e-6)
+
+
+def test_viterbi_ties_match_reference_rules():
+  """All-equal weights: blank beats lexical, so the all-blank path wins
+  (semirings.py:363; SURVEY section 7 'MaxTropical ties')."""
+  b, t, vocab = 2, 5, 3
+  for ctx, k in [(1, -1), (2, -1), (1, 2)]:
+    c = sum(vocab**i for i in range(ctx + 1))
+    table = torch.zeros([b, t, c, 1 + vocab], device='cuda', requires_grad=True)
+    lattice = make_lattice(vocab, ctx, k, table)
+    labels, _, weights = lattice.shortest_path(frames=frames_for(b, t),
+                                               num_frames=cuda([5, 3]), cache=None)
+    npt.assert_array_equal(labels.cpu(), 0)
+    npt.assert_array_equal(weights.cpu(), 0)
+    kk, fd = (0, True) if k < 0 else (k, False)
+    tab = np.zeros([b, t, c, 1 + vocab], np.float32)
+    _, o_gb, o_gl, _ = O.viterbi(tab[..., 0].copy(), tab[..., 1:].copy(), np.array([5, 3]),
+                                 O.FullNGram(vocab, ctx), kk, fd)
+    dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda([5, 3]),
+                               semiring=_lt().semirings.MaxTropical)
+    (gd,) = torch.autograd.grad(dist.sum(), table)
+    npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
+    npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+
+
+def test_neg_inf_weights_and_unreachable():
+  """-inf arcs: values stay finite where a path exists, gradients are 0 on
+  the -inf arcs (semirings.py:222-241); an unreachable label string gives
+  loss=+inf (tests/lattices_test.py:57)."""
+  rng = np.random.RandomState(0)
+  b, t, vocab, ctx = 3, 7, 4, 1
+  c = 1 + vocab
+  tab = rng.randn(b, t, c, 1 + vocab).astype(np.float32)
+  drop = rng.rand(b, t, c, 1 + vocab) < 0.3
+  drop[..., 0] = False
+  tab[drop] = -np.inf
+  nf = np.array([7, 5, 2])
+  labels = rng.randint(1, vocab + 1, size=(b, 4))
+  nl = np.array([2, 1, 4])      # utterance 2: 4 labels in 2 frames is unreachable
+  tab64 = tab.astype(np.float64)
+  with np.errstate(all='ignore'):
+    o_loss, o_gb, o_gl = O.lattice_loss_and_grads(
+        tab64[..., 0].copy(), tab64[..., 1:].copy(), nf, labels, nl, O.FullNGram(vocab, ctx))
+  table = cuda(tab).requires_grad_()
+  lattice = make_lattice(vocab, ctx, -1, table)
+  loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                 num_labels=cuda(nl), cache=None)
+  l = loss.detach().cpu().numpy()
+  assert np.isposinf(l[2])
+  fin = np.isfinite(o_loss)
+  npt.assert_allclose(l[fin], o_loss[fin], rtol=1e-5, atol=1e-5)
+  (gt,) = torch.autograd.grad(loss[:2].sum(), table)
+  gt = gt.cpu().numpy()
+  assert np.all(np.isfinite(gt))
+  assert np.all(gt[drop] == 0)
+  npt.assert_allclose(gt[:2][..., 0], o_gb[:2], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(gt[:2][..., 1:], o_gl[:2], rtol=1e-4, atol=1e-5)
+
+
+def test_empty_and_zero_length():
+  lt = _lt()
+  vocab, ctx = 3, 1
+  c = 4
+  table = torch.randn([2, 4, c, 1 + vocab], device='cuda')
+  lattice = make_lattice(vocab, ctx, -1, table)
+  # num_frames == 0: distance is the semiring one (tests/lattices_test.py:210-221)
+  for name, one in [('Log', 0.0), ('MaxTropical', 0.0), ('Real', 1.0)]:
+    dist, alphas = lattice._forward(cache=None, frames=frames_for(2, 4), num_frames=cuda([0, 0]),
+                                    semiring=getattr(lt.semirings, name))
+    npt.assert_array_equal(dist.cpu(), [one, one])
+    assert alphas.shape == (2, 4, c)
+  loss = lattice(frames=frames_for(2, 4), num_frames=cuda([0, 0]), labels=cuda([[1], [2]]),
+                 num_labels=cuda([0, 0]), cache=None)
+  npt.assert_array_equal(loss.cpu(), [0, 0])
+
+
+def test_full_size_properties_config1_and_2():
+  """Size-independent properties at BASELINE.json sizes (configs[1]: B=32 is cut
+  to B=4 to bound memory; T=1000, V=256): marginals of every real frame sum to
+  one, padding frames get zero gradient, the gradient is invariant to padding,
+  and chunked evaluation of the batch gives identical results."""
+  lt = _lt()
+  b, t, vocab, ctx = 4, 1000, 256, 1
+  c = 257
+  g = torch.Generator(device='cuda').manual_seed(0)
+  table = torch.randn([b, t, c, 1 + vocab], device='cuda', generator=g).requires_grad_()
+  nf = torch.tensor([1000, 731, 512, 1000], device='cuda')
+  lattice = make_lattice(vocab, ctx, -1, table)
+  dist, alphas = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=nf,
+                                  semiring=lt.semirings.Log)
+  (gd,) = torch.autograd.grad(dist.sum(), table)
+  per_frame = gd.sum((2, 3))
+  expect = (torch.arange(t, device='cuda')[None, :] < nf[:, None]).float()
+  npt.assert_allclose(per_frame.cpu(), expect.cpu(), rtol=0, atol=2e-4)
+  assert float(gd.min()) >= 0
+  # chunked over the batch == whole batch (utterances are independent)
+  lattice2 = make_lattice(vocab, ctx, -1, table[2:].detach())
+  dist2, _ = lattice2._forward(cache=None, frames=frames_for(2, t), num_frames=nf[2:],
+                               semiring=lt.semirings.Log)
+  npt.assert_array_equal(dist2.cpu(), dist[2:].detach().cpu())
+  # logZ bounds: max-path <= logZ <= max-path + log(#paths) with #paths <= (V+1)^T
+  vd, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=nf,
+                           semiring=lt.semirings.MaxTropical)
+  assert bool((vd <= dist + 1e-3).all())
+  assert bool((dist <= vd + nf.float() * np.log(1 + vocab) + 1e-2).all())

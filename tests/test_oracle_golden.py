@@ -220,3 +220,32 @@ def test_joint_golden(fname):
   s = g['state']
   npt.assert_allclose(blank[np.arange(len(s)), s], g['state_blank'], rtol=1e-5, atol=1e-6)
   npt.assert_allclose(lexical[np.arange(len(s)), s], g['state_lexical'], rtol=1e-5, atol=1e-6)
+
+
+# ---- the C restatement (oracle/lattice_oracle.c) agrees with the numpy oracle ----
+
+@pytest.mark.parametrize('vnk', [(5, 1, -1), (3, 2, -1), (4, 0, -1), (3, 1, 2), (2, 2, 3), (16, 1, -1)])
+def test_c_oracle_matches_numpy_oracle(vnk):
+  from oracle import c_oracle
+  if not c_oracle.available():
+    import __graft_entry__ as ge
+    ge.build_oracle()
+  v, n, k = vnk
+  rng = np.random.RandomState(v * 100 + n * 10 + k + 1)
+  c = sum(v**i for i in range(n + 1))
+  b, t, u = 4, 9, 5
+  tab = rng.randn(b, t, c, 1 + v).astype(np.float32)
+  nf = np.array([9, 6, 3, 0])
+  lab = rng.randint(1, v + 1, (b, u))
+  nl = np.array([4, 2, 5, 0])     # utterance 2: 5 labels in 3 frames (FrameDependent: unreachable)
+  kk, fd = (0, True) if k < 0 else (k, False)
+  with np.errstate(all='ignore'):
+    ol, ogb, ogl = O.lattice_loss_and_grads(
+        tab[..., 0].astype(np.float64), tab[..., 1:].astype(np.float64), nf, lab, nl,
+        O.FullNGram(v, n), kk, fd)
+  cl, cgb, cgl, _, _ = c_oracle.lattice_loss_and_grads(tab[..., 0], tab[..., 1:], nf, lab, nl, v, n, k)
+  npt.assert_array_equal(np.isfinite(cl), np.isfinite(ol))
+  fin = np.isfinite(ol)
+  npt.assert_allclose(cl[fin], ol[fin], rtol=1e-5, atol=1e-5)
+  npt.assert_allclose(cgb, ogb, rtol=1e-4, atol=2e-5)
+  npt.assert_allclose(cgl, ogl, rtol=1e-4, atol=2e-5)
