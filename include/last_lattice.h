@@ -51,6 +51,8 @@ extern "C" {
 
 int lt_version(void);
 const char* lt_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far. */
+unsigned long long lt_launch_count(void);
 /* Number of SMs, compute capability of the current device. */
 int lt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -32,6 +32,7 @@ _c_uint = ctypes.c_uint
 SIGNATURES = {
     'lt_version': [],
     'lt_last_error': [],
+    'lt_launch_count': [],
     'lt_device_info': [_ptr, _ptr, _ptr],
     'lt_lattice_forward': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
                            _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
@@ -83,9 +84,40 @@ def lib():
     for name, argtypes in SIGNATURES.items():
       fn = getattr(handle, name)     # AttributeError if a symbol is missing
       fn.argtypes = argtypes
-      fn.restype = ctypes.c_char_p if name == 'lt_last_error' else _c_int
-    _lib = handle
+      fn.restype = (ctypes.c_char_p if name == 'lt_last_error' else
+                    ctypes.c_ulonglong if name == 'lt_launch_count' else _c_int)
+    _lib = _TimedLib(handle)
   return _lib
+
+
+# Optional per-call CUDA-event timing (bench.py sets KERNEL_TIMER to a list; every
+# native call then appends (name, start_event, end_event) recorded on the
+# current stream of the current device -- the stream the kernel is launched on).
+KERNEL_TIMER = None
+_UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count')
+
+
+class _TimedLib:
+  def __init__(self, handle):
+    self._handle = handle
+
+  def __getattr__(self, name):
+    fn = getattr(self._handle, name)
+    if name in _UNTIMED:
+      return fn
+
+    def call(*args):
+      timer = KERNEL_TIMER
+      if timer is None:
+        return fn(*args)
+      start = torch.cuda.Event(enable_timing=True)
+      end = torch.cuda.Event(enable_timing=True)
+      start.record()
+      rc = fn(*args)
+      end.record()
+      timer.append((name, start, end))
+      return rc
+    return call
 
 
 def check(rc: int, what: str) -> None:

@@ -9,6 +9,10 @@
 namespace lt {
 
 static thread_local char g_error[512] = "";
+static unsigned long long g_launches = 0;   // atomically bumped; read by lt_launch_count
+
+void note_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -50,6 +54,8 @@ extern "C" {
 int lt_version(void) { return 100; }
 
 const char* lt_last_error(void) { return g_error; }
+
+unsigned long long lt_launch_count(void) { return launch_count(); }
 
 int lt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

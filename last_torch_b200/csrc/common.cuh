@@ -14,6 +14,7 @@ namespace lt {
 // ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void note_launch();   // bumps the process-wide kernel-launch counter (lt_launch_count)
 
 #define LT_CHECK_ARG(cond, ...)                    \
   do {                                             \
@@ -230,6 +231,13 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// after a <<<>>> launch: count it and surface launch errors
+#define LT_LAUNCHED()                   \
+  do {                                  \
+    ::lt::note_launch();                \
+    LT_CUDA(cudaGetLastError());        \
+  } while (0)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

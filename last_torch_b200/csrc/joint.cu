@@ -102,7 +102,7 @@ int joint_forward_simt(const float* pc, const float* pf, const float* wb, float 
     auto e = [=] __device__(int64_t m, int n, float acc) { E(m + r0, n, acc); };
     dim3 g((V + 1 + 63) / 64, (unsigned)((rows + 63) / 64), 1);
     tile_gemm_kernel<<<g, 256, 0, stream>>>(rows, V + 1, (int64_t)H, (int64_t)H, a, B, e);
-    LT_CUDA(cudaGetLastError());
+    LT_LAUNCHED();
   }
   return LT_OK;
 }
@@ -123,7 +123,7 @@ int joint_backward_simt(const float* pc, const float* pf, const float* wb, const
     auto e = [=] __device__(int64_t m, int j, float acc) { E(m + r0, j, acc); };
     dim3 g((H + 63) / 64, (unsigned)((rows + 63) / 64), 1);
     tile_gemm_kernel<<<g, 256, 0, stream>>>(rows, H, (int64_t)(V + 1), (int64_t)(V + 1), a, B, e);
-    LT_CUDA(cudaGetLastError());
+    LT_LAUNCHED();
   }
   {
     // split the M-long reduction over blockIdx.z
@@ -135,7 +135,7 @@ int joint_backward_simt(const float* pc, const float* pf, const float* wb, const
     JointBwd2Epi E{gwv, gwb, gbv, gbb, V, H};
     dim3 g((H + 1 + 63) / 64, (V + 1 + 63) / 64, (unsigned)nsplit);
     tile_gemm_kernel<<<g, 256, 0, stream>>>((int64_t)(V + 1), H + 1, M, kchunk, A, B, E);
-    LT_CUDA(cudaGetLastError());
+    LT_LAUNCHED();
   }
   return LT_OK;
 }

@@ -262,6 +262,7 @@ static int launch_cluster_b(KernelT kernel, int grid, int block, size_t smem, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   LT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  note_launch();
   return LT_OK;
 }
 

@@ -327,6 +327,7 @@ static int launch_cluster(KernelT kernel, int grid, int block, size_t smem, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   LT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  note_launch();
   return LT_OK;
 }
 

@@ -142,7 +142,7 @@ int semiring_plus_forward_launch(int sr, const float* a, const float* b, float* 
   else if (sr == LT_MAXTROPICAL) plus_fwd_kernel<LT_MAXTROPICAL><<<grid_for(n, 256), 256, 0, stream>>>(a, b, out, n);
   else if (sr == LT_REAL) plus_fwd_kernel<LT_REAL><<<grid_for(n, 256), 256, 0, stream>>>(a, b, out, n);
   else { set_error("lt_semiring_plus_forward: unknown semiring %d", sr); return LT_ERR_INVALID_ARGUMENT; }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -152,7 +152,7 @@ int semiring_plus_backward_launch(int sr, const float* a, const float* b, const 
   if (sr == LT_LOG) plus_bwd_kernel<LT_LOG><<<grid_for(n, 256), 256, 0, stream>>>(a, b, g, ga, gb, n);
   else if (sr == LT_MAXTROPICAL) plus_bwd_kernel<LT_MAXTROPICAL><<<grid_for(n, 256), 256, 0, stream>>>(a, b, g, ga, gb, n);
   else { set_error("lt_semiring_plus_backward: semiring must be Log or MaxTropical, got %d", sr); return LT_ERR_INVALID_ARGUMENT; }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -173,7 +173,7 @@ int semiring_sum_forward_launch(int sr, const float* a, int64_t outer, int64_t R
     if (sr == LT_LOG) sum_fwd_strided_kernel<LT_LOG><<<grid, 256, 0, stream>>>(a, outer, R, inner, out, argmax);
     else sum_fwd_strided_kernel<LT_MAXTROPICAL><<<grid, 256, 0, stream>>>(a, outer, R, inner, out, argmax);
   }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -187,7 +187,7 @@ int semiring_sum_backward_launch(int sr, const float* a, const float* out, const
     if (!argmax) { set_error("lt_semiring_sum_backward: MaxTropical needs argmax"); return LT_ERR_INVALID_ARGUMENT; }
     sum_bwd_kernel<LT_MAXTROPICAL><<<grid_for(n, 256), 256, 0, stream>>>(a, out, argmax, g, outer, R, inner, ga);
   } else { set_error("lt_semiring_sum_backward: semiring must be Log or MaxTropical, got %d", sr); return LT_ERR_INVALID_ARGUMENT; }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 

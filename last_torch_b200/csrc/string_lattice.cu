@@ -145,7 +145,9 @@ __global__ void string_backward_kernel(const StrParams p) {
       for (int t = nf - 1; t >= 0; --t) {
         const size_t off = base + (size_t)t * U1;
         const int i = p.backptr_in[off + u];
-        p.grad_blank_w[off + u] += g;
+        // FrameLabelDependent: i lexical arcs, then the frame-closing blank arc.
+        // FrameDependent: exactly one arc per frame, blank (0) or lexical (1).
+        if (FLD || i == 0) p.grad_blank_w[off + u] += g;
         for (int j = 1; j <= i; ++j) p.grad_lexical_w[off + u - j] += g;
         u -= i;
       }
@@ -227,7 +229,7 @@ int string_gather_launch(int V, int C, const float* blank, const float* lexical,
   if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
   string_gather_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
       V, C, blank, lexical, states, labels, T, U1, blank_w, lexical_w);
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -237,7 +239,7 @@ int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
   if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
   string_scatter_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
       V, C, gbw, glw, states, labels, T, U1, scale, gblank, glex);
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -254,7 +256,7 @@ static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     string_forward_kernel<SR, false><<<p.B, block, smem, stream>>>(p);
   }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 
@@ -271,7 +273,7 @@ static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     string_backward_kernel<SR, false><<<p.B, block, smem, stream>>>(p);
   }
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 

@@ -134,7 +134,7 @@ int viterbi_launch(const VitParams& base, cudaStream_t stream) {
   LT_CUDA(cudaFuncSetAttribute(viterbi_backtrace_kernel,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   viterbi_backtrace_kernel<<<p.B, 256, smem, stream>>>(p);
-  LT_CUDA(cudaGetLastError());
+  LT_LAUNCHED();
   return LT_OK;
 }
 

