@@ -101,6 +101,8 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
   p.levels = max_expansions >= 1 ? levels : nullptr;
   p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
+  if (T > 0 && lattice_fast_supported(g, max_expansions, flags, lexical))
+    return lattice_forward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,
                                         (cudaStream_t)stream);
 }
@@ -129,6 +131,9 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
   p.blank = blank; p.lexical = lexical; p.num_frames = num_frames;
   p.alphas = alphas; p.levels = levels; p.dist = dist; p.grad_dist = grad_dist;
   p.grad_blank = grad_blank; p.grad_lexical = grad_lexical; p.beta_final = beta_final;
+  if (lattice_fast_supported(g, max_expansions, flags, lexical) &&
+      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
+    return lattice_backward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   return lattice_backward_generic_launch(semiring, g, max_expansions, p, flags, sms,
                                          (cudaStream_t)stream);
 }

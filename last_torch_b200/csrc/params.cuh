@@ -80,6 +80,12 @@ int lattice_forward_generic_launch(int semiring, const NGram& g, int k, const Fw
                                    unsigned flags, int sm_count, cudaStream_t stream);
 int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const BwdParams& base,
                                     unsigned flags, int sm_count, cudaStream_t stream);
+// TMA / cluster fast path (lattice_fast.cu): bigram FrameDependent, V in {64..256}
+bool lattice_fast_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+int lattice_forward_fast_launch(int semiring, const NGram& g, const FwdParams& base,
+                                cudaStream_t stream);
+int lattice_backward_fast_launch(int semiring, const NGram& g, const BwdParams& base,
+                                 cudaStream_t stream);
 int viterbi_launch(const VitParams& base, cudaStream_t stream);
 int string_gather_launch(int V, int C, const float* blank, const float* lexical,
                          const int32_t* states, const int32_t* labels, int B, int T, int U1,

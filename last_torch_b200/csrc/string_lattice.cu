@@ -243,8 +243,146 @@ int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
   return LT_OK;
 }
 
+// ---------------------------------------------------------------------------
+// FrameDependent fast variants (U+1 <= 1024): one thread per chain state keeps
+// its alpha / beta in a REGISTER for all T frames; the per-frame weights are
+// loaded kChunk frames ahead into registers (the chain is sequential in T, the
+// weights are not), and the only per-frame communication is one neighbour
+// value through a ping-pong shared array + one __syncthreads.
+// ---------------------------------------------------------------------------
+constexpr int kChunk = 8;
+
+template <int SR>
+__global__ void __launch_bounds__(1024)
+string_forward_fd_fast(const StrParams p) {
+  using S = Sr<SR>;
+  __shared__ float mv[2][1024 + 1];
+  const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
+  const bool act = u < U1;
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  const size_t base = (size_t)b * p.T * U1;
+  float a = (u == 0) ? S::one() : S::zero();
+  float cb[kChunk], cl[kChunk], nb[kChunk], nl[kChunk];
+  auto load = [&](int t0, float (&bb)[kChunk], float (&ll)[kChunk]) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const int t = t0 + i;
+      const bool ok = act && t < nf;
+      bb[i] = ok ? ldg_stream(p.blank_w + base + (size_t)t * U1 + u) : S::one();
+      ll[i] = ok ? ldg_stream(p.lexical_w + base + (size_t)t * U1 + u) : S::zero();
+    }
+  };
+  if (u == 0) { mv[0][0] = S::zero(); mv[1][0] = S::zero(); }   // "u - 1" of state 0
+  load(0, nb, nl);
+  int par = 0;
+  for (int t0 = 0; t0 < nf; t0 += kChunk) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) { cb[i] = nb[i]; cl[i] = nl[i]; }
+    load(t0 + kChunk, nb, nl);
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const int t = t0 + i;
+      if (t < nf) {                                   // uniform over the block
+        if (act) {
+          if (p.alphas) p.alphas[base + (size_t)t * U1 + u] = a;
+          mv[par][u + 1] = S::times(a, cl[i]);
+        }
+        __syncthreads();
+        if (act) {
+          const float stay = S::times(a, cb[i]);
+          const float move = mv[par][u];
+          if constexpr (SR == LT_MAXTROPICAL) {
+            const bool tb = stay >= move;
+            a = tb ? stay : move;
+            if (p.backptr) p.backptr[base + (size_t)t * U1 + u] = tb ? 0 : 1;
+          } else {
+            a = S::plus(stay, move);
+          }
+        }
+        par ^= 1;
+      }
+    }
+  }
+  if (act && p.alphas)
+    for (int t = nf; t < p.T; ++t) p.alphas[base + (size_t)t * U1 + u] = a;
+  const int nl_b = p.num_labels[b];
+  if (act && u == nl_b) p.dist[b] = a;                          // lattices.py:375-377
+  if (u == 0 && (nl_b < 0 || nl_b >= U1)) p.dist[b] = S::zero();
+}
+
+template <int SR>   // LT_LOG or LT_REAL
+__global__ void __launch_bounds__(1024)
+string_backward_fd_fast(const StrParams p) {
+  using S = Sr<SR>;
+  __shared__ float sh[2][1024 + 1];
+  const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
+  const bool act = u < U1;
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  const int nl_b = p.num_labels[b];
+  const float z = p.dist_in[b];
+  const float g = p.grad_dist ? p.grad_dist[b] : 1.f;
+  const bool reachable = (nl_b >= 0 && nl_b < U1) && (SR == LT_REAL ? true : is_finite(z));
+  const size_t base = (size_t)b * p.T * U1;
+  if (act) {
+    for (int t = reachable ? nf : 0; t < p.T; ++t) {
+      p.grad_blank_w[base + (size_t)t * U1 + u] = 0.f;
+      p.grad_lexical_w[base + (size_t)t * U1 + u] = 0.f;
+    }
+  }
+  if (!reachable) return;
+  float beta = (u == nl_b) ? S::one() : S::zero();
+  float cb[kChunk], cl[kChunk], ca[kChunk], nb[kChunk], nl[kChunk], na[kChunk];
+  auto load = [&](int i0, float (&bb)[kChunk], float (&ll)[kChunk], float (&aa)[kChunk]) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const int t = nf - 1 - (i0 + i);
+      const bool ok = act && t >= 0;
+      const size_t o = base + (size_t)(ok ? t : 0) * U1 + (act ? u : 0);
+      bb[i] = ok ? ldg_stream(p.blank_w + o) : S::one();
+      ll[i] = ok ? ldg_stream(p.lexical_w + o) : S::zero();
+      aa[i] = ok ? p.alphas_in[o] : S::zero();
+    }
+  };
+  if (u == 0) { sh[0][U1] = S::zero(); sh[1][U1] = S::zero(); }   // "u + 1" of the last state
+  load(0, nb, nl, na);
+  int par = 0;
+  for (int i0 = 0; i0 < nf; i0 += kChunk) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) { cb[i] = nb[i]; cl[i] = nl[i]; ca[i] = na[i]; }
+    load(i0 + kChunk, nb, nl, na);
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const int t = nf - 1 - (i0 + i);
+      if (t >= 0) {                                   // uniform over the block
+        if (act) sh[par][u] = beta;
+        __syncthreads();
+        if (act) {
+          const float bn = sh[par][u + 1];
+          const float bb = S::times(cb[i], beta);
+          const float lb = S::times(cl[i], bn);
+          const size_t o = base + (size_t)t * U1 + u;
+          if constexpr (SR == LT_LOG) {
+            p.grad_blank_w[o] = g * fast_exp(ca[i] + bb - z);
+            p.grad_lexical_w[o] = g * fast_exp(ca[i] + lb - z);
+          } else {
+            p.grad_blank_w[o] = g * ca[i] * beta;
+            p.grad_lexical_w[o] = g * ca[i] * bn;
+          }
+          beta = S::plus(bb, lb);
+        }
+        par ^= 1;
+      }
+    }
+  }
+}
+
 template <int SR>
 static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
+  if (p.k < 1 && p.U1 <= 1024) {
+    string_forward_fd_fast<SR><<<p.B, block_for(p.U1), 0, stream>>>(p);
+    LT_LAUNCHED();
+    return LT_OK;
+  }
   const int block = block_for(p.U1);
   const size_t smem = sizeof(float) * 2 * p.U1;
   if (p.k >= 1) {
@@ -262,6 +400,13 @@ static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
 
 template <int SR>
 static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
+  if constexpr (SR != LT_MAXTROPICAL) {
+    if (p.k < 1 && p.U1 <= 1024) {
+      string_backward_fd_fast<SR><<<p.B, block_for(p.U1), 0, stream>>>(p);
+      LT_LAUNCHED();
+      return LT_OK;
+    }
+  }
   const int block = block_for(p.U1);
   const size_t smem = sizeof(float) * 4 * p.U1;
   if (p.k >= 1) {

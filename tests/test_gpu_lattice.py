@@ -132,7 +132,37 @@ ORACLE_CASES = [
     (7, 2, 8, 7, 0, -1, 5, 1.0),         # unigram: single context state
     (8, 2, 6, 64, 2, 2, 6, 1.0),         # configs[2] width (C=4161), FLD(2)
     (9, 5, 40, 33, 1, -1, 11, 4.0),      # odd vocab (no 16-byte alignment), wide range
+    (10, 3, 20, 128, 1, -1, 10, 1.0),    # TMA fast path, cluster of 2
+    (11, 2, 9, 192, 1, -1, 6, 3.0),      # TMA fast path, cluster of 3
+    (12, 5, 37, 64, 1, -1, 9, 1.0),      # TMA fast path, single CTA, T > ring depth
 ]
+
+
+def test_fast_path_ragged_and_empty_utterances():
+  """Fast (TMA) path with num_frames in {0, 1, < ring depth, T}: same results
+  as the generic kernels and as the oracle."""
+  b, t, vocab, ctx, u = 5, 23, 64, 1, 4
+  rng = np.random.RandomState(5)
+  table_np = rng.randn(b, t, 1 + vocab, 1 + vocab).astype(np.float32)
+  nf = np.array([0, 1, 2, 7, 23])
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = np.array([0, 1, 2, 4, 3])
+  tab64 = table_np.astype(np.float64)
+  o_loss, o_gb, o_gl = O.lattice_loss_and_grads(
+      tab64[..., 0].copy(), tab64[..., 1:].copy(), nf, labels, nl, O.FullNGram(vocab, ctx))
+  outs = []
+  for flags in [0, 1]:            # 0: fast path, 1: LT_FLAG_FORCE_GENERIC
+    table = cuda(table_np).requires_grad_()
+    lattice = make_lattice(vocab, ctx, -1, table, flags)
+    loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                   num_labels=cuda(nl), cache=None)
+    (gt,) = torch.autograd.grad(loss.sum(), table)
+    npt.assert_allclose(loss.detach().cpu(), o_loss, rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(gt.cpu().numpy()[..., 0], o_gb, rtol=1e-4, atol=1e-5)
+    npt.assert_allclose(gt.cpu().numpy()[..., 1:], o_gl, rtol=1e-4, atol=1e-5)
+    outs.append((loss.detach().cpu().numpy(), gt.cpu().numpy()))
+  npt.assert_allclose(outs[0][0], outs[1][0], rtol=2e-6, atol=2e-6)
+  npt.assert_allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=2e-6)
 
 
 @pytest.mark.parametrize('flags', [0, 1 << 8, 4 << 8, 8 << 8])
