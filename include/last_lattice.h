@@ -124,6 +124,11 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
  *   -> blank_w, lexical_w [B,T,U1]
  * scatter_add: its transpose, grad_dense[b,t,states[u],(label-1)] += scale*g
  */
+/* walk_states (contexts.py:109-146, FullNGram.next_state :190-205):
+ *   labels [B,U] int32 in [0,V] -> states [B,U+1], next_labels [B,U+1] */
+int lt_walk_states(int vocab_size, int context_size, const int32_t* labels,
+                   int B, int U, int32_t* states, int32_t* next_labels,
+                   void* stream);
 int lt_string_gather(int vocab_size, int num_states, const float* blank,
                      const float* lexical, const int32_t* states,
                      const int32_t* next_labels, int B, int T, int U1,

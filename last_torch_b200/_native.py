@@ -40,6 +40,7 @@ SIGNATURES = {
                             _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_viterbi_backtrace': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int,
                              _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_walk_states': [_c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr],
     'lt_string_gather': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr],
     'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,

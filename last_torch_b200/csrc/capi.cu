@@ -162,6 +162,18 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
   return viterbi_launch(p, (cudaStream_t)stream);
 }
 
+int lt_walk_states(int vocab_size, int context_size, const int32_t* labels, int B, int U,
+                   int32_t* states, int32_t* next_labels, void* stream) {
+  NGram g;
+  LT_CHECK_ARG(make_ngram(vocab_size, context_size, &g),
+               "lt_walk_states: bad FullNGram(vocab_size=%d, context_size=%d)", vocab_size,
+               context_size);
+  LT_CHECK_ARG(B >= 0 && U >= 0, "lt_walk_states: bad sizes B=%d U=%d", B, U);
+  if (B == 0) return LT_OK;
+  LT_CHECK_ARG(states && next_labels && (U == 0 || labels), "lt_walk_states: NULL pointer");
+  return walk_states_launch(g, labels, B, U, states, next_labels, (cudaStream_t)stream);
+}
+
 int lt_string_gather(int vocab_size, int num_states, const float* blank, const float* lexical,
                      const int32_t* states, const int32_t* next_labels, int B, int T, int U1,
                      float* blank_w, float* lexical_w, void* stream) {

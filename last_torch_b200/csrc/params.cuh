@@ -93,6 +93,8 @@ int string_gather_launch(int V, int C, const float* blank, const float* lexical,
 int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
                           float scale, float* gblank, float* glex, cudaStream_t stream);
+int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
+                       int32_t* next_labels, cudaStream_t stream);
 int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);
 int string_backward_launch(int semiring, const StrParams& p, cudaStream_t stream);
 int semiring_plus_forward_launch(int sr, const float* a, const float* b, float* out, int64_t n,

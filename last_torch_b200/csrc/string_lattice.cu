@@ -53,6 +53,33 @@ __global__ void string_scatter_kernel(int V, int C, const float* __restrict__ gb
   }
 }
 
+// ContextDependency.walk_states for FullNGram (contexts.py:109-146 with
+// next_state :190-205) plus the "next label" row of lattices.py:336-338 / :314-315.
+// One thread per utterance: U sequential integer steps.
+__global__ void walk_states_kernel(NGram g, const int32_t* __restrict__ labels, int B, int U,
+                                   int32_t* __restrict__ states, int32_t* __restrict__ next_labels) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int U1 = U + 1;
+  int s = 0;
+  states[(size_t)b * U1] = 0;
+  for (int u = 0; u < U; ++u) {
+    const int y = labels[(size_t)b * U + u];
+    if (y != 0) s = ngram_next(g, s, y - 1);          // epsilon (0) stays in place
+    states[(size_t)b * U1 + u + 1] = s;
+    next_labels[(size_t)b * U1 + u] = y < 1 ? 1 : y;  // label 0 is read as label 1
+  }
+  next_labels[(size_t)b * U1 + U] = 1;
+}
+
+int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
+                       int32_t* next_labels, cudaStream_t stream) {
+  if (B == 0) return LT_OK;
+  walk_states_kernel<<<(B + 127) / 128, 128, 0, stream>>>(g, labels, B, U, states, next_labels);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
 // ------------------------------------------------------------------ forward --
 
 // last_i[u] = alpha[u-i] (x) lex[u-i] (x) ... (x) lex[u-1], associated in the

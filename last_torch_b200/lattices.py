@@ -108,11 +108,9 @@ class RecognitionLattice(nn.Module, Generic[T]):
   def _string_indices(self, labels, device):
     """context states along the label string and the label leaving each of
     them (lattices.py:336-338; label 0 is read as label 1, :314-315)."""
-    labels = labels.reshape(-1, labels.shape[-1]).to(device=device, dtype=torch.int64)
-    states = self.context.walk_states(labels)
-    next_labels = torch.cat([labels, torch.ones_like(labels[:, :1])], dim=-1)
-    next_labels = torch.where(next_labels - 1 < 0, torch.ones_like(next_labels), next_labels)
-    return states.to(torch.int32).contiguous(), next_labels.to(torch.int32).contiguous()
+    labels = labels.reshape(-1, labels.shape[-1]).to(device=device, dtype=torch.int32)
+    return ops.walk_states(labels.contiguous(), self.context.vocab_size,
+                           self.context.context_size)
 
   # -- public API --------------------------------------------------------------
 

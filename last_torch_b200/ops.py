@@ -200,8 +200,37 @@ def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
 # K3: numerator on the label lattice
 # ---------------------------------------------------------------------------
 
+def walk_states(labels: torch.Tensor, V: int, n: int):
+  """labels [B,U] int32 (CUDA) -> (states [B,U+1], next_labels [B,U+1]) int32:
+  FullNGram.walk_states (contexts.py:109-146) and labels ++ [1] with label 0
+  read as label 1 (lattices.py:314-315, :336-338), in one kernel."""
+  labels = N.require_cuda(labels, 'labels', torch.int32)
+  B, U = labels.shape
+  states = torch.empty([B, U + 1], dtype=torch.int32, device=labels.device)
+  next_labels = torch.empty([B, U + 1], dtype=torch.int32, device=labels.device)
+  with torch.cuda.device(labels.device):
+    N.check(N.lib().lt_walk_states(V, n, N.ptr(labels), B, U, N.ptr(states), N.ptr(next_labels),
+                                   N.stream_ptr(labels.device)), 'lt_walk_states')
+  return states, next_labels
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+  """One extra stream per device for the (tiny, latency-bound) numerator
+  kernels, so that they overlap the HBM-bound denominator kernels."""
+  key = (device.type, device.index)
+  if key not in _SIDE_STREAMS:
+    _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+  return _SIDE_STREAMS[key]
+
 def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels,
-                        need_grad):
+                        need_grad, side=None):
+  """gather + string forward.  With `side` (a torch.cuda.Stream) the two kernels
+  are enqueued there (after everything already on the current stream); the
+  caller joins with current_stream().wait_stream(side).  Buffers are always
+  allocated on the current stream, so the caching allocator stays correct."""
   B, T, _ = blank.shape
   U1 = states.shape[-1]
   dev = blank.device
@@ -213,32 +242,45 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
   backptr = (torch.empty([B, T, U1], dtype=torch.uint8, device=dev)
              if need_grad and sr == N.MAXTROPICAL else None)
   with torch.cuda.device(dev):
-    L = N.lib()
-    N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
-                               N.ptr(next_labels), B, T, U1, N.ptr(bw), N.ptr(lw),
-                               N.stream_ptr(dev)), 'lt_string_gather')
-    N.check(L.lt_string_forward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels),
-                                B, T, U1, N.ptr(dist), N.ptr(alphas), N.ptr(backptr),
-                                N.stream_ptr(dev)), 'lt_string_forward')
+    if side is not None:
+      side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):           # stream(None) is a no-op
+      L = N.lib()
+      N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
+                                 N.ptr(next_labels), B, T, U1, N.ptr(bw), N.ptr(lw),
+                                 N.stream_ptr(dev)), 'lt_string_gather')
+      N.check(L.lt_string_forward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames),
+                                  N.ptr(num_labels), B, T, U1, N.ptr(dist), N.ptr(alphas),
+                                  N.ptr(backptr), N.stream_ptr(dev)), 'lt_string_forward')
   return dist, bw, lw, alphas, backptr
 
 
-def _string_backward_into(sr, k, V, C, bw, lw, num_frames, num_labels, alphas, backptr, dist,
-                          g_dist, states, next_labels, scale, gb, gl):
-  """Numerator posteriors scattered (x scale) into the dense gradient buffers."""
+def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist, g_dist,
+                     side=None):
+  """Numerator posteriors on the label lattice: (grad_blank_w, grad_lexical_w)."""
   B, T, U1 = bw.shape
   dev = bw.device
   gbw = torch.empty_like(bw)
   glw = torch.empty_like(lw)
   with torch.cuda.device(dev):
-    L = N.lib()
-    N.check(L.lt_string_backward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames),
-                                 N.ptr(num_labels), B, T, U1, N.ptr(alphas), N.ptr(backptr),
-                                 N.ptr(dist), N.ptr(g_dist), N.ptr(gbw), N.ptr(glw),
-                                 N.stream_ptr(dev)), 'lt_string_backward')
-    N.check(L.lt_string_scatter_add(V, C, N.ptr(gbw), N.ptr(glw), N.ptr(states),
-                                    N.ptr(next_labels), B, T, U1, float(scale), N.ptr(gb),
-                                    N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
+    if side is not None:
+      side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+      N.check(N.lib().lt_string_backward(
+          sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels), B, T, U1,
+          N.ptr(alphas), N.ptr(backptr), N.ptr(dist), N.ptr(g_dist), N.ptr(gbw), N.ptr(glw),
+          N.stream_ptr(dev)), 'lt_string_backward')
+  return gbw, glw
+
+
+def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl):
+  """grad_dense[b, t, states[u], next_labels[u] - 1] += scale * grad_w[b, t, u]."""
+  B, T, U1 = gbw.shape
+  dev = gbw.device
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_string_scatter_add(
+        V, C, N.ptr(gbw), N.ptr(glw), N.ptr(states), N.ptr(next_labels), B, T, U1, float(scale),
+        N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
 
 
 class StringForward(torch.autograd.Function):
@@ -263,8 +305,9 @@ class StringForward(torch.autograd.Function):
     g_dist = N.require_cuda(g_dist, 'grad_dist')
     gb = torch.zeros(shape, dtype=torch.float32, device=bw.device)
     gl = torch.zeros((*shape, V), dtype=torch.float32, device=bw.device)
-    _string_backward_into(sr, k, V, C, bw, lw, num_frames, num_labels, alphas, backptr, dist,
-                          g_dist, states, next_labels, 1.0, gb, gl)
+    gbw, glw = _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist,
+                                g_dist)
+    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl)
     return gb, gl, None, None, None, None, None, None, None
 
 
@@ -281,11 +324,16 @@ class LatticeLoss(torch.autograd.Function):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
     need_grad = any(ctx.needs_input_grad[:2])
+    # the numerator (tiny, latency-bound) runs on a side stream under the
+    # HBM-bound denominator kernel
+    side = _side_stream(blank.device)
+    num, bw, lw, s_alphas, _ = _string_forward_raw(
+        N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
+        side=side)
     log_z, alphas, _, levels, _, _ = _lattice_forward_raw(
         N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
         want_backptr=False)
-    num, bw, lw, s_alphas, _ = _string_forward_raw(
-        N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad)
+    torch.cuda.current_stream(blank.device).wait_stream(side)
     ctx.geom = (V, n, k, flags)
     ctx.save_for_backward(blank, lexical, num_frames, log_z, alphas, levels, bw, lw, num_labels,
                           s_alphas, num, states, next_labels)
@@ -305,11 +353,14 @@ class LatticeLoss(torch.autograd.Function):
     g_numr = N.require_cuda(g_numr, 'grad')
     gb = torch.empty_like(blank)
     gl = torch.empty_like(lexical)
+    side = _side_stream(dev)
+    gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
+                                g_numr, side=side)
     with torch.cuda.device(dev):
       N.check(N.lib().lt_lattice_backward(
           N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
           N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None, flags,
           N.stream_ptr(dev)), 'lt_lattice_backward')
-    _string_backward_into(N.LOG, k, V, C, bw, lw, num_frames, num_labels, s_alphas, None, num,
-                          g_numr, states, next_labels, 1.0, gb, gl)
+      torch.cuda.current_stream(dev).wait_stream(side)
+    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl)
     return gb, gl, None, None, None, None, None, None, None, None
