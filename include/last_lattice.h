@@ -185,10 +185,13 @@ int lt_semiring_sum_backward(int semiring, const float* a, const float* out,
  * The vocabulary projection runs on tcgen05 tensor cores with a 3-way bf16
  * split of both operands (fp32-accurate).
  */
+/* Bytes of device scratch lt_joint_forward needs (bf16 hi/lo split of W_vocab). */
+int64_t lt_joint_workspace_bytes(int C, int H, int V);
 int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
                      const float* w_blank, float b_blank, const float* w_vocab,
                      const float* b_vocab, int64_t N, int C, int H, int V,
-                     float* blank, float* lexical, void* stream);
+                     float* blank, float* lexical, void* workspace,
+                     void* stream);
 /* Gradients w.r.t. the joint pre-activation, reduced to the two projections:
  *   grad_proj_ctx [C,H] (+= over N), grad_proj_frame [N,H] (+= over C),
  *   grad_w_blank [H], grad_b_blank [1], grad_w_vocab [V,H], grad_b_vocab [V].

@@ -54,8 +54,9 @@ SIGNATURES = {
     'lt_semiring_sum_forward': [_c_int, _ptr, _c_i64, _c_i64, _c_i64, _ptr, _ptr, _ptr],
     'lt_semiring_sum_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_i64, _c_i64, _ptr,
                                  _ptr],
+    'lt_joint_workspace_bytes': [_c_int, _c_int, _c_int],
     'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
-                         _ptr, _ptr, _ptr],
+                         _ptr, _ptr, _ptr, _ptr],
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
 }
@@ -86,7 +87,8 @@ def lib():
       fn = getattr(handle, name)     # AttributeError if a symbol is missing
       fn.argtypes = argtypes
       fn.restype = (ctypes.c_char_p if name == 'lt_last_error' else
-                    ctypes.c_ulonglong if name == 'lt_launch_count' else _c_int)
+                    ctypes.c_ulonglong if name == 'lt_launch_count' else
+                    ctypes.c_int64 if name == 'lt_joint_workspace_bytes' else _c_int)
     _lib = _TimedLib(handle)
   return _lib
 
@@ -95,7 +97,8 @@ def lib():
 # native call then appends (name, start_event, end_event) recorded on the
 # current stream of the current device -- the stream the kernel is launched on).
 KERNEL_TIMER = None
-_UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count')
+_UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count',
+            'lt_joint_workspace_bytes')
 
 
 class _TimedLib:

@@ -144,15 +144,24 @@ int joint_backward_simt(const float* pc, const float* pf, const float* wb, const
 
 using namespace lt;
 
+extern "C" int64_t lt_joint_workspace_bytes(int C, int H, int V) {
+  (void)C;
+  return (int64_t)V * H * 2 * 2 + 256;   // W_vocab as bf16 hi + lo
+}
+
 extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
                                 const float* w_blank, float b_blank, const float* w_vocab,
                                 const float* b_vocab, int64_t N, int C, int H, int V,
-                                float* blank, float* lexical, void* stream) {
+                                float* blank, float* lexical, void* workspace, void* stream) {
   LT_CHECK_ARG(N >= 0 && C > 0 && H > 0 && V > 0, "lt_joint_forward: bad sizes N=%lld C=%d H=%d V=%d",
                (long long)N, C, H, V);
   if (N == 0) return LT_OK;
   LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && w_vocab && b_vocab && blank && lexical,
                "lt_joint_forward: NULL pointer");
+  if (workspace && reinterpret_cast<uintptr_t>(workspace) % 128 == 0 &&
+      joint_tc_supported(N, C, H, V, proj_ctx, proj_frame, lexical))
+    return joint_forward_tc_launch(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, N, C,
+                                   H, V, blank, lexical, workspace, (cudaStream_t)stream);
   return joint_forward_simt(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, N, C, H, V,
                             blank, lexical, (cudaStream_t)stream);
 }

@@ -1,0 +1,448 @@
+// K4 on 5th-generation tensor cores (tcgen05 + TMEM), hand-written.
+//
+// Precision: the reference computes the vocabulary projection in fp32
+// (weight_fns.py:220-227) and parity is 1e-5, which plain bf16 / tf32 inputs
+// cannot hold.  Both operands are therefore split  x = hi + lo  into two bf16
+// values (|x - hi - lo| <= 2^-17 |x|) and the product is accumulated in fp32 in
+// TMEM as  Ah*Bh + Ah*Bl + Al*Bh  (three tcgen05.mma per K step; the dropped
+// Al*Bl term is 2^-18 relative).
+//
+// This file currently holds the validated building block (ltx_umma_probe, used
+// by tests/test_gpu_umma.py): operands written by threads into the K-major
+// SWIZZLE_128B shared-memory layout, tcgen05.mma issued by one thread,
+// completion via tcgen05.commit -> mbarrier, accumulator read back with
+// tcgen05.ld.  The pipelined JointWeightFn kernels are built from it.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "params.cuh"
+#include "umma.cuh"
+
+namespace lt {
+namespace {
+
+__device__ __forceinline__ void mbar_init1(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTJ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTJ_DONE;\n"
+      "bra LTJ_WAIT;\n"
+      "LTJ_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Writes rows [0, nrows) x 64 K-elements of a row-major fp32 matrix (leading
+// dimension ld) as bf16 hi / lo tiles in the K-major SWIZZLE_128B layout.
+__device__ __forceinline__ void fill_tile_split(const float* __restrict__ src, int ld, int nrows,
+                                                unsigned char* hi, unsigned char* lo, int tid,
+                                                int nthreads) {
+  for (int idx = tid; idx < nrows * 8; idx += nthreads) {
+    const int row = idx >> 3, chunk = idx & 7;
+    const float4 x0 = *reinterpret_cast<const float4*>(src + (size_t)row * ld + chunk * 8);
+    const float4 x1 = *reinterpret_cast<const float4*>(src + (size_t)row * ld + chunk * 8 + 4);
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) umma::split_bf16(x[i], h[i], l[i]);
+    const uint32_t off = umma::swizzled_offset(row, chunk);
+    *reinterpret_cast<uint4*>(hi + off) =
+        make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]),
+                   umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+    *reinterpret_cast<uint4*>(lo + off) =
+        make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]),
+                   umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+  }
+}
+
+// D[128, N] = A[128, K] * B[N, K]^T  (fp32 in/out, bf16x3 on tcgen05).  One CTA.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                  int N, int K, int terms) {
+  extern __shared__ __align__(1024) unsigned char psmem_raw[];
+  // SWIZZLE_128B atoms need a 1024-byte aligned base: align by hand
+  unsigned char* psmem = psmem_raw + ((1024u - (smem_u32(psmem_raw) & 1023u)) & 1023u);
+  unsigned char* a_hi = psmem;                       // 128 x 128 B
+  unsigned char* a_lo = a_hi + 128 * 128;
+  unsigned char* b_hi = a_lo + 128 * 128;            // N x 128 B
+  unsigned char* b_lo = b_hi + 256 * 128;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init1(smem_u32(&mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_base), 256);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = umma::make_idesc_bf16(128, N);
+  const int nchunks = K / 64;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    fill_tile_split(A + kc * 64, K, 128, a_hi, a_lo, tid, blockDim.x);
+    fill_tile_split(B + kc * 64, K, N, b_hi, b_lo, tid, blockDim.x);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_thread_sync();
+      for (int k = 0; k < 4; ++k) {           // 4 x (K = 16 bf16 = 32 bytes) per 128-byte row
+        const uint64_t dah = umma::make_smem_desc_sw128(smem_u32(a_hi) + k * 32);
+        const uint64_t dal = umma::make_smem_desc_sw128(smem_u32(a_lo) + k * 32);
+        const uint64_t dbh = umma::make_smem_desc_sw128(smem_u32(b_hi) + k * 32);
+        const uint64_t dbl = umma::make_smem_desc_sw128(smem_u32(b_lo) + k * 32);
+        umma::mma_bf16(tmem, dah, dbh, idesc, (kc | k) > 0);
+        if (terms >= 2) umma::mma_bf16(tmem, dah, dbl, idesc, 1);
+        if (terms >= 3) umma::mma_bf16(tmem, dal, dbh, idesc, 1);
+      }
+      umma::commit(smem_u32(&mbar));          // arrives when the MMAs above have completed
+    }
+    mbar_wait_parity(smem_u32(&mbar), kc & 1);   // operands may be overwritten after this
+  }
+  umma::fence_after_thread_sync();
+  // epilogue: warp w owns TMEM lanes (= rows) 32w .. 32w+31
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t)row * N + c0 + i] = v[i];
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+
+// ===========================================================================
+// JointWeightFn forward on tcgen05 (weight_fns.py:208-227, whole-utterance form)
+//   lexical[m, :] = tanh(pc[c] + pf[n]) . W_vocab^T + b_vocab      m = n*C + c
+//   blank[m]      = tanh(pc[c] + pf[n]) . w_blank   + b_blank
+// Persistent CTAs (one per SM), tile = 128 rows x V columns, K = H in chunks of 64.
+// Warp roles (448 threads):
+//   warp 0      TMA producer: W_hi / W_lo chunk [V x 64] bf16 (SWIZZLE_128B tensor maps)
+//   warp 1      MMA issuer (one thread): 3 tcgen05.mma per 16-wide K step (bf16x3 split)
+//   warps 2-5   epilogue: TMEM -> registers -> + bias -> coalesced row stores
+//   warps 6-13  A producers: tanh(pc + pf) on the fly, hi/lo split, swizzled smem
+//               stores; the same threads accumulate the blank mat-vec in registers
+// Pipelines: smem full/empty (2 stages), TMEM full/empty (2 accumulators of 256 columns),
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  The [M, H] joint
+// activations never touch HBM.
+// ===========================================================================
+constexpr int kJThreads = 448;
+constexpr int kJStages = 2;
+constexpr int kJProducers = 256;
+
+struct JointTcParams {
+  const float* pc;       // [C, H]
+  const float* pf;       // [N, H]
+  const float* w_blank;  // [H]
+  const float* b_vocab;  // [V]
+  float b_blank;
+  long long M;           // N * C
+  int C, H, V;
+  float* blank;          // [M]
+  float* lexical;        // [M, V]
+};
+
+__device__ __forceinline__ void mbar_init_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                       uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU ops; absolute error ~1e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (2.f * kLog2e)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(-2.f, r, 1.f);
+}
+
+__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    umma::split_bf16(w[i], hi[i], lo[i]);
+}
+
+__global__ void __launch_bounds__(kJThreads, 1)
+joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
+                        const __grid_constant__ CUtensorMap map_lo, const JointTcParams p) {
+  extern __shared__ __align__(1024) unsigned char jsmem_raw[];
+  unsigned char* base = jsmem_raw + ((1024u - (smem_u32(jsmem_raw) & 1023u)) & 1023u);
+  const int V = p.V, H = p.H;
+  const uint32_t a_bytes = 128 * 128;                 // one 128 x 64 bf16 tile
+  const uint32_t b_bytes = (uint32_t)V * 128;         // one V x 64 bf16 tile
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
+  // stage layout: A_hi | A_lo | B_hi | B_lo
+  float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
+  float* s_bias = s_wb + H;                                                // [V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint64_t* full = bars;                    // [stages]  producers + TMA -> MMA
+  uint64_t* empty = bars + kJStages;        // [stages]  MMA (commit) -> producers, TMA
+  uint64_t* tfull = bars + 2 * kJStages;    // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = H / 64;
+  const long long num_tiles = (p.M + 127) / 128;
+
+  for (int i = tid; i < H; i += kJThreads) s_wb[i] = p.w_blank[i];
+  for (int i = tid; i < V; i += kJThreads) s_bias[i] = p.b_vocab[i];
+  if (tid == 0) {
+    for (int s = 0; s < kJStages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), kJProducers + 1);
+      mbar_init_n(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init_n(smem_u32(&tfull[a]), 1);
+      mbar_init_n(smem_u32(&tempty[a]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+  }
+  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------- TMA producer (B)
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kJStages;
+          mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full[s]);
+          const uint32_t dst = smem_u32(base) + s * stage_bytes + 2 * a_bytes;
+          mbar_expect_tx(bar, 2 * b_bytes);
+          tma_2d(dst, &map_hi, kc * 64, 0, bar);
+          tma_2d(dst + 256 * 128, &map_lo, kc * 64, 0, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_bf16(128, V);
+      uint32_t g = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+        umma::fence_after_thread_sync();
+        const uint32_t d = tmem + acc * 256;
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kJStages;
+          mbar_wait_parity(smem_u32(&full[s]), (g / kJStages) & 1);
+          umma::fence_after_thread_sync();
+          const uint32_t sa = smem_u32(base) + s * stage_bytes;
+          const uint32_t sb = sa + 2 * a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
+            const uint64_t dal = umma::make_smem_desc_sw128(sa + a_bytes + k * 32);
+            const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
+            const uint64_t dbl = umma::make_smem_desc_sw128(sb + 256 * 128 + k * 32);
+            umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
+            umma::mma_bf16(d, dah, dbl, idesc, 1);
+            umma::mma_bf16(d, dal, dbh, idesc, 1);
+          }
+          umma::commit(smem_u32(&empty[s]));           // stage reusable once these MMAs retire
+        }
+        umma::commit(smem_u32(&tfull[acc]));           // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
+      umma::fence_after_thread_sync();
+      const long long m = tile * 128 + quad * 32 + lane;
+      float* out = p.lexical + (size_t)m * V;
+      for (int c0 = 0; c0 < V; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            stg_stream4(out + c0 + j, make_float4(v[j] + s_bias[c0 + j], v[j + 1] + s_bias[c0 + j + 1],
+                                                  v[j + 2] + s_bias[c0 + j + 2],
+                                                  v[j + 3] + s_bias[c0 + j + 3]));
+        }
+      }
+      umma::fence_before_thread_sync();
+      mbar_arrive(smem_u32(&tempty[acc]));
+    }
+  } else {
+    // -------------------------------------------------------------- A producers
+    const int pidx = tid - 6 * 32;                      // 0 .. 255
+    const int row = pidx >> 1, half = pidx & 1;
+    uint32_t g = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m = tile * 128 + row;
+      const bool valid = m < p.M;
+      const long long n = valid ? m / p.C : 0;
+      const int c = valid ? (int)(m - n * p.C) : 0;
+      const float* pc_row = p.pc + (size_t)c * H + half * 32;
+      const float* pf_row = p.pf + (size_t)n * H + half * 32;
+      float bacc = 0.f;
+      for (int kc = 0; kc < nchunks; ++kc, ++g) {
+        const int s = g % kJStages;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(pc_row + kc * 64) + j);
+          const float4 f = __ldg(reinterpret_cast<const float4*>(pf_row + kc * 64) + j);
+          x[4 * j] = a.x + f.x; x[4 * j + 1] = a.y + f.y;
+          x[4 * j + 2] = a.z + f.z; x[4 * j + 3] = a.w + f.w;
+        }
+        const float* wb = s_wb + kc * 64 + half * 32;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t0 = valid ? tanh_fast(x[2 * j]) : 0.f;
+          const float t1 = valid ? tanh_fast(x[2 * j + 1]) : 0.f;
+          bacc = fmaf(t0, wb[2 * j], bacc);
+          bacc = fmaf(t1, wb[2 * j + 1], bacc);
+          __nv_bfloat16 h0, l0, h1, l1;
+          umma::split_bf16(t0, h0, l0);
+          umma::split_bf16(t1, h1, l1);
+          hi[j] = umma::pack_bf16(h0, h1);
+          lo[j] = umma::pack_bf16(l0, l1);
+        }
+        mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+        unsigned char* a_hi = base + s * stage_bytes;
+        unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = umma::swizzled_offset(row, half * 4 + j);
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(&full[s]));
+      }
+      bacc += __shfl_xor_sync(0xffffffffu, bacc, 1);
+      if (valid && half == 0) p.blank[m] = bacc + p.b_blank;
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+}  // namespace lt
+
+namespace lt {
+
+typedef CUresult (*EncodeTiledFnJ)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFnJ joint_encode_fn() {
+  static EncodeTiledFnJ fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+          cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFnJ>(sym);
+  return fn;
+}
+
+bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const void* pf,
+                        const void* lexical) {
+  if (getenv("LT_JOINT_SIMT")) return false;
+  if (V % 32 != 0 || V < 32 || V > 256) return false;
+  if (H % 64 != 0 || H > 4096) return false;
+  if (N * (int64_t)C < 1) return false;
+  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  return al(pc) && al(pf) && al(lexical);
+}
+
+// lexical / blank of all M = N*C joint rows on tcgen05 (bf16x3 split, fp32 accumulate).
+int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
+                            const float* wv, const float* bv, int64_t N, int C, int H, int V,
+                            float* blank, float* lexical, void* workspace, cudaStream_t stream) {
+  EncodeTiledFnJ encode = joint_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
+  // caller-provided scratch for the bf16 hi / lo split of W_vocab (V*H*4 bytes)
+  __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* wlo = whi + (size_t)V * H;
+  split_weights_kernel<<<(V * H + 255) / 256, 256, 0, stream>>>(wv, whi, wlo, V * H);
+  LT_LAUNCHED();
+  CUtensorMap map_hi, map_lo;
+  cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)V};
+  cuuint64_t strides[1] = {(cuuint64_t)H * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)V};
+  cuuint32_t estr[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult r = encode(i == 0 ? &map_hi : &map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        i == 0 ? whi : wlo, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (W_vocab) failed with %d", (int)r);
+      return LT_ERR_CUDA;
+    }
+  }
+  JointTcParams p = {};
+  p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
+  p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
+  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + sizeof(float) * (H + 256) +
+                      16 * 8 + 16 + 1024;
+  int dev = 0, sms = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (p.M + 127) / 128;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  LT_CUDA(cudaFuncSetAttribute(joint_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  joint_forward_tc_kernel<<<grid, kJThreads, smem, stream>>>(map_hi, map_lo, p);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
+}  // namespace lt
+
+// Diagnostic entry point (not part of include/last_lattice.h): D = A * B^T with
+// A [128,K], B [N,K] fp32 device pointers, N % 16 == 0, N <= 256, K % 64 == 0.
+extern "C" int ltx_umma_probe(const float* A, const float* B, float* D, int N, int K, int terms,
+                              void* stream) {
+  using namespace lt;
+  LT_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K > 0,
+               "ltx_umma_probe: need N %% 16 == 0, N <= 256, K %% 64 == 0 (N=%d K=%d)", N, K);
+  const size_t smem = 2 * 128 * 128 + 2 * 256 * 128 + 1024;
+  LT_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, terms);
+  LT_LAUNCHED();
+  return LT_OK;
+}

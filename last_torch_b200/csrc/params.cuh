@@ -106,6 +106,12 @@ int semiring_sum_forward_launch(int sr, const float* a, int64_t outer, int64_t R
 int semiring_sum_backward_launch(int sr, const float* a, const float* out, const int32_t* argmax,
                                  const float* g, int64_t outer, int64_t R, int64_t inner,
                                  float* ga, cudaStream_t stream);
+// tcgen05 joint projection (joint_tc.cu)
+bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const void* pf,
+                        const void* lexical);
+int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
+                            const float* wv, const float* bv, int64_t N, int C, int H, int V,
+                            float* blank, float* lexical, void* workspace, cudaStream_t stream);
 int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);
 
 }  // namespace lt

@@ -1,0 +1,104 @@
+// Minimal hand-written tcgen05 / TMEM plumbing for sm_100a (no CUTLASS):
+// shared-memory matrix descriptors (K-major, SWIZZLE_128B), instruction
+// descriptors for kind::f16 (bf16 inputs, fp32 accumulate), TMEM alloc / ld /
+// commit / fences.  Bit layouts follow the PTX ISA "tcgen05" matrix- and
+// instruction-descriptor tables.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lt {
+namespace umma {
+
+// ---- K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B --------
+// Row r (an M or N index) occupies 128 bytes = 64 bf16 along K.  Rows are grouped
+// in atoms of 8 rows x 128 B = 1024 B (tile base must be 1024-byte aligned); the
+// 16-byte chunk c of row r is stored at chunk position c ^ (r & 7).
+__device__ __forceinline__ uint32_t swizzled_offset(int row, int chunk16) {
+  return (uint32_t)row * 128u + (uint32_t)((chunk16 ^ (row & 7)) << 4);
+}
+
+// 64-bit shared-memory matrix descriptor.
+//   [0,14)  start address >> 4          [16,30) leading byte offset >> 4 (unused for
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row atoms)      swizzled K-major)
+//   [46,48) version = 1 (Blackwell)      [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;            // SBO
+  d |= (uint64_t)1 << 46;                       // version
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+
+// 32-bit instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major.
+//   [4,6) c_format 1=F32   [7,10) a_format 1=BF16   [10,13) b_format 1=BF16
+//   [15] a_major 0=K  [16] b_major 0=K   [17,23) N>>3   [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::
+                   "r"(smem_result_addr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void fence_before_thread_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_thread_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive (count 1) when all previously issued MMAs of this thread completed.
+__device__ __forceinline__ void commit(uint32_t mbar_smem_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+                   "r"(mbar_smem_addr) : "memory");
+}
+// Each thread of the warp reads 32 consecutive fp32 columns of ITS TMEM lane.
+// taddr = (lane_base << 16) | column; a warp may only touch lanes 32*(warp%4)..+31.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (hi, lo) bf16 split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+}  // namespace umma
+}  // namespace lt

@@ -28,11 +28,13 @@ class _JointProjection(torch.autograd.Function):
     dev = proj_frame.device
     blank = torch.empty([n, c], dtype=torch.float32, device=dev)
     lexical = torch.empty([n, c, v], dtype=torch.float32, device=dev)
+    workspace = torch.empty([int(N.lib().lt_joint_workspace_bytes(c, h, v))], dtype=torch.uint8,
+                            device=dev)
     with torch.cuda.device(dev):
       N.check(N.lib().lt_joint_forward(
           N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), float(b_blank), N.ptr(w_vocab),
-          N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.stream_ptr(dev)),
-          'lt_joint_forward')
+          N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.ptr(workspace),
+          N.stream_ptr(dev)), 'lt_joint_forward')
     ctx.save_for_backward(proj_ctx, proj_frame, w_blank, w_vocab)
     return blank, lexical
 

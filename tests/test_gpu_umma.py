@@ -1,0 +1,76 @@
+"""tcgen05 building block: D = A * B^T through hand-written UMMA descriptors,
+bf16 hi/lo split operands and an fp32 TMEM accumulator, against fp32 matmul."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _probe(a, b, terms):
+  from last_torch_b200 import _native as N
+  N.lib()
+  handle = ctypes.CDLL(N.LIB_PATH)
+  fn = handle.ltx_umma_probe
+  fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+  fn.restype = ctypes.c_int
+  n, k = b.shape
+  d = torch.empty([128, n], device='cuda')
+  rc = fn(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, terms,
+          torch.cuda.current_stream().cuda_stream)
+  assert rc == 0, handle.lt_last_error()
+  torch.cuda.synchronize()
+  return d
+
+
+@pytest.mark.parametrize('n,k', [(256, 64), (256, 512), (64, 128), (32, 64), (128, 256)])
+def test_umma_probe_matches_fp32_matmul(n, k):
+  g = torch.Generator(device='cuda').manual_seed(n * 1000 + k)
+  a = torch.randn([128, k], device='cuda', generator=g)
+  b = torch.randn([n, k], device='cuda', generator=g)
+  ref = (a.double() @ b.double().T)
+  scale = float(ref.abs().max())
+  d1 = _probe(a, b, 1)
+  d3 = _probe(a, b, 3)
+  err1 = float((d1.double() - ref).abs().max()) / scale
+  err3 = float((d3.double() - ref).abs().max()) / scale
+  # one bf16 term is ~2^-9 accurate, the three-term split ~2^-17
+  assert err1 < 2e-2, err1
+  assert err3 < 2e-5, (err1, err3)
+  assert err3 < err1 / 50
+
+
+@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 70), (65, 64, 128, 9), (33, 32, 64, 5),
+                                     (130, 128, 192, 31)])
+def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
+  """lt_joint_forward on the tcgen05 path (bf16x3 split, fp32 TMEM accumulate)
+  against the fp32 reference formula (weight_fns.py:208-227); 1e-5 of the
+  logit scale, and identical (to 1e-5) to the CUDA-core fp32 kernels."""
+  import os
+  import last_torch_b200 as lt
+  torch.manual_seed(c + v)
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=48,
+                                   feature_size=40)
+  cache = torch.randn([c, 48], device='cuda')
+  frames = torch.randn([n, 1, 40], device='cuda')
+  with torch.no_grad():
+    kb, kl = fn.all_frames(cache, frames)                  # kernel path: [n,1,c], [n,1,c,v]
+    pcx = fn.context_projection(cache).double()
+    pfx = fn.blank_projection(frames[:, 0]).double()
+    joint = torch.tanh(pcx[None] + pfx[:, None])
+    rl = joint @ fn.joint_projection_to_vocab.weight.double().T + fn.joint_projection_to_vocab.bias.double()
+    rb = joint @ fn.joint_projection_to_blank.weight.double()[0] + fn.joint_projection_to_blank.bias.double()
+    os.environ['LT_JOINT_SIMT'] = '1'
+    try:
+      sb, sl = fn.all_frames(cache, frames)
+    finally:
+      del os.environ['LT_JOINT_SIMT']
+  scale = float(rl.abs().max())
+  err_tc = float((kl[:, 0].double() - rl).abs().max()) / scale
+  err_simt = float((sl[:, 0].double() - rl).abs().max()) / scale
+  err_b = float((kb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6)
+  assert err_simt < 2e-6, err_simt
+  assert err_tc < 1e-5, (err_tc, err_simt)
+  assert err_b < 1e-5, err_b
