@@ -202,7 +202,11 @@ int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                       int64_t N, int C, int H, int V, float* grad_proj_ctx,
                       float* grad_proj_frame, float* grad_w_blank,
                       float* grad_b_blank, float* grad_w_vocab,
-                      float* grad_b_vocab, void* stream);
+                      float* grad_b_vocab, void* workspace, void* stream);
+/* Bytes of device scratch for lt_joint_backward (W_vocab^T as bf16 hi/lo + the
+ * [N*C, H] pre-activation gradient that is reduced into the two projections);
+ * workspace may be NULL, which selects the CUDA-core kernels. */
+int64_t lt_joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,8 @@ SIGNATURES = {
     'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr, _ptr],
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
-                          _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+                          _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_joint_backward_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
 }
 
 _lib = None
@@ -88,7 +89,8 @@ def lib():
       fn.argtypes = argtypes
       fn.restype = (ctypes.c_char_p if name == 'lt_last_error' else
                     ctypes.c_ulonglong if name == 'lt_launch_count' else
-                    ctypes.c_int64 if name == 'lt_joint_workspace_bytes' else _c_int)
+                    ctypes.c_int64 if name in ('lt_joint_workspace_bytes',
+                                                'lt_joint_backward_workspace_bytes') else _c_int)
     _lib = _TimedLib(handle)
   return _lib
 
@@ -98,7 +100,7 @@ def lib():
 # current stream of the current device -- the stream the kernel is launched on).
 KERNEL_TIMER = None
 _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count',
-            'lt_joint_workspace_bytes')
+            'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 
 class _TimedLib:

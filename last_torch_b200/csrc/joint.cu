@@ -110,11 +110,12 @@ int joint_forward_simt(const float* pc, const float* pf, const float* wb, float 
 int joint_backward_simt(const float* pc, const float* pf, const float* wb, const float* wv,
                         const float* gb, const float* gl, int64_t N, int C, int H, int V,
                         float* gpc, float* gpf, float* gwb, float* gbb, float* gwv, float* gbv,
-                        cudaStream_t stream) {
+                        int parts, cudaStream_t stream) {
+  // parts: bit 0 = dgrad (grad_proj_ctx / grad_proj_frame), bit 1 = wgrad (weights, biases)
   const int64_t M = N * C;
   if (M == 0) return LT_OK;
   const int64_t rows_per_launch = 65535ll * 64;
-  for (int64_t r0 = 0; r0 < M; r0 += rows_per_launch) {
+  for (int64_t r0 = 0; (parts & 1) && r0 < M; r0 += rows_per_launch) {
     const int64_t rows = min(rows_per_launch, M - r0);
     JointBwd1A A{gl, gb, V};
     JointBwd1B B{wv, wb, V, H};
@@ -125,7 +126,7 @@ int joint_backward_simt(const float* pc, const float* pf, const float* wb, const
     tile_gemm_kernel<<<g, 256, 0, stream>>>(rows, H, (int64_t)(V + 1), (int64_t)(V + 1), a, B, e);
     LT_LAUNCHED();
   }
-  {
+  if (parts & 2) {
     // split the M-long reduction over blockIdx.z
     int64_t kchunk = 4096;
     int64_t nsplit = (M + kchunk - 1) / kchunk;
@@ -166,19 +167,41 @@ extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
                             blank, lexical, (cudaStream_t)stream);
 }
 
+extern "C" int64_t lt_joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
+  return joint_backward_workspace_bytes(N, C, H, V);
+}
+
 extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                                  const float* w_blank, const float* w_vocab,
                                  const float* grad_blank, const float* grad_lexical, int64_t N,
                                  int C, int H, int V, float* grad_proj_ctx,
                                  float* grad_proj_frame, float* grad_w_blank, float* grad_b_blank,
-                                 float* grad_w_vocab, float* grad_b_vocab, void* stream) {
+                                 float* grad_w_vocab, float* grad_b_vocab, void* workspace,
+                                 void* stream) {
   LT_CHECK_ARG(N >= 0 && C > 0 && H > 0 && V > 0, "lt_joint_backward: bad sizes N=%lld C=%d H=%d V=%d",
                (long long)N, C, H, V);
   if (N == 0) return LT_OK;
   LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && w_vocab && grad_blank && grad_lexical &&
                grad_proj_ctx && grad_proj_frame && grad_w_blank && grad_b_blank && grad_w_vocab &&
                grad_b_vocab, "lt_joint_backward: NULL pointer");
+  int simt_parts = 3;
+  if (workspace && reinterpret_cast<uintptr_t>(workspace) % 256 == 0 &&
+      joint_dgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+    int rc = joint_dgrad_tc_launch(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank,
+                                   grad_lexical, N, C, H, V, grad_proj_ctx, grad_proj_frame,
+                                   workspace, (cudaStream_t)stream);
+    if (rc) return rc;
+    simt_parts = 2;
+  }
+  if (joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+    int rc = joint_wgrad_tc_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
+                                   grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
+                                   (cudaStream_t)stream);
+    if (rc) return rc;
+    simt_parts &= ~2;
+  }
+  if (simt_parts == 0) return LT_OK;
   return joint_backward_simt(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank, grad_lexical, N,
                              C, H, V, grad_proj_ctx, grad_proj_frame, grad_w_blank, grad_b_blank,
-                             grad_w_vocab, grad_b_vocab, (cudaStream_t)stream);
+                             grad_w_vocab, grad_b_vocab, simt_parts, (cudaStream_t)stream);
 }

@@ -120,6 +120,80 @@ umma_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
 }
 
 
+// MN-major probe: D[128, N] = At^T * Bt with At [K, 128], Bt [K, N] fp32 row-major
+// (both operands contiguous along M / N).  `swap` exchanges LBO and SBO in the
+// descriptors (used once to pin the descriptor semantics on hardware).
+__global__ void __launch_bounds__(128, 1)
+umma_probe_mn_kernel(const float* __restrict__ At, const float* __restrict__ Bt,
+                     float* __restrict__ D, int N, int K, int swap) {
+  extern __shared__ __align__(1024) unsigned char qsmem_raw[];
+  unsigned char* q = qsmem_raw + ((1024u - (smem_u32(qsmem_raw) & 1023u)) & 1023u);
+  unsigned char* a_hi = q;                        // [128 x 32] bf16 = 8 KB
+  unsigned char* a_lo = a_hi + 128 * 32 * 2;
+  unsigned char* b_hi = a_lo + 128 * 32 * 2;      // [256 x 32] bf16 = 16 KB
+  unsigned char* b_lo = b_hi + 256 * 32 * 2;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init1(smem_u32(&mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_base), 256);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = umma::make_idesc_bf16_mn(128, N);
+  for (int kc = 0; kc < K / 32; ++kc) {
+    for (int idx = tid; idx < 32 * (128 / 8); idx += blockDim.x) {      // A chunks
+      const int k = idx / 16, mn = (idx % 16) * 8;
+      __nv_bfloat16 h[8], l[8];
+      for (int i = 0; i < 8; ++i) umma::split_bf16(At[(size_t)(kc * 32 + k) * 128 + mn + i], h[i], l[i]);
+      const uint32_t off = umma::mn_major_chunk_offset(128, mn, k);
+      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+      *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+    }
+    for (int idx = tid; idx < 32 * (N / 8); idx += blockDim.x) {        // B chunks
+      const int k = idx / (N / 8), mn = (idx % (N / 8)) * 8;
+      __nv_bfloat16 h[8], l[8];
+      for (int i = 0; i < 8; ++i) umma::split_bf16(Bt[(size_t)(kc * 32 + k) * N + mn + i], h[i], l[i]);
+      const uint32_t off = umma::mn_major_chunk_offset(N, mn, k);
+      *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+      *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_thread_sync();
+      const uint32_t a_sbo = (128 / 64) * 1024, b_sbo = (N / 64) * 1024, lbo = 1024;
+      for (int ks = 0; ks < 2; ++ks) {            // K = 16 per instruction = 2 atoms deep
+        const uint32_t aoff = 2 * ks * a_sbo, boff = 2 * ks * b_sbo;
+        const uint64_t dah = umma::make_smem_desc_mn_sw128(smem_u32(a_hi) + aoff, swap ? a_sbo : lbo, swap ? lbo : a_sbo);
+        const uint64_t dal = umma::make_smem_desc_mn_sw128(smem_u32(a_lo) + aoff, swap ? a_sbo : lbo, swap ? lbo : a_sbo);
+        const uint64_t dbh = umma::make_smem_desc_mn_sw128(smem_u32(b_hi) + boff, swap ? b_sbo : lbo, swap ? lbo : b_sbo);
+        const uint64_t dbl = umma::make_smem_desc_mn_sw128(smem_u32(b_lo) + boff, swap ? b_sbo : lbo, swap ? lbo : b_sbo);
+        umma::mma_bf16(tmem, dah, dbh, idesc, (kc | ks) > 0);
+        umma::mma_bf16(tmem, dah, dbl, idesc, 1);
+        umma::mma_bf16(tmem, dal, dbh, idesc, 1);
+      }
+      umma::commit(smem_u32(&mbar));
+    }
+    mbar_wait_parity(smem_u32(&mbar), kc & 1);
+  }
+  umma::fence_after_thread_sync();
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t)row * N + c0 + i] = v[i];
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
 // ===========================================================================
 // JointWeightFn forward on tcgen05 (weight_fns.py:208-227, whole-utterance form)
 //   lexical[m, :] = tanh(pc[c] + pf[n]) . W_vocab^T + b_vocab      m = n*C + c
@@ -355,6 +429,437 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
+
+// ===========================================================================
+// JointWeightFn backward, part 1 (dgrad) on tcgen05:
+//   Gp[m, j] = (sum_v G[m, v] * W_vocab[v, j] + gb[m] * w_blank[j]) * (1 - h[m, j]^2)
+// with h = tanh(pc[c] + pf[n]) recomputed in the epilogue.  Same pipeline as the
+// forward kernel; a work unit is (128-row tile, block of NH <= 256 hidden columns).
+//   A operand: G rows (fp32 from HBM) split hi/lo on the fly, K = V in chunks of 64
+//   B operand: W_vocab^T [H, V] bf16 hi/lo (pre-split, TMA, SWIZZLE_128B)
+// Gp [M, H] is written to a caller-provided workspace and reduced into
+// grad_proj_ctx (sum over frames) / grad_proj_frame (sum over context states) by
+// joint_reduce_kernel (one streaming pass).
+// ===========================================================================
+struct JointDgradParams {
+  const float* pc;       // [C, H]
+  const float* pf;       // [N, H]
+  const float* w_blank;  // [H]
+  const float* gl;       // [M, V]  grad_lexical
+  const float* gb;       // [M]     grad_blank
+  long long M;
+  int C, H, V, NH;       // NH: hidden columns per unit (<= 256, multiple of 32)
+  float* gp;             // [M, H]
+};
+
+__global__ void transpose_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo, int V, int H) {
+  // w [V, H] -> hi/lo [H, V]
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * H; i += gridDim.x * blockDim.x) {
+    const int j = i / V, v = i % V;
+    umma::split_bf16(w[(size_t)v * H + j], hi[i], lo[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kJThreads, 1)
+joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
+                      const __grid_constant__ CUtensorMap map_lo, const JointDgradParams p) {
+  extern __shared__ __align__(1024) unsigned char dsmem_raw[];
+  unsigned char* base = dsmem_raw + ((1024u - (smem_u32(dsmem_raw) & 1023u)) & 1023u);
+  const int V = p.V, H = p.H, NH = p.NH;
+  const uint32_t a_bytes = 128 * 128;
+  const uint32_t b_bytes = (uint32_t)NH * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
+  float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + H);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kJStages;
+  uint64_t* tfull = bars + 2 * kJStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunks = V / 64;
+  const int nblk = H / NH;
+  const long long num_units = ((p.M + 127) / 128) * nblk;
+
+  for (int i = tid; i < H; i += kJThreads) s_wb[i] = p.w_blank[i];
+  if (tid == 0) {
+    for (int s = 0; s < kJStages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), kJProducers + 1);
+      mbar_init_n(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init_n(smem_u32(&tfull[a]), 1);
+      mbar_init_n(smem_u32(&tempty[a]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+  }
+  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int blk = (int)(unit % nblk);
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kJStages;
+          mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full[s]);
+          const uint32_t dst = smem_u32(base) + s * stage_bytes + 2 * a_bytes;
+          mbar_expect_tx(bar, 2 * b_bytes);
+          tma_2d(dst, &map_hi, kc * 64, blk * NH, bar);
+          tma_2d(dst + 256 * 128, &map_lo, kc * 64, blk * NH, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_bf16(128, NH);
+      uint32_t g = 0, it = 0;
+      for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+        umma::fence_after_thread_sync();
+        const uint32_t d = tmem + acc * 256;
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kJStages;
+          mbar_wait_parity(smem_u32(&full[s]), (g / kJStages) & 1);
+          umma::fence_after_thread_sync();
+          const uint32_t sa = smem_u32(base) + s * stage_bytes;
+          const uint32_t sb = sa + 2 * a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
+            const uint64_t dal = umma::make_smem_desc_sw128(sa + a_bytes + k * 32);
+            const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
+            const uint64_t dbl = umma::make_smem_desc_sw128(sb + 256 * 128 + k * 32);
+            umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
+            umma::mma_bf16(d, dah, dbl, idesc, 1);
+            umma::mma_bf16(d, dal, dbh, idesc, 1);
+          }
+          umma::commit(smem_u32(&empty[s]));
+        }
+        umma::commit(smem_u32(&tfull[acc]));
+      }
+    }
+  } else if (warp < 6) {
+    // epilogue: thread = one joint row; tanh' recomputed from pc / pf rows
+    const int quad = warp & 3;
+    uint32_t it = 0;
+    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const long long tile = unit / nblk;
+      const int blk = (int)(unit % nblk);
+      const uint32_t acc = it & 1;
+      const long long m = tile * 128 + quad * 32 + lane;
+      const bool valid = m < p.M;
+      const long long n = valid ? m / p.C : 0;
+      const int c = valid ? (int)(m - n * p.C) : 0;
+      const float gbm = valid ? p.gb[m] : 0.f;
+      const float* pc_row = p.pc + (size_t)c * H + blk * NH;
+      const float* pf_row = p.pf + (size_t)n * H + blk * NH;
+      const float* wb = s_wb + blk * NH;
+      float* out = p.gp + (size_t)m * H + blk * NH;
+      mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
+      umma::fence_after_thread_sync();
+      for (int c0 = 0; c0 < NH; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pc_row + c0 + j));
+            const float4 f = __ldg(reinterpret_cast<const float4*>(pf_row + c0 + j));
+            const float h0 = tanh_fast(a.x + f.x), h1 = tanh_fast(a.y + f.y);
+            const float h2 = tanh_fast(a.z + f.z), h3 = tanh_fast(a.w + f.w);
+            float4 o;
+            o.x = fmaf(gbm, wb[c0 + j], v[j]) * fmaf(-h0, h0, 1.f);
+            o.y = fmaf(gbm, wb[c0 + j + 1], v[j + 1]) * fmaf(-h1, h1, 1.f);
+            o.z = fmaf(gbm, wb[c0 + j + 2], v[j + 2]) * fmaf(-h2, h2, 1.f);
+            o.w = fmaf(gbm, wb[c0 + j + 3], v[j + 3]) * fmaf(-h3, h3, 1.f);
+            stg_stream4(out + c0 + j, o);
+          }
+        }
+      }
+      umma::fence_before_thread_sync();
+      mbar_arrive(smem_u32(&tempty[acc]));
+    }
+  } else {
+    // A producers: grad_lexical rows, hi/lo split, swizzled K-major stores
+    const int pidx = tid - 6 * 32;
+    const int row = pidx >> 1, half = pidx & 1;
+    uint32_t g = 0;
+    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const long long tile = unit / nblk;
+      const long long m = tile * 128 + row;
+      const bool valid = m < p.M;
+      const float* g_row = p.gl + (size_t)(valid ? m : 0) * V + half * 32;
+      for (int kc = 0; kc < nchunks; ++kc, ++g) {
+        const int s = g % kJStages;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) x = __ldg(reinterpret_cast<const float4*>(g_row + kc * 64) + j);
+          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+          umma::split_bf16(x.x, h0, l0); umma::split_bf16(x.y, h1, l1);
+          umma::split_bf16(x.z, h2, l2); umma::split_bf16(x.w, h3, l3);
+          hi[2 * j] = umma::pack_bf16(h0, h1); hi[2 * j + 1] = umma::pack_bf16(h2, h3);
+          lo[2 * j] = umma::pack_bf16(l0, l1); lo[2 * j + 1] = umma::pack_bf16(l2, l3);
+        }
+        mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+        unsigned char* a_hi = base + s * stage_bytes;
+        unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = umma::swizzled_offset(row, half * 4 + j);
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(&full[s]));
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// Gp [N, C, H] -> grad_proj_frame [N, H] (sum over c, written) and grad_proj_ctx
+// [C, H] (sum over n, accumulated with atomics once per CTA).  grid = (H / jw, nblocks);
+// block = 512 threads = (512 / jw) row groups x jw columns; smem = C * jw floats.
+__global__ void __launch_bounds__(512)
+joint_reduce_kernel(const float* __restrict__ gp, long long N, int C, int H, int jw,
+                    long long frames_per_block, float* __restrict__ g_pc,
+                    float* __restrict__ g_pf) {
+  extern __shared__ float racc[];                 // [C][jw] then [RG][jw] scratch
+  const int RG = 512 / jw;
+  float* pf_part = racc + (size_t)C * jw;
+  const int jj = threadIdx.x % jw, rg = threadIdx.x / jw;
+  const int j = blockIdx.x * jw + jj;
+  const long long n_lo = (long long)blockIdx.y * frames_per_block;
+  const long long n_hi = min(N, n_lo + frames_per_block);
+  for (int i = threadIdx.x; i < C * jw; i += 512) racc[i] = 0.f;
+  __syncthreads();
+  for (long long n = n_lo; n < n_hi; ++n) {
+    const float* row = gp + ((size_t)n * C) * H + j;
+    float acc = 0.f;
+    for (int c = rg; c < C; c += RG) {
+      const float x = ldg_stream(row + (size_t)c * H);
+      acc += x;
+      racc[c * jw + jj] += x;                     // (c, jj) is owned by exactly one thread
+    }
+    pf_part[rg * jw + jj] = acc;
+    __syncthreads();
+    if (rg == 0) {
+      float s = 0.f;
+      for (int r = 0; r < RG; ++r) s += pf_part[r * jw + jj];
+      g_pf[(size_t)n * H + j] += s;               // single owner of (n, j)
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < C * jw; i += 512) {
+    const int c = i / jw, q = i % jw;
+    atomicAdd(g_pc + (size_t)c * H + blockIdx.x * jw + q, racc[i]);
+  }
+}
+
+
+// ===========================================================================
+// JointWeightFn backward, part 2 (wgrad) on tcgen05:
+//   grad_W_vocab[v, j] = sum_m G[m, v] * h[m, j]        h = tanh(pc[c] + pf[n])
+// The reduction runs over ALL M = N*C joint rows, so both operands are contiguous
+// along M / N (G rows along v, h rows along j): MN-major SWIZZLE_128B tiles, written
+// by the producer warps (G split hi/lo; h recomputed, split hi/lo), K = 32 rows per
+// stage.  A CTA owns one block of NJ <= 256 hidden columns and a contiguous range of
+// rows; its [V, NJ] fp32 accumulator lives in TMEM for the whole range (V / 128
+// accumulators of 128 lanes x NJ columns) and is added to global memory once.
+// The same producer threads accumulate grad_b_vocab, grad_w_blank and grad_b_blank.
+// ===========================================================================
+constexpr int kWThreads = 288;          // warp 0: MMA issuer; warps 1-8: producers
+constexpr int kWStages = 3;
+constexpr int kWK = 32;                 // joint rows per stage
+
+struct JointWgradParams {
+  const float* pc;       // [C, H]
+  const float* pf;       // [N, H]
+  const float* gl;       // [M, V]
+  const float* gb;       // [M]
+  long long M, rows_per_cta;
+  int C, H, V, NJ;
+  float* gwv;            // [V, H]
+  float* gwb;            // [H]
+  float* gbv;            // [V]
+  float* gbb;            // [1]
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+joint_wgrad_tc_kernel(const JointWgradParams p) {
+  extern __shared__ __align__(1024) unsigned char wsmem_raw[];
+  unsigned char* base = wsmem_raw + ((1024u - (smem_u32(wsmem_raw) & 1023u)) & 1023u);
+  const int V = p.V, H = p.H, NJ = p.NJ;
+  const uint32_t op_bytes = 256 * kWK * 2;            // one [256 x 32] bf16 operand tile (max)
+  const uint32_t stage_bytes = 4 * op_bytes;          // A_hi | A_lo | B_hi | B_lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kWStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWStages;
+  uint64_t* done = bars + 2 * kWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nj = H / NJ;
+  const int jblk = blockIdx.x % nj;
+  const long long m_lo = (long long)(blockIdx.x / nj) * p.rows_per_cta;
+  const long long m_hi = min(p.M, m_lo + p.rows_per_cta);
+  if (m_lo >= m_hi) return;                           // uniform for the CTA
+  const int nchunks = (int)((m_hi - m_lo + kWK - 1) / kWK);
+
+  if (tid == 0) {
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), 256);
+      mbar_init_n(smem_u32(&empty[s]), 1);
+    }
+    mbar_init_n(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int nvb = V / 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_bf16_mn(128, NJ);
+      const uint32_t a_sbo = (uint32_t)(V / 64) * 1024, b_sbo = (uint32_t)(NJ / 64) * 1024;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int s = ch % kWStages;
+        mbar_wait_parity(smem_u32(&full[s]), (ch / kWStages) & 1);
+        umma::fence_after_thread_sync();
+        const uint32_t sa = smem_u32(base) + s * stage_bytes;
+        const uint32_t sb = sa + 2 * op_bytes;
+#pragma unroll
+        for (int ks = 0; ks < kWK / 16; ++ks) {
+          const uint64_t dbh = umma::make_smem_desc_mn_sw128(sb + 2 * ks * b_sbo, 1024, b_sbo);
+          const uint64_t dbl = umma::make_smem_desc_mn_sw128(sb + op_bytes + 2 * ks * b_sbo, 1024, b_sbo);
+          for (int vb = 0; vb < nvb; ++vb) {
+            const uint32_t aoff = 2 * ks * a_sbo + vb * 2 * 1024;
+            const uint64_t dah = umma::make_smem_desc_mn_sw128(sa + aoff, 1024, a_sbo);
+            const uint64_t dal = umma::make_smem_desc_mn_sw128(sa + op_bytes + aoff, 1024, a_sbo);
+            const uint32_t d = tmem + vb * 256;
+            umma::mma_bf16(d, dah, dbh, idesc, (ch | ks) > 0);
+            umma::mma_bf16(d, dah, dbl, idesc, 1);
+            umma::mma_bf16(d, dal, dbh, idesc, 1);
+          }
+        }
+        umma::commit(smem_u32(&empty[s]));
+      }
+      umma::commit(smem_u32(done));
+    }
+  } else {
+    const int pidx = tid - 32;                         // 0 .. 255
+    const int vchunks = V / 8, jchunks = NJ / 8;       // 16-byte chunks per row
+    const int a_iters = kWK * vchunks / 256, b_iters = kWK * jchunks / 256;
+    const int a_vch = pidx % vchunks, a_k0 = pidx / vchunks, a_kstep = 256 / vchunks;
+    const int b_jch = pidx % jchunks, b_k0 = pidx / jchunks, b_kstep = 256 / jchunks;
+    const int j0 = jblk * NJ + b_jch * 8;
+    float bv_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float wb_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float bb_acc = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int s = ch % kWStages;
+      mbar_wait_parity(smem_u32(&empty[s]), ((ch / kWStages) & 1) ^ 1);
+      unsigned char* a_hi = base + s * stage_bytes;
+      unsigned char* a_lo = a_hi + op_bytes;
+      unsigned char* b_hi = a_lo + op_bytes;
+      unsigned char* b_lo = b_hi + op_bytes;
+      const long long mrow0 = m_lo + (long long)ch * kWK;
+      for (int i = 0; i < a_iters; ++i) {              // A = G^T chunk
+        const int k = a_k0 + i * a_kstep;
+        const long long m = mrow0 + k;
+        float x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (m < m_hi) {
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.gl + (size_t)m * V + a_vch * 8));
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.gl + (size_t)m * V + a_vch * 8 + 4));
+          x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
+          x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        }
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { umma::split_bf16(x[e], h[e], l[e]); bv_acc[e] += x[e]; }
+        const uint32_t off = umma::mn_major_chunk_offset(V, a_vch * 8, k);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+      }
+      for (int i = 0; i < b_iters; ++i) {              // B = h^T chunk (recomputed)
+        const int k = b_k0 + i * b_kstep;
+        const long long m = mrow0 + k;
+        float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (m < m_hi) {
+          const long long n = m / p.C;
+          const int c = (int)(m - n * p.C);
+          const float* pcr = p.pc + (size_t)c * H + j0;
+          const float* pfr = p.pf + (size_t)n * H + j0;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pcr));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pcr + 4));
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pfr));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pfr + 4));
+          t[0] = tanh_fast(a0.x + f0.x); t[1] = tanh_fast(a0.y + f0.y);
+          t[2] = tanh_fast(a0.z + f0.z); t[3] = tanh_fast(a0.w + f0.w);
+          t[4] = tanh_fast(a1.x + f1.x); t[5] = tanh_fast(a1.y + f1.y);
+          t[6] = tanh_fast(a1.z + f1.z); t[7] = tanh_fast(a1.w + f1.w);
+          const float g = __ldg(p.gb + m);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) wb_acc[e] = fmaf(g, t[e], wb_acc[e]);
+          if (b_jch == 0) bb_acc += g;
+        }
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) umma::split_bf16(t[e], h[e], l[e]);
+        const uint32_t off = umma::mn_major_chunk_offset(NJ, b_jch * 8, k);
+        *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+        *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&full[s]));
+    }
+    // side sums: bias / blank-projection gradients
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(p.gwb + j0 + e, wb_acc[e]);
+    if (jblk == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(p.gbv + a_vch * 8 + e, bv_acc[e]);
+      if (b_jch == 0) atomicAdd(p.gbb, bb_acc);
+    }
+  }
+  // epilogue: warps 0-3 (TMEM lane quadrant = warp) add the accumulators to global memory
+  __syncthreads();
+  if (warp < 4) {
+    mbar_wait_parity(smem_u32(done), 0);
+    umma::fence_after_thread_sync();
+    for (int vb = 0; vb < nvb; ++vb) {
+      float* out = p.gwv + (size_t)(vb * 128 + warp * 32 + lane) * H + jblk * NJ;
+      for (int c0 = 0; c0 < NJ; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + vb * 256 + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(out + c0 + i, v[i]);
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 }  // namespace lt
 
@@ -430,7 +935,135 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   return LT_OK;
 }
 
+
+bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                              const void* pf) {
+  if (getenv("LT_JOINT_SIMT")) return false;
+  if (V % 64 != 0 || V < 64 || V > 4096) return false;
+  if (H % 32 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
+  if (N * (int64_t)C < 1) return false;
+  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  return al(gl) && al(pc) && al(pf);
+}
+
+int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
+  return (int64_t)H * V * 2 * 2 + 512 + N * (int64_t)C * H * 4;
+}
+
+// dgrad on tcgen05 + streaming reduction into grad_proj_ctx / grad_proj_frame.
+int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
+                          const float* gb, const float* gl, int64_t N, int C, int H, int V,
+                          float* gpc, float* gpf, void* workspace, cudaStream_t stream) {
+  EncodeTiledFnJ encode = joint_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
+  __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* wlo = whi + (size_t)H * V;
+  float* gp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                       (((size_t)H * V * 4 + 255) / 256) * 256);
+  transpose_split_kernel<<<(V * H + 255) / 256, 256, 0, stream>>>(wv, whi, wlo, V, H);
+  LT_LAUNCHED();
+  const int NH = H > 256 ? 256 : H;
+  CUtensorMap map_hi, map_lo;
+  cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)H};
+  cuuint64_t strides[1] = {(cuuint64_t)V * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)NH};
+  cuuint32_t estr[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult r = encode(i == 0 ? &map_hi : &map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        i == 0 ? whi : wlo, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (W_vocab^T) failed with %d", (int)r);
+      return LT_ERR_CUDA;
+    }
+  }
+  JointDgradParams p = {};
+  p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
+  p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NH = NH; p.gp = gp;
+  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + sizeof(float) * H +
+                      16 * 8 + 16 + 1024;
+  int dev = 0, sms = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long units = ((p.M + 127) / 128) * (H / NH);
+  const int grid = (int)(units < sms ? units : sms);
+  LT_CUDA(cudaFuncSetAttribute(joint_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  joint_dgrad_tc_kernel<<<grid, kJThreads, smem, stream>>>(map_hi, map_lo, p);
+  LT_LAUNCHED();
+  // reduction: pick the widest column block whose [C, jw] accumulator fits in shared memory
+  int jw = 128;
+  while (jw > 8 && ((size_t)C * jw * 4 + 512 * 4 > 200 * 1024 || H % jw != 0)) jw >>= 1;
+  if (H % jw != 0 || (size_t)C * jw * 4 + 512 * 4 > 200 * 1024) {
+    set_error("joint backward: %d context states do not fit the reduction kernel", C);
+    return LT_ERR_UNSUPPORTED;
+  }
+  const int jblocks = H / jw;
+  long long nblocks = (2 * sms + jblocks - 1) / jblocks;
+  if (nblocks > N) nblocks = N;
+  if (nblocks < 1) nblocks = 1;
+  const long long fpb = (N + nblocks - 1) / nblocks;
+  nblocks = (N + fpb - 1) / fpb;
+  const size_t rsmem = ((size_t)C * jw + 512) * sizeof(float);
+  LT_CUDA(cudaFuncSetAttribute(joint_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)rsmem));
+  joint_reduce_kernel<<<dim3(jblocks, (unsigned)nblocks), 512, rsmem, stream>>>(
+      gp, (long long)N, C, H, jw, fpb, gpc, gpf);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
+
+bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                              const void* pf) {
+  if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_WGRAD_SIMT")) return false;
+  if (V != 128 && V != 256) return false;
+  if (H % 64 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
+  if (N * (int64_t)C < 1) return false;
+  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  return al(gl) && al(pc) && al(pf);
+}
+
+int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,
+                          int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
+                          float* gbv, cudaStream_t stream) {
+  JointWgradParams p = {};
+  p.pc = pc; p.pf = pf; p.gl = gl; p.gb = gb;
+  p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NJ = H > 256 ? 256 : H;
+  p.gwv = gwv; p.gwb = gwb; p.gbv = gbv; p.gbb = gbb;
+  int dev = 0, sms = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nj = H / p.NJ;
+  long long ranges = sms / nj;
+  if (ranges < 1) ranges = 1;
+  long long rows = (p.M + ranges - 1) / ranges;
+  rows = (rows + kWK - 1) / kWK * kWK;
+  ranges = (p.M + rows - 1) / rows;
+  p.rows_per_cta = rows;
+  const size_t smem = (size_t)kWStages * 4 * 256 * kWK * 2 + 16 * 8 + 16 + 1024;
+  LT_CUDA(cudaFuncSetAttribute(joint_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  joint_wgrad_tc_kernel<<<(unsigned)(ranges * nj), kWThreads, smem, stream>>>(p);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
 }  // namespace lt
+
+extern "C" int ltx_umma_probe_mn(const float* At, const float* Bt, float* D, int N, int K, int swap,
+                                 void* stream) {
+  using namespace lt;
+  LT_CHECK_ARG(N % 64 == 0 && N >= 64 && N <= 256 && K % 32 == 0 && K > 0,
+               "ltx_umma_probe_mn: need N %% 64 == 0, N <= 256, K %% 32 == 0 (N=%d K=%d)", N, K);
+  const size_t smem = 2 * 128 * 64 + 2 * 256 * 64 + 1024;
+  LT_CUDA(cudaFuncSetAttribute(umma_probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  umma_probe_mn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(At, Bt, D, N, K, swap);
+  LT_LAUNCHED();
+  return LT_OK;
+}
 
 // Diagnostic entry point (not part of include/last_lattice.h): D = A * B^T with
 // A [128,K], B [N,K] fp32 device pointers, N % 16 == 0, N <= 256, K % 64 == 0.

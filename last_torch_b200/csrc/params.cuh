@@ -112,6 +112,17 @@ bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const vo
 int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
                             const float* wv, const float* bv, int64_t N, int C, int H, int V,
                             float* blank, float* lexical, void* workspace, cudaStream_t stream);
+bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                              const void* pf);
+int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
+int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
+                          const float* gb, const float* gl, int64_t N, int C, int H, int V,
+                          float* gpc, float* gpf, void* workspace, cudaStream_t stream);
+bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                              const void* pf);
+int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,
+                          int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
+                          float* gbv, cudaStream_t stream);
 int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);
 
 }  // namespace lt

@@ -40,6 +40,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- MN-major operand tile, SWIZZLE_128B ------------------------------------------
+// The contiguous direction is M (or N): 64 bf16 along MN form one 128-byte row, 8
+// consecutive K indices form a 1024-byte atom.  A tile [MN_total x K] is stored as
+// atoms indexed (kb = k / 8, mnb = mn / 64) at  (kb * (MN_total / 64) + mnb) * 1024:
+//   LBO = byte stride between consecutive 64-wide MN blocks  (1024)
+//   SBO = byte stride between consecutive 8-deep K blocks    (MN_total / 64 * 1024)
+// and inside an atom element (i = mn % 64, r = k % 8) sits at
+//   r * 128 + (((i / 8) ^ r) << 4) + (i % 8) * 2.
+__device__ __forceinline__ uint32_t mn_major_chunk_offset(int mn_total, int mn, int k) {
+  // byte offset of the 16-byte chunk that holds elements mn .. mn+7 (mn % 8 == 0) at depth k
+  const int kb = k >> 3, r = k & 7, mnb = mn >> 6, ch = (mn & 63) >> 3;
+  return (uint32_t)(kb * (mn_total >> 6) + mnb) * 1024u + (uint32_t)r * 128u +
+         (uint32_t)((ch ^ r) << 4);
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, D fp32, A/B bf16, both MN-major (bits 15 and 16 set)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::
                    "r"(smem_result_addr), "r"(ncols) : "memory");

@@ -74,3 +74,67 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
   assert err_simt < 2e-6, err_simt
   assert err_tc < 1e-5, (err_tc, err_simt)
   assert err_b < 1e-5, err_b
+
+
+@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 40), (65, 64, 128, 9), (130, 128, 256, 17)])
+def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
+  """Gradients of the whole-utterance JointWeightFn kernel path (tcgen05 dgrad +
+  streaming reduction, weight gradients) against torch autograd through the
+  per-frame reference formula, and against the CUDA-core kernels."""
+  import os
+  import last_torch_b200 as lt
+  torch.manual_seed(c * 7 + v)
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=48,
+                                   feature_size=40)
+  params = list(fn.parameters())
+  cache = torch.randn([c, 48], device='cuda', requires_grad=True)
+  frames = torch.randn([n, 1, 40], device='cuda', requires_grad=True)
+  wb = torch.randn([n, 1, c], device='cuda')
+  wl = torch.randn([n, 1, c, v], device='cuda')
+
+  def grads(path):
+    if path == 'simt':
+      os.environ['LT_JOINT_SIMT'] = '1'
+    try:
+      if path == 'ref':
+        b, l = fn(cache, frames.reshape(n, 40))
+        b, l = b.reshape(wb.shape), l.reshape(wl.shape)
+      else:
+        b, l = fn.all_frames(cache, frames)
+      return torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
+    finally:
+      os.environ.pop('LT_JOINT_SIMT', None)
+
+  ref, tc, simt = grads('ref'), grads('tc'), grads('simt')
+  for r, a, s in zip(ref, tc, simt):
+    scale = float(r.abs().max()) + 1e-12
+    assert float((s - r).abs().max()) / scale < 3e-5
+    assert float((a - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((a - r).abs().max()) / scale)
+
+
+def _probe_mn(at, bt, swap):
+  from last_torch_b200 import _native as N
+  N.lib()
+  handle = ctypes.CDLL(N.LIB_PATH)
+  fn = handle.ltx_umma_probe_mn
+  fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+  fn.restype = ctypes.c_int
+  k, n = bt.shape
+  d = torch.empty([128, n], device='cuda')
+  rc = fn(at.data_ptr(), bt.data_ptr(), d.data_ptr(), n, k, swap,
+          torch.cuda.current_stream().cuda_stream)
+  assert rc == 0
+  torch.cuda.synchronize()
+  return d
+
+
+@pytest.mark.parametrize('n,k', [(256, 32), (256, 128), (64, 64), (128, 96)])
+def test_umma_probe_mn_major(n, k):
+  """MN-major operands (both contiguous along M / N): D = At^T Bt."""
+  g = torch.Generator(device='cuda').manual_seed(n + k)
+  at = torch.randn([k, 128], device='cuda', generator=g)
+  bt = torch.randn([k, n], device='cuda', generator=g)
+  ref = at.double().T @ bt.double()
+  scale = float(ref.abs().max())
+  err = float((_probe_mn(at, bt, 0).double() - ref).abs().max()) / scale
+  assert err < 2e-5, err
