@@ -632,6 +632,66 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
+// Wide variant for H % 128 == 0: a warp owns a row (512 contiguous bytes, float4 per
+// lane), 16 warps sweep the C rows of a frame with 4 independent loads in flight per
+// thread; the [C, 128] column block of grad_proj_ctx is accumulated in shared memory.
+__global__ void __launch_bounds__(512)
+joint_reduce128_kernel(const float* __restrict__ gp, long long N, int C, int H,
+                       long long frames_per_block, float* __restrict__ g_pc,
+                       float* __restrict__ g_pf) {
+  extern __shared__ __align__(16) float4 r4[];    // [C][32] accumulators, then [16][32] partials
+  float4* part = r4 + (size_t)C * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int jcol = blockIdx.x * 128 + lane * 4;
+  const long long n_lo = (long long)blockIdx.y * frames_per_block;
+  const long long n_hi = min(N, n_lo + frames_per_block);
+  for (int i = threadIdx.x; i < C * 32; i += 512) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (long long n = n_lo; n < n_hi; ++n) {
+    const float* base = gp + ((size_t)n * C) * H + jcol;
+    float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = warp; c < C; c += 64) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + 16 * u;
+        x[u] = cc < C ? ldg_stream4(base + (size_t)cc * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + 16 * u;
+        if (cc < C) {
+          pf.x += x[u].x; pf.y += x[u].y; pf.z += x[u].z; pf.w += x[u].w;
+          float4 a = r4[cc * 32 + lane];          // (cc, lane) has exactly one owner thread
+          a.x += x[u].x; a.y += x[u].y; a.z += x[u].z; a.w += x[u].w;
+          r4[cc * 32 + lane] = a;
+        }
+      }
+    }
+    part[warp * 32 + lane] = pf;
+    __syncthreads();
+    if (warp == 0) {
+      float4 s = part[lane];
+#pragma unroll
+      for (int w = 1; w < 16; ++w) {
+        const float4 o = part[w * 32 + lane];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      float4* out = reinterpret_cast<float4*>(g_pf + (size_t)n * H + jcol);
+      float4 cur = *out;                          // single owner of (n, jcol..jcol+3)
+      cur.x += s.x; cur.y += s.y; cur.z += s.z; cur.w += s.w;
+      *out = cur;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < C * 32; i += 512) {
+    const int c = i >> 5, l = i & 31;
+    const float4 a = r4[i];
+    float* dst = g_pc + (size_t)c * H + blockIdx.x * 128 + l * 4;
+    atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
+  }
+}
+
 // Gp [N, C, H] -> grad_proj_frame [N, H] (sum over c, written) and grad_proj_ctx
 // [C, H] (sum over n, accumulated with atomics once per CTA).  grid = (H / jw, nblocks);
 // block = 512 threads = (512 / jw) row groups x jw columns; smem = C * jw floats.
@@ -993,6 +1053,22 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   joint_dgrad_tc_kernel<<<grid, kJThreads, smem, stream>>>(map_hi, map_lo, p);
   LT_LAUNCHED();
   // reduction: pick the widest column block whose [C, jw] accumulator fits in shared memory
+  if (H % 128 == 0 && ((size_t)C * 32 + 16 * 32) * sizeof(float4) <= 200 * 1024 &&
+      reinterpret_cast<uintptr_t>(gpf) % 16 == 0) {
+    const int jblocks = H / 128;
+    long long nblocks = (2 * sms + jblocks - 1) / jblocks;
+    if (nblocks > N) nblocks = N;
+    if (nblocks < 1) nblocks = 1;
+    const long long fpb = (N + nblocks - 1) / nblocks;
+    nblocks = (N + fpb - 1) / fpb;
+    const size_t rsmem = ((size_t)C * 32 + 16 * 32) * sizeof(float4);
+    LT_CUDA(cudaFuncSetAttribute(joint_reduce128_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    joint_reduce128_kernel<<<dim3(jblocks, (unsigned)nblocks), 512, rsmem, stream>>>(
+        gp, (long long)N, C, H, fpb, gpc, gpf);
+    LT_LAUNCHED();
+    return LT_OK;
+  }
   int jw = 128;
   while (jw > 8 && ((size_t)C * jw * 4 + 512 * 4 > 200 * 1024 || H % jw != 0)) jw >>= 1;
   if (H % jw != 0 || (size_t)C * jw * 4 + 512 * 4 > 200 * 1024) {
