@@ -212,8 +212,15 @@ def cpu_bounded_run(args, with_joint, seconds, reps=1):
   about `seconds`, and times `reps` passes.  Returns (units/s, description)."""
   from oracle import c_oracle
   import __graft_entry__ as ge
-  if not c_oracle.available():
-    ge.build_oracle()
+  ge.build_oracle()
+  # use every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
+  cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+  c_oracle.set_threads(cores)
+  try:
+    import threadpoolctl
+    threadpoolctl.threadpool_limits(limits=cores)
+  except Exception:
+    pass
   threads = c_oracle.num_threads()
   b = max(1, min(args.batch, threads))
   t = 8
@@ -282,6 +289,7 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')    # keep NCCL's banner off stdout
     dist.init_process_group('nccl', device_id=dev)
   if rank == 0:
     ge.build()

@@ -373,55 +373,70 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
     }
   } else {
     // -------------------------------------------------------------- A producers
-    const int pidx = tid - 6 * 32;                      // 0 .. 255
-    const int row = pidx >> 1, half = pidx & 1;
+    // 8 lanes cover one row's 64-wide K chunk (256 contiguous bytes of pc / pf, one
+    // 16-byte bf16 chunk per lane), 4 rows per warp, 4 passes over the 128 rows: global
+    // loads are fully coalesced and the 8 lanes of a row write 8 distinct swizzled chunks.
+    const int pw = warp - 6;                            // 0 .. 7
+    const int ch = lane & 7, rsub = lane >> 3;
     uint32_t g = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m = tile * 128 + row;
-      const bool valid = m < p.M;
-      const long long n = valid ? m / p.C : 0;
-      const int c = valid ? (int)(m - n * p.C) : 0;
-      const float* pc_row = p.pc + (size_t)c * H + half * 32;
-      const float* pf_row = p.pf + (size_t)n * H + half * 32;
-      float bacc = 0.f;
+      const float* pc_row[4];
+      const float* pf_row[4];
+      bool valid[4];
+      float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long m = tile * 128 + q * 32 + pw * 4 + rsub;
+        valid[q] = m < p.M;
+        const long long n = valid[q] ? m / p.C : 0;
+        const int c = valid[q] ? (int)(m - n * p.C) : 0;
+        pc_row[q] = p.pc + (size_t)c * H + ch * 8;
+        pf_row[q] = p.pf + (size_t)n * H + ch * 8;
+      }
       for (int kc = 0; kc < nchunks; ++kc, ++g) {
         const int s = g % kJStages;
-        float x[32];
+        uint4 hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(pc_row + kc * 64) + j);
-          const float4 f = __ldg(reinterpret_cast<const float4*>(pf_row + kc * 64) + j);
-          x[4 * j] = a.x + f.x; x[4 * j + 1] = a.y + f.y;
-          x[4 * j + 2] = a.z + f.z; x[4 * j + 3] = a.w + f.w;
-        }
-        const float* wb = s_wb + kc * 64 + half * 32;
-        uint32_t hi[16], lo[16];
+        for (int q = 0; q < 4; ++q) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64 + 4));
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64 + 4));
+          float t[8] = {a0.x + f0.x, a0.y + f0.y, a0.z + f0.z, a0.w + f0.w,
+                        a1.x + f1.x, a1.y + f1.y, a1.z + f1.z, a1.w + f1.w};
+          const float* wb = s_wb + kc * 64 + ch * 8;
+          __nv_bfloat16 h[8], l[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float t0 = valid ? tanh_fast(x[2 * j]) : 0.f;
-          const float t1 = valid ? tanh_fast(x[2 * j + 1]) : 0.f;
-          bacc = fmaf(t0, wb[2 * j], bacc);
-          bacc = fmaf(t1, wb[2 * j + 1], bacc);
-          __nv_bfloat16 h0, l0, h1, l1;
-          umma::split_bf16(t0, h0, l0);
-          umma::split_bf16(t1, h1, l1);
-          hi[j] = umma::pack_bf16(h0, h1);
-          lo[j] = umma::pack_bf16(l0, l1);
+          for (int e = 0; e < 8; ++e) {
+            t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
+            bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+            umma::split_bf16(t[e], h[e], l[e]);
+          }
+          hi[q] = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]),
+                             umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+          lo[q] = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]),
+                             umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
         }
         mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
         unsigned char* a_hi = base + s * stage_bytes;
         unsigned char* a_lo = a_hi + a_bytes;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = umma::swizzled_offset(row, half * 4 + j);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(smem_u32(&full[s]));
       }
-      bacc += __shfl_xor_sync(0xffffffffu, bacc, 1);
-      if (valid && half == 0) p.blank[m] = bacc + p.b_blank;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float b = bacc[q];
+        b += __shfl_xor_sync(0xffffffffu, b, 1);
+        b += __shfl_xor_sync(0xffffffffu, b, 2);
+        b += __shfl_xor_sync(0xffffffffu, b, 4);
+        if (valid[q] && ch == 0) p.blank[tile * 128 + q * 32 + pw * 4 + rsub] = b + p.b_blank;
+      }
     }
   }
   umma::fence_before_thread_sync();
@@ -471,7 +486,8 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const uint32_t b_bytes = (uint32_t)NH * 128;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
   float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + H);
+  float* s_tr = s_wb + H;                                                  // 4 x [32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
   uint64_t* full = bars;
   uint64_t* empty = bars + kJStages;
   uint64_t* tfull = bars + 2 * kJStages;
@@ -550,39 +566,63 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       }
     }
   } else if (warp < 6) {
-    // epilogue: thread = one joint row; tanh' recomputed from pc / pf rows
+    // epilogue.  The accumulator arrives with thread = joint row (TMEM lane), but the
+    // tanh' factor needs pc / pf rows: those are loaded COALESCED (8 lanes per row, 4 rows
+    // per instruction), 1 - tanh^2 is evaluated in that layout and transposed through a
+    // padded per-warp shared tile (conflict-free both ways) into the row-per-thread layout.
     const int quad = warp & 3;
+    float* tr = s_tr + quad * (32 * 33);
+    const int lc = (lane & 7) * 4, lr = lane >> 3;      // columns lc..lc+3 of rows lr + 4i
     uint32_t it = 0;
     for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const long long tile = unit / nblk;
       const int blk = (int)(unit % nblk);
       const uint32_t acc = it & 1;
-      const long long m = tile * 128 + quad * 32 + lane;
+      const long long m0 = tile * 128 + quad * 32;
+      const long long m = m0 + lane;
       const bool valid = m < p.M;
-      const long long n = valid ? m / p.C : 0;
-      const int c = valid ? (int)(m - n * p.C) : 0;
       const float gbm = valid ? p.gb[m] : 0.f;
-      const float* pc_row = p.pc + (size_t)c * H + blk * NH;
-      const float* pf_row = p.pf + (size_t)n * H + blk * NH;
+      const long long n0 = m0 < p.M ? m0 / p.C : 0;
+      const int c0r = m0 < p.M ? (int)(m0 - n0 * p.C) : 0;
       const float* wb = s_wb + blk * NH;
       float* out = p.gp + (size_t)m * H + blk * NH;
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
       for (int c0 = 0; c0 < NH; c0 += 32) {
+        float4 a[8], f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = lr + 4 * i;
+          long long n = n0;
+          int c = c0r + rr;
+          while (c >= p.C) { c -= p.C; ++n; }
+          a[i] = f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + rr < p.M) {
+            a[i] = __ldg(reinterpret_cast<const float4*>(p.pc + (size_t)c * H + blk * NH + c0 + lc));
+            f[i] = __ldg(reinterpret_cast<const float4*>(p.pf + (size_t)n * H + blk * NH + c0 + lc));
+          }
+        }
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
+        __syncwarp();                                   // previous group's reads of `tr` are done
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h0 = tanh_fast(a[i].x + f[i].x), h1 = tanh_fast(a[i].y + f[i].y);
+          const float h2 = tanh_fast(a[i].z + f[i].z), h3 = tanh_fast(a[i].w + f[i].w);
+          float* dst = tr + (lr + 4 * i) * 33 + lc;
+          dst[0] = fmaf(-h0, h0, 1.f); dst[1] = fmaf(-h1, h1, 1.f);
+          dst[2] = fmaf(-h2, h2, 1.f); dst[3] = fmaf(-h3, h3, 1.f);
+        }
+        __syncwarp();
         if (valid) {
+          const float* fr = tr + lane * 33;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(pc_row + c0 + j));
-            const float4 f = __ldg(reinterpret_cast<const float4*>(pf_row + c0 + j));
-            const float h0 = tanh_fast(a.x + f.x), h1 = tanh_fast(a.y + f.y);
-            const float h2 = tanh_fast(a.z + f.z), h3 = tanh_fast(a.w + f.w);
             float4 o;
-            o.x = fmaf(gbm, wb[c0 + j], v[j]) * fmaf(-h0, h0, 1.f);
-            o.y = fmaf(gbm, wb[c0 + j + 1], v[j + 1]) * fmaf(-h1, h1, 1.f);
-            o.z = fmaf(gbm, wb[c0 + j + 2], v[j + 2]) * fmaf(-h2, h2, 1.f);
-            o.w = fmaf(gbm, wb[c0 + j + 3], v[j + 3]) * fmaf(-h3, h3, 1.f);
+            o.x = fmaf(gbm, wb[c0 + j], v[j]) * fr[j];
+            o.y = fmaf(gbm, wb[c0 + j + 1], v[j + 1]) * fr[j + 1];
+            o.z = fmaf(gbm, wb[c0 + j + 2], v[j + 2]) * fr[j + 2];
+            o.w = fmaf(gbm, wb[c0 + j + 3], v[j + 3]) * fr[j + 3];
             stg_stream4(out + c0 + j, o);
           }
         }
@@ -591,36 +631,48 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       mbar_arrive(smem_u32(&tempty[acc]));
     }
   } else {
-    // A producers: grad_lexical rows, hi/lo split, swizzled K-major stores
-    const int pidx = tid - 6 * 32;
-    const int row = pidx >> 1, half = pidx & 1;
+    // A producers: grad_lexical rows, hi/lo split, swizzled K-major stores.  8 lanes per
+    // row (256 contiguous bytes per K chunk), 4 rows per warp, 4 passes: coalesced loads.
+    const int pw = warp - 6;
+    const int ch = lane & 7, rsub = lane >> 3;
     uint32_t g = 0;
     for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const long long tile = unit / nblk;
-      const long long m = tile * 128 + row;
-      const bool valid = m < p.M;
-      const float* g_row = p.gl + (size_t)(valid ? m : 0) * V + half * 32;
+      const float* g_row[4];
+      bool valid[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long m = tile * 128 + q * 32 + pw * 4 + rsub;
+        valid[q] = m < p.M;
+        g_row[q] = p.gl + (size_t)(valid[q] ? m : 0) * V + ch * 8;
+      }
       for (int kc = 0; kc < nchunks; ++kc, ++g) {
         const int s = g % kJStages;
-        uint32_t hi[16], lo[16];
+        uint4 hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) x = __ldg(reinterpret_cast<const float4*>(g_row + kc * 64) + j);
-          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-          umma::split_bf16(x.x, h0, l0); umma::split_bf16(x.y, h1, l1);
-          umma::split_bf16(x.z, h2, l2); umma::split_bf16(x.w, h3, l3);
-          hi[2 * j] = umma::pack_bf16(h0, h1); hi[2 * j + 1] = umma::pack_bf16(h2, h3);
-          lo[2 * j] = umma::pack_bf16(l0, l1); lo[2 * j + 1] = umma::pack_bf16(l2, l3);
+        for (int q = 0; q < 4; ++q) {
+          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+          if (valid[q]) {
+            x0 = ldg_stream4(g_row[q] + kc * 64);
+            x1 = ldg_stream4(g_row[q] + kc * 64 + 4);
+          }
+          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          __nv_bfloat16 h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) umma::split_bf16(x[e], h[e], l[e]);
+          hi[q] = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]),
+                             umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
+          lo[q] = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]),
+                             umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
         }
         mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
         unsigned char* a_hi = base + s * stage_bytes;
         unsigned char* a_lo = a_hi + a_bytes;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = umma::swizzled_offset(row, half * 4 + j);
-          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(smem_u32(&full[s]));
@@ -743,7 +795,8 @@ joint_reduce_kernel(const float* __restrict__ gp, long long N, int C, int H, int
 // accumulators of 128 lanes x NJ columns) and is added to global memory once.
 // The same producer threads accumulate grad_b_vocab, grad_w_blank and grad_b_blank.
 // ===========================================================================
-constexpr int kWThreads = 288;          // warp 0: MMA issuer; warps 1-8: producers
+constexpr int kWThreads = 544;          // warp 0: MMA issuer; warps 1-16: producers
+constexpr int kWProducers = 512;
 constexpr int kWStages = 3;
 constexpr int kWK = 32;                 // joint rows per stage
 
@@ -760,6 +813,8 @@ struct JointWgradParams {
   float* gbb;            // [1]
 };
 
+// AI / BI: 16-byte operand chunks per producer thread and stage (V / 128, NJ / 128)
+template <int AI, int BI>
 __global__ void __launch_bounds__(kWThreads, 1)
 joint_wgrad_tc_kernel(const JointWgradParams p) {
   extern __shared__ __align__(1024) unsigned char wsmem_raw[];
@@ -783,7 +838,7 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) {
-      mbar_init_n(smem_u32(&full[s]), 256);
+      mbar_init_n(smem_u32(&full[s]), kWProducers);
       mbar_init_n(smem_u32(&empty[s]), 1);
     }
     mbar_init_n(smem_u32(done), 1);
@@ -825,33 +880,57 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
       umma::commit(smem_u32(done));
     }
   } else {
-    const int pidx = tid - 32;                         // 0 .. 255
+    const int pidx = tid - 32;                         // 0 .. 511
     const int vchunks = V / 8, jchunks = NJ / 8;       // 16-byte chunks per row
-    const int a_iters = kWK * vchunks / 256, b_iters = kWK * jchunks / 256;
-    const int a_vch = pidx % vchunks, a_k0 = pidx / vchunks, a_kstep = 256 / vchunks;
-    const int b_jch = pidx % jchunks, b_k0 = pidx / jchunks, b_kstep = 256 / jchunks;
+    const int a_vch = pidx % vchunks, a_k0 = pidx / vchunks, a_kstep = kWProducers / vchunks;
+    const int b_jch = pidx % jchunks, b_k0 = pidx / jchunks, b_kstep = kWProducers / jchunks;
     const int j0 = jblk * NJ + b_jch * 8;
     float bv_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float wb_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float bb_acc = 0.f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ch = 0; ch < nchunks; ++ch) {
       const int s = ch % kWStages;
+      const long long mrow0 = m_lo + (long long)ch * kWK;
+      // ---- issue every global load of this stage first (memory-level parallelism)
+      float4 ax[AI][2], bp[BI][2], bf[BI][2];
+      float gbm[BI];
+#pragma unroll
+      for (int i = 0; i < AI; ++i) {
+        const long long m = mrow0 + a_k0 + i * a_kstep;
+        ax[i][0] = ax[i][1] = z4;
+        if (m < m_hi) {
+          ax[i][0] = ldg_stream4(p.gl + (size_t)m * V + a_vch * 8);
+          ax[i][1] = ldg_stream4(p.gl + (size_t)m * V + a_vch * 8 + 4);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BI; ++i) {
+        const long long m = mrow0 + b_k0 + i * b_kstep;
+        bp[i][0] = bp[i][1] = bf[i][0] = bf[i][1] = z4;
+        gbm[i] = 0.f;
+        if (m < m_hi) {
+          const long long n = m / p.C;
+          const int c = (int)(m - n * p.C);
+          const float* pcr = p.pc + (size_t)c * H + j0;
+          const float* pfr = p.pf + (size_t)n * H + j0;
+          bp[i][0] = __ldg(reinterpret_cast<const float4*>(pcr));
+          bp[i][1] = __ldg(reinterpret_cast<const float4*>(pcr + 4));
+          bf[i][0] = __ldg(reinterpret_cast<const float4*>(pfr));
+          bf[i][1] = __ldg(reinterpret_cast<const float4*>(pfr + 4));
+          gbm[i] = __ldg(p.gb + m);
+        }
+      }
       mbar_wait_parity(smem_u32(&empty[s]), ((ch / kWStages) & 1) ^ 1);
       unsigned char* a_hi = base + s * stage_bytes;
       unsigned char* a_lo = a_hi + op_bytes;
       unsigned char* b_hi = a_lo + op_bytes;
       unsigned char* b_lo = b_hi + op_bytes;
-      const long long mrow0 = m_lo + (long long)ch * kWK;
-      for (int i = 0; i < a_iters; ++i) {              // A = G^T chunk
+#pragma unroll
+      for (int i = 0; i < AI; ++i) {                   // A = G^T chunk
         const int k = a_k0 + i * a_kstep;
-        const long long m = mrow0 + k;
-        float x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (m < m_hi) {
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.gl + (size_t)m * V + a_vch * 8));
-          const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.gl + (size_t)m * V + a_vch * 8 + 4));
-          x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
-          x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
-        }
+        const float x[8] = {ax[i][0].x, ax[i][0].y, ax[i][0].z, ax[i][0].w,
+                            ax[i][1].x, ax[i][1].y, ax[i][1].z, ax[i][1].w};
         __nv_bfloat16 h[8], l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { umma::split_bf16(x[e], h[e], l[e]); bv_acc[e] += x[e]; }
@@ -859,31 +938,21 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
       }
-      for (int i = 0; i < b_iters; ++i) {              // B = h^T chunk (recomputed)
-        const int k = b_k0 + i * b_kstep;
-        const long long m = mrow0 + k;
-        float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (m < m_hi) {
-          const long long n = m / p.C;
-          const int c = (int)(m - n * p.C);
-          const float* pcr = p.pc + (size_t)c * H + j0;
-          const float* pfr = p.pf + (size_t)n * H + j0;
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pcr));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pcr + 4));
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pfr));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pfr + 4));
-          t[0] = tanh_fast(a0.x + f0.x); t[1] = tanh_fast(a0.y + f0.y);
-          t[2] = tanh_fast(a0.z + f0.z); t[3] = tanh_fast(a0.w + f0.w);
-          t[4] = tanh_fast(a1.x + f1.x); t[5] = tanh_fast(a1.y + f1.y);
-          t[6] = tanh_fast(a1.z + f1.z); t[7] = tanh_fast(a1.w + f1.w);
-          const float g = __ldg(p.gb + m);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) wb_acc[e] = fmaf(g, t[e], wb_acc[e]);
-          if (b_jch == 0) bb_acc += g;
-        }
+      for (int i = 0; i < BI; ++i) {                   // B = h^T chunk (recomputed)
+        const int k = b_k0 + i * b_kstep;
+        const bool live = mrow0 + k < m_hi;
+        float t[8] = {bp[i][0].x + bf[i][0].x, bp[i][0].y + bf[i][0].y, bp[i][0].z + bf[i][0].z,
+                      bp[i][0].w + bf[i][0].w, bp[i][1].x + bf[i][1].x, bp[i][1].y + bf[i][1].y,
+                      bp[i][1].z + bf[i][1].z, bp[i][1].w + bf[i][1].w};
         __nv_bfloat16 h[8], l[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) umma::split_bf16(t[e], h[e], l[e]);
+        for (int e = 0; e < 8; ++e) {
+          t[e] = live ? tanh_fast(t[e]) : 0.f;
+          wb_acc[e] = fmaf(gbm[i], t[e], wb_acc[e]);
+          umma::split_bf16(t[e], h[e], l[e]);
+        }
+        if (b_jch == 0) bb_acc += gbm[i];
         const uint32_t off = umma::mn_major_chunk_offset(NJ, b_jch * 8, k);
         *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
         *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
@@ -1041,8 +1110,8 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   JointDgradParams p = {};
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NH = NH; p.gp = gp;
-  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + sizeof(float) * H +
-                      16 * 8 + 16 + 1024;
+  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
+                      sizeof(float) * (H + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1095,7 +1164,7 @@ bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
                               const void* pf) {
   if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_WGRAD_SIMT")) return false;
   if (V != 128 && V != 256) return false;
-  if (H % 64 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
+  if (H % 128 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
   if (N * (int64_t)C < 1) return false;
   auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
   return al(gl) && al(pc) && al(pf);
@@ -1119,9 +1188,19 @@ int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, con
   ranges = (p.M + rows - 1) / rows;
   p.rows_per_cta = rows;
   const size_t smem = (size_t)kWStages * 4 * 256 * kWK * 2 + 16 * 8 + 16 + 1024;
-  LT_CUDA(cudaFuncSetAttribute(joint_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  joint_wgrad_tc_kernel<<<(unsigned)(ranges * nj), kWThreads, smem, stream>>>(p);
+  const unsigned grid = (unsigned)(ranges * nj);
+#define LT_WGRAD(AI, BI)                                                                       \
+  do {                                                                                         \
+    LT_CUDA(cudaFuncSetAttribute(joint_wgrad_tc_kernel<AI, BI>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    joint_wgrad_tc_kernel<AI, BI><<<grid, kWThreads, smem, stream>>>(p);                       \
+  } while (0)
+  const int ai = V / 128, bi = p.NJ / 128;
+  if (ai == 2 && bi == 2) LT_WGRAD(2, 2);
+  else if (ai == 2 && bi == 1) LT_WGRAD(2, 1);
+  else if (ai == 1 && bi == 2) LT_WGRAD(1, 2);
+  else LT_WGRAD(1, 1);
+#undef LT_WGRAD
   LT_LAUNCHED();
   return LT_OK;
 }

@@ -32,6 +32,10 @@ def num_threads():
   return int(lib().oracle_num_threads())
 
 
+def set_threads(n):
+  lib().oracle_set_threads(ctypes.c_int(int(n)))
+
+
 def _p(a):
   return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 

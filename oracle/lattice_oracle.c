@@ -355,3 +355,12 @@ int oracle_num_threads(void) {
 }
 
 int oracle_real_size(void) { return (int)sizeof(real); }
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline asks for all cores explicitly. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
