@@ -405,17 +405,12 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
           float t[8] = {a0.x + f0.x, a0.y + f0.y, a0.z + f0.z, a0.w + f0.w,
                         a1.x + f1.x, a1.y + f1.y, a1.z + f1.z, a1.w + f1.w};
           const float* wb = s_wb + kc * 64 + ch * 8;
-          __nv_bfloat16 h[8], l[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
             bacc[q] = fmaf(t[e], wb[e], bacc[q]);
-            umma::split_bf16(t[e], h[e], l[e]);
           }
-          hi[q] = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]),
-                             umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
-          lo[q] = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]),
-                             umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+          umma::split_pack8(t, hi[q], lo[q]);
         }
         mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
         unsigned char* a_hi = base + s * stage_bytes;
@@ -486,8 +481,7 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const uint32_t b_bytes = (uint32_t)NH * 128;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
   float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
-  float* s_tr = s_wb + H;                                                  // 4 x [32][33]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + H);
   uint64_t* full = bars;
   uint64_t* empty = bars + kJStages;
   uint64_t* tfull = bars + 2 * kJStages;
@@ -566,65 +560,33 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       }
     }
   } else if (warp < 6) {
-    // epilogue.  The accumulator arrives with thread = joint row (TMEM lane), but the
-    // tanh' factor needs pc / pf rows: those are loaded COALESCED (8 lanes per row, 4 rows
-    // per instruction), 1 - tanh^2 is evaluated in that layout and transposed through a
-    // padded per-warp shared tile (conflict-free both ways) into the row-per-thread layout.
+    // epilogue: thread = joint row (TMEM lane).  Only the rank-1 blank term is added here;
+    // the tanh' factor is applied by the reduction kernel, which streams this buffer anyway
+    // and has the warps to hide the pc / pf load latency (with it in this epilogue, one
+    // warp per TMEM quadrant serialised load -> tanh -> store and stalled the MMA pipe).
     const int quad = warp & 3;
-    float* tr = s_tr + quad * (32 * 33);
-    const int lc = (lane & 7) * 4, lr = lane >> 3;      // columns lc..lc+3 of rows lr + 4i
     uint32_t it = 0;
     for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const long long tile = unit / nblk;
       const int blk = (int)(unit % nblk);
       const uint32_t acc = it & 1;
-      const long long m0 = tile * 128 + quad * 32;
-      const long long m = m0 + lane;
+      const long long m = tile * 128 + quad * 32 + lane;
       const bool valid = m < p.M;
       const float gbm = valid ? p.gb[m] : 0.f;
-      const long long n0 = m0 < p.M ? m0 / p.C : 0;
-      const int c0r = m0 < p.M ? (int)(m0 - n0 * p.C) : 0;
       const float* wb = s_wb + blk * NH;
       float* out = p.gp + (size_t)m * H + blk * NH;
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
       for (int c0 = 0; c0 < NH; c0 += 32) {
-        float4 a[8], f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = lr + 4 * i;
-          long long n = n0;
-          int c = c0r + rr;
-          while (c >= p.C) { c -= p.C; ++n; }
-          a[i] = f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m0 + rr < p.M) {
-            a[i] = __ldg(reinterpret_cast<const float4*>(p.pc + (size_t)c * H + blk * NH + c0 + lc));
-            f[i] = __ldg(reinterpret_cast<const float4*>(p.pf + (size_t)n * H + blk * NH + c0 + lc));
-          }
-        }
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
-        __syncwarp();                                   // previous group's reads of `tr` are done
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h0 = tanh_fast(a[i].x + f[i].x), h1 = tanh_fast(a[i].y + f[i].y);
-          const float h2 = tanh_fast(a[i].z + f[i].z), h3 = tanh_fast(a[i].w + f[i].w);
-          float* dst = tr + (lr + 4 * i) * 33 + lc;
-          dst[0] = fmaf(-h0, h0, 1.f); dst[1] = fmaf(-h1, h1, 1.f);
-          dst[2] = fmaf(-h2, h2, 1.f); dst[3] = fmaf(-h3, h3, 1.f);
-        }
-        __syncwarp();
         if (valid) {
-          const float* fr = tr + lane * 33;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = fmaf(gbm, wb[c0 + j], v[j]) * fr[j];
-            o.y = fmaf(gbm, wb[c0 + j + 1], v[j + 1]) * fr[j + 1];
-            o.z = fmaf(gbm, wb[c0 + j + 2], v[j + 2]) * fr[j + 2];
-            o.w = fmaf(gbm, wb[c0 + j + 3], v[j + 3]) * fr[j + 3];
-            stg_stream4(out + c0 + j, o);
-          }
+          for (int j = 0; j < 32; j += 4)
+            stg_stream4(out + c0 + j,
+                        make_float4(fmaf(gbm, wb[c0 + j], v[j]), fmaf(gbm, wb[c0 + j + 1], v[j + 1]),
+                                    fmaf(gbm, wb[c0 + j + 2], v[j + 2]),
+                                    fmaf(gbm, wb[c0 + j + 3], v[j + 3])));
         }
       }
       umma::fence_before_thread_sync();
@@ -633,50 +595,55 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   } else {
     // A producers: grad_lexical rows, hi/lo split, swizzled K-major stores.  8 lanes per
     // row (256 contiguous bytes per K chunk), 4 rows per warp, 4 passes: coalesced loads.
+    // The loads of chunk i+1 are issued BEFORE chunk i is converted and stored, so the HBM
+    // latency of the gradient stream is hidden behind the conversion work.
     const int pw = warp - 6;
     const int ch = lane & 7, rsub = lane >> 3;
-    uint32_t g = 0;
-    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    auto issue = [&](long long unit, int kc, float4 (&x)[4][2]) {
       const long long tile = unit / nblk;
-      const float* g_row[4];
-      bool valid[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const long long m = tile * 128 + q * 32 + pw * 4 + rsub;
-        valid[q] = m < p.M;
-        g_row[q] = p.gl + (size_t)(valid[q] ? m : 0) * V + ch * 8;
-      }
-      for (int kc = 0; kc < nchunks; ++kc, ++g) {
-        const int s = g % kJStages;
-        uint4 hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-          if (valid[q]) {
-            x0 = ldg_stream4(g_row[q] + kc * 64);
-            x1 = ldg_stream4(g_row[q] + kc * 64 + 4);
-          }
-          const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          __nv_bfloat16 h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) umma::split_bf16(x[e], h[e], l[e]);
-          hi[q] = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]),
-                             umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
-          lo[q] = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]),
-                             umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+        x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M) {
+          const float* src = p.gl + (size_t)m * V + kc * 64 + ch * 8;
+          x[q][0] = ldg_stream4(src);
+          x[q][1] = ldg_stream4(src + 4);
         }
-        mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
-        unsigned char* a_hi = base + s * stage_bytes;
-        unsigned char* a_lo = a_hi + a_bytes;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
-          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(smem_u32(&full[s]));
       }
+    };
+    float4 cur[4][2], nxt[4][2];
+    long long unit = blockIdx.x;
+    int kc = 0;
+    if (unit < num_units) issue(unit, 0, cur);
+    uint32_t g = 0;
+    while (unit < num_units) {
+      long long nunit = unit;
+      int nkc = kc + 1;
+      if (nkc == nchunks) { nkc = 0; nunit += gridDim.x; }
+      if (nunit < num_units) issue(nunit, nkc, nxt);
+      const int s = g % kJStages;
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float x[8] = {cur[q][0].x, cur[q][0].y, cur[q][0].z, cur[q][0].w,
+                            cur[q][1].x, cur[q][1].y, cur[q][1].z, cur[q][1].w};
+        umma::split_pack8(x, hi[q], lo[q]);
+      }
+      mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+      unsigned char* a_hi = base + s * stage_bytes;
+      unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+        *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&full[s]));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; }
+      unit = nunit; kc = nkc; ++g;
     }
   }
   umma::fence_before_thread_sync();
@@ -688,7 +655,8 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
 // lane), 16 warps sweep the C rows of a frame with 4 independent loads in flight per
 // thread; the [C, 128] column block of grad_proj_ctx is accumulated in shared memory.
 __global__ void __launch_bounds__(512)
-joint_reduce128_kernel(const float* __restrict__ gp, long long N, int C, int H,
+joint_reduce128_kernel(const float* __restrict__ gp, const float* __restrict__ pc,
+                       const float* __restrict__ pf, long long N, int C, int H,
                        long long frames_per_block, float* __restrict__ g_pc,
                        float* __restrict__ g_pf) {
   extern __shared__ __align__(16) float4 r4[];    // [C][32] accumulators, then [16][32] partials
@@ -701,18 +669,28 @@ joint_reduce128_kernel(const float* __restrict__ gp, long long N, int C, int H,
   __syncthreads();
   for (long long n = n_lo; n < n_hi; ++n) {
     const float* base = gp + ((size_t)n * C) * H + jcol;
+    const float4 fr = __ldg(reinterpret_cast<const float4*>(pf + (size_t)n * H + jcol));
     float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = warp; c < C; c += 64) {
-      float4 x[4];
+      float4 x[4], a[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int cc = c + 16 * u;
-        x[u] = cc < C ? ldg_stream4(base + (size_t)cc * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[u] = a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc < C) {
+          x[u] = ldg_stream4(base + (size_t)cc * H);
+          a[u] = __ldg(reinterpret_cast<const float4*>(pc + (size_t)cc * H + jcol));
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int cc = c + 16 * u;
         if (cc < C) {
+          // d tanh: Gp = (G.W + gb*wb) * (1 - tanh(pc + pf)^2)
+          const float h0 = tanh_fast(a[u].x + fr.x), h1 = tanh_fast(a[u].y + fr.y);
+          const float h2 = tanh_fast(a[u].z + fr.z), h3 = tanh_fast(a[u].w + fr.w);
+          x[u].x *= fmaf(-h0, h0, 1.f); x[u].y *= fmaf(-h1, h1, 1.f);
+          x[u].z *= fmaf(-h2, h2, 1.f); x[u].w *= fmaf(-h3, h3, 1.f);
           pf.x += x[u].x; pf.y += x[u].y; pf.z += x[u].z; pf.w += x[u].w;
           float4 a = r4[cc * 32 + lane];          // (cc, lane) has exactly one owner thread
           a.x += x[u].x; a.y += x[u].y; a.z += x[u].z; a.w += x[u].w;
@@ -748,7 +726,8 @@ joint_reduce128_kernel(const float* __restrict__ gp, long long N, int C, int H,
 // [C, H] (sum over n, accumulated with atomics once per CTA).  grid = (H / jw, nblocks);
 // block = 512 threads = (512 / jw) row groups x jw columns; smem = C * jw floats.
 __global__ void __launch_bounds__(512)
-joint_reduce_kernel(const float* __restrict__ gp, long long N, int C, int H, int jw,
+joint_reduce_kernel(const float* __restrict__ gp, const float* __restrict__ pc,
+                    const float* __restrict__ pf, long long N, int C, int H, int jw,
                     long long frames_per_block, float* __restrict__ g_pc,
                     float* __restrict__ g_pf) {
   extern __shared__ float racc[];                 // [C][jw] then [RG][jw] scratch
@@ -762,9 +741,11 @@ joint_reduce_kernel(const float* __restrict__ gp, long long N, int C, int H, int
   __syncthreads();
   for (long long n = n_lo; n < n_hi; ++n) {
     const float* row = gp + ((size_t)n * C) * H + j;
+    const float fr = pf[(size_t)n * H + j];
     float acc = 0.f;
     for (int c = rg; c < C; c += RG) {
-      const float x = ldg_stream(row + (size_t)c * H);
+      const float h = tanh_fast(pc[(size_t)c * H + j] + fr);
+      const float x = ldg_stream(row + (size_t)c * H) * fmaf(-h, h, 1.f);
       acc += x;
       racc[c * jw + jj] += x;                     // (c, jj) is owned by exactly one thread
     }
@@ -931,12 +912,13 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
         const int k = a_k0 + i * a_kstep;
         const float x[8] = {ax[i][0].x, ax[i][0].y, ax[i][0].z, ax[i][0].w,
                             ax[i][1].x, ax[i][1].y, ax[i][1].z, ax[i][1].w};
-        __nv_bfloat16 h[8], l[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { umma::split_bf16(x[e], h[e], l[e]); bv_acc[e] += x[e]; }
+        for (int e = 0; e < 8; ++e) bv_acc[e] += x[e];
+        uint4 h4, l4;
+        umma::split_pack8(x, h4, l4);
         const uint32_t off = umma::mn_major_chunk_offset(V, a_vch * 8, k);
-        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
-        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+        *reinterpret_cast<uint4*>(a_hi + off) = h4;
+        *reinterpret_cast<uint4*>(a_lo + off) = l4;
       }
 #pragma unroll
       for (int i = 0; i < BI; ++i) {                   // B = h^T chunk (recomputed)
@@ -945,17 +927,17 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
         float t[8] = {bp[i][0].x + bf[i][0].x, bp[i][0].y + bf[i][0].y, bp[i][0].z + bf[i][0].z,
                       bp[i][0].w + bf[i][0].w, bp[i][1].x + bf[i][1].x, bp[i][1].y + bf[i][1].y,
                       bp[i][1].z + bf[i][1].z, bp[i][1].w + bf[i][1].w};
-        __nv_bfloat16 h[8], l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           t[e] = live ? tanh_fast(t[e]) : 0.f;
           wb_acc[e] = fmaf(gbm[i], t[e], wb_acc[e]);
-          umma::split_bf16(t[e], h[e], l[e]);
         }
         if (b_jch == 0) bb_acc += gbm[i];
+        uint4 h4, l4;
+        umma::split_pack8(t, h4, l4);
         const uint32_t off = umma::mn_major_chunk_offset(NJ, b_jch * 8, k);
-        *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(umma::pack_bf16(h[0], h[1]), umma::pack_bf16(h[2], h[3]), umma::pack_bf16(h[4], h[5]), umma::pack_bf16(h[6], h[7]));
-        *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(umma::pack_bf16(l[0], l[1]), umma::pack_bf16(l[2], l[3]), umma::pack_bf16(l[4], l[5]), umma::pack_bf16(l[6], l[7]));
+        *reinterpret_cast<uint4*>(b_hi + off) = h4;
+        *reinterpret_cast<uint4*>(b_lo + off) = l4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(smem_u32(&full[s]));
@@ -1111,7 +1093,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NH = NH; p.gp = gp;
   const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
-                      sizeof(float) * (H + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
+                      sizeof(float) * H + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1134,7 +1116,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
     LT_CUDA(cudaFuncSetAttribute(joint_reduce128_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     joint_reduce128_kernel<<<dim3(jblocks, (unsigned)nblocks), 512, rsmem, stream>>>(
-        gp, (long long)N, C, H, fpb, gpc, gpf);
+        gp, pc, pf, (long long)N, C, H, fpb, gpc, gpf);
     LT_LAUNCHED();
     return LT_OK;
   }
@@ -1154,7 +1136,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   LT_CUDA(cudaFuncSetAttribute(joint_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)rsmem));
   joint_reduce_kernel<<<dim3(jblocks, (unsigned)nblocks), 512, rsmem, stream>>>(
-      gp, (long long)N, C, H, jw, fpb, gpc, gpf);
+      gp, pc, pf, (long long)N, C, H, jw, fpb, gpc, gpf);
   LT_LAUNCHED();
   return LT_OK;
 }

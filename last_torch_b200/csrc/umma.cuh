@@ -126,6 +126,19 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// Packed variant: two values per cvt.rn.bf16x2.f32 (one ALU-pipe F2FP instead of two
+// XU-pipe F2F), bf16 -> fp32 by a 16-bit shift.  hi / lo hold (x0 low half, x1 high half).
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void split_pack8(const float (&x)[8], uint4& hi, uint4& lo) {
+  split_pack2(x[0], x[1], hi.x, lo.x);
+  split_pack2(x[2], x[3], hi.y, lo.y);
+  split_pack2(x[4], x[5], hi.z, lo.z);
+  split_pack2(x[6], x[7], hi.w, lo.w);
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
