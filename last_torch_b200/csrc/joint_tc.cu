@@ -212,6 +212,11 @@ umma_probe_mn_kernel(const float* __restrict__ At, const float* __restrict__ Bt,
 constexpr int kJThreads = 448;
 constexpr int kJStages = 2;
 constexpr int kJProducers = 256;
+// forward kernel: 16 producer warps (2 row passes each) -> more overlapping tanh chains
+constexpr int kFProdWarps = 8;
+constexpr int kFThreads = (6 + kFProdWarps) * 32;
+constexpr int kFProducers = kFProdWarps * 32;
+constexpr int kFPasses = 128 / (kFProdWarps * 4);
 
 struct JointTcParams {
   const float* pc;       // [C, H]
@@ -250,13 +255,30 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return fmaf(-2.f, r, 1.f);
 }
 
+
+// Epilogue store: the accumulator arrives with lane = row (TMEM lane) and 32 columns
+// per thread.  Writing it directly would touch 32 different 128-byte lines per store
+// instruction; instead the 32 x 32 block goes through a padded per-warp shared tile
+// (conflict-free both ways) and every store instruction writes ONE full line of one row.
+__device__ __forceinline__ void store_block_coalesced(const float (&v)[32], float* tr, int lane,
+                                                      float* out_row0, size_t row_stride,
+                                                      int rows_valid) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+  __syncwarp();
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r)
+    if (r < rows_valid) out_row0[(size_t)r * row_stride + lane] = tr[r * 33 + lane];
+}
+
 __global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     umma::split_bf16(w[i], hi[i], lo[i]);
 }
 
-__global__ void __launch_bounds__(kJThreads, 1)
+__global__ void __launch_bounds__(kFThreads, 1)
 joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
                         const __grid_constant__ CUtensorMap map_lo, const JointTcParams p) {
   extern __shared__ __align__(1024) unsigned char jsmem_raw[];
@@ -268,7 +290,8 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   // stage layout: A_hi | A_lo | B_hi | B_lo
   float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
   float* s_bias = s_wb + H;                                                // [V]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+  float* s_tr = s_bias + 256;                                              // 4 x [32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
   uint64_t* full = bars;                    // [stages]  producers + TMA -> MMA
   uint64_t* empty = bars + kJStages;        // [stages]  MMA (commit) -> producers, TMA
   uint64_t* tfull = bars + 2 * kJStages;    // [2]       MMA (commit) -> epilogue
@@ -279,11 +302,11 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int nchunks = H / 64;
   const long long num_tiles = (p.M + 127) / 128;
 
-  for (int i = tid; i < H; i += kJThreads) s_wb[i] = p.w_blank[i];
-  for (int i = tid; i < V; i += kJThreads) s_bias[i] = p.b_vocab[i];
+  for (int i = tid; i < H; i += kFThreads) s_wb[i] = p.w_blank[i];
+  for (int i = tid; i < V; i += kFThreads) s_bias[i] = p.b_vocab[i];
   if (tid == 0) {
     for (int s = 0; s < kJStages; ++s) {
-      mbar_init_n(smem_u32(&full[s]), kJProducers + 1);
+      mbar_init_n(smem_u32(&full[s]), kFProducers + 1);
       mbar_init_n(smem_u32(&empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -355,18 +378,15 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       const uint32_t acc = it & 1;
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
-      const long long m = tile * 128 + quad * 32 + lane;
-      float* out = p.lexical + (size_t)m * V;
+      const long long m0 = tile * 128 + quad * 32;
+      const int rows_valid = (int)max(0ll, min(32ll, p.M - m0));
+      float* out = p.lexical + (size_t)m0 * V;
       for (int c0 = 0; c0 < V; c0 += 32) {
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
-        if (m < p.M) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            stg_stream4(out + c0 + j, make_float4(v[j] + s_bias[c0 + j], v[j + 1] + s_bias[c0 + j + 1],
-                                                  v[j + 2] + s_bias[c0 + j + 2],
-                                                  v[j + 3] + s_bias[c0 + j + 3]));
-        }
+        for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
+        store_block_coalesced(v, s_tr + quad * (32 * 33), lane, out + c0, (size_t)V, rows_valid);
       }
       umma::fence_before_thread_sync();
       mbar_arrive(smem_u32(&tempty[acc]));
@@ -376,17 +396,18 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
     // 8 lanes cover one row's 64-wide K chunk (256 contiguous bytes of pc / pf, one
     // 16-byte bf16 chunk per lane), 4 rows per warp, 4 passes over the 128 rows: global
     // loads are fully coalesced and the 8 lanes of a row write 8 distinct swizzled chunks.
-    const int pw = warp - 6;                            // 0 .. 7
+    const int pw = warp - 6;                            // 0 .. kFProdWarps-1
     const int ch = lane & 7, rsub = lane >> 3;
     uint32_t g = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const float* pc_row[4];
-      const float* pf_row[4];
-      bool valid[4];
-      float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* pc_row[kFPasses];
+      const float* pf_row[kFPasses];
+      bool valid[kFPasses];
+      float bacc[kFPasses];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long m = tile * 128 + q * 32 + pw * 4 + rsub;
+      for (int q = 0; q < kFPasses; ++q) {
+        bacc[q] = 0.f;
+        const long long m = tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub;
         valid[q] = m < p.M;
         const long long n = valid[q] ? m / p.C : 0;
         const int c = valid[q] ? (int)(m - n * p.C) : 0;
@@ -395,9 +416,9 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       }
       for (int kc = 0; kc < nchunks; ++kc, ++g) {
         const int s = g % kJStages;
-        uint4 hi[4], lo[4];
+        uint4 hi[kFPasses], lo[kFPasses];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kFPasses; ++q) {
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64));
           const float4 a1 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64 + 4));
           const float4 f0 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64));
@@ -416,8 +437,8 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
         unsigned char* a_hi = base + s * stage_bytes;
         unsigned char* a_lo = a_hi + a_bytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
+        for (int q = 0; q < kFPasses; ++q) {
+          const uint32_t off = umma::swizzled_offset(q * (kFProdWarps * 4) + pw * 4 + rsub, ch);
           *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
           *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
         }
@@ -425,12 +446,12 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
         mbar_arrive(smem_u32(&full[s]));
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kFPasses; ++q) {
         float b = bacc[q];
         b += __shfl_xor_sync(0xffffffffu, b, 1);
         b += __shfl_xor_sync(0xffffffffu, b, 2);
         b += __shfl_xor_sync(0xffffffffu, b, 4);
-        if (valid[q] && ch == 0) p.blank[tile * 128 + q * 32 + pw * 4 + rsub] = b + p.b_blank;
+        if (valid[q] && ch == 0) p.blank[tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub] = b + p.b_blank;
       }
     }
   }
@@ -481,7 +502,8 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const uint32_t b_bytes = (uint32_t)NH * 128;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
   float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wb + H);
+  float* s_tr = s_wb + H;                                                  // 4 x [32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
   uint64_t* full = bars;
   uint64_t* empty = bars + kJStages;
   uint64_t* tfull = bars + 2 * kJStages;
@@ -570,24 +592,20 @@ joint_dgrad_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       const long long tile = unit / nblk;
       const int blk = (int)(unit % nblk);
       const uint32_t acc = it & 1;
-      const long long m = tile * 128 + quad * 32 + lane;
-      const bool valid = m < p.M;
-      const float gbm = valid ? p.gb[m] : 0.f;
+      const long long m0 = tile * 128 + quad * 32;
+      const long long m = m0 + lane;
+      const int rows_valid = (int)max(0ll, min(32ll, p.M - m0));
+      const float gbm = m < p.M ? p.gb[m] : 0.f;
       const float* wb = s_wb + blk * NH;
-      float* out = p.gp + (size_t)m * H + blk * NH;
+      float* out = p.gp + (size_t)m0 * H + blk * NH;
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
       for (int c0 = 0; c0 < NH; c0 += 32) {
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            stg_stream4(out + c0 + j,
-                        make_float4(fmaf(gbm, wb[c0 + j], v[j]), fmaf(gbm, wb[c0 + j + 1], v[j + 1]),
-                                    fmaf(gbm, wb[c0 + j + 2], v[j + 2]),
-                                    fmaf(gbm, wb[c0 + j + 3], v[j + 3])));
-        }
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(gbm, wb[c0 + j], v[j]);
+        store_block_coalesced(v, s_tr + quad * (32 * 33), lane, out + c0, (size_t)H, rows_valid);
       }
       umma::fence_before_thread_sync();
       mbar_arrive(smem_u32(&tempty[acc]));
@@ -1032,8 +1050,8 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   JointTcParams p = {};
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
-  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + sizeof(float) * (H + 256) +
-                      16 * 8 + 16 + 1024;
+  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
+                      sizeof(float) * (H + 256 + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1041,7 +1059,7 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   const int grid = (int)(tiles < sms ? tiles : sms);
   LT_CUDA(cudaFuncSetAttribute(joint_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  joint_forward_tc_kernel<<<grid, kJThreads, smem, stream>>>(map_hi, map_lo, p);
+  joint_forward_tc_kernel<<<grid, kFThreads, smem, stream>>>(map_hi, map_lo, p);
   LT_LAUNCHED();
   return LT_OK;
 }
@@ -1093,7 +1111,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NH = NH; p.gp = gp;
   const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
-                      sizeof(float) * H + 16 * 8 + 16 + 1024;
+                      sizeof(float) * (H + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
