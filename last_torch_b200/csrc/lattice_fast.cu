@@ -206,14 +206,18 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
 
   // finalizer threads: tid < 64 own destination q = 1 + col0 + tid; thread 64 of
   // rank 0 owns state 0 (no incoming lexical arc, contexts.py:217-218).
-  const bool is_fin = tid < kColsPerCta;
-  const bool is_q0 = (rank == 0 && tid == kColsPerCta);
-  const int q = is_fin ? 1 + col0 + tid : 0;
+  // Tree finalizer: 4 threads per destination column (tid < 256) each merge 4 of the 16
+  // per-warp partials, two shuffle merges combine them, the part == 0 thread publishes.
+  const bool in_tree = tid < 4 * kColsPerCta;
+  const int fcol = tid >> 2, fpart = tid & 3;
+  const bool is_fin = in_tree && fpart == 0;
+  const bool is_q0 = (rank == 0 && tid == 4 * kColsPerCta);
+  const int q = is_fin ? 1 + col0 + fcol : 0;
   float nblank = 0.f, ntail = 0.f;              // prefetched blank[t][q], lexical[t][V][col]
   if (nf > 0) {
     if (is_fin) {
       nblank = ldg_stream(p.blank + bt0 * C + q);
-      ntail = ldg_stream(p.lexical + bt0 * (size_t)C * V + (size_t)V * V + col0 + tid);
+      ntail = ldg_stream(p.lexical + bt0 * (size_t)C * V + (size_t)V * V + col0 + fcol);
     } else if (is_q0) {
       nblank = ldg_stream(p.blank + bt0 * C);
     }
@@ -231,7 +235,7 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
     if (t + 1 < nf) {
       if (is_fin) {
         nblank = ldg_stream(p.blank + (bt0 + t + 1) * C + q);
-        ntail = ldg_stream(p.lexical + (bt0 + t + 1) * (size_t)C * V + (size_t)V * V + col0 + tid);
+        ntail = ldg_stream(p.lexical + (bt0 + t + 1) * (size_t)C * V + (size_t)V * V + col0 + fcol);
       } else if (is_q0) {
         nblank = ldg_stream(p.blank + (bt0 + t + 1) * C);
       }
@@ -323,35 +327,52 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
       tma_load_2d(smem_u32(tiles) + stage * kStageBytes, &tmap, col0, (int)((bt0 + t + NS) * C), bar);
     }
 
-    if (is_fin) {
-      const float ab = S::times(cur[q], to_dom<SR>(cblank));
-      const float xt = S::times(cur[V], to_dom<SR>(ctail));   // source row V (not in the TMA box)
-      float v;
-      if constexpr (SR == LT_LOG) {
-        float m = part_m[tid], s = part_s[tid];
+    if (in_tree) {                      // warps 0-7, warp-uniform
+      const int w0 = fpart * 4;
+      float m = part_m[w0 * kColsPerCta + fcol];
+      float s = (SR == LT_REAL) ? 0.f : part_s[w0 * kColsPerCta + fcol];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) lse2_merge(m, s, part_m[w * kColsPerCta + tid], part_s[w * kColsPerCta + tid]);
-        lse2_merge(m, s, xt, xt == neg_inf() ? 0.f : 1.f);
-        v = log2_add_exp2(ab, msafe(m) + __log2f(s));
-      } else if constexpr (SR == LT_MAXTROPICAL) {
-        float m = part_m[tid]; int am = __float_as_int(part_s[tid]);
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) {
-          const float om = part_m[w * kColsPerCta + tid];
-          const int oa = __float_as_int(part_s[w * kColsPerCta + tid]);
-          if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+      for (int w = 1; w < 4; ++w) {
+        const float om = part_m[(w0 + w) * kColsPerCta + fcol];
+        if constexpr (SR == LT_LOG) {
+          lse2_merge(m, s, om, part_s[(w0 + w) * kColsPerCta + fcol]);
+        } else if constexpr (SR == LT_MAXTROPICAL) {
+          const int oa = __float_as_int(part_s[(w0 + w) * kColsPerCta + fcol]);
+          if (om > m || (om == m && oa < __float_as_int(s))) { m = om; s = __int_as_float(oa); }
+        } else {
+          m += om;
         }
-        if (xt > m) { m = xt; am = V; }
-        const bool take_blank = ab >= m;               // semirings.py:363
-        v = take_blank ? ab : m;
-        if (p.backptr) p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)am;
-      } else {
-        float m = part_m[tid];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) m += part_m[w * kColsPerCta + tid];
-        v = ab + (m + xt);
       }
-      xchg_store(nxt, q, v, &xbar[(t + 1) & 1], nrank);
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const float os = __shfl_xor_sync(0xffffffffu, s, o);
+        if constexpr (SR == LT_LOG) {
+          lse2_merge(m, s, om, os);
+        } else if constexpr (SR == LT_MAXTROPICAL) {
+          if (om > m || (om == m && __float_as_int(os) < __float_as_int(s))) { m = om; s = os; }
+        } else {
+          m += om;
+        }
+      }
+      if (is_fin) {
+        const float ab = S::times(cur[q], to_dom<SR>(cblank));
+        const float xt = S::times(cur[V], to_dom<SR>(ctail));   // source row V (not in the TMA box)
+        float v;
+        if constexpr (SR == LT_LOG) {
+          lse2_merge(m, s, xt, xt == neg_inf() ? 0.f : 1.f);
+          v = log2_add_exp2(ab, msafe(m) + __log2f(s));
+        } else if constexpr (SR == LT_MAXTROPICAL) {
+          int am = __float_as_int(s);
+          if (xt > m) { m = xt; am = V; }
+          const bool take_blank = ab >= m;               // semirings.py:363
+          v = take_blank ? ab : m;
+          if (p.backptr) p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)am;
+        } else {
+          v = ab + (m + xt);
+        }
+        xchg_store(nxt, q, v, &xbar[(t + 1) & 1], nrank);
+      }
     } else if (is_q0) {
       const float v = S::times(cur[0], to_dom<SR>(cblank));
       if constexpr (SR == LT_MAXTROPICAL) { if (p.backptr) p.backptr[(bt0 + t) * C] = (int16_t)-1; }
