@@ -47,6 +47,10 @@ extern "C" {
 
 /* flags for lt_lattice_forward / lt_lattice_backward */
 #define LT_FLAG_FORCE_GENERIC 1u     /* never take the TMA/cluster fast path   */
+#define LT_FLAG_FAST_V1 2u           /* first-generation fast path (one utterance per
+                                        cluster) instead of the interleaved-pair kernels */
+#define LT_FLAG_PAIR_CTA 4u          /* fast path: two utterances per 512-thread CTA
+                                        instead of two 256-thread CTAs per SM       */
 #define LT_FLAG_CLUSTER_SHIFT 8      /* bits 8..11: force cluster size (1,2,4,8) */
 
 int lt_version(void);
@@ -122,7 +126,10 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
  *   states [B,U1] int32 = walk_states(labels) (contexts.py:109-146)
  *   next_labels [B,U1] int32 in [1,V] (labels ++ [1], label 0 read as 1)
  *   -> blank_w, lexical_w [B,T,U1]
- * scatter_add: its transpose, grad_dense[b,t,states[u],(label-1)] += scale*g
+ * scatter_add: its transpose,
+ *   grad_dense[b,t,states[u],(label-1)] += scale * utt_scale[b] * g
+ *   (utt_scale [B] or NULL = 1: lets the numerator posteriors be computed once,
+ *   unscaled, and weighted by the upstream gradient of each utterance here)
  */
 /* walk_states (contexts.py:109-146, FullNGram.next_state :190-205):
  *   labels [B,U] int32 in [0,V] -> states [B,U+1], next_labels [B,U+1] */
@@ -136,7 +143,8 @@ int lt_string_gather(int vocab_size, int num_states, const float* blank,
 int lt_string_scatter_add(int vocab_size, int num_states,
                           const float* grad_blank_w, const float* grad_lexical_w,
                           const int32_t* states, const int32_t* next_labels,
-                          int B, int T, int U1, float scale, float* grad_blank,
+                          int B, int T, int U1, float scale,
+                          const float* utt_scale, float* grad_blank,
                           float* grad_lexical, void* stream);
 /* shortest_distance_step_scan (lattices.py:347-377) with
  * alignment.string_forward (alignments.py:327-329 / :427-432).

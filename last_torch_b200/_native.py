@@ -44,7 +44,7 @@ SIGNATURES = {
     'lt_string_gather': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr],
     'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
-                              _c_float, _ptr, _ptr, _ptr],
+                              _c_float, _ptr, _ptr, _ptr, _ptr],
     'lt_string_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr],
     'lt_string_backward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,

@@ -101,6 +101,8 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
   p.levels = max_expansions >= 1 ? levels : nullptr;
   p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
+  if (T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical))
+    return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (T > 0 && lattice_fast_supported(g, max_expansions, flags, lexical))
     return lattice_forward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,
@@ -131,6 +133,9 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
   p.blank = blank; p.lexical = lexical; p.num_frames = num_frames;
   p.alphas = alphas; p.levels = levels; p.dist = dist; p.grad_dist = grad_dist;
   p.grad_blank = grad_blank; p.grad_lexical = grad_lexical; p.beta_final = beta_final;
+  if (lattice_fast2_supported(g, max_expansions, flags, lexical) &&
+      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
+    return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (lattice_fast_supported(g, max_expansions, flags, lexical) &&
       reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
     return lattice_backward_fast_launch(semiring, g, p, (cudaStream_t)stream);
@@ -189,14 +194,15 @@ int lt_string_gather(int vocab_size, int num_states, const float* blank, const f
 int lt_string_scatter_add(int vocab_size, int num_states, const float* grad_blank_w,
                           const float* grad_lexical_w, const int32_t* states,
                           const int32_t* next_labels, int B, int T, int U1, float scale,
-                          float* grad_blank, float* grad_lexical, void* stream) {
+                          const float* utt_scale, float* grad_blank, float* grad_lexical,
+                          void* stream) {
   LT_CHECK_ARG(vocab_size > 0 && num_states > 0 && B >= 0 && T >= 0 && U1 >= 1,
                "lt_string_scatter_add: bad sizes V=%d C=%d B=%d T=%d U1=%d", vocab_size, num_states, B, T, U1);
   if (B == 0 || T == 0) return LT_OK;
   LT_CHECK_ARG(grad_blank_w && grad_lexical_w && states && next_labels && grad_blank && grad_lexical,
                "lt_string_scatter_add: NULL pointer");
   return string_scatter_launch(vocab_size, num_states, grad_blank_w, grad_lexical_w, states,
-                               next_labels, B, T, U1, scale, grad_blank, grad_lexical,
+                               next_labels, B, T, U1, scale, utt_scale, grad_blank, grad_lexical,
                                (cudaStream_t)stream);
 }
 

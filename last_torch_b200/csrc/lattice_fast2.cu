@@ -1,22 +1,24 @@
-// K1/K2 fast path for the headline shape: FullNGram context_size 1 (bigram,
-// C = V + 1 states), FrameDependent alignment, V in {64, 128, 192, 256}.
+// K1/K2 fast path, second generation: TWO utterances interleaved per cluster.
 //
-// B200-first design (see DESIGN.md "Fast path"):
-//   * one thread-block CLUSTER of S = V/64 CTAs per utterance, persistent over
-//     all T frames; alpha / beta live in shared memory (a full replica per CTA);
-//   * arc weights never depend on alpha, so they are streamed by TMA
-//     (cp.async.bulk[.tensor]) into a shared-memory ring several frames AHEAD of
-//     the recursion, completion tracked by mbarriers -- the HBM stream is
-//     decoupled from the sequential dependency chain;
-//   * forward: CTA r owns 64 destination columns of the [V+1, V] frame tile
-//     (2-D TMA box [V rows x 64 cols]); column log-sum-exp is two passes over
-//     REGISTERS (max, then one ex2 per arc), combined across warps in smem;
-//   * backward: CTA r owns 64 source rows (one contiguous 64*V*4-byte bulk
-//     copy); 8 lanes per row, conflict-free 128-bit smem reads, ONE ex2 per arc
-//     shared by the row log-sum-exp (beta) and the arc posterior, gradients
-//     written straight from registers with coalesced 128-bit streaming stores;
-//   * the new 64-entry slice of alpha / beta is all-gathered with DSMEM stores
-//     to every CTA of the cluster, followed by one cluster barrier per frame.
+// Same shapes as lattice_fast.cu (FullNGram context_size 1, FrameDependent,
+// V in {64, 128, 192, 256}) but organised so that the sequential dependency chain
+// of one utterance (reduce -> finalise -> DSMEM all-gather -> wake-up) is hidden
+// behind the arithmetic of another one on the same SM:
+//   * a cluster of CL = V/32 CTAs owns a PAIR of utterances; every CTA runs two
+//     independent 256-thread groups (named barriers 1 and 2), group g working on
+//     utterance 2*cluster + g and on 32 destination columns (forward) / 32 source
+//     rows (backward) of it; the two groups drift freely, so while one sits in its
+//     finaliser / exchange phase the other one keeps the FMA/MUFU pipes busy;
+//   * each group has its own TMA ring (3 stages of 32 KB at V = 256) fed by one
+//     elected thread, several frames ahead of the recursion;
+//   * forward, Log: the exact column maximum is established FIRST (per-thread max,
+//     two shuffles, one 1 KB exchange through shared memory), then every arc costs
+//     exactly one FFMA + one FADD + one MUFU.EX2 + one FADD; no (max, sum) pair
+//     merges anywhere, the finaliser adds eight partial sums;
+//   * the next frame's tile is pulled into registers BEFORE the group blocks on the
+//     alpha exchange, so the shared-memory reads are off the critical path;
+//   * state exchange as in lattice_fast.cu: st.async + mbarrier complete_tx, no
+//     cluster barrier and no fence inside the loop.
 //
 // Reference semantics: lattices.py:436-462 + alignments.py:294-297 (forward),
 // alignments.py:300-318 + lattices.py:775-779 (backward), contexts.py:207-256.
@@ -30,14 +32,18 @@ namespace lt {
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kColsPerCta = 64;
-
 using namespace fastptx;
 
-struct FastFwdParams {
-  int V, B, T, stages;
+constexpr int kGroupThreads = 256;
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kCols = 32;                       // destination columns (fwd) / source rows (bwd) per CTA
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
+}
+
+struct Fast2FwdParams {
+  int B, T, stages;
   const float* blank;
   const float* lexical;
   const int32_t* num_frames;
@@ -49,52 +55,63 @@ struct FastFwdParams {
 };
 
 // ============================================================== forward (K1) ==
-// VD = V / 64 = cluster size.  Tile stage: [V rows][64 cols] fp32.
-template <int SR, int VD>
-__global__ void __launch_bounds__(kThreads, 1)
-lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdParams p) {
+template <int SR, int V, int G>
+__global__ void __launch_bounds__(kGroupThreads * G, G == 1 ? 2 : 1)
+lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdParams p) {
   using S = Sr<SR>;
-  constexpr int V = 64 * VD;
+  constexpr int CL = V / kCols;                 // cluster size
   constexpr int C = V + 1;
   constexpr int CP = (C + 3) & ~3;
-  constexpr int RPT = 2 * VD;                   // rows per thread (V / 32 row groups)
-  constexpr uint32_t kStageBytes = V * kColsPerCta * 4;
-  extern __shared__ __align__(128) unsigned char fsmem[];
+  constexpr int RPT = V / 32;                   // rows per thread
+  constexpr uint32_t kStageBytes = V * kCols * 4;
+  constexpr int kPart = kGroupWarps * kCols;    // one partial array
+  extern __shared__ __align__(128) unsigned char smem2[];
   const int NS = p.stages;
-  float* tiles = reinterpret_cast<float*>(fsmem);
-  float* alpha_buf = reinterpret_cast<float*>(fsmem + (size_t)NS * kStageBytes);
-  float* part_m = alpha_buf + 2 * CP;
-  float* part_s = part_m + kWarps * kColsPerCta;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + kWarps * kColsPerCta);
 
-  const uint32_t nrank = VD;
+  const int tid = threadIdx.x;
+  const int grp = G == 1 ? 0 : tid >> 8;       // warp-uniform
+  const int gt = tid & (kGroupThreads - 1);
+  const int lane = gt & 31, warp = gt >> 5;
   const uint32_t rank = cluster_ctarank();
-  const int b = blockIdx.x / VD;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cg = tid & 15;                      // column group: columns 4cg .. 4cg+3
-  const int rg = tid >> 4;                      // row group: rows rg*RPT .. +RPT-1
-  const int nf = max(0, min(p.num_frames[b], p.T));
-  const size_t bt0 = (size_t)b * p.T;
-  const int col0 = rank * kColsPerCta;          // first tile column owned by this CTA
+  const int cluster_id = blockIdx.x / CL;
+  const int b = cluster_id * G + grp;
+  const bool active = b < p.B;
 
-  uint64_t* xbar = bars + NS;       // xbar[i]: "alpha buffer i has received all C entries"
-  if (tid == 0) {
-    prefetch_tensormap(&tmap);
+  // shared-memory carve-up: [group][stage] tiles, then per-group small state
+  float* tiles = reinterpret_cast<float*>(smem2) + (size_t)grp * NS * (kStageBytes / 4);
+  float* small = reinterpret_cast<float*>(smem2 + (size_t)G * NS * kStageBytes);
+  constexpr int kSmallFloats = 2 * CP + 4 * kPart + 2 * 16;   // alpha x2, pmax x2, psum x2, bars
+  small += (size_t)grp * kSmallFloats;
+  float* alpha_buf = small;
+  float* part_m = alpha_buf + 2 * CP;           // [2][warps][32]
+  float* part_s = part_m + 2 * kPart;           // [2][warps][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + 2 * kPart);   // NS full + 2 exchange
+  uint64_t* xbar = bars + NS;
+
+  const int cg = gt & 7;                        // column group: columns 4cg .. 4cg+3
+  const int rg = gt >> 3;                       // row group: rows rg*RPT .. +RPT-1
+  const int r0 = rg * RPT;
+  const int nf = active ? max(0, min(p.num_frames[b], p.T)) : 0;
+  const size_t bt0 = (size_t)(active ? b : 0) * p.T;
+  const int col0 = rank * kCols;
+
+  if (gt == 0) {
+    if (grp == 0) prefetch_tensormap(&tmap);
     for (int s = 0; s < NS + 2; ++s) mbar_init(smem_u32(&bars[s]), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  for (int c = tid; c < CP; c += kThreads) {
+  for (int c = gt; c < CP; c += kGroupThreads) {
     float v = S::zero();
-    if (c < C) v = p.alpha_init ? p.alpha_init[(size_t)b * C + c] : (c == 0 ? S::one() : S::zero());
+    if (c < C && active)
+      v = p.alpha_init ? p.alpha_init[(size_t)b * C + c] : (c == 0 ? S::one() : S::zero());
     alpha_buf[c] = to_dom<SR>(v);
     alpha_buf[CP + c] = S::zero();
   }
   __syncthreads();
   cluster_sync_all();
 
-  // prologue: fill the ring
-  if (tid == 0) {
+  if (gt == 0) {
     for (int s = 0; s < NS && s < nf; ++s) {
       const uint32_t bar = smem_u32(&bars[s]);
       mbar_arrive_expect_tx(bar, kStageBytes);
@@ -102,54 +119,53 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
     }
   }
 
-  // finalizer threads: tid < 64 own destination q = 1 + col0 + tid; thread 64 of
-  // rank 0 owns state 0 (no incoming lexical arc, contexts.py:217-218).
-  // Tree finalizer: 4 threads per destination column (tid < 256) each merge 4 of the 16
-  // per-warp partials, two shuffle merges combine them, the part == 0 thread publishes.
-  const bool in_tree = tid < 4 * kColsPerCta;
-  const int fcol = tid >> 2, fpart = tid & 3;
-  const bool is_fin = in_tree && fpart == 0;
-  const bool is_q0 = (rank == 0 && tid == 4 * kColsPerCta);
-  const int q = is_fin ? 1 + col0 + fcol : 0;
+  // finalisers: warp 0, lane j owns destination q = 1 + col0 + j; thread 32 of the
+  // group on rank 0 owns state 0 (no incoming lexical arc, contexts.py:217-218).
+  const bool is_fin = warp == 0;
+  const bool is_q0 = (rank == 0 && gt == 32);
+  const int q = is_fin ? 1 + col0 + lane : 0;
   float nblank = 0.f, ntail = 0.f;              // prefetched blank[t][q], lexical[t][V][col]
   if (nf > 0) {
     if (is_fin) {
       nblank = ldg_stream(p.blank + bt0 * C + q);
-      ntail = ldg_stream(p.lexical + bt0 * (size_t)C * V + (size_t)V * V + col0 + fcol);
+      ntail = ldg_stream(p.lexical + bt0 * (size_t)C * V + (size_t)V * V + col0 + lane);
     } else if (is_q0) {
       nblank = ldg_stream(p.blank + bt0 * C);
     }
   }
 
+  float4 x[RPT];
+  int stage = 0;
+  uint32_t parity = 0;
+  if (nf > 0) {
+    mbar_wait(smem_u32(&bars[0]), 0);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      x[i] = *reinterpret_cast<const float4*>(tiles + (size_t)(r0 + i) * kCols + cg * 4);
+  }
+
   for (int t = 0; t < nf; ++t) {
-    const int stage = t % NS;
-    const uint32_t parity = (t / NS) & 1;
     float* cur = alpha_buf + (t & 1) * CP;
     float* nxt = alpha_buf + ((t + 1) & 1) * CP;
+    float* pm_buf = part_m + (t & 1) * kPart;
+    float* ps_buf = part_s + (t & 1) * kPart;
     // alpha_t (t > 0) is complete once every CTA's st.async stores have landed
     if (t > 0) mbar_wait(smem_u32(&xbar[t & 1]), ((t - 1) >> 1) & 1);
-    if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(t + 1) & 1]), C * 4);
+    if (gt == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(t + 1) & 1]), C * 4);
     const float cblank = nblank, ctail = ntail;
     if (t + 1 < nf) {
       if (is_fin) {
         nblank = ldg_stream(p.blank + (bt0 + t + 1) * C + q);
-        ntail = ldg_stream(p.lexical + (bt0 + t + 1) * (size_t)C * V + (size_t)V * V + col0 + fcol);
+        ntail = ldg_stream(p.lexical + (bt0 + t + 1) * (size_t)C * V + (size_t)V * V + col0 + lane);
       } else if (is_q0) {
         nblank = ldg_stream(p.blank + (bt0 + t + 1) * C);
       }
     }
     if (p.alphas && (is_fin || is_q0)) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
 
-    mbar_wait(smem_u32(&bars[stage]), parity);
-    const float* tile = tiles + (size_t)stage * (kStageBytes / 4);
-    const int r0 = rg * RPT;
     float a[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) a[i] = cur[r0 + i];
-    float4 x[RPT];
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-      x[i] = *reinterpret_cast<const float4*>(tile + (size_t)(r0 + i) * kColsPerCta + cg * 4);
 
     float pm[4], ps[4];
     if constexpr (SR == LT_LOG) {
@@ -164,21 +180,10 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
         pm[0] = fmaxf(pm[0], x[i].x); pm[1] = fmaxf(pm[1], x[i].y);
         pm[2] = fmaxf(pm[2], x[i].z); pm[3] = fmaxf(pm[3], x[i].w);
       }
-      float ms[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { ms[j] = msafe(pm[j]); ps[j] = 0.f; }
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        ps[0] += ex2(x[i].x - ms[0]);
-        ps[1] += ex2(x[i].y - ms[1]);
-        ps[2] += ex2(x[i].z - ms[2]);
-        ps[3] += ex2(x[i].w - ms[3]);
-      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float om = __shfl_xor_sync(0xffffffffu, pm[j], 16);
-        const float os = __shfl_xor_sync(0xffffffffu, ps[j], 16);
-        lse2_merge(pm[j], ps[j], om, os);
+        pm[j] = fmaxf(pm[j], __shfl_xor_sync(0xffffffffu, pm[j], 8));
+        pm[j] = fmaxf(pm[j], __shfl_xor_sync(0xffffffffu, pm[j], 16));
       }
     } else if constexpr (SR == LT_MAXTROPICAL) {
       // (max, first arg-max row): rows ascend inside a thread, ties keep the lower row
@@ -193,11 +198,14 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
         if (v3 > pm[3]) { pm[3] = v3; ps[3] = __int_as_float(r0 + i); }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float om = __shfl_xor_sync(0xffffffffu, pm[j], 16);
-        const int oa = __shfl_xor_sync(0xffffffffu, __float_as_int(ps[j]), 16);
-        const int ma = __float_as_int(ps[j]);
-        if (om > pm[j] || (om == pm[j] && oa < ma)) { pm[j] = om; ps[j] = __int_as_float(oa); }
+      for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float om = __shfl_xor_sync(0xffffffffu, pm[j], o);
+          const int oa = __shfl_xor_sync(0xffffffffu, __float_as_int(ps[j]), o);
+          const int ma = __float_as_int(ps[j]);
+          if (om > pm[j] || (om == pm[j] && oa < ma)) { pm[j] = om; ps[j] = __int_as_float(oa); }
+        }
       }
     } else {
 #pragma unroll
@@ -208,124 +216,138 @@ lattice_forward_fast(const __grid_constant__ CUtensorMap tmap, const FastFwdPara
         pm[2] = fmaf(a[i], x[i].z, pm[2]); pm[3] = fmaf(a[i], x[i].w, pm[3]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pm[j] += __shfl_xor_sync(0xffffffffu, pm[j], 16);
+      for (int j = 0; j < 4; ++j) {
+        pm[j] += __shfl_xor_sync(0xffffffffu, pm[j], 8);
+        pm[j] += __shfl_xor_sync(0xffffffffu, pm[j], 16);
+      }
     }
-    if (lane < 16) {
-      *reinterpret_cast<float4*>(part_m + warp * kColsPerCta + cg * 4) =
-          make_float4(pm[0], pm[1], pm[2], pm[3]);
-      if constexpr (SR != LT_REAL)
-        *reinterpret_cast<float4*>(part_s + warp * kColsPerCta + cg * 4) =
-            make_float4(ps[0], ps[1], ps[2], ps[3]);
+    if (lane < 8) {
+      *reinterpret_cast<float4*>(pm_buf + warp * kCols + cg * 4) = make_float4(pm[0], pm[1], pm[2], pm[3]);
+      if constexpr (SR == LT_MAXTROPICAL)
+        *reinterpret_cast<float4*>(ps_buf + warp * kCols + cg * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
     }
-    __syncthreads();   // partials visible; every thread is done with this tile stage
+    group_sync(grp);   // #1: partial maxima visible; every thread holds its tile slice in registers
 
-    if (tid == 0 && t + NS < nf) {
+    if (gt == 0 && t + NS < nf) {               // the stage is free: refill it NS frames ahead
       const uint32_t bar = smem_u32(&bars[stage]);
       mbar_arrive_expect_tx(bar, kStageBytes);
       tma_load_2d(smem_u32(tiles) + stage * kStageBytes, &tmap, col0, (int)((bt0 + t + NS) * C), bar);
     }
 
-    if (in_tree) {                      // warps 0-7, warp-uniform
-      const int w0 = fpart * 4;
-      float m = part_m[w0 * kColsPerCta + fcol];
-      float s = (SR == LT_REAL) ? 0.f : part_s[w0 * kColsPerCta + fcol];
+    if constexpr (SR == LT_LOG) {
+      // exact column maximum, then ONE ex2 per arc
+      float4 mx = *reinterpret_cast<const float4*>(pm_buf + cg * 4);
 #pragma unroll
-      for (int w = 1; w < 4; ++w) {
-        const float om = part_m[(w0 + w) * kColsPerCta + fcol];
+      for (int w = 1; w < kGroupWarps; ++w) {
+        const float4 o = *reinterpret_cast<const float4*>(pm_buf + w * kCols + cg * 4);
+        mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
+      }
+      const float m0 = msafe(mx.x), m1 = msafe(mx.y), m2 = msafe(mx.z), m3 = msafe(mx.w);
+      ps[0] = ps[1] = ps[2] = ps[3] = 0.f;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        ps[0] += ex2(x[i].x - m0);
+        ps[1] += ex2(x[i].y - m1);
+        ps[2] += ex2(x[i].z - m2);
+        ps[3] += ex2(x[i].w - m3);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ps[j] += __shfl_xor_sync(0xffffffffu, ps[j], 8);
+        ps[j] += __shfl_xor_sync(0xffffffffu, ps[j], 16);
+      }
+      if (lane < 8)
+        *reinterpret_cast<float4*>(ps_buf + warp * kCols + cg * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+      group_sync(grp);   // #2: partial sums visible
+    }
+
+    // advance the ring; non-finaliser warps pull the next tile into registers now
+    if (++stage == NS) { stage = 0; parity ^= 1; }
+    if (!is_fin && t + 1 < nf) {
+      mbar_wait(smem_u32(&bars[stage]), parity);
+      const float* tile = tiles + (size_t)stage * (kStageBytes / 4);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i)
+        x[i] = *reinterpret_cast<const float4*>(tile + (size_t)(r0 + i) * kCols + cg * 4);
+    }
+
+    if (is_fin) {
+      float m = pm_buf[lane];
+      float s = (SR == LT_REAL) ? 0.f : ps_buf[lane];
+#pragma unroll
+      for (int w = 1; w < kGroupWarps; ++w) {
+        const float om = pm_buf[w * kCols + lane];
         if constexpr (SR == LT_LOG) {
-          lse2_merge(m, s, om, part_s[(w0 + w) * kColsPerCta + fcol]);
+          m = fmaxf(m, om);
+          s += ps_buf[w * kCols + lane];
         } else if constexpr (SR == LT_MAXTROPICAL) {
-          const int oa = __float_as_int(part_s[(w0 + w) * kColsPerCta + fcol]);
+          const int oa = __float_as_int(ps_buf[w * kCols + lane]);
           if (om > m || (om == m && oa < __float_as_int(s))) { m = om; s = __int_as_float(oa); }
         } else {
           m += om;
         }
       }
-#pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, m, o);
-        const float os = __shfl_xor_sync(0xffffffffu, s, o);
-        if constexpr (SR == LT_LOG) {
-          lse2_merge(m, s, om, os);
-        } else if constexpr (SR == LT_MAXTROPICAL) {
-          if (om > m || (om == m && __float_as_int(os) < __float_as_int(s))) { m = om; s = os; }
-        } else {
-          m += om;
-        }
+      const float ab = S::times(cur[q], to_dom<SR>(cblank));
+      const float xt = S::times(cur[V], to_dom<SR>(ctail));   // source row V (not in the TMA box)
+      float v;
+      if constexpr (SR == LT_LOG) {
+        lse2_merge(m, s, xt, xt == neg_inf() ? 0.f : 1.f);
+        v = log2_add_exp2(ab, msafe(m) + __log2f(s));
+      } else if constexpr (SR == LT_MAXTROPICAL) {
+        int am = __float_as_int(s);
+        if (xt > m) { m = xt; am = V; }
+        const bool take_blank = ab >= m;               // semirings.py:363
+        v = take_blank ? ab : m;
+        if (p.backptr) p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)am;
+      } else {
+        v = ab + (m + xt);
       }
-      if (is_fin) {
-        const float ab = S::times(cur[q], to_dom<SR>(cblank));
-        const float xt = S::times(cur[V], to_dom<SR>(ctail));   // source row V (not in the TMA box)
-        float v;
-        if constexpr (SR == LT_LOG) {
-          lse2_merge(m, s, xt, xt == neg_inf() ? 0.f : 1.f);
-          v = log2_add_exp2(ab, msafe(m) + __log2f(s));
-        } else if constexpr (SR == LT_MAXTROPICAL) {
-          int am = __float_as_int(s);
-          if (xt > m) { m = xt; am = V; }
-          const bool take_blank = ab >= m;               // semirings.py:363
-          v = take_blank ? ab : m;
-          if (p.backptr) p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)am;
-        } else {
-          v = ab + (m + xt);
-        }
-        xchg_store(nxt, q, v, &xbar[(t + 1) & 1], nrank);
+      xchg_store(nxt, q, v, &xbar[(t + 1) & 1], CL);
+      if (t + 1 < nf) {
+        mbar_wait(smem_u32(&bars[stage]), parity);
+        const float* tile = tiles + (size_t)stage * (kStageBytes / 4);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+          x[i] = *reinterpret_cast<const float4*>(tile + (size_t)(r0 + i) * kCols + cg * 4);
       }
     } else if (is_q0) {
       const float v = S::times(cur[0], to_dom<SR>(cblank));
       if constexpr (SR == LT_MAXTROPICAL) { if (p.backptr) p.backptr[(bt0 + t) * C] = (int16_t)-1; }
-      xchg_store(nxt, 0, v, &xbar[(t + 1) & 1], nrank);
+      xchg_store(nxt, 0, v, &xbar[(t + 1) & 1], CL);
     }
   }
   float* cur = alpha_buf + (nf & 1) * CP;
   if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
 
   // padding frames keep alpha (lattices.py:460-461) and are still recorded (:462)
-  if (is_fin || is_q0) {
+  if (active && (is_fin || is_q0)) {
     if (p.alphas)
       for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
     if (p.alpha_final) p.alpha_final[(size_t)b * C + q] = from_dom<SR>(cur[q]);
   }
-  if (rank == 0) {       // dist = (+)_c alpha_T[c]  (lattices.py:496)
-    float* red = part_m;
+  if (active && rank == 0 && warp == 1) {       // dist = (+)_c alpha_T[c]  (lattices.py:496)
     if constexpr (SR == LT_LOG) {
       float m = neg_inf();
-      for (int c = tid; c < C; c += kThreads) m = fmaxf(m, cur[c]);
-      red[tid] = m;
-      __syncthreads();
-      for (int s = kThreads >> 1; s > 0; s >>= 1) {
-        if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
-        __syncthreads();
-      }
-      const float ms = msafe(red[0]);
-      __syncthreads();
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, cur[c]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float ms = msafe(m);
       float s = 0.f;
-      for (int c = tid; c < C; c += kThreads) s += ex2(cur[c] - ms);      // log2 domain
-      red[tid] = s;
-      __syncthreads();
-      for (int st = kThreads >> 1; st > 0; st >>= 1) {
-        if (tid < st) red[tid] += red[tid + st];
-        __syncthreads();
-      }
-      if (tid == 0) p.dist[b] = (ms + __log2f(red[0])) * kLn2;
+      for (int c = lane; c < C; c += 32) s += ex2(cur[c] - ms);            // log2 domain
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) p.dist[b] = (ms + __log2f(s)) * kLn2;
     } else {
       float m = (SR == LT_REAL) ? 0.f : neg_inf();
-      for (int c = tid; c < C; c += kThreads) m = S::plus(m, cur[c]);
-      red[tid] = m;
-      __syncthreads();
-      for (int s = kThreads >> 1; s > 0; s >>= 1) {
-        if (tid < s) red[tid] = S::plus(red[tid], red[tid + s]);
-        __syncthreads();
-      }
-      if (tid == 0) p.dist[b] = red[0];
+      for (int c = lane; c < C; c += 32) m = S::plus(m, cur[c]);
+      for (int o = 16; o > 0; o >>= 1) m = S::plus(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) p.dist[b] = m;
     }
   }
   cluster_sync_all();
 }
 
 // ============================================================= backward (K2) ==
-struct FastBwdParams {
-  int V, B, T, stages;
+struct Fast2BwdParams {
+  int B, T, stages;
   const float* blank;
   const float* lexical;
   const int32_t* num_frames;
@@ -337,48 +359,55 @@ struct FastBwdParams {
   float* beta_final;
 };
 
-// One row (source state) of the frame handled by `NL` cooperating lanes:
-// x = lex + beta'[next]; Log: m, s, posterior = e * rs; Real: dot product.
-template <int SR, int VD>
-__global__ void __launch_bounds__(kThreads, 1)
-lattice_backward_fast(const FastBwdParams p) {
+template <int SR, int V, int G>
+__global__ void __launch_bounds__(kGroupThreads * G, G == 1 ? 2 : 1)
+lattice_backward_fast2(const Fast2BwdParams p) {
   using S = Sr<SR>;
-  constexpr int V = 64 * VD;
+  constexpr int CL = V / kCols;
   constexpr int C = V + 1;
-  constexpr int CH = 2 * VD;                    // float4 chunks per lane (8 lanes per row)
-  constexpr int kRows = 64;                     // rows per CTA (+ tail row V on the last rank)
+  constexpr int CH = V / 32;                    // float4 chunks per lane (8 lanes per row)
+  constexpr int kRows = kCols;                  // rows per CTA (+ tail row V on the last rank)
   constexpr uint32_t kSlabBytes = kRows * V * 4;
   constexpr uint32_t kStageBytes = kSlabBytes + V * 4;
   constexpr int BP = ((C + 3 + 3) & ~3) + 4;    // beta buffer: entry q at index 3 + q
-  extern __shared__ __align__(128) unsigned char bsmem[];
+  extern __shared__ __align__(128) unsigned char smem2[];
   const int NS = p.stages;
-  float* tiles = reinterpret_cast<float*>(bsmem);
-  float* beta_buf = reinterpret_cast<float*>(bsmem + (size_t)NS * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(beta_buf + 2 * BP);
 
-  const uint32_t nrank = VD;
+  const int tid = threadIdx.x;
+  const int grp = G == 1 ? 0 : tid >> 8;
+  const int gt = tid & (kGroupThreads - 1);
+  const int lane = gt & 31, warp = gt >> 5;
   const uint32_t rank = cluster_ctarank();
-  const bool last_rank = rank == nrank - 1;
-  const int b = blockIdx.x / VD;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool last_rank = rank == CL - 1;
+  const int cluster_id = blockIdx.x / CL;
+  const int b = cluster_id * G + grp;
+  const bool active = b < p.B;
+
+  float* tiles = reinterpret_cast<float*>(smem2) + (size_t)grp * NS * (kStageBytes / 4);
+  float* small = reinterpret_cast<float*>(smem2 + (size_t)G * NS * kStageBytes);
+  constexpr int kSmallFloats = 2 * BP + 2 * 16;
+  small += (size_t)grp * kSmallFloats;
+  float* beta_buf = small;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(beta_buf + 2 * BP);
+  uint64_t* xbar = bars + NS;
+
   const int sub = lane >> 3, sl = lane & 7;     // row within the warp, lane within the row
-  const int row = warp * 4 + sub;               // local row 0..63
+  const int row = warp * 4 + sub;               // local row 0..31
   const int prow = rank * kRows + row;          // source state
-  const int nf = max(0, min(p.num_frames[b], p.T));
-  const size_t bt0 = (size_t)b * p.T;
-  const float logz = p.dist[b];
+  const int nf = active ? max(0, min(p.num_frames[b], p.T)) : 0;
+  const size_t bt0 = (size_t)(active ? b : 0) * p.T;
+  const float logz = active ? p.dist[b] : 0.f;
   const float logz2 = logz * kLog2e;            // Log: everything on chip is in log2 units
-  const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
+  const float gscale = (active && p.grad_dist) ? p.grad_dist[b] : 1.f;
   const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
   const uint32_t stage_tx = last_rank ? kStageBytes : kSlabBytes;
 
-  uint64_t* xbar = bars + NS;       // xbar[i]: "beta buffer i has received all C entries"
-  if (tid == 0) {
+  if (gt == 0) {
     for (int s = 0; s < NS + 2; ++s) mbar_init(smem_u32(&bars[s]), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  for (int c = tid; c < 2 * BP; c += kThreads) beta_buf[c] = S::one();   // lattices.py:789-790
+  for (int c = gt; c < 2 * BP; c += kGroupThreads) beta_buf[c] = S::one();   // lattices.py:789-790
   __syncthreads();
   cluster_sync_all();
 
@@ -393,19 +422,22 @@ lattice_backward_fast(const FastBwdParams p) {
     if (last_rank)
       bulk_load_1d(dst + kSlabBytes, p.lexical + (bt0 + t) * (size_t)C * V + (size_t)V * V, V * 4, bar);
   };
-  if (tid == 0)
+  if (gt == 0)
     for (int it = 0; it < NS && it < nf; ++it) issue(it);
 
   // padding frames: zero gradients (lattices.py:775-779)
-  for (int t = nf; t < p.T; ++t) {
-    float4* gl = reinterpret_cast<float4*>(p.grad_lexical + (bt0 + t) * (size_t)C * V +
-                                           (size_t)rank * kRows * V);
-    for (int i = tid; i < kRows * V / 4; i += kThreads) stg_stream4(reinterpret_cast<float*>(gl + i), make_float4(0, 0, 0, 0));
-    if (tid < kRows) p.grad_blank[(bt0 + t) * C + rank * kRows + tid] = 0.f;
-    if (last_rank) {
-      float* tail = p.grad_lexical + (bt0 + t) * (size_t)C * V + (size_t)V * V;
-      for (int i = tid; i < V; i += kThreads) tail[i] = 0.f;
-      if (tid == 0) p.grad_blank[(bt0 + t) * C + V] = 0.f;
+  if (active) {
+    for (int t = nf; t < p.T; ++t) {
+      float4* gl = reinterpret_cast<float4*>(p.grad_lexical + (bt0 + t) * (size_t)C * V +
+                                             (size_t)rank * kRows * V);
+      for (int i = gt; i < kRows * V / 4; i += kGroupThreads)
+        stg_stream4(reinterpret_cast<float*>(gl + i), make_float4(0, 0, 0, 0));
+      if (gt < kRows) p.grad_blank[(bt0 + t) * C + rank * kRows + gt] = 0.f;
+      if (last_rank) {
+        float* tail = p.grad_lexical + (bt0 + t) * (size_t)C * V + (size_t)V * V;
+        for (int i = gt; i < V; i += kGroupThreads) tail[i] = 0.f;
+        if (gt == 0) p.grad_blank[(bt0 + t) * C + V] = 0.f;
+      }
     }
   }
 
@@ -420,19 +452,19 @@ lattice_backward_fast(const FastBwdParams p) {
     if (tail_owner) { n_talpha = p.alphas[o + V]; n_tblank = ldg_stream(p.blank + o + V); }
   }
 
+  int stage = 0;
+  uint32_t parity = 0;
   for (int it = 0; it < nf; ++it) {
     const int t = nf - 1 - it;
-    const int stage = it % NS;
-    const uint32_t parity = (it / NS) & 1;
     float* beta = beta_buf + (it & 1) * BP;          // beta_{t+1}; entry q at beta[3 + q]
     float* nxt = beta_buf + ((it + 1) & 1) * BP;
     if (it > 0) {
       // every row of the previous frame has been reduced cluster-wide: beta is
       // complete and the tile stage of iteration it-1 is free for the next TMA
       mbar_wait(smem_u32(&xbar[it & 1]), ((it - 1) >> 1) & 1);
-      if (tid == 0 && it - 1 + NS < nf) issue(it - 1 + NS);
+      if (gt == 0 && it - 1 + NS < nf) issue(it - 1 + NS);
     }
-    if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), C * 4);
+    if (gt == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), C * 4);
     const float c_alpha = n_alpha, c_blank = n_blank, c_talpha = n_talpha, c_tblank = n_tblank;
     if (t > 0) {
       const size_t o = (bt0 + t - 1) * C;
@@ -441,6 +473,7 @@ lattice_backward_fast(const FastBwdParams p) {
     }
     mbar_wait(smem_u32(&bars[stage]), parity);
     const float* tile = tiles + (size_t)stage * (kStageBytes / 4);
+    if (++stage == NS) { stage = 0; parity ^= 1; }
     const float* bnext = beta + 4;                     // bnext[y] = beta'[1 + y]
     float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
     float* gb = p.grad_blank + (bt0 + t) * C;
@@ -502,7 +535,7 @@ lattice_backward_fast(const FastBwdParams p) {
         if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
         else gb[prow] = gscale * c_alpha * bp;
         xchg_store(nxt, 3 + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
-                   &xbar[(it + 1) & 1], nrank);
+                   &xbar[(it + 1) & 1], CL);
       }
     }
     if (last_rank && warp == 0) {          // tail row: source state V, all 32 lanes
@@ -551,16 +584,16 @@ lattice_backward_fast(const FastBwdParams p) {
         if constexpr (SR == LT_LOG) gb[V] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
         else gb[V] = gscale * c_talpha * bp;
         xchg_store(nxt, 3 + V, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
-                   &xbar[(it + 1) & 1], nrank);
+                   &xbar[(it + 1) & 1], CL);
       }
     }
   }
   float* beta = beta_buf + (nf & 1) * BP;
   if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
-  if (p.beta_final) {
-    if (tid < kRows)
-      p.beta_final[(size_t)b * C + rank * kRows + tid] = from_dom<SR>(beta[3 + rank * kRows + tid]);
-    if (last_rank && tid == 0) p.beta_final[(size_t)b * C + V] = from_dom<SR>(beta[3 + V]);
+  if (active && p.beta_final) {
+    if (gt < kRows)
+      p.beta_final[(size_t)b * C + rank * kRows + gt] = from_dom<SR>(beta[3 + rank * kRows + gt]);
+    if (last_rank && gt == 0) p.beta_final[(size_t)b * C + V] = from_dom<SR>(beta[3 + V]);
   }
   cluster_sync_all();
 }
@@ -571,7 +604,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn2() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* sym = nullptr;
@@ -584,12 +617,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 template <typename KernelT, typename... Args>
-static int launch_fast(KernelT kernel, int grid, size_t smem, int cluster, cudaStream_t stream,
-                       Args... args) {
+static int launch_fast2(KernelT kernel, int grid, int threads, size_t smem, int cluster,
+                        cudaStream_t stream, Args... args) {
   LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cluster > 8)
+    LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -604,12 +639,12 @@ static int launch_fast(KernelT kernel, int grid, size_t smem, int cluster, cudaS
   return LT_OK;
 }
 
-constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kSmemBudget2 = 227 * 1024;
 
 }  // namespace
 
-bool lattice_fast_supported(const NGram& g, int k, unsigned flags, const void* lexical) {
-  if (flags & LT_FLAG_FORCE_GENERIC) return false;
+bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical) {
+  if (flags & (LT_FLAG_FORCE_GENERIC | LT_FLAG_FAST_V1)) return false;
   if ((flags >> LT_FLAG_CLUSTER_SHIFT) & 0xf) return false;   // explicit cluster size => generic
   if (k >= 1 || g.n != 1) return false;
   if (g.V % 64 != 0 || g.V > 256) return false;
@@ -617,72 +652,95 @@ bool lattice_fast_supported(const NGram& g, int k, unsigned flags, const void* l
   return true;
 }
 
-int lattice_forward_fast_launch(int semiring, const NGram& g, const FwdParams& base,
-                                cudaStream_t stream) {
-  const int V = g.V, C = g.C, VD = V / 64;
-  EncodeTiledFn encode = get_encode_fn();
+// G = 1: one 256-thread group per CTA, TWO CTAs per SM (the hardware co-schedules CTAs of
+// different utterances on an SM; 33 clusters of 8 are co-resident on a B200, against 15 when
+// a CTA fills the SM).  G = 2 (LT_FLAG_PAIR_CTA): both groups in one 512-thread CTA.
+static int shared_budget(int G) { return G == 1 ? 113 * 1024 : (int)kSmemBudget2; }
+
+int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
+                                 unsigned flags, cudaStream_t stream) {
+  const int V = g.V, C = g.C, CL = V / kCols;
+  const int G = (flags & LT_FLAG_PAIR_CTA) ? 2 : 1;
+  EncodeTiledFn encode = get_encode_fn2();
   if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
   CUtensorMap tmap;
   const cuuint64_t rows = (cuuint64_t)base.B * base.T * C;
   cuuint64_t dims[2] = {(cuuint64_t)V, rows};
   cuuint64_t strides[1] = {(cuuint64_t)V * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kColsPerCta, (cuuint32_t)V};
+  cuuint32_t box[2] = {(cuuint32_t)kCols, (cuuint32_t)V};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base.lexical),
                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return LT_ERR_CUDA; }
-  const size_t stage = (size_t)V * kColsPerCta * 4;
-  const size_t fixed = sizeof(float) * (2 * ((C + 3) & ~3) + 2 * kWarps * kColsPerCta) + 8 * 16 + 256;
-  int stages = (int)((kSmemBudget - fixed) / stage);
+  const size_t stage = (size_t)V * kCols * 4;
+  const int CP = (C + 3) & ~3;
+  const size_t small = sizeof(float) * (2 * CP + 4 * kGroupWarps * kCols + 2 * 16);
+  int stages = (int)((shared_budget(G) - G * small - 256) / (G * stage));
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("fast forward: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-  const size_t smem = stage * stages + fixed;
-  FastFwdParams p = {};
-  p.V = V; p.B = base.B; p.T = base.T; p.stages = stages;
+  const size_t smem = G * (stage * stages + small);
+  Fast2FwdParams p = {};
+  p.B = base.B; p.T = base.T; p.stages = stages;
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alpha_init = base.alpha_init; p.dist = base.dist; p.alphas = base.alphas;
   p.alpha_final = base.alpha_final; p.backptr = base.backptr;
-  const int grid = base.B * VD;
-#define LT_FWD(SR)                                                                             \
-  switch (VD) {                                                                                \
-    case 1: return launch_fast(lattice_forward_fast<SR, 1>, grid, smem, 1, stream, tmap, p);   \
-    case 2: return launch_fast(lattice_forward_fast<SR, 2>, grid, smem, 2, stream, tmap, p);   \
-    case 3: return launch_fast(lattice_forward_fast<SR, 3>, grid, smem, 3, stream, tmap, p);   \
-    default: return launch_fast(lattice_forward_fast<SR, 4>, grid, smem, 4, stream, tmap, p);  \
+  const int grid = ((base.B + G - 1) / G) * CL;
+  const int threads = kGroupThreads * G;
+#define LT_FWD2V(SR, VV)                                                                          \
+  return G == 1 ? launch_fast2(lattice_forward_fast2<SR, VV, 1>, grid, threads, smem, CL, stream, \
+                               tmap, p)                                                           \
+                : launch_fast2(lattice_forward_fast2<SR, VV, 2>, grid, threads, smem, CL, stream, \
+                               tmap, p);
+#define LT_FWD2(SR)                  \
+  switch (V) {                       \
+    case 64: LT_FWD2V(SR, 64)        \
+    case 128: LT_FWD2V(SR, 128)      \
+    case 192: LT_FWD2V(SR, 192)      \
+    default: LT_FWD2V(SR, 256)       \
   }
-  if (semiring == LT_LOG) { LT_FWD(LT_LOG) }
-  if (semiring == LT_MAXTROPICAL) { LT_FWD(LT_MAXTROPICAL) }
-  LT_FWD(LT_REAL)
-#undef LT_FWD
+  if (semiring == LT_LOG) { LT_FWD2(LT_LOG) }
+  if (semiring == LT_MAXTROPICAL) { LT_FWD2(LT_MAXTROPICAL) }
+  LT_FWD2(LT_REAL)
+#undef LT_FWD2
+#undef LT_FWD2V
 }
 
-int lattice_backward_fast_launch(int semiring, const NGram& g, const BwdParams& base,
-                                 cudaStream_t stream) {
-  const int V = g.V, C = g.C, VD = V / 64;
-  const size_t stage = (size_t)64 * V * 4 + (size_t)V * 4;
-  const size_t fixed = sizeof(float) * 2 * ((((C + 6) & ~3) + 4)) + 8 * 16 + 256;
-  int stages = (int)((kSmemBudget - fixed) / stage);
+int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,
+                                  unsigned flags, cudaStream_t stream) {
+  const int V = g.V, C = g.C, CL = V / kCols;
+  const int G = (flags & LT_FLAG_PAIR_CTA) ? 2 : 1;
+  const size_t stage = (size_t)kCols * V * 4 + (size_t)V * 4;
+  const int BP = ((C + 6) & ~3) + 4;
+  const size_t small = sizeof(float) * (2 * BP + 2 * 16);
+  int stages = (int)((shared_budget(G) - G * small - 256) / (G * stage));
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("fast backward: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-  const size_t smem = stage * stages + fixed;
-  FastBwdParams p = {};
-  p.V = V; p.B = base.B; p.T = base.T; p.stages = stages;
+  const size_t smem = G * (stage * stages + small);
+  Fast2BwdParams p = {};
+  p.B = base.B; p.T = base.T; p.stages = stages;
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alphas = base.alphas; p.dist = base.dist; p.grad_dist = base.grad_dist;
   p.grad_blank = base.grad_blank; p.grad_lexical = base.grad_lexical; p.beta_final = base.beta_final;
-  const int grid = base.B * VD;
-#define LT_BWD(SR)                                                                         \
-  switch (VD) {                                                                            \
-    case 1: return launch_fast(lattice_backward_fast<SR, 1>, grid, smem, 1, stream, p);    \
-    case 2: return launch_fast(lattice_backward_fast<SR, 2>, grid, smem, 2, stream, p);    \
-    case 3: return launch_fast(lattice_backward_fast<SR, 3>, grid, smem, 3, stream, p);    \
-    default: return launch_fast(lattice_backward_fast<SR, 4>, grid, smem, 4, stream, p);   \
+  const int grid = ((base.B + G - 1) / G) * CL;
+  const int threads = kGroupThreads * G;
+#define LT_BWD2V(SR, VV)                                                                           \
+  return G == 1 ? launch_fast2(lattice_backward_fast2<SR, VV, 1>, grid, threads, smem, CL, stream, \
+                               p)                                                                  \
+                : launch_fast2(lattice_backward_fast2<SR, VV, 2>, grid, threads, smem, CL, stream, \
+                               p);
+#define LT_BWD2(SR)                  \
+  switch (V) {                       \
+    case 64: LT_BWD2V(SR, 64)        \
+    case 128: LT_BWD2V(SR, 128)      \
+    case 192: LT_BWD2V(SR, 192)      \
+    default: LT_BWD2V(SR, 256)       \
   }
-  if (semiring == LT_LOG) { LT_BWD(LT_LOG) }
-  LT_BWD(LT_REAL)
-#undef LT_BWD
+  if (semiring == LT_LOG) { LT_BWD2(LT_LOG) }
+  LT_BWD2(LT_REAL)
+#undef LT_BWD2
+#undef LT_BWD2V
 }
 
 }  // namespace lt

@@ -86,13 +86,20 @@ int lattice_forward_fast_launch(int semiring, const NGram& g, const FwdParams& b
                                 cudaStream_t stream);
 int lattice_backward_fast_launch(int semiring, const NGram& g, const BwdParams& base,
                                  cudaStream_t stream);
+// second generation (lattice_fast2.cu): two utterances interleaved per cluster
+bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
+                                 unsigned flags, cudaStream_t stream);
+int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,
+                                  unsigned flags, cudaStream_t stream);
 int viterbi_launch(const VitParams& base, cudaStream_t stream);
 int string_gather_launch(int V, int C, const float* blank, const float* lexical,
                          const int32_t* states, const int32_t* labels, int B, int T, int U1,
                          float* blank_w, float* lexical_w, cudaStream_t stream);
 int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
-                          float scale, float* gblank, float* glex, cudaStream_t stream);
+                          float scale, const float* utt_scale, float* gblank, float* glex,
+                          cudaStream_t stream);
 int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
                        int32_t* next_labels, cudaStream_t stream);
 int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);

@@ -38,10 +38,13 @@ __global__ void string_scatter_kernel(int V, int C, const float* __restrict__ gb
                                       const float* __restrict__ glw,
                                       const int32_t* __restrict__ states,
                                       const int32_t* __restrict__ labels, int T, int U1,
-                                      float scale, float* __restrict__ gblank,
+                                      float scale, const float* __restrict__ utt_scale,
+                                      float* __restrict__ gblank,
                                       float* __restrict__ glex) {
   const size_t bt = blockIdx.x;
   const int b = (int)(bt / T);
+  if (utt_scale) scale *= utt_scale[b];
+  if (scale == 0.f) return;
   float* bl = gblank + bt * C;
   float* lx = glex + bt * (size_t)C * V;
   for (int u = threadIdx.x; u < U1; u += blockDim.x) {
@@ -262,10 +265,11 @@ int string_gather_launch(int V, int C, const float* blank, const float* lexical,
 
 int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
-                          float scale, float* gblank, float* glex, cudaStream_t stream) {
+                          float scale, const float* utt_scale, float* gblank, float* glex,
+                          cudaStream_t stream) {
   if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
   string_scatter_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
-      V, C, gbw, glw, states, labels, T, U1, scale, gblank, glex);
+      V, C, gbw, glw, states, labels, T, U1, scale, utt_scale, gblank, glex);
   LT_LAUNCHED();
   return LT_OK;
 }

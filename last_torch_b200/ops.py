@@ -96,7 +96,9 @@ class SemiringSum(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 
 def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_levels,
-                         want_backptr, alpha_init=None):
+                         want_backptr, alpha_init=None, stream=None):
+  """Buffers are allocated on the current stream; the kernel is enqueued on
+  `stream` when one is given (the caller orders it against the current stream)."""
   B, T, C = blank.shape
   dev = blank.device
   dist = torch.empty([B], dtype=torch.float32, device=dev)
@@ -110,7 +112,7 @@ def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_le
     backptr = torch.empty([B, T, max(k, 1), C], dtype=torch.int16, device=dev)
     if fld:
       termptr = torch.empty([B, T, C], dtype=torch.uint8, device=dev)
-  with torch.cuda.device(dev):
+  with torch.cuda.device(dev), torch.cuda.stream(stream):       # stream(None) is a no-op
     N.check(N.lib().lt_lattice_forward(
         sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alpha_init),
         N.ptr(dist), N.ptr(alphas), N.ptr(alpha_final), N.ptr(levels), N.ptr(backptr),
@@ -225,12 +227,28 @@ def _side_stream(device):
     _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
   return _SIDE_STREAMS[key]
 
+
+_HP_STREAMS = {}
+
+
+def _hp_stream(device):
+  """High-priority stream for the HBM-bound lattice kernel while numerator kernels
+  run beside it: its CTAs fill an SM exactly (two CTAs x 256 threads x 128
+  registers), so they must be placed BEFORE the small kernels grab slots --
+  otherwise a cluster waits for a numerator CTA to retire and the whole
+  recursion ends late."""
+  key = (device.type, device.index)
+  if key not in _HP_STREAMS:
+    _HP_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+  return _HP_STREAMS[key]
+
 def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels,
-                        need_grad, side=None):
+                        need_grad, side=None, ready=None):
   """gather + string forward.  With `side` (a torch.cuda.Stream) the two kernels
-  are enqueued there (after everything already on the current stream); the
-  caller joins with current_stream().wait_stream(side).  Buffers are always
-  allocated on the current stream, so the caching allocator stays correct."""
+  are enqueued there, after the event `ready` (or, without one, after everything
+  already on the current stream); the caller joins with
+  current_stream().wait_stream(side).  Buffers are always allocated on the
+  current stream, so the caching allocator stays correct."""
   B, T, _ = blank.shape
   U1 = states.shape[-1]
   dev = blank.device
@@ -243,7 +261,10 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
              if need_grad and sr == N.MAXTROPICAL else None)
   with torch.cuda.device(dev):
     if side is not None:
-      side.wait_stream(torch.cuda.current_stream(dev))
+      if ready is not None:
+        side.wait_event(ready)
+      else:
+        side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):           # stream(None) is a no-op
       L = N.lib()
       N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
@@ -256,15 +277,17 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
 
 
 def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist, g_dist,
-                     side=None):
+                     side=None, ready=None, out=None):
   """Numerator posteriors on the label lattice: (grad_blank_w, grad_lexical_w)."""
   B, T, U1 = bw.shape
   dev = bw.device
-  gbw = torch.empty_like(bw)
-  glw = torch.empty_like(lw)
+  gbw, glw = out if out is not None else (torch.empty_like(bw), torch.empty_like(lw))
   with torch.cuda.device(dev):
     if side is not None:
-      side.wait_stream(torch.cuda.current_stream(dev))
+      if ready is not None:
+        side.wait_event(ready)
+      else:
+        side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
       N.check(N.lib().lt_string_backward(
           sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels), B, T, U1,
@@ -273,14 +296,14 @@ def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dis
   return gbw, glw
 
 
-def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl):
-  """grad_dense[b, t, states[u], next_labels[u] - 1] += scale * grad_w[b, t, u]."""
+def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scale=None):
+  """grad_dense[b, t, states[u], next_labels[u] - 1] += scale * utt_scale[b] * grad_w[b, t, u]."""
   B, T, U1 = gbw.shape
   dev = gbw.device
   with torch.cuda.device(dev):
     N.check(N.lib().lt_string_scatter_add(
         V, C, N.ptr(gbw), N.ptr(glw), N.ptr(states), N.ptr(next_labels), B, T, U1, float(scale),
-        N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
+        N.ptr(utt_scale), N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
 
 
 class StringForward(torch.autograd.Function):
@@ -314,9 +337,13 @@ class StringForward(torch.autograd.Function):
 class LatticeLoss(torch.autograd.Function):
   """loss = logZ - numerator (lattices.py:131-183) as ONE autograd node.
 
-  Forward: K1 (Log) over the dense lattice + K3 over the label lattice.
+  Forward: K1 (Log) over the dense lattice on a high-priority stream; beside it,
+  on a side stream, the whole numerator: gather, K3 forward and (when gradients
+  are needed) K3 backward, i.e. the UNSCALED numerator posteriors -- the label
+  lattice is tiny, so its three kernels fit under the HBM-bound K1.
   Backward: K2 writes g * (arc posteriors) straight into the weight-gradient
-  buffers, then the numerator posteriors are scattered in with scale -1.
+  buffers; the stored numerator posteriors are then scattered in, weighted by
+  the upstream gradient of each utterance.
   """
 
   @staticmethod
@@ -324,43 +351,53 @@ class LatticeLoss(torch.autograd.Function):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
     need_grad = any(ctx.needs_input_grad[:2])
-    # the numerator (tiny, latency-bound) runs on a side stream under the
-    # HBM-bound denominator kernel
-    side = _side_stream(blank.device)
+    dev = blank.device
+    cur = torch.cuda.current_stream(dev)
+    side, hp = _side_stream(dev), _hp_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    hp.wait_event(ready)
+    # NOTE: every buffer handed to a kernel on `hp` / `side` must stay referenced until the
+    # joins below -- a tensor dropped earlier returns to the current stream's pool and the
+    # next allocation may alias it while the other stream still writes to it.
+    fwd = _lattice_forward_raw(
+        N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
+        want_backptr=False, stream=hp)
+    log_z, alphas, _, levels, _, _ = fwd
     num, bw, lw, s_alphas, _ = _string_forward_raw(
         N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
-        side=side)
-    log_z, alphas, _, levels, _, _ = _lattice_forward_raw(
-        N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
-        want_backptr=False)
-    torch.cuda.current_stream(blank.device).wait_stream(side)
+        side=side, ready=ready)
+    gbw = glw = None
+    if need_grad:
+      # posteriors of the label lattice with unit upstream gradient (scaled in backward)
+      gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
+                                  None, side=side, ready=ready)
+    cur.wait_stream(hp)
+    cur.wait_stream(side)
+    del fwd
     ctx.geom = (V, n, k, flags)
-    ctx.save_for_backward(blank, lexical, num_frames, log_z, alphas, levels, bw, lw, num_labels,
-                          s_alphas, num, states, next_labels)
+    ctx.save_for_backward(blank, lexical, num_frames, log_z, alphas, levels, gbw, glw, states,
+                          next_labels)
     ctx.mark_non_differentiable(alphas)
     return log_z - num, log_z, num, alphas
 
   @staticmethod
   def backward(ctx, g_loss, g_logz, g_num, _g_alphas):
     V, n, k, flags = ctx.geom
-    (blank, lexical, num_frames, log_z, alphas, levels, bw, lw, num_labels, s_alphas, num, states,
+    (blank, lexical, num_frames, log_z, alphas, levels, gbw, glw, states,
      next_labels) = ctx.saved_tensors
     B, T, C = blank.shape
     dev = blank.device
     g_den = g_loss if g_logz is None else g_loss + g_logz
     g_numr = -g_loss if g_num is None else g_num - g_loss
-    g_den = N.require_cuda(g_den, 'grad')
-    g_numr = N.require_cuda(g_numr, 'grad')
+    g_den = N.require_cuda(g_den, 'grad').contiguous()
+    g_numr = N.require_cuda(g_numr, 'grad').contiguous()
     gb = torch.empty_like(blank)
     gl = torch.empty_like(lexical)
-    side = _side_stream(dev)
-    gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
-                                g_numr, side=side)
     with torch.cuda.device(dev):
       N.check(N.lib().lt_lattice_backward(
           N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
           N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None, flags,
           N.stream_ptr(dev)), 'lt_lattice_backward')
-      torch.cuda.current_stream(dev).wait_stream(side)
-    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl)
+    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr)
     return gb, gl, None, None, None, None, None, None, None, None

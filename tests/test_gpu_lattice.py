@@ -18,7 +18,9 @@ from oracle import lattice_oracle as O
 pytestmark = pytest.mark.gpu
 
 SR = ['Real', 'Log', 'MaxTropical']
-CLUSTER_FLAGS = [0, 1 << 8, 2 << 8, 4 << 8]
+FAST_V1 = 2      # LT_FLAG_FAST_V1: first-generation fast path (one utterance per cluster)
+PAIR_CTA = 4     # LT_FLAG_PAIR_CTA: second generation with two utterances per 512-thread CTA
+CLUSTER_FLAGS = [0, FAST_V1, 1 << 8, 2 << 8, 4 << 8]
 
 
 def _lt():
@@ -151,7 +153,7 @@ def test_fast_path_ragged_and_empty_utterances():
   o_loss, o_gb, o_gl = O.lattice_loss_and_grads(
       tab64[..., 0].copy(), tab64[..., 1:].copy(), nf, labels, nl, O.FullNGram(vocab, ctx))
   outs = []
-  for flags in [0, 1]:            # 0: fast path, 1: LT_FLAG_FORCE_GENERIC
+  for flags in [1, 0, FAST_V1, PAIR_CTA]:   # 1: LT_FLAG_FORCE_GENERIC, 0 / 2 / 4: fast paths
     table = cuda(table_np).requires_grad_()
     lattice = make_lattice(vocab, ctx, -1, table, flags)
     loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
@@ -161,11 +163,12 @@ def test_fast_path_ragged_and_empty_utterances():
     npt.assert_allclose(gt.cpu().numpy()[..., 0], o_gb, rtol=1e-4, atol=1e-5)
     npt.assert_allclose(gt.cpu().numpy()[..., 1:], o_gl, rtol=1e-4, atol=1e-5)
     outs.append((loss.detach().cpu().numpy(), gt.cpu().numpy()))
-  npt.assert_allclose(outs[0][0], outs[1][0], rtol=2e-6, atol=2e-6)
-  npt.assert_allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=2e-6)
+  for other in outs[1:]:
+    npt.assert_allclose(outs[0][0], other[0], rtol=2e-6, atol=2e-6)
+    npt.assert_allclose(outs[0][1], other[1], rtol=1e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize('flags', [0, 1 << 8, 4 << 8, 8 << 8])
+@pytest.mark.parametrize('flags', [0, FAST_V1, 1 << 8, 4 << 8, 8 << 8])
 @pytest.mark.parametrize('case', ORACLE_CASES)
 def test_loss_and_grads_vs_oracle(case, flags):
   seed, b, t, vocab, ctx, k, u, scale = case
@@ -252,6 +255,92 @@ def test_viterbi_vs_oracle(case):
                                              cache=None)
   npt.assert_array_equal(labels.cpu(), o_labels)
   npt.assert_allclose(weights.cpu(), o_dist, rtol=1e-6)
+
+
+@pytest.mark.parametrize('flags', [0, FAST_V1, PAIR_CTA])
+@pytest.mark.parametrize('vocab', [64, 128, 192, 256])
+def test_fast_path_generations(vocab, flags):
+  """Both generations of the TMA / cluster fast path on every supported vocabulary,
+  with an odd batch (one idle utterance slot in the last pair), ragged lengths and
+  -inf arcs: Log / Real values, Log loss + gradients, MaxTropical distances and the
+  bit-exact Viterbi one-hot gradient against the oracle."""
+  lt = _lt()
+  b, t, ctx, u = 3, 11, 1, 5
+  rng = np.random.RandomState(vocab + flags)
+  c = 1 + vocab
+  table_np = (rng.randn(b, t, c, 1 + vocab) * 2.0).astype(np.float32)
+  drop = rng.rand(b, t, c, 1 + vocab) < 0.05
+  drop[..., 0] = False
+  table_np[drop] = -np.inf
+  nf = np.array([11, 4, 9])
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = np.array([5, 2, 3])
+  octx = O.FullNGram(vocab, ctx)
+  tab64 = table_np.astype(np.float64)
+  blank, lex = np.ascontiguousarray(tab64[..., 0]), np.ascontiguousarray(tab64[..., 1:])
+  with np.errstate(all='ignore'):
+    o_loss, o_gb, o_gl = O.lattice_loss_and_grads(blank, lex, nf, labels, nl, octx)
+    o_vd, o_vgb, o_vgl, _ = O.viterbi(table_np[..., 0].copy(), table_np[..., 1:].copy(), nf, octx,
+                                      0, True)
+  table = cuda(table_np).requires_grad_()
+  lattice = make_lattice(vocab, ctx, -1, table, flags)
+  loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                 num_labels=cuda(nl), cache=None)
+  fin = np.isfinite(o_loss)
+  npt.assert_array_equal(torch.isfinite(loss).cpu().numpy(), fin)
+  npt.assert_allclose(loss.detach().cpu().numpy()[fin], o_loss[fin], rtol=1e-5, atol=1e-5)
+  (gt,) = torch.autograd.grad(
+      torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum(), table)
+  gt = gt.cpu().numpy()
+  assert np.all(np.isfinite(gt))
+  assert np.all(gt[drop] == 0)
+  npt.assert_allclose(gt[fin][..., 0], o_gb[fin], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(gt[fin][..., 1:], o_gl[fin], rtol=1e-4, atol=1e-5)
+  vd, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                           semiring=lt.semirings.MaxTropical)
+  npt.assert_allclose(vd.detach().cpu(), o_vd, rtol=1e-6)
+  (gv,) = torch.autograd.grad(vd.sum(), table)
+  npt.assert_array_equal(gv.cpu().numpy()[..., 0], o_vgb)
+  npt.assert_array_equal(gv.cpu().numpy()[..., 1:], o_vgl)
+  # Real semiring on probabilities
+  prob = (np.exp(np.clip(table_np, -40, 5) * 0.25) / (1 + vocab)).astype(np.float32)
+  p64 = prob.astype(np.float64)
+  o_rd, o_ra = O.lattice_forward(np.ascontiguousarray(p64[..., 0]),
+                                 np.ascontiguousarray(p64[..., 1:]), nf, octx, O.REAL, 0, True)
+  ptab = cuda(prob).requires_grad_()
+  rl = make_lattice(vocab, ctx, -1, ptab, flags)
+  rd, ra = rl._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                       semiring=lt.semirings.Real)
+  npt.assert_allclose(rd.detach().cpu(), o_rd, rtol=1e-5)
+  npt.assert_allclose(ra.cpu(), o_ra, rtol=2e-5, atol=1e-30)
+  # d(dist)/d(weights) in the Real semiring against a generic-kernel run
+  (gr,) = torch.autograd.grad(rd.sum(), ptab)
+  ptab2 = cuda(prob).requires_grad_()
+  rd2, _ = make_lattice(vocab, ctx, -1, ptab2, 1)._forward(
+      cache=None, frames=frames_for(b, t), num_frames=cuda(nf), semiring=lt.semirings.Real)
+  (gr2,) = torch.autograd.grad(rd2.sum(), ptab2)
+  npt.assert_allclose(gr.cpu(), gr2.cpu(), rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize('flags', [0, FAST_V1, PAIR_CTA])
+def test_fast_path_ties(flags):
+  """All-equal weights on a fast-path shape: blank beats lexical, lowest source
+  row wins inside the reduction (semirings.py:363, :382)."""
+  b, t, vocab, ctx = 2, 6, 64, 1
+  c = 1 + vocab
+  tab = np.zeros([b, t, c, 1 + vocab], np.float32)
+  tab[1, :, :, 0] = -1.0        # utterance 1: lexical arcs beat blank, all tie with each other
+  nf = np.array([6, 4])
+  o_vd, o_gb, o_gl, _ = O.viterbi(tab[..., 0].copy(), tab[..., 1:].copy(), nf,
+                                  O.FullNGram(vocab, ctx), 0, True)
+  table = cuda(tab).requires_grad_()
+  lattice = make_lattice(vocab, ctx, -1, table, flags)
+  dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                             semiring=_lt().semirings.MaxTropical)
+  npt.assert_array_equal(dist.detach().cpu(), o_vd)
+  (gd,) = torch.autograd.grad(dist.sum(), table)
+  npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
+  npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
 
 
 def test_viterbi_ties_match_reference_rules():
