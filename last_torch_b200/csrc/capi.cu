@@ -103,6 +103,8 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
   if (T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical))
     return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
+  if (T > 0 && lattice_cols_supported(g, max_expansions, flags, lexical))
+    return lattice_forward_cols_launch(semiring, g, max_expansions, p, (cudaStream_t)stream);
   if (T > 0 && lattice_fast_supported(g, max_expansions, flags, lexical))
     return lattice_forward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,

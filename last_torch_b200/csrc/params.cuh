@@ -92,6 +92,10 @@ int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& 
                                  unsigned flags, cudaStream_t stream);
 int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,
                                   unsigned flags, cudaStream_t stream);
+// thread-per-column TMA path for context_size >= 2 (lattice_cols.cu), forward only
+bool lattice_cols_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdParams& base,
+                                cudaStream_t stream);
 int viterbi_launch(const VitParams& base, cudaStream_t stream);
 int string_gather_launch(int V, int C, const float* blank, const float* lexical,
                          const int32_t* states, const int32_t* labels, int B, int T, int U1,

@@ -137,6 +137,10 @@ ORACLE_CASES = [
     (10, 3, 20, 128, 1, -1, 10, 1.0),    # TMA fast path, cluster of 2
     (11, 2, 9, 192, 1, -1, 6, 3.0),      # TMA fast path, cluster of 3
     (12, 5, 37, 64, 1, -1, 9, 1.0),      # TMA fast path, single CTA, T > ring depth
+    (13, 3, 9, 16, 2, -1, 5, 1.0),       # thread-per-column path (n=2), single CTA, FrameDependent
+    (14, 2, 7, 32, 2, 3, 5, 1.0),        # thread-per-column path, cluster of 4, FLD(3)
+    (15, 2, 5, 64, 2, -1, 5, 2.0),       # configs[2] width, cluster of 8, FrameDependent
+    (16, 3, 8, 8, 3, 2, 6, 1.0),         # thread-per-column path, 4-gram states (n=3), cluster of 2
 ]
 
 
@@ -341,6 +345,31 @@ def test_fast_path_ties(flags):
   (gd,) = torch.autograd.grad(dist.sum(), table)
   npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
   npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+
+
+@pytest.mark.parametrize('k', [-1, 2])
+def test_cols_path_ties(k):
+  """All-equal weights on a thread-per-column shape (context_size 2): blank beats lexical,
+  fewer expansions win, lowest source row block wins (semirings.py:363, :382)."""
+  b, t, vocab, ctx = 2, 5, 16, 2
+  c = 1 + vocab + vocab * vocab
+  tab = np.zeros([b, t, c, 1 + vocab], np.float32)
+  tab[1, :, :, 0] = -1.0        # utterance 1: lexical arcs beat blank, all tie with each other
+  nf = np.array([5, 3])
+  kk, fd = (0, True) if k < 0 else (k, False)
+  o_vd, o_gb, o_gl, o_labels = O.viterbi(tab[..., 0].copy(), tab[..., 1:].copy(), nf,
+                                         O.FullNGram(vocab, ctx), kk, fd)
+  for flags in [0, 1]:
+    table = cuda(tab).requires_grad_()
+    lattice = make_lattice(vocab, ctx, k, table, flags)
+    dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                               semiring=_lt().semirings.MaxTropical)
+    npt.assert_array_equal(dist.detach().cpu(), o_vd)
+    (gd,) = torch.autograd.grad(dist.sum(), table)
+    npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
+    npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+    labels, _, _ = lattice.shortest_path(frames=frames_for(b, t), num_frames=cuda(nf), cache=None)
+    npt.assert_array_equal(labels.cpu(), o_labels)
 
 
 def test_viterbi_ties_match_reference_rules():
