@@ -1,0 +1,392 @@
+// JointWeightFn backward, data gradient, second generation: ONE tcgen05 kernel that goes
+// from grad_lexical / grad_blank to grad_proj_ctx and grad_proj_frame without writing the
+// [M, H] pre-activation gradient to memory (the first generation wrote 16.8 GB of it and
+// streamed it back through a reduction kernel).
+//
+//   Gp[m, j] = (sum_v G[m, v] W_vocab[v, j] + gb[m] w_blank[j]) * (1 - tanh^2(pc[c, j] + pf[n, j]))
+//   grad_proj_ctx[c, j]   = sum_n Gp[(n, c), j]        grad_proj_frame[n, j] = sum_c Gp[(n, c), j]
+//
+// The product is computed TRANSPOSED, D[j, i] = sum_v W^T[j, v] G[m_i, v], so that a TMEM lane
+// (= an epilogue thread) is a hidden unit j and the TMEM columns are joint rows:
+//   * a CTA owns one block of 128 hidden units for its whole life; the A operand, W_vocab^T
+//     [128 x V] as bf16 hi / lo (bf16x3 split, see joint_tc.cu), is loaded ONCE by TMA and stays
+//     resident in shared memory (128 KB at V = 256);
+//   * a work item is (block of 128 frames n0.., this hidden block); it is swept as C tiles, tile
+//     c = the 128 joint rows {(n0 + i, c)}: the B operand, their grad_lexical rows split hi / lo
+//     on the fly by 8 producer warps into a 2-stage K-major SWIZZLE_128B ring;
+//   * with that tiling the sum over frames (grad_proj_ctx[c, j]) is a serial sum over the
+//     columns of one tile in the epilogue thread, and the sum over context states
+//     (grad_proj_frame[n0 + i, j]) accumulates over the C tiles of the item IN TENSOR MEMORY:
+//     128 TMEM columns hold the running sums, 128 more hold pf[n0 + i, j] for the item, so the
+//     epilogue never touches shared or global memory per element (tcgen05.ld / tcgen05.st);
+//   * two accumulators (2 x 128 TMEM columns): the epilogue of tile c overlaps the MMAs of c+1.
+// TMEM map (512 columns): [0,128) D0 | [128,256) D1 | [256,384) pf | [384,512) grad_proj_frame.
+//
+// Reference: the autograd of weight_fns.py:208-227 (tanh joint + two Linear layers).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "params.cuh"
+#include "umma.cuh"
+
+namespace lt {
+namespace {
+
+__device__ __forceinline__ void mbar_init_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTD_WAIT%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTD_DONE%=;\n"
+      "bra LTD_WAIT%=;\n"
+      "LTD_DONE%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                       uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU ops; absolute error ~1e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (2.f * kLog2e)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(-2.f, r, 1.f);
+}
+
+// 16 consecutive fp32 TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+      "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+constexpr int kDThreads = 448;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6-13 producers
+constexpr int kDProducers = 256;
+constexpr int kDStages = 2;
+constexpr int kTile = 128;              // joint rows per tile = frames per work item
+constexpr int kJB = 128;                // hidden units per CTA
+constexpr int kGbRing = 8;               // tiles the producers may run ahead of the epilogue (< 8)
+
+struct Dgrad2Params {
+  const float* pc;       // [C, H]
+  const float* pf;       // [N, H]
+  const float* w_blank;  // [H]
+  const float* gl;       // [N*C, V]
+  const float* gb;       // [N*C]
+  long long N;
+  int C, H, V;
+  float* gpc;            // [C, H]  += (atomics)
+  float* gpf;            // [N, H]  += (single owner)
+};
+
+__global__ void __launch_bounds__(kDThreads, 1)
+joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
+                    const __grid_constant__ CUtensorMap map_lo, const Dgrad2Params p) {
+  extern __shared__ __align__(1024) unsigned char d2smem_raw[];
+  unsigned char* base = d2smem_raw + ((1024u - (smem_u32(d2smem_raw) & 1023u)) & 1023u);
+  const int V = p.V, H = p.H, C = p.C;
+  const int nk = V / 64;                              // K chunks
+  const uint32_t a_chunk = 2 * kJB * 128;             // hi | lo of one [128 j x 64 v] chunk
+  const uint32_t b_stage = 2 * kTile * 128;           // hi | lo of one [128 rows x 64 v] chunk
+  unsigned char* a_res = base;                        // nk chunks, resident
+  unsigned char* b_ring = a_res + (size_t)nk * a_chunk;
+  float* s_gb = reinterpret_cast<float*>(b_ring + kDStages * b_stage);      // [kGbRing][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + kGbRing * kTile);
+  uint64_t* full = bars;                    // [stages]  producers -> MMA
+  uint64_t* empty = full + kDStages;        // [stages]  MMA (commit) -> producers
+  uint64_t* tfull = empty + kDStages;       // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
+  uint64_t* gbfull = tempty + 2;            // [kGbRing] producers -> epilogue (grad_blank slice)
+  uint64_t* afull = gbfull + kGbRing;       // [1]       TMA -> MMA (resident A)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int njb = H / kJB;
+  const int jb = blockIdx.x % njb;
+  const int group = blockIdx.x / njb, ngroups = gridDim.x / njb;
+  const long long nblocks = (p.N + kTile - 1) / kTile;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDStages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), kDProducers);
+      mbar_init_n(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init_n(smem_u32(&tfull[a]), 1);
+      mbar_init_n(smem_u32(&tempty[a]), 128);
+    }
+    for (int r = 0; r < kGbRing; ++r) mbar_init_n(smem_u32(&gbfull[r]), kTile);
+    mbar_init_n(smem_u32(afull), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+  }
+  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ resident A: W_vocab^T block, once
+    if (lane == 0 && group < nblocks) {
+      const uint32_t bar = smem_u32(afull);
+      mbar_expect_tx(bar, (uint32_t)nk * a_chunk);
+      for (int kc = 0; kc < nk; ++kc) {
+        tma_2d(smem_u32(a_res) + kc * a_chunk, &map_hi, kc * 64, jb * kJB, bar);
+        tma_2d(smem_u32(a_res) + kc * a_chunk + kJB * 128, &map_lo, kc * 64, jb * kJB, bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0 && group < nblocks) {
+      const uint32_t idesc = umma::make_idesc_bf16(kJB, kTile);
+      mbar_wait_parity(smem_u32(afull), 0);
+      uint32_t g = 0, it = 0;
+      for (long long nb = group; nb < nblocks; nb += ngroups) {
+        for (int c = 0; c < C; ++c, ++it) {
+          const uint32_t acc = it & 1;
+          mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+          umma::fence_after_thread_sync();
+          const uint32_t d = tmem + acc * kTile;
+          for (int kc = 0; kc < nk; ++kc, ++g) {
+            const int s = g % kDStages;
+            mbar_wait_parity(smem_u32(&full[s]), (g / kDStages) & 1);
+            umma::fence_after_thread_sync();
+            const uint32_t sa = smem_u32(a_res) + kc * a_chunk;
+            const uint32_t sb = smem_u32(b_ring) + s * b_stage;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
+              const uint64_t dal = umma::make_smem_desc_sw128(sa + kJB * 128 + k * 32);
+              const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
+              const uint64_t dbl = umma::make_smem_desc_sw128(sb + kTile * 128 + k * 32);
+              umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
+              umma::mma_bf16(d, dah, dbl, idesc, 1);
+              umma::mma_bf16(d, dal, dbh, idesc, 1);
+            }
+            umma::commit(smem_u32(&empty[s]));
+          }
+          umma::commit(smem_u32(&tfull[acc]));
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;                          // TMEM lane quadrant of this warp
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int jg = jb * kJB + quad * 32 + lane;         // hidden unit of this thread
+    const float wbj = p.w_blank[jg];
+    const uint32_t t_pf = tmem + 2 * kTile + lane_base, t_acc = tmem + 3 * kTile + lane_base;
+    uint32_t it = 0;
+    for (long long nb = group; nb < nblocks; nb += ngroups) {
+      const long long n0 = nb * kTile;
+      const int nvalid = (int)min((long long)kTile, p.N - n0);
+      // item prologue: pf[n0 + i, jg] -> TMEM, running sums := 0
+      for (int c0 = 0; c0 < kTile; c0 += 16) {
+        float v[16], z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = (c0 + i < nvalid) ? __ldg(p.pf + (size_t)(n0 + c0 + i) * H + jg) : 0.f;
+          z[i] = 0.f;
+        }
+        tmem_st16(t_pf + c0, v);
+        tmem_st16(t_acc + c0, z);
+      }
+      tmem_wait_st();
+      float pcj = __ldg(p.pc + jg);
+      for (int c = 0; c < C; ++c, ++it) {
+        const uint32_t acc = it & 1, ring = it % kGbRing;
+        const float pc_cur = pcj;
+        if (c + 1 < C) pcj = __ldg(p.pc + (size_t)(c + 1) * H + jg);
+        mbar_wait_parity(smem_u32(&gbfull[ring]), (it / kGbRing) & 1);
+        mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
+        umma::fence_after_thread_sync();
+        const float* gbr = s_gb + ring * kTile;
+        const uint32_t t_d = tmem + acc * kTile + lane_base;
+        float csum = 0.f;
+        for (int c0 = 0; c0 < kTile; c0 += 16) {
+          float d[16], f[16], a[16];
+          tmem_ld16(t_d + c0, d);
+          tmem_ld16(t_pf + c0, f);
+          tmem_ld16(t_acc + c0, a);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = fmaf(gbr[c0 + i], wbj, d[i]);
+            const float h = tanh_fast(pc_cur + f[i]);
+            const float gp = x * fmaf(-h, h, 1.f);
+            csum += gp;
+            a[i] += gp;
+          }
+          tmem_st16(t_acc + c0, a);
+        }
+        tmem_wait_st();
+        umma::fence_before_thread_sync();
+        mbar_arrive(smem_u32(&tempty[acc]));
+        atomicAdd(p.gpc + (size_t)c * H + jg, csum);
+      }
+      // item epilogue: grad_proj_frame[n0 + i, jg] += running sums
+      for (int c0 = 0; c0 < kTile; c0 += 16) {
+        float a[16];
+        tmem_ld16(t_acc + c0, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < nvalid) p.gpf[(size_t)(n0 + c0 + i) * H + jg] += a[i];
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- B producers
+    // 8 lanes per joint row (256 contiguous bytes of grad_lexical per K chunk), 4 rows per
+    // warp, 4 passes over the 128 rows of the tile; the loads of the next chunk are issued
+    // before the current one is converted and stored.
+    const int pw = warp - 6;
+    const int ch = lane & 7, rsub = lane >> 3;
+    uint32_t g = 0, it = 0;
+    long long nb = group;
+    int c = 0, kc = 0;
+    auto issue = [&](long long nbq, int cq, int kq, float4 (&x)[4][2], float (&gbv)[4]) {
+      const long long n0 = nbq * kTile;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = q * 32 + pw * 4 + rsub;
+        const long long n = n0 + row;
+        x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gbv[q] = 0.f;
+        if (n < p.N) {
+          const size_t m = (size_t)n * C + cq;
+          const float* src = p.gl + m * V + kq * 64 + ch * 8;
+          x[q][0] = ldg_stream4(src);
+          x[q][1] = ldg_stream4(src + 4);
+          if (kq == 0 && ch == 0) gbv[q] = ldg_stream(p.gb + m);
+        }
+      }
+    };
+    float4 cur[4][2], nxt[4][2];
+    float gcur[4], gnxt[4];
+    if (nb < nblocks) issue(nb, 0, 0, cur, gcur);
+    while (nb < nblocks) {
+      long long nnb = nb;
+      int nc = c, nkc = kc + 1;
+      if (nkc == nk) { nkc = 0; if (++nc == C) { nc = 0; nnb += ngroups; } }
+      if (nnb < nblocks) issue(nnb, nc, nkc, nxt, gnxt);
+      const int s = g % kDStages;
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float x[8] = {cur[q][0].x, cur[q][0].y, cur[q][0].z, cur[q][0].w,
+                            cur[q][1].x, cur[q][1].y, cur[q][1].z, cur[q][1].w};
+        umma::split_pack8(x, hi[q], lo[q]);
+      }
+      if (kc == 0 && ch == 0) {              // grad_blank slice of this tile for the epilogue
+        const uint32_t ring = it % kGbRing;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_gb[ring * kTile + q * 32 + pw * 4 + rsub] = gcur[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mbar_arrive(smem_u32(&gbfull[ring]));
+      }
+      mbar_wait_parity(smem_u32(&empty[s]), ((g / kDStages) & 1) ^ 1);
+      unsigned char* b_hi = b_ring + s * b_stage;
+      unsigned char* b_lo = b_hi + kTile * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
+        *reinterpret_cast<uint4*>(b_hi + off) = hi[q];
+        *reinterpret_cast<uint4*>(b_lo + off) = lo[q];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(smem_u32(&full[s]));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; gcur[q] = gnxt[q]; }
+      if (nkc == 0) ++it;
+      nb = nnb; c = nc; kc = nkc; ++g;
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                            const void* pf) {
+  if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_DGRAD_V1")) return false;
+  if (V % 64 != 0 || V < 64 || V > 256) return false;
+  if (H % 128 != 0 || H > 4096) return false;
+  if (N < 1 || C < 1) return false;
+  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  return al(gl) && al(pc) && al(pf);
+}
+
+// whi / wlo: W_vocab^T [H, V] as bf16 hi / lo (transpose_split_kernel), map_* their tensor maps
+// with box [64 x 128].
+int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const float* pc,
+                        const float* pf, const float* wb, const float* gb, const float* gl,
+                        int64_t N, int C, int H, int V, float* gpc, float* gpf,
+                        cudaStream_t stream) {
+  Dgrad2Params p = {};
+  p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
+  p.N = N; p.C = C; p.H = H; p.V = V; p.gpc = gpc; p.gpf = gpf;
+  const int nk = V / 64;
+  const size_t smem = (size_t)nk * 2 * kJB * 128 + (size_t)kDStages * 2 * kTile * 128 +
+                      sizeof(float) * kGbRing * kTile + 8 * 32 + 16 + 1024;
+  int dev = 0, sms = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int njb = H / kJB;
+  int groups = sms / njb;
+  if (groups < 1) groups = 1;
+  const long long nblocks = (N + kTile - 1) / kTile;
+  if (groups > nblocks) groups = (int)nblocks;
+  LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  joint_dgrad2_kernel<<<groups * njb, kDThreads, smem, stream>>>(map_hi, map_lo, p);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
+}  // namespace lt

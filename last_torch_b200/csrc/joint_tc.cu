@@ -1075,8 +1075,16 @@ bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
   return al(gl) && al(pc) && al(pf);
 }
 
+static bool dgrad2_shape_ok(int H, int V) {
+  return !getenv("LT_JOINT_SIMT") && !getenv("LT_JOINT_DGRAD_V1") && V % 64 == 0 && V >= 64 &&
+         V <= 256 && H % 128 == 0 && H <= 4096;
+}
+
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
-  return (int64_t)H * V * 2 * 2 + 512 + N * (int64_t)C * H * 4;
+  // bf16 hi / lo of W_vocab^T; the first-generation dgrad also needs the [M, H] buffer
+  const int64_t split = (int64_t)H * V * 2 * 2 + 512;
+  if (dgrad2_shape_ok(H, V)) return split;
+  return split + N * (int64_t)C * H * 4;
 }
 
 // dgrad on tcgen05 + streaming reduction into grad_proj_ctx / grad_proj_frame.
@@ -1091,6 +1099,25 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
                                        (((size_t)H * V * 4 + 255) / 256) * 256);
   transpose_split_kernel<<<(V * H + 255) / 256, 256, 0, stream>>>(wv, whi, wlo, V, H);
   LT_LAUNCHED();
+  if (joint_dgrad2_supported(N, C, H, V, gl, pc, pf)) {
+    // second generation: fused tanh' + both reductions, no [M, H] round trip (joint_dgrad2.cu)
+    CUtensorMap m_hi, m_lo;
+    cuuint64_t dims2[2] = {(cuuint64_t)V, (cuuint64_t)H};
+    cuuint64_t strides2[1] = {(cuuint64_t)V * 2};
+    cuuint32_t box2[2] = {64, 128};
+    cuuint32_t estr2[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+      CUresult r = encode(i == 0 ? &m_hi : &m_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                          i == 0 ? whi : wlo, dims2, strides2, box2, estr2,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (W_vocab^T, 128-row box) failed with %d", (int)r);
+        return LT_ERR_CUDA;
+      }
+    }
+    return joint_dgrad2_launch(m_hi, m_lo, pc, pf, wb, gb, gl, N, C, H, V, gpc, gpf, stream);
+  }
   const int NH = H > 256 ? 256 : H;
   CUtensorMap map_hi, map_lo;
   cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)H};

@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 
+struct CUtensorMap_st;
+
 namespace lt {
 
 struct FwdParams {
@@ -129,6 +131,13 @@ int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
 int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
                           const float* gb, const float* gl, int64_t N, int C, int H, int V,
                           float* gpc, float* gpf, void* workspace, cudaStream_t stream);
+// fused dgrad + reductions (joint_dgrad2.cu)
+bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                            const void* pf);
+int joint_dgrad2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo,
+                        const float* pc, const float* pf, const float* wb, const float* gb,
+                        const float* gl, int64_t N, int C, int H, int V, float* gpc, float* gpf,
+                        cudaStream_t stream);
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,

@@ -76,7 +76,8 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
   assert err_b < 1e-5, err_b
 
 
-@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 40), (65, 64, 128, 9), (130, 128, 256, 17)])
+@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 40), (65, 64, 128, 9), (130, 128, 256, 17),
+                                     (257, 256, 512, 300), (33, 64, 128, 261), (17, 192, 384, 130)])
 def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
   """Gradients of the whole-utterance JointWeightFn kernel path (tcgen05 dgrad +
   streaming reduction, weight gradients) against torch autograd through the
