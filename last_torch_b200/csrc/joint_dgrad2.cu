@@ -20,6 +20,12 @@
 //     128 TMEM columns hold the running sums, 128 more hold pf[n0 + i, j] for the item, so the
 //     epilogue never touches shared or global memory per element (tcgen05.ld / tcgen05.st);
 //   * two accumulators (2 x 128 TMEM columns): the epilogue of tile c overlaps the MMAs of c+1.
+// Measured limits (B=32, T=1000, C=257, H=512, V=256: 11.8 ms, tensor pipe 24 %): with N = 128
+// every SS-mode tcgen05.mma reads 8 KB of shared memory per 64 issue cycles, i.e. the whole
+// 128 B/clk port, so the producers' stores slow the MMAs; the epilogue reads 3 x 64 KB of TMEM
+// per tile at 64 B/clk (as long as the tile's MMAs); and every grad_lexical row is fetched by
+// the four CTAs (hidden blocks) that need it.  MMAs + conversion alone take 5.3 ms, the
+// gradient loads add ~3 ms and the epilogue ~3 ms.
 // TMEM map (512 columns): [0,128) D0 | [128,256) D1 | [256,384) pf | [384,512) grad_proj_frame.
 //
 // Reference: the autograd of weight_fns.py:208-227 (tanh joint + two Linear layers).
@@ -102,8 +108,11 @@ __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-constexpr int kDThreads = 448;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, 6-13 producers
-constexpr int kDProducers = 256;
+constexpr int kDProdWarps = 16;
+constexpr int kDThreads = (6 + kDProdWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue,
+                                                    // warps 6.. producers
+constexpr int kDProducers = kDProdWarps * 32;
+constexpr int kDPasses = 128 / (kDProdWarps * 4);   // row passes per producer thread and chunk
 constexpr int kDStages = 2;
 constexpr int kTile = 128;              // joint rows per tile = frames per work item
 constexpr int kJB = 128;                // hidden units per CTA
@@ -281,68 +290,77 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   } else {
     // ---------------------------------------------------------------- B producers
     // 8 lanes per joint row (256 contiguous bytes of grad_lexical per K chunk), 4 rows per
-    // warp, 4 passes over the 128 rows of the tile; the loads of the next chunk are issued
-    // before the current one is converted and stored.
+    // warp, kDPasses passes over the 128 rows of the tile.  The loads run TWO chunks ahead of
+    // the conversion (register ring cur / n1 / n2): the ring has to cover the HBM / L2 latency
+    // of the gradient stream, which is what bounds this kernel.
     const int pw = warp - 6;
     const int ch = lane & 7, rsub = lane >> 3;
-    uint32_t g = 0, it = 0;
-    long long nb = group;
-    int c = 0, kc = 0;
-    auto issue = [&](long long nbq, int cq, int kq, float4 (&x)[4][2], float (&gbv)[4]) {
-      const long long n0 = nbq * kTile;
+    struct Pos { long long nb; int c, kc; };
+    auto advance = [&](Pos q) {
+      if (++q.kc == nk) { q.kc = 0; if (++q.c == C) { q.c = 0; q.nb += ngroups; } }
+      return q;
+    };
+    auto issue = [&](const Pos& q, float4 (&x)[kDPasses][2], float (&gbv)[kDPasses]) {
+      const long long n0 = q.nb * kTile;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = q * 32 + pw * 4 + rsub;
+      for (int r = 0; r < kDPasses; ++r) {
+        const int row = r * (kDProdWarps * 4) + pw * 4 + rsub;
         const long long n = n0 + row;
-        x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        gbv[q] = 0.f;
-        if (n < p.N) {
-          const size_t m = (size_t)n * C + cq;
-          const float* src = p.gl + m * V + kq * 64 + ch * 8;
-          x[q][0] = ldg_stream4(src);
-          x[q][1] = ldg_stream4(src + 4);
-          if (kq == 0 && ch == 0) gbv[q] = ldg_stream(p.gb + m);
+        x[r][0] = x[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gbv[r] = 0.f;
+        if (q.nb < nblocks && n < p.N) {
+          const size_t m = (size_t)n * C + q.c;
+          const float* src = p.gl + m * V + q.kc * 64 + ch * 8;
+          x[r][0] = ldg_stream4(src);
+          x[r][1] = ldg_stream4(src + 4);
+          if (q.kc == 0 && ch == 0) gbv[r] = ldg_stream(p.gb + m);
         }
       }
     };
-    float4 cur[4][2], nxt[4][2];
-    float gcur[4], gnxt[4];
-    if (nb < nblocks) issue(nb, 0, 0, cur, gcur);
-    while (nb < nblocks) {
-      long long nnb = nb;
-      int nc = c, nkc = kc + 1;
-      if (nkc == nk) { nkc = 0; if (++nc == C) { nc = 0; nnb += ngroups; } }
-      if (nnb < nblocks) issue(nnb, nc, nkc, nxt, gnxt);
+    float4 cur[kDPasses][2], n1[kDPasses][2], n2[kDPasses][2];
+    float gcur[kDPasses], g1[kDPasses], g2[kDPasses];
+    Pos pc0 = {group, 0, 0};
+    Pos p1 = advance(pc0), p2 = advance(p1);
+    issue(pc0, cur, gcur);
+    issue(p1, n1, g1);
+    uint32_t g = 0, it = 0;
+    while (pc0.nb < nblocks) {
+      issue(p2, n2, g2);
       const int s = g % kDStages;
-      uint4 hi[4], lo[4];
+      uint4 hi[kDPasses], lo[kDPasses];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float x[8] = {cur[q][0].x, cur[q][0].y, cur[q][0].z, cur[q][0].w,
-                            cur[q][1].x, cur[q][1].y, cur[q][1].z, cur[q][1].w};
-        umma::split_pack8(x, hi[q], lo[q]);
+      for (int r = 0; r < kDPasses; ++r) {
+        const float x[8] = {cur[r][0].x, cur[r][0].y, cur[r][0].z, cur[r][0].w,
+                            cur[r][1].x, cur[r][1].y, cur[r][1].z, cur[r][1].w};
+        umma::split_pack8(x, hi[r], lo[r]);
       }
-      if (kc == 0 && ch == 0) {              // grad_blank slice of this tile for the epilogue
+      if (pc0.kc == 0 && ch == 0) {          // grad_blank slice of this tile for the epilogue
         const uint32_t ring = it % kGbRing;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s_gb[ring * kTile + q * 32 + pw * 4 + rsub] = gcur[q];
+        for (int r = 0; r < kDPasses; ++r)
+          s_gb[ring * kTile + r * (kDProdWarps * 4) + pw * 4 + rsub] = gcur[r];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) mbar_arrive(smem_u32(&gbfull[ring]));
+        for (int r = 0; r < kDPasses; ++r) mbar_arrive(smem_u32(&gbfull[ring]));
       }
       mbar_wait_parity(smem_u32(&empty[s]), ((g / kDStages) & 1) ^ 1);
       unsigned char* b_hi = b_ring + s * b_stage;
       unsigned char* b_lo = b_hi + kTile * 128;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t off = umma::swizzled_offset(q * 32 + pw * 4 + rsub, ch);
-        *reinterpret_cast<uint4*>(b_hi + off) = hi[q];
-        *reinterpret_cast<uint4*>(b_lo + off) = lo[q];
+      for (int r = 0; r < kDPasses; ++r) {
+        const uint32_t off = umma::swizzled_offset(r * (kDProdWarps * 4) + pw * 4 + rsub, ch);
+        *reinterpret_cast<uint4*>(b_hi + off) = hi[r];
+        *reinterpret_cast<uint4*>(b_lo + off) = lo[r];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(smem_u32(&full[s]));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; gcur[q] = gnxt[q]; }
-      if (nkc == 0) ++it;
-      nb = nnb; c = nc; kc = nkc; ++g;
+      for (int r = 0; r < kDPasses; ++r) {
+        cur[r][0] = n1[r][0]; cur[r][1] = n1[r][1]; gcur[r] = g1[r];
+        n1[r][0] = n2[r][0]; n1[r][1] = n2[r][1]; g1[r] = g2[r];
+      }
+      if (p1.kc == 0) ++it;
+      pc0 = p1; p1 = p2; p2 = advance(p2);
+      ++g;
     }
   }
   umma::fence_before_thread_sync();
