@@ -380,9 +380,10 @@ def run_b200(args):
     kern[name] = {'ms': statistics.mean(ts), 'calls_per_step': len(ts) / args.steps}
   alg = {'lt_lattice_forward': 1.0 * w_bytes, 'lt_lattice_backward': 2.0 * w_bytes}
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of
-  # this exact workload (profiles/r01_ncu_final_summary.csv); only valid for the default shape.
-  default_shape = (B, T, V, n, U) == (32, 1000, 256, 1, 120)
-  ncu_traffic = {'lt_lattice_forward': 8.46e9 + 0.04e9, 'lt_lattice_backward': 8.49e9 + 8.40e9}
+  # this exact workload (profiles/r01_ncu_round1_final_summary.csv); only valid for the
+  # default shape.
+  default_shape = (B, T, V, n, U) == (32, 1000, 256, 1, 120) and args.flags == 0
+  ncu_traffic = {'lt_lattice_forward': 8.456e9 + 0.036e9, 'lt_lattice_backward': 8.490e9 + 8.403e9}
   for name, nbytes in alg.items():
     if name in kern:
       kern[name]['algorithmic_gb'] = nbytes / 1e9
@@ -394,7 +395,7 @@ def run_b200(args):
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['gbps'], 'peak': peak,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['frac'],
                 'traffic': ncu_traffic[dom] if default_shape else None,
-                'traffic_source': 'profiles/r01_ncu_final_summary.csv (ncu --set full)',
+                'traffic_source': 'profiles/r01_ncu_round1_final_summary.csv (ncu --set full)',
                 'algorithmic_bytes_per_launch': alg[dom],
                 'whole_step': {'algorithmic_gb': 3.0 * w_bytes / 1e9,
                                'gbps': 3.0 * w_bytes / 1e9 / (ms_step * 1e-3),
