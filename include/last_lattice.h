@@ -183,6 +183,46 @@ int lt_semiring_sum_backward(int semiring, const float* a, const float* out,
                              int64_t outer, int64_t reduce, int64_t inner,
                              float* grad_a, void* stream);
 
+/* ---- generic context DFA: contexts.NextStateTable (contexts.py:266-324) ------
+ * The same recursions as lt_lattice_forward / _backward / lt_viterbi_backtrace for a
+ * context dependency given as a table:
+ *   table      [C,V] int32  next state of (p, y), y zero-based
+ *   in_offsets [C+1], in_arcs [C*V] int32: CSR of INCOMING arcs -- the flat arc indices
+ *              p*V+y grouped by destination state, ascending inside a group (built once
+ *              by the host, e.g. a stable argsort of the table)
+ *   backarc    [B,T,max(k,1),C] int32, MaxTropical only: winning incoming arc of every
+ *              reduction (first arg-max in flat-arc order); for FrameDependent -1 means
+ *              "blank arc won" (semirings.py:363)
+ * forward_reduce / its gradient on arbitrary leading dims (w viewed as [outer, C, V]):
+ *   out[o,q] = (+)_{p -y-> q} w[o,p,y] for EVERY semiring (the reference implements the
+ *   Real semiring only); argarc [outer,C] int32 for MaxTropical.
+ */
+int lt_table_lattice_forward(int semiring, int max_expansions, const int32_t* table,
+                             const int32_t* in_offsets, const int32_t* in_arcs, int C, int V,
+                             const float* blank, const float* lexical,
+                             const int32_t* num_frames, int B, int T,
+                             const float* alpha_init, float* dist, float* alphas,
+                             float* alpha_final, float* levels, int32_t* backarc,
+                             uint8_t* termptr, void* stream);
+int lt_table_lattice_backward(int semiring, int max_expansions, const int32_t* table, int C,
+                              int V, const float* blank, const float* lexical,
+                              const int32_t* num_frames, int B, int T, const float* alphas,
+                              const float* levels, const float* dist,
+                              const float* grad_dist, float* grad_blank,
+                              float* grad_lexical, void* stream);
+int lt_table_viterbi_backtrace(int max_expansions, int C, int V, const int32_t* backarc,
+                               const uint8_t* termptr, const float* alpha_final,
+                               const int32_t* num_frames, int B, int T, int32_t* labels,
+                               int32_t* path_states, const float* grad_dist,
+                               float* grad_blank, float* grad_lexical, void* stream);
+int lt_table_reduce_forward(int semiring, const float* w, const int32_t* in_offsets,
+                            const int32_t* in_arcs, int64_t outer, int C, int V, float* out,
+                            int32_t* argarc, void* stream);
+int lt_table_reduce_backward(int semiring, const float* w, const float* out,
+                             const int32_t* argarc, const float* grad_out,
+                             const int32_t* table, int64_t outer, int C, int V,
+                             float* grad_w, void* stream);
+
 /* ---- K4: JointWeightFn (weight_fns.py:194-227) -------------------------------
  * joint = tanh(cache @ w_ctx^T + frames @ w_frame^T)   [N, C, H]
  * blank = joint @ w_blank + b_blank                     [N, C]

@@ -60,6 +60,17 @@ SIGNATURES = {
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_joint_backward_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
+    'lt_table_lattice_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr,
+                                 _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                 _ptr],
+    'lt_table_lattice_backward': [_c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int,
+                                  _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_table_viterbi_backtrace': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int,
+                                   _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_table_reduce_forward': [_c_int, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr, _ptr,
+                                _ptr],
+    'lt_table_reduce_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int,
+                                 _ptr, _ptr],
 }
 
 _lib = None

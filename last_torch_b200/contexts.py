@@ -137,3 +137,82 @@ class FullNGram(ContextDependency):
     num_states, vocab_size = self.shape()
     return self.next_state(
         torch.arange(num_states).unsqueeze(-1), torch.arange(vocab_size).unsqueeze(0) + 1)
+
+
+@dataclasses.dataclass(frozen=True)
+class NextStateTable(ContextDependency):
+  """Context dependency described as a transition lookup table
+  (contexts.py:266-324).
+
+  next_state_table: [num_states, vocab_size] int32; next_state_table[p, y - 1]
+  is the state reached from p with label y.
+
+  forward_reduce implements the documented contract out[q] = (+)_{p -y-> q}
+  w[p, y] (contexts.py:74-90) for EVERY semiring through a CSR of incoming arcs
+  (the reference only works for the Real semiring); MaxTropical ties
+  keep the first arc in (p, y) order.  Inside RecognitionLattice the table-driven
+  lattice kernels (csrc/lattice_table.cu) are used.
+  """
+  next_state_table: torch.Tensor
+
+  def __post_init__(self):
+    if self.next_state_table.ndim != 2:
+      raise ValueError(
+          'next_state_table should have shape [num_states, vocab_size], but'
+          f'got shape {self.next_state_table.shape}')
+    if 0 in self.next_state_table.size():
+      raise ValueError('next_state_table should have a non-zero size, but '
+                       f'got shape {self.next_state_table.shape}')
+    if self.next_state_table.dtype != torch.int32:
+      raise ValueError('next_state_table should be an int32 ndarray, but '
+                       f'got dtype {self.next_state_table.dtype}')
+    object.__setattr__(self, '_device_cache', {})
+
+  def shape(self) -> tuple[int, int]:
+    return self.next_state_table.shape
+
+  def start(self) -> int:
+    return 0
+
+  def next_state(self, state: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """contexts.py:297-304; accepts int or float index tensors."""
+    table = self.next_state_table.to(state.device)
+    is_epsilon = label == 0
+    zero_based_label = torch.where(is_epsilon, torch.zeros_like(label), label - 1)
+    nextstate = table[state.long(), zero_based_label.long()].to(state.dtype)
+    return torch.where(is_epsilon, state, nextstate)
+
+  def kernel_tables(self, device):
+    """(table [C,V], in_offsets [C+1], in_arcs [C*V]) int32 on `device`: the CSR of
+    incoming arcs the kernels pull from (arcs of a destination in ascending p*V+y order)."""
+    key = str(device)
+    if key not in self._device_cache:
+      table = self.next_state_table.to(device=device, dtype=torch.int64).contiguous()
+      c = table.shape[0]
+      if int(table.min()) < 0 or int(table.max()) >= c:
+        raise ValueError(f'next_state_table entries should be in [0, {c}), but got '
+                         f'[{int(table.min())}, {int(table.max())}]')
+      flat = table.reshape(-1)
+      order = torch.sort(flat, stable=True).indices
+      counts = torch.bincount(flat, minlength=c)
+      offsets = torch.zeros([c + 1], dtype=torch.int64, device=device)
+      offsets[1:] = torch.cumsum(counts, 0)
+      self._device_cache[key] = (table.to(torch.int32).contiguous(),
+                                 offsets.to(torch.int32).contiguous(),
+                                 order.to(torch.int32).contiguous())
+    return self._device_cache[key]
+
+  def forward_reduce(self, weights: torch.Tensor,
+                     semiring: semirings.Semiring[torch.Tensor]) -> torch.Tensor:
+    if weights.shape[-2:] != self.shape():
+      raise ValueError(f'weights.shape[-2:] should be {self.shape()} but got'
+                       f' {weights.shape[-2:]}')
+    from . import ops
+    return ops.TableReduce.apply(weights, self, semirings.kernel_id(semiring))
+
+  def backward_broadcast(self, weights: torch.Tensor) -> torch.Tensor:
+    num_states = weights.shape[-1]
+    if num_states != self.shape()[0]:
+      raise ValueError(f'weights.shape[-1] should be {self.shape()[0]} but '
+                       f'got {num_states}')
+    return weights[..., self.next_state_table.to(device=weights.device, dtype=torch.int64)]

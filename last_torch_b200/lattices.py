@@ -62,14 +62,20 @@ class RecognitionLattice(nn.Module, Generic[T]):
 
   def _geometry(self):
     """(V, n, k) for the kernels; raises for anything they do not implement."""
-    if not isinstance(self.context, contexts.FullNGram):
-      raise NotImplementedError(
-          'the lattice kernels implement contexts.FullNGram only; got '
-          f'{type(self.context).__name__} (no fallback path exists)')
     if not isinstance(self.alignment, alignments.TimeSyncAlignmentLattice):
       raise NotImplementedError(f'unsupported alignment {type(self.alignment).__name__}')
-    return (self.context.vocab_size, self.context.context_size,
-            self.alignment.kernel_max_expansions())
+    k = self.alignment.kernel_max_expansions()
+    if isinstance(self.context, contexts.NextStateTable):
+      # table-driven kernels (csrc/lattice_table.cu); n is meaningless for a generic DFA
+      return self.context.shape()[1], None, k
+    if not isinstance(self.context, contexts.FullNGram):
+      raise NotImplementedError(
+          'the lattice kernels implement contexts.FullNGram and contexts.NextStateTable; got '
+          f'{type(self.context).__name__} (no fallback path exists)')
+    return self.context.vocab_size, self.context.context_size, k
+
+  def _is_table(self) -> bool:
+    return isinstance(self.context, contexts.NextStateTable)
 
   @staticmethod
   def _check_frames(frames, num_frames):
@@ -109,6 +115,13 @@ class RecognitionLattice(nn.Module, Generic[T]):
     """context states along the label string and the label leaving each of
     them (lattices.py:336-338; label 0 is read as label 1, :314-315)."""
     labels = labels.reshape(-1, labels.shape[-1]).to(device=device, dtype=torch.int32)
+    if self._is_table():
+      # generic DFA: integer gathers through the table (contexts.py:109-146)
+      states = self.context.walk_states(labels.long()).to(torch.int32).contiguous()
+      ones = torch.ones_like(labels[:, :1])
+      next_labels = torch.cat([torch.where(labels == 0, torch.ones_like(labels), labels), ones],
+                              dim=1).contiguous()
+      return states, next_labels
     return ops.walk_states(labels.contiguous(), self.context.vocab_size,
                            self.context.context_size)
 
@@ -129,6 +142,12 @@ class RecognitionLattice(nn.Module, Generic[T]):
     blank, lexical = self._arc_weights(cache, frames, batch_dims)
     dev = blank.device
     states, next_labels = self._string_indices(labels, dev)
+    if self._is_table():
+      nf = ops._as_i32(num_frames.reshape(-1), dev)
+      log_z, _ = ops.TableLatticeForward.apply(blank, lexical, nf, self.context, N.LOG, k)
+      num = ops.StringForward.apply(blank, lexical, nf, states, next_labels,
+                                    ops._as_i32(num_labels.reshape(-1), dev), N.LOG, v, k)
+      return (log_z - num).reshape(batch_dims)
     loss, _, _, _ = ops.LatticeLoss.apply(
         blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
         ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags)
@@ -149,8 +168,13 @@ class RecognitionLattice(nn.Module, Generic[T]):
     with torch.no_grad():
       blank, lexical = self._arc_weights(cache, frames, batch_dims)
       dev = blank.device
-      labels, _, path_weights = ops.viterbi_path(
-          blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), v, n, k, self.kernel_flags)
+      if self._is_table():
+        labels, _, path_weights = ops.table_viterbi_path(
+            blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), self.context, k)
+      else:
+        labels, _, path_weights = ops.viterbi_path(
+            blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), v, n, k,
+            self.kernel_flags)
     num_alignment_states = self.alignment.num_states()
     alignment_labels = labels.to(torch.int64).reshape(*batch_dims, -1)
     num_alignment_labels = num_alignment_states * num_frames.to(dev)
@@ -212,8 +236,13 @@ class RecognitionLattice(nn.Module, Generic[T]):
         lexical = lexical + torch.broadcast_to(
             lexical_mask[0], (*batch_dims, t, c, v)).reshape(-1, t, c, v)
     dev = blank.device
-    dist, alphas = ops.LatticeForward.apply(
-        blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), sr, v, n, k, self.kernel_flags)
+    if self._is_table():
+      dist, alphas = ops.TableLatticeForward.apply(
+          blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), self.context, sr, k)
+    else:
+      dist, alphas = ops.LatticeForward.apply(
+          blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), sr, v, n, k,
+          self.kernel_flags)
     return dist.reshape(batch_dims), alphas.reshape(*batch_dims, t, c)
 
   def _forward_backward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor):

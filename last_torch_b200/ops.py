@@ -199,6 +199,134 @@ def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
 
 
 # ---------------------------------------------------------------------------
+# generic context DFA (contexts.NextStateTable): table-driven kernels
+# ---------------------------------------------------------------------------
+
+class TableReduce(torch.autograd.Function):
+  """NextStateTable.forward_reduce: out[..., q] = (+)_{p -y-> q} w[..., p, y]
+  (contexts.py:74-90) with the semiring's gradient (safe Log gradient,
+  first-arg-max MaxTropical gradient)."""
+
+  @staticmethod
+  def forward(ctx, weights, context, sr):
+    w = N.require_cuda(weights, 'weights')
+    table, offsets, arcs = context.kernel_tables(w.device)
+    c, v = table.shape
+    outer = w.numel() // (c * v)
+    out = torch.empty(w.shape[:-1], dtype=torch.float32, device=w.device)
+    argarc = (torch.empty(w.shape[:-1], dtype=torch.int32, device=w.device)
+              if sr == N.MAXTROPICAL else None)
+    with torch.cuda.device(w.device):
+      N.check(N.lib().lt_table_reduce_forward(
+          sr, N.ptr(w), N.ptr(offsets), N.ptr(arcs), outer, c, v, N.ptr(out), N.ptr(argarc),
+          N.stream_ptr(w.device)), 'lt_table_reduce_forward')
+    ctx.save_for_backward(w, out, argarc, table)
+    ctx.geom = (sr, outer, c, v)
+    return out
+
+  @staticmethod
+  def backward(ctx, g):
+    w, out, argarc, table = ctx.saved_tensors
+    sr, outer, c, v = ctx.geom
+    g = N.require_cuda(g, 'grad')
+    gw = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+      N.check(N.lib().lt_table_reduce_backward(
+          sr, N.ptr(w), N.ptr(out), N.ptr(argarc), N.ptr(g), N.ptr(table), outer, c, v,
+          N.ptr(gw), N.stream_ptr(w.device)), 'lt_table_reduce_backward')
+    return gw, None, None
+
+
+def _table_forward_raw(sr, k, context, blank, lexical, num_frames, want_levels, want_backarc):
+  B, T, C = blank.shape
+  dev = blank.device
+  table, offsets, arcs = context.kernel_tables(dev)
+  V = table.shape[1]
+  dist = torch.empty([B], dtype=torch.float32, device=dev)
+  alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev)
+  alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)
+  fld = k >= 1
+  levels = (torch.empty([B, T, k, C], dtype=torch.float32, device=dev)
+            if (fld and want_levels) else None)
+  backarc = termptr = None
+  if want_backarc and sr == N.MAXTROPICAL:
+    backarc = torch.empty([B, T, max(k, 1), C], dtype=torch.int32, device=dev)
+    if fld:
+      termptr = torch.empty([B, T, C], dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_table_lattice_forward(
+        sr, k, N.ptr(table), N.ptr(offsets), N.ptr(arcs), C, V, N.ptr(blank), N.ptr(lexical),
+        N.ptr(num_frames), B, T, None, N.ptr(dist), N.ptr(alphas), N.ptr(alpha_final),
+        N.ptr(levels), N.ptr(backarc), N.ptr(termptr), N.stream_ptr(dev)),
+        'lt_table_lattice_forward')
+  return dist, alphas, alpha_final, levels, backarc, termptr
+
+
+class TableLatticeForward(torch.autograd.Function):
+  """(dist, alphas) = RecognitionLattice._forward for a NextStateTable context."""
+
+  @staticmethod
+  def forward(ctx, blank, lexical, num_frames, context, sr, k):
+    C, V = context.shape()
+    blank, lexical = _check_weights(blank, lexical, V, C)
+    need_grad = any(ctx.needs_input_grad[:2])
+    dist, alphas, alpha_final, levels, backarc, termptr = _table_forward_raw(
+        sr, k, context, blank, lexical, num_frames, need_grad, need_grad)
+    ctx.geom = (sr, k, context)
+    ctx.save_for_backward(blank, lexical, num_frames, dist, alphas, alpha_final, levels, backarc,
+                          termptr)
+    ctx.mark_non_differentiable(alphas)
+    return dist, alphas
+
+  @staticmethod
+  def backward(ctx, g_dist, _g_alphas):
+    sr, k, context = ctx.geom
+    blank, lexical, num_frames, dist, alphas, alpha_final, levels, backarc, termptr = \
+        ctx.saved_tensors
+    B, T, C = blank.shape
+    V = lexical.shape[-1]
+    dev = blank.device
+    g_dist = N.require_cuda(g_dist, 'grad_dist')
+    table, _, _ = context.kernel_tables(dev)
+    with torch.cuda.device(dev):
+      if sr == N.MAXTROPICAL:
+        gb = torch.zeros_like(blank)
+        gl = torch.zeros_like(lexical)
+        labels = torch.empty([B, T, max(k, 0) + 1], dtype=torch.int32, device=dev)
+        N.check(N.lib().lt_table_viterbi_backtrace(
+            k, C, V, N.ptr(backarc), N.ptr(termptr), N.ptr(alpha_final), N.ptr(num_frames), B, T,
+            N.ptr(labels), None, N.ptr(g_dist), N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)),
+            'lt_table_viterbi_backtrace')
+      else:
+        gb = torch.empty_like(blank)
+        gl = torch.empty_like(lexical)
+        N.check(N.lib().lt_table_lattice_backward(
+            sr, k, N.ptr(table), C, V, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T,
+            N.ptr(alphas), N.ptr(levels), N.ptr(dist), N.ptr(g_dist), N.ptr(gb), N.ptr(gl),
+            N.stream_ptr(dev)), 'lt_table_lattice_backward')
+    return gb, gl, None, None, None, None
+
+
+def table_viterbi_path(blank, lexical, num_frames, context, k):
+  """MaxTropical forward + back-trace for a NextStateTable context; returns
+  (labels [B,T,k+1] int32 true 1-based labels, path_states [B,T+1], path_weights [B])."""
+  C, V = context.shape()
+  blank, lexical = _check_weights(blank.detach(), lexical.detach(), V, C)
+  B, T, _ = blank.shape
+  dev = blank.device
+  dist, _, alpha_final, _, backarc, termptr = _table_forward_raw(
+      N.MAXTROPICAL, k, context, blank, lexical, num_frames, False, True)
+  labels = torch.empty([B, T, max(k, 0) + 1], dtype=torch.int32, device=dev)
+  states = torch.empty([B, T + 1], dtype=torch.int32, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_table_viterbi_backtrace(
+        k, C, V, N.ptr(backarc), N.ptr(termptr), N.ptr(alpha_final), N.ptr(num_frames), B, T,
+        N.ptr(labels), N.ptr(states), None, None, None, N.stream_ptr(dev)),
+        'lt_table_viterbi_backtrace')
+  return labels, states, dist
+
+
+# ---------------------------------------------------------------------------
 # K3: numerator on the label lattice
 # ---------------------------------------------------------------------------
 

@@ -164,6 +164,60 @@ class SharedEmbCacher(WeightFnCacher[torch.Tensor]):
     return self.embedding.weight
 
 
+class SharedRNNCacher(WeightFnCacher[torch.Tensor]):
+  """Builds the context embedding table by running the n-gram context labels
+  through an RNN (weight_fns.py:245-294).
+
+  Used with contexts.FullNGram: row s of the result is the RNN state after
+  reading <start> followed by the labels of n-gram s, in FullNGram's state
+  order (start, unigrams, bigrams, ...).  Unlike the reference, which builds a
+  fresh randomly initialised LSTMCell on every call when `rnn_cell` is None
+  (SURVEY D7), the default cell is created ONCE and registered, so the cacher
+  has trainable state.  This runs once per optimiser step (C rows), outside
+  the per-frame hot path, on whatever device the module lives on.
+  """
+
+  def __init__(self, vocab_size: int, context_size: int, rnn_size: int, rnn_embedding_size: int,
+               rnn_cell: Optional[nn.RNNCellBase] = None, device: Optional[str] = None,
+               *args, **kwargs):
+    super().__init__(*args, **kwargs)
+    self.vocab_size = vocab_size
+    self.context_size = context_size
+    self.rnn_size = rnn_size
+    self.rnn_embedding_size = rnn_embedding_size
+    self.rnn_cell = (rnn_cell if rnn_cell is not None else
+                     nn.LSTMCell(rnn_embedding_size, rnn_size, device=device))
+    self.embedding = nn.Embedding(vocab_size + 1, rnn_embedding_size, device=device)
+
+  def _step(self, inputs, carry):
+    """One cell step; returns (hidden, cell) like the reference's unpacking."""
+    out = self.rnn_cell(inputs) if carry is None else self.rnn_cell(inputs, carry)
+    if isinstance(out, tuple):
+      return out
+    return out, out
+
+  def forward(self) -> torch.Tensor:
+    dev = self.embedding.weight.device
+    feed_cell_state = isinstance(self.rnn_cell, nn.LSTMCell)
+    v = self.vocab_size
+    hidden, cell = self._step(self.embedding(torch.zeros([1], dtype=torch.long, device=dev)), None)
+    parts = [cell]
+    inputs = None
+    for i in range(self.context_size):
+      if i == 0:
+        inputs = self.embedding(torch.arange(1, v + 1, device=dev))
+      else:
+        inputs = inputs.repeat(v, *([1] * (inputs.ndim - 1)))          # 'n ... -> (v n) ...'
+      tiled_hidden = torch.repeat_interleave(hidden, v, dim=0)          # 'n ... -> (n v) ...'
+      if feed_cell_state:
+        carry = (tiled_hidden, torch.repeat_interleave(cell, v, dim=0))
+      else:
+        carry = tiled_hidden
+      hidden, cell = self._step(inputs, carry)
+      parts.append(cell)
+    return torch.concatenate(parts, dim=0)
+
+
 class NullCacher(WeightFnCacher[type(None)]):
   """Returns None; used with TableWeightFn (weight_fns.py:297-304)."""
 

@@ -202,6 +202,63 @@ class FullNGram:
     return np.stack(out, axis=-1)
 
 
+class NextStateTable:
+  """contexts.py:266-324: a context DFA given as a [num_states, vocab_size]
+  table, next_state_table[p, y - 1] = state reached from p with label y.
+
+  forward_reduce follows the interface contract out[q] = (+)_{p -y-> q} w[p, y]
+  (contexts.py:74-90) in EVERY semiring; the reference body (contexts.py:306-317)
+  only realises it for the Real semiring, where its golden test
+  (tests/contexts_test.py:214-220) agrees with this restatement.
+  """
+
+  def __init__(self, next_state_table):
+    self.table = np.asarray(next_state_table).astype(np.int64)
+    assert self.table.ndim == 2 and self.table.size > 0
+
+  def shape(self):
+    return self.table.shape
+
+  def start(self):
+    return 0
+
+  def next_state(self, state, label):
+    """contexts.py:297-304 (epsilon label 0 stays in place)."""
+    state = np.asarray(state).astype(np.int64)
+    label = np.asarray(label).astype(np.int64)
+    nxt = self.table[state, np.where(label == 0, 0, label - 1)]
+    return np.where(label == 0, state, nxt)
+
+  def next_state_table(self):
+    return self.table
+
+  def forward_reduce(self, weights, sr):
+    c, v = self.table.shape
+    batch = weights.shape[:-2]
+    flat = weights.reshape(batch + (c * v,))
+    dest = self.table.reshape(-1)
+    out = np.full(batch + (c,), sr_zero(sr, weights.dtype.type), dtype=weights.dtype)
+    for q in range(c):
+      arcs = np.nonzero(dest == q)[0]
+      if arcs.size:
+        out[..., q] = sr_sum(sr, flat[..., arcs], axis=-1)
+    return out
+
+  def backward_broadcast(self, weights):
+    """contexts.py:319-324."""
+    return weights[..., self.table]
+
+  def walk_states(self, labels):
+    """contexts.py:109-146."""
+    labels = np.asarray(labels).astype(np.int64)
+    state = np.zeros(labels.shape[:-1], dtype=np.int64)
+    out = [state]
+    for i in range(labels.shape[-1]):
+      state = self.next_state(state, labels[..., i])
+      out.append(state)
+    return np.stack(out, axis=-1)
+
+
 # ---------------------------------------------------------------------------
 # Alignment lattices (reference: last_torch/alignments.py)
 #   max_expansions == 0  <=>  FrameDependent (alignments.py:266-329)

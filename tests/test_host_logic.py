@@ -253,3 +253,83 @@ def test_lattice_shape_errors(lt):
   with pytest.raises(ValueError, match='The length of blank_mask should be equal to 1'):
     lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=lt.semirings.Log,
                      blank_mask=[torch.zeros([1]), torch.zeros([1])])
+
+
+def test_next_state_table_host_logic():
+  """tests/contexts_test.py:176-239 (everything that is integer plumbing)."""
+  import last_torch_b200 as lt
+  with pytest.raises(ValueError, match='next_state_table should have a non-zero size'):
+    lt.contexts.NextStateTable(torch.zeros([1, 0], dtype=torch.int32))
+  with pytest.raises(ValueError, match='next_state_table should have a non-zero size'):
+    lt.contexts.NextStateTable(torch.zeros([0, 1], dtype=torch.int32))
+  with pytest.raises(ValueError, match='next_state_table should have shape'):
+    lt.contexts.NextStateTable(torch.zeros([1], dtype=torch.int32))
+  with pytest.raises(ValueError, match='next_state_table should be an int32 ndarray'):
+    lt.contexts.NextStateTable(torch.zeros([2, 3]))
+  table = lt.contexts.FullNGram(vocab_size=3, context_size=2).next_state_table()
+  assert table.shape == (13, 3)
+  ctx = lt.contexts.NextStateTable(table.to(torch.int32))
+  assert tuple(ctx.shape()) == (13, 3) and ctx.start() == 0
+  npt.assert_array_equal(
+      ctx.next_state(torch.Tensor([0, 1, 3, 4, 12]), torch.Tensor([1, 2, 3, 1, 2])),
+      [1, 5, 12, 4, 11])
+  npt.assert_array_equal(
+      ctx.next_state(torch.Tensor([0, 1, 3, 4, 12]), torch.Tensor([0, 0, 0, 0, 0])),
+      [0, 1, 3, 4, 12])
+  npt.assert_array_equal(ctx.backward_broadcast(torch.arange(13).reshape((1, 13))),
+                         [[[1, 2, 3]] + [[4, 5, 6], [7, 8, 9], [10, 11, 12]] * 4])
+  assert ctx.walk_states(torch.zeros([2, 3, 4], dtype=torch.int32)).shape == (2, 3, 5)
+  npt.assert_array_equal(ctx.walk_states(torch.Tensor([2, 3, 1])), [0, 2, 9, 10])
+  npt.assert_array_equal(ctx.walk_states(torch.Tensor([2, 0, 0, 3, 1])), [0, 2, 2, 2, 9, 10])
+  with pytest.raises(ValueError, match=r'weights\.shape\[-2:\] should be torch.Size\(\[13, 3\]\)'):
+    ctx.forward_reduce(torch.zeros([4, 3]), lt.semirings.Real)
+  with pytest.raises(ValueError, match=r'weights\.shape\[-1\] should be 13'):
+    ctx.backward_broadcast(torch.zeros([4]))
+  # CSR of incoming arcs: every arc once, grouped by destination, ascending inside a group
+  t, off, arcs = ctx.kernel_tables('cpu')
+  assert off[0] == 0 and off[-1] == 39 and sorted(arcs.tolist()) == list(range(39))
+  flat = t.reshape(-1)
+  for q in range(13):
+    grp = arcs[off[q]:off[q + 1]]
+    assert bool((flat[grp.long()] == q).all())
+    assert grp.tolist() == sorted(grp.tolist())
+
+
+def test_shared_rnn_cacher():
+  """tests/weight_fns_test.py:120-193: state ordering with a fake RNN cell."""
+  import last_torch_b200 as lt
+  pad, start = -2, -1
+
+  class FakeRNNCell(torch.nn.RNNCellBase):
+    def __init__(self, input_size, hidden_size, bias, num_chunks, device=None, dtype=None):
+      super().__init__(input_size, hidden_size, bias, num_chunks, device, dtype)
+
+    def forward(self, inputs, carry=None):
+      if carry is None:
+        carry = torch.full((1, self.hidden_size), pad)
+      carry = torch.concat(([carry[..., 1:], inputs[..., :1]]), dim=-1)
+      return carry, carry
+
+  embeddings = torch.broadcast_to(torch.Tensor([start, 1, 2, 3]).unsqueeze(-1), (4, 6))
+  cacher = lt.weight_fns.SharedRNNCacher(
+      vocab_size=3, context_size=2, rnn_size=4, rnn_embedding_size=6,
+      rnn_cell=FakeRNNCell(input_size=3, hidden_size=4, bias=False, num_chunks=1))
+  cacher.embedding = torch.nn.Embedding.from_pretrained(embeddings)
+  npt.assert_array_equal(cacher(), [
+      [pad, pad, pad, start],
+      [pad, pad, start, 1], [pad, pad, start, 2], [pad, pad, start, 3],
+      [pad, start, 1, 1], [pad, start, 1, 2], [pad, start, 1, 3],
+      [pad, start, 2, 1], [pad, start, 2, 2], [pad, start, 2, 3],
+      [pad, start, 3, 1], [pad, start, 3, 2], [pad, start, 3, 3]])
+  cacher = lt.weight_fns.SharedRNNCacher(
+      vocab_size=3, context_size=0, rnn_size=4, rnn_embedding_size=6,
+      rnn_cell=FakeRNNCell(input_size=3, hidden_size=4, bias=False, num_chunks=1))
+  cacher.embedding = torch.nn.Embedding.from_pretrained(embeddings)
+  npt.assert_array_equal(cacher(), [[pad, pad, pad, start]])
+  # the default cell is registered once (trainable, deterministic across calls: SURVEY D7)
+  cacher = lt.weight_fns.SharedRNNCacher(vocab_size=3, context_size=2, rnn_size=4,
+                                         rnn_embedding_size=6)
+  assert len(list(cacher.parameters())) == 5
+  out1, out2 = cacher(), cacher()
+  assert out1.shape == (13, 4)
+  npt.assert_array_equal(out1.detach(), out2.detach())

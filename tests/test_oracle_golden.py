@@ -249,3 +249,27 @@ def test_c_oracle_matches_numpy_oracle(vnk):
   npt.assert_allclose(cl[fin], ol[fin], rtol=1e-5, atol=1e-5)
   npt.assert_allclose(cgb, ogb, rtol=1e-4, atol=2e-5)
   npt.assert_allclose(cgl, ogl, rtol=1e-4, atol=2e-5)
+
+
+def test_next_state_table_known_answers():
+  # tests/contexts_test.py:189-239: NextStateTable built from FullNGram(3, 2)
+  table = O.FullNGram(3, 2).next_state_table()
+  assert table.shape == (13, 3)
+  ctx = O.NextStateTable(table)
+  assert ctx.shape() == (13, 3) and ctx.start() == 0
+  npt.assert_array_equal(ctx.next_state([0, 1, 3, 4, 12], [1, 2, 3, 1, 2]), [1, 5, 12, 4, 11])
+  npt.assert_array_equal(ctx.next_state([0, 1, 3, 4, 12], [0, 0, 0, 0, 0]), [0, 1, 3, 4, 12])
+  npt.assert_array_equal(
+      ctx.forward_reduce(np.arange(39, dtype=np.float64).reshape(1, 13, 3), O.REAL),
+      [[0, 0, 1, 2, 3 * 4 + 54, 4 * 4 + 54, 5 * 4 + 54, 6 * 4 + 54, 7 * 4 + 54, 8 * 4 + 54,
+        9 * 4 + 54, 10 * 4 + 54, 11 * 4 + 54]])
+  npt.assert_array_equal(ctx.backward_broadcast(np.arange(13).reshape(1, 13)),
+                         [[[1, 2, 3]] + [[4, 5, 6], [7, 8, 9], [10, 11, 12]] * 4])
+  npt.assert_array_equal(ctx.walk_states([2, 3, 1]), [0, 2, 9, 10])
+  npt.assert_array_equal(ctx.walk_states([2, 0, 0, 3, 1]), [0, 2, 2, 2, 9, 10])
+  # every semiring agrees with the closed-form FullNGram reduction on the same DFA
+  rng = np.random.RandomState(0)
+  w = rng.randn(2, 13, 3)
+  full = O.FullNGram(3, 2)
+  for sr in (O.REAL, O.LOG, O.MAXTROPICAL):
+    npt.assert_allclose(ctx.forward_reduce(w, sr), full.forward_reduce(w, sr), rtol=1e-12)
