@@ -223,6 +223,23 @@ int lt_table_reduce_backward(int semiring, const float* w, const float* out,
                              const int32_t* table, int64_t outer, int C, int V,
                              float* grad_w, void* stream);
 
+/* ---- local normalisation epilogues (weight_fns.py:99-136) ---------------------
+ * hat_normalize / log_softmax_normalize on M rows of (blank [M], lexical [M,V]):
+ *   LT_NORM_HAT          blank' = blank - softplus(blank), lex' = log_softmax(lex) - softplus(blank)
+ *   LT_NORM_LOG_SOFTMAX  (blank', lex') = log_softmax(blank ++ lex)
+ * backward: gradients w.r.t. the INPUTS from the cotangents of the outputs (the
+ * normalisers are recomputed from the inputs).
+ */
+#define LT_NORM_HAT 0
+#define LT_NORM_LOG_SOFTMAX 1
+int lt_local_normalize_forward(int mode, const float* blank, const float* lexical,
+                               int64_t M, int V, float* out_blank, float* out_lexical,
+                               void* stream);
+int lt_local_normalize_backward(int mode, const float* blank, const float* lexical,
+                                const float* grad_out_blank,
+                                const float* grad_out_lexical, int64_t M, int V,
+                                float* grad_blank, float* grad_lexical, void* stream);
+
 /* ---- K4: JointWeightFn (weight_fns.py:194-227) -------------------------------
  * joint = tanh(cache @ w_ctx^T + frames @ w_frame^T)   [N, C, H]
  * blank = joint @ w_blank + b_blank                     [N, C]

@@ -69,6 +69,9 @@ SIGNATURES = {
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_table_reduce_forward': [_c_int, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr, _ptr,
                                 _ptr],
+    'lt_local_normalize_forward': [_c_int, _ptr, _ptr, _c_i64, _c_int, _ptr, _ptr, _ptr],
+    'lt_local_normalize_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _ptr, _ptr,
+                                    _ptr],
     'lt_table_reduce_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int,
                                  _ptr, _ptr],
 }

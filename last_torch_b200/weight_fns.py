@@ -59,14 +59,58 @@ class WeightFnCacher(nn.Module, Generic[T], abc.ABC):
     """Builds the cached data."""
 
 
+class _LocalNormalize(torch.autograd.Function):
+  """Fused row-wise normaliser (csrc/normalize.cu) for CUDA fp32 weights."""
+
+  @staticmethod
+  def forward(ctx, blank, lexical, mode):
+    from . import _native as N
+    blank = N.require_cuda(blank, 'blank')
+    lexical = N.require_cuda(lexical, 'lexical')
+    v = lexical.shape[-1]
+    m = blank.numel()
+    ob, ol = torch.empty_like(blank), torch.empty_like(lexical)
+    with torch.cuda.device(blank.device):
+      N.check(N.lib().lt_local_normalize_forward(
+          mode, N.ptr(blank), N.ptr(lexical), m, v, N.ptr(ob), N.ptr(ol),
+          N.stream_ptr(blank.device)), 'lt_local_normalize_forward')
+    ctx.save_for_backward(blank, lexical)
+    ctx.mode = mode
+    return ob, ol
+
+  @staticmethod
+  def backward(ctx, gb, gl):
+    from . import _native as N
+    blank, lexical = ctx.saved_tensors
+    gb = N.require_cuda(gb, 'grad_blank')
+    gl = N.require_cuda(gl, 'grad_lexical')
+    db, dl = torch.empty_like(blank), torch.empty_like(lexical)
+    with torch.cuda.device(blank.device):
+      N.check(N.lib().lt_local_normalize_backward(
+          ctx.mode, N.ptr(blank), N.ptr(lexical), N.ptr(gb), N.ptr(gl), blank.numel(),
+          lexical.shape[-1], N.ptr(db), N.ptr(dl), N.stream_ptr(blank.device)),
+          'lt_local_normalize_backward')
+    return db, dl, None
+
+
+def _on_kernel_path(blank, lexical) -> bool:
+  return (blank.is_cuda and lexical.is_cuda and blank.dtype == torch.float32 and
+          lexical.dtype == torch.float32 and lexical.shape[:-1] == blank.shape)
+
+
 def hat_normalize(blank: torch.Tensor, lexical: torch.Tensor):
-  """HAT local normalisation (weight_fns.py:99-117)."""
+  """HAT local normalisation (weight_fns.py:99-117).  CUDA fp32 weights go through
+  the fused kernel; host tensors (the reference's unit-test use) keep the formula."""
+  if _on_kernel_path(blank, lexical):
+    return _LocalNormalize.apply(blank, lexical, 0)
   z = F.softplus(blank)
   return blank - z, F.log_softmax(lexical, dim=-1) - z.unsqueeze(-1)
 
 
 def log_softmax_normalize(blank: torch.Tensor, lexical: torch.Tensor):
   """Joint log-softmax over blank ++ lexical (weight_fns.py:120-136)."""
+  if _on_kernel_path(blank, lexical):
+    return _LocalNormalize.apply(blank, lexical, 1)
   all_weights = F.log_softmax(torch.cat([blank.unsqueeze(-1), lexical], dim=-1), dim=-1)
   return all_weights[..., 0], all_weights[..., 1:]
 

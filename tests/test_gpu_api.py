@@ -330,3 +330,72 @@ def test_no_cpu_fallback():
   lt = _lt()
   with pytest.raises(RuntimeError, match='no CPU fallback'):
     lt.semirings.Log.plus(torch.zeros([2], device='cpu'), torch.zeros([2], device='cpu'))
+
+
+@pytest.mark.parametrize('v', [2, 31, 256])
+def test_local_normalizers(v):
+  """hat_normalize / log_softmax_normalize kernels (weight_fns.py:99-136): the reference's
+  known answers (tests/weight_fns_test.py:25-41), probabilities summing to one, and values and
+  gradients against the reference formula evaluated in float64."""
+  import torch.nn.functional as F
+  import last_torch_b200 as lt
+  W = lt.weight_fns
+  blank = torch.tensor([2., 7.], device='cuda')
+  lexical = torch.tensor([[0., 1.], [3., 5.]], device='cuda')
+  nb, nl = W.hat_normalize(blank, lexical)
+  sp = np.log1p(np.exp(np.array([2., 7.])))                      # softplus(blank)
+  lse = np.log(np.exp(np.array([[0., 1.], [3., 5.]])).sum(-1))
+  npt.assert_allclose(nb.cpu(), np.array([2., 7.]) - sp, rtol=1e-5, atol=1e-7)
+  npt.assert_allclose(nl.cpu(), np.array([[0., 1.], [3., 5.]]) - lse[:, None] - sp[:, None],
+                      rtol=1e-5)
+  npt.assert_allclose((nb.exp() + nl.exp().sum(-1)).cpu(), [1, 1], rtol=1e-6)
+  nb, nl = W.log_softmax_normalize(blank, lexical)
+  npt.assert_allclose(nb.cpu(), [-0.40760595, -0.14293164], rtol=1e-5)
+  npt.assert_allclose(nl.cpu(), [[-2.407606, -1.4076059], [-4.1429315, -2.1429315]], rtol=1e-5)
+  g = torch.Generator(device='cuda').manual_seed(v)
+  b = (torch.randn([3, 5, 7], device='cuda', generator=g) * 3).requires_grad_()
+  l = (torch.randn([3, 5, 7, v], device='cuda', generator=g) * 3).requires_grad_()
+  cb = torch.randn(b.shape, device='cuda', generator=g)
+  cl = torch.randn(l.shape, device='cuda', generator=g)
+  for name in ['hat', 'log_softmax']:
+    fn = W.hat_normalize if name == 'hat' else W.log_softmax_normalize
+    ob, ol = fn(b, l)
+    npt.assert_allclose((ob.exp() + ol.exp().sum(-1)).detach().cpu(), 1.0, rtol=2e-5)
+    gb, gl = torch.autograd.grad((ob * cb).sum() + (ol * cl).sum(), [b, l])
+    b64, l64 = b.detach().double().requires_grad_(), l.detach().double().requires_grad_()
+    if name == 'hat':
+      z = F.softplus(b64)
+      rb, rl = b64 - z, F.log_softmax(l64, dim=-1) - z.unsqueeze(-1)
+    else:
+      a = F.log_softmax(torch.cat([b64.unsqueeze(-1), l64], dim=-1), dim=-1)
+      rb, rl = a[..., 0], a[..., 1:]
+    rgb, rgl = torch.autograd.grad((rb * cb.double()).sum() + (rl * cl.double()).sum(), [b64, l64])
+    npt.assert_allclose(ob.detach().cpu(), rb.detach().cpu(), rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(ol.detach().cpu(), rl.detach().cpu(), rtol=1e-5, atol=1e-5)
+    npt.assert_allclose(gb.cpu(), rgb.cpu(), rtol=1e-4, atol=1e-5)
+    npt.assert_allclose(gl.cpu(), rgl.cpu(), rtol=1e-4, atol=1e-5)
+
+
+def test_locally_normalized_lattice_loss():
+  """A locally normalised weight function skips the denominator (lattices.py:178-179):
+  loss = -numerator; probabilities of all label strings of a tiny lattice sum to one."""
+  import itertools
+  import last_torch_b200 as lt
+  torch.manual_seed(0)
+  vocab, t = 2, 3
+  context = lt.contexts.FullNGram(vocab_size=vocab, context_size=1)
+  table = torch.randn([1, t, context.num_states(), 1 + vocab], device='cuda')
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher(),
+      weight_fn_factory=lambda _: lt.weight_fns.LocallyNormalizedWeightFn(
+          lt.weight_fns.TableWeightFn(table), lt.weight_fns.log_softmax_normalize))
+  frames = torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None]
+  total = 0.0
+  for u in range(t + 1):
+    for labels in itertools.product(range(1, vocab + 1), repeat=u):
+      lab = torch.tensor([list(labels) + [1] * (t - u)], device='cuda')
+      loss = lattice(frames=frames, num_frames=torch.tensor([t], device='cuda'), labels=lab,
+                     num_labels=torch.tensor([u], device='cuda'), cache=None)
+      total += float(torch.exp(-loss))
+  npt.assert_allclose(total, 1.0, rtol=1e-5)
