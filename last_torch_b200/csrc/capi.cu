@@ -141,6 +141,8 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
   if (lattice_fast_supported(g, max_expansions, flags, lexical) &&
       reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
     return lattice_backward_fast_launch(semiring, g, p, (cudaStream_t)stream);
+  if (lattice_rows_supported(g, max_expansions, flags, lexical, grad_lexical))
+    return lattice_backward_rows_launch(semiring, g, p, sms, (cudaStream_t)stream);
   return lattice_backward_generic_launch(semiring, g, max_expansions, p, flags, sms,
                                          (cudaStream_t)stream);
 }

@@ -1,0 +1,328 @@
+// K2 for higher-order contexts (FullNGram context_size >= 2, FrameDependent, Log / Real):
+// the backward (beta) recursion + arc posteriors as "one 8-lane group per source row",
+// the companion of the thread-per-column forward in lattice_cols.cu.
+//
+// For a fixed source state p the V destinations next(p, .) are contiguous
+// (contexts.py:190-205): A + ((p - Alow) * V mod N) + y for the full-order part, 1 + p*V + y
+// for the low-order rows.  So a row of the frame is a contiguous stream of lexical[p, :]
+// against a contiguous, 16-byte aligned window of beta'.
+//   * cluster of CL CTAs per utterance, CTA r owns a contiguous range of source rows; a
+//     producer warp streams them with bulk (TMA) copies of 64 rows into a ring, several
+//     chunks ahead of the recursion (full / empty mbarriers);
+//   * 8 lanes per row, conflict-free LDS.128 of the slab and of the beta window; ONE
+//     exponential per arc serves both the row log-sum-exp (beta) and the arc posterior,
+//     which is written straight from registers with coalesced streaming stores;
+//   * beta lives in shared memory as a full replica per CTA (every CTA's windows wrap over all
+//     N full-order states), double-buffered, all-gathered with st.async + mbarrier
+//     complete_tx: no cluster barrier in the loop; two CTAs of 288 threads per SM.
+// Log arithmetic in log2 units as in lattice_fast2.cu.
+//
+// Reference semantics: alignments.py:300-318, lattices.py:775-779, contexts.py:232-256.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "fast_ptx.cuh"
+#include "params.cuh"
+
+namespace lt {
+
+namespace {
+
+using namespace fastptx;
+
+constexpr int kRConsumers = 256;
+constexpr int kRThreads = kRConsumers + 32;
+constexpr int kRChunk = 64;                   // rows per ring stage
+constexpr int kRPad = 3;                      // beta entry q at index kRPad + q (windows 16-B aligned)
+
+__device__ __forceinline__ void mbar_arrive_r(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct RowsParams {
+  NGram g;
+  int B, T;
+  int stages, cl, rpc;                        // ring depth, cluster size, rows per CTA
+  const float* blank;
+  const float* lexical;
+  const int32_t* num_frames;
+  const float* alphas;
+  const float* dist;
+  const float* grad_dist;
+  float* grad_blank;
+  float* grad_lexical;
+  float* beta_final;
+};
+
+// first destination of source row p (its V destinations are contiguous)
+__device__ __forceinline__ int row_window(const NGram& g, int p) {
+  return p < g.Alow ? g.off + p * g.V : g.A + ((p - g.Alow) * g.V) % g.N;
+}
+
+template <int SR, int CHL>      // CHL = V / 32 float4 chunks per lane
+__global__ void __launch_bounds__(kRThreads, 2)
+lattice_backward_rows(const RowsParams p) {
+  using S = Sr<SR>;
+  extern __shared__ __align__(128) unsigned char rsmem[];
+  const NGram& g = p.g;
+  const int C = g.C, V = g.V;
+  const int NS = p.stages;
+  const uint32_t stage_bytes = (uint32_t)kRChunk * V * 4;
+  const int BP = (kRPad + C + 3 + 3) & ~3;
+
+  float* tiles = reinterpret_cast<float*>(rsmem);
+  float* beta_buf = reinterpret_cast<float*>(rsmem + (size_t)NS * stage_bytes);   // [2][BP]
+  uint64_t* full = reinterpret_cast<uint64_t*>(beta_buf + 2 * BP);
+  uint64_t* empty = full + NS;
+  uint64_t* xbar = empty + NS;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t CL = p.cl;
+  const uint32_t rank = cluster_ctarank();
+  const int b = blockIdx.x / CL;
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  const size_t bt0 = (size_t)b * p.T;
+  const int p_lo = min(C, (int)rank * p.rpc), p_hi = min(C, p_lo + p.rpc);
+  const int nrows = p_hi - p_lo;
+  const int nchunks = (nrows + kRChunk - 1) / kRChunk;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), kRConsumers / 32);
+    }
+    mbar_init(smem_u32(&xbar[0]), 1);
+    mbar_init(smem_u32(&xbar[1]), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  for (int c = tid; c < 2 * BP; c += kRThreads) beta_buf[c] = to_dom<SR>(S::one());   // lattices.py:789-790
+  __syncthreads();
+  cluster_sync_all();
+
+  if (warp == kRConsumers / 32) {
+    // ------------------------------------------------------------ producer warp
+    if (lane == 0 && nrows > 0) {
+      int stage = 0;
+      uint32_t use = 0;
+      for (int it = 0; it < nf; ++it) {
+        const int t = nf - 1 - it;
+        const float* frame = p.lexical + (bt0 + t) * (size_t)C * V;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int r0 = p_lo + ch * kRChunk;
+          const uint32_t bytes = (uint32_t)min(kRChunk, p_hi - r0) * V * 4;
+          if (use > 0) mbar_wait(smem_u32(&empty[stage]), (use - 1) & 1);
+          const uint32_t bar = smem_u32(&full[stage]);
+          mbar_arrive_expect_tx(bar, bytes);
+          bulk_load_1d(smem_u32(tiles) + stage * stage_bytes, frame + (size_t)r0 * V, bytes, bar);
+          if (++stage == NS) { stage = 0; ++use; }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- consumers
+    const int sub = lane >> 3, sl = lane & 7;       // row within the warp pass, lane within the row
+    const int rloc = warp * 4 + sub;                // 0 .. 31: row inside a 32-row pass
+    const float logz = p.dist[b];
+    const float logz2 = (SR == LT_LOG) ? logz * kLog2e : logz;
+    const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
+    const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
+    const bool owner = sl == 0;
+
+    // padding frames: zero gradients (lattices.py:775-779)
+    for (int t = nf; t < p.T; ++t) {
+      float4* gl = reinterpret_cast<float4*>(p.grad_lexical + ((bt0 + t) * (size_t)C + p_lo) * V);
+      for (int i = tid; i < nrows * V / 4; i += kRConsumers)
+        stg_stream4(reinterpret_cast<float*>(gl + i), make_float4(0, 0, 0, 0));
+      for (int i = tid; i < nrows; i += kRConsumers) p.grad_blank[(bt0 + t) * C + p_lo + i] = 0.f;
+    }
+
+    // alpha_t[p], blank_t[p] of the two rows this owner lane handles in the NEXT chunk
+    float n_alpha[2] = {0.f, 0.f}, n_blank[2] = {0.f, 0.f};
+    auto prefetch = [&](int it, int ch) {
+      if (!owner || it >= nf) return;
+      const size_t o = (bt0 + (nf - 1 - it)) * C;
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int row = p_lo + ch * kRChunk + ps * 32 + rloc;
+        if (row < p_hi) { n_alpha[ps] = p.alphas[o + row]; n_blank[ps] = ldg_stream(p.blank + o + row); }
+      }
+    };
+    if (nrows > 0) prefetch(0, 0);
+
+    const uint32_t expect = (uint32_t)C * 4;
+    int stage = 0;
+    uint32_t use = 0;
+    for (int it = 0; it < nf; ++it) {
+      const int t = nf - 1 - it;
+      float* beta = beta_buf + (it & 1) * BP;          // beta_{t+1}; entry q at beta[kRPad + q]
+      float* nxt = beta_buf + ((it + 1) & 1) * BP;
+      if (it > 0) mbar_wait(smem_u32(&xbar[it & 1]), ((it - 1) >> 1) & 1);
+      if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), expect);
+      float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
+      float* gb = p.grad_blank + (bt0 + t) * C;
+
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const float c_alpha[2] = {n_alpha[0], n_alpha[1]}, c_blank[2] = {n_blank[0], n_blank[1]};
+        if (ch + 1 < nchunks) prefetch(it, ch + 1); else prefetch(it + 1, 0);
+        mbar_wait(smem_u32(&full[stage]), use & 1);
+        const float* tile = tiles + (size_t)stage * (stage_bytes / 4);
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int lrow = ps * 32 + rloc;                 // row inside the chunk
+          const int prow = p_lo + ch * kRChunk + lrow;     // source state
+          const bool live = prow < p_hi;
+          // a warp covers 4 consecutive rows; lanes of dead rows still take part in shuffles
+          const int pc = live ? prow : p_lo;
+          const float* trow = tile + (size_t)(live ? lrow : 0) * V;
+          const float* bwin = beta + kRPad + row_window(g, pc);
+          float4 x[CHL];
+#pragma unroll
+          for (int i = 0; i < CHL; ++i) {
+            const int c4 = (sl + 8 * i) * 4;
+            const float4 w = *reinterpret_cast<const float4*>(trow + c4);
+            const float4 bn = *reinterpret_cast<const float4*>(bwin + c4);
+            x[i] = make_float4(arc<SR>(w.x, bn.x), arc<SR>(w.y, bn.y), arc<SR>(w.z, bn.z),
+                               arc<SR>(w.w, bn.w));
+          }
+          const float alpha_raw = __shfl_sync(0xffffffffu, c_alpha[ps], lane & ~7);
+          const float alpha_p = to_dom<SR>(alpha_raw);
+          float* grow = gl + (size_t)pc * V;
+          float rowsum;
+          if constexpr (SR == LT_LOG) {
+            float m = neg_inf();
+#pragma unroll
+            for (int i = 0; i < CHL; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            const float ms = msafe(m);
+            const float rs = scale_ok ? gscale * ex2(alpha_p + ms - logz2) : 0.f;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < CHL; ++i) {
+              float4 e;
+              e.x = ex2(x[i].x - ms); e.y = ex2(x[i].y - ms);
+              e.z = ex2(x[i].z - ms); e.w = ex2(x[i].w - ms);
+              s += (e.x + e.y) + (e.z + e.w);
+              if (live) stg_stream4(grow + (sl + 8 * i) * 4, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            rowsum = ms + __log2f(s);
+          } else {
+            float s = 0.f;
+            const float ga = gscale * alpha_p;
+#pragma unroll
+            for (int i = 0; i < CHL; ++i) {
+              const int c4 = (sl + 8 * i) * 4;
+              const float4 bn = *reinterpret_cast<const float4*>(bwin + c4);
+              s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+              if (live) stg_stream4(grow + c4, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            rowsum = s;
+          }
+          if (owner && live) {
+            const float bp = beta[kRPad + prow];
+            const float bb = arc<SR>(c_blank[ps], bp);
+            if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
+            else gb[prow] = gscale * alpha_raw * bp;
+            xchg_store(nxt, kRPad + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
+                       &xbar[(it + 1) & 1], CL);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_r(smem_u32(&empty[stage]));
+        if (++stage == NS) { stage = 0; ++use; }
+      }
+    }
+    float* beta = beta_buf + (nf & 1) * BP;
+    if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
+    if (p.beta_final)
+      for (int i = tid; i < nrows; i += kRConsumers)
+        p.beta_final[(size_t)b * C + p_lo + i] = from_dom<SR>(beta[kRPad + p_lo + i]);
+  }
+  __syncthreads();
+  cluster_sync_all();
+}
+
+template <typename KernelT>
+static int launch_rows(KernelT kernel, int grid, size_t smem, int cluster, cudaStream_t stream,
+                       const RowsParams& p) {
+  LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kRThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LT_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  note_launch();
+  return LT_OK;
+}
+
+static size_t rows_fixed_bytes(const NGram& g) {
+  const size_t BP = (kRPad + g.C + 3 + 3) & ~3;
+  return sizeof(float) * 2 * BP + 8 * (2 * 8 + 2) + 256;
+}
+
+}  // namespace
+
+bool lattice_rows_supported(const NGram& g, int k, unsigned flags, const void* lexical,
+                            const void* grad_lexical) {
+  if (flags & LT_FLAG_FORCE_GENERIC) return false;
+  if ((flags >> LT_FLAG_CLUSTER_SHIFT) & 0xf) return false;
+  if (k >= 1 || g.n < 2) return false;
+  if (g.V % 32 != 0 || g.V > 256) return false;
+  if (reinterpret_cast<uintptr_t>(lexical) % 16 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(grad_lexical) % 16 != 0) return false;
+  return rows_fixed_bytes(g) + 2 * (size_t)kRChunk * g.V * 4 <= 112 * 1024;
+}
+
+int lattice_backward_rows_launch(int semiring, const NGram& g, const BwdParams& base, int sm_count,
+                                 cudaStream_t stream) {
+  // widest cluster that still gives every CTA a few chunks of rows
+  int cl = 8;
+  while (cl > 1 && g.C / cl < 2 * kRChunk) cl >>= 1;
+  const size_t budget = 112 * 1024;
+  const size_t fixed = rows_fixed_bytes(g);
+  const size_t stage = (size_t)kRChunk * g.V * 4;
+  int stages = (int)((budget - fixed) / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("rows path: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
+  const size_t smem = stage * stages + fixed;
+  RowsParams p = {};
+  p.g = g; p.B = base.B; p.T = base.T; p.stages = stages; p.cl = cl;
+  p.rpc = (g.C + cl - 1) / cl;
+  p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
+  p.alphas = base.alphas; p.dist = base.dist; p.grad_dist = base.grad_dist;
+  p.grad_blank = base.grad_blank; p.grad_lexical = base.grad_lexical; p.beta_final = base.beta_final;
+  const int grid = base.B * cl;
+  (void)sm_count;
+#define LT_ROWS(SR)                                                                        \
+  switch (g.V / 32) {                                                                      \
+    case 1: return launch_rows(lattice_backward_rows<SR, 1>, grid, smem, cl, stream, p);   \
+    case 2: return launch_rows(lattice_backward_rows<SR, 2>, grid, smem, cl, stream, p);   \
+    case 3: return launch_rows(lattice_backward_rows<SR, 3>, grid, smem, cl, stream, p);   \
+    case 4: return launch_rows(lattice_backward_rows<SR, 4>, grid, smem, cl, stream, p);   \
+    case 5: return launch_rows(lattice_backward_rows<SR, 5>, grid, smem, cl, stream, p);   \
+    case 6: return launch_rows(lattice_backward_rows<SR, 6>, grid, smem, cl, stream, p);   \
+    case 7: return launch_rows(lattice_backward_rows<SR, 7>, grid, smem, cl, stream, p);   \
+    default: return launch_rows(lattice_backward_rows<SR, 8>, grid, smem, cl, stream, p);  \
+  }
+  if (semiring == LT_LOG) { LT_ROWS(LT_LOG) }
+  LT_ROWS(LT_REAL)
+#undef LT_ROWS
+}
+
+}  // namespace lt

@@ -98,6 +98,11 @@ int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams&
 bool lattice_cols_supported(const NGram& g, int k, unsigned flags, const void* lexical);
 int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdParams& base,
                                 cudaStream_t stream);
+// 8-lanes-per-row TMA backward for context_size >= 2, FrameDependent (lattice_rows.cu)
+bool lattice_rows_supported(const NGram& g, int k, unsigned flags, const void* lexical,
+                            const void* grad_lexical);
+int lattice_backward_rows_launch(int semiring, const NGram& g, const BwdParams& base, int sm_count,
+                                 cudaStream_t stream);
 int viterbi_launch(const VitParams& base, cudaStream_t stream);
 int string_gather_launch(int V, int C, const float* blank, const float* lexical,
                          const int32_t* states, const int32_t* labels, int B, int T, int U1,

@@ -141,6 +141,7 @@ ORACLE_CASES = [
     (14, 2, 7, 32, 2, 3, 5, 1.0),        # thread-per-column path, cluster of 4, FLD(3)
     (15, 2, 5, 64, 2, -1, 5, 2.0),       # configs[2] width, cluster of 8, FrameDependent
     (16, 3, 8, 8, 3, 2, 6, 1.0),         # thread-per-column path, 4-gram states (n=3), cluster of 2
+    (17, 3, 9, 32, 2, -1, 5, 1.5),       # cols forward + 8-lanes-per-row backward, C = 1057
 ]
 
 
@@ -345,6 +346,46 @@ def test_fast_path_ties(flags):
   (gd,) = torch.autograd.grad(dist.sum(), table)
   npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
   npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+
+
+@pytest.mark.parametrize('vocab', [32, 64])
+def test_rows_backward_vs_generic(vocab):
+  """context_size 2, FrameDependent: the TMA column-forward / row-backward kernels against the
+  generic kernels -- Log and Real distances, alphas and gradients, with -inf arcs, ragged and
+  empty utterances and an upstream gradient that differs per utterance."""
+  lt = _lt()
+  b, t, ctx = 4, 7, 2
+  c = 1 + vocab + vocab * vocab
+  rng = np.random.RandomState(vocab)
+  table_np = rng.randn(b, t, c, 1 + vocab).astype(np.float32)
+  drop = rng.rand(b, t, c, 1 + vocab) < 0.03
+  drop[..., 0] = False
+  table_np[drop] = -np.inf
+  nf = cuda(np.array([7, 3, 0, 6]))
+  cot = cuda(np.array([1.0, -0.5, 2.0, 0.25]))
+  frames = frames_for(b, t)
+  for name in ['Log', 'Real']:
+    sr = getattr(lt.semirings, name)
+    tab = table_np if name == 'Log' else (np.exp(np.clip(table_np, -40, 5) * 0.25) /
+                                          (1 + vocab)).astype(np.float32)
+    res = []
+    for flags in [1, 0]:
+      table = cuda(tab).requires_grad_()
+      lattice = make_lattice(vocab, ctx, -1, table, flags)
+      dist, alphas = lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=sr)
+      (gd,) = torch.autograd.grad((dist * cot).sum(), table)
+      res.append((dist.detach().cpu().numpy(), alphas.cpu().numpy(), gd.cpu().numpy()))
+    (d0, a0, g0), (d1, a1, g1) = res
+    npt.assert_allclose(d1, d0, rtol=2e-6, atol=1e-6, err_msg=name)
+    fin = np.isfinite(a0)
+    npt.assert_array_equal(np.isfinite(a1), fin)
+    npt.assert_allclose(a1[fin], a0[fin], rtol=2e-6, atol=2e-5, err_msg=name)
+    assert np.all(np.isfinite(g1))
+    if name == 'Log':
+      assert np.all(g1[drop] == 0)
+    npt.assert_allclose(g1, g0, rtol=1e-4, atol=2e-6, err_msg=name)
+    assert np.all(g1[2] == 0)                               # empty utterance
+    assert np.all(g1[1, 3:] == 0)                           # padding frames
 
 
 @pytest.mark.parametrize('k', [-1, 2])
