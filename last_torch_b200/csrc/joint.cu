@@ -193,7 +193,13 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
     if (rc) return rc;
     simt_parts = 2;
   }
-  if (joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+  if (joint_wgrad2_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+    int rc = joint_wgrad2_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
+                                 grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
+                                 (cudaStream_t)stream);
+    if (rc) return rc;
+    simt_parts &= ~2;
+  } else if (joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     int rc = joint_wgrad_tc_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
                                    grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
                                    (cudaStream_t)stream);

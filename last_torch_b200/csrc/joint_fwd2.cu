@@ -1,0 +1,367 @@
+// JointWeightFn forward on tcgen05 with CTA PAIRS (cta_group::2), second generation of
+// joint_forward_tc_kernel (joint_tc.cu):
+//   lexical[m, :] = tanh(pc[c] + pf[n]) . W_vocab^T + b_vocab,  blank[m] = tanh(..) . w_blank + b
+// One tcgen05.mma.cta_group::2 instruction multiplies a 256-row tile (128 rows per CTA of the
+// pair) by the V columns of W_vocab.  Each CTA produces the tanh / bf16x3-split A operand of
+// its own 128 rows and loads only HALF of the W_vocab chunk (V/2 rows); the hardware feeds both
+// halves to both SMs.  Compared with the single-CTA kernel the B operand costs half the TMA
+// traffic and half the shared-memory reads per SM -- the single-CTA kernel saturates the
+// 128 B/clk shared-memory port (SS-mode MMA reads + operand stores) -- and the stage shrinks
+// from 96 KB to 64 KB, so the ring has three stages instead of two.
+//
+// Protocol (rank 0 of the pair = leader, the only MMA issuer):
+//   full[s]   (leader's)  producers of BOTH CTAs + both TMA threads -> MMA
+//   empty[s]  (per CTA)   MMA commit, multicast to both CTAs -> producers, TMA thread
+//   tfull[a]  (per CTA)   MMA commit, multicast -> epilogue warps of each CTA (own 128 rows)
+//   tempty[a] (leader's)  epilogue threads of BOTH CTAs -> MMA
+// Remote arrivals use the leader's copy of the barrier: the shared::cluster address of the
+// local variable with the peer bit (bit 24) cleared.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "params.cuh"
+#include "umma.cuh"
+
+namespace lt {
+namespace {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ void mbar_init_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTF_WAIT%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTF_DONE%=;\n"
+      "bra LTF_WAIT%=;\n"
+      "LTF_DONE%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTFC_WAIT%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTFC_DONE%=;\n"
+      "bra LTFC_WAIT%=;\n"
+      "LTFC_DONE%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::
+                   "r"(bar & kPeerBitMask), "r"(bytes) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's shared memory, the bytes complete on the leader's barrier
+__device__ __forceinline__ void tma_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                           uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1),
+      "r"(bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this address in BOTH CTAs once the MMAs issued so far retire
+__device__ __forceinline__ void commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::
+                   "r"(smem_result_addr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (2.f * kLog2e)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(-2.f, r, 1.f);
+}
+__device__ __forceinline__ void store_block_coalesced(const float (&v)[32], float* tr, int lane,
+                                                      float* out_row0, size_t row_stride,
+                                                      int rows_valid) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+  __syncwarp();
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r)
+    if (r < rows_valid) out_row0[(size_t)r * row_stride + lane] = tr[r * 33 + lane];
+}
+
+constexpr int kF2Stages = 3;
+constexpr int kF2ProdWarps = 8;
+constexpr int kF2Threads = (6 + kF2ProdWarps) * 32;
+constexpr int kF2Producers = kF2ProdWarps * 32;
+constexpr int kF2Passes = 128 / (kF2ProdWarps * 4);
+
+struct JointFwd2Params {
+  const float* pc;       // [C, H]
+  const float* pf;       // [N, H]
+  const float* w_blank;  // [H]
+  const float* b_vocab;  // [V]
+  float b_blank;
+  long long M;           // N * C
+  int C, H, V;
+  float* blank;          // [M]
+  float* lexical;        // [M, V]
+};
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+joint_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi,
+                         const __grid_constant__ CUtensorMap map_lo, const JointFwd2Params p) {
+  extern __shared__ __align__(1024) unsigned char f2smem_raw[];
+  unsigned char* base = f2smem_raw + ((1024u - (smem_u32(f2smem_raw) & 1023u)) & 1023u);
+  const int V = p.V, H = p.H, Vh = V / 2;
+  const uint32_t a_bytes = 128 * 128;                 // one 128 x 64 bf16 tile
+  const uint32_t bh_bytes = (uint32_t)Vh * 128;       // this CTA's half of a V x 64 bf16 tile
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * 128 * 128;     // A_hi | A_lo | B_hi/2 | B_lo/2
+  float* s_wb = reinterpret_cast<float*>(base + kF2Stages * stage_bytes);   // [H]
+  float* s_bias = s_wb + H;                                                 // [V]
+  float* s_tr = s_bias + 256;                                               // 4 x [32][33]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kF2Stages;
+  uint64_t* tfull = bars + 2 * kF2Stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nchunks = H / 64;
+  const long long num_tiles = (p.M + 255) / 256;      // 256-row tiles, 128 rows per CTA
+
+  for (int i = tid; i < H; i += kF2Threads) s_wb[i] = p.w_blank[i];
+  for (int i = tid; i < V; i += kF2Threads) s_bias[i] = p.b_vocab[i];
+  if (tid == 0) {
+    for (int s = 0; s < kF2Stages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), 2 * kF2Producers + 2);
+      mbar_init_n(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init_n(smem_u32(&tfull[a]), 1);
+      mbar_init_n(smem_u32(&tempty[a]), 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+  }
+  if (warp == 1) tmem_alloc_2cta(smem_u32(tmem_slot), 512);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  cluster_sync_all();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer: this CTA's half of B
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (long long tile = pair; tile < num_tiles; tile += npairs) {
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kF2Stages;
+          mbar_wait_parity(smem_u32(&empty[s]), ((g / kF2Stages) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full[s]);
+          const uint32_t dst = smem_u32(base) + s * stage_bytes + 2 * a_bytes;
+          mbar_expect_tx_leader(bar, 2 * bh_bytes);
+          tma_2d_2sm(dst, &map_hi, kc * 64, (int)rank * Vh, bar);
+          tma_2d_2sm(dst + 128 * 128, &map_lo, kc * 64, (int)rank * Vh, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma::make_idesc_bf16(256, V);
+      uint32_t g = 0, it = 0;
+      for (long long tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait_parity_cluster(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+        umma::fence_after_thread_sync();
+        const uint32_t d = tmem + acc * 256;
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kF2Stages;
+          mbar_wait_parity_cluster(smem_u32(&full[s]), (g / kF2Stages) & 1);
+          umma::fence_after_thread_sync();
+          const uint32_t sa = smem_u32(base) + s * stage_bytes;
+          const uint32_t sb = sa + 2 * a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
+            const uint64_t dal = umma::make_smem_desc_sw128(sa + a_bytes + k * 32);
+            const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
+            const uint64_t dbl = umma::make_smem_desc_sw128(sb + 128 * 128 + k * 32);
+            mma_bf16_2cta(d, dah, dbh, idesc, (kc | k) > 0);
+            mma_bf16_2cta(d, dah, dbl, idesc, 1);
+            mma_bf16_2cta(d, dal, dbh, idesc, 1);
+          }
+          commit_2cta(smem_u32(&empty[s]));            // stage reusable in both CTAs
+        }
+        commit_2cta(smem_u32(&tfull[acc]));            // accumulator complete in both CTAs
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------ epilogue: this CTA's 128 rows
+    const int quad = warp & 3;
+    uint32_t it = 0;
+    for (long long tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
+      umma::fence_after_thread_sync();
+      const long long m0 = tile * 256 + (long long)rank * 128 + quad * 32;
+      const int rows_valid = (int)max(0ll, min(32ll, p.M - m0));
+      float* out = p.lexical + (size_t)m0 * V;
+      for (int c0 = 0; c0 < V; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
+        store_block_coalesced(v, s_tr + quad * (32 * 33), lane, out + c0, (size_t)V, rows_valid);
+      }
+      umma::fence_before_thread_sync();
+      mbar_arrive_leader(smem_u32(&tempty[acc]));
+    }
+  } else {
+    // ------------------------------------------------ A producers: this CTA's 128 rows
+    const int pw = warp - 6;
+    const int ch = lane & 7, rsub = lane >> 3;
+    uint32_t g = 0;
+    for (long long tile = pair; tile < num_tiles; tile += npairs) {
+      const float* pc_row[kF2Passes];
+      const float* pf_row[kF2Passes];
+      bool valid[kF2Passes];
+      float bacc[kF2Passes];
+      const long long mbase = tile * 256 + (long long)rank * 128;
+#pragma unroll
+      for (int q = 0; q < kF2Passes; ++q) {
+        bacc[q] = 0.f;
+        const long long m = mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub;
+        valid[q] = m < p.M;
+        const long long n = valid[q] ? m / p.C : 0;
+        const int c = valid[q] ? (int)(m - n * p.C) : 0;
+        pc_row[q] = p.pc + (size_t)c * H + ch * 8;
+        pf_row[q] = p.pf + (size_t)n * H + ch * 8;
+      }
+      for (int kc = 0; kc < nchunks; ++kc, ++g) {
+        const int s = g % kF2Stages;
+        uint4 hi[kF2Passes], lo[kF2Passes];
+#pragma unroll
+        for (int q = 0; q < kF2Passes; ++q) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64 + 4));
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64 + 4));
+          float t[8] = {a0.x + f0.x, a0.y + f0.y, a0.z + f0.z, a0.w + f0.w,
+                        a1.x + f1.x, a1.y + f1.y, a1.z + f1.z, a1.w + f1.w};
+          const float* wb = s_wb + kc * 64 + ch * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
+            bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+          }
+          umma::split_pack8(t, hi[q], lo[q]);
+        }
+        mbar_wait_parity(smem_u32(&empty[s]), ((g / kF2Stages) & 1) ^ 1);
+        unsigned char* a_hi = base + s * stage_bytes;
+        unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+        for (int q = 0; q < kF2Passes; ++q) {
+          const uint32_t off = umma::swizzled_offset(q * (kF2ProdWarps * 4) + pw * 4 + rsub, ch);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_leader(smem_u32(&full[s]));
+      }
+#pragma unroll
+      for (int q = 0; q < kF2Passes; ++q) {
+        float bsum = bacc[q];
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+        if (valid[q] && ch == 0)
+          p.blank[mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub] = bsum + p.b_blank;
+      }
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
+}
+
+}  // namespace
+
+bool joint_fwd2_supported(int64_t N, int C, int H, int V) {
+  // Opt-in: measured 7.2 ms against 6.7 ms for the single-CTA kernel at configs[1] -- the forward
+  // is bound by the tanh / split producers (MUFU + load latency), not by the B operand, so
+  // halving the B traffic does not pay here.  Kept because it pins the cta_group::2 protocol
+  // (used by the weight-gradient kernel, joint_wgrad2.cu) on a kernel with a simple oracle.
+  if (getenv("LT_JOINT_SIMT") || !getenv("LT_JOINT_FWD_PAIR")) return false;
+  if (V != 256 && V != 128 && V != 64) return false;      // V/2 rows per CTA, 8-row atoms
+  if (H % 64 != 0 || H > 4096) return false;
+  return N * (int64_t)C >= 1;
+}
+
+// map_hi / map_lo: W_vocab [V, H] as bf16 hi / lo with box [64 x V/2] (SWIZZLE_128B)
+int joint_fwd2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const float* pc,
+                      const float* pf, const float* wb, float bb, const float* bv, int64_t N,
+                      int C, int H, int V, float* blank, float* lexical, cudaStream_t stream) {
+  JointFwd2Params p = {};
+  p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
+  p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
+  const size_t smem = (size_t)kF2Stages * (2 * 128 * 128 + 2 * 128 * 128) +
+                      sizeof(float) * (H + 256 + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
+  int dev = 0, sms = 0;
+  LT_CUDA(cudaGetDevice(&dev));
+  LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (p.M + 255) / 256;
+  long long pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  if (pairs < 1) pairs = 1;
+  LT_CUDA(cudaFuncSetAttribute(joint_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kF2Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LT_CUDA(cudaLaunchKernelEx(&cfg, joint_forward_tc2_kernel, map_hi, map_lo, p));
+  note_launch();
+  return LT_OK;
+}
+
+}  // namespace lt

@@ -1035,7 +1035,9 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   CUtensorMap map_hi, map_lo;
   cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)V};
   cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)V};
+  // CTA-pair kernel (joint_fwd2.cu): every CTA loads half of the W_vocab rows
+  const bool pair = joint_fwd2_supported(N, C, H, V);
+  cuuint32_t box[2] = {64, (cuuint32_t)(pair ? V / 2 : V)};
   cuuint32_t estr[2] = {1, 1};
   for (int i = 0; i < 2; ++i) {
     CUresult r = encode(i == 0 ? &map_hi : &map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -1047,6 +1049,8 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
       return LT_ERR_CUDA;
     }
   }
+  if (pair)
+    return joint_fwd2_launch(map_hi, map_lo, pc, pf, wb, bb, bv, N, C, H, V, blank, lexical, stream);
   JointTcParams p = {};
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;

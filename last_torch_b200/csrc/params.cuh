@@ -136,6 +136,11 @@ int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
 int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
                           const float* gb, const float* gl, int64_t N, int C, int H, int V,
                           float* gpc, float* gpf, void* workspace, cudaStream_t stream);
+// CTA-pair (cta_group::2) forward (joint_fwd2.cu)
+bool joint_fwd2_supported(int64_t N, int C, int H, int V);
+int joint_fwd2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo, const float* pc,
+                      const float* pf, const float* wb, float bb, const float* bv, int64_t N,
+                      int C, int H, int V, float* blank, float* lexical, cudaStream_t stream);
 // fused dgrad + reductions (joint_dgrad2.cu)
 bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                             const void* pf);
@@ -143,6 +148,12 @@ int joint_dgrad2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_
                         const float* pc, const float* pf, const float* wb, const float* gb,
                         const float* gl, int64_t N, int C, int H, int V, float* gpc, float* gpf,
                         cudaStream_t stream);
+// CTA-pair (cta_group::2) weight gradient (joint_wgrad2.cu)
+bool joint_wgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
+                            const void* pf);
+int joint_wgrad2_launch(const float* pc, const float* pf, const float* gb, const float* gl,
+                        int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
+                        float* gbv, cudaStream_t stream);
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,

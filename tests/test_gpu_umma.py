@@ -67,7 +67,14 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
       sb, sl = fn.all_frames(cache, frames)
     finally:
       del os.environ['LT_JOINT_SIMT']
+    os.environ['LT_JOINT_FWD_PAIR'] = '1'        # opt-in CTA-pair (cta_group::2) kernel
+    try:
+      pb, pl = fn.all_frames(cache, frames)
+    finally:
+      del os.environ['LT_JOINT_FWD_PAIR']
   scale = float(rl.abs().max())
+  assert float((pl[:, 0].double() - rl).abs().max()) / scale < 1e-5
+  assert float((pb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6) < 1e-5
   err_tc = float((kl[:, 0].double() - rl).abs().max()) / scale
   err_simt = float((sl[:, 0].double() - rl).abs().max()) / scale
   err_b = float((kb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6)
@@ -107,10 +114,19 @@ def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
       os.environ.pop('LT_JOINT_SIMT', None)
 
   ref, tc, simt = grads('ref'), grads('tc'), grads('simt')
-  for r, a, s in zip(ref, tc, simt):
+  # the CTA-pair (cta_group::2) kernels are opt-in; they must agree as well
+  os.environ['LT_JOINT_FWD_PAIR'] = '1'
+  os.environ['LT_JOINT_WGRAD_PAIR'] = '1'
+  try:
+    pair = grads('tc')
+  finally:
+    os.environ.pop('LT_JOINT_FWD_PAIR', None)
+    os.environ.pop('LT_JOINT_WGRAD_PAIR', None)
+  for r, a, s, q in zip(ref, tc, simt, pair):
     scale = float(r.abs().max()) + 1e-12
     assert float((s - r).abs().max()) / scale < 3e-5
     assert float((a - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((a - r).abs().max()) / scale)
+    assert float((q - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((q - r).abs().max()) / scale)
 
 
 def _probe_mn(at, bt, swap):
