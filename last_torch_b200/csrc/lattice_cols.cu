@@ -68,6 +68,50 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// On-chip number domain: the Log semiring is carried in LOG2 units (one bare MUFU.EX2 per arc,
+// w * log2(e) folded into an FFMA), Real / MaxTropical are carried as they are.
+template <int SR> struct Dom {
+  __device__ static float in(float x) { return SR == LT_LOG ? x * kLog2e : x; }
+  __device__ static float out(float x) { return SR == LT_LOG ? x * kLn2 : x; }
+  // on-chip value (x) natural-unit arc weight
+  __device__ static float times(float a, float w) {
+    if constexpr (SR == LT_LOG) return fmaf(w, kLog2e, a);
+    else if constexpr (SR == LT_MAXTROPICAL) return a + w;
+    else return a * w;
+  }
+  __device__ static float plus(float a, float b) {
+    if constexpr (SR == LT_LOG) return log2_add_exp2(a, b);
+    else return Sr<SR>::plus(a, b);
+  }
+};
+// (+)-accumulator in the on-chip domain: Acc<SR> for Real / MaxTropical, a log2-domain
+// (max, sum) pair for Log.
+template <int SR> struct DAcc : Acc<SR> {};
+template <> struct DAcc<LT_LOG> {
+  float m, s;
+  __device__ void init() { m = neg_inf(); s = 0.f; }
+  __device__ void add(float x, int) {
+    const float mn = fmaxf(m, x);
+    const float ms = msafe(mn);
+    const float sc = (m == neg_inf()) ? 0.f : ex2(msafe(m) - ms);
+    s = s * sc + ex2(x - ms);
+    m = mn;
+  }
+  template <int N> __device__ void add_chunk(const float (&x)[N], float cm) {
+    const float mn = fmaxf(m, cm);
+    const float ms = msafe(mn);
+    const float sc = (m == neg_inf()) ? 0.f : ex2(msafe(m) - ms);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc += ex2(x[i] - ms);
+    s = s * sc + acc;
+    m = mn;
+  }
+  __device__ void merge(const DAcc& o) { lse2_merge(m, s, o.m, o.s); }
+  __device__ float value() const { return msafe(m) + __log2f(s); }
+  __device__ int arg() const { return 0; }
+};
+
 struct ColsParams {
   NGram g;
   int k;            // max_expansions or -1
@@ -91,25 +135,25 @@ struct ColsParams {
 template <int SR, bool FLD>
 __device__ __forceinline__ float finish_dest(const ColsParams& p, size_t bt, int q, int level,
                                              float r, int arg, float src_q, float blank_q,
-                                             Acc<SR>& term) {
+                                             DAcc<SR>& term) {
   using S = Sr<SR>;
   const int C = p.g.C;
   if constexpr (!FLD) {
-    const float a = S::times(src_q, blank_q);
+    const float a = Dom<SR>::times(src_q, blank_q);
     if constexpr (SR == LT_MAXTROPICAL) {
       const bool take_blank = a >= r;                        // semirings.py:363
       if (p.backptr) p.backptr[bt * C + q] = take_blank ? (int16_t)-1 : (int16_t)arg;
       return take_blank ? a : r;
     } else {
-      return S::plus(a, r);
+      return Dom<SR>::plus(a, r);
     }
   } else {
-    if (level == 0) { term.init(); term.add(S::times(src_q, blank_q), 0); }   // term_0 = alpha (x) blank
-    if (p.levels) p.levels[(bt * p.k + level) * C + q] = r;
+    if (level == 0) { term.init(); term.add(Dom<SR>::times(src_q, blank_q), 0); }   // term_0 = alpha (x) blank
+    if (p.levels) p.levels[(bt * p.k + level) * C + q] = Dom<SR>::out(r);
     if constexpr (SR == LT_MAXTROPICAL) {
       if (p.backptr) p.backptr[(bt * p.k + level) * C + q] = (int16_t)arg;
     }
-    term.add(S::times(r, blank_q), level + 1);               // strict '>' keeps fewer expansions
+    term.add(Dom<SR>::times(r, blank_q), level + 1);         // strict '>' keeps fewer expansions
     if (level + 1 < p.k) return r;                           // last_{level+1}
     if constexpr (SR == LT_MAXTROPICAL) {
       if (p.termptr) p.termptr[bt * C + q] = (uint8_t)term.arg();
@@ -149,7 +193,8 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   const size_t bt0 = (size_t)b * p.T;
 
   auto init_value = [&](int st) -> float {
-    return p.alpha_init ? p.alpha_init[(size_t)b * C + st] : (st == 0 ? S::one() : S::zero());
+    return Dom<SR>::in(p.alpha_init ? p.alpha_init[(size_t)b * C + st]
+                                    : (st == 0 ? S::one() : S::zero()));
   };
 
   if (tid == 0) {
@@ -240,7 +285,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
       }
     }
     const uint32_t expect = (uint32_t)(W * K + (rank == 0 ? Alow : 0)) * 4;   // bytes per level
-    Acc<SR> term[ND];
+    DAcc<SR> term[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) term[d].init();
 
@@ -277,12 +322,12 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
         if (p.alphas) {
 #pragma unroll
           for (int d = 0; d < ND; ++d)
-            if (dq[d] >= 0) p.alphas[bt * C + dq[d]] = areg[d];
+            if (dq[d] >= 0) p.alphas[bt * C + dq[d]] = Dom<SR>::out(areg[d]);
         }
       }
 
       // ---- column reduction over the K rows, chunk by chunk
-      Acc<SR> acc[CPT];
+      DAcc<SR> acc[CPT];
 #pragma unroll
       for (int c = 0; c < CPT; ++c) acc[c].init();
       const float* srow = src + li;
@@ -313,7 +358,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
               const float sv = sp[r * kSrcStride];
 #pragma unroll
               for (int c = 0; c < CPT; ++c) {
-                x[c][r] = sv + w[c];
+                x[c][r] = fmaf(w[c], kLog2e, sv);
                 cm[c] = fmaxf(cm[c], x[c][r]);
               }
             } else {
@@ -332,7 +377,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
               load_w(r + u, w);
               const float sv = sp[(r + u) * kSrcStride];
 #pragma unroll
-              for (int c = 0; c < CPT; ++c) acc[c].add(S::times(sv, w[c]), kk0 + r + u);
+              for (int c = 0; c < CPT; ++c) acc[c].add(Dom<SR>::times(sv, w[c]), kk0 + r + u);
             }
           }
           for (; r < rows; ++r) {
@@ -340,7 +385,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
             load_w(r, w);
             const float sv = sp[r * kSrcStride];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) acc[c].add(S::times(sv, w[c]), kk0 + r);
+            for (int c = 0; c < CPT; ++c) acc[c].add(Dom<SR>::times(sv, w[c]), kk0 + r);
           }
         }
         __syncwarp();
@@ -361,7 +406,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
           arg = acc[d < CPT ? d : 0].arg();
         } else {
           r = S::zero();                                                   // state 0: no incoming arc
-          if (q >= g.off) r = S::times(src[LOW0 + (q - g.off) / V], clx[d >= CPT ? d - CPT : 0]);
+          if (q >= g.off) r = Dom<SR>::times(src[LOW0 + (q - g.off) / V], clx[d >= CPT ? d - CPT : 0]);
         }
         const float v = finish_dest<SR, FLD>(p, bt, q, level, r, arg, areg[d], cbl[d], term[d]);
         if (!FLD || level + 1 == nlev) areg[d] = v;
@@ -374,19 +419,19 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
 
     // padding frames keep alpha (lattices.py:460-461) and are still recorded (:462);
     // dist = (+)_c alpha_T[c] (lattices.py:496): per-thread, per-warp, per-CTA, per-cluster
-    Acc<SR> part; part.init();
+    DAcc<SR> part; part.init();
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       const int q = dq[d];
       if (q < 0) continue;
       if (p.alphas)
-        for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + q] = areg[d];
-      if (p.alpha_final) p.alpha_final[(size_t)b * C + q] = areg[d];
-      Acc<SR> one; one.init(); one.add(areg[d], q);
+        for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + q] = Dom<SR>::out(areg[d]);
+      if (p.alpha_final) p.alpha_final[(size_t)b * C + q] = Dom<SR>::out(areg[d]);
+      DAcc<SR> one; one.init(); one.add(areg[d], q);
       part.merge(one);
     }
     for (int o = 16; o > 0; o >>= 1) {
-      Acc<SR> other = part;
+      DAcc<SR> other = part;
       if constexpr (SR == LT_LOG) {
         other.m = __shfl_xor_sync(0xffffffffu, part.m, o);
         other.s = __shfl_xor_sync(0xffffffffu, part.s, o);
@@ -410,7 +455,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
     if (tid == 0) {
       for (int w = 1; w < kConsumers / 32; ++w) {
-        Acc<SR> other = part;
+        DAcc<SR> other = part;
         if constexpr (SR == LT_LOG) { other.m = red[2 * w]; other.s = red[2 * w + 1]; }
         else if constexpr (SR == LT_MAXTROPICAL) { other.m = red[2 * w]; other.a = __float_as_int(red[2 * w + 1]); }
         else { other.s = red[2 * w]; }
@@ -427,15 +472,15 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   __syncthreads();
   cluster_sync_all();
   if (rank == 0 && tid == 0) {
-    Acc<SR> tot; tot.init();
+    DAcc<SR> tot; tot.init();
     for (uint32_t r = 0; r < CL; ++r) {
-      Acc<SR> other = tot;
+      DAcc<SR> other = tot;
       if constexpr (SR == LT_LOG) { other.m = dpart[2 * r]; other.s = dpart[2 * r + 1]; }
       else if constexpr (SR == LT_MAXTROPICAL) { other.m = dpart[2 * r]; other.a = 0; }
       else { other.s = dpart[2 * r]; }
       tot.merge(other);
     }
-    p.dist[b] = tot.value();
+    p.dist[b] = Dom<SR>::out(tot.value());
   }
 }
 

@@ -54,11 +54,6 @@ struct RowsParams {
   float* beta_final;
 };
 
-// first destination of source row p (its V destinations are contiguous)
-__device__ __forceinline__ int row_window(const NGram& g, int p) {
-  return p < g.Alow ? g.off + p * g.V : g.A + ((p - g.Alow) * g.V) % g.N;
-}
-
 template <int SR, int CHL>      // CHL = V / 32 float4 chunks per lane
 __global__ void __launch_bounds__(kRThreads, 2)
 lattice_backward_rows(const RowsParams p) {
@@ -137,15 +132,26 @@ lattice_backward_rows(const RowsParams p) {
       for (int i = tid; i < nrows; i += kRConsumers) p.grad_blank[(bt0 + t) * C + p_lo + i] = 0.f;
     }
 
+    // Per-thread row bookkeeping.  A lane group visits rows row0, row0 + 32, row0 + 64, ... of
+    // every frame; the beta window of a full-order row advances by 32*V (mod N) per visit, so
+    // the closed form of row_window (an integer modulo) is evaluated once per kernel.
+    const int row0 = p_lo + rloc;
+    long long wr0l = ((long long)(row0 - g.Alow) * V) % g.N;
+    if (wr0l < 0) wr0l += g.N;
+    const int wr0 = (int)wr0l;
+    const int wstep = (32 * V) % g.N;
+
     // alpha_t[p], blank_t[p] of the two rows this owner lane handles in the NEXT chunk
     float n_alpha[2] = {0.f, 0.f}, n_blank[2] = {0.f, 0.f};
     auto prefetch = [&](int it, int ch) {
       if (!owner || it >= nf) return;
-      const size_t o = (bt0 + (nf - 1 - it)) * C;
+      const size_t o = (bt0 + (nf - 1 - it)) * C + row0 + ch * kRChunk;
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
-        const int row = p_lo + ch * kRChunk + ps * 32 + rloc;
-        if (row < p_hi) { n_alpha[ps] = p.alphas[o + row]; n_blank[ps] = ldg_stream(p.blank + o + row); }
+        if (row0 + ch * kRChunk + ps * 32 < p_hi) {
+          n_alpha[ps] = p.alphas[o + ps * 32];
+          n_blank[ps] = ldg_stream(p.blank + o + ps * 32);
+        }
       }
     };
     if (nrows > 0) prefetch(0, 0);
@@ -159,8 +165,9 @@ lattice_backward_rows(const RowsParams p) {
       float* nxt = beta_buf + ((it + 1) & 1) * BP;
       if (it > 0) mbar_wait(smem_u32(&xbar[it & 1]), ((it - 1) >> 1) & 1);
       if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), expect);
-      float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
       float* gb = p.grad_blank + (bt0 + t) * C;
+      float* grow = p.grad_lexical + ((bt0 + t) * (size_t)C + row0) * V + sl * 4;
+      int prow = row0, wrel = wr0;
 
       for (int ch = 0; ch < nchunks; ++ch) {
         const float c_alpha[2] = {n_alpha[0], n_alpha[1]}, c_blank[2] = {n_blank[0], n_blank[1]};
@@ -168,26 +175,24 @@ lattice_backward_rows(const RowsParams p) {
         mbar_wait(smem_u32(&full[stage]), use & 1);
         const float* tile = tiles + (size_t)stage * (stage_bytes / 4);
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          const int lrow = ps * 32 + rloc;                 // row inside the chunk
-          const int prow = p_lo + ch * kRChunk + lrow;     // source state
+        for (int ps = 0; ps < 2; ++ps, prow += 32, grow += (size_t)32 * V) {
           const bool live = prow < p_hi;
           // a warp covers 4 consecutive rows; lanes of dead rows still take part in shuffles
-          const int pc = live ? prow : p_lo;
-          const float* trow = tile + (size_t)(live ? lrow : 0) * V;
-          const float* bwin = beta + kRPad + row_window(g, pc);
+          const float* trow = tile + (live ? (ps * 32 + rloc) * V : 0) + sl * 4;
+          const int win = !live ? g.A : (prow < g.Alow ? g.off + prow * V : g.A + wrel);
+          const float* bwin = beta + kRPad + win + sl * 4;
+          wrel += wstep;
+          if (wrel >= g.N) wrel -= g.N;
           float4 x[CHL];
 #pragma unroll
           for (int i = 0; i < CHL; ++i) {
-            const int c4 = (sl + 8 * i) * 4;
-            const float4 w = *reinterpret_cast<const float4*>(trow + c4);
-            const float4 bn = *reinterpret_cast<const float4*>(bwin + c4);
+            const float4 w = *reinterpret_cast<const float4*>(trow + 32 * i);
+            const float4 bn = *reinterpret_cast<const float4*>(bwin + 32 * i);
             x[i] = make_float4(arc<SR>(w.x, bn.x), arc<SR>(w.y, bn.y), arc<SR>(w.z, bn.z),
                                arc<SR>(w.w, bn.w));
           }
           const float alpha_raw = __shfl_sync(0xffffffffu, c_alpha[ps], lane & ~7);
           const float alpha_p = to_dom<SR>(alpha_raw);
-          float* grow = gl + (size_t)pc * V;
           float rowsum;
           if constexpr (SR == LT_LOG) {
             float m = neg_inf();
@@ -205,7 +210,7 @@ lattice_backward_rows(const RowsParams p) {
               e.x = ex2(x[i].x - ms); e.y = ex2(x[i].y - ms);
               e.z = ex2(x[i].z - ms); e.w = ex2(x[i].w - ms);
               s += (e.x + e.y) + (e.z + e.w);
-              if (live) stg_stream4(grow + (sl + 8 * i) * 4, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+              if (live) stg_stream4(grow + 32 * i, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -216,10 +221,9 @@ lattice_backward_rows(const RowsParams p) {
             const float ga = gscale * alpha_p;
 #pragma unroll
             for (int i = 0; i < CHL; ++i) {
-              const int c4 = (sl + 8 * i) * 4;
-              const float4 bn = *reinterpret_cast<const float4*>(bwin + c4);
+              const float4 bn = *reinterpret_cast<const float4*>(bwin + 32 * i);
               s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-              if (live) stg_stream4(grow + c4, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
+              if (live) stg_stream4(grow + 32 * i, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);

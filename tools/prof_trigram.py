@@ -1,0 +1,22 @@
+"""One forward + backward of the trigram (FullNGram(64, 2)) Log loss for ncu:
+lattice_forward_cols<Log> and lattice_backward_rows<Log>."""
+import sys
+import torch
+sys.path.insert(0, '.')
+import last_torch_b200 as lt  # noqa: F401
+from last_torch_b200 import ops, _native as N
+B, T, V, n = 32, 200, 64, 2
+C = 1 + V + V * V
+g = torch.Generator(device='cuda').manual_seed(0)
+blank = torch.randn([B, T, C], device='cuda', generator=g)
+lex = torch.randn([B, T, C, V], device='cuda', generator=g)
+nf = torch.full([B], T, dtype=torch.int32, device='cuda')
+gd = torch.ones([B], device='cuda')
+gb = torch.empty_like(blank)
+gl = torch.empty_like(lex)
+for _ in range(2):
+  dist, alphas, _, _, _, _ = ops._lattice_forward_raw(N.LOG, V, n, -1, blank, lex, nf, 0, False, False)
+  N.check(N.lib().lt_lattice_backward(
+      N.LOG, V, n, -1, N.ptr(blank), N.ptr(lex), N.ptr(nf), B, T, N.ptr(alphas), None,
+      N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, 0, N.stream_ptr(blank.device)), 'bwd')
+torch.cuda.synchronize()
