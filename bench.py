@@ -370,10 +370,14 @@ def run_b200(args):
     return gb, gl
 
   ms_step, launches, kernels, clocks = timed(resident_step, args.steps, args.warmup)
-  units = world * B * T * C
+  # frames*states actually processed (padding frames of a ragged batch are not counted)
+  frames_done = torch.tensor([float(num_frames.sum())], device=dev)
+  if world > 1:
+    dist.all_reduce(frames_done)
+  units = float(frames_done.item()) * C
   value = units / (ms_step * 1e-3)
 
-  w_bytes = B * T * C * (V + 1) * 4
+  w_bytes = int(num_frames.sum()) * C * (V + 1) * 4      # arc weights of this rank's real frames
   peak, peak_src = peaks()
   kern = {}
   for name, ts in kernels.items():
