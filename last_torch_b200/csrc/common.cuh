@@ -227,6 +227,19 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// 256-bit global loads (sm_100: LDG.E.256; p must be 32-byte aligned).  A warp that reads 32
+// bytes per lane with two 128-bit loads touches every 128-byte line twice (16-byte accesses at a
+// 32-byte lane stride): twice the L1 data-pipe wavefronts of one 256-bit load.
+__device__ __forceinline__ void ldg_stream8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]),
+                 "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg_cached8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]),
+                 "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
 __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

@@ -13,13 +13,18 @@
 //     resident in shared memory (128 KB at V = 256);
 //   * a work item is (block of 128 frames n0.., this hidden block); it is swept as C tiles, tile
 //     c = the 128 joint rows {(n0 + i, c)}: the B operand, their grad_lexical rows split hi / lo
-//     on the fly by 8 producer warps into a 2-stage K-major SWIZZLE_128B ring;
+//     on the fly by 16 producer warps into a 3-stage K-major SWIZZLE_128B ring;
 //   * with that tiling the sum over frames (grad_proj_ctx[c, j]) is a serial sum over the
 //     columns of one tile in the epilogue thread, and the sum over context states
 //     (grad_proj_frame[n0 + i, j]) accumulates over the C tiles of the item IN TENSOR MEMORY:
 //     128 TMEM columns hold the running sums, 128 more hold pf[n0 + i, j] for the item, so the
 //     epilogue never touches shared or global memory per element (tcgen05.ld / tcgen05.st);
-//   * two accumulators (2 x 128 TMEM columns): the epilogue of tile c overlaps the MMAs of c+1.
+//   * two accumulators (2 x 128 TMEM columns): the epilogue of tile c overlaps the MMAs of c+1;
+//   * the (frame block, c) tiles of the whole problem form ONE sequence that is cut into equal
+//     contiguous ranges, one per CTA of a hidden block (no tail imbalance); a frame block that
+//     straddles two ranges is flushed by both owners, so grad_proj_frame is added atomically;
+//   * the epilogue reads TMEM in 8-column groups, the loads of group g+1 in flight while group
+//     g is being computed.
 // Measured limits (B=32, T=1000, C=257, H=512, V=256: 11.8 ms, tensor pipe 24 %): with N = 128
 // every SS-mode tcgen05.mma reads 8 KB of shared memory per 64 issue cycles, i.e. the whole
 // 128 B/clk port, so the producers' stores slow the MMAs; the epilogue reads 3 x 64 KB of TMEM
@@ -89,6 +94,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -113,10 +137,15 @@ constexpr int kDThreads = (6 + kDProdWarps) * 32;   // warp 0 TMA, warp 1 MMA, w
                                                     // warps 6.. producers
 constexpr int kDProducers = kDProdWarps * 32;
 constexpr int kDPasses = 128 / (kDProdWarps * 4);   // row passes per producer thread and chunk
-constexpr int kDStages = 2;
+constexpr int kDStages = 3;
 constexpr int kTile = 128;              // joint rows per tile = frames per work item
 constexpr int kJB = 128;                // hidden units per CTA
-constexpr int kGbRing = 8;               // tiles the producers may run ahead of the epilogue (< 8)
+// grad_blank ring (tiles): the producers run kDStages chunks ahead of the MMAs, which are at most
+// one tile (two accumulators) ahead of the epilogue -- two tiles with V / 64 = 4 chunks per tile
+// (3 slots, all that fits beside the 128 KB resident operand), up to four tiles with one chunk
+// per tile (8 slots).  A slot's mbarrier must never run two phases ahead of its reader.
+constexpr int kGbRingMax = 8;
+__host__ __device__ constexpr int gb_ring_slots(int V) { return V >= 256 ? 3 : kGbRingMax; }
 
 struct Dgrad2Params {
   const float* pc;       // [C, H]
@@ -127,7 +156,7 @@ struct Dgrad2Params {
   long long N;
   int C, H, V;
   float* gpc;            // [C, H]  += (atomics)
-  float* gpf;            // [N, H]  += (single owner)
+  float* gpf;            // [N, H]  += (atomics: a frame block can straddle two CTAs)
 };
 
 __global__ void __launch_bounds__(kDThreads, 1)
@@ -141,14 +170,15 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   const uint32_t b_stage = 2 * kTile * 128;           // hi | lo of one [128 rows x 64 v] chunk
   unsigned char* a_res = base;                        // nk chunks, resident
   unsigned char* b_ring = a_res + (size_t)nk * a_chunk;
-  float* s_gb = reinterpret_cast<float*>(b_ring + kDStages * b_stage);      // [kGbRing][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + kGbRing * kTile);
+  const uint32_t gbring = gb_ring_slots(V);
+  float* s_gb = reinterpret_cast<float*>(b_ring + kDStages * b_stage);      // [gbring][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + gbring * kTile);
   uint64_t* full = bars;                    // [stages]  producers -> MMA
   uint64_t* empty = full + kDStages;        // [stages]  MMA (commit) -> producers
   uint64_t* tfull = empty + kDStages;       // [2]       MMA (commit) -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
-  uint64_t* gbfull = tempty + 2;            // [kGbRing] producers -> epilogue (grad_blank slice)
-  uint64_t* afull = gbfull + kGbRing;       // [1]       TMA -> MMA (resident A)
+  uint64_t* gbfull = tempty + 2;            // [gbring]  producers -> epilogue (grad_blank slice)
+  uint64_t* afull = gbfull + kGbRingMax;       // [1]       TMA -> MMA (resident A)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,6 +186,11 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int jb = blockIdx.x % njb;
   const int group = blockIdx.x / njb, ngroups = gridDim.x / njb;
   const long long nblocks = (p.N + kTile - 1) / kTile;
+  // this CTA's contiguous range of the (frame block, c) tile sequence
+  const long long ttot = nblocks * C;
+  const long long t_lo = ttot * group / ngroups, t_hi = ttot * (group + 1) / ngroups;
+  const long long nb_lo = t_lo / C;
+  const int c_lo = (int)(t_lo - nb_lo * C);
 
   if (tid == 0) {
     for (int s = 0; s < kDStages; ++s) {
@@ -166,7 +201,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
       mbar_init_n(smem_u32(&tfull[a]), 1);
       mbar_init_n(smem_u32(&tempty[a]), 128);
     }
-    for (int r = 0; r < kGbRing; ++r) mbar_init_n(smem_u32(&gbfull[r]), kTile);
+    for (int r = 0; r < kGbRingMax; ++r) mbar_init_n(smem_u32(&gbfull[r]), kTile);
     mbar_init_n(smem_u32(afull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -180,7 +215,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
 
   if (warp == 0) {
     // ------------------------------------------------ resident A: W_vocab^T block, once
-    if (lane == 0 && group < nblocks) {
+    if (lane == 0 && t_lo < t_hi) {
       const uint32_t bar = smem_u32(afull);
       mbar_expect_tx(bar, (uint32_t)nk * a_chunk);
       for (int kc = 0; kc < nk; ++kc) {
@@ -190,36 +225,35 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0 && group < nblocks) {
+    if (lane == 0 && t_lo < t_hi) {
       const uint32_t idesc = umma::make_idesc_bf16(kJB, kTile);
       mbar_wait_parity(smem_u32(afull), 0);
-      uint32_t g = 0, it = 0;
-      for (long long nb = group; nb < nblocks; nb += ngroups) {
-        for (int c = 0; c < C; ++c, ++it) {
-          const uint32_t acc = it & 1;
-          mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+      uint32_t g = 0;
+      const uint32_t ntiles = (uint32_t)(t_hi - t_lo);
+      for (uint32_t it = 0; it < ntiles; ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+        umma::fence_after_thread_sync();
+        const uint32_t d = tmem + acc * kTile;
+        for (int kc = 0; kc < nk; ++kc, ++g) {
+          const uint32_t s = g % kDStages;
+          mbar_wait_parity(smem_u32(&full[s]), (g / kDStages) & 1);
           umma::fence_after_thread_sync();
-          const uint32_t d = tmem + acc * kTile;
-          for (int kc = 0; kc < nk; ++kc, ++g) {
-            const int s = g % kDStages;
-            mbar_wait_parity(smem_u32(&full[s]), (g / kDStages) & 1);
-            umma::fence_after_thread_sync();
-            const uint32_t sa = smem_u32(a_res) + kc * a_chunk;
-            const uint32_t sb = smem_u32(b_ring) + s * b_stage;
+          const uint32_t sa = smem_u32(a_res) + kc * a_chunk;
+          const uint32_t sb = smem_u32(b_ring) + s * b_stage;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
-              const uint64_t dal = umma::make_smem_desc_sw128(sa + kJB * 128 + k * 32);
-              const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
-              const uint64_t dbl = umma::make_smem_desc_sw128(sb + kTile * 128 + k * 32);
-              umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
-              umma::mma_bf16(d, dah, dbl, idesc, 1);
-              umma::mma_bf16(d, dal, dbh, idesc, 1);
-            }
-            umma::commit(smem_u32(&empty[s]));
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
+            const uint64_t dal = umma::make_smem_desc_sw128(sa + kJB * 128 + k * 32);
+            const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
+            const uint64_t dbl = umma::make_smem_desc_sw128(sb + kTile * 128 + k * 32);
+            umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
+            umma::mma_bf16(d, dah, dbl, idesc, 1);
+            umma::mma_bf16(d, dal, dbh, idesc, 1);
           }
-          umma::commit(smem_u32(&tfull[acc]));
+          umma::commit(smem_u32(&empty[s]));
         }
+        umma::commit(smem_u32(&tfull[acc]));
       }
     }
   } else if (warp < 6) {
@@ -230,9 +264,12 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     const float wbj = p.w_blank[jg];
     const uint32_t t_pf = tmem + 2 * kTile + lane_base, t_acc = tmem + 3 * kTile + lane_base;
     uint32_t it = 0;
-    for (long long nb = group; nb < nblocks; nb += ngroups) {
+    long long t = t_lo, nb = nb_lo;
+    int c = c_lo;
+    while (t < t_hi) {
       const long long n0 = nb * kTile;
       const int nvalid = (int)min((long long)kTile, p.N - n0);
+      const int c_end = (int)min((long long)C, c + (t_hi - t));
       // item prologue: pf[n0 + i, jg] -> TMEM, running sums := 0
       for (int c0 = 0; c0 < kTile; c0 += 16) {
         float v[16], z[16];
@@ -245,32 +282,43 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         tmem_st16(t_acc + c0, z);
       }
       tmem_wait_st();
-      float pcj = __ldg(p.pc + jg);
-      for (int c = 0; c < C; ++c, ++it) {
-        const uint32_t acc = it & 1, ring = it % kGbRing;
+      float pcj = __ldg(p.pc + (size_t)c * H + jg);
+      for (; c < c_end; ++c, ++t, ++it) {
+        const uint32_t acc = it & 1, ring = it % gbring;
         const float pc_cur = pcj;
-        if (c + 1 < C) pcj = __ldg(p.pc + (size_t)(c + 1) * H + jg);
-        mbar_wait_parity(smem_u32(&gbfull[ring]), (it / kGbRing) & 1);
+        if (c + 1 < c_end) pcj = __ldg(p.pc + (size_t)(c + 1) * H + jg);
+        mbar_wait_parity(smem_u32(&gbfull[ring]), (it / gbring) & 1);
         mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
         umma::fence_after_thread_sync();
         const float* gbr = s_gb + ring * kTile;
         const uint32_t t_d = tmem + acc * kTile + lane_base;
         float csum = 0.f;
-        for (int c0 = 0; c0 < kTile; c0 += 16) {
-          float d[16], f[16], a[16];
-          tmem_ld16(t_d + c0, d);
-          tmem_ld16(t_pf + c0, f);
-          tmem_ld16(t_acc + c0, a);
-          tmem_wait_ld();
+        // two register sets of 8 columns: the loads of one are in flight while the other is
+        // being computed (tcgen05.wait::ld after the compute covers them)
+        float d0[8], f0[8], a0[8], d1[8], f1[8], a1[8];
+        auto compute = [&](int c0, const float (&d)[8], const float (&f)[8], float (&a)[8]) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 8; ++i) {
             const float x = fmaf(gbr[c0 + i], wbj, d[i]);
             const float h = tanh_fast(pc_cur + f[i]);
             const float gp = x * fmaf(-h, h, 1.f);
             csum += gp;
             a[i] += gp;
           }
-          tmem_st16(t_acc + c0, a);
+          tmem_st8(t_acc + c0, a);
+        };
+        tmem_ld8(t_d, d0); tmem_ld8(t_pf, f0); tmem_ld8(t_acc, a0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile; c0 += 16) {
+          tmem_wait_ld();
+          tmem_ld8(t_d + c0 + 8, d1); tmem_ld8(t_pf + c0 + 8, f1); tmem_ld8(t_acc + c0 + 8, a1);
+          compute(c0, d0, f0, a0);
+          tmem_wait_ld();
+          if (c0 + 16 < kTile) {
+            tmem_ld8(t_d + c0 + 16, d0); tmem_ld8(t_pf + c0 + 16, f0);
+            tmem_ld8(t_acc + c0 + 16, a0);
+          }
+          compute(c0 + 8, d1, f1, a1);
         }
         tmem_wait_st();
         umma::fence_before_thread_sync();
@@ -284,8 +332,10 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < nvalid) p.gpf[(size_t)(n0 + c0 + i) * H + jg] += a[i];
+          if (c0 + i < nvalid) atomicAdd(p.gpf + (size_t)(n0 + c0 + i) * H + jg, a[i]);
       }
+      c = 0;
+      ++nb;
     }
   } else {
     // ---------------------------------------------------------------- B producers
@@ -295,9 +345,9 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     // of the gradient stream, which is what bounds this kernel.
     const int pw = warp - 6;
     const int ch = lane & 7, rsub = lane >> 3;
-    struct Pos { long long nb; int c, kc; };
+    struct Pos { long long nb, t; int c, kc; };          // t: index in the tile sequence
     auto advance = [&](Pos q) {
-      if (++q.kc == nk) { q.kc = 0; if (++q.c == C) { q.c = 0; q.nb += ngroups; } }
+      if (++q.kc == nk) { q.kc = 0; ++q.t; if (++q.c == C) { q.c = 0; ++q.nb; } }
       return q;
     };
     auto issue = [&](const Pos& q, float4 (&x)[kDPasses][2], float (&gbv)[kDPasses]) {
@@ -308,7 +358,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         const long long n = n0 + row;
         x[r][0] = x[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         gbv[r] = 0.f;
-        if (q.nb < nblocks && n < p.N) {
+        if (q.t < t_hi && n < p.N) {
           const size_t m = (size_t)n * C + q.c;
           const float* src = p.gl + m * V + q.kc * 64 + ch * 8;
           x[r][0] = ldg_stream4(src);
@@ -319,14 +369,14 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     };
     float4 cur[kDPasses][2], n1[kDPasses][2], n2[kDPasses][2];
     float gcur[kDPasses], g1[kDPasses], g2[kDPasses];
-    Pos pc0 = {group, 0, 0};
+    Pos pc0 = {nb_lo, t_lo, c_lo, 0};
     Pos p1 = advance(pc0), p2 = advance(p1);
     issue(pc0, cur, gcur);
     issue(p1, n1, g1);
     uint32_t g = 0, it = 0;
-    while (pc0.nb < nblocks) {
+    while (pc0.t < t_hi) {
       issue(p2, n2, g2);
-      const int s = g % kDStages;
+      const uint32_t s = g % kDStages;
       uint4 hi[kDPasses], lo[kDPasses];
 #pragma unroll
       for (int r = 0; r < kDPasses; ++r) {
@@ -335,7 +385,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         umma::split_pack8(x, hi[r], lo[r]);
       }
       if (pc0.kc == 0 && ch == 0) {          // grad_blank slice of this tile for the epilogue
-        const uint32_t ring = it % kGbRing;
+        const uint32_t ring = it % gbring;
 #pragma unroll
         for (int r = 0; r < kDPasses; ++r)
           s_gb[ring * kTile + r * (kDProdWarps * 4) + pw * 4 + rsub] = gcur[r];
@@ -391,7 +441,7 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, co
   p.N = N; p.C = C; p.H = H; p.V = V; p.gpc = gpc; p.gpf = gpf;
   const int nk = V / 64;
   const size_t smem = (size_t)nk * 2 * kJB * 128 + (size_t)kDStages * 2 * kTile * 128 +
-                      sizeof(float) * kGbRing * kTile + 8 * 32 + 16 + 1024;
+                      sizeof(float) * gb_ring_slots(V) * kTile + 8 * 32 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

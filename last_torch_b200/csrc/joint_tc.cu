@@ -13,6 +13,7 @@
 // completion via tcgen05.commit -> mbarrier, accumulator read back with
 // tcgen05.ld.  The pipelined JointWeightFn kernels are built from it.
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -794,10 +795,11 @@ joint_reduce_kernel(const float* __restrict__ gp, const float* __restrict__ pc,
 // accumulators of 128 lanes x NJ columns) and is added to global memory once.
 // The same producer threads accumulate grad_b_vocab, grad_w_blank and grad_b_blank.
 // ===========================================================================
-constexpr int kWThreads = 544;          // warp 0: MMA issuer; warps 1-16: producers
-constexpr int kWProducers = 512;
-constexpr int kWStages = 3;
-constexpr int kWK = 32;                 // joint rows per stage
+constexpr int kWThreads = 288;          // warp 0: MMA issuer; warps 1-8: producers (8 warps x ~190
+                                        // registers: room for the one-stage-ahead gradient prefetch)
+constexpr int kWProducers = 256;
+constexpr int kWStages = 6;
+constexpr int kWK = 16;                 // joint rows per stage
 
 struct JointWgradParams {
   const float* pc;       // [C, H]
@@ -879,86 +881,141 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
       umma::commit(smem_u32(done));
     }
   } else {
-    const int pidx = tid - 32;                         // 0 .. 511
-    const int vchunks = V / 8, jchunks = NJ / 8;       // 16-byte chunks per row
-    const int a_vch = pidx % vchunks, a_k0 = pidx / vchunks, a_kstep = kWProducers / vchunks;
-    const int b_jch = pidx % jchunks, b_k0 = pidx / jchunks, b_kstep = kWProducers / jchunks;
+    const int pidx = tid - 32;                         // 0 .. 255
+    // V = 128 * AI and NJ = 128 * BI (the launcher picks the instantiation), so every per-row
+    // stride below is a compile-time constant: a thread's operand rows are 16 / AI (16 / BI)
+    // joint rows apart = 2048 floats of grad_lexical, and 4096 bytes apart in the MN-major tile.
+    constexpr int kAStep = kWK / AI, kBStep = kWK / BI;
+    const int a_vch = pidx % (16 * AI), a_k0 = pidx / (16 * AI);
+    const int b_jch = pidx % (16 * BI), b_k0 = pidx / (16 * BI);
     const int j0 = jblk * NJ + b_jch * 8;
+    const uint32_t a_off0 = umma::mn_major_chunk_offset(128 * AI, a_vch * 8, a_k0);
+    const uint32_t b_off0 = umma::mn_major_chunk_offset(128 * BI, b_jch * 8, b_k0);
+    const int C = p.C;
     float bv_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float wb_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float bb_acc = 0.f;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch % kWStages;
+    const float* ga = p.gl + (size_t)(m_lo + a_k0) * (128 * AI) + a_vch * 8;   // stage 0, row 0
+    const float* pcj = p.pc + j0;
+    const float* pfj = p.pf + j0;
+    const int nfull = (int)((m_hi - m_lo) / kWK);      // stages whose kWK rows are all live
+
+    // Everything a stage consumes from global memory is loaded ONE STAGE AHEAD into registers
+    // with 256-bit loads (grad_lexical rows = the HBM stream, pc rows and grad_blank = L2
+    // hits).  pf[n, j0 .. j0+7] is the same for the C consecutive joint rows of a frame: it
+    // lives in registers -- pfa for the frame of the stage's first row, pfb for the next frame
+    // (C >= 32 > kWK: a stage touches at most two frames) -- and is reloaded when the first
+    // row crosses into a new frame.  Full stages (all but possibly the last one of the last
+    // CTA) take a path with no bounds checks at all.
+    // (fn, fc): frame and context state of the first row of the stage being PREFETCHED;
+    // (cn, cc): the same for the stage being converted.
+    const long long nframes = p.M / C;
+    long long fn = m_lo / C;
+    int fc = (int)(m_lo - fn * C);
+    long long cn = fn;
+    int cc = fc;
+    float pfa[8], pfb[8];
+    auto load_pf = [&](long long n, float (&v)[8]) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (n < nframes) ldg_cached8(pfj + (size_t)n * H, v);
+    };
+    load_pf(cn, pfa);
+    load_pf(cn + 1, pfb);
+    struct Pre {                       // one stage's worth of prefetched operands
+      float ax[AI][8];                 // grad_lexical
+      float bp[BI][8];                 // pc
+      float gbm[BI];                   // grad_blank
+    };
+    auto prefetch = [&](int ch, Pre& q, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       const long long mrow0 = m_lo + (long long)ch * kWK;
-      // ---- issue every global load of this stage first (memory-level parallelism)
-      float4 ax[AI][2], bp[BI][2], bf[BI][2];
-      float gbm[BI];
+      const float* src = ga + (size_t)ch * (kWK * 128 * AI);
 #pragma unroll
       for (int i = 0; i < AI; ++i) {
-        const long long m = mrow0 + a_k0 + i * a_kstep;
-        ax[i][0] = ax[i][1] = z4;
-        if (m < m_hi) {
-          ax[i][0] = ldg_stream4(p.gl + (size_t)m * V + a_vch * 8);
-          ax[i][1] = ldg_stream4(p.gl + (size_t)m * V + a_vch * 8 + 4);
+        if (!FULL) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q.ax[i][e] = 0.f;
         }
+        if (FULL || (ch < nchunks && mrow0 + a_k0 + i * kAStep < m_hi))
+          ldg_stream8(src + i * 2048, q.ax[i]);
       }
 #pragma unroll
       for (int i = 0; i < BI; ++i) {
-        const long long m = mrow0 + b_k0 + i * b_kstep;
-        bp[i][0] = bp[i][1] = bf[i][0] = bf[i][1] = z4;
-        gbm[i] = 0.f;
-        if (m < m_hi) {
-          const long long n = m / p.C;
-          const int c = (int)(m - n * p.C);
-          const float* pcr = p.pc + (size_t)c * H + j0;
-          const float* pfr = p.pf + (size_t)n * H + j0;
-          bp[i][0] = __ldg(reinterpret_cast<const float4*>(pcr));
-          bp[i][1] = __ldg(reinterpret_cast<const float4*>(pcr + 4));
-          bf[i][0] = __ldg(reinterpret_cast<const float4*>(pfr));
-          bf[i][1] = __ldg(reinterpret_cast<const float4*>(pfr + 4));
-          gbm[i] = __ldg(p.gb + m);
+        int c = fc + b_k0 + i * kBStep;
+        if (c >= C) c -= C;
+        if (!FULL) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q.bp[i][e] = 0.f;
+          q.gbm[i] = 0.f;
+        }
+        const long long m = mrow0 + b_k0 + i * kBStep;
+        if (FULL || (ch < nchunks && m < m_hi)) {
+          ldg_cached8(pcj + (size_t)c * H, q.bp[i]);
+          q.gbm[i] = __ldg(p.gb + m);
         }
       }
+      fc += kWK;
+      if (fc >= C) { fc -= C; ++fn; }
+    };
+    Pre bufa, bufb;                    // ping-pong: no register moves between stages
+    if (nfull > 0) prefetch(0, bufa, std::true_type{}); else prefetch(0, bufa, std::false_type{});
+
+    auto stage = [&](int ch, Pre& cur, Pre& nxt, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const int s = ch % kWStages;
+      if (ch + 1 < nfull) prefetch(ch + 1, nxt, std::true_type{});
+      else prefetch(ch + 1, nxt, std::false_type{});
       mbar_wait_parity(smem_u32(&empty[s]), ((ch / kWStages) & 1) ^ 1);
-      unsigned char* a_hi = base + s * stage_bytes;
-      unsigned char* a_lo = a_hi + op_bytes;
-      unsigned char* b_hi = a_lo + op_bytes;
-      unsigned char* b_lo = b_hi + op_bytes;
+      unsigned char* a_hi = base + s * stage_bytes + a_off0;
+      unsigned char* b_hi = base + s * stage_bytes + 2 * op_bytes + b_off0;
 #pragma unroll
       for (int i = 0; i < AI; ++i) {                   // A = G^T chunk
-        const int k = a_k0 + i * a_kstep;
-        const float x[8] = {ax[i][0].x, ax[i][0].y, ax[i][0].z, ax[i][0].w,
-                            ax[i][1].x, ax[i][1].y, ax[i][1].z, ax[i][1].w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) bv_acc[e] += x[e];
+        for (int e = 0; e < 8; ++e) bv_acc[e] += cur.ax[i][e];
         uint4 h4, l4;
-        umma::split_pack8(x, h4, l4);
-        const uint32_t off = umma::mn_major_chunk_offset(V, a_vch * 8, k);
-        *reinterpret_cast<uint4*>(a_hi + off) = h4;
-        *reinterpret_cast<uint4*>(a_lo + off) = l4;
+        umma::split_pack8(cur.ax[i], h4, l4);
+        *reinterpret_cast<uint4*>(a_hi + i * 4096) = h4;
+        *reinterpret_cast<uint4*>(a_hi + op_bytes + i * 4096) = l4;
       }
 #pragma unroll
       for (int i = 0; i < BI; ++i) {                   // B = h^T chunk (recomputed)
-        const int k = b_k0 + i * b_kstep;
-        const bool live = mrow0 + k < m_hi;
-        float t[8] = {bp[i][0].x + bf[i][0].x, bp[i][0].y + bf[i][0].y, bp[i][0].z + bf[i][0].z,
-                      bp[i][0].w + bf[i][0].w, bp[i][1].x + bf[i][1].x, bp[i][1].y + bf[i][1].y,
-                      bp[i][1].z + bf[i][1].z, bp[i][1].w + bf[i][1].w};
+        const bool live = FULL || m_lo + (long long)ch * kWK + b_k0 + i * kBStep < m_hi;
+        const bool wrapped = cc + b_k0 + i * kBStep >= C;       // warp-uniform
+        float t[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+          t[e] = cur.bp[i][e] + (wrapped ? pfb[e] : pfa[e]);
           t[e] = live ? tanh_fast(t[e]) : 0.f;
-          wb_acc[e] = fmaf(gbm[i], t[e], wb_acc[e]);
+          wb_acc[e] = fmaf(cur.gbm[i], t[e], wb_acc[e]);
         }
-        if (b_jch == 0) bb_acc += gbm[i];
+        if (b_jch == 0) bb_acc += cur.gbm[i];
         uint4 h4, l4;
         umma::split_pack8(t, h4, l4);
-        const uint32_t off = umma::mn_major_chunk_offset(NJ, b_jch * 8, k);
-        *reinterpret_cast<uint4*>(b_hi + off) = h4;
-        *reinterpret_cast<uint4*>(b_lo + off) = l4;
+        *reinterpret_cast<uint4*>(b_hi + i * 4096) = h4;
+        *reinterpret_cast<uint4*>(b_hi + op_bytes + i * 4096) = l4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(smem_u32(&full[s]));
+      cc += kWK;
+      if (cc >= C) {                                   // the next stage starts in a new frame
+        cc -= C; ++cn;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pfa[e] = pfb[e];
+        load_pf(cn + 1, pfb);
+      }
+    };
+    int ch = 0;
+#pragma unroll 1
+    for (; ch + 1 < nfull; ch += 2) {
+      stage(ch, bufa, bufb, std::true_type{});
+      stage(ch + 1, bufb, bufa, std::true_type{});
+    }
+    // at most one full stage left, then at most one partial stage (ch is even here)
+    if (ch < nfull) { stage(ch, bufa, bufb, std::true_type{}); ++ch; }
+    if (ch < nchunks) {
+      if (ch & 1) stage(ch, bufb, bufa, std::false_type{});
+      else stage(ch, bufa, bufb, std::false_type{});
     }
     // side sums: bias / blank-projection gradients
 #pragma unroll
@@ -1196,8 +1253,8 @@ bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
   if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_WGRAD_SIMT")) return false;
   if (V != 128 && V != 256) return false;
   if (H % 128 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
-  if (N * (int64_t)C < 1) return false;
-  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  if (N < 1 || C < 32) return false;      // a stage of kWK rows touches at most two frames
+  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 32 == 0; };   // 256-bit loads
   return al(gl) && al(pc) && al(pf);
 }
 
