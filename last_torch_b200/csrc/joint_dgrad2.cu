@@ -44,6 +44,8 @@
 namespace lt {
 namespace {
 
+__device__ __align__(32) float lt_zero_line[64];   // what rows past the last frame read
+
 __device__ __forceinline__ void mbar_init_n(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -339,79 +341,97 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     }
   } else {
     // ---------------------------------------------------------------- B producers
-    // 8 lanes per joint row (256 contiguous bytes of grad_lexical per K chunk), 4 rows per
-    // warp, kDPasses passes over the 128 rows of the tile.  The loads run TWO chunks ahead of
-    // the conversion (register ring cur / n1 / n2): the ring has to cover the HBM / L2 latency
-    // of the gradient stream, which is what bounds this kernel.
+    // 8 lanes per joint row (one 256-bit load each: 256 contiguous bytes of grad_lexical per row
+    // and K chunk), 4 rows per warp, kDPasses passes over the 128 rows of the tile.
+    //  * Along the CTA's tile sequence the chunks of a row are CONTIGUOUS in memory
+    //    ((c, kc) -> offset (c * V/64 + kc) * 64 floats), so a thread keeps one pointer per row
+    //    and adds 64 floats per chunk; only a new frame block recomputes it.  Rows past N point
+    //    at a zero line with step 0.
+    //  * Registers hold one chunk ahead of the conversion (two buffers, ping-pong); the HBM
+    //    latency is covered by L2 prefetches kPrefTiles tiles ahead of the loads.
     const int pw = warp - 6;
     const int ch = lane & 7, rsub = lane >> 3;
-    struct Pos { long long nb, t; int c, kc; };          // t: index in the tile sequence
-    auto advance = [&](Pos q) {
-      if (++q.kc == nk) { q.kc = 0; ++q.t; if (++q.c == C) { q.c = 0; ++q.nb; } }
-      return q;
-    };
-    auto issue = [&](const Pos& q, float4 (&x)[kDPasses][2], float (&gbv)[kDPasses]) {
-      const long long n0 = q.nb * kTile;
+    const uint32_t gtot = (uint32_t)(t_hi - t_lo) * (uint32_t)nk;
+    constexpr int kPrefTiles = 2;
+    const float* pp[kDPasses];
+    const float* gbp[kDPasses];
+    int pstep[kDPasses];                      // 64 floats per chunk, 0 for rows past N
+    long long pnb = nb_lo;
+    uint32_t left = 0, pkc = 0;               // chunks left in the frame block / K chunk, both at
+                                              // the LOAD position
+    auto place = [&](long long nb, int c) {
 #pragma unroll
       for (int r = 0; r < kDPasses; ++r) {
-        const int row = r * (kDProdWarps * 4) + pw * 4 + rsub;
-        const long long n = n0 + row;
-        x[r][0] = x[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        gbv[r] = 0.f;
-        if (q.t < t_hi && n < p.N) {
-          const size_t m = (size_t)n * C + q.c;
-          const float* src = p.gl + m * V + q.kc * 64 + ch * 8;
-          x[r][0] = ldg_stream4(src);
-          x[r][1] = ldg_stream4(src + 4);
-          if (q.kc == 0 && ch == 0) gbv[r] = ldg_stream(p.gb + m);
-        }
+        const long long n = nb * kTile + r * (kDProdWarps * 4) + pw * 4 + rsub;
+        const bool valid = n < p.N;
+        pp[r] = valid ? p.gl + ((size_t)n * C + c) * V + ch * 8 : lt_zero_line + ch * 8;
+        gbp[r] = valid ? p.gb + (size_t)n * C + c : lt_zero_line;
+        pstep[r] = valid ? 64 : 0;
       }
+      left = (uint32_t)(C - c) * (uint32_t)nk;
     };
-    float4 cur[kDPasses][2], n1[kDPasses][2], n2[kDPasses][2];
-    float gcur[kDPasses], g1[kDPasses], g2[kDPasses];
-    Pos pc0 = {nb_lo, t_lo, c_lo, 0};
-    Pos p1 = advance(pc0), p2 = advance(p1);
-    issue(pc0, cur, gcur);
-    issue(p1, n1, g1);
-    uint32_t g = 0, it = 0;
-    while (pc0.t < t_hi) {
-      issue(p2, n2, g2);
-      const uint32_t s = g % kDStages;
-      uint4 hi[kDPasses], lo[kDPasses];
+    place(nb_lo, c_lo);
+    struct Buf { float x[kDPasses][8]; float gb[kDPasses]; };
+    auto load = [&](Buf& b) {
 #pragma unroll
-      for (int r = 0; r < kDPasses; ++r) {
-        const float x[8] = {cur[r][0].x, cur[r][0].y, cur[r][0].z, cur[r][0].w,
-                            cur[r][1].x, cur[r][1].y, cur[r][1].z, cur[r][1].w};
-        umma::split_pack8(x, hi[r], lo[r]);
+      for (int r = 0; r < kDPasses; ++r) ldg_stream8(pp[r], b.x[r]);
+      if (pkc == 0 && ch == 0) {
+#pragma unroll
+        for (int r = 0; r < kDPasses; ++r) b.gb[r] = ldg_stream(gbp[r]);
       }
-      if (pc0.kc == 0 && ch == 0) {          // grad_blank slice of this tile for the epilogue
-        const uint32_t ring = it % gbring;
+      if (left > (uint32_t)(kPrefTiles * nk) && (ch & 3) == 0) {
 #pragma unroll
         for (int r = 0; r < kDPasses; ++r)
-          s_gb[ring * kTile + r * (kDProdWarps * 4) + pw * 4 + rsub] = gcur[r];
-#pragma unroll
-        for (int r = 0; r < kDPasses; ++r) mbar_arrive(smem_u32(&gbfull[ring]));
+          if (pstep[r])
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp[r] + kPrefTiles * V));
       }
-      mbar_wait_parity(smem_u32(&empty[s]), ((g / kDStages) & 1) ^ 1);
-      unsigned char* b_hi = b_ring + s * b_stage;
-      unsigned char* b_lo = b_hi + kTile * 128;
+#pragma unroll
+      for (int r = 0; r < kDPasses; ++r) pp[r] += pstep[r];
+      if (++pkc == (uint32_t)nk) {
+        pkc = 0;
+#pragma unroll
+        for (int r = 0; r < kDPasses; ++r) gbp[r] += pstep[r] >> 6;
+      }
+      if (--left == 0) { ++pnb; place(pnb, 0); }
+    };
+    uint32_t s = 0, par = 1;                  // ring stage / parity to wait for on empty[s]
+    uint32_t ckc = 0, ringpos = 0;            // K chunk and grad_blank ring slot, CONVERT position
+    const uint32_t row0_off = umma::swizzled_offset(pw * 4 + rsub, ch);   // row r: + r * 64 rows
+    auto convert = [&](const Buf& b) {
+      uint4 hi[kDPasses], lo[kDPasses];
+#pragma unroll
+      for (int r = 0; r < kDPasses; ++r) umma::split_pack8(b.x[r], hi[r], lo[r]);
+      if (ckc == 0 && ch == 0) {              // grad_blank slice of this tile for the epilogue
+#pragma unroll
+        for (int r = 0; r < kDPasses; ++r)
+          s_gb[ringpos * kTile + r * (kDProdWarps * 4) + pw * 4 + rsub] = b.gb[r];
+#pragma unroll
+        for (int r = 0; r < kDPasses; ++r) mbar_arrive(smem_u32(&gbfull[ringpos]));
+      }
+      mbar_wait_parity(smem_u32(&empty[s]), par);
+      unsigned char* b_hi = b_ring + s * b_stage + row0_off;
 #pragma unroll
       for (int r = 0; r < kDPasses; ++r) {
-        const uint32_t off = umma::swizzled_offset(r * (kDProdWarps * 4) + pw * 4 + rsub, ch);
-        *reinterpret_cast<uint4*>(b_hi + off) = hi[r];
-        *reinterpret_cast<uint4*>(b_lo + off) = lo[r];
+        // rows r * 64 apart: same swizzle phase (64 % 8 == 0), 64 * 128 bytes further
+        *reinterpret_cast<uint4*>(b_hi + r * (kDProdWarps * 4) * 128) = hi[r];
+        *reinterpret_cast<uint4*>(b_hi + kTile * 128 + r * (kDProdWarps * 4) * 128) = lo[r];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(smem_u32(&full[s]));
-#pragma unroll
-      for (int r = 0; r < kDPasses; ++r) {
-        cur[r][0] = n1[r][0]; cur[r][1] = n1[r][1]; gcur[r] = g1[r];
-        n1[r][0] = n2[r][0]; n1[r][1] = n2[r][1]; g1[r] = g2[r];
-      }
-      if (p1.kc == 0) ++it;
-      pc0 = p1; p1 = p2; p2 = advance(p2);
-      ++g;
+      if (++ckc == (uint32_t)nk) { ckc = 0; if (++ringpos == gbring) ringpos = 0; }
+      if (++s == kDStages) { s = 0; par ^= 1; }
+    };
+    Buf bufa, bufb;
+    if (gtot > 0) load(bufa);
+    uint32_t g = 0;
+#pragma unroll 1
+    for (; g + 1 < gtot; g += 2) {
+      load(bufb);
+      convert(bufa);
+      if (g + 2 < gtot) load(bufa);
+      convert(bufb);
     }
+    if (g < gtot) convert(bufa);
   }
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -426,8 +446,8 @@ bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, cons
   if (V % 64 != 0 || V < 64 || V > 256) return false;
   if (H % 128 != 0 || H > 4096) return false;
   if (N < 1 || C < 1) return false;
-  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-  return al(gl) && al(pc) && al(pf);
+  auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
+  return al(gl, 32) && al(pc, 16) && al(pf, 16);      // grad_lexical: 256-bit loads
 }
 
 // whi / wlo: W_vocab^T [H, V] as bf16 hi / lo (transpose_split_kernel), map_* their tensor maps
