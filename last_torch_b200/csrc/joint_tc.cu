@@ -400,61 +400,87 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
     const int pw = warp - 6;                            // 0 .. kFProdWarps-1
     const int ch = lane & 7, rsub = lane >> 3;
     uint32_t g = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const float* pc_row[kFPasses];
-      const float* pf_row[kFPasses];
-      bool valid[kFPasses];
-      float bacc[kFPasses];
-#pragma unroll
-      for (int q = 0; q < kFPasses; ++q) {
-        bacc[q] = 0.f;
-        const long long m = tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub;
-        valid[q] = m < p.M;
-        const long long n = valid[q] ? m / p.C : 0;
-        const int c = valid[q] ? (int)(m - n * p.C) : 0;
-        pc_row[q] = p.pc + (size_t)c * H + ch * 8;
-        pf_row[q] = p.pf + (size_t)n * H + ch * 8;
-      }
-      for (int kc = 0; kc < nchunks; ++kc, ++g) {
-        const int s = g % kJStages;
-        uint4 hi[kFPasses], lo[kFPasses];
+    // 256-bit loads: 8 lanes read 256 contiguous bytes of a row with ONE wavefront pair (two
+    // 128-bit loads per lane touch every line twice -- the L1 data pipe, shared with the
+    // tensor core's operand reads, is what bounds this kernel).  With C >= 128 a tile of 128
+    // consecutive joint rows touches at most two frames: pf is then loaded once per chunk
+    // for both of them instead of once per pass.
+    auto run = [&](auto two_frames_tag) {
+      constexpr bool TWO = decltype(two_frames_tag)::value;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const float* pc_row[kFPasses];
+        const float* pf_row[kFPasses];
+        bool valid[kFPasses], second[kFPasses];
+        float bacc[kFPasses];
+        const long long n_first = tile * 128 / p.C;
+        const long long n_last = min(tile * 128 + 127, p.M - 1) / p.C;
 #pragma unroll
         for (int q = 0; q < kFPasses; ++q) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64 + 4));
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64 + 4));
-          float t[8] = {a0.x + f0.x, a0.y + f0.y, a0.z + f0.z, a0.w + f0.w,
-                        a1.x + f1.x, a1.y + f1.y, a1.z + f1.z, a1.w + f1.w};
-          const float* wb = s_wb + kc * 64 + ch * 8;
+          bacc[q] = 0.f;
+          const long long m = tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub;
+          valid[q] = m < p.M;
+          const long long n = valid[q] ? m / p.C : 0;
+          const int c = valid[q] ? (int)(m - n * p.C) : 0;
+          second[q] = n != n_first;
+          pc_row[q] = p.pc + (size_t)c * H + ch * 8;
+          pf_row[q] = p.pf + (size_t)n * H + ch * 8;
+        }
+        const float* pf_a = p.pf + (size_t)n_first * H + ch * 8;
+        const float* pf_b = p.pf + (size_t)n_last * H + ch * 8;
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kJStages;
+          uint4 hi[kFPasses], lo[kFPasses];
+          float a[kFPasses][8], fa[8], fb[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
-            bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+          for (int q = 0; q < kFPasses; ++q) ldg_cached8(pc_row[q] + kc * 64, a[q]);
+          if (TWO) {
+            ldg_cached8(pf_a + kc * 64, fa);
+            ldg_cached8(pf_b + kc * 64, fb);
           }
-          umma::split_pack8(t, hi[q], lo[q]);
+#pragma unroll
+          for (int q = 0; q < kFPasses; ++q) {
+            float t[8];
+            if (TWO) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = a[q][e] + (second[q] ? fb[e] : fa[e]);
+            } else {
+              float f[8];
+              ldg_cached8(pf_row[q] + kc * 64, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = a[q][e] + f[e];
+            }
+            const float* wb = s_wb + kc * 64 + ch * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
+              bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+            }
+            umma::split_pack8(t, hi[q], lo[q]);
+          }
+          mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
+          unsigned char* a_hi = base + s * stage_bytes;
+          unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+          for (int q = 0; q < kFPasses; ++q) {
+            const uint32_t off = umma::swizzled_offset(q * (kFProdWarps * 4) + pw * 4 + rsub, ch);
+            *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+            *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(smem_u32(&full[s]));
         }
-        mbar_wait_parity(smem_u32(&empty[s]), ((g / kJStages) & 1) ^ 1);
-        unsigned char* a_hi = base + s * stage_bytes;
-        unsigned char* a_lo = a_hi + a_bytes;
 #pragma unroll
         for (int q = 0; q < kFPasses; ++q) {
-          const uint32_t off = umma::swizzled_offset(q * (kFProdWarps * 4) + pw * 4 + rsub, ch);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
-          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+          float b = bacc[q];
+          b += __shfl_xor_sync(0xffffffffu, b, 1);
+          b += __shfl_xor_sync(0xffffffffu, b, 2);
+          b += __shfl_xor_sync(0xffffffffu, b, 4);
+          if (valid[q] && ch == 0)
+            p.blank[tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub] = b + p.b_blank;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(smem_u32(&full[s]));
       }
-#pragma unroll
-      for (int q = 0; q < kFPasses; ++q) {
-        float b = bacc[q];
-        b += __shfl_xor_sync(0xffffffffu, b, 1);
-        b += __shfl_xor_sync(0xffffffffu, b, 2);
-        b += __shfl_xor_sync(0xffffffffu, b, 4);
-        if (valid[q] && ch == 0) p.blank[tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub] = b + p.b_blank;
-      }
-    }
+    };
+    if (p.C >= 128) run(std::true_type{}); else run(std::false_type{});
   }
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -1074,8 +1100,8 @@ bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const vo
   if (V % 32 != 0 || V < 32 || V > 256) return false;
   if (H % 64 != 0 || H > 4096) return false;
   if (N * (int64_t)C < 1) return false;
-  auto al = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-  return al(pc) && al(pf) && al(lexical);
+  auto al = [](const void* q, int a) { return reinterpret_cast<uintptr_t>(q) % a == 0; };
+  return al(pc, 32) && al(pf, 32) && al(lexical, 16);      // pc / pf: 256-bit loads
 }
 
 // lexical / blank of all M = N*C joint rows on tcgen05 (bf16x3 split, fp32 accumulate).
