@@ -250,8 +250,9 @@ int lt_local_normalize_backward(int mode, const float* blank, const float* lexic
  * The vocabulary projection runs on tcgen05 tensor cores with a 3-way bf16
  * split of both operands (fp32-accurate).
  */
-/* Bytes of device scratch lt_joint_forward needs (bf16 hi/lo split of W_vocab). */
-int64_t lt_joint_workspace_bytes(int C, int H, int V);
+/* Bytes of device scratch lt_joint_forward needs (bf16 hi/lo split of W_vocab and the
+ * e^(2x) tables of the two projections, (C + N) * H floats). */
+int64_t lt_joint_workspace_bytes(int64_t N, int C, int H, int V);
 int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
                      const float* w_blank, float b_blank, const float* w_vocab,
                      const float* b_vocab, int64_t N, int C, int H, int V,

@@ -54,7 +54,7 @@ SIGNATURES = {
     'lt_semiring_sum_forward': [_c_int, _ptr, _c_i64, _c_i64, _c_i64, _ptr, _ptr, _ptr],
     'lt_semiring_sum_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_i64, _c_i64, _ptr,
                                  _ptr],
-    'lt_joint_workspace_bytes': [_c_int, _c_int, _c_int],
+    'lt_joint_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
     'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr, _ptr],
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,

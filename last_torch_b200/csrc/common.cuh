@@ -227,6 +227,17 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// tanh(a + b) from the factors ea = e^(2a), eb = e^(2b) (joint exponential tables):
+//   tanh = 1 - 2 / (1 + ea * eb): ONE MUFU op (the reciprocal) and three FMA-pipe ops.
+__device__ __forceinline__ float rcp_1p(float e) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float tanh_from_exp(float ea, float eb) {
+  return fmaf(-2.f, rcp_1p(ea * eb), 1.f);
+}
+
 // 256-bit global loads (sm_100: LDG.E.256; p must be 32-byte aligned).  A warp that reads 32
 // bytes per lane with two 128-bit loads touches every 128-byte line twice (16-byte accesses at a
 // 32-byte lane stride): twice the L1 data-pipe wavefronts of one 256-bit load.

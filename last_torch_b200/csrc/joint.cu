@@ -145,9 +145,9 @@ int joint_backward_simt(const float* pc, const float* pf, const float* wb, const
 
 using namespace lt;
 
-extern "C" int64_t lt_joint_workspace_bytes(int C, int H, int V) {
-  (void)C;
-  return (int64_t)V * H * 2 * 2 + 256;   // W_vocab as bf16 hi + lo
+extern "C" int64_t lt_joint_workspace_bytes(int64_t N, int C, int H, int V) {
+  // W_vocab as bf16 hi + lo, then the exponential tables of proj_ctx and proj_frame
+  return joint_split_bytes(H, V) + joint_table_bytes(N, C, H);
 }
 
 extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
@@ -185,13 +185,19 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                grad_proj_ctx && grad_proj_frame && grad_w_blank && grad_b_blank && grad_w_vocab &&
                grad_b_vocab, "lt_joint_backward: NULL pointer");
   int simt_parts = 3;
-  if (workspace && reinterpret_cast<uintptr_t>(workspace) % 256 == 0 &&
-      joint_dgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+  const bool ws_ok = workspace && reinterpret_cast<uintptr_t>(workspace) % 256 == 0;
+  // e^(2 proj) tables of the tensor-core kernels (second region of the workspace)
+  float* ec = ws_ok ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                               joint_split_bytes(H, V)) : nullptr;
+  float* ef = ws_ok ? ec + (size_t)C * H : nullptr;
+  bool tables = false;
+  if (ws_ok && joint_dgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     int rc = joint_dgrad_tc_launch(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank,
                                    grad_lexical, N, C, H, V, grad_proj_ctx, grad_proj_frame,
-                                   workspace, (cudaStream_t)stream);
+                                   workspace, (cudaStream_t)stream);     // fills the tables
     if (rc) return rc;
     simt_parts = 2;
+    tables = true;
   }
   if (joint_wgrad2_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     int rc = joint_wgrad2_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
@@ -199,8 +205,12 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                                  (cudaStream_t)stream);
     if (rc) return rc;
     simt_parts &= ~2;
-  } else if (joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
-    int rc = joint_wgrad_tc_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
+  } else if (ws_ok && joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+    if (!tables) {
+      int rc = joint_exp_tables_launch(proj_ctx, proj_frame, N, C, H, ec, ef, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    int rc = joint_wgrad_tc_launch(ec, ef, grad_blank, grad_lexical, N, C, H, V,
                                    grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
                                    (cudaStream_t)stream);
     if (rc) return rc;

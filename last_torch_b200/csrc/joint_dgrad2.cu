@@ -150,8 +150,8 @@ constexpr int kGbRingMax = 8;
 __host__ __device__ constexpr int gb_ring_slots(int V) { return V >= 256 ? 3 : kGbRingMax; }
 
 struct Dgrad2Params {
-  const float* pc;       // [C, H]
-  const float* pf;       // [N, H]
+  const float* pc;       // [C, H]  e^(2 proj_ctx)   (joint_exp_table_kernel)
+  const float* pf;       // [N, H]  e^(2 proj_frame)
   const float* w_blank;  // [H]
   const float* gl;       // [N*C, V]
   const float* gb;       // [N*C]
@@ -298,12 +298,14 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         // two register sets of 8 columns: the loads of one are in flight while the other is
         // being computed (tcgen05.wait::ld after the compute covers them)
         float d0[8], f0[8], a0[8], d1[8], f1[8], a1[8];
+        // tanh' = 1 - tanh^2 = 4 r (1 - r) with r = 1 / (1 + E_c E_f): one MUFU op per element;
+        // the factor 4 is applied once, when csum / the running sums are flushed
         auto compute = [&](int c0, const float (&d)[8], const float (&f)[8], float (&a)[8]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float x = fmaf(gbr[c0 + i], wbj, d[i]);
-            const float h = tanh_fast(pc_cur + f[i]);
-            const float gp = x * fmaf(-h, h, 1.f);
+            const float r = rcp_1p(pc_cur * f[i]);
+            const float gp = x * fmaf(-r, r, r);
             csum += gp;
             a[i] += gp;
           }
@@ -325,7 +327,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         tmem_wait_st();
         umma::fence_before_thread_sync();
         mbar_arrive(smem_u32(&tempty[acc]));
-        atomicAdd(p.gpc + (size_t)c * H + jg, csum);
+        atomicAdd(p.gpc + (size_t)c * H + jg, 4.f * csum);
       }
       // item epilogue: grad_proj_frame[n0 + i, jg] += running sums
       for (int c0 = 0; c0 < kTile; c0 += 16) {
@@ -334,7 +336,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < nvalid) atomicAdd(p.gpf + (size_t)(n0 + c0 + i) * H + jg, a[i]);
+          if (c0 + i < nvalid) atomicAdd(p.gpf + (size_t)(n0 + c0 + i) * H + jg, 4.f * a[i]);
       }
       c = 0;
       ++nb;

@@ -220,8 +220,8 @@ constexpr int kFProducers = kFProdWarps * 32;
 constexpr int kFPasses = 128 / (kFProdWarps * 4);
 
 struct JointTcParams {
-  const float* pc;       // [C, H]
-  const float* pf;       // [N, H]
+  const float* pc;       // [C, H]  e^(2 proj_ctx)   (joint_exp_table_kernel)
+  const float* pf;       // [N, H]  e^(2 proj_frame)
   const float* w_blank;  // [H]
   const float* b_vocab;  // [V]
   float b_blank;
@@ -271,6 +271,23 @@ __device__ __forceinline__ void store_block_coalesced(const float (&v)[32], floa
 #pragma unroll 8
   for (int r = 0; r < 32; ++r)
     if (r < rows_valid) out_row0[(size_t)r * row_stride + lane] = tr[r * 33 + lane];
+}
+
+// Exponential tables of the two projections: out = e^(2x) = 2^(2 log2(e) x), exponent clamped
+// to +-63 so that the product of two entries is always a normal fp32 number.  tanh(pc + pf) then
+// costs one reciprocal: 1 - 2 / (1 + E_c E_f).  Evaluated in double precision (the table is
+// O((C + N) H), the joint is O(N C H)): each entry is correctly rounded, so the product carries
+// ~1.5 ulp -- no worse than rounding the fp32 argument 2 log2(e) (pc + pf) of an ex2.  The clamp
+// only matters for |x| > 21.8, where fp32 tanh has long saturated (|x| > 9.1) unless the OTHER
+// projection cancels it to within 9: both beyond 12.7 with opposite signs.
+__global__ void joint_exp_table_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                       long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double a = (double)x[i] * 2.8853900817779268;
+    a = a < -63.0 ? -63.0 : (a > 63.0 ? 63.0 : a);
+    out[i] = (float)exp2(a);
+  }
 }
 
 __global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
@@ -442,17 +459,14 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
             float t[8];
             if (TWO) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) t[e] = a[q][e] + (second[q] ? fb[e] : fa[e]);
+              for (int e = 0; e < 8; ++e) t[e] = second[q] ? fb[e] : fa[e];
             } else {
-              float f[8];
-              ldg_cached8(pf_row[q] + kc * 64, f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t[e] = a[q][e] + f[e];
+              ldg_cached8(pf_row[q] + kc * 64, t);
             }
             const float* wb = s_wb + kc * 64 + ch * 8;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
+              t[e] = valid[q] ? tanh_from_exp(a[q][e], t[e]) : 0.f;
               bacc[q] = fmaf(t[e], wb[e], bacc[q]);
             }
             umma::split_pack8(t, hi[q], lo[q]);
@@ -828,8 +842,8 @@ constexpr int kWStages = 6;
 constexpr int kWK = 16;                 // joint rows per stage
 
 struct JointWgradParams {
-  const float* pc;       // [C, H]
-  const float* pf;       // [N, H]
+  const float* pc;       // [C, H]  e^(2 proj_ctx)   (joint_exp_table_kernel)
+  const float* pf;       // [N, H]  e^(2 proj_frame)
   const float* gl;       // [M, V]
   const float* gb;       // [M]
   long long M, rows_per_cta;
@@ -1011,8 +1025,7 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
         float t[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          t[e] = cur.bp[i][e] + (wrapped ? pfb[e] : pfa[e]);
-          t[e] = live ? tanh_fast(t[e]) : 0.f;
+          t[e] = live ? tanh_from_exp(cur.bp[i][e], wrapped ? pfb[e] : pfa[e]) : 0.f;
           wb_acc[e] = fmaf(cur.gbm[i], t[e], wb_acc[e]);
         }
         if (b_jch == 0) bb_acc += cur.gbm[i];
@@ -1104,6 +1117,24 @@ bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const vo
   return al(pc, 32) && al(pf, 32) && al(lexical, 16);      // pc / pf: 256-bit loads
 }
 
+// workspace layout: [bf16 hi | lo of W_vocab (or its transpose)] [E_c [C,H] | E_f [N,H]] ...
+int64_t joint_split_bytes(int H, int V) { return (((int64_t)V * H * 4 + 255) / 256) * 256; }
+int64_t joint_table_bytes(int64_t N, int C, int H) {
+  return (((N + C) * (int64_t)H * 4 + 255) / 256) * 256;
+}
+// e^(2 pc) -> ec [C,H], e^(2 pf) -> ef [N,H]
+int joint_exp_tables_launch(const float* pc, const float* pf, int64_t N, int C, int H,
+                                   float* ec, float* ef, cudaStream_t stream) {
+  const long long nc = (long long)C * H, nf = (long long)N * H;
+  joint_exp_table_kernel<<<(unsigned)std::min<long long>((nc + 255) / 256, 4096), 256, 0, stream>>>(
+      pc, ec, nc);
+  LT_LAUNCHED();
+  joint_exp_table_kernel<<<(unsigned)std::min<long long>((nf + 255) / 256, 4096), 256, 0, stream>>>(
+      pf, ef, nf);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
 // lexical / blank of all M = N*C joint rows on tcgen05 (bf16x3 split, fp32 accumulate).
 int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
                             const float* wv, const float* bv, int64_t N, int C, int H, int V,
@@ -1134,8 +1165,12 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   }
   if (pair)
     return joint_fwd2_launch(map_hi, map_lo, pc, pf, wb, bb, bv, N, C, H, V, blank, lexical, stream);
+  float* ec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                       joint_split_bytes(H, V));
+  float* ef = ec + (size_t)C * H;
+  if (int rc = joint_exp_tables_launch(pc, pf, N, C, H, ec, ef, stream)) return rc;
   JointTcParams p = {};
-  p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
+  p.pc = ec; p.pf = ef; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
   const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
                       sizeof(float) * (H + 256 + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
@@ -1169,7 +1204,7 @@ static bool dgrad2_shape_ok(int H, int V) {
 
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
   // bf16 hi / lo of W_vocab^T; the first-generation dgrad also needs the [M, H] buffer
-  const int64_t split = (int64_t)H * V * 2 * 2 + 512;
+  const int64_t split = joint_split_bytes(H, V) + joint_table_bytes(N, C, H);
   if (dgrad2_shape_ok(H, V)) return split;
   return split + N * (int64_t)C * H * 4;
 }
@@ -1182,8 +1217,12 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
   if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
   __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(workspace);
   __nv_bfloat16* wlo = whi + (size_t)H * V;
-  float* gp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
-                                       (((size_t)H * V * 4 + 255) / 256) * 256);
+  float* ec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
+                                       joint_split_bytes(H, V));
+  float* ef = ec + (size_t)C * H;
+  float* gp = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ec) +
+                                       joint_table_bytes(N, C, H));
+  if (int rc = joint_exp_tables_launch(pc, pf, N, C, H, ec, ef, stream)) return rc;
   transpose_split_kernel<<<(V * H + 255) / 256, 256, 0, stream>>>(wv, whi, wlo, V, H);
   LT_LAUNCHED();
   if (joint_dgrad2_supported(N, C, H, V, gl, pc, pf)) {
@@ -1203,7 +1242,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
         return LT_ERR_CUDA;
       }
     }
-    return joint_dgrad2_launch(m_hi, m_lo, pc, pf, wb, gb, gl, N, C, H, V, gpc, gpf, stream);
+    return joint_dgrad2_launch(m_hi, m_lo, ec, ef, wb, gb, gl, N, C, H, V, gpc, gpf, stream);
   }
   const int NH = H > 256 ? 256 : H;
   CUtensorMap map_hi, map_lo;

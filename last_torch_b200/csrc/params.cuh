@@ -133,6 +133,11 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
 bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
+// workspace layout of both directions: [W_vocab bf16 hi | lo] [e^(2 pc) [C,H] | e^(2 pf) [N,H]] ...
+int64_t joint_split_bytes(int H, int V);
+int64_t joint_table_bytes(int64_t N, int C, int H);
+int joint_exp_tables_launch(const float* pc, const float* pf, int64_t N, int C, int H, float* ec,
+                            float* ef, cudaStream_t stream);
 int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
                           const float* gb, const float* gl, int64_t N, int C, int H, int V,
                           float* gpc, float* gpf, void* workspace, cudaStream_t stream);
@@ -156,7 +161,8 @@ int joint_wgrad2_launch(const float* pc, const float* pf, const float* gb, const
                         float* gbv, cudaStream_t stream);
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
-int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,
+// ec / ef: the exponential tables (joint_exp_tables_launch), not the projections
+int joint_wgrad_tc_launch(const float* ec, const float* ef, const float* gb, const float* gl,
                           int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
                           float* gbv, cudaStream_t stream);
 int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);

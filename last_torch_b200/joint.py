@@ -28,7 +28,7 @@ class _JointProjection(torch.autograd.Function):
     dev = proj_frame.device
     blank = torch.empty([n, c], dtype=torch.float32, device=dev)
     lexical = torch.empty([n, c, v], dtype=torch.float32, device=dev)
-    workspace = torch.empty([int(N.lib().lt_joint_workspace_bytes(c, h, v))], dtype=torch.uint8,
+    workspace = torch.empty([int(N.lib().lt_joint_workspace_bytes(n, c, h, v))], dtype=torch.uint8,
                             device=dev)
     with torch.cuda.device(dev):
       N.check(N.lib().lt_joint_forward(
