@@ -9,6 +9,9 @@ WANT = [
     'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__grid_size',
     'launch__block_size', 'launch__cluster_dim_x', 'launch__occupancy_limit_shared_mem',
     'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
 ]
 out_path, raws = sys.argv[1], sys.argv[2:]
