@@ -129,6 +129,39 @@ def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
     assert float((q - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((q - r).abs().max()) / scale)
 
 
+@pytest.mark.parametrize('c,v,h,n', [(65, 64, 128, 148 * 128 + 77), (130, 128, 256, 37 * 128 * 2 + 5)])
+def test_joint_backward_frame_blocks_straddle_ctas(c, v, h, n):
+  """More 128-frame blocks than CTAs per hidden block: the fused dgrad cuts the (frame block, c)
+  tile sequence into equal ranges, so blocks straddle two CTAs and grad_proj_frame is flushed by
+  both; the last block is partial (rows past N read the zero line).  Tensor-core path against the
+  CUDA-core kernels (themselves checked against autograd above)."""
+  import os
+  import last_torch_b200 as lt
+  torch.manual_seed(n)
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=24,
+                                   feature_size=16)
+  params = list(fn.parameters())
+  cache = torch.randn([c, 24], device='cuda', requires_grad=True)
+  frames = torch.randn([n, 1, 16], device='cuda', requires_grad=True)
+  wb = torch.randn([n, 1, c], device='cuda')
+  wl = torch.randn([n, 1, c, v], device='cuda')
+
+  def run(simt):
+    if simt:
+      os.environ['LT_JOINT_SIMT'] = '1'
+    try:
+      b, l = fn.all_frames(cache, frames)
+      g = torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
+      return [b.detach(), l.detach()] + list(g)
+    finally:
+      os.environ.pop('LT_JOINT_SIMT', None)
+
+  tc, simt = run(False), run(True)
+  for a, s in zip(tc, simt):
+    scale = float(s.abs().max()) + 1e-12
+    assert float((a - s).abs().max()) / scale < 3e-5, (tuple(s.shape), float((a - s).abs().max()) / scale)
+
+
 def _probe_mn(at, bt, swap):
   from last_torch_b200 import _native as N
   N.lib()
