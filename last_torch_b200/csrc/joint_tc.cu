@@ -298,7 +298,8 @@ __global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
 
 __global__ void __launch_bounds__(kFThreads, 1)
 joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
-                        const __grid_constant__ CUtensorMap map_lo, const JointTcParams p) {
+                        const __grid_constant__ CUtensorMap map_lo,
+                        const __grid_constant__ CUtensorMap map_out, const JointTcParams p) {
   extern __shared__ __align__(1024) unsigned char jsmem_raw[];
   unsigned char* base = jsmem_raw + ((1024u - (smem_u32(jsmem_raw) & 1023u)) & 1023u);
   const int V = p.V, H = p.H;
@@ -306,10 +307,11 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const uint32_t b_bytes = (uint32_t)V * 128;         // one V x 64 bf16 tile
   const uint32_t stage_bytes = 2 * a_bytes + 2 * 256 * 128;
   // stage layout: A_hi | A_lo | B_hi | B_lo
-  float* s_wb = reinterpret_cast<float*>(base + kJStages * stage_bytes);   // [H]
+  // epilogue staging: one [32 rows x 128 B] SWIZZLE_128B tile per epilogue warp (1024-aligned)
+  unsigned char* s_out = base + kJStages * stage_bytes;                    // 4 x 4096 B
+  float* s_wb = reinterpret_cast<float*>(s_out + 4 * 4096);                // [H], permuted
   float* s_bias = s_wb + H;                                                // [V]
-  float* s_tr = s_bias + 256;                                              // 4 x [32][33]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* full = bars;                    // [stages]  producers + TMA -> MMA
   uint64_t* empty = bars + kJStages;        // [stages]  MMA (commit) -> producers, TMA
   uint64_t* tfull = bars + 2 * kJStages;    // [2]       MMA (commit) -> epilogue
@@ -320,9 +322,16 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int nchunks = H / 64;
   const long long num_tiles = (p.M + 127) / 128;
 
-  for (int i = tid; i < H; i += kFThreads) s_wb[i] = p.w_blank[i];
+  // w_blank permuted inside every 64-wide chunk so that the 8 producer lanes of a row read two
+  // contiguous 128-byte runs (elements 0-3 of each lane, then elements 4-7) with one wavefront
+  // each instead of 16-byte pieces at a 32-byte stride
+  for (int i = tid; i < H; i += kFThreads) {
+    const int w = i & 63, lane8 = w >> 3, e = w & 7;
+    s_wb[(i & ~63) + (e < 4 ? lane8 * 4 + e : 32 + lane8 * 4 + (e - 4))] = p.w_blank[i];
+  }
   for (int i = tid; i < V; i += kFThreads) s_bias[i] = p.b_vocab[i];
   if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     for (int s = 0; s < kJStages; ++s) {
       mbar_init_n(smem_u32(&full[s]), kFProducers + 1);
       mbar_init_n(smem_u32(&empty[s]), 1);
@@ -397,18 +406,42 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
       const long long m0 = tile * 128 + quad * 32;
-      const int rows_valid = (int)max(0ll, min(32ll, p.M - m0));
-      float* out = p.lexical + (size_t)m0 * V;
+      // The accumulator arrives with lane = row and 32 consecutive columns per thread.  Each
+      // thread writes its 128 bytes into a [32 x 128 B] SWIZZLE_128B staging tile (conflict-
+      // free 128-bit stores) and ONE bulk tensor store per block moves it to global memory --
+      // full lines, rows past M clipped by the hardware, and no load / store instruction of
+      // the output goes through the LSU (it is the L1 data pipe that bounds this kernel).
+      unsigned char* stage_tile = s_out + quad * 4096;
       for (int c0 = 0; c0 < V; c0 += 32) {
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
-        store_block_coalesced(v, s_tr + quad * (32 * 33), lane, out + c0, (size_t)V, rows_valid);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+        // the previous block's bulk store must have finished READING the staging tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(stage_tile + umma::swizzled_offset(lane, k)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m0 < p.M) {
+          asm volatile(
+              "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                  &map_out),
+              "r"(c0), "r"((int)m0), "r"(smem_u32(stage_tile))
+              : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       umma::fence_before_thread_sync();
       mbar_arrive(smem_u32(&tempty[acc]));
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // -------------------------------------------------------------- A producers
     // 8 lanes cover one row's 64-wide K chunk (256 contiguous bytes of pc / pf, one
@@ -463,7 +496,9 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
             } else {
               ldg_cached8(pf_row[q] + kc * 64, t);
             }
-            const float* wb = s_wb + kc * 64 + ch * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(s_wb + kc * 64 + ch * 4);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_wb + kc * 64 + 32 + ch * 4);
+            const float wb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               t[e] = valid[q] ? tanh_from_exp(a[q][e], t[e]) : 0.f;
@@ -1172,8 +1207,23 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   JointTcParams p = {};
   p.pc = ec; p.pf = ef; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
-  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) +
-                      sizeof(float) * (H + 256 + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
+  // output map: lexical [M, V] fp32, box = one epilogue block (32 rows x 32 columns = 128 B rows)
+  CUtensorMap map_out;
+  {
+    cuuint64_t odims[2] = {(cuuint64_t)V, (cuuint64_t)p.M};
+    cuuint64_t ostrides[1] = {(cuuint64_t)V * 4};
+    cuuint32_t obox[2] = {32, 32};
+    cuuint32_t oestr[2] = {1, 1};
+    CUresult r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, lexical, odims, ostrides,
+                        obox, oestr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (lexical output) failed with %d", (int)r);
+      return LT_ERR_CUDA;
+    }
+  }
+  const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + 4 * 4096 +
+                      sizeof(float) * (H + 256) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1181,7 +1231,7 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   const int grid = (int)(tiles < sms ? tiles : sms);
   LT_CUDA(cudaFuncSetAttribute(joint_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  joint_forward_tc_kernel<<<grid, kFThreads, smem, stream>>>(map_hi, map_lo, p);
+  joint_forward_tc_kernel<<<grid, kFThreads, smem, stream>>>(map_hi, map_lo, map_out, p);
   LT_LAUNCHED();
   return LT_OK;
 }
