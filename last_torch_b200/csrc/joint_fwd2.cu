@@ -18,6 +18,7 @@
 // local variable with the peer bit (bit 24) cleared.
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "params.cuh"
@@ -121,8 +122,8 @@ constexpr int kF2Producers = kF2ProdWarps * 32;
 constexpr int kF2Passes = 128 / (kF2ProdWarps * 4);
 
 struct JointFwd2Params {
-  const float* pc;       // [C, H]
-  const float* pf;       // [N, H]
+  const float* pc;       // [C, H]  e^(2 proj_ctx)   (joint_exp_table_kernel)
+  const float* pf;       // [N, H]  e^(2 proj_frame)
   const float* w_blank;  // [H]
   const float* b_vocab;  // [V]
   float b_blank;
@@ -134,17 +135,19 @@ struct JointFwd2Params {
 
 __global__ void __launch_bounds__(kF2Threads, 1)
 joint_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi,
-                         const __grid_constant__ CUtensorMap map_lo, const JointFwd2Params p) {
+                         const __grid_constant__ CUtensorMap map_lo,
+                         const __grid_constant__ CUtensorMap map_out, const JointFwd2Params p) {
   extern __shared__ __align__(1024) unsigned char f2smem_raw[];
   unsigned char* base = f2smem_raw + ((1024u - (smem_u32(f2smem_raw) & 1023u)) & 1023u);
   const int V = p.V, H = p.H, Vh = V / 2;
   const uint32_t a_bytes = 128 * 128;                 // one 128 x 64 bf16 tile
   const uint32_t bh_bytes = (uint32_t)Vh * 128;       // this CTA's half of a V x 64 bf16 tile
   const uint32_t stage_bytes = 2 * a_bytes + 2 * 128 * 128;     // A_hi | A_lo | B_hi/2 | B_lo/2
-  float* s_wb = reinterpret_cast<float*>(base + kF2Stages * stage_bytes);   // [H]
+  // epilogue staging: one [32 rows x 128 B] SWIZZLE_128B tile per epilogue warp (1024-aligned)
+  unsigned char* s_out = base + kF2Stages * stage_bytes;                    // 4 x 4096 B
+  float* s_wb = reinterpret_cast<float*>(s_out + 4 * 4096);                 // [H], permuted
   float* s_bias = s_wb + H;                                                 // [V]
-  float* s_tr = s_bias + 256;                                               // 4 x [32][33]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* full = bars;
   uint64_t* empty = bars + kF2Stages;
   uint64_t* tfull = bars + 2 * kF2Stages;
@@ -157,11 +160,16 @@ joint_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int nchunks = H / 64;
   const long long num_tiles = (p.M + 255) / 256;      // 256-row tiles, 128 rows per CTA
 
-  for (int i = tid; i < H; i += kF2Threads) s_wb[i] = p.w_blank[i];
+  // w_blank permuted inside every 64-wide chunk (see joint_forward_tc_kernel)
+  for (int i = tid; i < H; i += kF2Threads) {
+    const int w = i & 63, lane8 = w >> 3, e = w & 7;
+    s_wb[(i & ~63) + (e < 4 ? lane8 * 4 + e : 32 + lane8 * 4 + (e - 4))] = p.w_blank[i];
+  }
   for (int i = tid; i < V; i += kF2Threads) s_bias[i] = p.b_vocab[i];
   if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     for (int s = 0; s < kF2Stages; ++s) {
-      mbar_init_n(smem_u32(&full[s]), 2 * kF2Producers + 2);
+      mbar_init_n(smem_u32(&full[s]), 2 * kF2ProdWarps + 2);   // one arrival per producer warp
       mbar_init_n(smem_u32(&empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -235,80 +243,121 @@ joint_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi,
       mbar_wait_parity(smem_u32(&tfull[acc]), (it >> 1) & 1);
       umma::fence_after_thread_sync();
       const long long m0 = tile * 256 + (long long)rank * 128 + quad * 32;
-      const int rows_valid = (int)max(0ll, min(32ll, p.M - m0));
-      float* out = p.lexical + (size_t)m0 * V;
+      // swizzled staging tile + one bulk tensor store per 32 x 32 block (see joint_tc.cu)
+      unsigned char* stage_tile = s_out + quad * 4096;
       for (int c0 = 0; c0 < V; c0 += 32) {
         float v[32];
         umma::tmem_ld32(tmem + acc * 256 + ((uint32_t)(quad * 32) << 16) + c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
-        store_block_coalesced(v, s_tr + quad * (32 * 33), lane, out + c0, (size_t)V, rows_valid);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(stage_tile + umma::swizzled_offset(lane, k)) =
+              make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m0 < p.M) {
+          asm volatile(
+              "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                  &map_out),
+              "r"(c0), "r"((int)m0), "r"(smem_u32(stage_tile))
+              : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       umma::fence_before_thread_sync();
       mbar_arrive_leader(smem_u32(&tempty[acc]));
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ------------------------------------------------ A producers: this CTA's 128 rows
     const int pw = warp - 6;
     const int ch = lane & 7, rsub = lane >> 3;
     uint32_t g = 0;
-    for (long long tile = pair; tile < num_tiles; tile += npairs) {
-      const float* pc_row[kF2Passes];
-      const float* pf_row[kF2Passes];
-      bool valid[kF2Passes];
-      float bacc[kF2Passes];
-      const long long mbase = tile * 256 + (long long)rank * 128;
-#pragma unroll
-      for (int q = 0; q < kF2Passes; ++q) {
-        bacc[q] = 0.f;
-        const long long m = mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub;
-        valid[q] = m < p.M;
-        const long long n = valid[q] ? m / p.C : 0;
-        const int c = valid[q] ? (int)(m - n * p.C) : 0;
-        pc_row[q] = p.pc + (size_t)c * H + ch * 8;
-        pf_row[q] = p.pf + (size_t)n * H + ch * 8;
-      }
-      for (int kc = 0; kc < nchunks; ++kc, ++g) {
-        const int s = g % kF2Stages;
-        uint4 hi[kF2Passes], lo[kF2Passes];
+    // 256-bit loads of the exponential tables; with C >= 128 the 128 rows of this CTA touch at
+    // most two frames, whose pf slices are loaded once per chunk (see joint_forward_tc_kernel)
+    auto run = [&](auto two_frames_tag) {
+      constexpr bool TWO = decltype(two_frames_tag)::value;
+      for (long long tile = pair; tile < num_tiles; tile += npairs) {
+        const float* pc_row[kF2Passes];
+        const float* pf_row[kF2Passes];
+        bool valid[kF2Passes], second[kF2Passes];
+        float bacc[kF2Passes];
+        const long long mbase = tile * 256 + (long long)rank * 128;
+        const long long n_first = min(mbase, p.M - 1) / p.C;
+        const long long n_last = min(mbase + 127, p.M - 1) / p.C;
 #pragma unroll
         for (int q = 0; q < kF2Passes; ++q) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(pc_row[q] + kc * 64 + 4));
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(pf_row[q] + kc * 64 + 4));
-          float t[8] = {a0.x + f0.x, a0.y + f0.y, a0.z + f0.z, a0.w + f0.w,
-                        a1.x + f1.x, a1.y + f1.y, a1.z + f1.z, a1.w + f1.w};
-          const float* wb = s_wb + kc * 64 + ch * 8;
+          bacc[q] = 0.f;
+          const long long m = mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub;
+          valid[q] = m < p.M;
+          const long long n = valid[q] ? m / p.C : 0;
+          const int c = valid[q] ? (int)(m - n * p.C) : 0;
+          second[q] = n != n_first;
+          pc_row[q] = p.pc + (size_t)c * H + ch * 8;
+          pf_row[q] = p.pf + (size_t)n * H + ch * 8;
+        }
+        const float* pf_a = p.pf + (size_t)n_first * H + ch * 8;
+        const float* pf_b = p.pf + (size_t)n_last * H + ch * 8;
+        for (int kc = 0; kc < nchunks; ++kc, ++g) {
+          const int s = g % kF2Stages;
+          uint4 hi[kF2Passes], lo[kF2Passes];
+          float a[kF2Passes][8], fa[8], fb[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            t[e] = valid[q] ? tanh_fast(t[e]) : 0.f;
-            bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+          for (int q = 0; q < kF2Passes; ++q) ldg_cached8(pc_row[q] + kc * 64, a[q]);
+          if (TWO) {
+            ldg_cached8(pf_a + kc * 64, fa);
+            ldg_cached8(pf_b + kc * 64, fb);
           }
-          umma::split_pack8(t, hi[q], lo[q]);
+#pragma unroll
+          for (int q = 0; q < kF2Passes; ++q) {
+            float t[8];
+            if (TWO) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = second[q] ? fb[e] : fa[e];
+            } else {
+              ldg_cached8(pf_row[q] + kc * 64, t);
+            }
+            const float4 w0 = *reinterpret_cast<const float4*>(s_wb + kc * 64 + ch * 4);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_wb + kc * 64 + 32 + ch * 4);
+            const float wb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              t[e] = valid[q] ? tanh_from_exp(a[q][e], t[e]) : 0.f;
+              bacc[q] = fmaf(t[e], wb[e], bacc[q]);
+            }
+            umma::split_pack8(t, hi[q], lo[q]);
+          }
+          mbar_wait_parity(smem_u32(&empty[s]), ((g / kF2Stages) & 1) ^ 1);
+          unsigned char* a_hi = base + s * stage_bytes;
+          unsigned char* a_lo = a_hi + a_bytes;
+#pragma unroll
+          for (int q = 0; q < kF2Passes; ++q) {
+            const uint32_t off = umma::swizzled_offset(q * (kF2ProdWarps * 4) + pw * 4 + rsub, ch);
+            *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
+            *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(smem_u32(&full[s]));
         }
-        mbar_wait_parity(smem_u32(&empty[s]), ((g / kF2Stages) & 1) ^ 1);
-        unsigned char* a_hi = base + s * stage_bytes;
-        unsigned char* a_lo = a_hi + a_bytes;
 #pragma unroll
         for (int q = 0; q < kF2Passes; ++q) {
-          const uint32_t off = umma::swizzled_offset(q * (kF2ProdWarps * 4) + pw * 4 + rsub, ch);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi[q];
-          *reinterpret_cast<uint4*>(a_lo + off) = lo[q];
+          float bsum = bacc[q];
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+          if (valid[q] && ch == 0)
+            p.blank[mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub] = bsum + p.b_blank;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_leader(smem_u32(&full[s]));
       }
-#pragma unroll
-      for (int q = 0; q < kF2Passes; ++q) {
-        float bsum = bacc[q];
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
-        if (valid[q] && ch == 0)
-          p.blank[mbase + q * (kF2ProdWarps * 4) + pw * 4 + rsub] = bsum + p.b_blank;
-      }
-    }
+    };
+    if (p.C >= 128) run(std::true_type{}); else run(std::false_type{});
   }
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -330,14 +379,15 @@ bool joint_fwd2_supported(int64_t N, int C, int H, int V) {
 }
 
 // map_hi / map_lo: W_vocab [V, H] as bf16 hi / lo with box [64 x V/2] (SWIZZLE_128B)
-int joint_fwd2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const float* pc,
+int joint_fwd2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
+                      const CUtensorMap& map_out, const float* pc,
                       const float* pf, const float* wb, float bb, const float* bv, int64_t N,
                       int C, int H, int V, float* blank, float* lexical, cudaStream_t stream) {
   JointFwd2Params p = {};
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.b_vocab = bv; p.b_blank = bb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.blank = blank; p.lexical = lexical;
-  const size_t smem = (size_t)kF2Stages * (2 * 128 * 128 + 2 * 128 * 128) +
-                      sizeof(float) * (H + 256 + 4 * 32 * 33) + 16 * 8 + 16 + 1024;
+  const size_t smem = (size_t)kF2Stages * (2 * 128 * 128 + 2 * 128 * 128) + 4 * 4096 +
+                      sizeof(float) * (H + 256) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -359,7 +409,7 @@ int joint_fwd2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LT_CUDA(cudaLaunchKernelEx(&cfg, joint_forward_tc2_kernel, map_hi, map_lo, p));
+  LT_CUDA(cudaLaunchKernelEx(&cfg, joint_forward_tc2_kernel, map_hi, map_lo, map_out, p));
   note_launch();
   return LT_OK;
 }

@@ -1198,8 +1198,6 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
       return LT_ERR_CUDA;
     }
   }
-  if (pair)
-    return joint_fwd2_launch(map_hi, map_lo, pc, pf, wb, bb, bv, N, C, H, V, blank, lexical, stream);
   float* ec = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
                                        joint_split_bytes(H, V));
   float* ef = ec + (size_t)C * H;
@@ -1222,6 +1220,9 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
       return LT_ERR_CUDA;
     }
   }
+  if (pair)
+    return joint_fwd2_launch(map_hi, map_lo, map_out, ec, ef, wb, bb, bv, N, C, H, V, blank,
+                             lexical, stream);
   const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + 4 * 4096 +
                       sizeof(float) * (H + 256) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;

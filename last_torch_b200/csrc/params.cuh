@@ -143,7 +143,9 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
                           float* gpc, float* gpf, void* workspace, cudaStream_t stream);
 // CTA-pair (cta_group::2) forward (joint_fwd2.cu)
 bool joint_fwd2_supported(int64_t N, int C, int H, int V);
-int joint_fwd2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo, const float* pc,
+// pc / pf: the exponential tables (joint_exp_tables_launch); map_out: lexical [M, V], 32 x 32 box
+int joint_fwd2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo,
+                      const CUtensorMap_st& map_out, const float* pc,
                       const float* pf, const float* wb, float bb, const float* bv, int64_t N,
                       int C, int H, int V, float* blank, float* lexical, cudaStream_t stream);
 // fused dgrad + reductions (joint_dgrad2.cu)
