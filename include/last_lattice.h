@@ -268,7 +268,14 @@ int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                       int64_t N, int C, int H, int V, float* grad_proj_ctx,
                       float* grad_proj_frame, float* grad_w_blank,
                       float* grad_b_blank, float* grad_w_vocab,
-                      float* grad_b_vocab, void* workspace, void* stream);
+                      float* grad_b_vocab, void* workspace,
+                      int grad_lexical_format, void* stream);
+/* grad_lexical_format: 0 = fp32 [N, C, V]; 1 = "split rows": every row of V floats is replaced,
+ * in the same V*4 bytes, by [V bf16 hi | V bf16 lo] with hi + lo = the value to 2^-17 -- the
+ * operand form of the tensor-core kernels, which lt_lattice_backward can emit directly
+ * (LT_FLAG_GRAD_SPLIT), so the fused dgrad loads it with TMA and converts nothing.  Only when
+ * lt_joint_backward_split_supported() returns 1. */
+int lt_joint_backward_split_supported(int64_t N, int C, int H, int V);
 /* Bytes of device scratch for lt_joint_backward (W_vocab^T as bf16 hi/lo + the
  * [N*C, H] pre-activation gradient that is reduced into the two projections);
  * workspace may be NULL, which selects the CUDA-core kernels. */

@@ -58,7 +58,8 @@ SIGNATURES = {
     'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr, _ptr],
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
-                          _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+                          _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
+    'lt_joint_backward_split_supported': [_c_i64, _c_int, _c_int, _c_int],
     'lt_joint_backward_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
     'lt_table_lattice_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr,
                                  _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
@@ -114,6 +115,7 @@ def lib():
 # current stream of the current device -- the stream the kernel is launched on).
 KERNEL_TIMER = None
 _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count',
+            'lt_joint_backward_split_supported',
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 

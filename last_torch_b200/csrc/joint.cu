@@ -167,6 +167,10 @@ extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
                             blank, lexical, (cudaStream_t)stream);
 }
 
+extern "C" int lt_joint_backward_split_supported(int64_t N, int C, int H, int V) {
+  return joint_backward_split_supported(N, C, H, V) ? 1 : 0;
+}
+
 extern "C" int64_t lt_joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
   return joint_backward_workspace_bytes(N, C, H, V);
 }
@@ -177,15 +181,35 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                                  int C, int H, int V, float* grad_proj_ctx,
                                  float* grad_proj_frame, float* grad_w_blank, float* grad_b_blank,
                                  float* grad_w_vocab, float* grad_b_vocab, void* workspace,
-                                 void* stream) {
+                                 int grad_lexical_format, void* stream) {
   LT_CHECK_ARG(N >= 0 && C > 0 && H > 0 && V > 0, "lt_joint_backward: bad sizes N=%lld C=%d H=%d V=%d",
                (long long)N, C, H, V);
   if (N == 0) return LT_OK;
   LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && w_vocab && grad_blank && grad_lexical &&
                grad_proj_ctx && grad_proj_frame && grad_w_blank && grad_b_blank && grad_w_vocab &&
                grad_b_vocab, "lt_joint_backward: NULL pointer");
+  LT_CHECK_ARG(grad_lexical_format == 0 || grad_lexical_format == 1,
+               "lt_joint_backward: grad_lexical_format must be 0 (fp32) or 1 (split rows)");
   int simt_parts = 3;
   const bool ws_ok = workspace && reinterpret_cast<uintptr_t>(workspace) % 256 == 0;
+  int split = grad_lexical_format;
+  if (split) {
+    LT_CHECK_ARG(ws_ok && joint_backward_split_supported(N, C, H, V) &&
+                     reinterpret_cast<uintptr_t>(grad_lexical) % 32 == 0,
+                 "lt_joint_backward: split-row grad_lexical is not supported for this shape "
+                 "(ask lt_joint_backward_split_supported first)");
+  }
+  const float* dgrad_gl = grad_lexical;
+  if (!split && ws_ok && getenv("LT_JOINT_DGRAD_SPLIT_TEST") &&
+      joint_backward_split_supported(N, C, H, V)) {
+    // test hook: run the fused dgrad on a split copy of the fp32 gradient
+    unsigned char* copy = reinterpret_cast<unsigned char*>(workspace) + joint_split_bytes(H, V) +
+                          joint_table_bytes(N, C, H);
+    int rc = joint_split_rows_launch(grad_lexical, copy, N * (int64_t)C, V, (cudaStream_t)stream);
+    if (rc) return rc;
+    dgrad_gl = reinterpret_cast<const float*>(copy);
+    split = 2;      // dgrad only
+  }
   // e^(2 proj) tables of the tensor-core kernels (second region of the workspace)
   float* ec = ws_ok ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
                                                joint_split_bytes(H, V)) : nullptr;
@@ -193,8 +217,8 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
   bool tables = false;
   if (ws_ok && joint_dgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     int rc = joint_dgrad_tc_launch(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank,
-                                   grad_lexical, N, C, H, V, grad_proj_ctx, grad_proj_frame,
-                                   workspace, (cudaStream_t)stream);     // fills the tables
+                                   dgrad_gl, split != 0, N, C, H, V, grad_proj_ctx,
+                                   grad_proj_frame, workspace, (cudaStream_t)stream);  // + tables
     if (rc) return rc;
     simt_parts = 2;
     tables = true;

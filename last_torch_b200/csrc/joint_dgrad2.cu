@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int
       "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                       uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 // tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU ops; absolute error ~1e-7
 __device__ __forceinline__ float tanh_fast(float x) {
   float e, r;
@@ -138,6 +145,9 @@ constexpr int kDProdWarps = 16;
 constexpr int kDThreads = (6 + kDProdWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue,
                                                     // warps 6.. producers
 constexpr int kDProducers = kDProdWarps * 32;
+constexpr int kDSplitThreads = 6 * 32;    // split-row variant: TMA, MMA, 4 epilogue warps, no producers
+                                          // (8 epilogue warps, two per TMEM lane quadrant, measured
+                                          // slower: 5.15 vs 4.92 ms)
 constexpr int kDPasses = 128 / (kDProdWarps * 4);   // row passes per producer thread and chunk
 constexpr int kDStages = 3;
 constexpr int kTile = 128;              // joint rows per tile = frames per work item
@@ -161,9 +171,15 @@ struct Dgrad2Params {
   float* gpf;            // [N, H]  += (atomics: a frame block can straddle two CTAs)
 };
 
-__global__ void __launch_bounds__(kDThreads, 1)
+// SPLIT: grad_lexical arrives as rows of [V bf16 hi | V bf16 lo] (same bytes as fp32; written by
+// the lattice backward kernel, see lt_lattice_backward / LT_FLAG_GRAD_SPLIT).  The B operand is
+// then a plain TMA load -- one [128 frames x 1 state x 64] box of map_g per half -- and the 16
+// producer warps disappear: warp 0 issues the loads and ferries the grad_blank slices.
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kDSplitThreads : kDThreads, 1)
 joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
-                    const __grid_constant__ CUtensorMap map_lo, const Dgrad2Params p) {
+                    const __grid_constant__ CUtensorMap map_lo,
+                    const __grid_constant__ CUtensorMap map_g, const Dgrad2Params p) {
   extern __shared__ __align__(1024) unsigned char d2smem_raw[];
   unsigned char* base = d2smem_raw + ((1024u - (smem_u32(d2smem_raw) & 1023u)) & 1023u);
   const int V = p.V, H = p.H, C = p.C;
@@ -196,18 +212,19 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
 
   if (tid == 0) {
     for (int s = 0; s < kDStages; ++s) {
-      mbar_init_n(smem_u32(&full[s]), kDProducers);
+      mbar_init_n(smem_u32(&full[s]), SPLIT ? 1 : kDProducers);
       mbar_init_n(smem_u32(&empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init_n(smem_u32(&tfull[a]), 1);
       mbar_init_n(smem_u32(&tempty[a]), 128);
     }
-    for (int r = 0; r < kGbRingMax; ++r) mbar_init_n(smem_u32(&gbfull[r]), kTile);
+    for (int r = 0; r < kGbRingMax; ++r) mbar_init_n(smem_u32(&gbfull[r]), SPLIT ? 32 : kTile);
     mbar_init_n(smem_u32(afull), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    if (SPLIT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
   }
   if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
   umma::fence_before_thread_sync();
@@ -223,6 +240,45 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
       for (int kc = 0; kc < nk; ++kc) {
         tma_2d(smem_u32(a_res) + kc * a_chunk, &map_hi, kc * 64, jb * kJB, bar);
         tma_2d(smem_u32(a_res) + kc * a_chunk + kJB * 128, &map_lo, kc * 64, jb * kJB, bar);
+      }
+    }
+    if constexpr (SPLIT) {
+      // ---------------------------------------------- B loader: TMA boxes of the split rows
+      // lane l ferries grad_blank of rows l, l+32, l+64, l+96 of every tile, loaded one tile
+      // ahead; the ring slot is written when the tile's first chunk gets its stage (same
+      // lead over the epilogue as the register producers of the fp32 variant)
+      auto load_gb = [&](long long nb, int c, float (&v)[4]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const long long n = nb * kTile + r * 32 + lane;
+          v[r] = (nb < nblocks && n < p.N) ? ldg_stream(p.gb + (size_t)n * C + c) : 0.f;
+        }
+      };
+      long long nb = nb_lo;
+      int c = c_lo;
+      float gbv[4];
+      if (t_lo < t_hi) load_gb(nb, c, gbv);
+      uint32_t s = 0, par = 1, ringpos = 0;
+      for (long long t = t_lo; t < t_hi; ++t) {
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait_parity(smem_u32(&empty[s]), par);
+          if (lane == 0) {
+            const uint32_t bar = smem_u32(&full[s]);
+            const uint32_t dst = smem_u32(b_ring) + s * b_stage;
+            mbar_expect_tx(bar, b_stage);
+            tma_3d(dst, &map_g, kc * 64, c, (int)(nb * kTile), bar);
+            tma_3d(dst + kTile * 128, &map_g, V + kc * 64, c, (int)(nb * kTile), bar);
+          }
+          if (kc == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s_gb[ringpos * kTile + r * 32 + lane] = gbv[r];
+            mbar_arrive(smem_u32(&gbfull[ringpos]));
+            if (++ringpos == gbring) ringpos = 0;
+          }
+          if (++s == kDStages) { s = 0; par ^= 1; }
+        }
+        if (++c == C) { c = 0; ++nb; }
+        if (t + 1 < t_hi) load_gb(nb, c, gbv);
       }
     }
   } else if (warp == 1) {
@@ -260,6 +316,8 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------------ epilogue
+    constexpr int kCols = kTile;
+    constexpr int col0 = 0;
     const int quad = warp & 3;                          // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int jg = jb * kJB + quad * 32 + lane;         // hidden unit of this thread
@@ -273,7 +331,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
       const int nvalid = (int)min((long long)kTile, p.N - n0);
       const int c_end = (int)min((long long)C, c + (t_hi - t));
       // item prologue: pf[n0 + i, jg] -> TMEM, running sums := 0
-      for (int c0 = 0; c0 < kTile; c0 += 16) {
+      for (int c0 = col0; c0 < col0 + kCols; c0 += 16) {
         float v[16], z[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -311,14 +369,14 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
           }
           tmem_st8(t_acc + c0, a);
         };
-        tmem_ld8(t_d, d0); tmem_ld8(t_pf, f0); tmem_ld8(t_acc, a0);
+        tmem_ld8(t_d + col0, d0); tmem_ld8(t_pf + col0, f0); tmem_ld8(t_acc + col0, a0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTile; c0 += 16) {
+        for (int c0 = col0; c0 < col0 + kCols; c0 += 16) {
           tmem_wait_ld();
           tmem_ld8(t_d + c0 + 8, d1); tmem_ld8(t_pf + c0 + 8, f1); tmem_ld8(t_acc + c0 + 8, a1);
           compute(c0, d0, f0, a0);
           tmem_wait_ld();
-          if (c0 + 16 < kTile) {
+          if (c0 + 16 < col0 + kCols) {
             tmem_ld8(t_d + c0 + 16, d0); tmem_ld8(t_pf + c0 + 16, f0);
             tmem_ld8(t_acc + c0 + 16, a0);
           }
@@ -330,7 +388,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         atomicAdd(p.gpc + (size_t)c * H + jg, 4.f * csum);
       }
       // item epilogue: grad_proj_frame[n0 + i, jg] += running sums
-      for (int c0 = 0; c0 < kTile; c0 += 16) {
+      for (int c0 = col0; c0 < col0 + kCols; c0 += 16) {
         float a[16];
         tmem_ld16(t_acc + c0, a);
         tmem_wait_ld();
@@ -341,7 +399,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
       c = 0;
       ++nb;
     }
-  } else {
+  } else if constexpr (!SPLIT) {
     // ---------------------------------------------------------------- B producers
     // 8 lanes per joint row (one 256-bit load each: 256 contiguous bytes of grad_lexical per row
     // and K chunk), 4 rows per warp, kDPasses passes over the 128 rows of the tile.
@@ -453,8 +511,10 @@ bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, cons
 }
 
 // whi / wlo: W_vocab^T [H, V] as bf16 hi / lo (transpose_split_kernel), map_* their tensor maps
-// with box [64 x 128].
-int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const float* pc,
+// with box [64 x 128].  split != 0: gl holds rows of [V bf16 hi | V bf16 lo] and map_g is its
+// 3-D tensor map {2V, C, N} with box {64, 1, 128}; otherwise gl is fp32 and map_g is unused.
+int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
+                        const CUtensorMap& map_g, int split, const float* pc,
                         const float* pf, const float* wb, const float* gb, const float* gl,
                         int64_t N, int C, int H, int V, float* gpc, float* gpf,
                         cudaStream_t stream) {
@@ -472,9 +532,15 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo, co
   if (groups < 1) groups = 1;
   const long long nblocks = (N + kTile - 1) / kTile;
   if (groups > nblocks) groups = (int)nblocks;
-  LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  joint_dgrad2_kernel<<<groups * njb, kDThreads, smem, stream>>>(map_hi, map_lo, p);
+  if (split) {
+    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_dgrad2_kernel<true><<<groups * njb, kDSplitThreads, smem, stream>>>(map_hi, map_lo, map_g, p);
+  } else {
+    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_dgrad2_kernel<false><<<groups * njb, kDThreads, smem, stream>>>(map_hi, map_lo, map_g, p);
+  }
   LT_LAUNCHED();
   return LT_OK;
 }

@@ -1253,17 +1253,48 @@ static bool dgrad2_shape_ok(int H, int V) {
          V <= 256 && H % 128 == 0 && H <= 4096;
 }
 
+// fp32 rows -> rows of [V bf16 hi | V bf16 lo] (the form the lattice backward kernel can emit
+// directly); used by tests and by LT_JOINT_DGRAD_SPLIT_TEST=1
+__global__ void joint_split_rows_kernel(const float* __restrict__ g, unsigned char* __restrict__ out,
+                                        long long M, int V) {
+  const long long items = M * (V / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (V / 8);
+    const int v0 = (int)(i % (V / 8)) * 8;
+    float x[8];
+    ldg_stream8(g + m * V + v0, x);
+    uint4 hi, lo;
+    umma::split_pack8(x, hi, lo);
+    unsigned char* row = out + (size_t)m * V * 4;
+    *reinterpret_cast<uint4*>(row + v0 * 2) = hi;
+    *reinterpret_cast<uint4*>(row + V * 2 + v0 * 2) = lo;
+  }
+}
+int joint_split_rows_launch(const float* g, void* out, int64_t M, int V, cudaStream_t stream) {
+  joint_split_rows_kernel<<<4096, 256, 0, stream>>>(g, reinterpret_cast<unsigned char*>(out), M, V);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+// split-format grad_lexical: the fused dgrad AND the tensor-core wgrad must both apply
+bool joint_backward_split_supported(int64_t N, int C, int H, int V) {
+  return dgrad2_shape_ok(H, V) && (V == 128 || V == 256) && H % 128 == 0 && H <= 4096 &&
+         (H <= 256 || H % 256 == 0) && N >= 1 && C >= 32 && !getenv("LT_JOINT_WGRAD_SIMT") &&
+         !getenv("LT_JOINT_WGRAD_PAIR");
+}
+
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
   // bf16 hi / lo of W_vocab^T; the first-generation dgrad also needs the [M, H] buffer
   const int64_t split = joint_split_bytes(H, V) + joint_table_bytes(N, C, H);
-  if (dgrad2_shape_ok(H, V)) return split;
+  if (dgrad2_shape_ok(H, V))
+    return split + (getenv("LT_JOINT_DGRAD_SPLIT_TEST") ? N * (int64_t)C * V * 4 : 0);
   return split + N * (int64_t)C * H * 4;
 }
 
 // dgrad on tcgen05 + streaming reduction into grad_proj_ctx / grad_proj_frame.
 int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
-                          const float* gb, const float* gl, int64_t N, int C, int H, int V,
-                          float* gpc, float* gpf, void* workspace, cudaStream_t stream) {
+                          const float* gb, const float* gl, int split, int64_t N, int C, int H,
+                          int V, float* gpc, float* gpf, void* workspace, cudaStream_t stream) {
   EncodeTiledFnJ encode = joint_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
   __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(workspace);
@@ -1293,8 +1324,25 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
         return LT_ERR_CUDA;
       }
     }
-    return joint_dgrad2_launch(m_hi, m_lo, ec, ef, wb, gb, gl, N, C, H, V, gpc, gpf, stream);
+    CUtensorMap m_g = m_hi;
+    if (split) {
+      // rows of [V bf16 hi | V bf16 lo]: {2V, C, N} bf16, one [128 frames x 1 state x 64] box
+      cuuint64_t gd[3] = {(cuuint64_t)2 * V, (cuuint64_t)C, (cuuint64_t)N};
+      cuuint64_t gs[2] = {(cuuint64_t)V * 4, (cuuint64_t)C * V * 4};
+      cuuint32_t gbox[3] = {64, 1, 128};
+      cuuint32_t ge[3] = {1, 1, 1};
+      CUresult r = encode(&m_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<float*>(gl), gd,
+                          gs, gbox, ge, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (split grad_lexical) failed with %d", (int)r);
+        return LT_ERR_CUDA;
+      }
+    }
+    return joint_dgrad2_launch(m_hi, m_lo, m_g, split, ec, ef, wb, gb, gl, N, C, H, V, gpc, gpf,
+                               stream);
   }
+  if (split) { set_error("split grad_lexical needs the fused dgrad kernel"); return LT_ERR_UNSUPPORTED; }
   const int NH = H > 256 ? 256 : H;
   CUtensorMap map_hi, map_lo;
   cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)H};

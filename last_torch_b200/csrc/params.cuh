@@ -138,9 +138,12 @@ int64_t joint_split_bytes(int H, int V);
 int64_t joint_table_bytes(int64_t N, int C, int H);
 int joint_exp_tables_launch(const float* pc, const float* pf, int64_t N, int C, int H, float* ec,
                             float* ef, cudaStream_t stream);
+// split: grad_lexical rows are [V bf16 hi | V bf16 lo] (only the fused dgrad takes that form)
 int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, const float* wv,
-                          const float* gb, const float* gl, int64_t N, int C, int H, int V,
-                          float* gpc, float* gpf, void* workspace, cudaStream_t stream);
+                          const float* gb, const float* gl, int split, int64_t N, int C, int H,
+                          int V, float* gpc, float* gpf, void* workspace, cudaStream_t stream);
+bool joint_backward_split_supported(int64_t N, int C, int H, int V);
+int joint_split_rows_launch(const float* g, void* out, int64_t M, int V, cudaStream_t stream);
 // CTA-pair (cta_group::2) forward (joint_fwd2.cu)
 bool joint_fwd2_supported(int64_t N, int C, int H, int V);
 // pc / pf: the exponential tables (joint_exp_tables_launch); map_out: lexical [M, V], 32 x 32 box
@@ -152,6 +155,7 @@ int joint_fwd2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo
 bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                             const void* pf);
 int joint_dgrad2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo,
+                        const CUtensorMap_st& map_g, int split,
                         const float* pc, const float* pf, const float* wb, const float* gb,
                         const float* gl, int64_t N, int C, int H, int V, float* gpc, float* gpf,
                         cudaStream_t stream);

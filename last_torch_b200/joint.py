@@ -59,7 +59,7 @@ class _JointProjection(torch.autograd.Function):
       N.check(N.lib().lt_joint_backward(
           N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(w_vocab), N.ptr(g_blank),
           N.ptr(g_lexical), n, c, h, v, N.ptr(g_pc), N.ptr(g_pf), N.ptr(g_wb), N.ptr(g_bb),
-          N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), N.stream_ptr(dev)), 'lt_joint_backward')
+          N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), 0, N.stream_ptr(dev)), 'lt_joint_backward')
     return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv
 
 
