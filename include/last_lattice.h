@@ -52,6 +52,9 @@ extern "C" {
 #define LT_FLAG_PAIR_CTA 4u          /* fast path: two utterances per 512-thread CTA
                                         instead of two 256-thread CTAs per SM       */
 #define LT_FLAG_CLUSTER_SHIFT 8      /* bits 8..11: force cluster size (1,2,4,8) */
+#define LT_FLAG_GRAD_SPLIT 16u       /* lt_lattice_backward: write grad_lexical as "split rows"
+                                        (see lt_joint_backward); only when
+                                        lt_lattice_backward_split_supported() returns 1 */
 
 int lt_version(void);
 const char* lt_last_error(void);
@@ -270,6 +273,15 @@ int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                       float* grad_b_blank, float* grad_w_vocab,
                       float* grad_b_vocab, void* workspace,
                       int grad_lexical_format, void* stream);
+/* 1 if lt_lattice_backward can emit split rows for this lattice (TMA fast path). */
+int lt_lattice_backward_split_supported(int semiring, int vocab_size, int context_size,
+                                        int max_expansions, unsigned flags);
+/* lt_string_scatter_add for a split-row grad_lexical (grad_blank stays fp32). */
+int lt_string_scatter_add_split(int vocab_size, int num_states, const float* grad_blank_w,
+                                const float* grad_lexical_w, const int32_t* states,
+                                const int32_t* next_labels, int B, int T, int U1, float scale,
+                                const float* utt_scale, float* grad_blank, float* grad_lexical,
+                                void* stream);
 /* grad_lexical_format: 0 = fp32 [N, C, V]; 1 = "split rows": every row of V floats is replaced,
  * in the same V*4 bytes, by [V bf16 hi | V bf16 lo] with hi + lo = the value to 2^-17 -- the
  * operand form of the tensor-core kernels, which lt_lattice_backward can emit directly

@@ -21,6 +21,7 @@ REAL, LOG, MAXTROPICAL = 0, 1, 2
 FRAME_DEPENDENT = -1
 FLAG_FORCE_GENERIC = 1
 FLAG_CLUSTER_SHIFT = 8
+FLAG_GRAD_SPLIT = 16
 
 _c_int = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -45,6 +46,8 @@ SIGNATURES = {
                          _ptr, _ptr, _ptr],
     'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                               _c_float, _ptr, _ptr, _ptr, _ptr],
+    'lt_string_scatter_add_split': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                                    _c_float, _ptr, _ptr, _ptr, _ptr],
     'lt_string_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr],
     'lt_string_backward': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
@@ -60,6 +63,7 @@ SIGNATURES = {
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
     'lt_joint_backward_split_supported': [_c_i64, _c_int, _c_int, _c_int],
+    'lt_lattice_backward_split_supported': [_c_int, _c_int, _c_int, _c_int, ctypes.c_uint],
     'lt_joint_backward_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
     'lt_table_lattice_forward': [_c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr,
                                  _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
@@ -115,7 +119,7 @@ def lib():
 # current stream of the current device -- the stream the kernel is launched on).
 KERNEL_TIMER = None
 _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count',
-            'lt_joint_backward_split_supported',
+            'lt_joint_backward_split_supported', 'lt_lattice_backward_split_supported',
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 

@@ -138,6 +138,11 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
   if (lattice_fast2_supported(g, max_expansions, flags, lexical) &&
       reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
     return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
+  if (flags & LT_FLAG_GRAD_SPLIT) {
+    set_error("lt_lattice_backward: LT_FLAG_GRAD_SPLIT needs the TMA fast path "
+              "(lt_lattice_backward_split_supported)");
+    return LT_ERR_UNSUPPORTED;
+  }
   if (lattice_fast_supported(g, max_expansions, flags, lexical) &&
       reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
     return lattice_backward_fast_launch(semiring, g, p, (cudaStream_t)stream);
@@ -207,7 +212,36 @@ int lt_string_scatter_add(int vocab_size, int num_states, const float* grad_blan
                "lt_string_scatter_add: NULL pointer");
   return string_scatter_launch(vocab_size, num_states, grad_blank_w, grad_lexical_w, states,
                                next_labels, B, T, U1, scale, utt_scale, grad_blank, grad_lexical,
-                               (cudaStream_t)stream);
+                               0, (cudaStream_t)stream);
+}
+
+int lt_string_scatter_add_split(int vocab_size, int num_states, const float* grad_blank_w,
+                                const float* grad_lexical_w, const int32_t* states,
+                                const int32_t* next_labels, int B, int T, int U1, float scale,
+                                const float* utt_scale, float* grad_blank, float* grad_lexical,
+                                void* stream) {
+  LT_CHECK_ARG(vocab_size > 0 && num_states > 0 && B >= 0 && T >= 0 && U1 >= 1 && U1 <= 4096,
+               "lt_string_scatter_add_split: bad sizes V=%d C=%d B=%d T=%d U1=%d", vocab_size,
+               num_states, B, T, U1);
+  if (B == 0 || T == 0) return LT_OK;
+  LT_CHECK_ARG(grad_blank_w && grad_lexical_w && states && next_labels && grad_blank && grad_lexical,
+               "lt_string_scatter_add_split: NULL pointer");
+  return string_scatter_launch(vocab_size, num_states, grad_blank_w, grad_lexical_w, states,
+                               next_labels, B, T, U1, scale, utt_scale, grad_blank, grad_lexical,
+                               1, (cudaStream_t)stream);
+}
+
+int lt_lattice_backward_split_supported(int semiring, int vocab_size, int context_size,
+                                        int max_expansions, unsigned flags) {
+  if (semiring != LT_LOG && semiring != LT_REAL) return 0;
+  if (vocab_size < 1 || context_size < 0) return 0;
+  NGram g;
+  if (check_common("lt_lattice_backward_split_supported", semiring, vocab_size, context_size,
+                   max_expansions, 1, 1, &g))
+    return 0;
+  if (flags & LT_FLAG_PAIR_CTA) return 0;
+  return lattice_fast2_supported(g, max_expansions, flags & ~LT_FLAG_GRAD_SPLIT,
+                                 reinterpret_cast<const void*>(uintptr_t(256))) ? 1 : 0;
 }
 
 static int check_string(const char* fn, int semiring, int k, int B, int T, int U1) {

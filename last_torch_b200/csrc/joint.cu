@@ -199,7 +199,7 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                  "lt_joint_backward: split-row grad_lexical is not supported for this shape "
                  "(ask lt_joint_backward_split_supported first)");
   }
-  const float* dgrad_gl = grad_lexical;
+  const float* dgrad_gl = grad_lexical;      // what the tensor-core kernels read
   if (!split && ws_ok && getenv("LT_JOINT_DGRAD_SPLIT_TEST") &&
       joint_backward_split_supported(N, C, H, V)) {
     // test hook: run the fused dgrad on a split copy of the fp32 gradient
@@ -208,7 +208,7 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
     int rc = joint_split_rows_launch(grad_lexical, copy, N * (int64_t)C, V, (cudaStream_t)stream);
     if (rc) return rc;
     dgrad_gl = reinterpret_cast<const float*>(copy);
-    split = 2;      // dgrad only
+    split = 1;      // both tensor-core kernels read the split copy
   }
   // e^(2 proj) tables of the tensor-core kernels (second region of the workspace)
   float* ec = ws_ok ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
@@ -223,7 +223,7 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
     simt_parts = 2;
     tables = true;
   }
-  if (joint_wgrad2_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+  if (!split && joint_wgrad2_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     int rc = joint_wgrad2_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
                                  grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
                                  (cudaStream_t)stream);
@@ -234,13 +234,17 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
       int rc = joint_exp_tables_launch(proj_ctx, proj_frame, N, C, H, ec, ef, (cudaStream_t)stream);
       if (rc) return rc;
     }
-    int rc = joint_wgrad_tc_launch(ec, ef, grad_blank, grad_lexical, N, C, H, V,
+    int rc = joint_wgrad_tc_launch(ec, ef, grad_blank, dgrad_gl, split, N, C, H, V,
                                    grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
                                    (cudaStream_t)stream);
     if (rc) return rc;
     simt_parts &= ~2;
   }
   if (simt_parts == 0) return LT_OK;
+  if (split) {
+    set_error("lt_joint_backward: split-row grad_lexical reached a CUDA-core kernel");
+    return LT_ERR_UNSUPPORTED;
+  }
   return joint_backward_simt(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank, grad_lexical, N,
                              C, H, V, grad_proj_ctx, grad_proj_frame, grad_w_blank, grad_b_blank,
                              grad_w_vocab, grad_b_vocab, simt_parts, (cudaStream_t)stream);

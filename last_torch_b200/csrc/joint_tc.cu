@@ -890,7 +890,9 @@ struct JointWgradParams {
 };
 
 // AI / BI: 16-byte operand chunks per producer thread and stage (V / 128, NJ / 128)
-template <int AI, int BI>
+// SPLIT: grad_lexical rows are [V bf16 hi | V bf16 lo] (lt_lattice_backward with
+// LT_FLAG_GRAD_SPLIT): the A operand is copied, not converted.
+template <int AI, int BI, bool SPLIT>
 __global__ void __launch_bounds__(kWThreads, 1)
 joint_wgrad_tc_kernel(const JointWgradParams p) {
   extern __shared__ __align__(1024) unsigned char wsmem_raw[];
@@ -998,7 +1000,7 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
     load_pf(cn, pfa);
     load_pf(cn + 1, pfb);
     struct Pre {                       // one stage's worth of prefetched operands
-      float ax[AI][8];                 // grad_lexical
+      float ax[AI][8];                 // grad_lexical (SPLIT: words 0-3 = hi pairs, 4-7 = lo pairs)
       float bp[BI][8];                 // pc
       float gbm[BI];                   // grad_blank
     };
@@ -1012,8 +1014,19 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) q.ax[i][e] = 0.f;
         }
-        if (FULL || (ch < nchunks && mrow0 + a_k0 + i * kAStep < m_hi))
-          ldg_stream8(src + i * 2048, q.ax[i]);
+        if (FULL || (ch < nchunks && mrow0 + a_k0 + i * kAStep < m_hi)) {
+          if (SPLIT) {
+            // this thread's 8 elements: 16 bytes of the hi half, 16 bytes of the lo half
+            const unsigned char* row = reinterpret_cast<const unsigned char*>(src + i * 2048) -
+                                       a_vch * 32 + a_vch * 16;
+            const float4 h = ldg_stream4(reinterpret_cast<const float*>(row));
+            const float4 l = ldg_stream4(reinterpret_cast<const float*>(row + V * 2));
+            q.ax[i][0] = h.x; q.ax[i][1] = h.y; q.ax[i][2] = h.z; q.ax[i][3] = h.w;
+            q.ax[i][4] = l.x; q.ax[i][5] = l.y; q.ax[i][6] = l.z; q.ax[i][7] = l.w;
+          } else {
+            ldg_stream8(src + i * 2048, q.ax[i]);
+          }
+        }
       }
 #pragma unroll
       for (int i = 0; i < BI; ++i) {
@@ -1046,10 +1059,24 @@ joint_wgrad_tc_kernel(const JointWgradParams p) {
       unsigned char* b_hi = base + s * stage_bytes + 2 * op_bytes + b_off0;
 #pragma unroll
       for (int i = 0; i < AI; ++i) {                   // A = G^T chunk
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bv_acc[e] += cur.ax[i][e];
         uint4 h4, l4;
-        umma::split_pack8(cur.ax[i], h4, l4);
+        if (SPLIT) {
+          h4 = make_uint4(__float_as_uint(cur.ax[i][0]), __float_as_uint(cur.ax[i][1]),
+                          __float_as_uint(cur.ax[i][2]), __float_as_uint(cur.ax[i][3]));
+          l4 = make_uint4(__float_as_uint(cur.ax[i][4]), __float_as_uint(cur.ax[i][5]),
+                          __float_as_uint(cur.ax[i][6]), __float_as_uint(cur.ax[i][7]));
+          const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {           // value = hi + lo (bf16 -> fp32 by a shift)
+            bv_acc[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            bv_acc[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) +
+                                 __uint_as_float(lw[e] & 0xffff0000u);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bv_acc[e] += cur.ax[i][e];
+          umma::split_pack8(cur.ax[i], h4, l4);
+        }
         *reinterpret_cast<uint4*>(a_hi + i * 4096) = h4;
         *reinterpret_cast<uint4*>(a_hi + op_bytes + i * 4096) = l4;
       }
@@ -1423,8 +1450,8 @@ bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
 }
 
 int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, const float* gl,
-                          int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
-                          float* gbv, cudaStream_t stream) {
+                          int split, int64_t N, int C, int H, int V, float* gwb, float* gbb,
+                          float* gwv, float* gbv, cudaStream_t stream) {
   JointWgradParams p = {};
   p.pc = pc; p.pf = pf; p.gl = gl; p.gb = gb;
   p.M = (long long)N * C; p.C = C; p.H = H; p.V = V; p.NJ = H > 256 ? 256 : H;
@@ -1441,11 +1468,15 @@ int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, con
   p.rows_per_cta = rows;
   const size_t smem = (size_t)kWStages * 4 * 256 * kWK * 2 + 16 * 8 + 16 + 1024;
   const unsigned grid = (unsigned)(ranges * nj);
+#define LT_WGRAD1(AI, BI, SP)                                                                  \
+  do {                                                                                         \
+    LT_CUDA(cudaFuncSetAttribute(joint_wgrad_tc_kernel<AI, BI, SP>,                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    joint_wgrad_tc_kernel<AI, BI, SP><<<grid, kWThreads, smem, stream>>>(p);                   \
+  } while (0)
 #define LT_WGRAD(AI, BI)                                                                       \
   do {                                                                                         \
-    LT_CUDA(cudaFuncSetAttribute(joint_wgrad_tc_kernel<AI, BI>,                                \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    joint_wgrad_tc_kernel<AI, BI><<<grid, kWThreads, smem, stream>>>(p);                       \
+    if (split) LT_WGRAD1(AI, BI, true); else LT_WGRAD1(AI, BI, false);                         \
   } while (0)
   const int ai = V / 128, bi = p.NJ / 128;
   if (ai == 2 && bi == 2) LT_WGRAD(2, 2);
@@ -1453,6 +1484,7 @@ int joint_wgrad_tc_launch(const float* pc, const float* pf, const float* gb, con
   else if (ai == 1 && bi == 2) LT_WGRAD(1, 2);
   else LT_WGRAD(1, 1);
 #undef LT_WGRAD
+#undef LT_WGRAD1
   LT_LAUNCHED();
   return LT_OK;
 }

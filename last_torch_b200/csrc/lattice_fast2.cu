@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "fast_ptx.cuh"
 #include "params.cuh"
+#include "umma.cuh"
 
 namespace lt {
 
@@ -357,9 +358,29 @@ struct Fast2BwdParams {
   float* grad_blank;
   float* grad_lexical;
   float* beta_final;
+  int split;             // LT_FLAG_GRAD_SPLIT: rows of [V bf16 hi | V bf16 lo] instead of fp32
 };
 
-template <int SR, int V, int G>
+// Four consecutive gradients of one row.  fp32: one 16-byte store.  Split rows: the same 16
+// bytes as two 8-byte stores -- 4 bf16 "hi" at element offset c4 of the row's first half, the 4
+// bf16 residuals "lo" at the same offset of its second half (hi + lo = value to 2^-17).  It is
+// the operand form of the tensor-core joint backward (joint_dgrad2.cu loads it by TMA).
+__device__ __forceinline__ void store_grad4(float* row, int c4, int V, bool split, float4 v) {
+  if (!split) {
+    stg_stream4(row + c4, v);
+  } else {
+    uint32_t h0, l0, h1, l1;
+    umma::split_pack2(v.x, v.y, h0, l0);
+    umma::split_pack2(v.z, v.w, h1, l1);
+    unsigned char* r = reinterpret_cast<unsigned char*>(row);
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(r + c4 * 2), "r"(h0),
+                 "r"(h1) : "memory");
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(r + V * 2 + c4 * 2),
+                 "r"(l0), "r"(l1) : "memory");
+  }
+}
+
+template <int SR, int V, int G, bool SPLIT>
 __global__ void __launch_bounds__(kGroupThreads * G, G == 1 ? 2 : 1)
 lattice_backward_fast2(const Fast2BwdParams p) {
   using S = Sr<SR>;
@@ -400,6 +421,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   const float logz2 = logz * kLog2e;            // Log: everything on chip is in log2 units
   const float gscale = (active && p.grad_dist) ? p.grad_dist[b] : 1.f;
   const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
+  constexpr bool split = SPLIT;      // compile-time: the fp32 kernel is unchanged
   const uint32_t stage_tx = last_rank ? kStageBytes : kSlabBytes;
 
   if (gt == 0) {
@@ -508,7 +530,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           e.x = ex2(x[i].x - ms); e.y = ex2(x[i].y - ms);
           e.z = ex2(x[i].z - ms); e.w = ex2(x[i].w - ms);
           s += (e.x + e.y) + (e.z + e.w);
-          stg_stream4(grow + (sl + 8 * i) * 4, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          store_grad4(grow, (sl + 8 * i) * 4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -522,7 +544,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           const int c4 = (sl + 8 * i) * 4;
           const float4 bn = *reinterpret_cast<const float4*>(bnext + c4);
           s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-          stg_stream4(grow + c4, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
+          store_grad4(grow, c4, V, split, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -562,7 +584,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           e.x = ex2(arc<SR>(w.x, bn.x) - ms); e.y = ex2(arc<SR>(w.y, bn.y) - ms);
           e.z = ex2(arc<SR>(w.z, bn.z) - ms); e.w = ex2(arc<SR>(w.w, bn.w) - ms);
           s += (e.x + e.y) + (e.z + e.w);
-          stg_stream4(grow + c4, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          store_grad4(grow, c4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         rowsum = ms + __log2f(s);
@@ -573,7 +595,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           const float4 w = *reinterpret_cast<const float4*>(trow + c4);
           const float4 bn = *reinterpret_cast<const float4*>(bnext + c4);
           s += (w.x * bn.x + w.y * bn.y) + (w.z * bn.z + w.w * bn.w);
-          stg_stream4(grow + c4, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
+          store_grad4(grow, c4, V, split, make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w));
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         rowsum = s;
@@ -723,13 +745,18 @@ int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams&
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alphas = base.alphas; p.dist = base.dist; p.grad_dist = base.grad_dist;
   p.grad_blank = base.grad_blank; p.grad_lexical = base.grad_lexical; p.beta_final = base.beta_final;
+  p.split = (flags & LT_FLAG_GRAD_SPLIT) ? 1 : 0;
+  if (p.split && G != 1) { set_error("LT_FLAG_GRAD_SPLIT excludes LT_FLAG_PAIR_CTA"); return LT_ERR_UNSUPPORTED; }
   const int grid = ((base.B + G - 1) / G) * CL;
   const int threads = kGroupThreads * G;
-#define LT_BWD2V(SR, VV)                                                                           \
-  return G == 1 ? launch_fast2(lattice_backward_fast2<SR, VV, 1>, grid, threads, smem, CL, stream, \
-                               p)                                                                  \
-                : launch_fast2(lattice_backward_fast2<SR, VV, 2>, grid, threads, smem, CL, stream, \
-                               p);
+#define LT_BWD2V(SR, VV)                                                                        \
+  if (p.split)                                                                                  \
+    return launch_fast2(lattice_backward_fast2<SR, VV, 1, true>, grid, threads, smem, CL,       \
+                        stream, p);                                                             \
+  return G == 1 ? launch_fast2(lattice_backward_fast2<SR, VV, 1, false>, grid, threads, smem,   \
+                               CL, stream, p)                                                   \
+                : launch_fast2(lattice_backward_fast2<SR, VV, 2, false>, grid, threads, smem,   \
+                               CL, stream, p);
 #define LT_BWD2(SR)                  \
   switch (V) {                       \
     case 64: LT_BWD2V(SR, 64)        \

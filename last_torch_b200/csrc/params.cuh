@@ -110,7 +110,7 @@ int string_gather_launch(int V, int C, const float* blank, const float* lexical,
 int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
                           float scale, const float* utt_scale, float* gblank, float* glex,
-                          cudaStream_t stream);
+                          int split, cudaStream_t stream);
 int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
                        int32_t* next_labels, cudaStream_t stream);
 int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);
@@ -168,9 +168,10 @@ int joint_wgrad2_launch(const float* pc, const float* pf, const float* gb, const
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 // ec / ef: the exponential tables (joint_exp_tables_launch), not the projections
+// split: grad_lexical rows are [V bf16 hi | V bf16 lo]
 int joint_wgrad_tc_launch(const float* ec, const float* ef, const float* gb, const float* gl,
-                          int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
-                          float* gbv, cudaStream_t stream);
+                          int split, int64_t N, int C, int H, int V, float* gwb, float* gbb,
+                          float* gwv, float* gbv, cudaStream_t stream);
 int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);
 
 }  // namespace lt

@@ -13,6 +13,7 @@
 // chain state; alpha/beta live in shared memory for all T frames.
 #include "common.cuh"
 #include "params.cuh"
+#include "umma.cuh"
 
 namespace lt {
 
@@ -53,6 +54,55 @@ __global__ void string_scatter_kernel(int V, int C, const float* __restrict__ gb
     const float a = gbw[bt * U1 + u], c = glw[bt * U1 + u];
     if (a != 0.f) atomicAdd(bl + s, scale * a);
     if (c != 0.f) atomicAdd(lx + (size_t)s * V + y, scale * c);
+  }
+}
+
+// The same for a split-row grad_lexical (rows of [V bf16 hi | V bf16 lo], see
+// lt_joint_backward): there is no atomic on a (hi, lo) pair that lives in two places, so the
+// block first merges the label positions that hit the same arc -- position u owns its target if
+// no earlier position has it, and adds the contributions of all later duplicates -- and every
+// owner then does ONE plain read-modify-write (value = hi + lo, re-split).  Blocks handle
+// different frames, owners different arcs: no two threads touch the same 16-bit word.
+__global__ void string_scatter_split_kernel(int V, int C, const float* __restrict__ gbw,
+                                            const float* __restrict__ glw,
+                                            const int32_t* __restrict__ states,
+                                            const int32_t* __restrict__ labels, int T, int U1,
+                                            float scale, const float* __restrict__ utt_scale,
+                                            float* __restrict__ gblank,
+                                            unsigned char* __restrict__ glex) {
+  extern __shared__ int32_t s_key[];               // [U1] arc index s * V + y
+  float* s_val = reinterpret_cast<float*>(s_key + U1);
+  const size_t bt = blockIdx.x;
+  const int b = (int)(bt / T);
+  if (utt_scale) scale *= utt_scale[b];
+  if (scale == 0.f) return;
+  float* bl = gblank + bt * C;
+  unsigned char* lx = glex + bt * (size_t)C * V * 4;
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+    const int s = states[(size_t)b * U1 + u];
+    const int y = labels[(size_t)b * U1 + u] - 1;
+    s_key[u] = s * V + y;
+    s_val[u] = scale * glw[bt * U1 + u];
+    const float a = gbw[bt * U1 + u];
+    if (a != 0.f) atomicAdd(bl + s, scale * a);
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+    const int key = s_key[u];
+    bool owner = true;
+    for (int w = 0; w < u; ++w) owner = owner && s_key[w] != key;
+    if (!owner) continue;
+    float add = s_val[u];
+    for (int w = u + 1; w < U1; ++w) add += s_key[w] == key ? s_val[w] : 0.f;
+    if (add == 0.f) continue;
+    const int s = key / V, y = key - s * V;
+    unsigned short* hi = reinterpret_cast<unsigned short*>(lx + (size_t)s * V * 4) + y;
+    unsigned short* lo = hi + V;
+    const float v = __uint_as_float((uint32_t)*hi << 16) + __uint_as_float((uint32_t)*lo << 16) + add;
+    __nv_bfloat16 h, l;
+    umma::split_bf16(v, h, l);
+    *hi = __bfloat16_as_ushort(h);
+    *lo = __bfloat16_as_ushort(l);
   }
 }
 
@@ -266,8 +316,16 @@ int string_gather_launch(int V, int C, const float* blank, const float* lexical,
 int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
                           float scale, const float* utt_scale, float* gblank, float* glex,
-                          cudaStream_t stream) {
+                          int split, cudaStream_t stream) {
   if ((size_t)B * T == 0 || U1 == 0) return LT_OK;
+  if (split) {
+    string_scatter_split_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256),
+                                  (size_t)U1 * 8, stream>>>(
+        V, C, gbw, glw, states, labels, T, U1, scale, utt_scale, gblank,
+        reinterpret_cast<unsigned char*>(glex));
+    LT_LAUNCHED();
+    return LT_OK;
+  }
   string_scatter_kernel<<<(unsigned)((size_t)B * T), min(block_for(U1), 256), 0, stream>>>(
       V, C, gbw, glw, states, labels, T, U1, scale, utt_scale, gblank, glex);
   LT_LAUNCHED();

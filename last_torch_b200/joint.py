@@ -16,7 +16,7 @@ class _JointProjection(torch.autograd.Function):
   """(blank [N,C], lexical [N,C,V]) from proj_ctx [C,H], proj_frame [N,H]."""
 
   @staticmethod
-  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab):
+  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, split_grad=None):
     proj_ctx = N.require_cuda(proj_ctx, 'proj_ctx')
     proj_frame = N.require_cuda(proj_frame, 'proj_frame')
     w_blank = N.require_cuda(w_blank.reshape(-1), 'w_blank')
@@ -36,6 +36,9 @@ class _JointProjection(torch.autograd.Function):
           N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.ptr(workspace),
           N.stream_ptr(dev)), 'lt_joint_forward')
     ctx.save_for_backward(proj_ctx, proj_frame, w_blank, w_vocab)
+    ctx.split_grad = split_grad
+    if split_grad is not None:     # may the consumer hand back split-row gradients (ops.SplitGrad)?
+      split_grad.joint_ok = bool(N.lib().lt_joint_backward_split_supported(n, c, h, v))
     return blank, lexical
 
   @staticmethod
@@ -47,6 +50,10 @@ class _JointProjection(torch.autograd.Function):
     dev = proj_frame.device
     g_blank = N.require_cuda(g_blank, 'grad_blank')
     g_lexical = N.require_cuda(g_lexical, 'grad_lexical')
+    sg = ctx.split_grad
+    fmt = 1 if (sg is not None and sg.emitted) else 0      # split rows from the lattice backward
+    if sg is not None:
+      sg.emitted = False
     g_pc = torch.zeros_like(proj_ctx)
     g_pf = torch.zeros_like(proj_frame)
     g_wb = torch.zeros_like(w_blank)
@@ -59,11 +66,11 @@ class _JointProjection(torch.autograd.Function):
       N.check(N.lib().lt_joint_backward(
           N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(w_vocab), N.ptr(g_blank),
           N.ptr(g_lexical), n, c, h, v, N.ptr(g_pc), N.ptr(g_pf), N.ptr(g_wb), N.ptr(g_bb),
-          N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), 0, N.stream_ptr(dev)), 'lt_joint_backward')
-    return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv
+          N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), fmt, N.stream_ptr(dev)), 'lt_joint_backward')
+    return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv, None
 
 
-def joint_all_frames(fn, cache, frames):
+def joint_all_frames(fn, cache, frames, split_grad=None):
   """fn: weight_fns.JointWeightFn; cache [C,E]; frames [batch..., T, D]."""
   batch_shape = frames.shape[:-1]
   proj_ctx = fn.context_projection(cache)                                   # [C,H]
@@ -71,6 +78,6 @@ def joint_all_frames(fn, cache, frames):
   blank, lexical = _JointProjection.apply(
       proj_ctx, proj_frame, fn.joint_projection_to_blank.weight,
       fn.joint_projection_to_blank.bias.reshape(()), fn.joint_projection_to_vocab.weight,
-      fn.joint_projection_to_vocab.bias)
+      fn.joint_projection_to_vocab.bias, split_grad)
   c, v = proj_ctx.shape[0], fn.vocab_size
   return blank.reshape(*batch_shape, c), lexical.reshape(*batch_shape, c, v)

@@ -94,10 +94,13 @@ class RecognitionLattice(nn.Module, Generic[T]):
       raise ValueError('num_labels and num_frames have different batch_dims: '
                        f'{tuple(num_labels.shape)} vs {batch_dims}')
 
-  def _arc_weights(self, cache, frames, batch_dims):
+  def _arc_weights(self, cache, frames, batch_dims, split_grad=None):
     """Dense arc weights of all frames, flattened to one batch axis:
     blank [B,T,C], lexical [B,T,C,V] (fp32, contiguous, CUDA)."""
-    blank, lexical = self.weight_fn.all_frames(cache, frames)
+    if split_grad is not None:
+      blank, lexical = self.weight_fn.all_frames(cache, frames, split_grad=split_grad)
+    else:
+      blank, lexical = self.weight_fn.all_frames(cache, frames)
     c, v = self.context.shape()
     t = frames.shape[-2]
     blank = blank.reshape(-1, t, c)
@@ -139,7 +142,11 @@ class RecognitionLattice(nn.Module, Generic[T]):
                                    labels=labels, num_labels=num_labels,
                                    semiring=semirings.Log)
     v, n, k = self._geometry()
-    blank, lexical = self._arc_weights(cache, frames, batch_dims)
+    # JointWeightFn + FullNGram: the lattice backward may hand its posteriors to the projection's
+    # backward in the tensor cores' operand form (ops.SplitGrad); `lexical` stays in this method
+    split_grad = (ops.SplitGrad() if type(self.weight_fn) is weight_fns.JointWeightFn
+                  and not self._is_table() else None)
+    blank, lexical = self._arc_weights(cache, frames, batch_dims, split_grad)
     dev = blank.device
     states, next_labels = self._string_indices(labels, dev)
     if self._is_table():
@@ -150,7 +157,7 @@ class RecognitionLattice(nn.Module, Generic[T]):
       return (log_z - num).reshape(batch_dims)
     loss, _, _, _ = ops.LatticeLoss.apply(
         blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
-        ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags)
+        ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags, split_grad)
     return loss.reshape(batch_dims)
 
   def shortest_path(self, frames: torch.Tensor, num_frames: torch.Tensor,

@@ -6,6 +6,8 @@ arithmetic step below is a hand-written sm_100a kernel.
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native as N
@@ -424,12 +426,28 @@ def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dis
   return gbw, glw
 
 
-def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scale=None):
+class SplitGrad:
+  """Handshake between JointWeightFn's projection and the lattice loss inside
+  RecognitionLattice.forward: when both sides can (`joint_ok`, set by the projection's forward;
+  lt_lattice_backward_split_supported), the lattice backward kernel writes grad_lexical as
+  "split rows" -- [V bf16 hi | V bf16 lo] in the V*4 bytes of every row, the operand form of the
+  tensor-core joint backward (include/last_lattice.h, lt_joint_backward) -- and sets `emitted`,
+  which the projection's backward reads.  The buffer travels through autograd as an opaque
+  float32 tensor of the right shape; `lexical` has no other consumer on that path."""
+
+  def __init__(self):
+    self.joint_ok = False
+    self.emitted = False
+
+
+def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scale=None,
+                    split=False):
   """grad_dense[b, t, states[u], next_labels[u] - 1] += scale * utt_scale[b] * grad_w[b, t, u]."""
   B, T, U1 = gbw.shape
   dev = gbw.device
+  fn = N.lib().lt_string_scatter_add_split if split else N.lib().lt_string_scatter_add
   with torch.cuda.device(dev):
-    N.check(N.lib().lt_string_scatter_add(
+    N.check(fn(
         V, C, N.ptr(gbw), N.ptr(glw), N.ptr(states), N.ptr(next_labels), B, T, U1, float(scale),
         N.ptr(utt_scale), N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
 
@@ -475,9 +493,11 @@ class LatticeLoss(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags):
+  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags,
+              split_grad=None):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
+    ctx.split_grad = split_grad
     need_grad = any(ctx.needs_input_grad[:2])
     dev = blank.device
     cur = torch.cuda.current_stream(dev)
@@ -522,10 +542,19 @@ class LatticeLoss(torch.autograd.Function):
     g_numr = N.require_cuda(g_numr, 'grad').contiguous()
     gb = torch.empty_like(blank)
     gl = torch.empty_like(lexical)
+    sg = ctx.split_grad
+    split = bool(sg is not None and sg.joint_ok and ctx.needs_input_grad[1] and
+                 not os.environ.get('LT_NO_SPLIT_GRAD') and
+                 N.lib().lt_lattice_backward_split_supported(N.LOG, V, n, k, flags))
+    if split:
+      flags |= N.FLAG_GRAD_SPLIT
     with torch.cuda.device(dev):
       N.check(N.lib().lt_lattice_backward(
           N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
           N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None, flags,
           N.stream_ptr(dev)), 'lt_lattice_backward')
-    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr)
-    return gb, gl, None, None, None, None, None, None, None, None
+    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr,
+                    split=split)
+    if sg is not None:
+      sg.emitted = split
+    return gb, gl, None, None, None, None, None, None, None, None, None

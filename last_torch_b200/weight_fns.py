@@ -186,10 +186,10 @@ class JointWeightFn(WeightFn[torch.Tensor]):
     lexical = self.joint_projection_to_vocab(joint)
     return blank, lexical
 
-  def all_frames(self, cache, frames):
+  def all_frames(self, cache, frames, split_grad=None):
     self._ensure(cache, frames)
     from . import joint as joint_ops   # CUDA (tcgen05) vocabulary projection
-    return joint_ops.joint_all_frames(self, cache, frames)
+    return joint_ops.joint_all_frames(self, cache, frames, split_grad)
 
 
 class SharedEmbCacher(WeightFnCacher[torch.Tensor]):

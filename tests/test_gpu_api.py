@@ -259,6 +259,57 @@ def test_call_joint_weight_fn():
   assert all(float(g.abs().sum()) > 0 for g in grads)
 
 
+@pytest.mark.parametrize('vocab,hidden,batch,frames', [(128, 128, 3, 40), (256, 256, 2, 70)])
+def test_joint_lattice_split_row_gradients(vocab, hidden, batch, frames):
+  """RecognitionLattice.forward with JointWeightFn: the lattice backward kernel hands its arc
+  posteriors to the tensor-core joint backward as split rows ([V bf16 hi | V bf16 lo], read by
+  TMA; ops.SplitGrad).  Same parameter gradients as the fp32 hand-over (LT_NO_SPLIT_GRAD=1),
+  with ragged utterances (zero rows on padding frames) and label strings with repeated bigrams
+  (several numerator positions land on one arc of the split buffer)."""
+  import os
+  lt = _lt()
+  from last_torch_b200 import ops
+  torch.manual_seed(vocab + batch)
+  context = lt.contexts.FullNGram(vocab_size=vocab, context_size=1)
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=hidden, device='cuda'))
+  x = torch.randn([batch, frames, 16], device='cuda')
+  num_frames = torch.tensor([frames, frames - 7, frames // 2][:batch], device='cuda')
+  labels = torch.randint(1, vocab + 1, [batch, 12], device='cuda')
+  labels[:, 4:8] = labels[:, 0:4]            # repeated bigrams
+  labels[0, 8:] = labels[0, 8]               # ... and a run of one label
+  num_labels = torch.tensor([12, 9, 5][:batch], device='cuda')
+  weights = torch.rand([batch], device='cuda') + 0.5
+
+  def run(no_split):
+    if no_split:
+      os.environ['LT_NO_SPLIT_GRAD'] = '1'
+    try:
+      lattice.zero_grad()
+      loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
+      (loss * weights).sum().backward()
+      return loss.detach(), [p.grad.clone() for p in lattice.parameters()]
+    finally:
+      os.environ.pop('LT_NO_SPLIT_GRAD', None)
+
+  loss_s, g_s = run(False)
+  loss_f, g_f = run(True)
+  npt.assert_array_equal(loss_s.cpu(), loss_f.cpu())
+  assert len(g_s) == 7
+  for a, b in zip(g_s, g_f):
+    scale = float(b.abs().max()) + 1e-12
+    assert float((a - b).abs().max()) / scale < 2e-5, (tuple(b.shape), float((a - b).abs().max()) / scale)
+  # the split path really ran: the handshake object reports it for this shape
+  from last_torch_b200 import _native as N
+  c = vocab + 1
+  assert N.lib().lt_joint_backward_split_supported(batch * frames, c, hidden, vocab) == 1
+  assert N.lib().lt_lattice_backward_split_supported(N.LOG, vocab, 1, -1, 0) == 1
+
+
 def test_shortest_path_api():
   # tests/lattices_test.py:91-127 and :151-176
   lt = _lt()
