@@ -81,6 +81,70 @@ __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, int
       "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// ---- CTA pair (cta_group::2) plumbing, as in joint_fwd2.cu: rank 0 of the cluster is the leader
+// and the only MMA issuer; "leader" barriers are addressed through the shared::cluster window
+// with the peer bit (bit 24) cleared.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void mbar_wait_parity_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTDC_WAIT%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTDC_DONE%=;\n"
+      "bra LTDC_WAIT%=;\n"
+      "LTDC_DONE%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::
+                   "r"(bar & kPeerBitMask), "r"(bytes) : "memory");
+}
+// 2-SM TMA loads: data lands in THIS CTA's shared memory, the bytes complete on the leader's barrier
+__device__ __forceinline__ void tma_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                           uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1),
+      "r"(bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_3d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                           int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+      "r"(bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::
+                   "r"(smem_result_addr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
 // tanh(x) = 1 - 2 / (1 + e^(2x)): two MUFU ops; absolute error ~1e-7
 __device__ __forceinline__ float tanh_fast(float x) {
   float e, r;
@@ -150,6 +214,7 @@ constexpr int kDSplitThreads = 6 * 32;    // split-row variant: TMA, MMA, 4 epil
                                           // slower: 5.15 vs 4.92 ms)
 constexpr int kDPasses = 128 / (kDProdWarps * 4);   // row passes per producer thread and chunk
 constexpr int kDStages = 3;
+constexpr int kDPairStages = 5;          // CTA-pair variant: 16 KB stages (64 rows per CTA)
 constexpr int kTile = 128;              // joint rows per tile = frames per work item
 constexpr int kJB = 128;                // hidden units per CTA
 // grad_blank ring (tiles): the producers run kDStages chunks ahead of the MMAs, which are at most
@@ -175,7 +240,13 @@ struct Dgrad2Params {
 // the lattice backward kernel, see lt_lattice_backward / LT_FLAG_GRAD_SPLIT).  The B operand is
 // then a plain TMA load -- one [128 frames x 1 state x 64] box of map_g per half -- and the 16
 // producer warps disappear: warp 0 issues the loads and ferries the grad_blank slices.
-template <bool SPLIT>
+// PAIR (split rows only): a cluster of two CTAs shares every tile of 128 joint rows.  CTA r
+// owns hidden block 2 * jp + r (its own resident A, accumulators, epilogue) and loads HALF of
+// the tile's rows (64); one tcgen05.mma.cta_group::2 with M = 256 multiplies both hidden blocks
+// by the whole tile, each SM reading only its half of B from shared memory.  At N = 128 the
+// single-CTA kernel's operand reads alone are one 128-byte wavefront per clock; the pair reads
+// 96 bytes per clock and writes half the TMA bytes.
+template <bool SPLIT, bool PAIR>
 __global__ void __launch_bounds__(SPLIT ? kDSplitThreads : kDThreads, 1)
 joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo,
@@ -185,24 +256,31 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int V = p.V, H = p.H, C = p.C;
   const int nk = V / 64;                              // K chunks
   const uint32_t a_chunk = 2 * kJB * 128;             // hi | lo of one [128 j x 64 v] chunk
-  const uint32_t b_stage = 2 * kTile * 128;           // hi | lo of one [128 rows x 64 v] chunk
+  static_assert(!PAIR || SPLIT, "the CTA-pair variant reads split rows");
+  constexpr int kBRows = PAIR ? kTile / 2 : kTile;    // tile rows in this CTA's shared memory
+  constexpr int kStages = PAIR ? kDPairStages : kDStages;
+  const uint32_t b_stage = 2 * kBRows * 128;          // hi | lo of one [rows x 64 v] chunk
   unsigned char* a_res = base;                        // nk chunks, resident
   unsigned char* b_ring = a_res + (size_t)nk * a_chunk;
-  const uint32_t gbring = gb_ring_slots(V);
-  float* s_gb = reinterpret_cast<float*>(b_ring + kDStages * b_stage);      // [gbring][128]
+  const uint32_t gbring = PAIR ? kGbRingMax : gb_ring_slots(V);
+  float* s_gb = reinterpret_cast<float*>(b_ring + kStages * b_stage);       // [gbring][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + gbring * kTile);
   uint64_t* full = bars;                    // [stages]  producers -> MMA
-  uint64_t* empty = full + kDStages;        // [stages]  MMA (commit) -> producers
-  uint64_t* tfull = empty + kDStages;       // [2]       MMA (commit) -> epilogue
+  uint64_t* empty = full + kStages;         // [stages]  MMA (commit) -> producers
+  uint64_t* tfull = empty + kStages;        // [2]       MMA (commit) -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
   uint64_t* gbfull = tempty + 2;            // [gbring]  producers -> epilogue (grad_blank slice)
   uint64_t* afull = gbfull + kGbRingMax;       // [1]       TMA -> MMA (resident A)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;   // 0 = leader
   const int njb = H / kJB;
-  const int jb = blockIdx.x % njb;
-  const int group = blockIdx.x / njb, ngroups = gridDim.x / njb;
+  // PAIR: cluster id = blockIdx.x / 2 enumerates (group, pair of hidden blocks)
+  const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int nunits = PAIR ? njb / 2 : njb;
+  const int jb = PAIR ? (unit % nunits) * 2 + (int)rank : unit % nunits;
+  const int group = unit / nunits, ngroups = (PAIR ? gridDim.x >> 1 : gridDim.x) / nunits;
   const long long nblocks = (p.N + kTile - 1) / kTile;
   // this CTA's contiguous range of the (frame block, c) tile sequence
   const long long ttot = nblocks * C;
@@ -211,24 +289,29 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   const int c_lo = (int)(t_lo - nb_lo * C);
 
   if (tid == 0) {
-    for (int s = 0; s < kDStages; ++s) {
-      mbar_init_n(smem_u32(&full[s]), SPLIT ? 1 : kDProducers);
+    // PAIR: full / tempty / afull are the LEADER's (arrivals from both CTAs)
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init_n(smem_u32(&full[s]), PAIR ? 2 : (SPLIT ? 1 : kDProducers));
       mbar_init_n(smem_u32(&empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init_n(smem_u32(&tfull[a]), 1);
-      mbar_init_n(smem_u32(&tempty[a]), 128);
+      mbar_init_n(smem_u32(&tempty[a]), PAIR ? 8 : 128);      // PAIR: one arrival per warp
     }
     for (int r = 0; r < kGbRingMax; ++r) mbar_init_n(smem_u32(&gbfull[r]), SPLIT ? 32 : kTile);
-    mbar_init_n(smem_u32(afull), 1);
+    mbar_init_n(smem_u32(afull), PAIR ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
     if (SPLIT) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
   }
-  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(smem_u32(tmem_slot), 512);
+    else umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  }
   umma::fence_before_thread_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   umma::fence_after_thread_sync();
   const uint32_t tmem = *tmem_slot;
 
@@ -236,10 +319,17 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     // ------------------------------------------------ resident A: W_vocab^T block, once
     if (lane == 0 && t_lo < t_hi) {
       const uint32_t bar = smem_u32(afull);
-      mbar_expect_tx(bar, (uint32_t)nk * a_chunk);
+      if (PAIR) mbar_expect_tx_leader(bar, (uint32_t)nk * a_chunk);
+      else mbar_expect_tx(bar, (uint32_t)nk * a_chunk);
       for (int kc = 0; kc < nk; ++kc) {
-        tma_2d(smem_u32(a_res) + kc * a_chunk, &map_hi, kc * 64, jb * kJB, bar);
-        tma_2d(smem_u32(a_res) + kc * a_chunk + kJB * 128, &map_lo, kc * 64, jb * kJB, bar);
+        const uint32_t dst = smem_u32(a_res) + kc * a_chunk;
+        if (PAIR) {
+          tma_2d_2sm(dst, &map_hi, kc * 64, jb * kJB, bar);
+          tma_2d_2sm(dst + kJB * 128, &map_lo, kc * 64, jb * kJB, bar);
+        } else {
+          tma_2d(dst, &map_hi, kc * 64, jb * kJB, bar);
+          tma_2d(dst + kJB * 128, &map_lo, kc * 64, jb * kJB, bar);
+        }
       }
     }
     if constexpr (SPLIT) {
@@ -265,9 +355,16 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
           if (lane == 0) {
             const uint32_t bar = smem_u32(&full[s]);
             const uint32_t dst = smem_u32(b_ring) + s * b_stage;
-            mbar_expect_tx(bar, b_stage);
-            tma_3d(dst, &map_g, kc * 64, c, (int)(nb * kTile), bar);
-            tma_3d(dst + kTile * 128, &map_g, V + kc * 64, c, (int)(nb * kTile), bar);
+            if (PAIR) {      // this CTA's 64 rows of the tile, counted on the leader's barrier
+              const int n0 = (int)(nb * kTile) + (int)rank * kBRows;
+              mbar_expect_tx_leader(bar, b_stage);
+              tma_3d_2sm(dst, &map_g, kc * 64, c, n0, bar);
+              tma_3d_2sm(dst + kBRows * 128, &map_g, V + kc * 64, c, n0, bar);
+            } else {
+              mbar_expect_tx(bar, b_stage);
+              tma_3d(dst, &map_g, kc * 64, c, (int)(nb * kTile), bar);
+              tma_3d(dst + kTile * 128, &map_g, V + kc * 64, c, (int)(nb * kTile), bar);
+            }
           }
           if (kc == 0) {
 #pragma unroll
@@ -275,7 +372,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
             mbar_arrive(smem_u32(&gbfull[ringpos]));
             if (++ringpos == gbring) ringpos = 0;
           }
-          if (++s == kDStages) { s = 0; par ^= 1; }
+          if (++s == kStages) { s = 0; par ^= 1; }
         }
         if (++c == C) { c = 0; ++nb; }
         if (t + 1 < t_hi) load_gb(nb, c, gbv);
@@ -283,19 +380,22 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0 && t_lo < t_hi) {
-      const uint32_t idesc = umma::make_idesc_bf16(kJB, kTile);
-      mbar_wait_parity(smem_u32(afull), 0);
+    if (lane == 0 && t_lo < t_hi && rank == 0) {
+      const uint32_t idesc = umma::make_idesc_bf16(PAIR ? 2 * kJB : kJB, kTile);
+      auto wait = [&](uint32_t bar, uint32_t parity) {     // PAIR: arrivals come from both CTAs
+        if (PAIR) mbar_wait_parity_cluster(bar, parity); else mbar_wait_parity(bar, parity);
+      };
+      wait(smem_u32(afull), 0);
       uint32_t g = 0;
       const uint32_t ntiles = (uint32_t)(t_hi - t_lo);
       for (uint32_t it = 0; it < ntiles; ++it) {
         const uint32_t acc = it & 1;
-        mbar_wait_parity(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
+        wait(smem_u32(&tempty[acc]), ((it >> 1) & 1) ^ 1);
         umma::fence_after_thread_sync();
         const uint32_t d = tmem + acc * kTile;
         for (int kc = 0; kc < nk; ++kc, ++g) {
-          const uint32_t s = g % kDStages;
-          mbar_wait_parity(smem_u32(&full[s]), (g / kDStages) & 1);
+          const uint32_t s = g % kStages;
+          wait(smem_u32(&full[s]), (g / kStages) & 1);
           umma::fence_after_thread_sync();
           const uint32_t sa = smem_u32(a_res) + kc * a_chunk;
           const uint32_t sb = smem_u32(b_ring) + s * b_stage;
@@ -304,14 +404,20 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
             const uint64_t dah = umma::make_smem_desc_sw128(sa + k * 32);
             const uint64_t dal = umma::make_smem_desc_sw128(sa + kJB * 128 + k * 32);
             const uint64_t dbh = umma::make_smem_desc_sw128(sb + k * 32);
-            const uint64_t dbl = umma::make_smem_desc_sw128(sb + kTile * 128 + k * 32);
-            umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
-            umma::mma_bf16(d, dah, dbl, idesc, 1);
-            umma::mma_bf16(d, dal, dbh, idesc, 1);
+            const uint64_t dbl = umma::make_smem_desc_sw128(sb + kBRows * 128 + k * 32);
+            if (PAIR) {
+              mma_bf16_2cta(d, dah, dbh, idesc, (kc | k) > 0);
+              mma_bf16_2cta(d, dah, dbl, idesc, 1);
+              mma_bf16_2cta(d, dal, dbh, idesc, 1);
+            } else {
+              umma::mma_bf16(d, dah, dbh, idesc, (kc | k) > 0);
+              umma::mma_bf16(d, dah, dbl, idesc, 1);
+              umma::mma_bf16(d, dal, dbh, idesc, 1);
+            }
           }
-          umma::commit(smem_u32(&empty[s]));
+          if (PAIR) commit_2cta(smem_u32(&empty[s])); else umma::commit(smem_u32(&empty[s]));
         }
-        umma::commit(smem_u32(&tfull[acc]));
+        if (PAIR) commit_2cta(smem_u32(&tfull[acc])); else umma::commit(smem_u32(&tfull[acc]));
       }
     }
   } else if (warp < 6) {
@@ -384,7 +490,12 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         }
         tmem_wait_st();
         umma::fence_before_thread_sync();
-        mbar_arrive(smem_u32(&tempty[acc]));
+        if (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(smem_u32(&tempty[acc]));
+        } else {
+          mbar_arrive(smem_u32(&tempty[acc]));
+        }
         atomicAdd(p.gpc + (size_t)c * H + jg, 4.f * csum);
       }
       // item epilogue: grad_proj_frame[n0 + i, jg] += running sums
@@ -495,10 +606,18 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
   umma::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2cta(tmem, 512); else umma::tmem_dealloc(tmem, 512);
+  }
 }
 
 }  // namespace
+
+// CTA-pair variant of the split-row kernel: pairs of hidden blocks (opt-in while it is measured)
+bool joint_dgrad2_pair(int H, int V) {
+  return getenv("LT_JOINT_DGRAD_PAIR") != nullptr && H % (2 * kJB) == 0 && V % 64 == 0;
+}
 
 bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                             const void* pf) {
@@ -522,8 +641,12 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
   p.N = N; p.C = C; p.H = H; p.V = V; p.gpc = gpc; p.gpf = gpf;
   const int nk = V / 64;
-  const size_t smem = (size_t)nk * 2 * kJB * 128 + (size_t)kDStages * 2 * kTile * 128 +
-                      sizeof(float) * gb_ring_slots(V) * kTile + 8 * 32 + 16 + 1024;
+  const bool pair = split && joint_dgrad2_pair(H, V);
+  const size_t smem = (size_t)nk * 2 * kJB * 128 +
+                      (pair ? (size_t)kDPairStages * kTile * 128
+                            : (size_t)kDStages * 2 * kTile * 128) +
+                      sizeof(float) * (pair ? kGbRingMax : gb_ring_slots(V)) * kTile + 8 * 32 +
+                      16 + 1024;
   int dev = 0, sms = 0;
   LT_CUDA(cudaGetDevice(&dev));
   LT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -532,14 +655,32 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
   if (groups < 1) groups = 1;
   const long long nblocks = (N + kTile - 1) / kTile;
   if (groups > nblocks) groups = (int)nblocks;
-  if (split) {
-    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<true>,
+  if (pair) {
+    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<true, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_dgrad2_kernel<true><<<groups * njb, kDSplitThreads, smem, stream>>>(map_hi, map_lo, map_g, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * njb));      // clusters of two CTAs = hidden-block pairs
+    cfg.blockDim = dim3(kDSplitThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LT_CUDA(cudaLaunchKernelEx(&cfg, joint_dgrad2_kernel<true, true>, map_hi, map_lo, map_g, p));
+  } else if (split) {
+    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_dgrad2_kernel<true, false><<<groups * njb, kDSplitThreads, smem, stream>>>(
+        map_hi, map_lo, map_g, p);
   } else {
-    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<false>,
+    LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_dgrad2_kernel<false><<<groups * njb, kDThreads, smem, stream>>>(map_hi, map_lo, map_g, p);
+    joint_dgrad2_kernel<false, false><<<groups * njb, kDThreads, smem, stream>>>(map_hi, map_lo,
+                                                                                 map_g, p);
   }
   LT_LAUNCHED();
   return LT_OK;
