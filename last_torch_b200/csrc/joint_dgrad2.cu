@@ -459,34 +459,39 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
         const float* gbr = s_gb + ring * kTile;
         const uint32_t t_d = tmem + acc * kTile + lane_base;
         float csum = 0.f;
-        // two register sets of 8 columns: the loads of one are in flight while the other is
-        // being computed (tcgen05.wait::ld after the compute covers them)
-        float d0[8], f0[8], a0[8], d1[8], f1[8], a1[8];
+        // two register sets of GW columns: the loads of one are in flight while the other is
+        // being computed (tcgen05.wait::ld after the compute covers them).  GW = 16 in the
+        // split-row variant (192 threads: registers to spare, half as many waits per tile),
+        // 8 where 22 warps share the register file.
+        constexpr int GW = SPLIT ? 16 : 8;
+        float d0[GW], f0[GW], a0[GW], d1[GW], f1[GW], a1[GW];
+        auto ld = [&](uint32_t taddr, float (&v)[GW]) {
+          if constexpr (GW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
+        };
         // tanh' = 1 - tanh^2 = 4 r (1 - r) with r = 1 / (1 + E_c E_f): one MUFU op per element;
         // the factor 4 is applied once, when csum / the running sums are flushed
-        auto compute = [&](int c0, const float (&d)[8], const float (&f)[8], float (&a)[8]) {
+        auto compute = [&](int c0, const float (&d)[GW], const float (&f)[GW], float (&a)[GW]) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < GW; ++i) {
             const float x = fmaf(gbr[c0 + i], wbj, d[i]);
             const float r = rcp_1p(pc_cur * f[i]);
             const float gp = x * fmaf(-r, r, r);
             csum += gp;
             a[i] += gp;
           }
-          tmem_st8(t_acc + c0, a);
+          if constexpr (GW == 16) tmem_st16(t_acc + c0, a); else tmem_st8(t_acc + c0, a);
         };
-        tmem_ld8(t_d + col0, d0); tmem_ld8(t_pf + col0, f0); tmem_ld8(t_acc + col0, a0);
+        ld(t_d + col0, d0); ld(t_pf + col0, f0); ld(t_acc + col0, a0);
 #pragma unroll 1
-        for (int c0 = col0; c0 < col0 + kCols; c0 += 16) {
+        for (int c0 = col0; c0 < col0 + kCols; c0 += 2 * GW) {
           tmem_wait_ld();
-          tmem_ld8(t_d + c0 + 8, d1); tmem_ld8(t_pf + c0 + 8, f1); tmem_ld8(t_acc + c0 + 8, a1);
+          ld(t_d + c0 + GW, d1); ld(t_pf + c0 + GW, f1); ld(t_acc + c0 + GW, a1);
           compute(c0, d0, f0, a0);
           tmem_wait_ld();
-          if (c0 + 16 < col0 + kCols) {
-            tmem_ld8(t_d + c0 + 16, d0); tmem_ld8(t_pf + c0 + 16, f0);
-            tmem_ld8(t_acc + c0 + 16, a0);
+          if (c0 + 2 * GW < col0 + kCols) {
+            ld(t_d + c0 + 2 * GW, d0); ld(t_pf + c0 + 2 * GW, f0); ld(t_acc + c0 + 2 * GW, a0);
           }
-          compute(c0 + 8, d1, f1, a1);
+          compute(c0 + GW, d1, f1, a1);
         }
         tmem_wait_st();
         umma::fence_before_thread_sync();
