@@ -81,6 +81,24 @@ __device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, int
       "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// ---- TMA multicast: the hidden blocks of one tile range form a cluster; every CTA loads 1/mc
+// of a B tile and multicasts it to all of them (the same shared-memory offset and the same
+// mbarrier offset in every destination CTA), so a gradient row leaves L2 once, not mc times.
+__device__ __forceinline__ void tma_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                          int c2, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst), "l"(map), "r"(c0),
+      "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this offset in every CTA of `mask` once the MMAs retire
+__device__ __forceinline__ void commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+
 // ---- CTA pair (cta_group::2) plumbing, as in joint_fwd2.cu: rank 0 of the cluster is the leader
 // and the only MMA issuer; "leader" barriers are addressed through the shared::cluster window
 // with the peer bit (bit 24) cleared.
@@ -234,6 +252,7 @@ struct Dgrad2Params {
   int C, H, V;
   float* gpc;            // [C, H]  += (atomics)
   float* gpf;            // [N, H]  += (atomics: a frame block can straddle two CTAs)
+  int mc;                // split rows: CTAs per cluster that share every B tile by TMA multicast
 };
 
 // SPLIT: grad_lexical arrives as rows of [V bf16 hi | V bf16 lo] (same bytes as fp32; written by
@@ -275,6 +294,9 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;   // 0 = leader
+  const int mc = (SPLIT && !PAIR) ? p.mc : 1;           // multicast cluster (= hidden blocks)
+  const uint32_t mrank = mc > 1 ? cluster_ctarank() : 0;
+  const uint16_t mmask = (uint16_t)((1u << mc) - 1u);
   const int njb = H / kJB;
   // PAIR: cluster id = blockIdx.x / 2 enumerates (group, pair of hidden blocks)
   const int unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;
@@ -292,7 +314,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
     // PAIR: full / tempty / afull are the LEADER's (arrivals from both CTAs)
     for (int s = 0; s < kStages; ++s) {
       mbar_init_n(smem_u32(&full[s]), PAIR ? 2 : (SPLIT ? 1 : kDProducers));
-      mbar_init_n(smem_u32(&empty[s]), 1);
+      mbar_init_n(smem_u32(&empty[s]), mc);       // multicast: every CTA's MMAs free the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init_n(smem_u32(&tfull[a]), 1);
@@ -311,7 +333,7 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
   umma::fence_before_thread_sync();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
+  if (PAIR || mc > 1) cluster_sync_all();       // barriers initialised cluster-wide
   umma::fence_after_thread_sync();
   const uint32_t tmem = *tmem_slot;
 
@@ -360,6 +382,15 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
               mbar_expect_tx_leader(bar, b_stage);
               tma_3d_2sm(dst, &map_g, kc * 64, c, n0, bar);
               tma_3d_2sm(dst + kBRows * 128, &map_g, V + kc * 64, c, n0, bar);
+            } else if (mc > 1) {
+              // my 128 / mc rows of the tile, to the same place in every CTA of the cluster;
+              // this CTA's barrier collects the bytes of all mc slices
+              const int rows = kTile / mc;
+              const int n0 = (int)(nb * kTile) + (int)mrank * rows;
+              const uint32_t off = mrank * rows * 128;
+              mbar_expect_tx(bar, b_stage);
+              tma_3d_mc(dst + off, &map_g, kc * 64, c, n0, bar, mmask);
+              tma_3d_mc(dst + kTile * 128 + off, &map_g, V + kc * 64, c, n0, bar, mmask);
             } else {
               mbar_expect_tx(bar, b_stage);
               tma_3d(dst, &map_g, kc * 64, c, (int)(nb * kTile), bar);
@@ -415,7 +446,9 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
               umma::mma_bf16(d, dal, dbh, idesc, 1);
             }
           }
-          if (PAIR) commit_2cta(smem_u32(&empty[s])); else umma::commit(smem_u32(&empty[s]));
+          if (PAIR) commit_2cta(smem_u32(&empty[s]));
+          else if (mc > 1) commit_mc(smem_u32(&empty[s]), mmask);
+          else umma::commit(smem_u32(&empty[s]));
         }
         if (PAIR) commit_2cta(smem_u32(&tfull[acc])); else umma::commit(smem_u32(&tfull[acc]));
       }
@@ -611,13 +644,25 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
   }
   umma::fence_before_thread_sync();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
+  if (PAIR || mc > 1) cluster_sync_all();       // no CTA leaves while peers still signal it
   if (warp == 1) {
     if (PAIR) tmem_dealloc_2cta(tmem, 512); else umma::tmem_dealloc(tmem, 512);
   }
 }
 
 }  // namespace
+
+// split rows: CTAs per cluster sharing each B tile by TMA multicast = number of hidden blocks
+// (the CTAs of a group walk the same tile sequence), when that is a legal cluster size.
+// Opt-in: it cuts the L2 -> SM operand traffic by the cluster size (6.9 TB/s without it) but
+// couples the three-stage rings of four CTAs -- a stage is refilled only when ALL of them have
+// consumed it -- and measured 9.3 ms against 4.9 ms.
+int joint_dgrad2_multicast(int H, int V) {
+  (void)V;
+  if (!getenv("LT_JOINT_DGRAD_MULTICAST") || getenv("LT_JOINT_DGRAD_PAIR")) return 1;
+  const int njb = H / kJB;
+  return (njb == 2 || njb == 4 || njb == 8) ? njb : 1;
+}
 
 // CTA-pair variant of the split-row kernel: pairs of hidden blocks (opt-in while it is measured)
 bool joint_dgrad2_pair(int H, int V) {
@@ -644,7 +689,7 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
                         cudaStream_t stream) {
   Dgrad2Params p = {};
   p.pc = pc; p.pf = pf; p.w_blank = wb; p.gl = gl; p.gb = gb;
-  p.N = N; p.C = C; p.H = H; p.V = V; p.gpc = gpc; p.gpf = gpf;
+  p.N = N; p.C = C; p.H = H; p.V = V; p.gpc = gpc; p.gpf = gpf; p.mc = 1;
   const int nk = V / 64;
   const bool pair = split && joint_dgrad2_pair(H, V);
   const size_t smem = (size_t)nk * 2 * kJB * 128 +
@@ -679,8 +724,25 @@ int joint_dgrad2_launch(const CUtensorMap& map_hi, const CUtensorMap& map_lo,
   } else if (split) {
     LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<true, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_dgrad2_kernel<true, false><<<groups * njb, kDSplitThreads, smem, stream>>>(
-        map_hi, map_lo, map_g, p);
+    p.mc = joint_dgrad2_multicast(H, V);
+    if (p.mc > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(groups * njb));    // cluster = the njb hidden blocks of a group
+      cfg.blockDim = dim3(kDSplitThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)p.mc;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      LT_CUDA(cudaLaunchKernelEx(&cfg, joint_dgrad2_kernel<true, false>, map_hi, map_lo, map_g, p));
+    } else {
+      joint_dgrad2_kernel<true, false><<<groups * njb, kDSplitThreads, smem, stream>>>(
+          map_hi, map_lo, map_g, p);
+    }
   } else {
     LT_CUDA(cudaFuncSetAttribute(joint_dgrad2_kernel<false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1356,7 +1356,8 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
       // rows of [V bf16 hi | V bf16 lo]: {2V, C, N} bf16, one [128 frames x 1 state x 64] box
       cuuint64_t gd[3] = {(cuuint64_t)2 * V, (cuuint64_t)C, (cuuint64_t)N};
       cuuint64_t gs[2] = {(cuuint64_t)V * 4, (cuuint64_t)C * V * 4};
-      cuuint32_t gbox[3] = {64, 1, (cuuint32_t)(joint_dgrad2_pair(H, V) ? 64 : 128)};
+      cuuint32_t gbox[3] = {64, 1, (cuuint32_t)(joint_dgrad2_pair(H, V)
+                                                    ? 64 : 128 / joint_dgrad2_multicast(H, V))};
       cuuint32_t ge[3] = {1, 1, 1};
       CUresult r = encode(&m_g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<float*>(gl), gd,
                           gs, gbox, ge, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

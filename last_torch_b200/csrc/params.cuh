@@ -144,6 +144,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
                           int V, float* gpc, float* gpf, void* workspace, cudaStream_t stream);
 bool joint_backward_split_supported(int64_t N, int C, int H, int V);
 bool joint_dgrad2_pair(int H, int V);      // map_g box: 64 frames instead of 128
+int joint_dgrad2_multicast(int H, int V);  // map_g box: 128 / this frames
 int joint_split_rows_launch(const float* g, void* out, int64_t M, int V, cudaStream_t stream);
 // CTA-pair (cta_group::2) forward (joint_fwd2.cu)
 bool joint_fwd2_supported(int64_t N, int C, int H, int V);
