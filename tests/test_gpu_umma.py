@@ -162,6 +162,41 @@ def test_joint_backward_frame_blocks_straddle_ctas(c, v, h, n):
     assert float((a - s).abs().max()) / scale < 3e-5, (tuple(s.shape), float((a - s).abs().max()) / scale)
 
 
+@pytest.mark.parametrize('variant', ['', 'LT_JOINT_DGRAD_PAIR', 'LT_JOINT_DGRAD_MULTICAST'])
+def test_joint_backward_split_row_kernels(variant):
+  """The split-row forms of the tensor-core backward kernels (fused dgrad fed by TMA, weight
+  gradient copying its A operand) on a split copy of the fp32 gradient
+  (LT_JOINT_DGRAD_SPLIT_TEST), plus the opt-in CTA-pair and TMA-multicast variants of the
+  dgrad: same gradients as the fp32 kernels."""
+  import os
+  import last_torch_b200 as lt
+  c, v, h, n = 257, 256, 512, 300
+  torch.manual_seed(7)
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=24,
+                                   feature_size=16)
+  params = list(fn.parameters())
+  cache = torch.randn([c, 24], device='cuda', requires_grad=True)
+  frames = torch.randn([n, 1, 16], device='cuda', requires_grad=True)
+  wb = torch.rand([n, 1, c], device='cuda') / c
+  wl = torch.rand([n, 1, c, v], device='cuda') / (c * v)
+
+  def run(envs):
+    for e in envs:
+      os.environ[e] = '1'
+    try:
+      b, l = fn.all_frames(cache, frames)
+      return torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
+    finally:
+      for e in envs:
+        os.environ.pop(e, None)
+
+  ref = run([])
+  got = run(['LT_JOINT_DGRAD_SPLIT_TEST'] + ([variant] if variant else []))
+  for a, r in zip(got, ref):
+    scale = float(r.abs().max()) + 1e-12
+    assert float((a - r).abs().max()) / scale < 2e-5, (tuple(r.shape), float((a - r).abs().max()) / scale)
+
+
 def _probe_mn(at, bt, swap):
   from last_torch_b200 import _native as N
   N.lib()
