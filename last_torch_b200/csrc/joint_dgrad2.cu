@@ -4,6 +4,7 @@
 // streamed it back through a reduction kernel).
 //
 //   Gp[m, j] = (sum_v G[m, v] W_vocab[v, j] + gb[m] w_blank[j]) * (1 - tanh^2(pc[c, j] + pf[n, j]))
+//            = (...) * 4 r (1 - r),  r = 1 / (1 + E_c[c, j] E_f[n, j])   (exponential tables)
 //   grad_proj_ctx[c, j]   = sum_n Gp[(n, c), j]        grad_proj_frame[n, j] = sum_c Gp[(n, c), j]
 //
 // The product is computed TRANSPOSED, D[j, i] = sum_v W^T[j, v] G[m_i, v], so that a TMEM lane
@@ -25,12 +26,15 @@
 //     straddles two ranges is flushed by both owners, so grad_proj_frame is added atomically;
 //   * the epilogue reads TMEM in 8-column groups, the loads of group g+1 in flight while group
 //     g is being computed.
-// Measured limits (B=32, T=1000, C=257, H=512, V=256: 11.8 ms, tensor pipe 24 %): with N = 128
-// every SS-mode tcgen05.mma reads 8 KB of shared memory per 64 issue cycles, i.e. the whole
-// 128 B/clk port, so the producers' stores slow the MMAs; the epilogue reads 3 x 64 KB of TMEM
-// per tile at 64 B/clk (as long as the tile's MMAs); and every grad_lexical row is fetched by
-// the four CTAs (hidden blocks) that need it.  MMAs + conversion alone take 5.3 ms, the
-// gradient loads add ~3 ms and the epilogue ~3 ms.
+// Two input forms of grad_lexical (template SPLIT): fp32 rows, split hi / lo on the fly by 16
+// producer warps (6.6 ms at B=32, T=1000, C=257, H=512, V=256; the first version took 11.8 ms
+// with 266 producer instructions per 16-element chunk), or "split rows" written by the lattice
+// backward kernel, loaded by TMA with no producer warps at all (4.9 ms, tensor pipe 65 %).
+// What bounds the latter: with N = 128 every SS-mode tcgen05.mma reads 8 KB of shared memory per
+// 64 issue cycles -- the whole 128 B/clk port whenever the tensor core is active -- and every
+// gradient row is pulled from L2 by the four CTAs (hidden blocks) that need it (6.9 TB/s).
+// DESIGN.md section 6 lists what was tried against that (CTA pairs, TMA multicast, more epilogue
+// warps, register-resident sums) and did not help.
 // TMEM map (512 columns): [0,128) D0 | [128,256) D1 | [256,384) pf | [384,512) grad_proj_frame.
 //
 // Reference: the autograd of weight_fns.py:208-227 (tanh joint + two Linear layers).
