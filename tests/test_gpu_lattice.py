@@ -519,3 +519,46 @@ def test_full_size_properties_config1_and_2():
                            semiring=lt.semirings.MaxTropical)
   assert bool((vd <= dist + 1e-3).all())
   assert bool((dist <= vd + nf.float() * np.log(1 + vocab) + 1e-2).all())
+
+
+@pytest.mark.parametrize('vocab', [64, 128, 192, 256])
+@pytest.mark.parametrize('semiring', ['log', 'real'])
+def test_backward_split_row_emission(vocab, semiring):
+  """lt_lattice_backward with LT_FLAG_GRAD_SPLIT: every row of grad_lexical holds
+  [V bf16 hi | V bf16 lo] in its V*4 bytes and hi + lo is the fp32 gradient to 2^-17 -- with an
+  odd batch, ragged and empty utterances (zero rows on padding frames) and a non-unit upstream
+  gradient; grad_blank is unchanged."""
+  _lt()
+  from last_torch_b200 import ops, _native as N
+  sr = N.LOG if semiring == 'log' else N.REAL
+  b, t, c = 3, 11, vocab + 1
+  g = torch.Generator(device='cuda').manual_seed(vocab)
+  blank = torch.randn([b, t, c], device='cuda', generator=g)
+  lex = torch.randn([b, t, c, vocab], device='cuda', generator=g)
+  if semiring == 'real':
+    blank, lex = blank * 0.01 + 1.0 / c, lex * 0.01 + 1.0 / c
+  nf = torch.tensor([t, 6, 0], dtype=torch.int32, device='cuda')
+  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, -1, 0) == 1
+  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 2, -1, 0) == 0
+  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, 2, 0) == 0
+  out = ops._lattice_forward_raw(sr, vocab, 1, -1, blank, lex, nf, 0, False, False)
+  dist, alphas = out[0], out[1]
+  gd = torch.tensor([1.0, -0.5, 2.0], device='cuda')
+
+  def bwd(flags):
+    gb = torch.full_like(blank, 7.0)
+    gl = torch.full_like(lex, 7.0)
+    N.check(N.lib().lt_lattice_backward(
+        sr, vocab, 1, -1, N.ptr(blank), N.ptr(lex), N.ptr(nf), b, t, N.ptr(alphas), None,
+        N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, flags, N.stream_ptr(blank.device)),
+        'lt_lattice_backward')
+    return gb, gl
+
+  gb0, gl0 = bwd(0)
+  gb1, gs = bwd(N.FLAG_GRAD_SPLIT)
+  npt.assert_array_equal(gb1.cpu().numpy(), gb0.cpu().numpy())
+  rows = gs.view(torch.bfloat16).reshape(b, t, c, 2, vocab).float()
+  rec = rows[..., 0, :] + rows[..., 1, :]
+  err = (rec - gl0).abs()
+  assert bool((err <= gl0.abs() * 2.0 ** -16 + 1e-37).all()), float(err.max())
+  assert float(rec[1, 6:].abs().max()) == 0.0 and float(rec[2].abs().max()) == 0.0
