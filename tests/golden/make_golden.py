@@ -282,6 +282,73 @@ def joint_case(name, vocab, ctx, hidden, emb, feat, batch, seed):
   print(f'{name}: joint ok blank{tuple(blank.shape)} lexical{tuple(lexical.shape)}')
 
 
+def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames, labels,
+                       num_labels, seed):
+  """The whole GNAT loss of the reference with its own JointWeightFn inside the lattice
+  (lattices.py:131-183 + weight_fns.py:194-227), bigram context, in the shape envelope of the
+  tensor-core kernels.  The Linear shim of joint_case makes the weights deterministic (SURVEY D6);
+  the cache tensor is passed explicitly (D7).  Loss value: the reference as shipped.  Parameter
+  gradients: patched Log autograd (D1/D2) through `_forward - _string_forward`, because
+  `forward()` detaches the denominator (D3)."""
+  import last_torch.weight_fns as wf
+  torch.manual_seed(seed)
+  c = vocab + 1
+  cache_mods = {}
+
+  class ShimNN:
+    def __getattr__(self, item):
+      return getattr(torch.nn, item)
+
+    @staticmethod
+    def Linear(i, o, bias=True, device=None):
+      key = (i, o, bias)
+      if key not in cache_mods:
+        cache_mods[key] = torch.nn.Linear(i, o, bias=bias)
+      return cache_mods[key]
+
+  assert emb != feat, 'shim keys must be distinguishable'
+  saved = wf.nn
+  wf.nn = ShimNN()
+  try:
+    lattice = last_torch.RecognitionLattice(
+        context=last_torch.contexts.FullNGram(vocab_size=vocab, context_size=1),
+        alignment=last_torch.alignments.FrameDependent(),
+        weight_fn_factory=lambda ctx: wf.JointWeightFn(vocab_size=vocab, hidden_size=hidden),
+        weight_fn_cacher_factory=lambda ctx: last_torch.weight_fns.NullCacher())
+    cache = torch.randn([c, emb]).requires_grad_()
+    frames = torch.randn([batch, t_max, feat])
+    nf = torch.tensor(num_frames).float()
+    lab = torch.tensor(labels).float()
+    nl = torch.tensor(num_labels).float()
+    remove_patches()
+    with torch.no_grad():
+      loss = lattice(frames=frames, num_frames=nf, labels=lab, num_labels=nl, cache=cache)
+    apply_patches()
+    log_z, _ = lattice._forward(cache=cache, frames=frames, num_frames=nf,
+                                semiring=last_torch.semirings.Log)
+    num = lattice._string_forward(cache=cache, frames=frames, num_frames=nf, labels=lab,
+                                  num_labels=nl, semiring=last_torch.semirings.Log)
+    mods = dict(w_ctx=cache_mods[(emb, hidden, False)], w_frame=cache_mods[(feat, hidden, False)],
+                blank=cache_mods[(hidden, 1, True)], vocab=cache_mods[(hidden, vocab, True)])
+    leaves = [cache, mods['w_ctx'].weight, mods['w_frame'].weight, mods['blank'].weight,
+              mods['blank'].bias, mods['vocab'].weight, mods['vocab'].bias]
+    grads = torch.autograd.grad((log_z - num).sum(), leaves)
+    remove_patches()
+  finally:
+    wf.nn = saved
+    remove_patches()
+  names = ['cache', 'w_ctx', 'w_frame', 'w_blank', 'b_blank', 'w_vocab', 'b_vocab']
+  out = dict(vocab=vocab, hidden=hidden, frames=frames.numpy(), num_frames=np.asarray(num_frames),
+             labels=np.asarray(labels), num_labels=np.asarray(num_labels),
+             loss=loss.numpy(), loss_patched=(log_z - num).detach().numpy())
+  for n, leaf, g in zip(names, leaves, grads):
+    out[n] = leaf.detach().numpy()
+    out['grad_' + n] = g.numpy()
+  np.savez_compressed(os.path.join(OUT, f'jointlattice_{name}.npz'), **out)
+  print(f'{name}: joint lattice ok loss={out["loss"]} |grad w_vocab|max='
+        f'{np.abs(out["grad_w_vocab"]).max():.3e}')
+
+
 def main():
   torch.set_num_threads(4)
   lattice_case('fd_bigram_v3', vocab=3, ctx=1, k=None, batch=4, t_max=6,
@@ -332,6 +399,9 @@ def main():
              seed=30)
   joint_case('trigram_v3', vocab=3, ctx=2, hidden=32, emb=12, feat=20, batch=4,
              seed=31)
+  joint_lattice_case('bigram_v128_h128', vocab=128, hidden=128, emb=24, feat=16, batch=2,
+                     t_max=5, num_frames=[5, 3], labels=[[7, 100, 7], [128, 1, 0]],
+                     num_labels=[3, 2], seed=40)
 
 
 if __name__ == '__main__':

@@ -217,6 +217,55 @@ def test_joint_golden(fname):
     npt.assert_allclose(a.cpu(), b.cpu(), rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('fname', golden_files('jointlattice_'))
+@pytest.mark.parametrize('split', [True, False])
+def test_joint_lattice_golden(fname, split):
+  """The reference's whole GNAT loss with JointWeightFn inside the lattice (vocab 128, hidden
+  128: tcgen05 forward, TMA fast path, tensor-core backward with and without the split-row
+  hand-over) -- loss of the reference as shipped, parameter gradients of its patched autograd."""
+  import os
+  lt = _lt()
+  g = np.load(os.path.join(GOLDEN_DIR, fname))
+  v, h = int(g['vocab']), int(g['hidden'])
+  e, d = g['cache'].shape[1], g['frames'].shape[2]
+  context = lt.contexts.FullNGram(vocab_size=v, context_size=1)
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=e, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=v, hidden_size=h, device='cuda', embedding_size=e, feature_size=d))
+  fn, cacher = lattice.weight_fn, lattice.weight_fn_cacher
+  with torch.no_grad():
+    cacher.embedding.weight.copy_(T(g['cache']))
+    fn.context_projection.weight.copy_(T(g['w_ctx']))
+    fn.blank_projection.weight.copy_(T(g['w_frame']))
+    fn.joint_projection_to_blank.weight.copy_(T(g['w_blank']))
+    fn.joint_projection_to_blank.bias.copy_(T(g['b_blank']))
+    fn.joint_projection_to_vocab.weight.copy_(T(g['w_vocab']))
+    fn.joint_projection_to_vocab.bias.copy_(T(g['b_vocab']))
+  if not split:
+    os.environ['LT_NO_SPLIT_GRAD'] = '1'
+  try:
+    loss = lattice(frames=T(g['frames']), num_frames=T(g['num_frames']), labels=T(g['labels']),
+                   num_labels=T(g['num_labels']))
+    loss.sum().backward()
+  finally:
+    os.environ.pop('LT_NO_SPLIT_GRAD', None)
+  npt.assert_allclose(loss.detach().cpu(), g['loss'], rtol=1e-5)
+  got = {'cache': cacher.embedding.weight.grad, 'w_ctx': fn.context_projection.weight.grad,
+         'w_frame': fn.blank_projection.weight.grad,
+         'w_blank': fn.joint_projection_to_blank.weight.grad,
+         'b_blank': fn.joint_projection_to_blank.bias.grad,
+         'w_vocab': fn.joint_projection_to_vocab.weight.grad,
+         'b_vocab': fn.joint_projection_to_vocab.bias.grad}
+  for name, a in got.items():
+    ref = g['grad_' + name]
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(a.cpu().numpy() - ref).max())
+    assert err <= 1e-4 * scale + 1e-6, (name, err / scale)
+
+
 # ---- RecognitionLattice API (tests/lattices_test.py) ---------------------------
 
 def _joint_lattice(vocab_size, context_size, alignment):

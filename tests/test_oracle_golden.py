@@ -222,6 +222,37 @@ def test_joint_golden(fname):
   npt.assert_allclose(lexical[np.arange(len(s)), s], g['state_lexical'], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('fname', golden_files('jointlattice_'))
+def test_joint_lattice_golden(fname):
+  """The whole GNAT loss of the reference with its JointWeightFn inside the lattice
+  (tests/golden/make_golden.py: joint_lattice_case), in the tensor-core shape envelope: loss
+  value of the reference as shipped, parameter gradients from its patched Log autograd."""
+  g = _load(fname)
+  f64 = lambda k: g[k].astype(np.float64)
+  v = int(g['vocab'])
+  blank, lex = O.joint_weights(f64('cache'), f64('frames'), f64('w_ctx'), f64('w_frame'),
+                               f64('w_blank')[0], float(g['b_blank'][0]), f64('w_vocab'),
+                               f64('b_vocab'))
+  loss, gb, gl = O.lattice_loss_and_grads(blank, lex, g['num_frames'], g['labels'],
+                                          g['num_labels'], O.FullNGram(v, 1))
+  npt.assert_allclose(loss, g['loss'], rtol=1e-5)
+  npt.assert_allclose(loss, g['loss_patched'], rtol=1e-5)
+  joint = np.tanh((f64('cache') @ f64('w_ctx').T)[None, None] +
+                  (f64('frames') @ f64('w_frame').T)[:, :, None, :])          # [B,T,C,H]
+  dpre = (gl @ f64('w_vocab') + gb[..., None] * f64('w_blank')[0]) * (1.0 - joint * joint)
+  want = {
+      'w_vocab': np.einsum('btcv,btch->vh', gl, joint), 'b_vocab': gl.sum(axis=(0, 1, 2)),
+      'w_blank': np.einsum('btc,btch->h', gb, joint)[None], 'b_blank': gb.sum()[None],
+      'w_ctx': dpre.sum(axis=(0, 1)).T @ f64('cache'),
+      'w_frame': np.einsum('bth,btd->hd', dpre.sum(axis=2), f64('frames')),
+      'cache': dpre.sum(axis=(0, 1)) @ f64('w_ctx'),
+  }
+  for name, w in want.items():
+    ref = g['grad_' + name]
+    scale = np.abs(ref).max()
+    assert np.abs(w - ref).max() <= 2e-5 * scale + 1e-7, (name, np.abs(w - ref).max() / scale)
+
+
 # ---- the C restatement (oracle/lattice_oracle.c) agrees with the numpy oracle ----
 
 @pytest.mark.parametrize('vnk', [(5, 1, -1), (3, 2, -1), (4, 0, -1), (3, 1, 2), (2, 2, 3), (16, 1, -1)])
