@@ -54,6 +54,10 @@ class _JointProjection(torch.autograd.Function):
     fmt = 1 if (sg is not None and sg.emitted) else 0      # split rows from the lattice backward
     if sg is not None:
       sg.emitted = False
+      if fmt and g_lexical.data_ptr() != sg.ptr:
+        # autograd summed / copied / hooked the opaque buffer: its bytes are no longer split rows
+        raise RuntimeError('grad_lexical was modified between the lattice backward and the joint '
+                           'backward; set LT_NO_SPLIT_GRAD=1 to hand gradients over in float32')
     g_pc = torch.zeros_like(proj_ctx)
     g_pf = torch.zeros_like(proj_frame)
     g_wb = torch.zeros_like(w_blank)

@@ -438,6 +438,7 @@ class SplitGrad:
   def __init__(self):
     self.joint_ok = False
     self.emitted = False
+    self.ptr = 0          # data_ptr of the split-row buffer (the consumer checks it got THAT one)
 
 
 def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scale=None,
@@ -557,4 +558,5 @@ class LatticeLoss(torch.autograd.Function):
                     split=split)
     if sg is not None:
       sg.emitted = split
+      sg.ptr = gl.data_ptr()
     return gb, gl, None, None, None, None, None, None, None, None, None
