@@ -283,7 +283,7 @@ def joint_case(name, vocab, ctx, hidden, emb, feat, batch, seed):
 
 
 def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames, labels,
-                       num_labels, seed):
+                       num_labels, seed, ctx=1, k=None):
   """The whole GNAT loss of the reference with its own JointWeightFn inside the lattice
   (lattices.py:131-183 + weight_fns.py:194-227), bigram context, in the shape envelope of the
   tensor-core kernels.  The Linear shim of joint_case makes the weights deterministic (SURVEY D6);
@@ -292,7 +292,7 @@ def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames,
   `forward()` detaches the denominator (D3)."""
   import last_torch.weight_fns as wf
   torch.manual_seed(seed)
-  c = vocab + 1
+  c = sum(vocab**i for i in range(ctx + 1))
   cache_mods = {}
 
   class ShimNN:
@@ -311,10 +311,11 @@ def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames,
   wf.nn = ShimNN()
   try:
     lattice = last_torch.RecognitionLattice(
-        context=last_torch.contexts.FullNGram(vocab_size=vocab, context_size=1),
-        alignment=last_torch.alignments.FrameDependent(),
-        weight_fn_factory=lambda ctx: wf.JointWeightFn(vocab_size=vocab, hidden_size=hidden),
-        weight_fn_cacher_factory=lambda ctx: last_torch.weight_fns.NullCacher())
+        context=last_torch.contexts.FullNGram(vocab_size=vocab, context_size=ctx),
+        alignment=(last_torch.alignments.FrameDependent() if k is None else
+                   last_torch.alignments.FrameLabelDependent(max_expansions=k)),
+        weight_fn_factory=lambda _: wf.JointWeightFn(vocab_size=vocab, hidden_size=hidden),
+        weight_fn_cacher_factory=lambda _: last_torch.weight_fns.NullCacher())
     cache = torch.randn([c, emb]).requires_grad_()
     frames = torch.randn([batch, t_max, feat])
     nf = torch.tensor(num_frames).float()
@@ -338,7 +339,8 @@ def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames,
     wf.nn = saved
     remove_patches()
   names = ['cache', 'w_ctx', 'w_frame', 'w_blank', 'b_blank', 'w_vocab', 'b_vocab']
-  out = dict(vocab=vocab, hidden=hidden, frames=frames.numpy(), num_frames=np.asarray(num_frames),
+  out = dict(vocab=vocab, hidden=hidden, context_size=ctx, k=-1 if k is None else k,
+             frames=frames.numpy(), num_frames=np.asarray(num_frames),
              labels=np.asarray(labels), num_labels=np.asarray(num_labels),
              loss=loss.numpy(), loss_patched=(log_z - num).detach().numpy())
   for n, leaf, g in zip(names, leaves, grads):
@@ -402,6 +404,12 @@ def main():
   joint_lattice_case('bigram_v128_h128', vocab=128, hidden=128, emb=24, feat=16, batch=2,
                      t_max=5, num_frames=[5, 3], labels=[[7, 100, 7], [128, 1, 0]],
                      num_labels=[3, 2], seed=40)
+  joint_lattice_case('bigram_v64_h128', vocab=64, hidden=128, emb=24, feat=16, batch=3,
+                     t_max=6, num_frames=[6, 4, 2], labels=[[5, 5, 64, 1], [9, 33, 0, 0], [2, 0, 0, 0]],
+                     num_labels=[4, 2, 1], seed=41)
+  joint_lattice_case('trigram_v3_fld2', vocab=3, hidden=32, emb=12, feat=20, batch=3, t_max=5,
+                     num_frames=[5, 4, 2], labels=[[1, 3, 2, 2, 1], [2, 2, 0, 0, 0], [3, 1, 0, 0, 0]],
+                     num_labels=[5, 2, 2], seed=42, ctx=2, k=2)
 
 
 if __name__ == '__main__':

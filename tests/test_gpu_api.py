@@ -220,17 +220,22 @@ def test_joint_golden(fname):
 @pytest.mark.parametrize('fname', golden_files('jointlattice_'))
 @pytest.mark.parametrize('split', [True, False])
 def test_joint_lattice_golden(fname, split):
-  """The reference's whole GNAT loss with JointWeightFn inside the lattice (vocab 128, hidden
-  128: tcgen05 forward, TMA fast path, tensor-core backward with and without the split-row
-  hand-over) -- loss of the reference as shipped, parameter gradients of its patched autograd."""
+  """The reference's whole GNAT loss with JointWeightFn inside the lattice -- vocab 128 / hidden
+  128 (tcgen05 forward, TMA fast path, tensor-core backward with and without the split-row
+  hand-over), vocab 64 (tcgen05 forward and dgrad, CUDA-core weight gradient) and a trigram
+  FrameLabelDependent(2) lattice (CUDA-core joint, generic lattice kernels): loss of the
+  reference as shipped, parameter gradients of its patched autograd."""
   import os
   lt = _lt()
   g = np.load(os.path.join(GOLDEN_DIR, fname))
   v, h = int(g['vocab']), int(g['hidden'])
   e, d = g['cache'].shape[1], g['frames'].shape[2]
-  context = lt.contexts.FullNGram(vocab_size=v, context_size=1)
+  k = int(g['k'])
+  context = lt.contexts.FullNGram(vocab_size=v, context_size=int(g['context_size']))
   lattice = lt.RecognitionLattice(
-      context=context, alignment=lt.alignments.FrameDependent(),
+      context=context,
+      alignment=(lt.alignments.FrameDependent() if k < 0 else
+                 lt.alignments.FrameLabelDependent(max_expansions=k)),
       weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
           num_context_states=c.shape()[0], embedding_size=e, device='cuda'),
       weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
