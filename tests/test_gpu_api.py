@@ -271,6 +271,55 @@ def test_joint_lattice_golden(fname, split):
     assert err <= 1e-4 * scale + 1e-6, (name, err / scale)
 
 
+def test_joint_lattice_full_size_properties():
+  """BASELINE configs[1] + configs[3] end to end (B=32, T=1000, bigram vocab 256, U=120, joint
+  hidden 512) through RecognitionLattice.forward: size-independent properties of the parameter
+  gradients, with and without the split-row hand-over.
+    * adding a constant to every arc weight of a FrameDependent lattice moves logZ and the
+      numerator by the same T * const, so sum_v grad_b_vocab + grad_b_blank = 0;
+    * both hand-over forms give the same loss and the same gradients."""
+  import os
+  lt = _lt()
+  b, t, v, h, u = 32, 1000, 256, 512, 120
+  torch.manual_seed(0)
+  context = lt.contexts.FullNGram(vocab_size=v, context_size=1)
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=64, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=h, device='cuda'))
+  x = torch.randn([b, t, 80], device='cuda')
+  num_frames = torch.randint(t // 2, t + 1, [b], device='cuda')
+  labels = torch.randint(1, v + 1, [b, u], device='cuda')
+  num_labels = torch.full([b], u, device='cuda')
+
+  def run(no_split):
+    if no_split:
+      os.environ['LT_NO_SPLIT_GRAD'] = '1'
+    try:
+      lattice.zero_grad()
+      loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
+      loss.sum().backward()
+      return loss.detach().clone(), {n: p.grad.clone() for n, p in lattice.named_parameters()}
+    finally:
+      os.environ.pop('LT_NO_SPLIT_GRAD', None)
+
+  loss_s, g_s = run(False)
+  loss_f, g_f = run(True)
+  assert bool(torch.isfinite(loss_s).all())
+  npt.assert_array_equal(loss_s.cpu(), loss_f.cpu())
+  mass = float(num_frames.sum())
+  for grads in (g_s, g_f):
+    bv = [g for n, g in grads.items() if n.endswith('joint_projection_to_vocab.bias')][0]
+    bb = [g for n, g in grads.items() if n.endswith('joint_projection_to_blank.bias')][0]
+    assert float(bv.abs().sum()) > 0.1 * mass          # the gradient is not trivially small
+    assert abs(float(bv.double().sum() + bb.double().sum())) < 5e-3 * mass
+  for n in g_s:
+    scale = float(g_f[n].abs().max()) + 1e-12
+    assert float((g_s[n] - g_f[n]).abs().max()) / scale < 1e-4, n
+
+
 # ---- RecognitionLattice API (tests/lattices_test.py) ---------------------------
 
 def _joint_lattice(vocab_size, context_size, alignment):
