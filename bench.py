@@ -450,7 +450,10 @@ def run_b200(args):
            'gpu_launches_per_step': e_launches / e_steps,
            'kernels_ms': {k: statistics.mean(v) for k, v in e_kernels.items()},
            'api': 'RecognitionLattice.forward + autograd.grad w.r.t. JointWeightFn/SharedEmbCacher '
-                  'parameters'}
+                  'parameters',
+           'grad_handover': ('float32' if os.environ.get('LT_NO_SPLIT_GRAD') else
+                             'split rows (bf16 hi | lo) from the lattice backward to the joint '
+                             'backward where both kernels support it')}
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu:
