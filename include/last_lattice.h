@@ -199,7 +199,15 @@ int lt_semiring_sum_backward(int semiring, const float* a, const float* out,
  * forward_reduce / its gradient on arbitrary leading dims (w viewed as [outer, C, V]):
  *   out[o,q] = (+)_{p -y-> q} w[o,p,y] for EVERY semiring (the reference implements the
  *   Real semiring only); argarc [outer,C] int32 for MaxTropical.
+ * FrameDependent lattices with V % 4 == 0 (and C <= 1024 forward) run on a CLUSTER of up to 8
+ * CTAs per utterance (csrc/lattice_table2.cu: every CTA streams a slab of source rows with
+ * bulk copies, one cluster barrier per frame); everything else runs one CTA per utterance.
+ * lt_table_lattice_cluster() returns the cluster size the forward (backward != 0: the
+ * backward) kernel of such a lattice would use with 16-byte aligned weights, 0 for the
+ * one-CTA kernels.  Environment: LT_TABLE_CLUSTER=1|2|4|8 forces a size, LT_TABLE_V1=1 the
+ * one-CTA kernels.
  */
+int lt_table_lattice_cluster(int C, int V, int max_expansions, int backward);
 int lt_table_lattice_forward(int semiring, int max_expansions, const int32_t* table,
                              const int32_t* in_offsets, const int32_t* in_arcs, int C, int V,
                              const float* blank, const float* lexical,

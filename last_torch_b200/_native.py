@@ -72,6 +72,7 @@ SIGNATURES = {
                                   _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_table_viterbi_backtrace': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int,
                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_table_lattice_cluster': [_c_int, _c_int, _c_int, _c_int],
     'lt_table_reduce_forward': [_c_int, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr, _ptr,
                                 _ptr],
     'lt_local_normalize_forward': [_c_int, _ptr, _ptr, _c_i64, _c_int, _ptr, _ptr, _ptr],

@@ -16,32 +16,10 @@
 // out[q] = (+)_{p -y-> q} w[p, y] (contexts.py:74-90), first arg-max in flat-arc order.
 #include "common.cuh"
 #include "params.cuh"
+#include "table_params.cuh"
 
 namespace lt {
 
-struct TableParams {
-  int C, V, k, B, T;
-  const int32_t* table;        // [C, V] next state of (p, y)
-  const int32_t* in_offsets;   // [C + 1]
-  const int32_t* in_arcs;      // [C * V]
-  const float* blank;
-  const float* lexical;
-  const int32_t* num_frames;
-  const float* alpha_init;
-  float* dist;
-  float* alphas;
-  float* alpha_final;
-  float* levels;
-  int32_t* backarc;            // [B, T, max(k,1), C]
-  uint8_t* termptr;            // [B, T, C]
-  // backward
-  const float* alphas_in;
-  const float* levels_in;
-  const float* dist_in;
-  const float* grad_dist;
-  float* grad_blank;
-  float* grad_lexical;
-};
 
 namespace {
 
@@ -403,6 +381,7 @@ static size_t table_smem(int C, bool fld, bool backward) {
 }
 
 int table_lattice_forward_launch(int semiring, const TableParams& p, cudaStream_t stream) {
+  if (table2_forward_supported(p)) return table2_forward_launch(semiring, p, stream);
   const bool fld = p.k >= 1;
   const size_t smem = table_smem(p.C, fld, false);
   if (smem > 227 * 1024) {
@@ -430,6 +409,7 @@ int table_lattice_forward_launch(int semiring, const TableParams& p, cudaStream_
 }
 
 int table_lattice_backward_launch(int semiring, const TableParams& p, cudaStream_t stream) {
+  if (table2_backward_supported(p)) return table2_backward_launch(semiring, p, stream);
   const bool fld = p.k >= 1;
   const size_t smem = table_smem(p.C, fld, true);
   if (smem > 227 * 1024) {
@@ -513,6 +493,11 @@ static int check_table_args(const char* fn, int semiring, int C, int V, int k, i
                "%s: max_expansions must be LT_FRAME_DEPENDENT or in [1, 254], got %d", fn, k);
   LT_CHECK_ARG(B >= 0 && T >= 0, "%s: negative batch (%d) or frame count (%d)", fn, B, T);
   return LT_OK;
+}
+
+int lt_table_lattice_cluster(int C, int V, int max_expansions, int backward) {
+  if (C <= 0 || V <= 0) return 0;
+  return table2_cluster_size(C, V, max_expansions, backward != 0);
 }
 
 int lt_table_lattice_forward(int semiring, int max_expansions, const int32_t* table,

@@ -186,3 +186,114 @@ def test_random_dfa_vs_oracle(seed, c, vocab, k):
         score += table_np[bi, ti, q, 0]
     npt.assert_allclose(score, o_dist[bi], rtol=1e-5)
     assert np.all(lab[bi, nf[bi]:] == 0)
+
+
+@pytest.mark.parametrize('cluster', [0, 1, 2, 4, 8])
+@pytest.mark.parametrize('seed,c,vocab,ties', [(10, 20, 8, False), (11, 257, 12, False),
+                                               (12, 130, 64, False), (13, 40, 16, True),
+                                               (14, 257, 256, False)])
+def test_cluster_table_kernels(seed, c, vocab, ties, cluster, monkeypatch):
+  """The cluster-per-utterance kernels (csrc/lattice_table2.cu) for every cluster size against
+  the fp64 oracle (loss + gradients, Log / MaxTropical / Real forward) and, bit for bit in the
+  MaxTropical semiring (integer weights = ties everywhere when `ties`), against the one-CTA
+  kernels.  cluster 0 = the size the library picks itself."""
+  lt = _lt()
+  from last_torch_b200 import _native as N
+  rng = np.random.RandomState(seed)
+  nst = rng.randint(0, max(2, c - 2), size=(c, vocab)).astype(np.int32)
+  nst[0, 0] = 1
+  nst[:, vocab - 1] = c // 2          # one state with a large in-degree
+  ctx = lt.contexts.NextStateTable(torch.from_numpy(nst))
+  octx = O.NextStateTable(nst)
+  b, t, u = 4, 11, 4
+  if ties:
+    table_np = rng.randint(-2, 3, size=(b, t, c, 1 + vocab)).astype(np.float32)
+  else:
+    table_np = rng.randn(b, t, c, 1 + vocab).astype(np.float32)
+    drop = rng.rand(b, t, c, 1 + vocab) < 0.03
+    drop[..., 0] = False
+    table_np[drop] = -np.inf
+  nf = np.array([11, 6, 0, 1])
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = np.array([4, 3, 0, 1])
+  frames = frames_for(b, t)
+
+  def run():
+    table = cuda(table_np).requires_grad_()
+    lattice = make_lattice(ctx, -1, table)
+    loss = lattice(frames=frames, num_frames=cuda(nf), labels=cuda(labels), num_labels=cuda(nl),
+                   cache=None)
+    fin = torch.isfinite(loss)
+    (gt,) = torch.autograd.grad(torch.where(fin, loss, torch.zeros_like(loss)).sum(), table)
+    out = {'loss': loss.detach().cpu().numpy(), 'grad': gt.cpu().numpy()}
+    for name in ['Log', 'MaxTropical', 'Real']:
+      tab = table
+      if name == 'Real':
+        tab = cuda((np.exp(np.clip(table_np, -40, 5) * 0.25) / (1 + vocab)).astype(np.float32))
+        tab.requires_grad_()
+      lat = make_lattice(ctx, -1, tab)
+      dist, alphas = lat._forward(cache=None, frames=frames, num_frames=cuda(nf),
+                                  semiring=getattr(lt.semirings, name))
+      (gd,) = torch.autograd.grad(dist.sum(), tab)
+      out[name] = (dist.detach().cpu().numpy(), alphas.cpu().numpy(), gd.cpu().numpy())
+    path = lattice.shortest_path(frames=frames, num_frames=cuda(nf), cache=None)
+    out['path'] = [x.cpu().numpy() for x in path]
+    return out
+
+  monkeypatch.setenv('LT_TABLE_V1', '1')
+  assert N.lib().lt_table_lattice_cluster(c, vocab, -1, 0) == 0
+  v1 = run()
+  monkeypatch.delenv('LT_TABLE_V1')
+  if cluster:
+    monkeypatch.setenv('LT_TABLE_CLUSTER', str(cluster))
+  used = N.lib().lt_table_lattice_cluster(c, vocab, -1, 0)
+  used_bwd = N.lib().lt_table_lattice_cluster(c, vocab, -1, 1)
+  if cluster:
+    assert used in (0, cluster) and used_bwd in (0, cluster)   # 0: shape outside its limits
+    if (c, vocab, cluster) in [(257, 256, 8), (20, 8, 2), (130, 64, 4), (257, 12, 8)]:
+      assert used == cluster and used_bwd == cluster
+  else:
+    assert used >= 1 and used_bwd >= 1
+    if (c, vocab) == (257, 256):
+      assert used == 8 and used_bwd == 8
+  v2 = run()
+
+  # against the one-CTA kernels
+  npt.assert_array_equal(np.isfinite(v2['loss']), np.isfinite(v1['loss']))
+  fin = np.isfinite(v1['loss'])
+  npt.assert_allclose(v2['loss'][fin], v1['loss'][fin], rtol=1e-5, atol=1e-5)
+  npt.assert_allclose(v2['grad'][fin], v1['grad'][fin], rtol=1e-4, atol=2e-6)
+  for name in ['Log', 'MaxTropical', 'Real']:
+    d1, a1, g1 = v1[name]
+    d2, a2, g2 = v2[name]
+    f = np.isfinite(a1)
+    npt.assert_array_equal(np.isfinite(a2), f, err_msg=name)
+    if name == 'MaxTropical':
+      npt.assert_array_equal(d2, d1)
+      npt.assert_array_equal(a2[f], a1[f])
+      npt.assert_array_equal(g2, g1)          # same winning arcs, ties included
+    else:
+      npt.assert_allclose(d2, d1, rtol=1e-5, atol=1e-6, err_msg=name)
+      npt.assert_allclose(a2[f], a1[f], rtol=1e-5, atol=1e-5, err_msg=name)
+      npt.assert_allclose(g2, g1, rtol=1e-4, atol=2e-6, err_msg=name)
+  for x, y in zip(v1['path'], v2['path']):
+    npt.assert_array_equal(y, x)
+
+  # against the fp64 oracle
+  tab64 = table_np.astype(np.float64)
+  blank, lex = np.ascontiguousarray(tab64[..., 0]), np.ascontiguousarray(tab64[..., 1:])
+  with np.errstate(all='ignore'):
+    o_loss, o_gb, o_gl = O.lattice_loss_and_grads(blank, lex, nf, labels, nl, octx, 0, True)
+  ofin = np.isfinite(o_loss)
+  npt.assert_array_equal(np.isfinite(v2['loss']), ofin)
+  npt.assert_allclose(v2['loss'][ofin], o_loss[ofin], rtol=1e-5, atol=1e-5)
+  npt.assert_allclose(v2['grad'][ofin][..., 0], o_gb[ofin], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(v2['grad'][ofin][..., 1:], o_gl[ofin], rtol=1e-4, atol=1e-5)
+  for name, sr in [('Log', O.LOG), ('MaxTropical', O.MAXTROPICAL)]:
+    with np.errstate(all='ignore'):
+      o_dist, o_alphas = O.lattice_forward(blank, lex, nf, octx, sr, 0, True)
+    d2, a2, _ = v2[name]
+    npt.assert_allclose(d2, o_dist, rtol=1e-5, atol=1e-5, err_msg=name)
+    f2 = np.isfinite(o_alphas)
+    npt.assert_array_equal(np.isfinite(a2), f2)
+    npt.assert_allclose(a2[f2], o_alphas[f2], rtol=1e-5, atol=2e-4, err_msg=name)
