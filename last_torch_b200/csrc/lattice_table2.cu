@@ -11,16 +11,21 @@
 //   * forward: destination-major PULL restricted to the local slab.  The global CSR of
 //     incoming arcs is ascending in p V + y inside a destination, so the arcs of destination
 //     q that start in this CTA's rows are a contiguous piece of q's segment; the pieces are
-//     found once by binary search and copied to shared memory as 16-bit slab offsets.  Every
-//     thread reduces the local arcs of its destinations (no atomics in any semiring, first
-//     arg-max in flat-arc order), writes a partial (m, s) / (max, arc) / sum, and after ONE
-//     cluster barrier every CTA merges the CL partials of every destination in rank order
-//     (= ascending arc order) -- all CTAs hold the full new alpha, nothing is broadcast;
+//     found once by binary search and kept in shared memory as 16-bit slab offsets in ELL
+//     order (a warp reads consecutive halfwords; arcs beyond the average in-degree + 1 stay in
+//     global memory).  One thread per destination reduces its local arcs (no atomics in any
+//     semiring, first arg-max in flat-arc order) and sends the partial VALUE -- one float --
+//     to every CTA of the cluster with st.async; every CTA merges the CL partials of every
+//     destination in rank order (= ascending arc order), so all CTAs hold the full new alpha
+//     and the CTA that holds a MaxTropical winner writes its back-pointer;
 //   * backward: source-major, one warp per local row, beta'[table[p, y]] a shared-memory
-//     gather, ONE exponential per arc for the row log-sum-exp and the arc posterior; the new
-//     beta of a row is stored into every CTA's buffer, ONE cluster barrier per frame;
-//   * partial / beta buffers alternate per frame, so the single barrier also covers the
-//     write-after-read hazards, and the slab stage of a frame is refilled right after it.
+//     gather (the slab of the table is kept in shared memory as 16-bit states), ONE
+//     exponential per arc for the row log-sum-exp and the arc posterior; the new beta of a
+//     row goes to every CTA's buffer with st.async;
+//   * no cluster barrier inside either loop: the st.async stores complete the transaction
+//     count of the receiver's mbarrier (as in lattice_fast2.cu); partial / beta buffers and
+//     their mbarriers alternate per frame, and a slab stage is refilled as soon as the frame
+//     that used it is known to be finished.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -35,9 +40,10 @@ namespace {
 using namespace fastptx;
 
 constexpr int kT2Threads = 256;
-constexpr int kT2Warps = kT2Threads / 32;
 constexpr int kT2MaxQ = 4;          // destinations per thread in the forward kernel
 constexpr int kT2MaxStages = 4;
+constexpr int kT2MaxThreads = 512;  // forward: one thread per destination where C allows
+constexpr int kT2MaxCluster = 8;
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int lo, int hi,
                                                int key) {
@@ -47,21 +53,61 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
   }
   return lo;
 }
-__device__ __forceinline__ float2 ld_cluster_f2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr)
-               : "memory");
-  return v;
+constexpr int kT2CachedThreads = 320;   // register-cached forward: two CTAs per SM
+constexpr int kT2Cache = 36;        // arcs per destination a thread can keep in registers
+constexpr float kClampLow = -3.0e38f;
+
+// (+) over `ne` arcs of one destination.  fetch(i) = (local source row << 16) | slab offset.
+// Log works in LOG2 units (src is alpha * log2 e): one FFMA per arc, a clamped running
+// maximum (never -inf, so no special cases) and bare ex2; value = m + log2(s).
+template <int SR, int NMAX, typename F>
+__device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __restrict__ src,
+                                             const float* __restrict__ slab, int base,
+                                             float& m, float& s, int& arg) {
+  using S = Sr<SR>;
+#pragma unroll
+  for (int i = 0; i < NMAX; i += 4) {
+    if (i >= ne) break;
+    float x[4];
+    uint32_t pk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i + u < ne) {
+        pk[u] = fetch(i + u);
+        const float w = slab[pk[u] & 0xffffu], a = src[pk[u] >> 16];
+        x[u] = SR == LT_LOG ? fmaf(w, kLog2e, a) : S::times(a, w);
+      } else {
+        pk[u] = 0;
+        x[u] = S::zero();
+      }
+    }
+    if constexpr (SR == LT_LOG) {
+      const float mn = fmaxf(m, fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+      s = fmaf(s, ex2(m - mn), (ex2(x[0] - mn) + ex2(x[1] - mn)) + (ex2(x[2] - mn) + ex2(x[3] - mn)));
+      m = mn;
+    } else if constexpr (SR == LT_MAXTROPICAL) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (x[u] > m) { m = x[u]; arg = base + (int)(pk[u] & 0xffffu); }   // ascending: first max
+    } else {
+      s += (x[0] + x[1]) + (x[2] + x[3]);
+    }
+  }
 }
 
 // ============================================================== forward ==
-template <int SR>
-__global__ void __launch_bounds__(kT2Threads)
-table_forward2_kernel(const TableParams p, const int R, const int NS, const uint32_t magic) {
+// Partial of one destination over the local slab, as ONE float: the (+)-value itself
+// (Log: msafe(m) + log s).  The winning arc of a MaxTropical partial stays in a register of
+// the thread that found it: every CTA merges the same CL values in rank order, so each CTA
+// knows whether it holds the winner and writes the back-pointer itself.
+template <int SR, bool CACHED>
+__global__ void __launch_bounds__(CACHED ? kT2CachedThreads : kT2MaxThreads, CACHED ? 2 : 1)
+table_forward2_kernel(const TableParams p, const int R, const int NS, const uint32_t magic,
+                      const int ell) {
   using S = Sr<SR>;
   extern __shared__ __align__(128) unsigned char t2sm[];
   const int C = p.C, V = p.V, Cp = (C + 3) & ~3;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nth = blockDim.x;
   const uint32_t rank = cluster_ctarank(), CL = cluster_nctarank();
   const int b = blockIdx.x / CL;
   const int row0 = rank * R, nrows = min(R, C - row0);
@@ -72,44 +118,48 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
   float* slabs = reinterpret_cast<float*>(t2sm);
   unsigned char* ptr = t2sm + (size_t)NS * stage_floats * 4;
   float* alpha = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * Cp * 4;
-  float2* part = reinterpret_cast<float2*>(ptr); ptr += (size_t)2 * Cp * 8;
-  int* seg_lo = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;
-  int* seg_n = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += kT2MaxStages * 8;
-  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // [nrows * V] slab offsets
+  float* part = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * kT2MaxCluster * Cp * 4;   // [2][CL][Cp]
+  int* seg_g = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // global start of the piece
+  int* seg_n = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // arcs in the piece
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += (kT2MaxStages + 2) * 8;
+  uint64_t* xbar = bars + kT2MaxStages;
+  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // ELL: arcs[i * Cp + q], i < ell
 
   const int nf = max(0, min(p.num_frames[b], p.T));
   const size_t bt0 = (size_t)b * p.T;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    mbar_init(smem_u32(&xbar[0]), 1);
+    mbar_init(smem_u32(&xbar[1]), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  // local piece of every destination's arc segment (global positions in seg_lo for now)
-  for (int q = tid; q < C; q += kT2Threads) {
+  // local piece of every destination's arc segment; its first `ell` arcs as 16-bit slab
+  // offsets in ELL order (a warp reads consecutive halfwords), the rest stays in global memory
+  for (int q = tid; q < C; q += nth) {
     const int lo = p.in_offsets[q], hi = p.in_offsets[q + 1];
     const int a0 = lower_bound_i32(p.in_arcs, lo, hi, base);
     const int a1 = lower_bound_i32(p.in_arcs, a0, hi, lim);
-    seg_lo[q] = a0;
+    seg_g[q] = a0;
     seg_n[q] = a1 - a0;
+    const int ne = min(a1 - a0, ell);
+    for (int i = 0; i < ne; ++i) arcs[(size_t)i * Cp + q] = (uint16_t)(p.in_arcs[a0 + i] - base);
   }
-  for (int c = tid; c < C; c += kT2Threads)
-    alpha[c] = p.alpha_init ? p.alpha_init[(size_t)b * C + c] : (c == 0 ? S::one() : S::zero());
+  for (int c = tid; c < C; c += nth)
+    alpha[c] = to_dom<SR>(p.alpha_init ? p.alpha_init[(size_t)b * C + c]
+                                       : (c == 0 ? S::one() : S::zero()));
   __syncthreads();
-  int* gpos = reinterpret_cast<int*>(part);                 // scratch: global segment starts
-  for (int q = tid; q < C; q += kT2Threads) gpos[q] = seg_lo[q];
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int q = 0; q < C; ++q) { seg_lo[q] = run; run += seg_n[q]; }
+  // CACHED (one destination per thread, <= kT2Cache local arcs): the arc list in registers
+  uint32_t ar[CACHED ? kT2Cache : 1];
+  if constexpr (CACHED) {
+    const int ne = tid < C ? min(seg_n[tid], ell) : 0;
+#pragma unroll
+    for (int i = 0; i < kT2Cache; ++i) {
+      const uint32_t a = i < ne ? arcs[(size_t)i * Cp + tid] : 0u;
+      ar[i] = (__umulhi(a, magic) << 16) | a;
+    }
   }
-  __syncthreads();
-  for (int q = tid; q < C; q += kT2Threads) {
-    const int n = seg_n[q], g0 = gpos[q], l0 = seg_lo[q];
-    for (int i = 0; i < n; ++i) arcs[l0 + i] = (uint16_t)(p.in_arcs[g0 + i] - base);
-  }
-  __syncthreads();
   cluster_sync_all();
 
   auto issue = [&](int t) {
@@ -126,76 +176,112 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
   float* nxt = alpha + Cp;
   for (int t = 0; t < nf; ++t) {
     const int stage = t % NS;
-    float2* pbuf = part + (size_t)(t & 1) * Cp;
+    float* pbuf = part + (size_t)(t & 1) * kT2MaxCluster * Cp;
+    uint64_t* xb = &xbar[t & 1];
+    if (tid == 0) {
+      // every thread passed the barrier that ended frame t-1: its stage is free
+      if (t > 0 && t - 1 + NS < nf) issue(t - 1 + NS);
+      mbar_arrive_expect_tx(smem_u32(xb), (uint32_t)C * CL * 4);
+    }
     float bl[kT2MaxQ];
+    int warc[kT2MaxQ];
 #pragma unroll
     for (int j = 0; j < kT2MaxQ; ++j) {
-      const int q = tid + j * kT2Threads;
+      const int q = tid + j * nth;
       bl[j] = q < C ? ldg_stream(p.blank + (bt0 + t) * C + q) : 0.f;
+      warc[j] = 0;
     }
     mbar_wait(smem_u32(&bars[stage]), (t / NS) & 1);
     const float* slab = slabs + (size_t)stage * stage_floats;
     const float* src = cur + row0;
 #pragma unroll
     for (int j = 0; j < kT2MaxQ; ++j) {
-      const int q = tid + j * kT2Threads;
+      const int q = tid + j * nth;
       if (q >= C) break;
-      if (p.alphas && (uint32_t)q % CL == rank) p.alphas[(bt0 + t) * C + q] = cur[q];
-      const uint16_t* al = arcs + seg_lo[q];
+      if (p.alphas && (uint32_t)q % CL == rank)
+        p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
       const int n = seg_n[q];
-      Acc<SR> acc;
-      acc.init();
-      int i = 0;
-      if constexpr (SR == LT_LOG) {
-        for (; i + 4 <= n; i += 4) {
-          float x[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t a = al[i + u];
-            x[u] = src[__umulhi(a, magic)] + slab[a];
+      const int ne = min(n, ell);
+      float m = SR == LT_LOG ? kClampLow : neg_inf(), sum = 0.f;
+      int arg = 0;
+      if constexpr (CACHED) {
+        reduce_piece<SR, kT2Cache>([&](int i) { return ar[i]; }, ne, src, slab, base, m, sum, arg);
+      } else {
+        const uint16_t* al = arcs + q;
+        for (int i0 = 0; i0 < ne; i0 += 32)
+          reduce_piece<SR, 32>([&](int i) {
+            const uint32_t a = al[(size_t)(i0 + i) * Cp];
+            return (__umulhi(a, magic) << 16) | a;
+          }, ne - i0, src, slab, base, m, sum, arg);
+      }
+      if (n > ell) {                                   // overflow of a high in-degree state
+        const int32_t* ga = p.in_arcs + seg_g[q];
+        for (int i = ell; i < n; ++i) {
+          const uint32_t a = (uint32_t)(ga[i] - base);
+          const float w = slab[a], av = src[a / (uint32_t)V];
+          if constexpr (SR == LT_LOG) {
+            const float x = fmaf(w, kLog2e, av), mn = fmaxf(m, x);
+            sum = fmaf(sum, ex2(m - mn), ex2(x - mn));
+            m = mn;
+          } else if constexpr (SR == LT_MAXTROPICAL) {
+            const float x = av + w;
+            if (x > m) { m = x; arg = base + (int)a; }
+          } else {
+            sum = fmaf(av, w, sum);
           }
-          acc.add_chunk(x, fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
         }
       }
-      for (; i < n; ++i) {
-        const uint32_t a = al[i];
-        acc.add(S::times(src[__umulhi(a, magic)], slab[a]), base + (int)a);
-      }
-      float2 out;
-      if constexpr (SR == LT_LOG) out = make_float2(acc.m, acc.s);
-      else if constexpr (SR == LT_MAXTROPICAL) out = make_float2(acc.m, __int_as_float(acc.a));
-      else out = make_float2(acc.s, 0.f);
-      pbuf[q] = out;
+      warc[j] = arg;
+      const float pv = SR == LT_LOG ? m + __log2f(sum) : (SR == LT_MAXTROPICAL ? m : sum);
+      // all-to-all: slot [my rank][q] of every CTA's buffer, 4 bytes of its transaction count
+      const uint32_t dst = smem_u32(&pbuf[(size_t)rank * Cp + q]), bb = smem_u32(xb);
+      for (uint32_t r = 0; r < CL; ++r)
+        st_async_f32(map_shared_rank(dst, r), pv, map_shared_rank(bb, r));
     }
-    __syncwarp();
-    cluster_sync_all();      // partials of every CTA visible; this CTA is done with the stage
-    if (tid == 0 && t + NS < nf) issue(t + NS);
+    mbar_wait(smem_u32(xb), (t >> 1) & 1);     // the partials of every CTA have landed
 
 #pragma unroll
     for (int j = 0; j < kT2MaxQ; ++j) {
-      const int q = tid + j * kT2Threads;
+      const int q = tid + j * nth;
       if (q >= C) break;
-      const uint32_t mine = smem_u32(&pbuf[q]);
-      Acc<SR> tot;
-      tot.init();
-      for (uint32_t r = 0; r < CL; ++r) {
-        const float2 pr = ld_cluster_f2(map_shared_rank(mine, r));
-        Acc<SR> o;
-        if constexpr (SR == LT_LOG) { o.m = pr.x; o.s = pr.y; }
-        else if constexpr (SR == LT_MAXTROPICAL) { o.m = pr.x; o.a = __float_as_int(pr.y); }
-        else { o.s = pr.x; }
-        if (r == 0) tot = o; else tot.merge(o);
+      float pv[kT2MaxCluster];
+#pragma unroll
+      for (int r = 0; r < kT2MaxCluster; ++r)
+        pv[r] = (uint32_t)r < CL ? pbuf[(size_t)r * Cp + q] : S::zero();
+      float tot;
+      int win = 0;
+      if constexpr (SR == LT_LOG) {
+        float m = pv[0];
+#pragma unroll
+        for (int r = 1; r < kT2MaxCluster; ++r) m = fmaxf(m, pv[r]);
+        const float ms = fmaxf(m, kClampLow);
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < kT2MaxCluster; ++r) sum += ex2(pv[r] - ms);
+        tot = ms + __log2f(sum);
+      } else if constexpr (SR == LT_MAXTROPICAL) {
+        tot = pv[0];
+#pragma unroll
+        for (int r = 1; r < kT2MaxCluster; ++r)
+          if (pv[r] > tot) { tot = pv[r]; win = r; }   // strict: the lowest rank = lowest arc wins ties
+      } else {
+        tot = pv[0];
+#pragma unroll
+        for (int r = 1; r < kT2MaxCluster; ++r) tot += pv[r];
       }
-      const float a0 = S::times(cur[q], bl[j]);
+      const float a0 = S::times(cur[q], to_dom<SR>(bl[j]));
       float v;
       if constexpr (SR == LT_MAXTROPICAL) {
-        const float rr = tot.value();
-        const bool take_blank = a0 >= rr;            // semirings.py:363
-        v = take_blank ? a0 : rr;
-        if (p.backarc && (uint32_t)q % CL == rank)
-          p.backarc[(bt0 + t) * C + q] = take_blank ? -1 : tot.arg();
+        const bool take_blank = a0 >= tot;           // semirings.py:363
+        v = take_blank ? a0 : tot;
+        if (p.backarc) {
+          if (take_blank) { if ((uint32_t)q % CL == rank) p.backarc[(bt0 + t) * C + q] = -1; }
+          else if ((uint32_t)win == rank) p.backarc[(bt0 + t) * C + q] = warc[j];
+        }
+      } else if constexpr (SR == LT_LOG) {
+        v = log2_add_exp2(a0, tot);
       } else {
-        v = S::plus(a0, tot.value());
+        v = a0 + tot;
       }
       nxt[q] = v;
     }
@@ -203,16 +289,16 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
 
-  for (int c = tid; c < C; c += kT2Threads) {
+  for (int c = tid; c < C; c += nth) {
     if ((uint32_t)c % CL != rank) continue;
     if (p.alphas)
-      for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + c] = cur[c];
-    if (p.alpha_final) p.alpha_final[(size_t)b * C + c] = cur[c];
+      for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + c] = from_dom<SR>(cur[c]);
+    if (p.alpha_final) p.alpha_final[(size_t)b * C + c] = from_dom<SR>(cur[c]);
   }
   if (rank == 0 && tid < 32) {         // dist = (+)_c alpha_T[c]  (lattices.py:496)
     Acc<SR> acc;
     acc.init();
-    for (int c = tid; c < C; c += 32) acc.add(cur[c], c);
+    for (int c = tid; c < C; c += 32) acc.add(from_dom<SR>(cur[c]), c);
     for (int o = 16; o > 0; o >>= 1) {
       Acc<SR> other;
       if constexpr (SR == LT_LOG) {
@@ -228,10 +314,13 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
     }
     if (tid == 0) p.dist[b] = acc.value();
   }
-  cluster_sync_all();      // nobody leaves while its partials may still be read
+  cluster_sync_all();      // nobody leaves while stores into its buffers may be in flight
 }
 
 // ============================================================= backward ==
+// 8 lanes per row, 4 rows per warp, 32 rows per pass (as lattice_fast2.cu's K2): a lane holds
+// up to 32 arcs of its row in registers, so the row maximum and the row sum are 3-step
+// shuffles and every arc costs one FFMA + one FADD + one ex2.  Log works in LOG2 units on chip.
 template <int SR>
 __global__ void __launch_bounds__(kT2Threads)
 table_backward2_kernel(const TableParams p, const int R, const int NS) {
@@ -239,6 +328,7 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
   extern __shared__ __align__(128) unsigned char t2sm[];
   const int C = p.C, V = p.V, Cp = (C + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane >> 3, sl = lane & 7;                 // row within the warp, lane within the row
   const uint32_t rank = cluster_ctarank(), CL = cluster_nctarank();
   const int b = blockIdx.x / CL;
   const int row0 = rank * R, nrows = min(R, C - row0);
@@ -249,21 +339,25 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
   float* slabs = reinterpret_cast<float*>(t2sm);
   unsigned char* ptr = t2sm + (size_t)NS * stage_floats * 4;
   float* beta_buf = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * Cp * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += kT2MaxStages * 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += (kT2MaxStages + 2) * 8;
+  uint64_t* xbar = bars + kT2MaxStages;
   uint16_t* tbl = reinterpret_cast<uint16_t*>(ptr);         // [nrows * V] next states of the slab
 
   const int nf = max(0, min(p.num_frames[b], p.T));
   const size_t bt0 = (size_t)b * p.T;
   const float logz = p.dist_in[b];
+  const float logz_d = to_dom<SR>(logz);
   const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
   const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    mbar_init(smem_u32(&xbar[0]), 1);
+    mbar_init(smem_u32(&xbar[1]), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  for (int c = tid; c < 2 * Cp; c += kT2Threads) beta_buf[c] = S::one();   // lattices.py:789-790
+  for (int c = tid; c < 2 * Cp; c += kT2Threads) beta_buf[c] = to_dom<SR>(S::one());   // lattices.py:789-790
   for (int i = tid; i < nrows * V; i += kT2Threads) tbl[i] = (uint16_t)p.table[base + i];
   __syncthreads();
   cluster_sync_all();
@@ -287,22 +381,30 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
     for (int r = tid; r < nrows; r += kT2Threads) p.grad_blank[(bt0 + t) * C + row0 + r] = 0.f;
   }
 
-  // lane l of a warp fetches alpha_t[p], blank_t[p] of the warp's l-th row, one frame ahead
-  const int my_lr = warp + lane * kT2Warps;
-  float n_alpha = 0.f, n_blank = 0.f;
-  if (nf > 0 && my_lr < nrows) {
-    n_alpha = p.alphas_in[(bt0 + nf - 1) * C + row0 + my_lr];
-    n_blank = ldg_stream(p.blank + (bt0 + nf - 1) * C + row0 + my_lr);
-  }
+  // the row owner (lane sl == 0) fetches alpha_t[p], blank_t[p] of its rows in the first two
+  // passes one frame ahead
+  const int slot = warp * 4 + sub;
+  const bool own0 = sl == 0 && slot < nrows, own1 = sl == 0 && slot + 32 < nrows;
+  float n_alpha0 = 0.f, n_alpha1 = 0.f, n_blank0 = 0.f, n_blank1 = 0.f;
+  auto prefetch = [&](int t) {
+    const size_t o = (bt0 + t) * C + row0 + slot;
+    if (own0) { n_alpha0 = p.alphas_in[o]; n_blank0 = ldg_stream(p.blank + o); }
+    if (own1) { n_alpha1 = p.alphas_in[o + 32]; n_blank1 = ldg_stream(p.blank + o + 32); }
+  };
+  if (nf > 0) prefetch(nf - 1);
 
   for (int it = 0; it < nf; ++it) {
     const int t = nf - 1 - it;
     const int stage = it % NS;
-    const float c_alpha = n_alpha, c_blank = n_blank;
-    if (t > 0 && my_lr < nrows) {
-      n_alpha = p.alphas_in[(bt0 + t - 1) * C + row0 + my_lr];
-      n_blank = ldg_stream(p.blank + (bt0 + t - 1) * C + row0 + my_lr);
+    if (it > 0) {
+      // every row of the previous frame has arrived from every CTA: beta is complete and
+      // the slab stage of iteration it-1 is free
+      mbar_wait(smem_u32(&xbar[it & 1]), ((it - 1) >> 1) & 1);
+      if (tid == 0 && it - 1 + NS < nf) issue(it - 1 + NS);
     }
+    if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), (uint32_t)C * 4);
+    const float c_alpha0 = n_alpha0, c_alpha1 = n_alpha1, c_blank0 = n_blank0, c_blank1 = n_blank1;
+    if (t > 0) prefetch(t - 1);
     const float* beta = beta_buf + (size_t)(it & 1) * Cp;         // beta_{t+1}
     float* nxt = beta_buf + (size_t)((it + 1) & 1) * Cp;
     const float* alpha = p.alphas_in + (bt0 + t) * C;
@@ -311,111 +413,145 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
     float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
     mbar_wait(smem_u32(&bars[stage]), (it / NS) & 1);
     const float* slab = slabs + (size_t)stage * stage_floats;
-    for (int lr = warp; lr < nrows; lr += kT2Warps) {
-      const int prow = row0 + lr;
-      const int li = (lr - warp) / kT2Warps;                 // warp-uniform
-      const float a = li < 32 ? __shfl_sync(0xffffffffu, c_alpha, li) : alpha[prow];
-      const float bk = li < 32 ? __shfl_sync(0xffffffffu, c_blank, li) : ldg_stream(blank + prow);
-      const float* row = slab + (size_t)lr * V;
-      const uint16_t* trow = tbl + (size_t)lr * V;
+
+    for (int pass = 0; pass * 32 < nrows; ++pass) {
+      const int lr = pass * 32 + slot;
+      const bool live = lr < nrows;                  // uniform over the 8 lanes of a row
+      const int lrc = live ? lr : 0;
+      const int prow = row0 + lrc;
+      float a_own, k_own;
+      if (pass < 2) { a_own = pass ? c_alpha1 : c_alpha0; k_own = pass ? c_blank1 : c_blank0; }
+      else { a_own = alpha[prow]; k_own = ldg_stream(blank + prow); }
+      const float alpha_p = to_dom<SR>(__shfl_sync(0xffffffffu, a_own, lane & ~7));
+      const float* row = slab + (size_t)lrc * V;
+      const uint16_t* trow = tbl + (size_t)lrc * V;
       float* grow = gl + (size_t)prow * V;
       float rowv;
       if (V <= 256) {
-        // the whole row in registers: 8 values per lane
-        float x[8], bv[8];
+        float4 x[8];
+        float4 bv[SR == LT_REAL ? 8 : 1];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int y = lane + 32 * i;
-          if (y < V) {
-            bv[i] = beta[trow[y]];
-            x[i] = S::times(row[y], bv[i]);
+          const int c4 = (sl + 8 * i) * 4;
+          if (c4 < V) {
+            const float4 w = *reinterpret_cast<const float4*>(row + c4);
+            const uint2 tq = *reinterpret_cast<const uint2*>(trow + c4);
+            const float4 bn = make_float4(beta[tq.x & 0xffffu], beta[tq.x >> 16],
+                                          beta[tq.y & 0xffffu], beta[tq.y >> 16]);
+            x[i] = make_float4(arc<SR>(w.x, bn.x), arc<SR>(w.y, bn.y), arc<SR>(w.z, bn.z),
+                               arc<SR>(w.w, bn.w));
+            if constexpr (SR == LT_REAL) bv[i] = bn;
           } else {
-            bv[i] = 0.f;
-            x[i] = S::zero();
+            const float z = SR == LT_LOG ? neg_inf() : 0.f;
+            x[i] = make_float4(z, z, z, z);
+            if constexpr (SR == LT_REAL) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if constexpr (SR == LT_LOG) {
-          float m = x[0];
+          float m = neg_inf();
 #pragma unroll
-          for (int i = 1; i < 8; ++i) m = fmaxf(m, x[i]);
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          for (int i = 0; i < 8; ++i)
+            m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
           const float ms = msafe(m);
-          const float rs = scale_ok ? gscale * fast_exp(a + ms - logz) : 0.f;
+          const float rs = scale_ok ? gscale * ex2(alpha_p + ms - logz_d) : 0.f;
           float s = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int y = lane + 32 * i;
-            const float e = fast_exp(x[i] - ms);
-            s += e;
-            if (y < V) __stcs(grow + y, e * rs);
+            const int c4 = (sl + 8 * i) * 4;
+            float4 e;
+            e.x = ex2(x[i].x - ms); e.y = ex2(x[i].y - ms);
+            e.z = ex2(x[i].z - ms); e.w = ex2(x[i].w - ms);
+            s += (e.x + e.y) + (e.z + e.w);
+            if (live && c4 < V)
+              stg_stream4(grow + c4, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
           }
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          rowv = ms + fast_log(s);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          rowv = ms + __log2f(s);
         } else {
-          const float ga = gscale * a;
+          const float ga = gscale * alpha_p;
           float s = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int y = lane + 32 * i;
-            s += x[i];
-            if (y < V) __stcs(grow + y, ga * bv[i]);
+            const int c4 = (sl + 8 * i) * 4;
+            s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+            if (live && c4 < V)
+              stg_stream4(grow + c4, make_float4(ga * bv[i].x, ga * bv[i].y, ga * bv[i].z, ga * bv[i].w));
           }
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
           rowv = s;
         }
       } else {
+        // wide vocabularies: two passes over the row in shared memory
         if constexpr (SR == LT_LOG) {
           float m = neg_inf();
-          for (int y = lane; y < V; y += 32) m = fmaxf(m, row[y] + beta[trow[y]]);
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          for (int y = sl; y < V; y += 8) m = fmaxf(m, arc<SR>(row[y], beta[trow[y]]));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
           const float ms = msafe(m);
-          const float rs = scale_ok ? gscale * fast_exp(a + ms - logz) : 0.f;
+          const float rs = scale_ok ? gscale * ex2(alpha_p + ms - logz_d) : 0.f;
           float s = 0.f;
-          for (int y = lane; y < V; y += 32) {
-            const float e = fast_exp(row[y] + beta[trow[y]] - ms);
+          for (int y = sl; y < V; y += 8) {
+            const float e = ex2(arc<SR>(row[y], beta[trow[y]]) - ms);
             s += e;
-            grow[y] = e * rs;
+            if (live) __stcs(grow + y, e * rs);
           }
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          rowv = ms + fast_log(s);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          rowv = ms + __log2f(s);
         } else {
-          const float ga = gscale * a;
+          const float ga = gscale * alpha_p;
           float s = 0.f;
-          for (int y = lane; y < V; y += 32) {
+          for (int y = sl; y < V; y += 8) {
             const float bvv = beta[trow[y]];
             s += row[y] * bvv;
-            grow[y] = ga * bvv;
+            if (live) __stcs(grow + y, ga * bvv);
           }
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
           rowv = s;
         }
       }
-      if (lane == 0) {
+      if (sl == 0 && live) {
         const float bp = beta[prow];
-        const float bb = S::times(bk, bp);
-        if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * fast_exp(a + bb - logz) : 0.f;
-        else gb[prow] = gscale * a * bp;
-        bcast_f32(nxt, prow, S::plus(bb, rowv), CL);
+        const float bb = arc<SR>(k_own, bp);
+        if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz_d) : 0.f;
+        else gb[prow] = gscale * a_own * bp;
+        xchg_store(nxt, prow, SR == LT_LOG ? log2_add_exp2(bb, rowv) : bb + rowv,
+                   &xbar[(it + 1) & 1], CL);
       }
     }
-    __syncwarp();
-    cluster_sync_all();      // beta_t complete everywhere; this CTA is done with the stage
-    if (tid == 0 && it + NS < nf) issue(it + NS);
   }
-  cluster_sync_all();
+  if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
+  cluster_sync_all();      // nobody leaves while stores into its buffers may be in flight
 }
 
 // ------------------------------------------------------------------ host ----
 struct T2Geom {
-  int CL, R, NS;
+  int CL, R, NS, threads, ell;
+  bool cached;
   size_t smem;
   uint32_t magic;
 };
 
+// ELL width of the forward kernel's arc lists: the average in-degree of a slab, plus one
+static int t2_ell(const TableParams& p, int R) { return (int)(((size_t)R * p.V + p.C - 1) / p.C) + 1; }
+
 static size_t t2_fixed_bytes(const TableParams& p, int R, bool backward) {
   const size_t Cp = (p.C + 3) & ~3;
-  if (backward) return 2 * Cp * 4 + kT2MaxStages * 8 + (((size_t)R * p.V * 2 + 15) & ~(size_t)15);
-  return 2 * Cp * 4 + 2 * Cp * 8 + 2 * Cp * 4 + kT2MaxStages * 8 + (((size_t)R * p.V * 2 + 15) & ~(size_t)15);
+  const size_t bars = (kT2MaxStages + 2) * 8;
+  if (backward) return 2 * Cp * 4 + bars + (((size_t)R * p.V * 2 + 15) & ~(size_t)15);
+  return 2 * Cp * 4 + 2 * kT2MaxCluster * Cp * 4 + 2 * Cp * 4 + bars +
+         (((size_t)t2_ell(p, R) * Cp * 2 + 15) & ~(size_t)15);
 }
 
 static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
@@ -424,7 +560,7 @@ static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
   if (p.V % 4 != 0) return false;                                   // 16-byte bulk copies
   if (reinterpret_cast<uintptr_t>(p.lexical) % 16 != 0) return false;
   if (backward && reinterpret_cast<uintptr_t>(p.grad_lexical) % 16 != 0) return false;
-  if (!backward && p.C > kT2Threads * kT2MaxQ) return false;
+  if (!backward && p.C > kT2MaxThreads * kT2MaxQ) return false;
   if (p.C > 65535) return false;                                    // 16-bit next states
   const char* env = getenv("LT_TABLE_CLUSTER");
   const int forced = env ? atoi(env) : 0;
@@ -441,6 +577,14 @@ static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
     int ns = (int)((budget - fixed) / slab);
     if (ns > kT2MaxStages) ns = kT2MaxStages;
     g->CL = cl; g->R = R; g->NS = ns;
+    g->ell = t2_ell(p, R);
+    g->threads = kT2Threads;
+    if (!backward) {                       // one thread per destination where C allows
+      g->threads = (p.C + 31) / 32 * 32;
+      if (g->threads < 128) g->threads = 128;
+      if (g->threads > kT2MaxThreads) g->threads = kT2MaxThreads;
+    }
+    g->cached = !backward && p.C <= g->threads && g->threads <= kT2CachedThreads && g->ell <= kT2Cache && !getenv("LT_TABLE_NO_CACHE");
     g->smem = fixed + (size_t)ns * slab;
     g->magic = (uint32_t)(((1ull << 32) + p.V - 1) / p.V);          // a / V for a < 2^16
     return true;
@@ -453,7 +597,7 @@ static int launch_t2(KernelT kernel, const T2Geom& g, int B, cudaStream_t stream
   LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * g.CL);
-  cfg.blockDim = dim3(kT2Threads);
+  cfg.blockDim = dim3(g.threads);
   cfg.dynamicSmemBytes = g.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -490,11 +634,15 @@ bool table2_backward_supported(const TableParams& p) {
 int table2_forward_launch(int semiring, const TableParams& p, cudaStream_t stream) {
   T2Geom g;
   if (!t2_geometry(p, false, &g)) { set_error("table cluster path: unsupported shape"); return LT_ERR_UNSUPPORTED; }
-  if (semiring == LT_LOG)
-    return launch_t2(table_forward2_kernel<LT_LOG>, g, p.B, stream, p, g.R, g.NS, g.magic);
-  if (semiring == LT_MAXTROPICAL)
-    return launch_t2(table_forward2_kernel<LT_MAXTROPICAL>, g, p.B, stream, p, g.R, g.NS, g.magic);
-  return launch_t2(table_forward2_kernel<LT_REAL>, g, p.B, stream, p, g.R, g.NS, g.magic);
+#define LT_T2F(SR)                                                                              \
+  return g.cached ? launch_t2(table_forward2_kernel<SR, true>, g, p.B, stream, p, g.R, g.NS,    \
+                              g.magic, g.ell)                                                   \
+                  : launch_t2(table_forward2_kernel<SR, false>, g, p.B, stream, p, g.R, g.NS,   \
+                              g.magic, g.ell)
+  if (semiring == LT_LOG) LT_T2F(LT_LOG);
+  if (semiring == LT_MAXTROPICAL) LT_T2F(LT_MAXTROPICAL);
+  LT_T2F(LT_REAL);
+#undef LT_T2F
 }
 
 int table2_backward_launch(int semiring, const TableParams& p, cudaStream_t stream) {
