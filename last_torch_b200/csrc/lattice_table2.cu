@@ -53,18 +53,38 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
   }
   return lo;
 }
-constexpr int kT2CachedThreads = 320;   // register-cached forward: two CTAs per SM
-constexpr int kT2Cache = 36;        // arcs per destination a thread can keep in registers
 constexpr float kClampLow = -3.0e38f;
 
-// (+) over `ne` arcs of one destination.  fetch(i) = (local source row << 16) | slab offset.
-// Log works in LOG2 units (src is alpha * log2 e): one FFMA per arc, a clamped running
-// maximum (never -inf, so no special cases) and bare ex2; value = m + log2(s).
+// 16 bytes to a peer CTA, completing 16 bytes of its mbarrier transaction count: a quarter of
+// the remote transactions (and of the serialised complete_tx updates) of four scalar stores
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::
+          "r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)),
+      "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(remote_bar)
+      : "memory");
+}
+
+// slab offset a (0xffff = padding) -> (4 * source state) << 18 | 4 * slab offset
+__device__ __forceinline__ uint32_t pack_arc(uint32_t a, uint32_t magic, int row0, int Cp) {
+  const bool pad = a == 0xffffu;
+  const uint32_t state = pad ? (uint32_t)Cp : (uint32_t)row0 + __umulhi(a, magic);
+  return (state << 20) | (pad ? 0u : a << 2);
+}
+
+// (+) over the arcs of one destination, four at a time without predicates.
+// fetch(i) = (4 * source state) << 18 | 4 * slab offset; the lists are padded to a multiple of
+// four with arcs from a SENTINEL source state (alpha slot Cp, always the semiring zero), so a
+// padded arc contributes nothing.  Log works in LOG2 units (alpha * log2 e): one FFMA per
+// arc, a clamped running maximum (never -inf, so no special cases) and bare ex2;
+// value = m + log2(s).
 template <int SR, int NMAX, typename F>
-__device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __restrict__ src,
+__device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __restrict__ alpha,
                                              const float* __restrict__ slab, int base,
                                              float& m, float& s, int& arg) {
   using S = Sr<SR>;
+  const char* ab = reinterpret_cast<const char*>(alpha);
+  const char* sb = reinterpret_cast<const char*>(slab);
 #pragma unroll
   for (int i = 0; i < NMAX; i += 4) {
     if (i >= ne) break;
@@ -72,14 +92,10 @@ __device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __res
     uint32_t pk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (i + u < ne) {
-        pk[u] = fetch(i + u);
-        const float w = slab[pk[u] & 0xffffu], a = src[pk[u] >> 16];
-        x[u] = SR == LT_LOG ? fmaf(w, kLog2e, a) : S::times(a, w);
-      } else {
-        pk[u] = 0;
-        x[u] = S::zero();
-      }
+      pk[u] = fetch(i + u);
+      const float w = *reinterpret_cast<const float*>(sb + (pk[u] & 0x3ffffu));
+      const float a = *reinterpret_cast<const float*>(ab + (pk[u] >> 18));
+      x[u] = SR == LT_LOG ? fmaf(w, kLog2e, a) : S::times(a, w);
     }
     if constexpr (SR == LT_LOG) {
       const float mn = fmaxf(m, fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
@@ -88,7 +104,7 @@ __device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __res
     } else if constexpr (SR == LT_MAXTROPICAL) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (x[u] > m) { m = x[u]; arg = base + (int)(pk[u] & 0xffffu); }   // ascending: first max
+        if (x[u] > m) { m = x[u]; arg = base + (int)((pk[u] & 0x3ffffu) >> 2); }   // ascending: first max
     } else {
       s += (x[0] + x[1]) + (x[2] + x[3]);
     }
@@ -100,8 +116,8 @@ __device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __res
 // (Log: msafe(m) + log s).  The winning arc of a MaxTropical partial stays in a register of
 // the thread that found it: every CTA merges the same CL values in rank order, so each CTA
 // knows whether it holds the winner and writes the back-pointer itself.
-template <int SR, bool CACHED>
-__global__ void __launch_bounds__(CACHED ? kT2CachedThreads : kT2MaxThreads, CACHED ? 2 : 1)
+template <int SR>
+__global__ void __launch_bounds__(kT2MaxThreads)
 table_forward2_kernel(const TableParams p, const int R, const int NS, const uint32_t magic,
                       const int ell) {
   using S = Sr<SR>;
@@ -117,13 +133,13 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
 
   float* slabs = reinterpret_cast<float*>(t2sm);
   unsigned char* ptr = t2sm + (size_t)NS * stage_floats * 4;
-  float* alpha = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * Cp * 4;
+  float* alpha = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * (Cp + 4) * 4;   // slot Cp: sentinel
   float* part = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * kT2MaxCluster * Cp * 4;   // [2][CL][Cp]
   int* seg_g = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // global start of the piece
   int* seg_n = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // arcs in the piece
   uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += (kT2MaxStages + 2) * 8;
   uint64_t* xbar = bars + kT2MaxStages;
-  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // ELL: arcs[i * Cp + q], i < ell
+  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // ELL: arcs[i * Cp + q], i < ell; 0xffff = padding
 
   const int nf = max(0, min(p.num_frames[b], p.T));
   const size_t bt0 = (size_t)b * p.T;
@@ -145,21 +161,13 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
     seg_n[q] = a1 - a0;
     const int ne = min(a1 - a0, ell);
     for (int i = 0; i < ne; ++i) arcs[(size_t)i * Cp + q] = (uint16_t)(p.in_arcs[a0 + i] - base);
+    for (int i = ne; i < ell; ++i) arcs[(size_t)i * Cp + q] = 0xffffu;
   }
+  if (tid < 2) alpha[(size_t)tid * (Cp + 4) + Cp] = to_dom<SR>(S::zero());
   for (int c = tid; c < C; c += nth)
     alpha[c] = to_dom<SR>(p.alpha_init ? p.alpha_init[(size_t)b * C + c]
                                        : (c == 0 ? S::one() : S::zero()));
   __syncthreads();
-  // CACHED (one destination per thread, <= kT2Cache local arcs): the arc list in registers
-  uint32_t ar[CACHED ? kT2Cache : 1];
-  if constexpr (CACHED) {
-    const int ne = tid < C ? min(seg_n[tid], ell) : 0;
-#pragma unroll
-    for (int i = 0; i < kT2Cache; ++i) {
-      const uint32_t a = i < ne ? arcs[(size_t)i * Cp + tid] : 0u;
-      ar[i] = (__umulhi(a, magic) << 16) | a;
-    }
-  }
   cluster_sync_all();
 
   auto issue = [&](int t) {
@@ -173,15 +181,19 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
     for (int t = 0; t < NS && t < nf; ++t) issue(t);
 
   float* cur = alpha;
-  float* nxt = alpha + Cp;
+  float* nxt = alpha + (Cp + 4);
+  bool mine[kT2MaxQ];                  // this CTA writes the outputs of destination q
+#pragma unroll
+  for (int j = 0; j < kT2MaxQ; ++j) mine[j] = (uint32_t)(tid + j * nth) % CL == rank;
+  int stage = 0;
+  uint32_t parity = 0;
   for (int t = 0; t < nf; ++t) {
-    const int stage = t % NS;
     float* pbuf = part + (size_t)(t & 1) * kT2MaxCluster * Cp;
     uint64_t* xb = &xbar[t & 1];
     if (tid == 0) {
       // every thread passed the barrier that ended frame t-1: its stage is free
       if (t > 0 && t - 1 + NS < nf) issue(t - 1 + NS);
-      mbar_arrive_expect_tx(smem_u32(xb), (uint32_t)C * CL * 4);
+      mbar_arrive_expect_tx(smem_u32(xb), (uint32_t)Cp * CL * 4);
     }
     float bl[kT2MaxQ];
     int warc[kT2MaxQ];
@@ -191,34 +203,32 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
       bl[j] = q < C ? ldg_stream(p.blank + (bt0 + t) * C + q) : 0.f;
       warc[j] = 0;
     }
-    mbar_wait(smem_u32(&bars[stage]), (t / NS) & 1);
+    mbar_wait(smem_u32(&bars[stage]), parity);
     const float* slab = slabs + (size_t)stage * stage_floats;
-    const float* src = cur + row0;
+    if (++stage == NS) { stage = 0; parity ^= 1; }
 #pragma unroll
     for (int j = 0; j < kT2MaxQ; ++j) {
       const int q = tid + j * nth;
-      if (q >= C) break;
-      if (p.alphas && (uint32_t)q % CL == rank)
-        p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
+      if (q - (tid & 31) >= C) break;                  // warp-uniform
+      float pv = S::zero();
+      if (q < C) {
+      if (p.alphas && mine[j]) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
       const int n = seg_n[q];
       const int ne = min(n, ell);
       float m = SR == LT_LOG ? kClampLow : neg_inf(), sum = 0.f;
       int arg = 0;
-      if constexpr (CACHED) {
-        reduce_piece<SR, kT2Cache>([&](int i) { return ar[i]; }, ne, src, slab, base, m, sum, arg);
-      } else {
+      {
         const uint16_t* al = arcs + q;
         for (int i0 = 0; i0 < ne; i0 += 32)
           reduce_piece<SR, 32>([&](int i) {
-            const uint32_t a = al[(size_t)(i0 + i) * Cp];
-            return (__umulhi(a, magic) << 16) | a;
-          }, ne - i0, src, slab, base, m, sum, arg);
+            return pack_arc(al[(size_t)(i0 + i) * Cp], magic, row0, Cp);
+          }, ne - i0, cur, slab, base, m, sum, arg);
       }
       if (n > ell) {                                   // overflow of a high in-degree state
         const int32_t* ga = p.in_arcs + seg_g[q];
         for (int i = ell; i < n; ++i) {
           const uint32_t a = (uint32_t)(ga[i] - base);
-          const float w = slab[a], av = src[a / (uint32_t)V];
+          const float w = slab[a], av = cur[row0 + a / (uint32_t)V];
           if constexpr (SR == LT_LOG) {
             const float x = fmaf(w, kLog2e, av), mn = fmaxf(m, x);
             sum = fmaf(sum, ex2(m - mn), ex2(x - mn));
@@ -232,11 +242,22 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
         }
       }
       warc[j] = arg;
-      const float pv = SR == LT_LOG ? m + __log2f(sum) : (SR == LT_MAXTROPICAL ? m : sum);
-      // all-to-all: slot [my rank][q] of every CTA's buffer, 4 bytes of its transaction count
-      const uint32_t dst = smem_u32(&pbuf[(size_t)rank * Cp + q]), bb = smem_u32(xb);
-      for (uint32_t r = 0; r < CL; ++r)
-        st_async_f32(map_shared_rank(dst, r), pv, map_shared_rank(bb, r));
+      pv = SR == LT_LOG ? m + __log2f(sum) : (SR == LT_MAXTROPICAL ? m : sum);
+      }
+      // all-to-all, four destinations per store: lane k of a quad sends the quad's 16 bytes to
+      // ranks k, k + 4: slot [my rank][q0..q0+3] of their buffers
+      const int lane = tid & 31, qb = lane & ~3;
+      float4 quad;
+      quad.x = __shfl_sync(0xffffffffu, pv, qb);
+      quad.y = __shfl_sync(0xffffffffu, pv, qb + 1);
+      quad.z = __shfl_sync(0xffffffffu, pv, qb + 2);
+      quad.w = __shfl_sync(0xffffffffu, pv, qb + 3);
+      const int q0 = q - (lane & 3);
+      if (q0 < C) {
+        const uint32_t dst = smem_u32(&pbuf[(size_t)rank * Cp + q0]), bb = smem_u32(xb);
+        for (uint32_t r = lane & 3; r < CL; r += 4)
+          st_async_v4(map_shared_rank(dst, r), quad, map_shared_rank(bb, r));
+      }
     }
     mbar_wait(smem_u32(xb), (t >> 1) & 1);     // the partials of every CTA have landed
 
@@ -269,13 +290,15 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
 #pragma unroll
         for (int r = 1; r < kT2MaxCluster; ++r) tot += pv[r];
       }
-      const float a0 = S::times(cur[q], to_dom<SR>(bl[j]));
+      float blv = bl[j];
+      asm volatile("" : "+f"(blv));    // first use of the load stays after the exchange wait
+      const float a0 = S::times(cur[q], to_dom<SR>(blv));
       float v;
       if constexpr (SR == LT_MAXTROPICAL) {
         const bool take_blank = a0 >= tot;           // semirings.py:363
         v = take_blank ? a0 : tot;
         if (p.backarc) {
-          if (take_blank) { if ((uint32_t)q % CL == rank) p.backarc[(bt0 + t) * C + q] = -1; }
+          if (take_blank) { if (mine[j]) p.backarc[(bt0 + t) * C + q] = -1; }
           else if ((uint32_t)win == rank) p.backarc[(bt0 + t) * C + q] = warc[j];
         }
       } else if constexpr (SR == LT_LOG) {
@@ -393,9 +416,10 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
   };
   if (nf > 0) prefetch(nf - 1);
 
+  int stage = 0;
+  uint32_t parity = 0;
   for (int it = 0; it < nf; ++it) {
     const int t = nf - 1 - it;
-    const int stage = it % NS;
     if (it > 0) {
       // every row of the previous frame has arrived from every CTA: beta is complete and
       // the slab stage of iteration it-1 is free
@@ -411,8 +435,9 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
     const float* blank = p.blank + (bt0 + t) * C;
     float* gb = p.grad_blank + (bt0 + t) * C;
     float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
-    mbar_wait(smem_u32(&bars[stage]), (it / NS) & 1);
+    mbar_wait(smem_u32(&bars[stage]), parity);
     const float* slab = slabs + (size_t)stage * stage_floats;
+    if (++stage == NS) { stage = 0; parity ^= 1; }
 
     for (int pass = 0; pass * 32 < nrows; ++pass) {
       const int lr = pass * 32 + slot;
@@ -538,19 +563,20 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
 // ------------------------------------------------------------------ host ----
 struct T2Geom {
   int CL, R, NS, threads, ell;
-  bool cached;
   size_t smem;
   uint32_t magic;
 };
 
 // ELL width of the forward kernel's arc lists: the average in-degree of a slab, plus one
-static int t2_ell(const TableParams& p, int R) { return (int)(((size_t)R * p.V + p.C - 1) / p.C) + 1; }
+static int t2_ell(const TableParams& p, int R) {
+  return ((int)(((size_t)R * p.V + p.C - 1) / p.C) + 1 + 3) & ~3;      // lists are read four at a time
+}
 
 static size_t t2_fixed_bytes(const TableParams& p, int R, bool backward) {
   const size_t Cp = (p.C + 3) & ~3;
   const size_t bars = (kT2MaxStages + 2) * 8;
   if (backward) return 2 * Cp * 4 + bars + (((size_t)R * p.V * 2 + 15) & ~(size_t)15);
-  return 2 * Cp * 4 + 2 * kT2MaxCluster * Cp * 4 + 2 * Cp * 4 + bars +
+  return 2 * (Cp + 4) * 4 + 2 * kT2MaxCluster * Cp * 4 + 2 * Cp * 4 + bars +
          (((size_t)t2_ell(p, R) * Cp * 2 + 15) & ~(size_t)15);
 }
 
@@ -584,7 +610,6 @@ static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
       if (g->threads < 128) g->threads = 128;
       if (g->threads > kT2MaxThreads) g->threads = kT2MaxThreads;
     }
-    g->cached = !backward && p.C <= g->threads && g->threads <= kT2CachedThreads && g->ell <= kT2Cache && !getenv("LT_TABLE_NO_CACHE");
     g->smem = fixed + (size_t)ns * slab;
     g->magic = (uint32_t)(((1ull << 32) + p.V - 1) / p.V);          // a / V for a < 2^16
     return true;
@@ -634,11 +659,8 @@ bool table2_backward_supported(const TableParams& p) {
 int table2_forward_launch(int semiring, const TableParams& p, cudaStream_t stream) {
   T2Geom g;
   if (!t2_geometry(p, false, &g)) { set_error("table cluster path: unsupported shape"); return LT_ERR_UNSUPPORTED; }
-#define LT_T2F(SR)                                                                              \
-  return g.cached ? launch_t2(table_forward2_kernel<SR, true>, g, p.B, stream, p, g.R, g.NS,    \
-                              g.magic, g.ell)                                                   \
-                  : launch_t2(table_forward2_kernel<SR, false>, g, p.B, stream, p, g.R, g.NS,   \
-                              g.magic, g.ell)
+#define LT_T2F(SR) \
+  return launch_t2(table_forward2_kernel<SR>, g, p.B, stream, p, g.R, g.NS, g.magic, g.ell)
   if (semiring == LT_LOG) LT_T2F(LT_LOG);
   if (semiring == LT_MAXTROPICAL) LT_T2F(LT_MAXTROPICAL);
   LT_T2F(LT_REAL);
