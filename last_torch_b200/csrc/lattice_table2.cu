@@ -39,7 +39,7 @@ namespace {
 
 using namespace fastptx;
 
-constexpr int kT2Threads = 256;
+constexpr int kT2BwdThreads = 288;  // backward: 36 rows per pass, two CTAs per SM
 constexpr int kT2MaxQ = 4;          // destinations per thread in the forward kernel
 constexpr int kT2MaxStages = 4;
 constexpr int kT2MaxThreads = 512;  // forward: one thread per destination where C allows
@@ -341,16 +341,18 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
 }
 
 // ============================================================= backward ==
-// 8 lanes per row, 4 rows per warp, 32 rows per pass (as lattice_fast2.cu's K2): a lane holds
+// 8 lanes per row, 4 rows per warp, blockDim / 8 rows per pass (as lattice_fast2.cu's K2; the
+// block is sized so that a slab of up to 36 rows is ONE pass): a lane holds
 // up to 32 arcs of its row in registers, so the row maximum and the row sum are 3-step
 // shuffles and every arc costs one FFMA + one FADD + one ex2.  Log works in LOG2 units on chip.
 template <int SR>
-__global__ void __launch_bounds__(kT2Threads)
+__global__ void __launch_bounds__(kT2BwdThreads, 2)
 table_backward2_kernel(const TableParams p, const int R, const int NS) {
   using S = Sr<SR>;
   extern __shared__ __align__(128) unsigned char t2sm[];
   const int C = p.C, V = p.V, Cp = (C + 3) & ~3;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int rpp = nth >> 3;                                 // rows per pass: 8 lanes per row
   const int sub = lane >> 3, sl = lane & 7;                 // row within the warp, lane within the row
   const uint32_t rank = cluster_ctarank(), CL = cluster_nctarank();
   const int b = blockIdx.x / CL;
@@ -380,8 +382,8 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
     fence_barrier_init();
     fence_proxy_async();
   }
-  for (int c = tid; c < 2 * Cp; c += kT2Threads) beta_buf[c] = to_dom<SR>(S::one());   // lattices.py:789-790
-  for (int i = tid; i < nrows * V; i += kT2Threads) tbl[i] = (uint16_t)p.table[base + i];
+  for (int c = tid; c < 2 * Cp; c += nth) beta_buf[c] = to_dom<SR>(S::one());   // lattices.py:789-790
+  for (int i = tid; i < nrows * V; i += nth) tbl[i] = (uint16_t)p.table[base + i];
   __syncthreads();
   cluster_sync_all();
 
@@ -399,20 +401,20 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
   // padding frames: zero gradients of this CTA's rows (lattices.py:775-779)
   for (int t = nf; t < p.T; ++t) {
     float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V + base;
-    for (int i = tid * 4; i < nrows * V; i += kT2Threads * 4)
+    for (int i = tid * 4; i < nrows * V; i += nth * 4)
       stg_stream4(gl + i, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int r = tid; r < nrows; r += kT2Threads) p.grad_blank[(bt0 + t) * C + row0 + r] = 0.f;
+    for (int r = tid; r < nrows; r += nth) p.grad_blank[(bt0 + t) * C + row0 + r] = 0.f;
   }
 
   // the row owner (lane sl == 0) fetches alpha_t[p], blank_t[p] of its rows in the first two
   // passes one frame ahead
   const int slot = warp * 4 + sub;
-  const bool own0 = sl == 0 && slot < nrows, own1 = sl == 0 && slot + 32 < nrows;
+  const bool own0 = sl == 0 && slot < nrows, own1 = sl == 0 && slot + rpp < nrows;
   float n_alpha0 = 0.f, n_alpha1 = 0.f, n_blank0 = 0.f, n_blank1 = 0.f;
   auto prefetch = [&](int t) {
     const size_t o = (bt0 + t) * C + row0 + slot;
     if (own0) { n_alpha0 = p.alphas_in[o]; n_blank0 = ldg_stream(p.blank + o); }
-    if (own1) { n_alpha1 = p.alphas_in[o + 32]; n_blank1 = ldg_stream(p.blank + o + 32); }
+    if (own1) { n_alpha1 = p.alphas_in[o + rpp]; n_blank1 = ldg_stream(p.blank + o + rpp); }
   };
   if (nf > 0) prefetch(nf - 1);
 
@@ -439,8 +441,9 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
     const float* slab = slabs + (size_t)stage * stage_floats;
     if (++stage == NS) { stage = 0; parity ^= 1; }
 
-    for (int pass = 0; pass * 32 < nrows; ++pass) {
-      const int lr = pass * 32 + slot;
+    for (int pass = 0; pass * rpp < nrows; ++pass) {
+      if (pass * rpp + warp * 4 >= nrows) break;       // warp-uniform: no live row left for this warp
+      const int lr = pass * rpp + slot;
       const bool live = lr < nrows;                  // uniform over the 8 lanes of a row
       const int lrc = live ? lr : 0;
       const int prow = row0 + lrc;
@@ -604,7 +607,9 @@ static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
     if (ns > kT2MaxStages) ns = kT2MaxStages;
     g->CL = cl; g->R = R; g->NS = ns;
     g->ell = t2_ell(p, R);
-    g->threads = kT2Threads;
+    g->threads = ((R + 3) / 4) * 32;       // backward: 8 lanes per row, one pass where R <= 36
+    if (g->threads < 128) g->threads = 128;
+    if (g->threads > kT2BwdThreads) g->threads = kT2BwdThreads;
     if (!backward) {                       // one thread per destination where C allows
       g->threads = (p.C + 31) / 32 * 32;
       if (g->threads < 128) g->threads = 128;
