@@ -65,36 +65,27 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
       : "memory");
 }
 
-// slab offset a (0xffff = padding) -> (4 * source state) << 18 | 4 * slab offset
-__device__ __forceinline__ uint32_t pack_arc(uint32_t a, uint32_t magic, int row0, int Cp) {
-  const bool pad = a == 0xffffu;
-  const uint32_t state = pad ? (uint32_t)Cp : (uint32_t)row0 + __umulhi(a, magic);
-  return (state << 20) | (pad ? 0u : a << 2);
-}
-
-// (+) over the arcs of one destination, four at a time without predicates.
-// fetch(i) = (4 * source state) << 18 | 4 * slab offset; the lists are padded to a multiple of
-// four with arcs from a SENTINEL source state (alpha slot Cp, always the semiring zero), so a
-// padded arc contributes nothing.  Log works in LOG2 units (alpha * log2 e): one FFMA per
-// arc, a clamped running maximum (never -inf, so no special cases) and bare ex2;
-// value = m + log2(s).
+// (+) over the arcs of one destination, four at a time without predicates.  fetch(i) = slab
+// offset of the i-th local arc; its source row is offset / V (one IMAD.HI with a magic
+// constant).  The lists are padded to a multiple of four with the offset ONE PAST the slab: that
+// float of every ring stage holds the semiring zero (the bulk copies never touch it), so a
+// padded arc contributes nothing whatever alpha it is paired with.  Log works in LOG2 units
+// (src is alpha * log2 e): one FFMA per arc, a clamped running maximum (never -inf, so no
+// special cases) and bare ex2; value = m + log2(s).
 template <int SR, int NMAX, typename F>
-__device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __restrict__ alpha,
-                                             const float* __restrict__ slab, int base,
-                                             float& m, float& s, int& arg) {
+__device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __restrict__ src,
+                                             const float* __restrict__ slab, uint32_t magic,
+                                             int base, float& m, float& s, int& arg) {
   using S = Sr<SR>;
-  const char* ab = reinterpret_cast<const char*>(alpha);
-  const char* sb = reinterpret_cast<const char*>(slab);
 #pragma unroll
   for (int i = 0; i < NMAX; i += 4) {
     if (i >= ne) break;
     float x[4];
-    uint32_t pk[4];
+    uint32_t off[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      pk[u] = fetch(i + u);
-      const float w = *reinterpret_cast<const float*>(sb + (pk[u] & 0x3ffffu));
-      const float a = *reinterpret_cast<const float*>(ab + (pk[u] >> 18));
+      off[u] = fetch(i + u);
+      const float w = slab[off[u]], a = src[__umulhi(off[u], magic)];
       x[u] = SR == LT_LOG ? fmaf(w, kLog2e, a) : S::times(a, w);
     }
     if constexpr (SR == LT_LOG) {
@@ -104,7 +95,7 @@ __device__ __forceinline__ void reduce_piece(F fetch, int ne, const float* __res
     } else if constexpr (SR == LT_MAXTROPICAL) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (x[u] > m) { m = x[u]; arg = base + (int)((pk[u] & 0x3ffffu) >> 2); }   // ascending: first max
+        if (x[u] > m) { m = x[u]; arg = base + (int)off[u]; }   // ascending: first max
     } else {
       s += (x[0] + x[1]) + (x[2] + x[3]);
     }
@@ -129,17 +120,17 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
   const int row0 = rank * R, nrows = min(R, C - row0);
   const int base = row0 * V, lim = (row0 + nrows) * V;
   const uint32_t slab_bytes = (uint32_t)nrows * V * 4;
-  const size_t stage_floats = (size_t)R * V;
+  const size_t stage_floats = (size_t)R * V + 4;            // + the padding arc's weight
 
   float* slabs = reinterpret_cast<float*>(t2sm);
   unsigned char* ptr = t2sm + (size_t)NS * stage_floats * 4;
-  float* alpha = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * (Cp + 4) * 4;   // slot Cp: sentinel
+  float* alpha = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * (Cp + 4) * 4;   // slots >= C: 0
   float* part = reinterpret_cast<float*>(ptr); ptr += (size_t)2 * kT2MaxCluster * Cp * 4;   // [2][CL][Cp]
   int* seg_g = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // global start of the piece
   int* seg_n = reinterpret_cast<int*>(ptr); ptr += (size_t)Cp * 4;     // arcs in the piece
   uint64_t* bars = reinterpret_cast<uint64_t*>(ptr); ptr += (kT2MaxStages + 2) * 8;
   uint64_t* xbar = bars + kT2MaxStages;
-  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // ELL: arcs[i * Cp + q], i < ell; 0xffff = padding
+  uint16_t* arcs = reinterpret_cast<uint16_t*>(ptr);        // ELL: arcs[i * Cp + q], i < ell; nrows * V = padding
 
   const int nf = max(0, min(p.num_frames[b], p.T));
   const size_t bt0 = (size_t)b * p.T;
@@ -161,9 +152,10 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
     seg_n[q] = a1 - a0;
     const int ne = min(a1 - a0, ell);
     for (int i = 0; i < ne; ++i) arcs[(size_t)i * Cp + q] = (uint16_t)(p.in_arcs[a0 + i] - base);
-    for (int i = ne; i < ell; ++i) arcs[(size_t)i * Cp + q] = 0xffffu;
+    for (int i = ne; i < ell; ++i) arcs[(size_t)i * Cp + q] = (uint16_t)(nrows * V);
   }
-  if (tid < 2) alpha[(size_t)tid * (Cp + 4) + Cp] = to_dom<SR>(S::zero());
+  if (tid < NS) slabs[(size_t)tid * stage_floats + (size_t)nrows * V] = S::zero();   // natural units
+  for (int c = C + tid; c < Cp + 4; c += nth) { alpha[c] = 0.f; alpha[(Cp + 4) + c] = 0.f; }
   for (int c = tid; c < C; c += nth)
     alpha[c] = to_dom<SR>(p.alpha_init ? p.alpha_init[(size_t)b * C + c]
                                        : (c == 0 ? S::one() : S::zero()));
@@ -220,9 +212,8 @@ table_forward2_kernel(const TableParams p, const int R, const int NS, const uint
       {
         const uint16_t* al = arcs + q;
         for (int i0 = 0; i0 < ne; i0 += 32)
-          reduce_piece<SR, 32>([&](int i) {
-            return pack_arc(al[(size_t)(i0 + i) * Cp], magic, row0, Cp);
-          }, ne - i0, cur, slab, base, m, sum, arg);
+          reduce_piece<SR, 32>([&](int i) { return (uint32_t)al[(size_t)(i0 + i) * Cp]; },
+                               ne - i0, cur + row0, slab, magic, base, m, sum, arg);
       }
       if (n > ell) {                                   // overflow of a high in-degree state
         const int32_t* ga = p.in_arcs + seg_g[q];
@@ -596,9 +587,9 @@ static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
   for (int cl = 1; cl <= 8; cl <<= 1) {
     const int R = (p.C + cl - 1) / cl;
     if ((cl - 1) * R >= p.C) continue;                              // a rank without rows
-    const size_t slab = (size_t)R * p.V * 4;
+    const size_t slab = (size_t)R * p.V * 4 + (backward ? 0 : 16);   // forward: + the padding arc's weight
     if (forced ? cl != forced : (slab > 40 * 1024 && cl < 8)) continue;
-    if (!backward && (size_t)R * p.V > 65535) return false;         // 16-bit slab offsets
+    if (!backward && (size_t)R * p.V + 1 > 65535) return false;     // 16-bit slab offsets
     const size_t fixed = t2_fixed_bytes(p, R, backward);
     size_t budget = 113 * 1024;                                     // two CTAs per SM
     if (fixed + 2 * slab > budget) budget = 227 * 1024;
