@@ -66,6 +66,28 @@ def test_capi_validates_arguments_without_a_gpu(lt):
                                  None, None, None, 0, None), 'lt_lattice_forward')
 
 
+def test_table_kernel_path_query_without_a_gpu(lt, monkeypatch):
+  """lt_table_lattice_cluster: which NextStateTable lattices run on the cluster kernels
+  (csrc/lattice_table2.cu) and with how many CTAs per utterance -- host logic only."""
+  from last_torch_b200 import _native as N
+  L = N.lib()
+  monkeypatch.delenv('LT_TABLE_V1', raising=False)
+  monkeypatch.delenv('LT_TABLE_CLUSTER', raising=False)
+  for backward in (0, 1):
+    assert L.lt_table_lattice_cluster(257, 256, -1, backward) == 8   # configs[1] geometry
+    assert L.lt_table_lattice_cluster(20, 8, -1, backward) == 1      # one small slab
+    assert L.lt_table_lattice_cluster(257, 256, 2, backward) == 0    # FrameLabelDependent
+    assert L.lt_table_lattice_cluster(300, 17, -1, backward) == 0    # rows are not 16-byte multiples
+    assert L.lt_table_lattice_cluster(0, 8, -1, backward) == 0
+    assert L.lt_table_lattice_cluster(1025, 32, -1, backward) == 4   # smallest cluster with slabs <= 40 KB
+    assert L.lt_table_lattice_cluster(4161, 64, -1, backward) == 0   # C > 2048 / two slabs exceed 227 KB
+  monkeypatch.setenv('LT_TABLE_CLUSTER', '2')
+  assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 2
+  assert L.lt_table_lattice_cluster(257, 256, -1, 0) == 0            # two slabs of 129 rows do not fit
+  monkeypatch.setenv('LT_TABLE_V1', '1')
+  assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 0
+
+
 def test_missing_library_fails_loudly(lt, monkeypatch):
   from last_torch_b200 import _native
   monkeypatch.setattr(_native, '_lib', None)
