@@ -14,8 +14,10 @@ from last_torch_b200 import ops, _native as N
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 FLAGS = [int(x) for x in sys.argv[3:]] or [0, 1]
-V, n, k = 64, 2, 2
-C = 1 + V + V * V
+# geometry overrides (e.g. LT_V=256 LT_N=1 LT_K=2: FrameLabelDependent on the configs[1] bigram)
+import os
+V, n, k = int(os.environ.get('LT_V', 64)), int(os.environ.get('LT_N', 2)), int(os.environ.get('LT_K', 2))
+C = sum(V ** i for i in range(n + 1))
 g = torch.Generator(device='cuda').manual_seed(0)
 blank = torch.randn([B, T, C], device='cuda', generator=g)
 lex = torch.randn([B, T, C, V], device='cuda', generator=g)
@@ -38,7 +40,7 @@ def timeit(fn, n=5):
 
 
 ref = None
-for kk, name in [(k, 'FrameLabelDependent(2)'), (-1, 'FrameDependent')]:
+for kk, name in [(k, f'FrameLabelDependent({k})'), (-1, 'FrameDependent')]:
   for flags in FLAGS:
     out = ops._lattice_forward_raw(N.MAXTROPICAL, V, n, kk, blank, lex, nf, flags, False, True)
     ms = timeit(lambda: ops._lattice_forward_raw(N.MAXTROPICAL, V, n, kk, blank, lex, nf, flags,
