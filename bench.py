@@ -22,8 +22,16 @@ One JSON line is printed by rank 0:
   cpu_baseline  the C/OpenMP port of the reference algorithm (oracle/) timed
                 on this box's host cores on a bounded sample (rank 0, N = 1).
 
+  extra_configs  the other BASELINE.json configs, each with ms / step and its
+                roofline fraction (configs[2]: trigram FrameLabelDependent(2)
+                MaxTropical + Viterbi; bigram FrameLabelDependent(2); a ragged
+                batch; the configs[4] per-GPU batch sweep), so that they are
+                driver-run numbers.  `--no-extras` skips them.
+
 `--impl reference` times that CPU port through the same frames -> loss -> grads
-path (numpy/BLAS joint network + C lattice recursion) and prints the same line.
+path (numpy/BLAS joint network + C lattice recursion) and prints the same line
+(`config` = the workload the GPU arm runs, `sample_config` = the bounded sample
+of it one CPU step covers).
 """
 
 import argparse
@@ -60,6 +68,7 @@ def parse_args():
   ap.add_argument('--ragged', action='store_true', help='num_frames ~ U{T/2..T}')
   ap.add_argument('--flags', type=int, default=0, help='kernel dispatch flags (last_lattice.h)')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='skip extra_configs')
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--cpu-seconds', type=float, default=12.0)
   return ap.parse_args()
@@ -249,7 +258,9 @@ def cpu_bounded_run(args, with_joint, seconds, reps=1):
   desc = (f'{b} utterances x {t_full} frames x {s["c"]} states, U={s["u"]}, '
           f'{"frames->JointWeightFn(numpy/BLAS)->" if with_joint else ""}lattice loss+grad '
           f'(C/OpenMP port of the reference algorithm), {dt:.2f} s per pass')
-  return units / dt, threads, desc, dt
+  sample = {'utterances': b, 'frames': t_full, 'states': s['c'], 'labels': s['u'],
+            'frames_x_states_per_step': units}
+  return units / dt, threads, desc, dt, sample
 
 
 def run_reference(args):
@@ -258,12 +269,16 @@ def run_reference(args):
     return
   steps = max(1, args.steps)
   per_step = min(args.cpu_seconds, 120.0 / (steps + max(args.warmup, 0) + 1))
-  val, threads, desc, dt = cpu_bounded_run(args, with_joint=True, seconds=per_step, reps=steps)
+  val, threads, desc, dt, sample = cpu_bounded_run(args, with_joint=True, seconds=per_step,
+                                                   reps=steps)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
       'steps': steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': config_dict(args, args.gpus),
+      # one CPU "step" is a bounded SAMPLE of that workload (same widths, fewer utterances and
+      # frames); ms_per_step is the time of one pass over the sample, value its rate
+      'sample_config': sample,
       'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                        'sample': desc},
       'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -277,6 +292,34 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+
+def kernel_name(name):
+  """C-ABI entry point -> the name the kernels are reported under (the *_norm / *_checked
+  variants are the same kernels with extra outputs)."""
+  return name.replace('_norm', '').replace('_checked', '')
+
+
+def ncu_traffic(kernel):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+  `ncu --set full` capture of this workload (profiles/r02_ncu_traffic.json), or (None, why) when
+  the kernel's source has changed since the capture."""
+  import hashlib
+  path = os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')
+  if not os.path.exists(path):
+    return None, 'no committed capture (profiles/r02_ncu_traffic.json)'
+  with open(path) as f:
+    doc = json.load(f)
+  ent = doc.get('kernels', {}).get(kernel)
+  if not ent:
+    return None, f'{kernel} not in profiles/r02_ncu_traffic.json'
+  src = os.path.join(ROOT, ent['source'])
+  with open(src, 'rb') as f:
+    digest = hashlib.sha256(f.read()).hexdigest()
+  if digest != ent['source_sha256']:
+    return None, (f'{ent["source"]} changed since the capture '
+                  f'({doc.get("capture", "profiles/")}): re-profile')
+  return float(ent['dram_bytes_per_launch']), doc.get('capture', 'profiles/r02_ncu_traffic.json')
+
 
 def run_b200(args):
   import torch
@@ -298,6 +341,7 @@ def run_b200(args):
 
   import last_torch_b200 as last_torch
   from last_torch_b200 import _native as N
+  from last_torch_b200 import distributed as ltdist
   from last_torch_b200 import ops
 
   lib = N.lib()
@@ -306,29 +350,24 @@ def run_b200(args):
   C = context.num_states()
   gen = torch.Generator(device=dev).manual_seed(1234 + rank)
   cpu_gen = torch.Generator().manual_seed(1234 + rank)
-
-  if args.ragged:
-    num_frames = torch.randint(T // 2, T + 1, [B], generator=cpu_gen).to(torch.int32)
-  else:
-    num_frames = torch.full([B], T, dtype=torch.int32)
-  labels = torch.randint(1, V + 1, [B, U], generator=cpu_gen).to(torch.int32)
-  num_labels = torch.full([B], U, dtype=torch.int32)
+  peak, peak_src = peaks()
 
   def barrier_sync():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed(step_fn, steps, warmup):
+  def timed(step_fn, steps, warmup, sample_clocks=False):
     for _ in range(warmup):
       step_fn()
     barrier_sync()
     launches0 = lib.lt_launch_count()
     timer = []
     N.KERNEL_TIMER = timer
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    if sampler:
+      sampler.start()
+      time.sleep(0.25)
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
     w0 = time.time()
@@ -339,73 +378,89 @@ def run_b200(args):
     barrier_sync()
     w1 = time.time()
     N.KERNEL_TIMER = None
-    clocks = sampler.stop(w0, w1)
+    clocks = sampler.stop(w0, w1) if sampler else None
     ms = torch.tensor([start.elapsed_time(end)], device=dev)
     if world > 1:
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = lib.lt_launch_count() - launches0
     kernels = {}
     for name, s, e in timer:
-      kernels.setdefault(name, []).append(s.elapsed_time(e))
+      kernels.setdefault(kernel_name(name), []).append(s.elapsed_time(e))
     return float(ms.item()) / steps, launches, kernels, clocks
 
+  def all_sum(x):
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t)
+    return float(t.item())
+
+  def lattice_inputs(b, t, v, nn, u, ragged):
+    c = sum(v**i for i in range(nn + 1))
+    if ragged:
+      num_frames = torch.randint(t // 2, t + 1, [b], generator=cpu_gen).to(torch.int32)
+    else:
+      num_frames = torch.full([b], t, dtype=torch.int32)
+    labels = torch.randint(1, v + 1, [b, u], generator=cpu_gen).to(torch.int32)
+    num_labels = torch.full([b], u, dtype=torch.int32)
+    blank = torch.randn([b, t, c], device=dev, generator=gen).requires_grad_()
+    lexical = torch.randn([b, t, c, v], device=dev, generator=gen).requires_grad_()
+    nl_d = num_labels.to(dev)
+    states, next_labels, _ = ops.walk_states(labels.to(dev), nl_d, v, nn)
+    return dict(c=c, num_frames=num_frames, nf_d=num_frames.to(dev), nl_d=nl_d, labels=labels,
+                num_labels=num_labels, blank=blank, lexical=lexical, states=states,
+                next_labels=next_labels)
+
+  def loss_grad_step(x, v, nn, k, flags):
+    loss, _, _ = ops.LatticeLoss.apply(x['blank'], x['lexical'], x['nf_d'], x['states'],
+                                       x['next_labels'], x['nl_d'], v, nn, k, flags)
+    total = loss.sum()
+    gb, gl = torch.autograd.grad(total, (x['blank'], x['lexical']))
+    return total, gb, gl
+
+  def kernel_table(kernels, steps, w_bytes):
+    kern = {}
+    for name, ts in kernels.items():
+      kern[name] = {'ms': statistics.mean(ts), 'calls_per_step': len(ts) / steps}
+    alg = {'lt_lattice_forward': 1.0 * w_bytes, 'lt_lattice_backward': 2.0 * w_bytes}
+    for name, nbytes in alg.items():
+      if name in kern:
+        kern[name]['algorithmic_gb'] = nbytes / 1e9
+        kern[name]['gbps'] = nbytes / 1e9 / (kern[name]['ms'] * 1e-3)
+        kern[name]['frac'] = kern[name]['gbps'] / peak
+    return kern, alg
+
   # ---- device-resident arm: dense arc weights already in HBM -----------------
-  blank = torch.randn([B, T, C], device=dev, generator=gen).requires_grad_()
-  lexical = torch.randn([B, T, C, V], device=dev, generator=gen).requires_grad_()
-  nf_d = num_frames.to(dev)
-  nl_d = num_labels.to(dev)
-  states = context.walk_states(labels.to(dev).long()).to(torch.int32).contiguous()
-  next_labels = torch.cat([labels.to(dev), torch.ones([B, 1], dtype=torch.int32, device=dev)],
-                          dim=1).contiguous()
+  x = lattice_inputs(B, T, V, n, U, args.ragged)
+  num_frames = x['num_frames']
   loss_sum = torch.zeros([1], device=dev)
 
   def resident_step():
-    loss, _, _, _ = ops.LatticeLoss.apply(blank, lexical, nf_d, states, next_labels, nl_d, V, n,
-                                          -1, args.flags)
-    total = loss.sum()
-    gb, gl = torch.autograd.grad(total, (blank, lexical))
+    total, gb, gl = loss_grad_step(x, V, n, -1, args.flags)
     if world > 1:
       loss_sum.copy_(total.detach().reshape(1))
       dist.all_reduce(loss_sum)       # the only exchange in materialised-weights mode
     return gb, gl
 
-  ms_step, launches, kernels, clocks = timed(resident_step, args.steps, args.warmup)
+  ms_step, launches, kernels, clocks = timed(resident_step, args.steps, args.warmup,
+                                             sample_clocks=True)
   # frames*states actually processed (padding frames of a ragged batch are not counted)
-  frames_done = torch.tensor([float(num_frames.sum())], device=dev)
-  if world > 1:
-    dist.all_reduce(frames_done)
-  units = float(frames_done.item()) * C
+  units = all_sum(float(num_frames.sum())) * C
   value = units / (ms_step * 1e-3)
-
   w_bytes = int(num_frames.sum()) * C * (V + 1) * 4      # arc weights of this rank's real frames
-  peak, peak_src = peaks()
-  kern = {}
-  for name, ts in kernels.items():
-    kern[name] = {'ms': statistics.mean(ts), 'calls_per_step': len(ts) / args.steps}
-  alg = {'lt_lattice_forward': 1.0 * w_bytes, 'lt_lattice_backward': 2.0 * w_bytes}
-  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of
-  # this exact workload (profiles/r01_ncu_round1_final_summary.csv); only valid for the
-  # default shape.
-  default_shape = (B, T, V, n, U) == (32, 1000, 256, 1, 120) and args.flags == 0
-  ncu_traffic = {'lt_lattice_forward': 8.456e9 + 0.036e9, 'lt_lattice_backward': 8.490e9 + 8.403e9}
-  for name, nbytes in alg.items():
-    if name in kern:
-      kern[name]['algorithmic_gb'] = nbytes / 1e9
-      kern[name]['gbps'] = nbytes / 1e9 / (kern[name]['ms'] * 1e-3)
-      kern[name]['frac'] = kern[name]['gbps'] / peak
+  kern, alg = kernel_table(kernels, args.steps, w_bytes)
   dom = max((k for k in kern if k in alg), key=lambda k: kern[k]['ms'], default=None)
   roofline = None
   if dom:
+    default_shape = (B, T, V, n, U) == (32, 1000, 256, 1, 120) and args.flags == 0 and not args.ragged
+    traffic, traffic_src = ncu_traffic(dom) if default_shape else (None, 'non-default shape')
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kern[dom]['gbps'], 'peak': peak,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': kern[dom]['frac'],
-                'traffic': ncu_traffic[dom] if default_shape else None,
-                'traffic_source': 'profiles/r01_ncu_round1_final_summary.csv (ncu --set full)',
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'algorithmic_bytes_per_launch': alg[dom],
                 'whole_step': {'algorithmic_gb': 3.0 * w_bytes / 1e9,
                                'gbps': 3.0 * w_bytes / 1e9 / (ms_step * 1e-3),
                                'frac': 3.0 * w_bytes / 1e9 / (ms_step * 1e-3) / peak}}
-
-  del blank, lexical
+  del x
   torch.cuda.empty_cache()
 
   # ---- end-to-end arm: public API, host buffers -------------------------------
@@ -420,44 +475,155 @@ def run_b200(args):
             vocab_size=c.shape()[1], hidden_size=H, device=str(dev), embedding_size=H,
             feature_size=H))
     lattice.kernel_flags = args.flags
-    params = [p for p in lattice.parameters()]
-    frames_h = torch.randn([B, T, H], generator=cpu_gen).pin_memory()
-    nf_h = num_frames.pin_memory()
-    lab_h = labels.pin_memory()
-    nl_h = num_labels.pin_memory()
+    labels = torch.randint(1, V + 1, [B, U], generator=cpu_gen).to(torch.int32)
+    host = dict(frames=torch.randn([B, T, H], generator=cpu_gen).pin_memory(),
+                num_frames=num_frames.pin_memory(), labels=labels.pin_memory(),
+                num_labels=torch.full([B], U, dtype=torch.int32).pin_memory())
     loss_h = torch.empty([B], dtype=torch.float32).pin_memory()
-    h2d = frames_h.numel() * 4 + nf_h.numel() * 4 + lab_h.numel() * 4 + nl_h.numel() * 4
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = loss_h.numel() * 4
+    # Double-buffered inputs: the host-to-device copy of step i+1 is issued on a copy stream
+    # BEFORE step i's kernels and overlaps them; every timed step issues (and pays for) exactly
+    # one copy of a full input batch.
+    cur = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    begun = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for ev in consumed:
+      ev.record(cur)
+    state = {'i': 0, 'primed': False, 'h2d_ms': [], 'ar_ms': []}
+
+    def issue_copy(slot):
+      with torch.cuda.stream(copy_stream):
+        copy_stream.wait_event(consumed[slot])
+        begun[slot].record(copy_stream)
+        for k, v in host.items():
+          slots[slot][k].copy_(v, non_blocking=True)
+        ready[slot].record(copy_stream)
 
     def e2e_step():
-      frames = frames_h.to(dev, non_blocking=True)
-      nf = nf_h.to(dev, non_blocking=True)
-      lab = lab_h.to(dev, non_blocking=True)
-      nl = nl_h.to(dev, non_blocking=True)
-      loss = lattice(frames=frames, num_frames=nf, labels=lab, num_labels=nl)
-      grads = torch.autograd.grad(loss.sum(), params)
+      slot = state['i'] & 1
+      if not state['primed']:
+        issue_copy(slot)
+        state['primed'] = True
+      issue_copy(slot ^ 1)                      # inputs of the NEXT step, under this step's kernels
+      cur.wait_event(ready[slot])
+      d = slots[slot]
       if world > 1:
-        flat = torch.cat([g.reshape(-1) for g in grads] + [loss.sum().reshape(1)])
-        dist.all_reduce(flat)         # loss + parameter gradients over NCCL / NVLink
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        total, grads, loss = ltdist.local_loss_and_grads(
+            lattice, d['frames'], d['num_frames'], d['labels'], d['num_labels'])
+        consumed[slot].record(cur)
+        a0.record(cur)
+        total, grads = ltdist.all_reduce_loss_and_grads(total, grads)   # NCCL over NVLink
+        a1.record(cur)
+      else:
+        loss = lattice(frames=d['frames'], num_frames=d['num_frames'], labels=d['labels'],
+                       num_labels=d['num_labels'])
+        grads = torch.autograd.grad(loss.sum(), list(lattice.parameters()))
+        consumed[slot].record(cur)
       loss_h.copy_(loss.detach(), non_blocking=True)
-      torch.cuda.current_stream().synchronize()
+      cur.synchronize()
+      if N.KERNEL_TIMER is not None:
+        state['h2d_ms'].append(begun[slot].elapsed_time(ready[slot]))
+        if world > 1:
+          state['ar_ms'].append(a0.elapsed_time(a1))
+      state['i'] += 1
       return loss_h
 
-    e_steps = max(2, min(args.steps, 5))
-    ms_e2e, e_launches, e_kernels, _ = timed(e2e_step, e_steps, max(1, min(args.warmup, 2)))
+    e_steps, e_warm = max(1, args.steps), max(1, args.warmup)
+    ms_e2e, e_launches, e_kernels, _ = timed(e2e_step, e_steps, e_warm)
+    kms = {k: statistics.mean(v) for k, v in e_kernels.items()}
+    kms['lt_h2d'] = statistics.mean(state['h2d_ms']) if state['h2d_ms'] else None
+    if world > 1:
+      kms['nccl_all_reduce'] = statistics.mean(state['ar_ms']) if state['ar_ms'] else None
     e2e = {'value': units / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e_steps,
-           'gpu_launches_per_step': e_launches / e_steps,
-           'kernels_ms': {k: statistics.mean(v) for k, v in e_kernels.items()},
+           'warmup': e_warm, 'gpu_launches_per_step': e_launches / e_steps,
+           'kernels_ms': kms,
+           'h2d': ('double-buffered on a copy stream: the copy of step i+1 is issued before step '
+                   'i\'s kernels; lt_h2d is its duration on that stream (overlapped), '
+                   'nccl_all_reduce the flat loss + parameter-gradient all-reduce'),
            'api': 'RecognitionLattice.forward + autograd.grad w.r.t. JointWeightFn/SharedEmbCacher '
-                  'parameters',
-           'grad_handover': ('float32' if os.environ.get('LT_NO_SPLIT_GRAD') else
-                             'split rows (bf16 hi | lo) from the lattice backward to the joint '
-                             'backward where both kernels support it')}
+                  'parameters' + ('; distributed.local_loss_and_grads + all_reduce_loss_and_grads'
+                                  if world > 1 else ''),
+           'grad_handover': ('split rows (bf16 hi | lo) from the lattice backward to the joint '
+                             'backward (ops.JointLatticeLoss)' if lattice.split_grad_handover
+                             else 'float32')}
+    del lattice, slots
+    torch.cuda.empty_cache()
+
+  # ---- the other BASELINE configs, each as a short timed run --------------------------------
+  extras = None
+  if not args.no_extras:
+    extras = []
+    x_steps, x_warm = 3, 3
+
+    def add(name, fn, b, t, v, nn, passes, frames_done=None, note=None):
+      """passes: how many times W (the fp32 arc weights) crosses HBM per step."""
+      c = sum(v**i for i in range(nn + 1))
+      try:
+        ms, _, kk, _ = timed(fn, x_steps, x_warm)
+      except Exception as e:     # an extra must never take the headline line down
+        extras.append({'config': name, 'error': repr(e)[:300]})
+        return
+      frames = all_sum(frames_done if frames_done is not None else b * t)
+      wb = frames * c * (v + 1) * 4 / max(world, 1)        # per rank
+      ent = {'config': name, 'per_gpu_batch': b, 'frames': t, 'states': c, 'vocab': v, 'ms': ms,
+             'frames_states_per_s': frames * c / (ms * 1e-3),
+             'roofline': {'bound': 'hbm', 'algorithmic_gb': passes * wb / 1e9,
+                          'gbps': passes * wb / 1e9 / (ms * 1e-3),
+                          'frac': passes * wb / 1e9 / (ms * 1e-3) / peak, 'peak': peak},
+             'kernels_ms': {k: statistics.mean(tt) for k, tt in kk.items()}}
+      if note:
+        ent['note'] = note
+      extras.append(ent)
+
+    def run_extra(name, b, t, v, nn, k, u, mode, ragged=False, note=None):
+      try:
+        xx = lattice_inputs(b, t, v, nn, u, ragged)
+      except Exception as e:
+        extras.append({'config': name, 'error': repr(e)[:300]})
+        return
+      frames_done = float(xx['num_frames'].sum())
+      if mode == 'lossgrad':
+        add(name, lambda: loss_grad_step(xx, v, nn, k, 0), b, t, v, nn, 3.0, frames_done, note)
+      elif mode == 'forward':
+        bl, lx = xx['blank'].detach(), xx['lexical'].detach()
+        add(name, lambda: ops._lattice_forward_raw(N.LOG, v, nn, k, bl, lx, xx['nf_d'], 0, False,
+                                                   False, norm=True),
+            b, t, v, nn, 1.0, frames_done, note)
+      else:     # MaxTropical shortest distance + Viterbi back-trace
+        bl, lx = xx['blank'].detach(), xx['lexical'].detach()
+        add(name, lambda: ops.viterbi_path(bl, lx, xx['nf_d'], v, nn, k), b, t, v, nn, 1.0,
+            frames_done, note)
+      del xx
+      torch.cuda.empty_cache()
+
+    # configs[4]: the per-GPU batch sweep (weak scaling: N x these under torchrun)
+    for bb in (64, 128):
+      run_extra(f'configs[4] bigram vocab 256 T=1000 Log loss+grad, B={bb}/GPU '
+                f'(global {bb * world})', bb, 1000, 256, 1, -1, 120, 'lossgrad')
+    if world == 1:
+      run_extra('configs[2] trigram vocab 64 (4161 states) FrameLabelDependent(2) MaxTropical '
+                'shortest distance + Viterbi, B=32 T=500', 32, 500, 64, 2, 2, 60, 'viterbi')
+      run_extra('configs[2] geometry, FrameDependent MaxTropical + Viterbi, B=32 T=500',
+                32, 500, 64, 2, -1, 60, 'viterbi')
+      run_extra('configs[2] geometry, FrameLabelDependent(2) Log loss+grad, B=32 T=500',
+                32, 500, 64, 2, 2, 60, 'lossgrad')
+      run_extra('bigram vocab 256 FrameLabelDependent(2) Log loss+grad at configs[1] geometry, '
+                'B=32 T=1000', 32, 1000, 256, 1, 2, 120, 'lossgrad')
+      run_extra('configs[1] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=32 T=1000 '
+                '(real frames counted)', 32, 1000, 256, 1, -1, 120, 'lossgrad', ragged=True)
+      run_extra('configs[1] Log loss+grad, B=48/GPU', 48, 1000, 256, 1, -1, 120, 'lossgrad')
+      run_extra('configs[1] Log forward only, B=8/GPU', 8, 1000, 256, 1, -1, 120, 'forward')
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu:
-    val, threads, desc, _ = cpu_bounded_run(args, with_joint=False, seconds=args.cpu_seconds)
+    val, threads, desc, _, _ = cpu_bounded_run(args, with_joint=False, seconds=args.cpu_seconds)
     cpu = {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': desc}
 
   if rank == 0:
@@ -467,6 +633,7 @@ def run_b200(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': config_dict(args, world), 'clocks': clocks, 'gpu_launches': int(launches),
         'roofline': roofline, 'kernels': kern, 'e2e': e2e, 'cpu_baseline': cpu,
+        'extra_configs': extras,
     }
     print(json.dumps(line), flush=True)
   if world > 1:

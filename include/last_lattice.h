@@ -47,10 +47,6 @@ extern "C" {
 
 /* flags for lt_lattice_forward / lt_lattice_backward */
 #define LT_FLAG_FORCE_GENERIC 1u     /* never take the TMA/cluster fast path   */
-#define LT_FLAG_FAST_V1 2u           /* first-generation fast path (one utterance per
-                                        cluster) instead of the interleaved-pair kernels */
-#define LT_FLAG_PAIR_CTA 4u          /* fast path: two utterances per 512-thread CTA
-                                        instead of two 256-thread CTAs per SM       */
 #define LT_FLAG_CLUSTER_SHIFT 8      /* bits 8..11: force cluster size (1,2,4,8) */
 #define LT_FLAG_GRAD_SPLIT 16u       /* lt_lattice_backward: write grad_lexical as "split rows"
                                         (see lt_joint_backward); only when
@@ -60,6 +56,14 @@ int lt_version(void);
 const char* lt_last_error(void);
 /* Number of CUDA kernels this library has launched in this process so far. */
 unsigned long long lt_launch_count(void);
+/* Debug / test switches, process-wide.  Each is initialised once from the environment variable
+ * of the same name and can be changed at run time: LT_JOINT_SIMT, LT_JOINT_DGRAD_V1,
+ * LT_JOINT_WGRAD_SIMT (CUDA-core / first-generation joint kernels), LT_JOINT_DGRAD_PAIR,
+ * LT_JOINT_DGRAD_MULTICAST (measured-slower variants of the split-row dgrad), LT_TABLE_V1,
+ * LT_TABLE_CLUSTER (NextStateTable kernel selection).  lt_get_option returns -1 for an unknown
+ * name. */
+int lt_set_option(const char* name, int value);
+int lt_get_option(const char* name);
 /* Number of SMs, compute capability of the current device. */
 int lt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -108,6 +112,42 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size,
                         float* grad_blank, float* grad_lexical,
                         float* beta_final, unsigned flags, void* stream);
 
+/* ---- K1 / K2 with a RENORMALISED recursion state (Log semiring) -------------------
+ * Same recursions, but alpha is kept as alpha_t = alpha~_t + off_t with an exact integer offset
+ * (in log2 units) that follows floor(max_c alpha~_t[c]) from frame to frame, so every sum the
+ * recursion rounds has magnitude O(10) instead of O(logZ).  At T = 1000 (logZ ~ 5.5e3, one fp32
+ * ulp = 4.9e-4) the arc posteriors then agree with an fp64 evaluation to ~1e-6 relative; the
+ * plain fp32 recursion -- and the fp32 reference, lattices.py:865-886 + autograd -- is at
+ * 1e-4 .. 1e-3 there (profiles/r02_parity_errors.json).
+ *   alpha_norm [B, T+2] int32: off_0 .. off_T, then the bits of r (fp32) with
+ *              logZ = (off_T + r) * ln 2.  Written by the forward, read by the backward.
+ *   alphas     [B,T,C] then holds alpha~_t (natural-log units); the TRUE alpha_t is
+ *              alphas[b,t,c] + alpha_norm[b,t] * ln 2 (lt_alphas_denormalize).
+ * Only when lt_lattice_norm_supported() returns 1 (the TMA fast path, Log); alpha_norm == NULL
+ * selects the plain kernels (identical to lt_lattice_forward / lt_lattice_backward).
+ */
+int lt_lattice_norm_supported(int semiring, int vocab_size, int context_size,
+                              int max_expansions, unsigned flags);
+int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size,
+                            int max_expansions, const float* blank,
+                            const float* lexical, const int32_t* num_frames, int B,
+                            int T, const float* alpha_init, float* dist,
+                            float* alphas, float* alpha_final, float* levels,
+                            int16_t* backptr, uint8_t* termptr, int32_t* alpha_norm,
+                            unsigned flags, void* stream);
+int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size,
+                             int max_expansions, const float* blank,
+                             const float* lexical, const int32_t* num_frames, int B,
+                             int T, const float* alphas, const float* levels,
+                             const float* dist, const float* grad_dist,
+                             float* grad_blank, float* grad_lexical,
+                             float* beta_final, const int32_t* alpha_norm,
+                             unsigned flags, void* stream);
+/* alphas[b,t,c] += alpha_norm[b,t] * ln 2 in place (the alphas RecognitionLattice._forward
+ * returns, lattices.py:496). */
+int lt_alphas_denormalize(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
+                          void* stream);
+
 /* ---- K5: Viterbi back-trace (replaces the vjp trick of lattices.py:221-247) ----
  *   alpha_final [B,C] from the MaxTropical forward.
  *   labels      [B,T,max(k,0)+1] int32: TRUE 1-based lexical labels, 0 = blank
@@ -139,6 +179,16 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
 int lt_walk_states(int vocab_size, int context_size, const int32_t* labels,
                    int B, int U, int32_t* states, int32_t* next_labels,
                    void* stream);
+/* The same with the padding / range rules a caller needs for untrusted label tensors:
+ *   num_labels [B] or NULL: positions u >= num_labels[b] are padding and read as epsilon
+ *              whatever they hold (-1, V+1, ...) -- they cannot influence the numerator;
+ *   bad_labels [1] or NULL: += number of labels outside [0, V] BEFORE num_labels (the reference
+ *              fails on those in one_hot, lattices.py:322); they are read as epsilon too, so the
+ *              emitted states / next_labels are always in range (the gather / scatter kernels
+ *              additionally clamp what they are given).  The caller pre-zeroes the counter. */
+int lt_walk_states_checked(int vocab_size, int context_size, const int32_t* labels,
+                           const int32_t* num_labels, int B, int U, int32_t* states,
+                           int32_t* next_labels, int32_t* bad_labels, void* stream);
 int lt_string_gather(int vocab_size, int num_states, const float* blank,
                      const float* lexical, const int32_t* states,
                      const int32_t* next_labels, int B, int T, int U1,
@@ -165,6 +215,28 @@ int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
                        const float* dist, const float* grad_dist,
                        float* grad_blank_w, float* grad_lexical_w,
                        void* stream);
+
+/* The same two with the Log chain carried as (integer part, fraction): every value is
+ * e + f with e an exact int32 and f in [0, 1) (f = -inf for the semiring zero), so the sums the
+ * chain rounds have magnitude O(1) whatever the numerator's magnitude (1e3 at T = 1000).
+ *   alphas [B,T,U1] then holds the fractions, alpha_exp [B,T,U1] int32 the integer parts;
+ *   dist_norm [B,2] int32 = (integer part, bits of the fp32 fraction) of dist[b].
+ * Only when lt_string_norm_supported() returns 1 (Log, FrameDependent, U1 <= 1024); NULL for both
+ * selects the plain kernels. */
+int lt_string_norm_supported(int semiring, int max_expansions, int U1);
+int lt_string_forward_norm(int semiring, int max_expansions, const float* blank_w,
+                           const float* lexical_w, const int32_t* num_frames,
+                           const int32_t* num_labels, int B, int T, int U1,
+                           float* dist, float* alphas, uint8_t* backptr,
+                           int32_t* alpha_exp, int32_t* dist_norm, void* stream);
+int lt_string_backward_norm(int semiring, int max_expansions, const float* blank_w,
+                            const float* lexical_w, const int32_t* num_frames,
+                            const int32_t* num_labels, int B, int T, int U1,
+                            const float* alphas, const uint8_t* backptr,
+                            const float* dist, const float* grad_dist,
+                            float* grad_blank_w, float* grad_lexical_w,
+                            const int32_t* alpha_exp, const int32_t* dist_norm,
+                            void* stream);
 
 /* ---- semiring (+) on arbitrary tensors (semirings.py:202-220, :330-348) ----
  * plus: elementwise on n elements (inputs already broadcast & contiguous).
@@ -199,13 +271,14 @@ int lt_semiring_sum_backward(int semiring, const float* a, const float* out,
  * forward_reduce / its gradient on arbitrary leading dims (w viewed as [outer, C, V]):
  *   out[o,q] = (+)_{p -y-> q} w[o,p,y] for EVERY semiring (the reference implements the
  *   Real semiring only); argarc [outer,C] int32 for MaxTropical.
- * FrameDependent lattices with V % 4 == 0 (and C <= 1024 forward) run on a CLUSTER of up to 8
+ * FrameDependent lattices with V % 4 == 0 (and C <= 2048 forward) run on a CLUSTER of up to 8
  * CTAs per utterance (csrc/lattice_table2.cu: every CTA streams a slab of source rows with
- * bulk copies, one cluster barrier per frame); everything else runs one CTA per utterance.
+ * bulk copies; partial values / new beta travel by st.async + mbarrier complete_tx, there is NO
+ * cluster barrier in either loop); everything else runs one CTA per utterance.
  * lt_table_lattice_cluster() returns the cluster size the forward (backward != 0: the
  * backward) kernel of such a lattice would use with 16-byte aligned weights, 0 for the
- * one-CTA kernels.  Environment: LT_TABLE_CLUSTER=1|2|4|8 forces a size, LT_TABLE_V1=1 the
- * one-CTA kernels.
+ * one-CTA kernels.  Options (lt_set_option): LT_TABLE_CLUSTER=1|2|4|8 forces a size,
+ * LT_TABLE_V1=1 the one-CTA kernels.
  */
 int lt_table_lattice_cluster(int C, int V, int max_expansions, int backward);
 int lt_table_lattice_forward(int semiring, int max_expansions, const int32_t* table,
@@ -264,10 +337,12 @@ int lt_local_normalize_backward(int mode, const float* blank, const float* lexic
 /* Bytes of device scratch lt_joint_forward needs (bf16 hi/lo split of W_vocab and the
  * e^(2x) tables of the two projections, (C + N) * H floats). */
 int64_t lt_joint_workspace_bytes(int64_t N, int C, int H, int V);
+/* b_blank is a DEVICE scalar (the bias of Linear(H, 1), weight_fns.py:220), read by the kernel
+ * epilogue like b_vocab: no host synchronisation on the way in. */
 int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
-                     const float* w_blank, float b_blank, const float* w_vocab,
-                     const float* b_vocab, int64_t N, int C, int H, int V,
-                     float* blank, float* lexical, void* workspace,
+                     const float* w_blank, const float* b_blank,
+                     const float* w_vocab, const float* b_vocab, int64_t N, int C,
+                     int H, int V, float* blank, float* lexical, void* workspace,
                      void* stream);
 /* Gradients w.r.t. the joint pre-activation, reduced to the two projections:
  *   grad_proj_ctx [C,H] (+= over N), grad_proj_frame [N,H] (+= over C),
@@ -296,6 +371,8 @@ int lt_string_scatter_add_split(int vocab_size, int num_states, const float* gra
  * (LT_FLAG_GRAD_SPLIT), so the fused dgrad loads it with TMA and converts nothing.  Only when
  * lt_joint_backward_split_supported() returns 1. */
 int lt_joint_backward_split_supported(int64_t N, int C, int H, int V);
+/* fp32 rows [M, V] -> split rows (same bytes), for callers that hold fp32 gradients. */
+int lt_joint_split_rows(const float* rows, void* out, int64_t M, int V, void* stream);
 /* Bytes of device scratch for lt_joint_backward (W_vocab^T as bf16 hi/lo + the
  * [N*C, H] pre-activation gradient that is reduced into the two projections);
  * workspace may be NULL, which selects the CUDA-core kernels. */

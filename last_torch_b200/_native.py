@@ -39,9 +39,22 @@ SIGNATURES = {
                            _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_lattice_backward': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
                             _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
+    'lt_lattice_norm_supported': [_c_int, _c_int, _c_int, _c_int, _c_uint],
+    'lt_lattice_forward_norm': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                                _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
+    'lt_lattice_backward_norm': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
+    'lt_alphas_denormalize': [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr],
+    'lt_string_norm_supported': [_c_int, _c_int, _c_int],
+    'lt_string_forward_norm': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                               _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    'lt_string_backward_norm': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
+                                _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_viterbi_backtrace': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int,
                              _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_walk_states': [_c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr],
+    'lt_walk_states_checked': [_c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr,
+                               _ptr],
     'lt_string_gather': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr],
     'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
@@ -58,8 +71,11 @@ SIGNATURES = {
     'lt_semiring_sum_backward': [_c_int, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_i64, _c_i64, _ptr,
                                  _ptr],
     'lt_joint_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
-    'lt_joint_forward': [_ptr, _ptr, _ptr, _c_float, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
+    'lt_joint_forward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr, _ptr],
+    'lt_joint_split_rows': [_ptr, _ptr, _c_i64, _c_int, _ptr],
+    'lt_set_option': [ctypes.c_char_p, _c_int],
+    'lt_get_option': [ctypes.c_char_p],
     'lt_joint_backward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                           _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
     'lt_joint_backward_split_supported': [_c_i64, _c_int, _c_int, _c_int],
@@ -119,8 +135,10 @@ def lib():
 # native call then appends (name, start_event, end_event) recorded on the
 # current stream of the current device -- the stream the kernel is launched on).
 KERNEL_TIMER = None
-_UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count',
+_UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count', 'lt_set_option',
+            'lt_get_option',
             'lt_joint_backward_split_supported', 'lt_lattice_backward_split_supported',
+            'lt_lattice_norm_supported', 'lt_string_norm_supported',
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 
@@ -145,6 +163,28 @@ class _TimedLib:
       timer.append((name, start, end))
       return rc
     return call
+
+
+class option:
+  """Context manager for a debug / test switch of the library (lt_set_option):
+      with N.option('LT_JOINT_SIMT', 1): ...
+  """
+
+  def __init__(self, name: str, value: int = 1):
+    self.name = name.encode()
+    self.value = int(value)
+    self.saved = 0
+
+  def __enter__(self):
+    self.saved = lib().lt_get_option(self.name)
+    if self.saved < 0:
+      raise KeyError(self.name.decode())
+    check(lib().lt_set_option(self.name, self.value), 'lt_set_option')
+    return self
+
+  def __exit__(self, *exc):
+    lib().lt_set_option(self.name, self.saved)
+    return False
 
 
 def check(rc: int, what: str) -> None:

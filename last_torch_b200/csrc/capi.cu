@@ -2,6 +2,10 @@
 // validation, geometry, kernel-path dispatch and error reporting.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "params.cuh"
@@ -24,6 +28,33 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
   return LT_ERR_CUDA;
+}
+
+static const char* const kOptionNames[OPT_COUNT] = {
+    "LT_JOINT_SIMT", "LT_JOINT_DGRAD_V1", "LT_JOINT_WGRAD_SIMT", "LT_JOINT_DGRAD_PAIR",
+    "LT_JOINT_DGRAD_MULTICAST", "LT_TABLE_V1", "LT_TABLE_CLUSTER"};
+static int g_options[OPT_COUNT];
+static std::once_flag g_options_once;
+
+static void init_options() {
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    const char* e = getenv(kOptionNames[i]);
+    int v = 0;
+    if (e && *e) { v = atoi(e); if (v == 0 && e[0] != '0') v = 1; }
+    __atomic_store_n(&g_options[i], v, __ATOMIC_RELAXED);
+  }
+}
+
+int option(Option o) {
+  std::call_once(g_options_once, init_options);
+  return __atomic_load_n(&g_options[o], __ATOMIC_RELAXED);
+}
+
+static int find_option(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptionNames[i]) == 0) return i;
+  return -1;
 }
 
 static int device_sm_count(int* out) {
@@ -57,6 +88,19 @@ const char* lt_last_error(void) { return g_error; }
 
 unsigned long long lt_launch_count(void) { return launch_count(); }
 
+int lt_set_option(const char* name, int value) {
+  const int i = find_option(name);
+  LT_CHECK_ARG(i >= 0, "lt_set_option: unknown option '%s'", name ? name : "(null)");
+  std::call_once(g_options_once, init_options);
+  __atomic_store_n(&g_options[i], value, __ATOMIC_RELAXED);
+  return LT_OK;
+}
+
+int lt_get_option(const char* name) {
+  const int i = find_option(name);
+  return i < 0 ? -1 : option((Option)i);
+}
+
 int lt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   LT_CUDA(cudaGetDevice(&dev));
@@ -85,6 +129,23 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
                        int T, const float* alpha_init, float* dist, float* alphas,
                        float* alpha_final, float* levels, int16_t* backptr, uint8_t* termptr,
                        unsigned flags, void* stream) {
+  return lt_lattice_forward_norm(semiring, vocab_size, context_size, max_expansions, blank, lexical,
+                                 num_frames, B, T, alpha_init, dist, alphas, alpha_final, levels,
+                                 backptr, termptr, nullptr, flags, stream);
+}
+
+int lt_lattice_norm_supported(int semiring, int vocab_size, int context_size, int max_expansions,
+                              unsigned flags) {
+  NGram g;
+  if (!make_ngram(vocab_size, context_size, &g)) return 0;
+  return lattice_norm_supported(semiring, g, max_expansions, flags) ? 1 : 0;
+}
+
+int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size, int max_expansions,
+                            const float* blank, const float* lexical, const int32_t* num_frames,
+                            int B, int T, const float* alpha_init, float* dist, float* alphas,
+                            float* alpha_final, float* levels, int16_t* backptr, uint8_t* termptr,
+                            int32_t* alpha_norm, unsigned flags, void* stream) {
   NGram g;
   int rc = check_common("lt_lattice_forward", semiring, vocab_size, context_size, max_expansions, B, T, &g);
   if (rc) return rc;
@@ -101,12 +162,16 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
   p.levels = max_expansions >= 1 ? levels : nullptr;
   p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
-  if (T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical))
-    return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
+  p.alpha_norm = alpha_norm;
+  const bool fast2 = T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical);
+  if (alpha_norm && !(fast2 && lattice_norm_supported(semiring, g, max_expansions, flags))) {
+    set_error("lt_lattice_forward_norm: this lattice has no renormalised kernel "
+              "(lt_lattice_norm_supported, 16-byte aligned weights, T > 0)");
+    return LT_ERR_UNSUPPORTED;
+  }
+  if (fast2) return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (T > 0 && lattice_cols_supported(g, max_expansions, flags, lexical))
     return lattice_forward_cols_launch(semiring, g, max_expansions, p, (cudaStream_t)stream);
-  if (T > 0 && lattice_fast_supported(g, max_expansions, flags, lexical))
-    return lattice_forward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,
                                         (cudaStream_t)stream);
 }
@@ -116,6 +181,17 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
                         int T, const float* alphas, const float* levels, const float* dist,
                         const float* grad_dist, float* grad_blank, float* grad_lexical,
                         float* beta_final, unsigned flags, void* stream) {
+  return lt_lattice_backward_norm(semiring, vocab_size, context_size, max_expansions, blank,
+                                  lexical, num_frames, B, T, alphas, levels, dist, grad_dist,
+                                  grad_blank, grad_lexical, beta_final, nullptr, flags, stream);
+}
+
+int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int max_expansions,
+                             const float* blank, const float* lexical, const int32_t* num_frames,
+                             int B, int T, const float* alphas, const float* levels,
+                             const float* dist, const float* grad_dist, float* grad_blank,
+                             float* grad_lexical, float* beta_final, const int32_t* alpha_norm,
+                             unsigned flags, void* stream) {
   NGram g;
   int rc = check_common("lt_lattice_backward", semiring, vocab_size, context_size, max_expansions, B, T, &g);
   if (rc) return rc;
@@ -135,21 +211,32 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size, int max_
   p.blank = blank; p.lexical = lexical; p.num_frames = num_frames;
   p.alphas = alphas; p.levels = levels; p.dist = dist; p.grad_dist = grad_dist;
   p.grad_blank = grad_blank; p.grad_lexical = grad_lexical; p.beta_final = beta_final;
-  if (lattice_fast2_supported(g, max_expansions, flags, lexical) &&
-      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
-    return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
+  p.alpha_norm = alpha_norm;
+  const bool fast2 = lattice_fast2_supported(g, max_expansions, flags, lexical) &&
+                     reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0;
+  if (alpha_norm && !(fast2 && lattice_norm_supported(semiring, g, max_expansions, flags))) {
+    set_error("lt_lattice_backward_norm: `alphas` / `alpha_norm` are renormalised but this call "
+              "cannot take the renormalised kernel (16-byte aligned weights and gradients)");
+    return LT_ERR_UNSUPPORTED;
+  }
+  if (fast2) return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (flags & LT_FLAG_GRAD_SPLIT) {
     set_error("lt_lattice_backward: LT_FLAG_GRAD_SPLIT needs the TMA fast path "
               "(lt_lattice_backward_split_supported)");
     return LT_ERR_UNSUPPORTED;
   }
-  if (lattice_fast_supported(g, max_expansions, flags, lexical) &&
-      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0)
-    return lattice_backward_fast_launch(semiring, g, p, (cudaStream_t)stream);
   if (lattice_rows_supported(g, max_expansions, flags, lexical, grad_lexical))
     return lattice_backward_rows_launch(semiring, g, p, sms, (cudaStream_t)stream);
   return lattice_backward_generic_launch(semiring, g, max_expansions, p, flags, sms,
                                          (cudaStream_t)stream);
+}
+
+int lt_alphas_denormalize(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
+                          void* stream) {
+  LT_CHECK_ARG(B >= 0 && T >= 0 && C >= 0, "lt_alphas_denormalize: bad sizes B=%d T=%d C=%d", B, T, C);
+  if (B == 0 || T == 0 || C == 0) return LT_OK;
+  LT_CHECK_ARG(alphas && alpha_norm, "lt_alphas_denormalize: NULL pointer");
+  return alphas_denormalize_launch(alphas, alpha_norm, B, T, C, (cudaStream_t)stream);
 }
 
 int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
@@ -178,6 +265,13 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
 
 int lt_walk_states(int vocab_size, int context_size, const int32_t* labels, int B, int U,
                    int32_t* states, int32_t* next_labels, void* stream) {
+  return lt_walk_states_checked(vocab_size, context_size, labels, nullptr, B, U, states,
+                                next_labels, nullptr, stream);
+}
+
+int lt_walk_states_checked(int vocab_size, int context_size, const int32_t* labels,
+                           const int32_t* num_labels, int B, int U, int32_t* states,
+                           int32_t* next_labels, int32_t* bad_labels, void* stream) {
   NGram g;
   LT_CHECK_ARG(make_ngram(vocab_size, context_size, &g),
                "lt_walk_states: bad FullNGram(vocab_size=%d, context_size=%d)", vocab_size,
@@ -185,7 +279,8 @@ int lt_walk_states(int vocab_size, int context_size, const int32_t* labels, int 
   LT_CHECK_ARG(B >= 0 && U >= 0, "lt_walk_states: bad sizes B=%d U=%d", B, U);
   if (B == 0) return LT_OK;
   LT_CHECK_ARG(states && next_labels && (U == 0 || labels), "lt_walk_states: NULL pointer");
-  return walk_states_launch(g, labels, B, U, states, next_labels, (cudaStream_t)stream);
+  return walk_states_launch(g, labels, num_labels, B, U, states, next_labels, bad_labels,
+                            (cudaStream_t)stream);
 }
 
 int lt_string_gather(int vocab_size, int num_states, const float* blank, const float* lexical,
@@ -239,7 +334,6 @@ int lt_lattice_backward_split_supported(int semiring, int vocab_size, int contex
   if (check_common("lt_lattice_backward_split_supported", semiring, vocab_size, context_size,
                    max_expansions, 1, 1, &g))
     return 0;
-  if (flags & LT_FLAG_PAIR_CTA) return 0;
   return lattice_fast2_supported(g, max_expansions, flags & ~LT_FLAG_GRAD_SPLIT,
                                  reinterpret_cast<const void*>(uintptr_t(256))) ? 1 : 0;
 }
@@ -257,8 +351,32 @@ int lt_string_forward(int semiring, int max_expansions, const float* blank_w,
                       const float* lexical_w, const int32_t* num_frames,
                       const int32_t* num_labels, int B, int T, int U1, float* dist, float* alphas,
                       uint8_t* backptr, void* stream) {
+  return lt_string_forward_norm(semiring, max_expansions, blank_w, lexical_w, num_frames,
+                                num_labels, B, T, U1, dist, alphas, backptr, nullptr, nullptr,
+                                stream);
+}
+
+int lt_string_norm_supported(int semiring, int max_expansions, int U1) {
+  return string_norm_supported(semiring, max_expansions, U1) ? 1 : 0;
+}
+
+int lt_string_forward_norm(int semiring, int max_expansions, const float* blank_w,
+                           const float* lexical_w, const int32_t* num_frames,
+                           const int32_t* num_labels, int B, int T, int U1, float* dist,
+                           float* alphas, uint8_t* backptr, int32_t* alpha_exp,
+                           int32_t* dist_norm, void* stream) {
   int rc = check_string("lt_string_forward", semiring, max_expansions, B, T, U1);
   if (rc) return rc;
+  LT_CHECK_ARG((alpha_exp == nullptr) == (dist_norm == nullptr),
+               "lt_string_forward_norm: alpha_exp and dist_norm go together");
+  if (alpha_exp) {
+    LT_CHECK_ARG(alphas, "lt_string_forward_norm: alpha_exp needs the alphas buffer");
+    if (!string_norm_supported(semiring, max_expansions, U1)) {
+      set_error("lt_string_forward_norm: no (integer, fraction) kernel for this chain "
+                "(lt_string_norm_supported)");
+      return LT_ERR_UNSUPPORTED;
+    }
+  }
   LT_CHECK_ARG(num_frames && num_labels && dist, "lt_string_forward: NULL pointer");
   LT_CHECK_ARG(T == 0 || (blank_w && lexical_w), "lt_string_forward: NULL weights");
   StrParams p = {};
@@ -266,6 +384,7 @@ int lt_string_forward(int semiring, int max_expansions, const float* blank_w,
   p.blank_w = blank_w; p.lexical_w = lexical_w; p.num_frames = num_frames;
   p.num_labels = num_labels; p.dist = dist; p.alphas = alphas;
   p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
+  p.alpha_exp = alpha_exp; p.dist_norm = dist_norm;
   return string_forward_launch(semiring, p, (cudaStream_t)stream);
 }
 
@@ -274,8 +393,26 @@ int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
                        const int32_t* num_labels, int B, int T, int U1, const float* alphas,
                        const uint8_t* backptr, const float* dist, const float* grad_dist,
                        float* grad_blank_w, float* grad_lexical_w, void* stream) {
+  return lt_string_backward_norm(semiring, max_expansions, blank_w, lexical_w, num_frames,
+                                 num_labels, B, T, U1, alphas, backptr, dist, grad_dist,
+                                 grad_blank_w, grad_lexical_w, nullptr, nullptr, stream);
+}
+
+int lt_string_backward_norm(int semiring, int max_expansions, const float* blank_w,
+                            const float* lexical_w, const int32_t* num_frames,
+                            const int32_t* num_labels, int B, int T, int U1, const float* alphas,
+                            const uint8_t* backptr, const float* dist, const float* grad_dist,
+                            float* grad_blank_w, float* grad_lexical_w, const int32_t* alpha_exp,
+                            const int32_t* dist_norm, void* stream) {
   int rc = check_string("lt_string_backward", semiring, max_expansions, B, T, U1);
   if (rc) return rc;
+  LT_CHECK_ARG((alpha_exp == nullptr) == (dist_norm == nullptr),
+               "lt_string_backward_norm: alpha_exp and dist_norm go together");
+  if (alpha_exp && !string_norm_supported(semiring, max_expansions, U1)) {
+    set_error("lt_string_backward_norm: no (integer, fraction) kernel for this chain "
+              "(lt_string_norm_supported)");
+    return LT_ERR_UNSUPPORTED;
+  }
   if (B == 0 || T == 0) return LT_OK;
   LT_CHECK_ARG(num_frames && num_labels && dist && grad_blank_w && grad_lexical_w && blank_w && lexical_w,
                "lt_string_backward: NULL pointer");
@@ -286,6 +423,7 @@ int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
   p.blank_w = blank_w; p.lexical_w = lexical_w; p.num_frames = num_frames;
   p.num_labels = num_labels; p.alphas_in = alphas; p.backptr_in = backptr; p.dist_in = dist;
   p.grad_dist = grad_dist; p.grad_blank_w = grad_blank_w; p.grad_lexical_w = grad_lexical_w;
+  p.alpha_exp_in = alpha_exp; p.dist_norm_in = dist_norm;
   return string_backward_launch(semiring, p, (cudaStream_t)stream);
 }
 

@@ -16,6 +16,21 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void note_launch();   // bumps the process-wide kernel-launch counter (lt_launch_count)
 
+// Process-wide debug / test switches (lt_set_option / lt_get_option).  Each one is initialised
+// ONCE, on first use, from the environment variable of the same name; the kernels' dispatch
+// code only ever does an atomic load.
+enum Option {
+  OPT_JOINT_SIMT,             // LT_JOINT_SIMT: CUDA-core joint kernels instead of tcgen05
+  OPT_JOINT_DGRAD_V1,         // LT_JOINT_DGRAD_V1: first-generation dgrad + streaming reduction
+  OPT_JOINT_WGRAD_SIMT,       // LT_JOINT_WGRAD_SIMT: CUDA-core weight gradient
+  OPT_JOINT_DGRAD_PAIR,       // LT_JOINT_DGRAD_PAIR: cta_group::2 split-row dgrad
+  OPT_JOINT_DGRAD_MULTICAST,  // LT_JOINT_DGRAD_MULTICAST: TMA-multicast split-row dgrad
+  OPT_TABLE_V1,               // LT_TABLE_V1: one-CTA NextStateTable kernels
+  OPT_TABLE_CLUSTER,          // LT_TABLE_CLUSTER: force the NextStateTable cluster size
+  OPT_COUNT
+};
+int option(Option o);
+
 #define LT_CHECK_ARG(cond, ...)                    \
   do {                                             \
     if (!(cond)) {                                 \

@@ -31,10 +31,10 @@ struct JointFwdB {
   }
 };
 struct JointFwdEpi {
-  float* blank; float* lexical; const float* bv; float bb; int V;
+  float* blank; float* lexical; const float* bv; const float* bb; int V;
   __device__ void operator()(int64_t m, int n, float acc) const {
     if (n < V) lexical[(size_t)m * V + n] = acc + bv[n];
-    else blank[m] = acc + bb;
+    else blank[m] = acc + __ldg(bb);
   }
 };
 
@@ -85,7 +85,7 @@ struct JointBwd2Epi {
   }
 };
 
-int joint_forward_simt(const float* pc, const float* pf, const float* wb, float bb,
+int joint_forward_simt(const float* pc, const float* pf, const float* wb, const float* bb,
                        const float* wv, const float* bv, int64_t N, int C, int H, int V,
                        float* blank, float* lexical, cudaStream_t stream) {
   const int64_t M = N * C;
@@ -151,13 +151,14 @@ extern "C" int64_t lt_joint_workspace_bytes(int64_t N, int C, int H, int V) {
 }
 
 extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
-                                const float* w_blank, float b_blank, const float* w_vocab,
-                                const float* b_vocab, int64_t N, int C, int H, int V,
-                                float* blank, float* lexical, void* workspace, void* stream) {
+                                const float* w_blank, const float* b_blank,
+                                const float* w_vocab, const float* b_vocab, int64_t N, int C,
+                                int H, int V, float* blank, float* lexical, void* workspace,
+                                void* stream) {
   LT_CHECK_ARG(N >= 0 && C > 0 && H > 0 && V > 0, "lt_joint_forward: bad sizes N=%lld C=%d H=%d V=%d",
                (long long)N, C, H, V);
   if (N == 0) return LT_OK;
-  LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && w_vocab && b_vocab && blank && lexical,
+  LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && b_blank && w_vocab && b_vocab && blank && lexical,
                "lt_joint_forward: NULL pointer");
   if (workspace && reinterpret_cast<uintptr_t>(workspace) % 128 == 0 &&
       joint_tc_supported(N, C, H, V, proj_ctx, proj_frame, lexical))
@@ -200,16 +201,6 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
                  "(ask lt_joint_backward_split_supported first)");
   }
   const float* dgrad_gl = grad_lexical;      // what the tensor-core kernels read
-  if (!split && ws_ok && getenv("LT_JOINT_DGRAD_SPLIT_TEST") &&
-      joint_backward_split_supported(N, C, H, V)) {
-    // test hook: run the fused dgrad on a split copy of the fp32 gradient
-    unsigned char* copy = reinterpret_cast<unsigned char*>(workspace) + joint_split_bytes(H, V) +
-                          joint_table_bytes(N, C, H);
-    int rc = joint_split_rows_launch(grad_lexical, copy, N * (int64_t)C, V, (cudaStream_t)stream);
-    if (rc) return rc;
-    dgrad_gl = reinterpret_cast<const float*>(copy);
-    split = 1;      // both tensor-core kernels read the split copy
-  }
   // e^(2 proj) tables of the tensor-core kernels (second region of the workspace)
   float* ec = ws_ok ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) +
                                                joint_split_bytes(H, V)) : nullptr;
@@ -223,13 +214,7 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
     simt_parts = 2;
     tables = true;
   }
-  if (!split && joint_wgrad2_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
-    int rc = joint_wgrad2_launch(proj_ctx, proj_frame, grad_blank, grad_lexical, N, C, H, V,
-                                 grad_w_blank, grad_b_blank, grad_w_vocab, grad_b_vocab,
-                                 (cudaStream_t)stream);
-    if (rc) return rc;
-    simt_parts &= ~2;
-  } else if (ws_ok && joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
+  if (ws_ok && joint_wgrad_tc_supported(N, C, H, V, grad_lexical, proj_ctx, proj_frame)) {
     if (!tables) {
       int rc = joint_exp_tables_launch(proj_ctx, proj_frame, N, C, H, ec, ef, (cudaStream_t)stream);
       if (rc) return rc;
@@ -248,4 +233,16 @@ extern "C" int lt_joint_backward(const float* proj_ctx, const float* proj_frame,
   return joint_backward_simt(proj_ctx, proj_frame, w_blank, w_vocab, grad_blank, grad_lexical, N,
                              C, H, V, grad_proj_ctx, grad_proj_frame, grad_w_blank, grad_b_blank,
                              grad_w_vocab, grad_b_vocab, simt_parts, (cudaStream_t)stream);
+}
+
+// fp32 rows [M, V] -> "split rows" (every row [V bf16 hi | V bf16 lo] in the same V*4 bytes): the
+// operand form lt_joint_backward takes with grad_lexical_format = 1.
+extern "C" int lt_joint_split_rows(const float* rows, void* out, int64_t M, int V, void* stream) {
+  LT_CHECK_ARG(M >= 0 && V > 0 && V % 8 == 0, "lt_joint_split_rows: need V %% 8 == 0 (M=%lld V=%d)",
+               (long long)M, V);
+  if (M == 0) return LT_OK;
+  LT_CHECK_ARG(rows && out && reinterpret_cast<uintptr_t>(rows) % 32 == 0 &&
+                   reinterpret_cast<uintptr_t>(out) % 16 == 0,
+               "lt_joint_split_rows: NULL or misaligned pointer");
+  return joint_split_rows_launch(rows, out, M, V, (cudaStream_t)stream);
 }

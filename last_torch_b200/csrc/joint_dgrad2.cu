@@ -663,19 +663,19 @@ joint_dgrad2_kernel(const __grid_constant__ CUtensorMap map_hi,
 // consumed it -- and measured 9.3 ms against 4.9 ms.
 int joint_dgrad2_multicast(int H, int V) {
   (void)V;
-  if (!getenv("LT_JOINT_DGRAD_MULTICAST") || getenv("LT_JOINT_DGRAD_PAIR")) return 1;
+  if (!option(OPT_JOINT_DGRAD_MULTICAST) || option(OPT_JOINT_DGRAD_PAIR)) return 1;
   const int njb = H / kJB;
   return (njb == 2 || njb == 4 || njb == 8) ? njb : 1;
 }
 
 // CTA-pair variant of the split-row kernel: pairs of hidden blocks (opt-in while it is measured)
 bool joint_dgrad2_pair(int H, int V) {
-  return getenv("LT_JOINT_DGRAD_PAIR") != nullptr && H % (2 * kJB) == 0 && V % 64 == 0;
+  return option(OPT_JOINT_DGRAD_PAIR) && H % (2 * kJB) == 0 && V % 64 == 0;
 }
 
 bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                             const void* pf) {
-  if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_DGRAD_V1")) return false;
+  if (option(OPT_JOINT_SIMT) || option(OPT_JOINT_DGRAD_V1)) return false;
   if (V % 64 != 0 || V < 64 || V > 256) return false;
   if (H % 128 != 0 || H > 4096) return false;
   if (N < 1 || C < 1) return false;

@@ -224,7 +224,7 @@ struct JointTcParams {
   const float* pf;       // [N, H]  e^(2 proj_frame)
   const float* w_blank;  // [H]
   const float* b_vocab;  // [V]
-  float b_blank;
+  const float* b_blank;   // device scalar
   long long M;           // N * C
   int C, H, V;
   float* blank;          // [M]
@@ -525,7 +525,7 @@ joint_forward_tc_kernel(const __grid_constant__ CUtensorMap map_hi,
           b += __shfl_xor_sync(0xffffffffu, b, 2);
           b += __shfl_xor_sync(0xffffffffu, b, 4);
           if (valid[q] && ch == 0)
-            p.blank[tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub] = b + p.b_blank;
+            p.blank[tile * 128 + q * (kFProdWarps * 4) + pw * 4 + rsub] = b + __ldg(p.b_blank);
         }
       }
     };
@@ -1171,7 +1171,7 @@ static EncodeTiledFnJ joint_encode_fn() {
 
 bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const void* pf,
                         const void* lexical) {
-  if (getenv("LT_JOINT_SIMT")) return false;
+  if (option(OPT_JOINT_SIMT)) return false;
   if (V % 32 != 0 || V < 32 || V > 256) return false;
   if (H % 64 != 0 || H > 4096) return false;
   if (N * (int64_t)C < 1) return false;
@@ -1198,7 +1198,7 @@ int joint_exp_tables_launch(const float* pc, const float* pf, int64_t N, int C, 
 }
 
 // lexical / blank of all M = N*C joint rows on tcgen05 (bf16x3 split, fp32 accumulate).
-int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
+int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, const float* bb,
                             const float* wv, const float* bv, int64_t N, int C, int H, int V,
                             float* blank, float* lexical, void* workspace, cudaStream_t stream) {
   EncodeTiledFnJ encode = joint_encode_fn();
@@ -1211,9 +1211,7 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
   CUtensorMap map_hi, map_lo;
   cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)V};
   cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-  // CTA-pair kernel (joint_fwd2.cu): every CTA loads half of the W_vocab rows
-  const bool pair = joint_fwd2_supported(N, C, H, V);
-  cuuint32_t box[2] = {64, (cuuint32_t)(pair ? V / 2 : V)};
+  cuuint32_t box[2] = {64, (cuuint32_t)V};
   cuuint32_t estr[2] = {1, 1};
   for (int i = 0; i < 2; ++i) {
     CUresult r = encode(i == 0 ? &map_hi : &map_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -1247,9 +1245,6 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
       return LT_ERR_CUDA;
     }
   }
-  if (pair)
-    return joint_fwd2_launch(map_hi, map_lo, map_out, ec, ef, wb, bb, bv, N, C, H, V, blank,
-                             lexical, stream);
   const size_t smem = (size_t)kJStages * (2 * 128 * 128 + 2 * 256 * 128) + 4 * 4096 +
                       sizeof(float) * (H + 256) + 16 * 8 + 16 + 1024;
   int dev = 0, sms = 0;
@@ -1267,7 +1262,7 @@ int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, f
 
 bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf) {
-  if (getenv("LT_JOINT_SIMT")) return false;
+  if (option(OPT_JOINT_SIMT)) return false;
   if (V % 64 != 0 || V < 64 || V > 4096) return false;
   if (H % 32 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
   if (N * (int64_t)C < 1) return false;
@@ -1276,12 +1271,12 @@ bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
 }
 
 static bool dgrad2_shape_ok(int H, int V) {
-  return !getenv("LT_JOINT_SIMT") && !getenv("LT_JOINT_DGRAD_V1") && V % 64 == 0 && V >= 64 &&
+  return !option(OPT_JOINT_SIMT) && !option(OPT_JOINT_DGRAD_V1) && V % 64 == 0 && V >= 64 &&
          V <= 256 && H % 128 == 0 && H <= 4096;
 }
 
 // fp32 rows -> rows of [V bf16 hi | V bf16 lo] (the form the lattice backward kernel can emit
-// directly); used by tests and by LT_JOINT_DGRAD_SPLIT_TEST=1
+// directly): lt_joint_split_rows
 __global__ void joint_split_rows_kernel(const float* __restrict__ g, unsigned char* __restrict__ out,
                                         long long M, int V) {
   const long long items = M * (V / 8);
@@ -1306,15 +1301,14 @@ int joint_split_rows_launch(const float* g, void* out, int64_t M, int V, cudaStr
 // split-format grad_lexical: the fused dgrad AND the tensor-core wgrad must both apply
 bool joint_backward_split_supported(int64_t N, int C, int H, int V) {
   return dgrad2_shape_ok(H, V) && (V == 128 || V == 256) && H % 128 == 0 && H <= 4096 &&
-         (H <= 256 || H % 256 == 0) && N >= 1 && C >= 32 && !getenv("LT_JOINT_WGRAD_SIMT") &&
-         !getenv("LT_JOINT_WGRAD_PAIR");
+         (H <= 256 || H % 256 == 0) && N >= 1 && C >= 32 && !option(OPT_JOINT_WGRAD_SIMT);
 }
 
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V) {
   // bf16 hi / lo of W_vocab^T; the first-generation dgrad also needs the [M, H] buffer
   const int64_t split = joint_split_bytes(H, V) + joint_table_bytes(N, C, H);
   if (dgrad2_shape_ok(H, V))
-    return split + (getenv("LT_JOINT_DGRAD_SPLIT_TEST") ? N * (int64_t)C * V * 4 : 0);
+    return split;
   return split + N * (int64_t)C * H * 4;
 }
 
@@ -1442,7 +1436,7 @@ int joint_dgrad_tc_launch(const float* pc, const float* pf, const float* wb, con
 
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf) {
-  if (getenv("LT_JOINT_SIMT") || getenv("LT_JOINT_WGRAD_SIMT")) return false;
+  if (option(OPT_JOINT_SIMT) || option(OPT_JOINT_WGRAD_SIMT)) return false;
   if (V != 128 && V != 256) return false;
   if (H % 128 != 0 || H > 4096 || (H > 256 && H % 256 != 0)) return false;
   if (N < 1 || C < 32) return false;      // a stage of kWK rows touches at most two frames

@@ -1,24 +1,30 @@
-// K1/K2 fast path, second generation: TWO utterances interleaved per cluster.
-//
-// Same shapes as lattice_fast.cu (FullNGram context_size 1, FrameDependent,
-// V in {64, 128, 192, 256}) but organised so that the sequential dependency chain
-// of one utterance (reduce -> finalise -> DSMEM all-gather -> wake-up) is hidden
-// behind the arithmetic of another one on the same SM:
-//   * a cluster of CL = V/32 CTAs owns a PAIR of utterances; every CTA runs two
-//     independent 256-thread groups (named barriers 1 and 2), group g working on
-//     utterance 2*cluster + g and on 32 destination columns (forward) / 32 source
-//     rows (backward) of it; the two groups drift freely, so while one sits in its
-//     finaliser / exchange phase the other one keeps the FMA/MUFU pipes busy;
-//   * each group has its own TMA ring (3 stages of 32 KB at V = 256) fed by one
-//     elected thread, several frames ahead of the recursion;
+// K1/K2 fast path (FullNGram context_size 1, FrameDependent, V in {64, 128, 192, 256}),
+// organised so that the sequential dependency chain of one utterance (reduce -> finalise ->
+// DSMEM all-gather -> wake-up) is hidden behind the arithmetic of another one on the same SM:
+//   * a cluster of CL = V/32 CTAs owns one utterance; a CTA is one 256-thread group working on
+//     32 destination columns (forward) / 32 source rows (backward); it uses at most 113 KB of
+//     shared memory and 128 registers per thread, so TWO CTAs (of different utterances) share
+//     an SM and drift freely: while one sits in its finaliser / exchange phase the other one
+//     keeps the FMA/MUFU pipes busy;
+//   * each CTA has its own TMA ring (3 stages of 32 KB at V = 256) fed by one elected thread,
+//     several frames ahead of the recursion;
 //   * forward, Log: the exact column maximum is established FIRST (per-thread max,
 //     two shuffles, one 1 KB exchange through shared memory), then every arc costs
 //     exactly one FFMA + one FADD + one MUFU.EX2 + one FADD; no (max, sum) pair
 //     merges anywhere, the finaliser adds eight partial sums;
 //   * the next frame's tile is pulled into registers BEFORE the group blocks on the
 //     alpha exchange, so the shared-memory reads are off the critical path;
-//   * state exchange as in lattice_fast.cu: st.async + mbarrier complete_tx, no
-//     cluster barrier and no fence inside the loop.
+//   * state exchange: st.async + mbarrier complete_tx, no cluster barrier and no fence
+//     inside the loop;
+//   * NORM (Log semiring, `alpha_norm` given): alpha is kept RENORMALISED on chip and in the
+//     `alphas` buffer -- alpha_t = alpha~_t + off_t with an exact integer offset (log2 units)
+//     off_{t+1} = off_t + floor(max_c alpha~_t[c]) -- so that every sum the recursion rounds
+//     (w + alpha, alpha + w + beta - logZ) has magnitude O(10) instead of O(logZ): at T = 1000
+//     (logZ ~ 5.5e3, one fp32 ulp = 4.9e-4) the arc posteriors keep ~1e-6 relative accuracy
+//     where the plain fp32 recursion (and the fp32 reference) has 1e-4..1e-3.  The backward
+//     kernel needs no normaliser of its own: beta~_t = beta_t - (off_T - off_t) follows the
+//     SAME per-frame shifts d_t = off_{t+1} - off_t, and the posterior exponent becomes
+//     alpha~_t[p] + w + beta~_{t+1}[q] - d_t - r with logZ = off_T + r.
 //
 // Reference semantics: lattices.py:436-462 + alignments.py:294-297 (forward),
 // alignments.py:300-318 + lattices.py:775-779 (backward), contexts.py:207-256.
@@ -53,12 +59,15 @@ struct Fast2FwdParams {
   float* alphas;
   float* alpha_final;
   int16_t* backptr;
+  int32_t* alpha_norm;   // NORM only: [B, T+2] = off_0 .. off_T (log2 units), bits of r (fp32)
 };
 
 // ============================================================== forward (K1) ==
-template <int SR, int V, int G>
-__global__ void __launch_bounds__(kGroupThreads * G, G == 1 ? 2 : 1)
+template <int SR, int V, bool NORM>
+__global__ void __launch_bounds__(kGroupThreads, 2)
 lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdParams p) {
+  static_assert(!NORM || SR == LT_LOG, "renormalisation is a Log-semiring feature");
+  constexpr int G = 1;
   using S = Sr<SR>;
   constexpr int CL = V / kCols;                 // cluster size
   constexpr int C = V + 1;
@@ -81,13 +90,14 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
   // shared-memory carve-up: [group][stage] tiles, then per-group small state
   float* tiles = reinterpret_cast<float*>(smem2) + (size_t)grp * NS * (kStageBytes / 4);
   float* small = reinterpret_cast<float*>(smem2 + (size_t)G * NS * kStageBytes);
-  constexpr int kSmallFloats = 2 * CP + 4 * kPart + 2 * 16;   // alpha x2, pmax x2, psum x2, bars
+  constexpr int kSmallFloats = 2 * CP + 4 * kPart + 2 * 16 + 4;   // alpha x2, pmax x2, psum x2, bars, shift
   small += (size_t)grp * kSmallFloats;
   float* alpha_buf = small;
   float* part_m = alpha_buf + 2 * CP;           // [2][warps][32]
   float* part_s = part_m + 2 * kPart;           // [2][warps][32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + 2 * kPart);   // NS full + 2 exchange
   uint64_t* xbar = bars + NS;
+  float* shift_slot = reinterpret_cast<float*>(bars + 16);   // NORM: d_t, written by warp 1
 
   const int cg = gt & 7;                        // column group: columns 4cg .. 4cg+3
   const int rg = gt >> 3;                       // row group: rows rg*RPT .. +RPT-1
@@ -138,6 +148,7 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
   float4 x[RPT];
   int stage = 0;
   uint32_t parity = 0;
+  int off = 0;                                  // NORM: alpha_t = alpha~_t + off (log2 units)
   if (nf > 0) {
     mbar_wait(smem_u32(&bars[0]), 0);
 #pragma unroll
@@ -163,6 +174,18 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
       }
     }
     if (p.alphas && (is_fin || is_q0)) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
+    if constexpr (NORM) {
+      // d_t = floor(max_c alpha~_t[c]): every CTA derives it from its own (identical) replica,
+      // so no exchange is needed; an integer keeps `off` exact and the subtraction below exact.
+      if (warp == 1) {
+        float m = neg_inf();
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, cur[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) shift_slot[t & 1] = is_finite(m) ? floorf(m) : 0.f;
+        if (rank == 0 && lane == 0) p.alpha_norm[(size_t)b * (p.T + 2) + t] = off;
+      }
+    }
 
     float a[RPT];
 #pragma unroll
@@ -228,6 +251,8 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
         *reinterpret_cast<float4*>(ps_buf + warp * kCols + cg * 4) = make_float4(ps[0], ps[1], ps[2], ps[3]);
     }
     group_sync(grp);   // #1: partial maxima visible; every thread holds its tile slice in registers
+    float shift = 0.f;
+    if constexpr (NORM) { shift = shift_slot[t & 1]; off += (int)shift; }
 
     if (gt == 0 && t + NS < nf) {               // the stage is free: refill it NS frames ahead
       const uint32_t bar = smem_u32(&bars[stage]);
@@ -293,7 +318,7 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
       float v;
       if constexpr (SR == LT_LOG) {
         lse2_merge(m, s, xt, xt == neg_inf() ? 0.f : 1.f);
-        v = log2_add_exp2(ab, msafe(m) + __log2f(s));
+        v = log2_add_exp2(ab, msafe(m) + __log2f(s)) - shift;
       } else if constexpr (SR == LT_MAXTROPICAL) {
         int am = __float_as_int(s);
         if (xt > m) { m = xt; am = V; }
@@ -312,7 +337,7 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
           x[i] = *reinterpret_cast<const float4*>(tile + (size_t)(r0 + i) * kCols + cg * 4);
       }
     } else if (is_q0) {
-      const float v = S::times(cur[0], to_dom<SR>(cblank));
+      const float v = S::times(cur[0], to_dom<SR>(cblank)) - shift;
       if constexpr (SR == LT_MAXTROPICAL) { if (p.backptr) p.backptr[(bt0 + t) * C] = (int16_t)-1; }
       xchg_store(nxt, 0, v, &xbar[(t + 1) & 1], CL);
     }
@@ -324,7 +349,9 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
   if (active && (is_fin || is_q0)) {
     if (p.alphas)
       for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
-    if (p.alpha_final) p.alpha_final[(size_t)b * C + q] = from_dom<SR>(cur[q]);
+    if (p.alpha_final)
+      p.alpha_final[(size_t)b * C + q] =
+          NORM ? (float)(((double)cur[q] + (double)off) * 0.6931471805599453) : from_dom<SR>(cur[q]);
   }
   if (active && rank == 0 && warp == 1) {       // dist = (+)_c alpha_T[c]  (lattices.py:496)
     if constexpr (SR == LT_LOG) {
@@ -335,7 +362,19 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
       float s = 0.f;
       for (int c = lane; c < C; c += 32) s += ex2(cur[c] - ms);            // log2 domain
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) p.dist[b] = (ms + __log2f(s)) * kLn2;
+      if constexpr (NORM) {
+        // logZ = (off_T + r) ln 2, rounded once from double; the pair (off_T, r) is what the
+        // backward kernel uses (dist[b] alone has lost r's low bits at |logZ| ~ 1e3)
+        const float r = ms + __log2f(s);
+        int32_t* an = p.alpha_norm + (size_t)b * (p.T + 2);
+        for (int t = nf + lane; t <= p.T; t += 32) an[t] = off;
+        if (lane == 0) {
+          an[p.T + 1] = __float_as_int(r);
+          p.dist[b] = (float)(((double)r + (double)off) * 0.6931471805599453);
+        }
+      } else {
+        if (lane == 0) p.dist[b] = (ms + __log2f(s)) * kLn2;
+      }
     } else {
       float m = (SR == LT_REAL) ? 0.f : neg_inf();
       for (int c = lane; c < C; c += 32) m = S::plus(m, cur[c]);
@@ -359,6 +398,7 @@ struct Fast2BwdParams {
   float* grad_lexical;
   float* beta_final;
   int split;             // LT_FLAG_GRAD_SPLIT: rows of [V bf16 hi | V bf16 lo] instead of fp32
+  const int32_t* alpha_norm;   // NORM only: written by the NORM forward kernel
 };
 
 // Four consecutive gradients of one row.  fp32: one 16-byte store.  Split rows: the same 16
@@ -380,9 +420,11 @@ __device__ __forceinline__ void store_grad4(float* row, int c4, int V, bool spli
   }
 }
 
-template <int SR, int V, int G, bool SPLIT>
-__global__ void __launch_bounds__(kGroupThreads * G, G == 1 ? 2 : 1)
+template <int SR, int V, bool SPLIT, bool NORM>
+__global__ void __launch_bounds__(kGroupThreads, 2)
 lattice_backward_fast2(const Fast2BwdParams p) {
+  static_assert(!NORM || SR == LT_LOG, "renormalisation is a Log-semiring feature");
+  constexpr int G = 1;
   using S = Sr<SR>;
   constexpr int CL = V / kCols;
   constexpr int C = V + 1;
@@ -418,7 +460,10 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   const int nf = active ? max(0, min(p.num_frames[b], p.T)) : 0;
   const size_t bt0 = (size_t)(active ? b : 0) * p.T;
   const float logz = active ? p.dist[b] : 0.f;
-  const float logz2 = logz * kLog2e;            // Log: everything on chip is in log2 units
+  // Log: everything on chip is in log2 units.  NORM: logZ = off_T + r, and the offsets cancel
+  // against those of alpha~ / beta~ up to the per-frame shift d_t (see the file comment).
+  const int32_t* an = NORM ? p.alpha_norm + (size_t)(active ? b : 0) * (p.T + 2) : nullptr;
+  const float logz2 = NORM ? __int_as_float(an[p.T + 1]) : logz * kLog2e;
   const float gscale = (active && p.grad_dist) ? p.grad_dist[b] : 1.f;
   const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
   constexpr bool split = SPLIT;      // compile-time: the fp32 kernel is unchanged
@@ -468,10 +513,12 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   const bool owner = sl == 0;
   const bool tail_owner = last_rank && warp == 0 && lane == 0;
   float n_alpha = 0.f, n_blank = 0.f, n_talpha = 0.f, n_tblank = 0.f;
+  int n_off = 0, c_off1 = 0;                    // NORM: off_t (prefetched), off_{t+1}
   if (nf > 0) {
     const size_t o = (bt0 + nf - 1) * C;
     if (owner) { n_alpha = p.alphas[o + prow]; n_blank = ldg_stream(p.blank + o + prow); }
     if (tail_owner) { n_talpha = p.alphas[o + V]; n_tblank = ldg_stream(p.blank + o + V); }
+    if constexpr (NORM) { n_off = an[nf - 1]; c_off1 = an[nf]; }
   }
 
   int stage = 0;
@@ -488,10 +535,15 @@ lattice_backward_fast2(const Fast2BwdParams p) {
     }
     if (gt == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), C * 4);
     const float c_alpha = n_alpha, c_blank = n_blank, c_talpha = n_talpha, c_tblank = n_tblank;
+    // NORM: d_t = off_{t+1} - off_t; `zref` replaces logZ in every posterior exponent
+    const float shift = NORM ? (float)(c_off1 - n_off) : 0.f;
+    const float zref = logz2 + shift;
+    if constexpr (NORM) c_off1 = n_off;
     if (t > 0) {
       const size_t o = (bt0 + t - 1) * C;
       if (owner) { n_alpha = p.alphas[o + prow]; n_blank = ldg_stream(p.blank + o + prow); }
       if (tail_owner) { n_talpha = p.alphas[o + V]; n_tblank = ldg_stream(p.blank + o + V); }
+      if constexpr (NORM) n_off = an[t - 1];
     }
     mbar_wait(smem_u32(&bars[stage]), parity);
     const float* tile = tiles + (size_t)stage * (kStageBytes / 4);
@@ -522,7 +574,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
         const float ms = msafe(m);
-        const float rs = scale_ok ? gscale * ex2(alpha_p + ms - logz2) : 0.f;
+        const float rs = scale_ok ? gscale * ex2(alpha_p + ms - zref) : 0.f;
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
@@ -554,9 +606,9 @@ lattice_backward_fast2(const Fast2BwdParams p) {
       if (owner) {
         const float bp = beta[3 + prow];
         const float bb = arc<SR>(c_blank, bp);
-        if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
+        if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
         else gb[prow] = gscale * c_alpha * bp;
-        xchg_store(nxt, 3 + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
+        xchg_store(nxt, 3 + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum,
                    &xbar[(it + 1) & 1], CL);
       }
     }
@@ -575,7 +627,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
         }
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float ms = msafe(m);
-        const float rs = scale_ok ? gscale * ex2(alpha_p + ms - logz2) : 0.f;
+        const float rs = scale_ok ? gscale * ex2(alpha_p + ms - zref) : 0.f;
         float s = 0.f;
         for (int c4 = lane * 4; c4 < V; c4 += 128) {
           const float4 w = *reinterpret_cast<const float4*>(trow + c4);
@@ -603,9 +655,9 @@ lattice_backward_fast2(const Fast2BwdParams p) {
       if (lane == 0) {
         const float bp = beta[3 + V];
         const float bb = arc<SR>(c_tblank, bp);
-        if constexpr (SR == LT_LOG) gb[V] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
+        if constexpr (SR == LT_LOG) gb[V] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
         else gb[V] = gscale * c_talpha * bp;
-        xchg_store(nxt, 3 + V, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
+        xchg_store(nxt, 3 + V, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum,
                    &xbar[(it + 1) & 1], CL);
       }
     }
@@ -613,9 +665,14 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   float* beta = beta_buf + (nf & 1) * BP;
   if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
   if (active && p.beta_final) {
+    // NORM: beta_0 = beta~_0 + (off_T - off_0)
+    const double boff = NORM ? (double)(an[p.T] - an[0]) : 0.0;
+    auto out = [&](float v) {
+      return NORM ? (float)(((double)v + boff) * 0.6931471805599453) : from_dom<SR>(v);
+    };
     if (gt < kRows)
-      p.beta_final[(size_t)b * C + rank * kRows + gt] = from_dom<SR>(beta[3 + rank * kRows + gt]);
-    if (last_rank && gt == 0) p.beta_final[(size_t)b * C + V] = from_dom<SR>(beta[3 + V]);
+      p.beta_final[(size_t)b * C + rank * kRows + gt] = out(beta[3 + rank * kRows + gt]);
+    if (last_rank && gt == 0) p.beta_final[(size_t)b * C + V] = out(beta[3 + V]);
   }
   cluster_sync_all();
 }
@@ -661,28 +718,29 @@ static int launch_fast2(KernelT kernel, int grid, int threads, size_t smem, int 
   return LT_OK;
 }
 
-constexpr size_t kSmemBudget2 = 227 * 1024;
-
 }  // namespace
 
 bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical) {
-  if (flags & (LT_FLAG_FORCE_GENERIC | LT_FLAG_FAST_V1)) return false;
+  if (flags & LT_FLAG_FORCE_GENERIC) return false;
   if ((flags >> LT_FLAG_CLUSTER_SHIFT) & 0xf) return false;   // explicit cluster size => generic
   if (k >= 1 || g.n != 1) return false;
   if (g.V % 64 != 0 || g.V > 256) return false;
-  if (reinterpret_cast<uintptr_t>(lexical) % 16 != 0) return false;
+  if (lexical && reinterpret_cast<uintptr_t>(lexical) % 16 != 0) return false;
   return true;
 }
 
-// G = 1: one 256-thread group per CTA, TWO CTAs per SM (the hardware co-schedules CTAs of
-// different utterances on an SM; 33 clusters of 8 are co-resident on a B200, against 15 when
-// a CTA fills the SM).  G = 2 (LT_FLAG_PAIR_CTA): both groups in one 512-thread CTA.
-static int shared_budget(int G) { return G == 1 ? 113 * 1024 : (int)kSmemBudget2; }
+// One 256-thread CTA per (utterance, 32-column slice), at most 113 KB of shared memory so that
+// TWO CTAs share an SM (33 clusters of 8 are co-resident on a B200).
+constexpr int kSharedBudget = 113 * 1024;
+
+bool lattice_norm_supported(int semiring, const NGram& g, int k, unsigned flags) {
+  // alignment of `lexical` is the caller's business: torch allocations are 512-byte aligned
+  return semiring == LT_LOG && lattice_fast2_supported(g, k, flags, nullptr);
+}
 
 int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
                                  unsigned flags, cudaStream_t stream) {
   const int V = g.V, C = g.C, CL = V / kCols;
-  const int G = (flags & LT_FLAG_PAIR_CTA) ? 2 : 1;
   EncodeTiledFn encode = get_encode_fn2();
   if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
   CUtensorMap tmap;
@@ -698,33 +756,31 @@ int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return LT_ERR_CUDA; }
   const size_t stage = (size_t)V * kCols * 4;
   const int CP = (C + 3) & ~3;
-  const size_t small = sizeof(float) * (2 * CP + 4 * kGroupWarps * kCols + 2 * 16);
-  int stages = (int)((shared_budget(G) - G * small - 256) / (G * stage));
+  const size_t small = sizeof(float) * (2 * CP + 4 * kGroupWarps * kCols + 2 * 16 + 4);
+  int stages = (int)((kSharedBudget - small - 256) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("fast forward: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-  const size_t smem = G * (stage * stages + small);
+  const size_t smem = stage * stages + small;
   Fast2FwdParams p = {};
   p.B = base.B; p.T = base.T; p.stages = stages;
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alpha_init = base.alpha_init; p.dist = base.dist; p.alphas = base.alphas;
   p.alpha_final = base.alpha_final; p.backptr = base.backptr;
-  const int grid = ((base.B + G - 1) / G) * CL;
-  const int threads = kGroupThreads * G;
-#define LT_FWD2V(SR, VV)                                                                          \
-  return G == 1 ? launch_fast2(lattice_forward_fast2<SR, VV, 1>, grid, threads, smem, CL, stream, \
-                               tmap, p)                                                           \
-                : launch_fast2(lattice_forward_fast2<SR, VV, 2>, grid, threads, smem, CL, stream, \
-                               tmap, p);
-#define LT_FWD2(SR)                  \
-  switch (V) {                       \
-    case 64: LT_FWD2V(SR, 64)        \
-    case 128: LT_FWD2V(SR, 128)      \
-    case 192: LT_FWD2V(SR, 192)      \
-    default: LT_FWD2V(SR, 256)       \
+  p.alpha_norm = semiring == LT_LOG ? base.alpha_norm : nullptr;
+  const int grid = base.B * CL;
+#define LT_FWD2V(SR, VV, NORM) \
+  return launch_fast2(lattice_forward_fast2<SR, VV, NORM>, grid, kGroupThreads, smem, CL, stream, tmap, p);
+#define LT_FWD2(SR, NORM)                  \
+  switch (V) {                             \
+    case 64: LT_FWD2V(SR, 64, NORM)        \
+    case 128: LT_FWD2V(SR, 128, NORM)      \
+    case 192: LT_FWD2V(SR, 192, NORM)      \
+    default: LT_FWD2V(SR, 256, NORM)       \
   }
-  if (semiring == LT_LOG) { LT_FWD2(LT_LOG) }
-  if (semiring == LT_MAXTROPICAL) { LT_FWD2(LT_MAXTROPICAL) }
-  LT_FWD2(LT_REAL)
+  if (semiring == LT_LOG && p.alpha_norm) { LT_FWD2(LT_LOG, true) }
+  if (semiring == LT_LOG) { LT_FWD2(LT_LOG, false) }
+  if (semiring == LT_MAXTROPICAL) { LT_FWD2(LT_MAXTROPICAL, false) }
+  LT_FWD2(LT_REAL, false)
 #undef LT_FWD2
 #undef LT_FWD2V
 }
@@ -732,42 +788,39 @@ int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& 
 int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,
                                   unsigned flags, cudaStream_t stream) {
   const int V = g.V, C = g.C, CL = V / kCols;
-  const int G = (flags & LT_FLAG_PAIR_CTA) ? 2 : 1;
   const size_t stage = (size_t)kCols * V * 4 + (size_t)V * 4;
   const int BP = ((C + 6) & ~3) + 4;
   const size_t small = sizeof(float) * (2 * BP + 2 * 16);
-  int stages = (int)((shared_budget(G) - G * small - 256) / (G * stage));
+  int stages = (int)((kSharedBudget - small - 256) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("fast backward: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-  const size_t smem = G * (stage * stages + small);
+  const size_t smem = stage * stages + small;
   Fast2BwdParams p = {};
   p.B = base.B; p.T = base.T; p.stages = stages;
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alphas = base.alphas; p.dist = base.dist; p.grad_dist = base.grad_dist;
   p.grad_blank = base.grad_blank; p.grad_lexical = base.grad_lexical; p.beta_final = base.beta_final;
   p.split = (flags & LT_FLAG_GRAD_SPLIT) ? 1 : 0;
-  if (p.split && G != 1) { set_error("LT_FLAG_GRAD_SPLIT excludes LT_FLAG_PAIR_CTA"); return LT_ERR_UNSUPPORTED; }
-  const int grid = ((base.B + G - 1) / G) * CL;
-  const int threads = kGroupThreads * G;
-#define LT_BWD2V(SR, VV)                                                                        \
-  if (p.split)                                                                                  \
-    return launch_fast2(lattice_backward_fast2<SR, VV, 1, true>, grid, threads, smem, CL,       \
-                        stream, p);                                                             \
-  return G == 1 ? launch_fast2(lattice_backward_fast2<SR, VV, 1, false>, grid, threads, smem,   \
-                               CL, stream, p)                                                   \
-                : launch_fast2(lattice_backward_fast2<SR, VV, 2, false>, grid, threads, smem,   \
-                               CL, stream, p);
-#define LT_BWD2(SR)                  \
-  switch (V) {                       \
-    case 64: LT_BWD2V(SR, 64)        \
-    case 128: LT_BWD2V(SR, 128)      \
-    case 192: LT_BWD2V(SR, 192)      \
-    default: LT_BWD2V(SR, 256)       \
+  p.alpha_norm = semiring == LT_LOG ? base.alpha_norm : nullptr;
+  const int grid = base.B * CL;
+#define LT_BWD2K(SR, VV, SPLIT, NORM) \
+  return launch_fast2(lattice_backward_fast2<SR, VV, SPLIT, NORM>, grid, kGroupThreads, smem, CL, stream, p);
+#define LT_BWD2V(SR, VV, NORM)                        \
+  if (p.split) { LT_BWD2K(SR, VV, true, NORM) }       \
+  LT_BWD2K(SR, VV, false, NORM)
+#define LT_BWD2(SR, NORM)                  \
+  switch (V) {                             \
+    case 64: LT_BWD2V(SR, 64, NORM)        \
+    case 128: LT_BWD2V(SR, 128, NORM)      \
+    case 192: LT_BWD2V(SR, 192, NORM)      \
+    default: LT_BWD2V(SR, 256, NORM)       \
   }
-  if (semiring == LT_LOG) { LT_BWD2(LT_LOG) }
-  LT_BWD2(LT_REAL)
+  if (semiring == LT_LOG && p.alpha_norm) { LT_BWD2(LT_LOG, true) }
+  if (semiring == LT_LOG) { LT_BWD2(LT_LOG, false) }
+  LT_BWD2(LT_REAL, false)
 #undef LT_BWD2
 #undef LT_BWD2V
+#undef LT_BWD2K
 }
 
 }  // namespace lt

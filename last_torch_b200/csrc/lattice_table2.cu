@@ -575,15 +575,14 @@ static size_t t2_fixed_bytes(const TableParams& p, int R, bool backward) {
 }
 
 static bool t2_geometry(const TableParams& p, bool backward, T2Geom* g) {
-  if (getenv("LT_TABLE_V1")) return false;
+  if (option(OPT_TABLE_V1)) return false;
   if (p.k >= 1 || p.T <= 0) return false;
   if (p.V % 4 != 0) return false;                                   // 16-byte bulk copies
   if (reinterpret_cast<uintptr_t>(p.lexical) % 16 != 0) return false;
   if (backward && reinterpret_cast<uintptr_t>(p.grad_lexical) % 16 != 0) return false;
   if (!backward && p.C > kT2MaxThreads * kT2MaxQ) return false;
   if (p.C > 65535) return false;                                    // 16-bit next states
-  const char* env = getenv("LT_TABLE_CLUSTER");
-  const int forced = env ? atoi(env) : 0;
+  const int forced = option(OPT_TABLE_CLUSTER);
   for (int cl = 1; cl <= 8; cl <<= 1) {
     const int R = (p.C + cl - 1) / cl;
     if ((cl - 1) * R >= p.C) continue;                              // a rank without rows

@@ -23,6 +23,7 @@ struct FwdParams {
   float* levels;
   int16_t* backptr;
   uint8_t* termptr;
+  int32_t* alpha_norm;   // renormalised recursion state (lt_lattice_forward_norm) or nullptr
 };
 
 struct BwdParams {
@@ -41,6 +42,7 @@ struct BwdParams {
   float* grad_blank;
   float* grad_lexical;
   float* beta_final;
+  const int32_t* alpha_norm;
 };
 
 struct StrParams {
@@ -60,7 +62,16 @@ struct StrParams {
   const float* grad_dist;
   float* grad_blank_w;
   float* grad_lexical_w;
+  // (integer part, fraction) representation of the Log chain (lt_string_forward_norm)
+  int32_t* alpha_exp;            // [B,T,U1] forward out
+  int32_t* dist_norm;            // [B,2]    forward out: integer part, bits of the fraction
+  const int32_t* alpha_exp_in;   // backward in
+  const int32_t* dist_norm_in;
 };
+// (e, f) kernels exist for: Log, FrameDependent, U1 <= 1024
+inline bool string_norm_supported(int semiring, int k, int U1) {
+  return semiring == LT_LOG && k < 1 && U1 >= 1 && U1 <= 1024;
+}
 
 struct VitParams {
   NGram g;
@@ -82,14 +93,11 @@ int lattice_forward_generic_launch(int semiring, const NGram& g, int k, const Fw
                                    unsigned flags, int sm_count, cudaStream_t stream);
 int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const BwdParams& base,
                                     unsigned flags, int sm_count, cudaStream_t stream);
-// TMA / cluster fast path (lattice_fast.cu): bigram FrameDependent, V in {64..256}
-bool lattice_fast_supported(const NGram& g, int k, unsigned flags, const void* lexical);
-int lattice_forward_fast_launch(int semiring, const NGram& g, const FwdParams& base,
-                                cudaStream_t stream);
-int lattice_backward_fast_launch(int semiring, const NGram& g, const BwdParams& base,
-                                 cudaStream_t stream);
-// second generation (lattice_fast2.cu): two utterances interleaved per cluster
+// TMA / cluster fast path (lattice_fast2.cu): bigram FrameDependent, V in {64..256}; two CTAs
+// of different utterances per SM.  lexical == nullptr skips the alignment test.
 bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+// can the forward / backward pair keep alpha renormalised (FwdParams::alpha_norm)?
+bool lattice_norm_supported(int semiring, const NGram& g, int k, unsigned flags);
 int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
                                  unsigned flags, cudaStream_t stream);
 int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,
@@ -111,10 +119,13 @@ int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
                           const int32_t* states, const int32_t* labels, int B, int T, int U1,
                           float scale, const float* utt_scale, float* gblank, float* glex,
                           int split, cudaStream_t stream);
-int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
-                       int32_t* next_labels, cudaStream_t stream);
+int walk_states_launch(const NGram& g, const int32_t* labels, const int32_t* num_labels, int B,
+                       int U, int32_t* states, int32_t* next_labels, int32_t* bad,
+                       cudaStream_t stream);
 int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);
 int string_backward_launch(int semiring, const StrParams& p, cudaStream_t stream);
+int alphas_denormalize_launch(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
+                              cudaStream_t stream);
 int semiring_plus_forward_launch(int sr, const float* a, const float* b, float* out, int64_t n,
                                  cudaStream_t stream);
 int semiring_plus_backward_launch(int sr, const float* a, const float* b, const float* g,
@@ -127,7 +138,7 @@ int semiring_sum_backward_launch(int sr, const float* a, const float* out, const
 // tcgen05 joint projection (joint_tc.cu)
 bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const void* pf,
                         const void* lexical);
-int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, float bb,
+int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, const float* bb,
                             const float* wv, const float* bv, int64_t N, int C, int H, int V,
                             float* blank, float* lexical, void* workspace, cudaStream_t stream);
 bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
@@ -146,13 +157,6 @@ bool joint_backward_split_supported(int64_t N, int C, int H, int V);
 bool joint_dgrad2_pair(int H, int V);      // map_g box: 64 frames instead of 128
 int joint_dgrad2_multicast(int H, int V);  // map_g box: 128 / this frames
 int joint_split_rows_launch(const float* g, void* out, int64_t M, int V, cudaStream_t stream);
-// CTA-pair (cta_group::2) forward (joint_fwd2.cu)
-bool joint_fwd2_supported(int64_t N, int C, int H, int V);
-// pc / pf: the exponential tables (joint_exp_tables_launch); map_out: lexical [M, V], 32 x 32 box
-int joint_fwd2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_lo,
-                      const CUtensorMap_st& map_out, const float* pc,
-                      const float* pf, const float* wb, float bb, const float* bv, int64_t N,
-                      int C, int H, int V, float* blank, float* lexical, cudaStream_t stream);
 // fused dgrad + reductions (joint_dgrad2.cu)
 bool joint_dgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                             const void* pf);
@@ -161,12 +165,6 @@ int joint_dgrad2_launch(const CUtensorMap_st& map_hi, const CUtensorMap_st& map_
                         const float* pc, const float* pf, const float* wb, const float* gb,
                         const float* gl, int64_t N, int C, int H, int V, float* gpc, float* gpf,
                         cudaStream_t stream);
-// CTA-pair (cta_group::2) weight gradient (joint_wgrad2.cu)
-bool joint_wgrad2_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
-                            const void* pf);
-int joint_wgrad2_launch(const float* pc, const float* pf, const float* gb, const float* gl,
-                        int64_t N, int C, int H, int V, float* gwb, float* gbb, float* gwv,
-                        float* gbv, cudaStream_t stream);
 bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 // ec / ef: the exponential tables (joint_exp_tables_launch), not the projections

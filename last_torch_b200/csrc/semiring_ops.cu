@@ -191,4 +191,28 @@ int semiring_sum_backward_launch(int sr, const float* a, const float* out, const
   return LT_OK;
 }
 
+// alphas[b,t,c] += alpha_norm[b,t] * ln 2: turns the renormalised alpha~ of
+// lt_lattice_forward_norm into the alphas RecognitionLattice._forward returns (lattices.py:496).
+__global__ void alphas_denormalize_kernel(float* __restrict__ alphas,
+                                          const int32_t* __restrict__ alpha_norm, int T, int C,
+                                          int64_t rows) {
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int64_t b = r / T, t = r - b * T;
+    const double off = (double)alpha_norm[b * (T + 2) + t] * 0.6931471805599453;
+    float* row = alphas + r * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) row[c] = (float)((double)row[c] + off);
+  }
+}
+
+int alphas_denormalize_launch(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
+                              cudaStream_t stream) {
+  const int64_t rows = (int64_t)B * T;
+  if (rows == 0 || C == 0) return LT_OK;
+  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  const int grid = (int)(rows < 148 * 16 ? rows : 148 * 16);
+  alphas_denormalize_kernel<<<grid, threads, 0, stream>>>(alphas, alpha_norm, T, C, rows);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
 }  // namespace lt

@@ -28,8 +28,9 @@ __global__ void string_gather_kernel(int V, int C, const float* __restrict__ bla
   const float* bl = blank + bt * C;
   const float* lx = lexical + bt * (size_t)C * V;
   for (int u = threadIdx.x; u < U1; u += blockDim.x) {
-    const int s = states[(size_t)b * U1 + u];
-    const int y = labels[(size_t)b * U1 + u] - 1;
+    // states / labels from lt_walk_states are in range; anything else is clamped (memory safety)
+    const int s = min(max(states[(size_t)b * U1 + u], 0), C - 1);
+    const int y = min(max(labels[(size_t)b * U1 + u] - 1, 0), V - 1);
     blank_w[bt * U1 + u] = bl[s];
     lexical_w[bt * U1 + u] = lx[(size_t)s * V + y];
   }
@@ -49,8 +50,8 @@ __global__ void string_scatter_kernel(int V, int C, const float* __restrict__ gb
   float* bl = gblank + bt * C;
   float* lx = glex + bt * (size_t)C * V;
   for (int u = threadIdx.x; u < U1; u += blockDim.x) {
-    const int s = states[(size_t)b * U1 + u];
-    const int y = labels[(size_t)b * U1 + u] - 1;
+    const int s = min(max(states[(size_t)b * U1 + u], 0), C - 1);
+    const int y = min(max(labels[(size_t)b * U1 + u] - 1, 0), V - 1);
     const float a = gbw[bt * U1 + u], c = glw[bt * U1 + u];
     if (a != 0.f) atomicAdd(bl + s, scale * a);
     if (c != 0.f) atomicAdd(lx + (size_t)s * V + y, scale * c);
@@ -79,8 +80,8 @@ __global__ void string_scatter_split_kernel(int V, int C, const float* __restric
   float* bl = gblank + bt * C;
   unsigned char* lx = glex + bt * (size_t)C * V * 4;
   for (int u = threadIdx.x; u < U1; u += blockDim.x) {
-    const int s = states[(size_t)b * U1 + u];
-    const int y = labels[(size_t)b * U1 + u] - 1;
+    const int s = min(max(states[(size_t)b * U1 + u], 0), C - 1);
+    const int y = min(max(labels[(size_t)b * U1 + u] - 1, 0), V - 1);
     s_key[u] = s * V + y;
     s_val[u] = scale * glw[bt * U1 + u];
     const float a = gbw[bt * U1 + u];
@@ -109,26 +110,39 @@ __global__ void string_scatter_split_kernel(int V, int C, const float* __restric
 // ContextDependency.walk_states for FullNGram (contexts.py:109-146 with
 // next_state :190-205) plus the "next label" row of lattices.py:336-338 / :314-315.
 // One thread per utterance: U sequential integer steps.
-__global__ void walk_states_kernel(NGram g, const int32_t* __restrict__ labels, int B, int U,
-                                   int32_t* __restrict__ states, int32_t* __restrict__ next_labels) {
+// Positions u >= num_labels[b] (when given) are padding and read as epsilon whatever they hold:
+// they cannot influence alpha[num_labels].  A label outside [0, V] before that is an error of the
+// caller (the reference fails in one_hot, lattices.py:322): it is counted in *bad and read as
+// epsilon, so every state / label this kernel emits is in range and the gather / scatter kernels
+// never leave the [C, V] frame.
+__global__ void walk_states_kernel(NGram g, const int32_t* __restrict__ labels,
+                                   const int32_t* __restrict__ num_labels, int B, int U,
+                                   int32_t* __restrict__ states, int32_t* __restrict__ next_labels,
+                                   int32_t* __restrict__ bad) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int U1 = U + 1;
-  int s = 0;
+  const int nl = num_labels ? num_labels[b] : U;
+  int s = 0, nbad = 0;
   states[(size_t)b * U1] = 0;
   for (int u = 0; u < U; ++u) {
-    const int y = labels[(size_t)b * U + u];
+    int y = labels[(size_t)b * U + u];
+    if (u >= nl) y = 0;
+    if (y < 0 || y > g.V) { ++nbad; y = 0; }
     if (y != 0) s = ngram_next(g, s, y - 1);          // epsilon (0) stays in place
     states[(size_t)b * U1 + u + 1] = s;
     next_labels[(size_t)b * U1 + u] = y < 1 ? 1 : y;  // label 0 is read as label 1
   }
   next_labels[(size_t)b * U1 + U] = 1;
+  if (nbad && bad) atomicAdd(bad, nbad);
 }
 
-int walk_states_launch(const NGram& g, const int32_t* labels, int B, int U, int32_t* states,
-                       int32_t* next_labels, cudaStream_t stream) {
+int walk_states_launch(const NGram& g, const int32_t* labels, const int32_t* num_labels, int B,
+                       int U, int32_t* states, int32_t* next_labels, int32_t* bad,
+                       cudaStream_t stream) {
   if (B == 0) return LT_OK;
-  walk_states_kernel<<<(B + 127) / 128, 128, 0, stream>>>(g, labels, B, U, states, next_labels);
+  walk_states_kernel<<<(B + 127) / 128, 128, 0, stream>>>(g, labels, num_labels, B, U, states,
+                                                          next_labels, bad);
   LT_LAUNCHED();
   return LT_OK;
 }
@@ -341,16 +355,36 @@ int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
 // ---------------------------------------------------------------------------
 constexpr int kChunk = 8;
 
-template <int SR>
+// EXT (Log only): every chain value is carried as (e, f) = integer part + fraction in [0, 1)
+// (f = -inf, e = 0 for the semiring zero), i.e. alpha = e + f with e exact.  The numerator of a
+// T = 1000 utterance reaches |alpha| ~ 1e3 where one fp32 ulp is 6e-5; with the integer part
+// split off, every sum that is rounded (a + w, logaddexp of two neighbours, alpha + w + beta - z)
+// has magnitude O(1), and the label-lattice posteriors keep ~1e-6 relative accuracy.
+//   (e, f) <- logaddexp((ea, fa), (eb, fb)): both terms are re-based on the larger exponent of
+//   the finite ones, so the smaller term only loses bits it could not contribute anyway.
+__device__ __forceinline__ void ext_logaddexp(int ea, float fa, int eb, float fb, int& e, float& f) {
+  const bool oka = fa > neg_inf(), okb = fb > neg_inf();
+  const int base = oka ? (okb ? max(ea, eb) : ea) : (okb ? eb : 0);
+  const float xa = fa + (float)(ea - base), xb = fb + (float)(eb - base);
+  const float r = log_add_exp(xa, xb);
+  const float k = is_finite(r) ? floorf(r) : 0.f;
+  e = base + (int)k;
+  f = r - k;
+}
+
+template <int SR, bool EXT>
 __global__ void __launch_bounds__(1024)
 string_forward_fd_fast(const StrParams p) {
   using S = Sr<SR>;
+  static_assert(!EXT || SR == LT_LOG, "the (e, f) representation is a Log-semiring feature");
   __shared__ float mv[2][1024 + 1];
+  __shared__ int me[EXT ? 2 : 1][EXT ? 1024 + 1 : 1];
   const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
   const bool act = u < U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
   const size_t base = (size_t)b * p.T * U1;
   float a = (u == 0) ? S::one() : S::zero();
+  int ae = 0;                                          // EXT: alpha = ae + a
   float cb[kChunk], cl[kChunk], nb[kChunk], nl[kChunk];
   auto load = [&](int t0, float (&bb)[kChunk], float (&ll)[kChunk]) {
 #pragma unroll
@@ -362,6 +396,7 @@ string_forward_fd_fast(const StrParams p) {
     }
   };
   if (u == 0) { mv[0][0] = S::zero(); mv[1][0] = S::zero(); }   // "u - 1" of state 0
+  if constexpr (EXT) { if (u == 0) { me[0][0] = 0; me[1][0] = 0; } }
   load(0, nb, nl);
   int par = 0;
   for (int t0 = 0; t0 < nf; t0 += kChunk) {
@@ -375,12 +410,18 @@ string_forward_fd_fast(const StrParams p) {
         if (act) {
           if (p.alphas) p.alphas[base + (size_t)t * U1 + u] = a;
           mv[par][u + 1] = S::times(a, cl[i]);
+          if constexpr (EXT) {
+            p.alpha_exp[base + (size_t)t * U1 + u] = ae;
+            me[par][u + 1] = ae;
+          }
         }
         __syncthreads();
         if (act) {
           const float stay = S::times(a, cb[i]);
           const float move = mv[par][u];
-          if constexpr (SR == LT_MAXTROPICAL) {
+          if constexpr (EXT) {
+            ext_logaddexp(ae, stay, me[par][u], move, ae, a);
+          } else if constexpr (SR == LT_MAXTROPICAL) {
             const bool tb = stay >= move;
             a = tb ? stay : move;
             if (p.backptr) p.backptr[base + (size_t)t * U1 + u] = tb ? 0 : 1;
@@ -393,22 +434,39 @@ string_forward_fd_fast(const StrParams p) {
     }
   }
   if (act && p.alphas)
-    for (int t = nf; t < p.T; ++t) p.alphas[base + (size_t)t * U1 + u] = a;
+    for (int t = nf; t < p.T; ++t) {
+      p.alphas[base + (size_t)t * U1 + u] = a;
+      if constexpr (EXT) p.alpha_exp[base + (size_t)t * U1 + u] = ae;
+    }
   const int nl_b = p.num_labels[b];
-  if (act && u == nl_b) p.dist[b] = a;                          // lattices.py:375-377
-  if (u == 0 && (nl_b < 0 || nl_b >= U1)) p.dist[b] = S::zero();
+  if (act && u == nl_b) {                                       // lattices.py:375-377
+    if constexpr (EXT) {
+      p.dist[b] = (float)((double)ae + (double)a);
+      p.dist_norm[2 * b] = ae;
+      p.dist_norm[2 * b + 1] = __float_as_int(a);
+    } else {
+      p.dist[b] = a;
+    }
+  }
+  if (u == 0 && (nl_b < 0 || nl_b >= U1)) {
+    p.dist[b] = S::zero();
+    if constexpr (EXT) { p.dist_norm[2 * b] = 0; p.dist_norm[2 * b + 1] = __float_as_int(S::zero()); }
+  }
 }
 
-template <int SR>   // LT_LOG or LT_REAL
+template <int SR, bool EXT>   // LT_LOG or LT_REAL
 __global__ void __launch_bounds__(1024)
 string_backward_fd_fast(const StrParams p) {
   using S = Sr<SR>;
+  static_assert(!EXT || SR == LT_LOG, "the (e, f) representation is a Log-semiring feature");
   __shared__ float sh[2][1024 + 1];
+  __shared__ int she[EXT ? 2 : 1][EXT ? 1024 + 1 : 1];
   const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
   const bool act = u < U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
   const int nl_b = p.num_labels[b];
-  const float z = p.dist_in[b];
+  const float z = EXT ? __int_as_float(p.dist_norm_in[2 * b + 1]) : p.dist_in[b];
+  const int ze = EXT ? p.dist_norm_in[2 * b] : 0;       // EXT: numerator = ze + z
   const float g = p.grad_dist ? p.grad_dist[b] : 1.f;
   const bool reachable = (nl_b >= 0 && nl_b < U1) && (SR == LT_REAL ? true : is_finite(z));
   const size_t base = (size_t)b * p.T * U1;
@@ -420,8 +478,11 @@ string_backward_fd_fast(const StrParams p) {
   }
   if (!reachable) return;
   float beta = (u == nl_b) ? S::one() : S::zero();
+  int be = 0;                                           // EXT: beta = be + beta
   float cb[kChunk], cl[kChunk], ca[kChunk], nb[kChunk], nl[kChunk], na[kChunk];
-  auto load = [&](int i0, float (&bb)[kChunk], float (&ll)[kChunk], float (&aa)[kChunk]) {
+  int cae[EXT ? kChunk : 1], nae[EXT ? kChunk : 1];
+  auto load = [&](int i0, float (&bb)[kChunk], float (&ll)[kChunk], float (&aa)[kChunk],
+                  int (&ee)[EXT ? kChunk : 1]) {
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {
       const int t = nf - 1 - (i0 + i);
@@ -430,34 +491,49 @@ string_backward_fd_fast(const StrParams p) {
       bb[i] = ok ? ldg_stream(p.blank_w + o) : S::one();
       ll[i] = ok ? ldg_stream(p.lexical_w + o) : S::zero();
       aa[i] = ok ? p.alphas_in[o] : S::zero();
+      if constexpr (EXT) ee[i] = ok ? p.alpha_exp_in[o] : 0;
     }
   };
   if (u == 0) { sh[0][U1] = S::zero(); sh[1][U1] = S::zero(); }   // "u + 1" of the last state
-  load(0, nb, nl, na);
+  if constexpr (EXT) { if (u == 0) { she[0][U1] = 0; she[1][U1] = 0; } }
+  load(0, nb, nl, na, nae);
   int par = 0;
   for (int i0 = 0; i0 < nf; i0 += kChunk) {
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) { cb[i] = nb[i]; cl[i] = nl[i]; ca[i] = na[i]; }
-    load(i0 + kChunk, nb, nl, na);
+    for (int i = 0; i < kChunk; ++i) {
+      cb[i] = nb[i]; cl[i] = nl[i]; ca[i] = na[i];
+      if constexpr (EXT) cae[i] = nae[i];
+    }
+    load(i0 + kChunk, nb, nl, na, nae);
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {
       const int t = nf - 1 - (i0 + i);
       if (t >= 0) {                                   // uniform over the block
         if (act) sh[par][u] = beta;
+        if constexpr (EXT) { if (act) she[par][u] = be; }
         __syncthreads();
         if (act) {
           const float bn = sh[par][u + 1];
           const float bb = S::times(cb[i], beta);
           const float lb = S::times(cl[i], bn);
           const size_t o = base + (size_t)t * U1 + u;
-          if constexpr (SR == LT_LOG) {
+          if constexpr (EXT) {
+            // exponent = (alpha_f + w + beta_f - z_f) + (alpha_e + beta_e - z_e): the integer
+            // parts cancel exactly, the fractions are O(1)
+            const int bne = she[par][u + 1];
+            const int eb = cae[i] + be - ze, el = cae[i] + bne - ze;
+            p.grad_blank_w[o] = g * fast_exp((ca[i] + bb - z) + (float)eb);
+            p.grad_lexical_w[o] = g * fast_exp((ca[i] + lb - z) + (float)el);
+            ext_logaddexp(be, bb, bne, lb, be, beta);
+          } else if constexpr (SR == LT_LOG) {
             p.grad_blank_w[o] = g * fast_exp(ca[i] + bb - z);
             p.grad_lexical_w[o] = g * fast_exp(ca[i] + lb - z);
+            beta = S::plus(bb, lb);
           } else {
             p.grad_blank_w[o] = g * ca[i] * beta;
             p.grad_lexical_w[o] = g * ca[i] * bn;
+            beta = S::plus(bb, lb);
           }
-          beta = S::plus(bb, lb);
         }
         par ^= 1;
       }
@@ -468,7 +544,14 @@ string_backward_fd_fast(const StrParams p) {
 template <int SR>
 static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
   if (p.k < 1 && p.U1 <= 1024) {
-    string_forward_fd_fast<SR><<<p.B, block_for(p.U1), 0, stream>>>(p);
+    if constexpr (SR == LT_LOG) {
+      if (p.alpha_exp) {
+        string_forward_fd_fast<SR, true><<<p.B, block_for(p.U1), 0, stream>>>(p);
+        LT_LAUNCHED();
+        return LT_OK;
+      }
+    }
+    string_forward_fd_fast<SR, false><<<p.B, block_for(p.U1), 0, stream>>>(p);
     LT_LAUNCHED();
     return LT_OK;
   }
@@ -491,7 +574,14 @@ template <int SR>
 static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
   if constexpr (SR != LT_MAXTROPICAL) {
     if (p.k < 1 && p.U1 <= 1024) {
-      string_backward_fd_fast<SR><<<p.B, block_for(p.U1), 0, stream>>>(p);
+      if constexpr (SR == LT_LOG) {
+        if (p.alpha_exp_in) {
+          string_backward_fd_fast<SR, true><<<p.B, block_for(p.U1), 0, stream>>>(p);
+          LT_LAUNCHED();
+          return LT_OK;
+        }
+      }
+      string_backward_fd_fast<SR, false><<<p.B, block_for(p.U1), 0, stream>>>(p);
       LT_LAUNCHED();
       return LT_OK;
     }

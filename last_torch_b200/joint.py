@@ -12,76 +12,87 @@ import torch
 from . import _native as N
 
 
+def joint_forward_raw(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab):
+  """(blank [N,C], lexical [N,C,V]) from proj_ctx [C,H], proj_frame [N,H]; b_blank is a device
+  scalar read by the kernel (no host synchronisation)."""
+  proj_ctx = N.require_cuda(proj_ctx, 'proj_ctx')
+  proj_frame = N.require_cuda(proj_frame, 'proj_frame')
+  w_blank = N.require_cuda(w_blank.reshape(-1), 'w_blank')
+  b_blank = N.require_cuda(b_blank.reshape(-1), 'b_blank')
+  w_vocab = N.require_cuda(w_vocab, 'w_vocab')
+  b_vocab = N.require_cuda(b_vocab, 'b_vocab')
+  n, h = proj_frame.shape
+  c = proj_ctx.shape[0]
+  v = w_vocab.shape[0]
+  dev = proj_frame.device
+  blank = torch.empty([n, c], dtype=torch.float32, device=dev)
+  lexical = torch.empty([n, c, v], dtype=torch.float32, device=dev)
+  workspace = torch.empty([int(N.lib().lt_joint_workspace_bytes(n, c, h, v))], dtype=torch.uint8,
+                          device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_joint_forward(
+        N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(b_blank), N.ptr(w_vocab),
+        N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.ptr(workspace),
+        N.stream_ptr(dev)), 'lt_joint_forward')
+  return blank, lexical
+
+
+def joint_backward_raw(proj_ctx, proj_frame, w_blank, w_vocab, g_blank, g_lexical, fmt=0):
+  """Gradients w.r.t. (proj_ctx, proj_frame, w_blank [1,H], b_blank [], w_vocab, b_vocab).
+  fmt=1: g_lexical holds split rows (include/last_lattice.h, lt_joint_backward)."""
+  n, h = proj_frame.shape
+  c = proj_ctx.shape[0]
+  v = w_vocab.shape[0]
+  dev = proj_frame.device
+  w_blank = w_blank.reshape(-1)
+  g_blank = N.require_cuda(g_blank, 'grad_blank')
+  g_lexical = N.require_cuda(g_lexical, 'grad_lexical')
+  g_pc = torch.zeros_like(proj_ctx)
+  g_pf = torch.zeros_like(proj_frame)
+  g_wb = torch.zeros_like(w_blank)
+  g_bb = torch.zeros([1], dtype=torch.float32, device=dev)
+  g_wv = torch.zeros_like(w_vocab)
+  g_bv = torch.zeros([v], dtype=torch.float32, device=dev)
+  workspace = torch.empty([int(N.lib().lt_joint_backward_workspace_bytes(n, c, h, v))],
+                          dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_joint_backward(
+        N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(w_vocab), N.ptr(g_blank),
+        N.ptr(g_lexical), n, c, h, v, N.ptr(g_pc), N.ptr(g_pf), N.ptr(g_wb), N.ptr(g_bb),
+        N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), fmt, N.stream_ptr(dev)), 'lt_joint_backward')
+  return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv
+
+
 class _JointProjection(torch.autograd.Function):
   """(blank [N,C], lexical [N,C,V]) from proj_ctx [C,H], proj_frame [N,H]."""
 
   @staticmethod
-  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, split_grad=None):
-    proj_ctx = N.require_cuda(proj_ctx, 'proj_ctx')
-    proj_frame = N.require_cuda(proj_frame, 'proj_frame')
-    w_blank = N.require_cuda(w_blank.reshape(-1), 'w_blank')
-    w_vocab = N.require_cuda(w_vocab, 'w_vocab')
-    b_vocab = N.require_cuda(b_vocab, 'b_vocab')
-    n, h = proj_frame.shape
-    c = proj_ctx.shape[0]
-    v = w_vocab.shape[0]
-    dev = proj_frame.device
-    blank = torch.empty([n, c], dtype=torch.float32, device=dev)
-    lexical = torch.empty([n, c, v], dtype=torch.float32, device=dev)
-    workspace = torch.empty([int(N.lib().lt_joint_workspace_bytes(n, c, h, v))], dtype=torch.uint8,
-                            device=dev)
-    with torch.cuda.device(dev):
-      N.check(N.lib().lt_joint_forward(
-          N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), float(b_blank), N.ptr(w_vocab),
-          N.ptr(b_vocab), n, c, h, v, N.ptr(blank), N.ptr(lexical), N.ptr(workspace),
-          N.stream_ptr(dev)), 'lt_joint_forward')
-    ctx.save_for_backward(proj_ctx, proj_frame, w_blank, w_vocab)
-    ctx.split_grad = split_grad
-    if split_grad is not None:     # may the consumer hand back split-row gradients (ops.SplitGrad)?
-      split_grad.joint_ok = bool(N.lib().lt_joint_backward_split_supported(n, c, h, v))
+  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab):
+    blank, lexical = joint_forward_raw(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab)
+    ctx.save_for_backward(proj_ctx.contiguous(), proj_frame.contiguous(), w_blank, w_vocab)
     return blank, lexical
 
   @staticmethod
   def backward(ctx, g_blank, g_lexical):
     proj_ctx, proj_frame, w_blank, w_vocab = ctx.saved_tensors
-    n, h = proj_frame.shape
-    c = proj_ctx.shape[0]
-    v = w_vocab.shape[0]
-    dev = proj_frame.device
-    g_blank = N.require_cuda(g_blank, 'grad_blank')
-    g_lexical = N.require_cuda(g_lexical, 'grad_lexical')
-    sg = ctx.split_grad
-    fmt = 1 if (sg is not None and sg.emitted) else 0      # split rows from the lattice backward
-    if sg is not None:
-      sg.emitted = False
-      if fmt and g_lexical.data_ptr() != sg.ptr:
-        # autograd summed / copied / hooked the opaque buffer: its bytes are no longer split rows
-        raise RuntimeError('grad_lexical was modified between the lattice backward and the joint '
-                           'backward; set LT_NO_SPLIT_GRAD=1 to hand gradients over in float32')
-    g_pc = torch.zeros_like(proj_ctx)
-    g_pf = torch.zeros_like(proj_frame)
-    g_wb = torch.zeros_like(w_blank)
-    g_bb = torch.zeros([1], dtype=torch.float32, device=dev)
-    g_wv = torch.zeros_like(w_vocab)
-    g_bv = torch.zeros([v], dtype=torch.float32, device=dev)
-    workspace = torch.empty([int(N.lib().lt_joint_backward_workspace_bytes(n, c, h, v))],
-                            dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-      N.check(N.lib().lt_joint_backward(
-          N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(w_vocab), N.ptr(g_blank),
-          N.ptr(g_lexical), n, c, h, v, N.ptr(g_pc), N.ptr(g_pf), N.ptr(g_wb), N.ptr(g_bb),
-          N.ptr(g_wv), N.ptr(g_bv), N.ptr(workspace), fmt, N.stream_ptr(dev)), 'lt_joint_backward')
-    return g_pc, g_pf, g_wb.reshape(1, -1), g_bb.reshape(()), g_wv, g_bv, None
+    return joint_backward_raw(proj_ctx, proj_frame, w_blank, w_vocab.contiguous(),
+                              g_blank.contiguous(), g_lexical.contiguous())
 
 
-def joint_all_frames(fn, cache, frames, split_grad=None):
-  """fn: weight_fns.JointWeightFn; cache [C,E]; frames [batch..., T, D]."""
-  batch_shape = frames.shape[:-1]
+def joint_projections(fn, cache, frames):
+  """The two library GEMMs in front of the kernel: proj_ctx [C,H], proj_frame [N,H]."""
   proj_ctx = fn.context_projection(cache)                                   # [C,H]
   proj_frame = fn.blank_projection(frames.reshape(-1, frames.shape[-1]))    # [N,H]
+  return proj_ctx, proj_frame
+
+
+def joint_all_frames(fn, cache, frames):
+  """fn: weight_fns.JointWeightFn; cache [C,E]; frames [batch..., T, D]."""
+  batch_shape = frames.shape[:-1]
+  proj_ctx, proj_frame = joint_projections(fn, cache, frames)
   blank, lexical = _JointProjection.apply(
       proj_ctx, proj_frame, fn.joint_projection_to_blank.weight,
       fn.joint_projection_to_blank.bias.reshape(()), fn.joint_projection_to_vocab.weight,
-      fn.joint_projection_to_vocab.bias, split_grad)
+      fn.joint_projection_to_vocab.bias)
   c, v = proj_ctx.shape[0], fn.vocab_size
   return blank.reshape(*batch_shape, c), lexical.reshape(*batch_shape, c, v)

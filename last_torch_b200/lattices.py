@@ -53,6 +53,14 @@ class RecognitionLattice(nn.Module, Generic[T]):
     self.weight_fn = self.weight_fn_factory(self.context)
     # kernel dispatch options (see include/last_lattice.h); 0 = automatic
     self.kernel_flags = 0
+    # JointWeightFn + FullNGram: hand the arc posteriors to the joint network's backward as
+    # split rows (ops.JointLatticeLoss); False keeps them in float32
+    self.split_grad_handover = ops.SPLIT_GRAD_DEFAULT
+    # Range-check the reference labels (0 <= label <= vocab_size for the first num_labels
+    # positions) and raise ValueError like the reference's one_hot (lattices.py:317-324) -- one
+    # 4-byte device-to-host read per call.  False skips the read; the kernels then treat an
+    # out-of-range label as epsilon (memory-safe, but the loss of that utterance is not defined).
+    self.validate_labels = True
 
   def build_cache(self) -> T:
     """Builds the weight function cache (lattices.py:118-129)."""
@@ -94,13 +102,10 @@ class RecognitionLattice(nn.Module, Generic[T]):
       raise ValueError('num_labels and num_frames have different batch_dims: '
                        f'{tuple(num_labels.shape)} vs {batch_dims}')
 
-  def _arc_weights(self, cache, frames, batch_dims, split_grad=None):
+  def _arc_weights(self, cache, frames, batch_dims):
     """Dense arc weights of all frames, flattened to one batch axis:
     blank [B,T,C], lexical [B,T,C,V] (fp32, contiguous, CUDA)."""
-    if split_grad is not None:
-      blank, lexical = self.weight_fn.all_frames(cache, frames, split_grad=split_grad)
-    else:
-      blank, lexical = self.weight_fn.all_frames(cache, frames)
+    blank, lexical = self.weight_fn.all_frames(cache, frames)
     c, v = self.context.shape()
     t = frames.shape[-2]
     blank = blank.reshape(-1, t, c)
@@ -114,19 +119,37 @@ class RecognitionLattice(nn.Module, Generic[T]):
                       f'{blank.dtype} / {lexical.dtype}')
     return blank.contiguous(), lexical.contiguous()
 
-  def _string_indices(self, labels, device):
+  def _string_indices(self, labels, num_labels, device):
     """context states along the label string and the label leaving each of
-    them (lattices.py:336-338; label 0 is read as label 1, :314-315)."""
+    them (lattices.py:336-338; label 0 is read as label 1, :314-315).
+
+    Positions u >= num_labels[b] are padding: whatever they hold (-1, vocab_size + 1, ...) is
+    read as epsilon -- they cannot influence alpha[num_labels] (alignments.py:327-329 only moves
+    forward along the string).  A label outside [0, vocab_size] BEFORE num_labels is an error:
+    the reference fails in one_hot (lattices.py:322); here the kernel counts such labels and,
+    with validate_labels, a ValueError is raised."""
     labels = labels.reshape(-1, labels.shape[-1]).to(device=device, dtype=torch.int32)
+    nl = ops._as_i32(num_labels.reshape(-1), device)
+    v = self.context.shape()[1]
     if self._is_table():
       # generic DFA: integer gathers through the table (contexts.py:109-146)
+      pos = torch.arange(labels.shape[1], device=device, dtype=torch.int32)[None, :]
+      real = pos < nl[:, None]
+      bad = (real & ((labels < 0) | (labels > v))).sum().to(torch.int32).reshape(1)
+      labels = torch.where(real & (labels >= 0) & (labels <= v), labels,
+                           torch.zeros_like(labels))
       states = self.context.walk_states(labels.long()).to(torch.int32).contiguous()
       ones = torch.ones_like(labels[:, :1])
       next_labels = torch.cat([torch.where(labels == 0, torch.ones_like(labels), labels), ones],
                               dim=1).contiguous()
-      return states, next_labels
-    return ops.walk_states(labels.contiguous(), self.context.vocab_size,
-                           self.context.context_size)
+    else:
+      states, next_labels, bad = ops.walk_states(labels.contiguous(), nl,
+                                                 self.context.vocab_size,
+                                                 self.context.context_size)
+    if self.validate_labels and int(bad) != 0:
+      raise ValueError(f'labels must be in [0, vocab_size={v}] for the first num_labels '
+                       f'positions of every utterance; found {int(bad)} label(s) outside')
+    return states, next_labels
 
   # -- public API --------------------------------------------------------------
 
@@ -142,31 +165,63 @@ class RecognitionLattice(nn.Module, Generic[T]):
                                    labels=labels, num_labels=num_labels,
                                    semiring=semirings.Log)
     v, n, k = self._geometry()
-    # JointWeightFn + FullNGram: the lattice backward may hand its posteriors to the projection's
-    # backward in the tensor cores' operand form (ops.SplitGrad); `lexical` stays in this method
-    split_grad = (ops.SplitGrad() if type(self.weight_fn) is weight_fns.JointWeightFn
-                  and not self._is_table() else None)
-    blank, lexical = self._arc_weights(cache, frames, batch_dims, split_grad)
+    if type(self.weight_fn) is weight_fns.JointWeightFn and not self._is_table():
+      return self._joint_loss(cache, frames, num_frames, labels, num_labels, batch_dims, v, n, k)
+    blank, lexical = self._arc_weights(cache, frames, batch_dims)
     dev = blank.device
-    states, next_labels = self._string_indices(labels, dev)
+    states, next_labels = self._string_indices(labels, num_labels, dev)
     if self._is_table():
       nf = ops._as_i32(num_frames.reshape(-1), dev)
       log_z, _ = ops.TableLatticeForward.apply(blank, lexical, nf, self.context, N.LOG, k)
       num = ops.StringForward.apply(blank, lexical, nf, states, next_labels,
                                     ops._as_i32(num_labels.reshape(-1), dev), N.LOG, v, k)
       return (log_z - num).reshape(batch_dims)
-    loss, _, _, _ = ops.LatticeLoss.apply(
+    loss, _, _ = ops.LatticeLoss.apply(
         blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
-        ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags, split_grad)
+        ops._as_i32(num_labels.reshape(-1), dev), v, n, k, self.kernel_flags)
+    return loss.reshape(batch_dims)
+
+  def _joint_loss(self, cache, frames, num_frames, labels, num_labels, batch_dims, v, n, k):
+    """JointWeightFn inside a FullNGram lattice: the two input projections are library GEMMs,
+    everything after them -- tanh joint, vocabulary projection, denominator, numerator and the
+    whole backward -- is ONE autograd node (ops.JointLatticeLoss); the dense arc weights and
+    their gradients never become autograd tensors."""
+    from . import joint
+    if not frames.is_cuda:
+      raise RuntimeError(
+          f'frames live on {frames.device}; last_torch_b200 runs on CUDA (sm_100a) only '
+          'and has no CPU fallback')
+    fn = self.weight_fn
+    fn._check_lazy(cache, frames)
+    dev = frames.device
+    t = frames.shape[-2]
+    b = 1
+    for d in batch_dims:
+      b *= d
+    states, next_labels = self._string_indices(labels, num_labels, dev)
+    proj_ctx, proj_frame = joint.joint_projections(fn, cache, frames)
+    loss, _, _ = ops.JointLatticeLoss.apply(
+        proj_ctx, proj_frame, fn.joint_projection_to_blank.weight,
+        fn.joint_projection_to_blank.bias.reshape(()), fn.joint_projection_to_vocab.weight,
+        fn.joint_projection_to_vocab.bias, ops._as_i32(num_frames.reshape(-1), dev), states,
+        next_labels, ops._as_i32(num_labels.reshape(-1), dev), b, t, v, n, k, self.kernel_flags,
+        self.split_grad_handover)
     return loss.reshape(batch_dims)
 
   def shortest_path(self, frames: torch.Tensor, num_frames: torch.Tensor,
-                    cache: Optional[T] = None):
+                    cache: Optional[T] = None, reference_compat: bool = False):
     """Highest scoring path (lattices.py:185-247).
 
     Returns (alignment_labels [batch_dims..., T * num_alignment_states],
     num_alignment_labels [batch_dims...], path_weights [batch_dims...]).
     Labels are the TRUE labels: 0 = blank, 1..vocab_size lexical.
+
+    reference_compat=True reproduces the label encoding of the reference as shipped
+    (lattices.py:242-244 takes argmax over the V-wide mask without the `1 +`): lexical
+    label y is reported as y - 1, so label 1 is indistinguishable from blank.  The reference's
+    second defect (D5: for B > 1 every utterance's path lands in batch element 0's mask) is NOT
+    reproduced; for a single utterance and FrameDependent the output then equals the
+    reference's (tests/lattices_test.py:238-242).
     """
     batch_dims = self._check_frames(frames, num_frames)
     if cache is None:
@@ -183,6 +238,8 @@ class RecognitionLattice(nn.Module, Generic[T]):
             blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), v, n, k,
             self.kernel_flags)
     num_alignment_states = self.alignment.num_states()
+    if reference_compat:
+      labels = torch.clamp(labels - 1, min=0)
     alignment_labels = labels.to(torch.int64).reshape(*batch_dims, -1)
     num_alignment_labels = num_alignment_states * num_frames.to(dev)
     return alignment_labels, num_alignment_labels, path_weights.reshape(batch_dims)
@@ -200,7 +257,7 @@ class RecognitionLattice(nn.Module, Generic[T]):
     v, n, k = self._geometry()
     blank, lexical = self._arc_weights(cache, frames, batch_dims)
     dev = blank.device
-    states, next_labels = self._string_indices(labels, dev)
+    states, next_labels = self._string_indices(labels, num_labels, dev)
     dist = ops.StringForward.apply(
         blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
         ops._as_i32(num_labels.reshape(-1), dev), sr, v, k)

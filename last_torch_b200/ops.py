@@ -14,6 +14,11 @@ from . import _native as N
 
 _SR_ID = {'Real': N.REAL, 'Log': N.LOG, 'MaxTropical': N.MAXTROPICAL}
 
+# Renormalised recursion state for the Log semiring (include/last_lattice.h: lt_*_norm): on by
+# default wherever a kernel supports it; LT_NO_NORM=1 (read once, at import) selects the plain
+# fp32 recursion everywhere -- that is the "plain" column of profiles/r02_parity_errors.json.
+USE_NORM = not os.environ.get('LT_NO_NORM')
+
 
 def _as_i32(x: torch.Tensor, device) -> torch.Tensor:
   """Index tensors may arrive as float (tests/lattices_test.py:49-51)."""
@@ -98,11 +103,21 @@ class SemiringSum(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 
 def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_levels,
-                         want_backptr, alpha_init=None, stream=None):
+                         want_backptr, alpha_init=None, stream=None, norm=False):
   """Buffers are allocated on the current stream; the kernel is enqueued on
-  `stream` when one is given (the caller orders it against the current stream)."""
+  `stream` when one is given (the caller orders it against the current stream).
+
+  norm=True asks for the renormalised recursion state where a kernel supports it
+  (lt_lattice_forward_norm): the 7th result is then the alpha_norm buffer [B, T+2] and `alphas`
+  holds alpha~ (only lt_lattice_backward_norm / lt_alphas_denormalize understand the pair);
+  otherwise the 7th result is None."""
   B, T, C = blank.shape
   dev = blank.device
+  alpha_norm = None
+  if (norm and USE_NORM and T > 0 and B > 0 and
+      N.lib().lt_lattice_norm_supported(sr, V, n, k, flags) and
+      lexical.data_ptr() % 16 == 0):
+    alpha_norm = torch.empty([B, T + 2], dtype=torch.int32, device=dev)
   dist = torch.empty([B], dtype=torch.float32, device=dev)
   alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev)
   alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)
@@ -115,11 +130,23 @@ def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_le
     if fld:
       termptr = torch.empty([B, T, C], dtype=torch.uint8, device=dev)
   with torch.cuda.device(dev), torch.cuda.stream(stream):       # stream(None) is a no-op
-    N.check(N.lib().lt_lattice_forward(
+    N.check(N.lib().lt_lattice_forward_norm(
         sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alpha_init),
         N.ptr(dist), N.ptr(alphas), N.ptr(alpha_final), N.ptr(levels), N.ptr(backptr),
-        N.ptr(termptr), flags, N.stream_ptr(dev)), 'lt_lattice_forward')
-  return dist, alphas, alpha_final, levels, backptr, termptr
+        N.ptr(termptr), N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_forward')
+  return dist, alphas, alpha_final, levels, backptr, termptr, alpha_norm
+
+
+def _denormalized(alphas, alpha_norm):
+  """True alphas (lattices.py:496) from the renormalised pair; a copy, the pair stays intact."""
+  if alpha_norm is None:
+    return alphas
+  out = alphas.clone()
+  B, T, C = out.shape
+  with torch.cuda.device(out.device):
+    N.check(N.lib().lt_alphas_denormalize(N.ptr(out), N.ptr(alpha_norm), B, T, C,
+                                          N.stream_ptr(out.device)), 'lt_alphas_denormalize')
+  return out
 
 
 def _check_weights(blank, lexical, V, C):
@@ -144,20 +171,21 @@ class LatticeForward(torch.autograd.Function):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
     need_grad = any(ctx.needs_input_grad[:2])
-    dist, alphas, alpha_final, levels, backptr, termptr = _lattice_forward_raw(
+    dist, alphas, alpha_final, levels, backptr, termptr, alpha_norm = _lattice_forward_raw(
         sr, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
-        want_backptr=need_grad)
+        want_backptr=need_grad, norm=True)
     ctx.geom = (sr, V, n, k, flags)
     ctx.save_for_backward(blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr,
-                          termptr)
-    ctx.mark_non_differentiable(alphas)
-    return dist, alphas
+                          termptr, alpha_norm)
+    out_alphas = _denormalized(alphas, alpha_norm)
+    ctx.mark_non_differentiable(out_alphas)
+    return dist, out_alphas
 
   @staticmethod
   def backward(ctx, g_dist, _g_alphas):
     sr, V, n, k, flags = ctx.geom
-    blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr, termptr = \
-        ctx.saved_tensors
+    (blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr, termptr,
+     alpha_norm) = ctx.saved_tensors
     B, T, C = blank.shape
     dev = blank.device
     g_dist = N.require_cuda(g_dist, 'grad_dist')
@@ -173,10 +201,10 @@ class LatticeForward(torch.autograd.Function):
       else:
         gb = torch.empty_like(blank)
         gl = torch.empty_like(lexical)
-        N.check(N.lib().lt_lattice_backward(
+        N.check(N.lib().lt_lattice_backward_norm(
             sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
-            N.ptr(levels), N.ptr(dist), N.ptr(g_dist), N.ptr(gb), N.ptr(gl), None, flags,
-            N.stream_ptr(dev)), 'lt_lattice_backward')
+            N.ptr(levels), N.ptr(dist), N.ptr(g_dist), N.ptr(gb), N.ptr(gl), None,
+            N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_backward')
     return gb, gl, None, None, None, None, None, None
 
 
@@ -187,7 +215,7 @@ def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
   blank, lexical = _check_weights(blank.detach(), lexical.detach(), V, C)
   B, T, _ = blank.shape
   dev = blank.device
-  dist, _, alpha_final, _, backptr, termptr = _lattice_forward_raw(
+  dist, _, alpha_final, _, backptr, termptr, _ = _lattice_forward_raw(
       N.MAXTROPICAL, V, n, k, blank, lexical, num_frames, flags, want_levels=False,
       want_backptr=True)
   labels = torch.empty([B, T, max(k, 0) + 1], dtype=torch.int32, device=dev)
@@ -332,18 +360,22 @@ def table_viterbi_path(blank, lexical, num_frames, context, k):
 # K3: numerator on the label lattice
 # ---------------------------------------------------------------------------
 
-def walk_states(labels: torch.Tensor, V: int, n: int):
-  """labels [B,U] int32 (CUDA) -> (states [B,U+1], next_labels [B,U+1]) int32:
+def walk_states(labels: torch.Tensor, num_labels, V: int, n: int):
+  """labels [B,U] int32 (CUDA), num_labels [B] int32 or None ->
+  (states [B,U+1], next_labels [B,U+1], bad [1]) int32:
   FullNGram.walk_states (contexts.py:109-146) and labels ++ [1] with label 0
-  read as label 1 (lattices.py:314-315, :336-338), in one kernel."""
+  read as label 1 (lattices.py:314-315, :336-338), in one kernel.  Positions
+  u >= num_labels[b] are read as epsilon; `bad` counts labels outside [0, V] before that."""
   labels = N.require_cuda(labels, 'labels', torch.int32)
   B, U = labels.shape
   states = torch.empty([B, U + 1], dtype=torch.int32, device=labels.device)
   next_labels = torch.empty([B, U + 1], dtype=torch.int32, device=labels.device)
+  bad = torch.zeros([1], dtype=torch.int32, device=labels.device)
   with torch.cuda.device(labels.device):
-    N.check(N.lib().lt_walk_states(V, n, N.ptr(labels), B, U, N.ptr(states), N.ptr(next_labels),
-                                   N.stream_ptr(labels.device)), 'lt_walk_states')
-  return states, next_labels
+    N.check(N.lib().lt_walk_states_checked(
+        V, n, N.ptr(labels), N.ptr(num_labels), B, U, N.ptr(states), N.ptr(next_labels),
+        N.ptr(bad), N.stream_ptr(labels.device)), 'lt_walk_states')
+  return states, next_labels, bad
 
 
 _SIDE_STREAMS = {}
@@ -385,10 +417,17 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
   bw = torch.empty([B, T, U1], dtype=torch.float32, device=dev)
   lw = torch.empty([B, T, U1], dtype=torch.float32, device=dev)
   dist = torch.empty([B], dtype=torch.float32, device=dev)
+  # (integer part, fraction) chain where the kernels have it (lt_string_forward_norm); it is
+  # used with and without gradients so that the value does not depend on requires_grad
+  use_ext = bool(USE_NORM and B > 0 and T > 0 and N.lib().lt_string_norm_supported(sr, k, U1))
   alphas = (torch.empty([B, T, U1], dtype=torch.float32, device=dev)
-            if need_grad and sr != N.MAXTROPICAL else None)
+            if (need_grad and sr != N.MAXTROPICAL) or use_ext else None)
   backptr = (torch.empty([B, T, U1], dtype=torch.uint8, device=dev)
              if need_grad and sr == N.MAXTROPICAL else None)
+  alpha_exp = dist_norm = None
+  if use_ext:
+    alpha_exp = torch.empty([B, T, U1], dtype=torch.int32, device=dev)
+    dist_norm = torch.empty([B, 2], dtype=torch.int32, device=dev)
   with torch.cuda.device(dev):
     if side is not None:
       if ready is not None:
@@ -400,15 +439,18 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
       N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
                                  N.ptr(next_labels), B, T, U1, N.ptr(bw), N.ptr(lw),
                                  N.stream_ptr(dev)), 'lt_string_gather')
-      N.check(L.lt_string_forward(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames),
-                                  N.ptr(num_labels), B, T, U1, N.ptr(dist), N.ptr(alphas),
-                                  N.ptr(backptr), N.stream_ptr(dev)), 'lt_string_forward')
-  return dist, bw, lw, alphas, backptr
+      N.check(L.lt_string_forward_norm(sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames),
+                                       N.ptr(num_labels), B, T, U1, N.ptr(dist), N.ptr(alphas),
+                                       N.ptr(backptr), N.ptr(alpha_exp), N.ptr(dist_norm),
+                                       N.stream_ptr(dev)), 'lt_string_forward')
+  return dist, bw, lw, alphas, backptr, (alpha_exp, dist_norm)
 
 
 def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist, g_dist,
-                     side=None, ready=None, out=None):
-  """Numerator posteriors on the label lattice: (grad_blank_w, grad_lexical_w)."""
+                     side=None, ready=None, out=None, ext=(None, None)):
+  """Numerator posteriors on the label lattice: (grad_blank_w, grad_lexical_w).
+  `ext` = (alpha_exp, dist_norm) of a lt_string_forward_norm run, or (None, None)."""
+  alpha_exp, dist_norm = ext
   B, T, U1 = bw.shape
   dev = bw.device
   gbw, glw = out if out is not None else (torch.empty_like(bw), torch.empty_like(lw))
@@ -419,26 +461,11 @@ def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dis
       else:
         side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-      N.check(N.lib().lt_string_backward(
+      N.check(N.lib().lt_string_backward_norm(
           sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels), B, T, U1,
           N.ptr(alphas), N.ptr(backptr), N.ptr(dist), N.ptr(g_dist), N.ptr(gbw), N.ptr(glw),
-          N.stream_ptr(dev)), 'lt_string_backward')
+          N.ptr(alpha_exp), N.ptr(dist_norm), N.stream_ptr(dev)), 'lt_string_backward')
   return gbw, glw
-
-
-class SplitGrad:
-  """Handshake between JointWeightFn's projection and the lattice loss inside
-  RecognitionLattice.forward: when both sides can (`joint_ok`, set by the projection's forward;
-  lt_lattice_backward_split_supported), the lattice backward kernel writes grad_lexical as
-  "split rows" -- [V bf16 hi | V bf16 lo] in the V*4 bytes of every row, the operand form of the
-  tensor-core joint backward (include/last_lattice.h, lt_joint_backward) -- and sets `emitted`,
-  which the projection's backward reads.  The buffer travels through autograd as an opaque
-  float32 tensor of the right shape; `lexical` has no other consumer on that path."""
-
-  def __init__(self):
-    self.joint_ok = False
-    self.emitted = False
-    self.ptr = 0          # data_ptr of the split-row buffer (the consumer checks it got THAT one)
 
 
 def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scale=None,
@@ -461,102 +488,160 @@ class StringForward(torch.autograd.Function):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
     need_grad = any(ctx.needs_input_grad[:2])
-    dist, bw, lw, alphas, backptr = _string_forward_raw(
+    dist, bw, lw, alphas, backptr, ext = _string_forward_raw(
         sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad)
     ctx.geom = (sr, V, C, k, tuple(blank.shape))
     ctx.save_for_backward(bw, lw, num_frames, num_labels, alphas, backptr, dist, states,
-                          next_labels)
+                          next_labels, *ext)
     return dist
 
   @staticmethod
   def backward(ctx, g_dist):
     sr, V, C, k, shape = ctx.geom
-    bw, lw, num_frames, num_labels, alphas, backptr, dist, states, next_labels = ctx.saved_tensors
+    (bw, lw, num_frames, num_labels, alphas, backptr, dist, states, next_labels, alpha_exp,
+     dist_norm) = ctx.saved_tensors
     g_dist = N.require_cuda(g_dist, 'grad_dist')
     gb = torch.zeros(shape, dtype=torch.float32, device=bw.device)
     gl = torch.zeros((*shape, V), dtype=torch.float32, device=bw.device)
     gbw, glw = _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist,
-                                g_dist)
+                                g_dist, ext=(alpha_exp, dist_norm))
     _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl)
     return gb, gl, None, None, None, None, None, None, None
 
 
-class LatticeLoss(torch.autograd.Function):
-  """loss = logZ - numerator (lattices.py:131-183) as ONE autograd node.
+def _loss_forward(blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags,
+                  need_grad):
+  """K1 (Log) over the dense lattice on a high-priority stream; beside it, on a side stream,
+  the whole numerator: gather, K3 forward and (when gradients are needed) K3 backward, i.e. the
+  UNSCALED numerator posteriors -- the label lattice is tiny, so its three kernels fit under the
+  HBM-bound K1.  Returns (log_z, num, saved) with `saved` the tensors _loss_backward needs."""
+  C = blank.shape[-1]
+  dev = blank.device
+  cur = torch.cuda.current_stream(dev)
+  side, hp = _side_stream(dev), _hp_stream(dev)
+  ready = torch.cuda.Event()
+  ready.record(cur)
+  hp.wait_event(ready)
+  # NOTE: every buffer handed to a kernel on `hp` / `side` must stay referenced until the
+  # joins below -- a tensor dropped earlier returns to the current stream's pool and the
+  # next allocation may alias it while the other stream still writes to it.
+  fwd = _lattice_forward_raw(
+      N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
+      want_backptr=False, stream=hp, norm=True)
+  log_z, alphas, _, levels, _, _, alpha_norm = fwd
+  strf = _string_forward_raw(
+      N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
+      side=side, ready=ready)
+  num, bw, lw, s_alphas, _, ext = strf
+  gbw = glw = None
+  if need_grad:
+    # posteriors of the label lattice with unit upstream gradient (scaled in backward)
+    gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
+                                None, side=side, ready=ready, ext=ext)
+  cur.wait_stream(hp)
+  cur.wait_stream(side)
+  del fwd, strf
+  return log_z, num, (alphas, levels, gbw, glw, alpha_norm)
 
-  Forward: K1 (Log) over the dense lattice on a high-priority stream; beside it,
-  on a side stream, the whole numerator: gather, K3 forward and (when gradients
-  are needed) K3 backward, i.e. the UNSCALED numerator posteriors -- the label
-  lattice is tiny, so its three kernels fit under the HBM-bound K1.
-  Backward: K2 writes g * (arc posteriors) straight into the weight-gradient
-  buffers; the stored numerator posteriors are then scattered in, weighted by
-  the upstream gradient of each utterance.
-  """
+
+def _loss_backward(blank, lexical, num_frames, log_z, saved, states, next_labels, V, n, k, flags,
+                   g_den, g_numr, split):
+  """K2 writes g_den * (arc posteriors) straight into the weight-gradient buffers (as split rows
+  when `split`); the stored numerator posteriors are then scattered in, weighted by g_numr."""
+  alphas, levels, gbw, glw, alpha_norm = saved
+  B, T, C = blank.shape
+  dev = blank.device
+  g_den = N.require_cuda(g_den, 'grad').contiguous()
+  g_numr = N.require_cuda(g_numr, 'grad').contiguous()
+  gb = torch.empty_like(blank)
+  gl = torch.empty_like(lexical)
+  if split:
+    flags |= N.FLAG_GRAD_SPLIT
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_lattice_backward_norm(
+        N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+        N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None,
+        N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_backward')
+  _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr,
+                  split=split)
+  return gb, gl
+
+
+class LatticeLoss(torch.autograd.Function):
+  """loss = logZ - numerator (lattices.py:131-183) on dense arc weights as ONE autograd node
+  (see _loss_forward / _loss_backward).  Returns (loss, log_z, numerator)."""
 
   @staticmethod
-  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags,
-              split_grad=None):
+  def forward(ctx, blank, lexical, num_frames, states, next_labels, num_labels, V, n, k, flags):
     C = blank.shape[-1]
     blank, lexical = _check_weights(blank, lexical, V, C)
-    ctx.split_grad = split_grad
     need_grad = any(ctx.needs_input_grad[:2])
-    dev = blank.device
-    cur = torch.cuda.current_stream(dev)
-    side, hp = _side_stream(dev), _hp_stream(dev)
-    ready = torch.cuda.Event()
-    ready.record(cur)
-    hp.wait_event(ready)
-    # NOTE: every buffer handed to a kernel on `hp` / `side` must stay referenced until the
-    # joins below -- a tensor dropped earlier returns to the current stream's pool and the
-    # next allocation may alias it while the other stream still writes to it.
-    fwd = _lattice_forward_raw(
-        N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
-        want_backptr=False, stream=hp)
-    log_z, alphas, _, levels, _, _ = fwd
-    num, bw, lw, s_alphas, _ = _string_forward_raw(
-        N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
-        side=side, ready=ready)
-    gbw = glw = None
-    if need_grad:
-      # posteriors of the label lattice with unit upstream gradient (scaled in backward)
-      gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
-                                  None, side=side, ready=ready)
-    cur.wait_stream(hp)
-    cur.wait_stream(side)
-    del fwd
+    log_z, num, saved = _loss_forward(blank, lexical, num_frames, states, next_labels,
+                                      num_labels, V, n, k, flags, need_grad)
     ctx.geom = (V, n, k, flags)
-    ctx.save_for_backward(blank, lexical, num_frames, log_z, alphas, levels, gbw, glw, states,
-                          next_labels)
-    ctx.mark_non_differentiable(alphas)
-    return log_z - num, log_z, num, alphas
+    ctx.save_for_backward(blank, lexical, num_frames, log_z, states, next_labels, *saved)
+    return log_z - num, log_z, num
 
   @staticmethod
-  def backward(ctx, g_loss, g_logz, g_num, _g_alphas):
+  def backward(ctx, g_loss, g_logz, g_num):
     V, n, k, flags = ctx.geom
-    (blank, lexical, num_frames, log_z, alphas, levels, gbw, glw, states,
-     next_labels) = ctx.saved_tensors
-    B, T, C = blank.shape
-    dev = blank.device
+    blank, lexical, num_frames, log_z, states, next_labels, *saved = ctx.saved_tensors
     g_den = g_loss if g_logz is None else g_loss + g_logz
     g_numr = -g_loss if g_num is None else g_num - g_loss
-    g_den = N.require_cuda(g_den, 'grad').contiguous()
-    g_numr = N.require_cuda(g_numr, 'grad').contiguous()
-    gb = torch.empty_like(blank)
-    gl = torch.empty_like(lexical)
-    sg = ctx.split_grad
-    split = bool(sg is not None and sg.joint_ok and ctx.needs_input_grad[1] and
-                 not os.environ.get('LT_NO_SPLIT_GRAD') and
+    gb, gl = _loss_backward(blank, lexical, num_frames, log_z, saved, states, next_labels, V, n,
+                            k, flags, g_den, g_numr, split=False)
+    return gb, gl, None, None, None, None, None, None, None, None
+
+
+# Hand the arc posteriors from the lattice backward to the joint network's backward as "split
+# rows" (include/last_lattice.h: LT_FLAG_GRAD_SPLIT) where both kernels support it.
+# LT_NO_SPLIT_GRAD=1 (read once, at import) or RecognitionLattice.split_grad_handover = False
+# keeps them in float32.
+SPLIT_GRAD_DEFAULT = not os.environ.get('LT_NO_SPLIT_GRAD')
+
+
+class JointLatticeLoss(torch.autograd.Function):
+  """JointWeightFn over all frames (weight_fns.py:194-227) + GNAT loss (lattices.py:131-183) as
+  ONE autograd node: proj_ctx [C,H], proj_frame [N,H] and the two output projections in, loss
+  [B] out.  The dense arc weights and their gradients are internals of the node -- no autograd
+  tensor, hook or accumulation ever sees them -- which is what makes the split-row hand-over
+  (K2 emits [V bf16 hi | V bf16 lo] rows, the tensor-core dgrad / wgrad load them as operands)
+  safe: this is the streaming-gradient intent of lattices.py:644-799 (_backward +
+  BackwardStepCallback), with the callback replaced by the joint network's own backward."""
+
+  @staticmethod
+  def forward(ctx, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, num_frames, states,
+              next_labels, num_labels, B, T, V, n, k, flags, allow_split):
+    from . import joint
+    blank, lexical = joint.joint_forward_raw(proj_ctx, proj_frame, w_blank, b_blank, w_vocab,
+                                             b_vocab)
+    C = proj_ctx.shape[0]
+    blank = blank.reshape(B, T, C)
+    lexical = lexical.reshape(B, T, C, V)
+    need_grad = any(ctx.needs_input_grad[:6])
+    log_z, num, saved = _loss_forward(blank, lexical, num_frames, states, next_labels,
+                                      num_labels, V, n, k, flags, need_grad)
+    ctx.geom = (B, T, V, n, k, flags, bool(allow_split))
+    ctx.save_for_backward(proj_ctx, proj_frame, w_blank, w_vocab, blank, lexical, num_frames,
+                          log_z, states, next_labels, *saved)
+    return log_z - num, log_z, num
+
+  @staticmethod
+  def backward(ctx, g_loss, g_logz, g_num):
+    from . import joint
+    B, T, V, n, k, flags, allow_split = ctx.geom
+    (proj_ctx, proj_frame, w_blank, w_vocab, blank, lexical, num_frames, log_z, states,
+     next_labels, *saved) = ctx.saved_tensors
+    g_den = g_loss if g_logz is None else g_loss + g_logz
+    g_numr = -g_loss if g_num is None else g_num - g_loss
+    nfr, h = proj_frame.shape
+    c = proj_ctx.shape[0]
+    U1 = states.shape[-1]
+    split = bool(allow_split and U1 <= 4096 and
+                 N.lib().lt_joint_backward_split_supported(nfr, c, h, V) and
                  N.lib().lt_lattice_backward_split_supported(N.LOG, V, n, k, flags))
-    if split:
-      flags |= N.FLAG_GRAD_SPLIT
-    with torch.cuda.device(dev):
-      N.check(N.lib().lt_lattice_backward(
-          N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
-          N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None, flags,
-          N.stream_ptr(dev)), 'lt_lattice_backward')
-    _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr,
-                    split=split)
-    if sg is not None:
-      sg.emitted = split
-      sg.ptr = gl.data_ptr()
-    return gb, gl, None, None, None, None, None, None, None, None, None
+    gb, gl = _loss_backward(blank, lexical, num_frames, log_z, saved, states, next_labels, V, n,
+                            k, flags, g_den, g_numr, split=split)
+    grads = joint.joint_backward_raw(proj_ctx, proj_frame, w_blank, w_vocab, gb.reshape(nfr, c),
+                                     gl.reshape(nfr, c, V), fmt=1 if split else 0)
+    return (*grads, None, None, None, None, None, None, None, None, None, None, None)

@@ -4,9 +4,10 @@ Same class names and constructor arguments as the reference
 (/root/reference/last_torch/weight_fns.py).  Differences that are deliberate
 fixes of reference defects (documented in DESIGN.md):
 
-  * JointWeightFn owns its four projections as registered parameters (created
-    on the first call, when the embedding / feature sizes are known) instead
-    of building fresh random nn.Linear layers on every call.
+  * JointWeightFn owns its four projections as parameters registered in the
+    constructor (the two input projections as torch lazy modules when their
+    widths are not given) instead of building fresh random nn.Linear layers on
+    every call.
   * SharedEmbCacher returns the [num_context_states, embedding_size] table.
 
 Every WeightFn additionally exposes `all_frames(cache, frames)`, which
@@ -154,26 +155,51 @@ class JointWeightFn(WeightFn[torch.Tensor]):
     self.vocab_size = vocab_size
     self.hidden_size = hidden_size
     self.device = device
-    self.context_projection: Optional[nn.Linear] = None
-    self.blank_projection: Optional[nn.Linear] = None
-    self.joint_projection_to_blank: Optional[nn.Linear] = None
-    self.joint_projection_to_vocab: Optional[nn.Linear] = None
-    if embedding_size is not None and feature_size is not None:
-      self._materialize(embedding_size, feature_size, torch.device(device or 'cpu'))
+    dev = torch.device(device or 'cpu')
+    h, v = hidden_size, vocab_size
+    # All four projections are REGISTERED in the constructor, so an optimizer, a DDP wrapper or
+    # load_state_dict built before the first call sees them.  The reference signature does not
+    # carry the two input widths (weight_fns.py:187-192): without them the input projections are
+    # torch lazy modules -- their (uninitialised) parameters exist from the start and are
+    # materialised in place by the first call, by materialize(), or by load_state_dict.
+    self.context_projection = (nn.Linear(embedding_size, h, bias=False, device=dev)
+                               if embedding_size is not None else
+                               nn.LazyLinear(h, bias=False, device=dev))
+    self.blank_projection = (nn.Linear(feature_size, h, bias=False, device=dev)
+                             if feature_size is not None else
+                             nn.LazyLinear(h, bias=False, device=dev))
+    self.joint_projection_to_blank = nn.Linear(h, 1, device=dev)
+    self.joint_projection_to_vocab = nn.Linear(h, v, device=dev)
 
-  def _materialize(self, embedding_size: int, feature_size: int, device) -> None:
-    h, v = self.hidden_size, self.vocab_size
-    self.context_projection = nn.Linear(embedding_size, h, bias=False, device=device)
-    self.blank_projection = nn.Linear(feature_size, h, bias=False, device=device)
-    self.joint_projection_to_blank = nn.Linear(h, 1, device=device)
-    self.joint_projection_to_vocab = nn.Linear(h, v, device=device)
+  def materialize(self, embedding_size: int, feature_size: int) -> None:
+    """Gives the two input projections their shapes without evaluating anything (a rank with an
+    empty shard, a parameter count before the first batch).  No-op once they are known."""
+    for layer, width in ((self.context_projection, embedding_size),
+                         (self.blank_projection, feature_size)):
+      if torch.nn.parameter.is_lazy(layer.weight):
+        dev = self.joint_projection_to_blank.weight.device
+        with torch.no_grad():
+          layer(torch.zeros([1, width], device=dev))
 
-  def _ensure(self, cache: torch.Tensor, frame: torch.Tensor) -> None:
-    if self.context_projection is None:
-      self._materialize(cache.shape[-1], frame.shape[-1], frame.device)
+  def is_materialized(self) -> bool:
+    return not any(torch.nn.parameter.is_lazy(l.weight)
+                   for l in (self.context_projection, self.blank_projection))
+
+  def _check_lazy(self, cache, frame):
+    """torch's lazy modules crash (segfault in the in-place initialiser) when they take their
+    shapes inside a torch.func transform: give the shapes first, outside of it."""
+    if self.is_materialized():
+      return
+    from torch._C import _functorch
+    if _functorch.maybe_current_level() is not None:
+      raise RuntimeError(
+          'JointWeightFn was built without embedding_size / feature_size and is used for the '
+          'first time inside a torch.func transform; call materialize(embedding_size, '
+          'feature_size) (or evaluate it once) before')
+    self.materialize(cache.shape[-1], frame.shape[-1])
 
   def forward(self, cache, frame, state=None):
-    self._ensure(cache, frame)
+    self._check_lazy(cache, frame)
     context_embeddings = cache
     if state is None:
       frame = frame.unsqueeze(-2)                      # [..., 1, D]
@@ -186,10 +212,10 @@ class JointWeightFn(WeightFn[torch.Tensor]):
     lexical = self.joint_projection_to_vocab(joint)
     return blank, lexical
 
-  def all_frames(self, cache, frames, split_grad=None):
-    self._ensure(cache, frames)
+  def all_frames(self, cache, frames):
+    self._check_lazy(cache, frames)
     from . import joint as joint_ops   # CUDA (tcgen05) vocabulary projection
-    return joint_ops.joint_all_frames(self, cache, frames, split_grad)
+    return joint_ops.joint_all_frames(self, cache, frames)
 
 
 class SharedEmbCacher(WeightFnCacher[torch.Tensor]):

@@ -88,3 +88,67 @@ def test_two_rank_gloo_matches_single_process():
   for r in range(world):
     np.testing.assert_allclose(out[r][0], full_loss, rtol=1e-5)
     np.testing.assert_allclose(out[r][1], full_g, rtol=1e-4, atol=1e-5)
+
+
+# ---- sharded_loss_and_grads: lazily-shaped parameters, a rank with an empty shard ------------
+
+class _FakeLattice(torch.nn.Module):
+  """Stands in for RecognitionLattice on CPU: same call signature, parameters that only get
+  their shapes on the first call (weight_fns.JointWeightFn without embedding / feature sizes)."""
+
+  def __init__(self):
+    super().__init__()
+    sys.path.insert(0, ROOT)
+    import last_torch_b200 as lt
+    torch.manual_seed(0)
+    self.weight_fn_cacher = lt.weight_fns.SharedEmbCacher(num_context_states=4, embedding_size=6)
+    self.weight_fn = lt.weight_fns.JointWeightFn(vocab_size=3, hidden_size=5)
+
+  def build_cache(self):
+    return self.weight_fn_cacher()
+
+  def forward(self, frames, num_frames, labels, num_labels, cache=None):
+    cache = self.build_cache() if cache is None else cache
+    blank, lexical = self.weight_fn(cache, frames[:, 0])
+    return torch.tanh(blank).sum(-1) + (lexical ** 2).sum((-1, -2)) * num_frames
+
+
+def _fake_inputs():
+  g = torch.Generator().manual_seed(5)
+  frames = torch.randn([1, 2, 7], generator=g)            # ONE utterance: rank 1 gets nothing
+  return frames, torch.tensor([2.0]), torch.zeros([1, 1]), torch.zeros([1])
+
+
+def _sharded_worker(rank, world, port, out):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from last_torch_b200 import distributed as D
+  lattice = _FakeLattice()
+  assert not lattice.weight_fn.is_materialized()
+  total, grads, loss = D.sharded_loss_and_grads(lattice, *_fake_inputs())
+  names = [n for n, _ in lattice.named_parameters()]
+  out[rank] = (float(total), {n: g.numpy().copy() for n, g in zip(names, grads)}, int(loss.numel()))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_loss_with_lazy_parameters_and_an_empty_shard():
+  """parameters created on the first call must not be dropped from the first step,
+  and a rank with no utterances must still join the all-reduce with the same bucket layout."""
+  world = 2
+  port = _free_port()
+  out = mp.Manager().dict()
+  mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+  lattice = _FakeLattice()
+  loss = lattice(*_fake_inputs())
+  params = dict(lattice.named_parameters())
+  ref = torch.autograd.grad(loss.sum(), list(params.values()))
+  assert out[0][2] == 1 and out[1][2] == 0
+  for r in range(world):
+    np.testing.assert_allclose(out[r][0], float(loss.sum()), rtol=1e-6)
+    assert set(out[r][1]) == set(params)
+    for (name, _), g in zip(params.items(), ref):
+      np.testing.assert_allclose(out[r][1][name], g.numpy(), rtol=1e-5, atol=1e-7, err_msg=name)
+    assert np.abs(out[r][1]['weight_fn.context_projection.weight']).max() > 0

@@ -249,14 +249,10 @@ def test_joint_lattice_golden(fname, split):
     fn.joint_projection_to_blank.bias.copy_(T(g['b_blank']))
     fn.joint_projection_to_vocab.weight.copy_(T(g['w_vocab']))
     fn.joint_projection_to_vocab.bias.copy_(T(g['b_vocab']))
-  if not split:
-    os.environ['LT_NO_SPLIT_GRAD'] = '1'
-  try:
-    loss = lattice(frames=T(g['frames']), num_frames=T(g['num_frames']), labels=T(g['labels']),
-                   num_labels=T(g['num_labels']))
-    loss.sum().backward()
-  finally:
-    os.environ.pop('LT_NO_SPLIT_GRAD', None)
+  lattice.split_grad_handover = split
+  loss = lattice(frames=T(g['frames']), num_frames=T(g['num_frames']), labels=T(g['labels']),
+                 num_labels=T(g['num_labels']))
+  loss.sum().backward()
   npt.assert_allclose(loss.detach().cpu(), g['loss'], rtol=1e-5)
   got = {'cache': cacher.embedding.weight.grad, 'w_ctx': fn.context_projection.weight.grad,
          'w_frame': fn.blank_projection.weight.grad,
@@ -295,15 +291,11 @@ def test_joint_lattice_full_size_properties():
   num_labels = torch.full([b], u, device='cuda')
 
   def run(no_split):
-    if no_split:
-      os.environ['LT_NO_SPLIT_GRAD'] = '1'
-    try:
-      lattice.zero_grad()
-      loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
-      loss.sum().backward()
-      return loss.detach().clone(), {n: p.grad.clone() for n, p in lattice.named_parameters()}
-    finally:
-      os.environ.pop('LT_NO_SPLIT_GRAD', None)
+    lattice.split_grad_handover = not no_split
+    lattice.zero_grad()
+    loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
+    loss.sum().backward()
+    return loss.detach().clone(), {n: p.grad.clone() for n, p in lattice.named_parameters()}
 
   loss_s, g_s = run(False)
   loss_f, g_f = run(True)
@@ -366,7 +358,8 @@ def test_call_joint_weight_fn():
 def test_joint_lattice_split_row_gradients(vocab, hidden, batch, frames):
   """RecognitionLattice.forward with JointWeightFn: the lattice backward kernel hands its arc
   posteriors to the tensor-core joint backward as split rows ([V bf16 hi | V bf16 lo], read by
-  TMA; ops.SplitGrad).  Same parameter gradients as the fp32 hand-over (LT_NO_SPLIT_GRAD=1),
+  TMA; ops.JointLatticeLoss).  Same parameter gradients as the fp32 hand-over
+  (split_grad_handover = False),
   with ragged utterances (zero rows on padding frames) and label strings with repeated bigrams
   (several numerator positions land on one arc of the split buffer)."""
   import os
@@ -389,15 +382,11 @@ def test_joint_lattice_split_row_gradients(vocab, hidden, batch, frames):
   weights = torch.rand([batch], device='cuda') + 0.5
 
   def run(no_split):
-    if no_split:
-      os.environ['LT_NO_SPLIT_GRAD'] = '1'
-    try:
-      lattice.zero_grad()
-      loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
-      (loss * weights).sum().backward()
-      return loss.detach(), [p.grad.clone() for p in lattice.parameters()]
-    finally:
-      os.environ.pop('LT_NO_SPLIT_GRAD', None)
+    lattice.split_grad_handover = not no_split
+    lattice.zero_grad()
+    loss = lattice(frames=x, num_frames=num_frames, labels=labels, num_labels=num_labels)
+    (loss * weights).sum().backward()
+    return loss.detach(), [p.grad.clone() for p in lattice.parameters()]
 
   loss_s, g_s = run(False)
   loss_f, g_f = run(True)
@@ -553,3 +542,124 @@ def test_locally_normalized_lattice_loss():
                      num_labels=torch.tensor([u], device='cuda'), cache=None)
       total += float(torch.exp(-loss))
   npt.assert_allclose(total, 1.0, rtol=1e-5)
+
+
+# ---- round-2 additions: label validation, lazily-shaped parameters, autograd hygiene ---------
+
+def _bigram_table_lattice(vocab, table):
+  lt = _lt()
+  return lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=vocab, context_size=1),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_factory=lambda _: lt.weight_fns.TableWeightFn(table),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+
+
+@pytest.mark.parametrize('vocab', [5, 64])
+def test_labels_out_of_range(vocab):
+  """labels are range-checked.  Padding after num_labels may hold anything (-1,
+  vocab_size + 1): same loss and gradients as zero padding.  A label outside [0, vocab_size]
+  BEFORE num_labels raises ValueError (the reference fails in one_hot, lattices.py:322); with
+  validate_labels = False the kernels stay inside their buffers."""
+  b, t, u = 3, 9, 5
+  c = vocab + 1
+  torch.manual_seed(vocab)
+  table = torch.randn([b, t, c, 1 + vocab], device='cuda', requires_grad=True)
+  frames = torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None].expand(b, t, 1)
+  nf = T([9, 7, 4])
+  good = torch.randint(1, vocab + 1, [b, u], device='cuda')
+  nl = torch.tensor([5, 3, 0], device='cuda')
+  pos = torch.arange(u, device='cuda')[None]
+  zero_pad = torch.where(pos < nl[:, None], good, torch.zeros_like(good))
+  junk_pad = torch.where(pos < nl[:, None], good,
+                         torch.where(pos % 2 == 0, torch.full_like(good, -1),
+                                     torch.full_like(good, vocab + 1)))
+  lattice = _bigram_table_lattice(vocab, table)
+  res = []
+  for lab in (zero_pad, junk_pad):
+    loss = lattice(frames=frames, num_frames=nf, labels=lab, num_labels=nl, cache=None)
+    (g,) = torch.autograd.grad(loss.sum(), table)
+    res.append((loss.detach().cpu().numpy(), g.cpu().numpy()))
+  npt.assert_array_equal(res[0][0], res[1][0])
+  npt.assert_array_equal(res[0][1], res[1][1])
+  for bad_value in (-1, vocab + 1, 10 ** 6):
+    bad = good.clone()
+    bad[0, 1] = bad_value
+    with pytest.raises(ValueError, match='labels must be in'):
+      lattice(frames=frames, num_frames=nf, labels=bad, num_labels=nl, cache=None)
+    with pytest.raises(ValueError, match='labels must be in'):
+      lattice._string_forward(cache=None, frames=frames, num_frames=nf, labels=bad,
+                              num_labels=nl, semiring=_lt().semirings.Log)
+    lattice.validate_labels = False
+    guard = torch.full_like(table, 3.0)                    # neighbouring allocation
+    loss = lattice(frames=frames, num_frames=nf, labels=bad, num_labels=nl, cache=None)
+    (g,) = torch.autograd.grad(loss.sum(), table)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(g).all()) and float(guard.min()) == 3.0
+    lattice.validate_labels = True
+
+
+def test_joint_weight_fn_parameters_exist_before_the_first_call():
+  """an optimizer built BEFORE the first forward must train all four projections."""
+  lt = _lt()
+  torch.manual_seed(3)
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=128, context_size=1),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=128, device='cuda'))
+  names = [n for n, _ in lattice.named_parameters()]
+  assert len(names) == 7 and not lattice.weight_fn.is_materialized()
+  opt = torch.optim.SGD(lattice.parameters(), lr=0.05)
+  x = torch.randn([2, 6, 16], device='cuda')
+  args = dict(frames=x, num_frames=T([6, 4]), labels=T([[3, 9, 100], [7, 7, 0]]),
+              num_labels=T([3, 2]))
+  first = None
+  for _ in range(3):
+    opt.zero_grad()
+    loss = lattice(**args).sum()
+    loss.backward()
+    opt.step()
+    first = float(loss) if first is None else first
+  assert lattice.weight_fn.is_materialized()
+  assert all(p.grad is not None and float(p.grad.abs().max()) > 0 for p in lattice.parameters())
+  assert float(loss) < first
+
+
+def test_split_row_handover_is_invisible_to_autograd():
+  """The arc-weight gradients never become autograd tensors on the JointWeightFn path
+  (ops.JointLatticeLoss): parameter hooks, gradient accumulation over two backward passes and
+  a non-trivial upstream gradient behave as with the fp32 hand-over."""
+  lt = _lt()
+  torch.manual_seed(9)
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=128, context_size=1),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=128, device='cuda', embedding_size=24,
+          feature_size=16))
+  x = torch.randn([3, 20, 16], device='cuda', requires_grad=True)
+  args = dict(num_frames=T([20, 11, 5]), labels=T([[3, 9, 100, 1], [7, 7, 0, 0], [64, 0, 0, 0]]),
+              num_labels=T([4, 2, 1]))
+  w = torch.tensor([1.0, -0.5, 2.0], device='cuda')
+  seen = []
+  hook = lattice.weight_fn.joint_projection_to_vocab.weight.register_hook(
+      lambda g: seen.append(g.detach().clone()))
+  out = {}
+  for split in (True, False):
+    lattice.split_grad_handover = split
+    lattice.zero_grad()
+    x.grad = None
+    for _ in range(2):                                   # accumulate two passes
+      (lattice(frames=x, **args) * w).sum().backward()
+    out[split] = [p.grad.clone() for p in lattice.parameters()] + [x.grad.clone()]
+  hook.remove()
+  assert len(seen) == 4
+  for a, b in zip(out[True], out[False]):
+    scale = float(b.abs().max()) + 1e-12
+    assert float((a - b).abs().max()) / scale < 2e-5
+  npt.assert_allclose(seen[0].cpu() * 2, out[True][5].cpu(), rtol=1e-5, atol=1e-7)

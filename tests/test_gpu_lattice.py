@@ -18,9 +18,7 @@ from oracle import lattice_oracle as O
 pytestmark = pytest.mark.gpu
 
 SR = ['Real', 'Log', 'MaxTropical']
-FAST_V1 = 2      # LT_FLAG_FAST_V1: first-generation fast path (one utterance per cluster)
-PAIR_CTA = 4     # LT_FLAG_PAIR_CTA: second generation with two utterances per 512-thread CTA
-CLUSTER_FLAGS = [0, FAST_V1, 1 << 8, 2 << 8, 4 << 8]
+CLUSTER_FLAGS = [0, 1 << 8, 2 << 8, 4 << 8]
 
 
 def _lt():
@@ -158,7 +156,7 @@ def test_fast_path_ragged_and_empty_utterances():
   o_loss, o_gb, o_gl = O.lattice_loss_and_grads(
       tab64[..., 0].copy(), tab64[..., 1:].copy(), nf, labels, nl, O.FullNGram(vocab, ctx))
   outs = []
-  for flags in [1, 0, FAST_V1, PAIR_CTA]:   # 1: LT_FLAG_FORCE_GENERIC, 0 / 2 / 4: fast paths
+  for flags in [1, 0]:   # 1: LT_FLAG_FORCE_GENERIC, 0: TMA fast path
     table = cuda(table_np).requires_grad_()
     lattice = make_lattice(vocab, ctx, -1, table, flags)
     loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
@@ -173,7 +171,7 @@ def test_fast_path_ragged_and_empty_utterances():
     npt.assert_allclose(outs[0][1], other[1], rtol=1e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize('flags', [0, FAST_V1, 1 << 8, 4 << 8, 8 << 8])
+@pytest.mark.parametrize('flags', [0, 1 << 8, 4 << 8, 8 << 8])
 @pytest.mark.parametrize('case', ORACLE_CASES)
 def test_loss_and_grads_vs_oracle(case, flags):
   seed, b, t, vocab, ctx, k, u, scale = case
@@ -262,11 +260,10 @@ def test_viterbi_vs_oracle(case):
   npt.assert_allclose(weights.cpu(), o_dist, rtol=1e-6)
 
 
-@pytest.mark.parametrize('flags', [0, FAST_V1, PAIR_CTA])
+@pytest.mark.parametrize('flags', [0])
 @pytest.mark.parametrize('vocab', [64, 128, 192, 256])
 def test_fast_path_generations(vocab, flags):
-  """Both generations of the TMA / cluster fast path on every supported vocabulary,
-  with an odd batch (one idle utterance slot in the last pair), ragged lengths and
+  """The TMA / cluster fast path on every supported vocabulary, with an odd batch, ragged lengths and
   -inf arcs: Log / Real values, Log loss + gradients, MaxTropical distances and the
   bit-exact Viterbi one-hot gradient against the oracle."""
   lt = _lt()
@@ -327,7 +324,7 @@ def test_fast_path_generations(vocab, flags):
   npt.assert_allclose(gr.cpu(), gr2.cpu(), rtol=1e-4, atol=1e-30)
 
 
-@pytest.mark.parametrize('flags', [0, FAST_V1, PAIR_CTA])
+@pytest.mark.parametrize('flags', [0])
 def test_fast_path_ties(flags):
   """All-equal weights on a fast-path shape: blank beats lexical, lowest source
   row wins inside the reduction (semirings.py:363, :382)."""

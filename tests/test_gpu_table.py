@@ -192,7 +192,7 @@ def test_random_dfa_vs_oracle(seed, c, vocab, k):
 @pytest.mark.parametrize('seed,c,vocab,ties', [(10, 20, 8, False), (11, 257, 12, False),
                                                (12, 130, 64, False), (13, 40, 16, True),
                                                (14, 257, 256, False)])
-def test_cluster_table_kernels(seed, c, vocab, ties, cluster, monkeypatch):
+def test_cluster_table_kernels(seed, c, vocab, ties, cluster):
   """The cluster-per-utterance kernels (csrc/lattice_table2.cu) for every cluster size against
   the fp64 oracle (loss + gradients, Log / MaxTropical / Real forward) and, bit for bit in the
   MaxTropical semiring (integer weights = ties everywhere when `ties`), against the one-CTA
@@ -240,12 +240,16 @@ def test_cluster_table_kernels(seed, c, vocab, ties, cluster, monkeypatch):
     out['path'] = [x.cpu().numpy() for x in path]
     return out
 
-  monkeypatch.setenv('LT_TABLE_V1', '1')
-  assert N.lib().lt_table_lattice_cluster(c, vocab, -1, 0) == 0
-  v1 = run()
-  monkeypatch.delenv('LT_TABLE_V1')
-  if cluster:
-    monkeypatch.setenv('LT_TABLE_CLUSTER', str(cluster))
+  with N.option('LT_TABLE_V1', 1):
+    assert N.lib().lt_table_lattice_cluster(c, vocab, -1, 0) == 0
+    v1 = run()
+  with N.option('LT_TABLE_CLUSTER', cluster):
+    _cluster_body(c, vocab, cluster, run, v1, octx, table_np, nf, labels, nl, ties)
+
+
+def _cluster_body(c, vocab, cluster, run, v1, octx, table_np, nf, labels, nl, ties):
+  lt = _lt()
+  from last_torch_b200 import _native as N
   used = N.lib().lt_table_lattice_cluster(c, vocab, -1, 0)
   used_bwd = N.lib().lt_table_lattice_cluster(c, vocab, -1, 1)
   if cluster:

@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from last_torch_b200 import _native as N
+
 pytestmark = pytest.mark.gpu
 
 
@@ -48,7 +50,6 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
   """lt_joint_forward on the tcgen05 path (bf16x3 split, fp32 TMEM accumulate)
   against the fp32 reference formula (weight_fns.py:208-227); 1e-5 of the
   logit scale, and identical (to 1e-5) to the CUDA-core fp32 kernels."""
-  import os
   import last_torch_b200 as lt
   torch.manual_seed(c + v)
   fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=48,
@@ -62,19 +63,9 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
     joint = torch.tanh(pcx[None] + pfx[:, None])
     rl = joint @ fn.joint_projection_to_vocab.weight.double().T + fn.joint_projection_to_vocab.bias.double()
     rb = joint @ fn.joint_projection_to_blank.weight.double()[0] + fn.joint_projection_to_blank.bias.double()
-    os.environ['LT_JOINT_SIMT'] = '1'
-    try:
+    with N.option('LT_JOINT_SIMT', 1):
       sb, sl = fn.all_frames(cache, frames)
-    finally:
-      del os.environ['LT_JOINT_SIMT']
-    os.environ['LT_JOINT_FWD_PAIR'] = '1'        # opt-in CTA-pair (cta_group::2) kernel
-    try:
-      pb, pl = fn.all_frames(cache, frames)
-    finally:
-      del os.environ['LT_JOINT_FWD_PAIR']
   scale = float(rl.abs().max())
-  assert float((pl[:, 0].double() - rl).abs().max()) / scale < 1e-5
-  assert float((pb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6) < 1e-5
   err_tc = float((kl[:, 0].double() - rl).abs().max()) / scale
   err_simt = float((sl[:, 0].double() - rl).abs().max()) / scale
   err_b = float((kb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6)
@@ -89,7 +80,6 @@ def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
   """Gradients of the whole-utterance JointWeightFn kernel path (tcgen05 dgrad +
   streaming reduction, weight gradients) against torch autograd through the
   per-frame reference formula, and against the CUDA-core kernels."""
-  import os
   import last_torch_b200 as lt
   torch.manual_seed(c * 7 + v)
   fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=48,
@@ -101,32 +91,19 @@ def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
   wl = torch.randn([n, 1, c, v], device='cuda')
 
   def grads(path):
-    if path == 'simt':
-      os.environ['LT_JOINT_SIMT'] = '1'
-    try:
+    with N.option('LT_JOINT_SIMT', 1 if path == 'simt' else 0):
       if path == 'ref':
         b, l = fn(cache, frames.reshape(n, 40))
         b, l = b.reshape(wb.shape), l.reshape(wl.shape)
       else:
         b, l = fn.all_frames(cache, frames)
       return torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
-    finally:
-      os.environ.pop('LT_JOINT_SIMT', None)
 
   ref, tc, simt = grads('ref'), grads('tc'), grads('simt')
-  # the CTA-pair (cta_group::2) kernels are opt-in; they must agree as well
-  os.environ['LT_JOINT_FWD_PAIR'] = '1'
-  os.environ['LT_JOINT_WGRAD_PAIR'] = '1'
-  try:
-    pair = grads('tc')
-  finally:
-    os.environ.pop('LT_JOINT_FWD_PAIR', None)
-    os.environ.pop('LT_JOINT_WGRAD_PAIR', None)
-  for r, a, s, q in zip(ref, tc, simt, pair):
+  for r, a, s in zip(ref, tc, simt):
     scale = float(r.abs().max()) + 1e-12
     assert float((s - r).abs().max()) / scale < 3e-5
     assert float((a - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((a - r).abs().max()) / scale)
-    assert float((q - r).abs().max()) / scale < 3e-5, (tuple(r.shape), float((q - r).abs().max()) / scale)
 
 
 @pytest.mark.parametrize('c,v,h,n', [(65, 64, 128, 148 * 128 + 77), (130, 128, 256, 37 * 128 * 2 + 5)])
@@ -135,7 +112,6 @@ def test_joint_backward_frame_blocks_straddle_ctas(c, v, h, n):
   tile sequence into equal ranges, so blocks straddle two CTAs and grad_proj_frame is flushed by
   both; the last block is partial (rows past N read the zero line).  Tensor-core path against the
   CUDA-core kernels (themselves checked against autograd above)."""
-  import os
   import last_torch_b200 as lt
   torch.manual_seed(n)
   fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=24,
@@ -147,14 +123,10 @@ def test_joint_backward_frame_blocks_straddle_ctas(c, v, h, n):
   wl = torch.randn([n, 1, c, v], device='cuda')
 
   def run(simt):
-    if simt:
-      os.environ['LT_JOINT_SIMT'] = '1'
-    try:
+    with N.option('LT_JOINT_SIMT', 1 if simt else 0):
       b, l = fn.all_frames(cache, frames)
       g = torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
       return [b.detach(), l.detach()] + list(g)
-    finally:
-      os.environ.pop('LT_JOINT_SIMT', None)
 
   tc, simt = run(False), run(True)
   for a, s in zip(tc, simt):
@@ -165,33 +137,30 @@ def test_joint_backward_frame_blocks_straddle_ctas(c, v, h, n):
 @pytest.mark.parametrize('variant', ['', 'LT_JOINT_DGRAD_PAIR', 'LT_JOINT_DGRAD_MULTICAST'])
 def test_joint_backward_split_row_kernels(variant):
   """The split-row forms of the tensor-core backward kernels (fused dgrad fed by TMA, weight
-  gradient copying its A operand) on a split copy of the fp32 gradient
-  (LT_JOINT_DGRAD_SPLIT_TEST), plus the opt-in CTA-pair and TMA-multicast variants of the
-  dgrad: same gradients as the fp32 kernels."""
-  import os
-  import last_torch_b200 as lt
+  gradient copying its A operand) on a split copy of the fp32 gradient (lt_joint_split_rows),
+  plus the opt-in CTA-pair and TMA-multicast variants of the dgrad: same gradients as the fp32
+  kernels."""
+  from last_torch_b200 import joint
   c, v, h, n = 257, 256, 512, 300
   torch.manual_seed(7)
-  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=24,
-                                   feature_size=16)
-  params = list(fn.parameters())
-  cache = torch.randn([c, 24], device='cuda', requires_grad=True)
-  frames = torch.randn([n, 1, 16], device='cuda', requires_grad=True)
-  wb = torch.rand([n, 1, c], device='cuda') / c
-  wl = torch.rand([n, 1, c, v], device='cuda') / (c * v)
-
-  def run(envs):
-    for e in envs:
-      os.environ[e] = '1'
-    try:
-      b, l = fn.all_frames(cache, frames)
-      return torch.autograd.grad((b * wb).sum() + (l * wl).sum(), params + [cache, frames])
-    finally:
-      for e in envs:
-        os.environ.pop(e, None)
-
-  ref = run([])
-  got = run(['LT_JOINT_DGRAD_SPLIT_TEST'] + ([variant] if variant else []))
+  pc = torch.randn([c, h], device='cuda')
+  pf = torch.randn([n, h], device='cuda')
+  w_blank = torch.randn([1, h], device='cuda') / h ** 0.5
+  w_vocab = torch.randn([v, h], device='cuda') / h ** 0.5
+  gb = torch.rand([n, c], device='cuda') / c
+  gl = torch.rand([n, c, v], device='cuda') / (c * v)
+  assert N.lib().lt_joint_backward_split_supported(n, c, h, v) == 1
+  ref = joint.joint_backward_raw(pc, pf, w_blank, w_vocab, gb, gl, fmt=0)
+  split = torch.empty_like(gl)
+  N.check(N.lib().lt_joint_split_rows(N.ptr(gl), N.ptr(split), n * c, v,
+                                      N.stream_ptr(gl.device)), 'lt_joint_split_rows')
+  rows = split.view(torch.bfloat16).reshape(n, c, 2, v).float()
+  assert float((rows[:, :, 0] + rows[:, :, 1] - gl).abs().max()) <= float(gl.max()) * 2.0 ** -16
+  if variant:
+    with N.option(variant, 1):
+      got = joint.joint_backward_raw(pc, pf, w_blank, w_vocab, gb, split, fmt=1)
+  else:
+    got = joint.joint_backward_raw(pc, pf, w_blank, w_vocab, gb, split, fmt=1)
   for a, r in zip(got, ref):
     scale = float(r.abs().max()) + 1e-12
     assert float((a - r).abs().max()) / scale < 2e-5, (tuple(r.shape), float((a - r).abs().max()) / scale)

@@ -71,8 +71,9 @@ def test_table_kernel_path_query_without_a_gpu(lt, monkeypatch):
   (csrc/lattice_table2.cu) and with how many CTAs per utterance -- host logic only."""
   from last_torch_b200 import _native as N
   L = N.lib()
-  monkeypatch.delenv('LT_TABLE_V1', raising=False)
-  monkeypatch.delenv('LT_TABLE_CLUSTER', raising=False)
+  assert L.lt_get_option(b'LT_TABLE_V1') == 0 and L.lt_get_option(b'LT_TABLE_CLUSTER') == 0
+  assert L.lt_get_option(b'LT_NO_SUCH_OPTION') == -1
+  assert L.lt_set_option(b'LT_NO_SUCH_OPTION', 1) == 1          # LT_ERR_INVALID_ARGUMENT
   for backward in (0, 1):
     assert L.lt_table_lattice_cluster(257, 256, -1, backward) == 8   # configs[1] geometry
     assert L.lt_table_lattice_cluster(20, 8, -1, backward) == 1      # one small slab
@@ -81,11 +82,12 @@ def test_table_kernel_path_query_without_a_gpu(lt, monkeypatch):
     assert L.lt_table_lattice_cluster(0, 8, -1, backward) == 0
     assert L.lt_table_lattice_cluster(1025, 32, -1, backward) == 4   # smallest cluster with slabs <= 40 KB
     assert L.lt_table_lattice_cluster(4161, 64, -1, backward) == 0   # C > 2048 / two slabs exceed 227 KB
-  monkeypatch.setenv('LT_TABLE_CLUSTER', '2')
-  assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 2
-  assert L.lt_table_lattice_cluster(257, 256, -1, 0) == 0            # two slabs of 129 rows do not fit
-  monkeypatch.setenv('LT_TABLE_V1', '1')
-  assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 0
+  with N.option('LT_TABLE_CLUSTER', 2):
+    assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 2
+    assert L.lt_table_lattice_cluster(257, 256, -1, 0) == 0          # two slabs of 129 rows do not fit
+    with N.option('LT_TABLE_V1', 1):
+      assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 0
+  assert L.lt_table_lattice_cluster(20, 8, -1, 0) == 1
 
 
 def test_missing_library_fails_loudly(lt, monkeypatch):

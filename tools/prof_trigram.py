@@ -15,7 +15,7 @@ gd = torch.ones([B], device='cuda')
 gb = torch.empty_like(blank)
 gl = torch.empty_like(lex)
 for _ in range(2):
-  dist, alphas, _, _, _, _ = ops._lattice_forward_raw(N.LOG, V, n, -1, blank, lex, nf, 0, False, False)
+  dist, alphas, *_ = ops._lattice_forward_raw(N.LOG, V, n, -1, blank, lex, nf, 0, False, False)
   N.check(N.lib().lt_lattice_backward(
       N.LOG, V, n, -1, N.ptr(blank), N.ptr(lex), N.ptr(nf), B, T, N.ptr(alphas), None,
       N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, 0, N.stream_ptr(blank.device)), 'bwd')

@@ -1,0 +1,103 @@
+"""Drop-in proof: runs the REFERENCE's own test-suite against this repo's `last_torch` alias.
+
+    python tools/run_reference_tests.py --prepare     # in the build container: copies
+        /root/reference/tests/*.py into _reference_tests/ (git-ignored, never committed;
+        the directory travels to the GPU box with the gpurun snapshot) and writes the harness
+        conftest there
+    python tools/run_reference_tests.py [--cpu] [pytest args]   # runs them (GPU box: default
+        device cuda; --cpu: host-side tests only, for iterating without a GPU)
+
+The harness conftest does three things and edits no test: (1) puts the repo root first on
+sys.path so that `import last_torch` is the alias package; (2) makes tensors the tests create land
+on the GPU (torch.set_default_device + the legacy default tensor type for `torch.Tensor([...])`)
+and lets numpy.testing read CUDA tensors (Tensor.__array__ via .cpu()); (3) marks the tests in
+XFAIL below -- each one cites the reference defect or the deliberate
+deviation that makes it fail -- as expected failures.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEST = os.path.join(ROOT, '_reference_tests')
+REFERENCE = os.environ.get('LAST_TORCH_REFERENCE', '/root/reference')
+
+CONFTEST = r'''"""Harness for running the reference's tests against the `last_torch` alias
+(written by tools/run_reference_tests.py --prepare; not part of the reference)."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+
+import torch  # noqa: E402
+
+USE_CUDA = os.environ.get('LT_REFTEST_DEVICE', 'cuda') == 'cuda' and torch.cuda.is_available()
+if USE_CUDA:
+  import warnings
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore')
+    torch.set_default_tensor_type(torch.cuda.FloatTensor)    # torch.Tensor([...]) -> cuda
+  torch.set_default_device('cuda')
+  _orig_array = torch.Tensor.__array__
+
+  def _array(self, dtype=None):
+    return _orig_array(self.detach().cpu(), dtype) if dtype is not None else \
+        _orig_array(self.detach().cpu())
+  torch.Tensor.__array__ = _array
+
+import last_torch  # noqa: E402  (the alias)
+assert 'last_torch_b200' in last_torch.RecognitionLattice.__module__
+
+from run_reference_tests import XFAIL  # noqa: E402
+
+
+def pytest_collection_modifyitems(config, items):
+  for item in items:
+    key = item.nodeid.split('::', 1)[-1] if '::' in item.nodeid else item.nodeid
+    fname = os.path.basename(item.fspath)
+    for (f, test), why in XFAIL.items():
+      if f == fname and key.endswith(test):
+        item.add_marker(pytest.mark.xfail(reason=why, strict=False))
+'''
+
+# (file, test id suffix) -> why it is expected to fail against this implementation.
+XFAIL = {
+}
+
+
+def prepare():
+  src = os.path.join(REFERENCE, 'tests')
+  if not os.path.isdir(src):
+    raise SystemExit(f'{src} not found (the reference only exists in the build container)')
+  os.makedirs(DEST, exist_ok=True)
+  for f in sorted(os.listdir(src)):
+    if f.endswith('_test.py'):
+      shutil.copy(os.path.join(src, f), os.path.join(DEST, f))
+  with open(os.path.join(DEST, 'conftest.py'), 'w') as f:
+    f.write(CONFTEST)
+  print('prepared', DEST, sorted(os.listdir(DEST)))
+
+
+def main():
+  args = sys.argv[1:]
+  if '--prepare' in args:
+    prepare()
+    return 0
+  env = dict(os.environ)
+  if '--cpu' in args:
+    args.remove('--cpu')
+    env['LT_REFTEST_DEVICE'] = 'cpu'
+  if not os.path.isdir(DEST):
+    raise SystemExit('run with --prepare first (in the build container)')
+  cmd = [sys.executable, '-m', 'pytest', DEST, '-q', '-p', 'no:cacheprovider',
+         '-o', 'python_files=*_test.py', '--rootdir', DEST] + args
+  return subprocess.call(cmd, env=env, cwd=DEST)
+
+
+if __name__ == '__main__':
+  sys.exit(main())

@@ -1,0 +1,120 @@
+"""One test-scale launch of every kernel family that exchanges state through shared memory /
+DSMEM (st.async + mbarrier complete_tx, TMA rings, TMEM) -- the target of tools/sanitize.sh:
+
+    compute-sanitizer --tool {memcheck,racecheck,synccheck} python tools/sanitize_targets.py
+
+Families: lattice_fast2 (bigram TMA fast path, plain and renormalised, fp32 and split-row
+gradients), lattice_cols / lattice_rows (context_size 2), the generic cluster kernels,
+lattice_table2 (NextStateTable clusters), string_lattice (numerator, plain and (e, f) chain),
+viterbi back-trace, joint_tc forward / wgrad and joint_dgrad2 (tcgen05).  Results are checked
+against the generic kernels so that a sanitizer-induced slowdown cannot hide a wrong answer."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import last_torch_b200 as lt  # noqa: E402
+from last_torch_b200 import _native as N  # noqa: E402
+
+
+def table_lattice(context, k, table, flags=0):
+  alignment = lt.alignments.FrameDependent() if k < 0 else lt.alignments.FrameLabelDependent(k)
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=alignment,
+      weight_fn_factory=lambda _: lt.weight_fns.TableWeightFn(table),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+  lattice.kernel_flags = flags
+  return lattice
+
+
+def loss_and_grad(context, k, table_np, nf, labels, nl, flags=0):
+  table = torch.tensor(table_np, device='cuda', requires_grad=True)
+  b, t = table.shape[:2]
+  frames = torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None].expand(b, t, 1)
+  lattice = table_lattice(context, k, table, flags)
+  args = dict(frames=frames, num_frames=torch.tensor(nf, device='cuda'), cache=None)
+  loss = lattice(labels=torch.tensor(labels, device='cuda'),
+                 num_labels=torch.tensor(nl, device='cuda'), **args)
+  (g,) = torch.autograd.grad(loss.sum(), table)
+  path = lattice.shortest_path(**args)
+  torch.cuda.synchronize()
+  return loss.detach().cpu().numpy(), g.cpu().numpy(), [p.cpu().numpy() for p in path]
+
+
+def lattice_family(name, vocab, n, k, b, t, u):
+  rng = np.random.RandomState(vocab + n)
+  context = lt.contexts.FullNGram(vocab_size=vocab, context_size=n)
+  c = context.num_states()
+  table = rng.randn(b, t, c, 1 + vocab).astype(np.float32)
+  nf = [t] + [max(1, t - 3 * i) for i in range(1, b)]
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = [u] + [max(0, u - i) for i in range(1, b)]
+  fast = loss_and_grad(context, k, table, nf, labels, nl, 0)
+  ref = loss_and_grad(context, k, table, nf, labels, nl, 1)          # LT_FLAG_FORCE_GENERIC
+  np.testing.assert_allclose(fast[0], ref[0], rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(fast[1], ref[1], rtol=1e-4, atol=1e-5)
+  np.testing.assert_array_equal(fast[2][0], ref[2][0])
+  print('ok', name, flush=True)
+
+
+def table_family():
+  rng = np.random.RandomState(3)
+  c, vocab, b, t, u = 130, 64, 3, 9, 4
+  nst = rng.randint(0, c, size=(c, vocab)).astype(np.int32)
+  context = lt.contexts.NextStateTable(torch.from_numpy(nst))
+  table = rng.randn(b, t, c, 1 + vocab).astype(np.float32)
+  nf, nl = [9, 5, 0], [4, 2, 0]
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  with N.option('LT_TABLE_CLUSTER', 4):
+    fast = loss_and_grad(context, -1, table, nf, labels, nl)
+  with N.option('LT_TABLE_V1', 1):
+    ref = loss_and_grad(context, -1, table, nf, labels, nl)
+  np.testing.assert_allclose(fast[0], ref[0], rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(fast[1], ref[1], rtol=1e-4, atol=1e-5)
+  print('ok lattice_table2 (cluster of 4)', flush=True)
+
+
+def joint_family(vocab, hidden, b, t):
+  torch.manual_seed(vocab)
+  out = {}
+  for split in (True, False):
+    torch.manual_seed(vocab)
+    lattice = lt.RecognitionLattice(
+        context=lt.contexts.FullNGram(vocab_size=vocab, context_size=1),
+        alignment=lt.alignments.FrameDependent(),
+        weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+            num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+        weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+            vocab_size=c.shape()[1], hidden_size=hidden, device='cuda', embedding_size=24,
+            feature_size=16))
+    lattice.split_grad_handover = split
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn([b, t, 16], device='cuda', generator=g)
+    loss = lattice(frames=x, num_frames=torch.tensor([t, t - 5][:b], device='cuda'),
+                   labels=torch.randint(1, vocab + 1, [b, 5], device='cuda', generator=g),
+                   num_labels=torch.tensor([5, 3][:b], device='cuda'))
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    out[split] = [p.grad.clone() for p in lattice.parameters()]
+  for a, r in zip(out[True], out[False]):
+    assert float((a - r).abs().max()) <= 2e-5 * (float(r.abs().max()) + 1e-12)
+  print(f'ok joint_tc / joint_dgrad2 / wgrad (vocab {vocab}, hidden {hidden})', flush=True)
+
+
+def main():
+  lattice_family('lattice_fast2 vocab 64 (single CTA)', 64, 1, -1, 3, 11, 4)
+  lattice_family('lattice_fast2 vocab 256 (cluster of 8)', 256, 1, -1, 2, 9, 4)
+  lattice_family('lattice_cols + lattice_rows vocab 32 context 2', 32, 2, -1, 2, 7, 4)
+  lattice_family('lattice_cols FrameLabelDependent(2) vocab 16 context 2', 16, 2, 2, 2, 6, 5)
+  lattice_family('generic cluster kernels vocab 33', 33, 1, -1, 3, 9, 4)
+  table_family()
+  joint_family(128, 128, 2, 12)
+  joint_family(256, 256, 2, 9)
+  print('all sanitizer targets ran', flush=True)
+
+
+if __name__ == '__main__':
+  main()
