@@ -119,12 +119,15 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size,
  * ulp = 4.9e-4) the arc posteriors then agree with an fp64 evaluation to ~1e-6 relative; the
  * plain fp32 recursion -- and the fp32 reference, lattices.py:865-886 + autograd -- is at
  * 1e-4 .. 1e-3 there (profiles/r02_parity_errors.json).
- *   alpha_norm [B, T+2] int32: off_0 .. off_T, then the bits of r (fp32) with
- *              logZ = (off_T + r) * ln 2.  Written by the forward, read by the backward.
+ *   alpha_norm [B, T+3] int32: off_0 .. off_T, then the bits of r (fp32), then the unit u of the
+ *              offsets (0: log2 units -- the TMA fast path works in log2; 1: natural log -- the
+ *              generic kernels): logZ = off_T * (u ? 1 : ln 2) + r' with r' = r in the same unit.
+ *              Written by the forward, read by the backward of the same lattice.
  *   alphas     [B,T,C] then holds alpha~_t (natural-log units); the TRUE alpha_t is
- *              alphas[b,t,c] + alpha_norm[b,t] * ln 2 (lt_alphas_denormalize).
- * Only when lt_lattice_norm_supported() returns 1 (the TMA fast path, Log); alpha_norm == NULL
- * selects the plain kernels (identical to lt_lattice_forward / lt_lattice_backward).
+ *              alphas[b,t,c] + alpha_norm[b,t] * (u ? 1 : ln 2)  (lt_alphas_denormalize).
+ * Only when lt_lattice_norm_supported() returns 1 (Log semiring; the TMA fast path and the generic
+ * kernels, i.e. every FullNGram lattice except the context_size >= 2 thread-per-column path);
+ * alpha_norm == NULL selects the plain kernels (identical to lt_lattice_forward / _backward).
  */
 int lt_lattice_norm_supported(int semiring, int vocab_size, int context_size,
                               int max_expansions, unsigned flags);
@@ -143,7 +146,7 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size,
                              float* grad_blank, float* grad_lexical,
                              float* beta_final, const int32_t* alpha_norm,
                              unsigned flags, void* stream);
-/* alphas[b,t,c] += alpha_norm[b,t] * ln 2 in place (the alphas RecognitionLattice._forward
+/* alphas[b,t,c] += alpha_norm[b,t] * (unit) in place (the alphas RecognitionLattice._forward
  * returns, lattices.py:496). */
 int lt_alphas_denormalize(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
                           void* stream);

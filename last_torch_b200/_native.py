@@ -142,26 +142,43 @@ _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count', 
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 
+# NVTX range per C-ABI call (nsys / ncu --nvtx show the entry point around its kernels); the
+# push/pop cost ~0.1 us when no tool is attached.  LT_NO_NVTX=1 (read once) switches them off.
+_NVTX = not os.environ.get('LT_NO_NVTX')
+
+
 class _TimedLib:
   def __init__(self, handle):
     self._handle = handle
+    self._wrapped = {}
 
   def __getattr__(self, name):
     fn = getattr(self._handle, name)
     if name in _UNTIMED:
       return fn
+    cached = self._wrapped.get(name)
+    if cached is not None:
+      return cached
+    nvtx = torch.cuda.nvtx if (_NVTX and torch.cuda.is_available()) else None
 
     def call(*args):
       timer = KERNEL_TIMER
-      if timer is None:
-        return fn(*args)
-      start = torch.cuda.Event(enable_timing=True)
-      end = torch.cuda.Event(enable_timing=True)
-      start.record()
-      rc = fn(*args)
-      end.record()
-      timer.append((name, start, end))
-      return rc
+      if nvtx is not None:
+        nvtx.range_push(name)
+      try:
+        if timer is None:
+          return fn(*args)
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = fn(*args)
+        end.record()
+        timer.append((name, start, end))
+        return rc
+      finally:
+        if nvtx is not None:
+          nvtx.range_pop()
+    self._wrapped[name] = call
     return call
 
 

@@ -208,6 +208,8 @@ class NextStateTable(ContextDependency):
       raise ValueError(f'weights.shape[-2:] should be {self.shape()} but got'
                        f' {weights.shape[-2:]}')
     from . import ops
+    if not weights.is_floating_point():
+      weights = weights.to(torch.float32)     # the reference's torch ops take integer tensors
     return ops.TableReduce.apply(weights, self, semirings.kernel_id(semiring))
 
   def backward_broadcast(self, weights: torch.Tensor) -> torch.Tensor:

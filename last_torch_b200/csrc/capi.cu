@@ -134,11 +134,26 @@ int lt_lattice_forward(int semiring, int vocab_size, int context_size, int max_e
                                  backptr, termptr, nullptr, flags, stream);
 }
 
+}  // extern "C"
+
+namespace lt {
+int lattice_norm_family(int semiring, const NGram& g, int k, unsigned flags, const void* lexical) {
+  if (semiring != LT_LOG) return 0;
+  if (lattice_fast2_supported(g, k, flags, lexical)) return 1;
+  // the thread-per-column forward (context_size >= 2) has no renormalised variant
+  const void* probe = lexical ? lexical : reinterpret_cast<const void*>(uintptr_t(256));
+  if (lattice_cols_supported(g, k, flags, probe)) return 0;
+  return 2;
+}
+}  // namespace lt
+
+extern "C" {
+
 int lt_lattice_norm_supported(int semiring, int vocab_size, int context_size, int max_expansions,
                               unsigned flags) {
   NGram g;
   if (!make_ngram(vocab_size, context_size, &g)) return 0;
-  return lattice_norm_supported(semiring, g, max_expansions, flags) ? 1 : 0;
+  return lattice_norm_family(semiring, g, max_expansions, flags, nullptr) ? 1 : 0;
 }
 
 int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size, int max_expansions,
@@ -164,9 +179,9 @@ int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size, int 
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
   p.alpha_norm = alpha_norm;
   const bool fast2 = T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical);
-  if (alpha_norm && !(fast2 && lattice_norm_supported(semiring, g, max_expansions, flags))) {
+  if (alpha_norm && (T == 0 || !lattice_norm_family(semiring, g, max_expansions, flags, lexical))) {
     set_error("lt_lattice_forward_norm: this lattice has no renormalised kernel "
-              "(lt_lattice_norm_supported, 16-byte aligned weights, T > 0)");
+              "(lt_lattice_norm_supported, T > 0)");
     return LT_ERR_UNSUPPORTED;
   }
   if (fast2) return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
@@ -214,10 +229,22 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
   p.alpha_norm = alpha_norm;
   const bool fast2 = lattice_fast2_supported(g, max_expansions, flags, lexical) &&
                      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0;
-  if (alpha_norm && !(fast2 && lattice_norm_supported(semiring, g, max_expansions, flags))) {
-    set_error("lt_lattice_backward_norm: `alphas` / `alpha_norm` are renormalised but this call "
-              "cannot take the renormalised kernel (16-byte aligned weights and gradients)");
-    return LT_ERR_UNSUPPORTED;
+  if (alpha_norm) {
+    // the pair must stay inside one kernel family: the offsets' unit differs between them
+    const int family = lattice_norm_family(semiring, g, max_expansions, flags, lexical);
+    if (family == 0 || (family == 1 && !fast2)) {
+      set_error("lt_lattice_backward_norm: `alphas` / `alpha_norm` are renormalised but this "
+                "call cannot take the kernel family that wrote them (16-byte aligned gradients?)");
+      return LT_ERR_UNSUPPORTED;
+    }
+    if (family == 2) {
+      if (flags & LT_FLAG_GRAD_SPLIT) {
+        set_error("lt_lattice_backward: LT_FLAG_GRAD_SPLIT needs the TMA fast path");
+        return LT_ERR_UNSUPPORTED;
+      }
+      return lattice_backward_generic_launch(semiring, g, max_expansions, p, flags, sms,
+                                             (cudaStream_t)stream);
+    }
   }
   if (fast2) return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (flags & LT_FLAG_GRAD_SPLIT) {

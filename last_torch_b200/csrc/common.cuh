@@ -99,10 +99,14 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 __device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
 __device__ __forceinline__ bool is_finite(float x) { return fabsf(x) <= 3.402823466e38f; }
 
-// Accurate-enough exp/log on the SFU (ex2.approx / lg2.approx have ~1-2 ulp
-// relative error on their normal range; far inside the 1e-5 parity budget).
-__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
-__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
+// exp / log of the latency-bound kernels (generic lattice kernels, numerator chain, semiring
+// ops, one-CTA table kernels): the accurate library versions (<= 2 ulp).  exp2f(x * log2e)
+// rounds the product at ulp(x * log2e) -- 1e-6 relative at |x| ~ 20 -- and lg2.approx * ln2
+// is as loose; these kernels are not instruction-bound, so they can afford the reference's
+// accuracy.  The HBM-bound fast paths work in log2 units with bare MUFU ops instead
+// (fast_ptx.cuh) and bound their error by renormalising the recursion state.
+__device__ __forceinline__ float fast_exp(float x) { return expf(x); }
+__device__ __forceinline__ float fast_log(float x) { return logf(x); }
 
 template <int SR> struct Sr;
 
@@ -150,6 +154,13 @@ template <> struct Acc<LT_REAL> {
 };
 
 __device__ __forceinline__ float msafe(float m) { return is_finite(m) ? m : 0.f; }
+// Per-frame shift of the renormalised recursions: floor(max), an integer so that the running
+// offset is exact; 0 when the maximum is not finite, and clamped so that offsets of absurd
+// magnitude (weights like -1e30 standing in for -inf) stay inside int32.
+__device__ __forceinline__ float norm_shift(float m) {
+  if (!is_finite(m)) return 0.f;
+  return fminf(fmaxf(floorf(m), -16777216.f), 16777216.f);
+}
 
 template <> struct Acc<LT_LOG> {
   float m, s;

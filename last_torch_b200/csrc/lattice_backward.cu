@@ -152,9 +152,15 @@ lattice_backward_generic(const BwdParams p) {
   int nf = p.num_frames[b];
   nf = max(0, min(nf, p.T));
   const size_t bt0 = (size_t)b * p.T;
-  const float logz = p.dist[b];
+  const float logz_plain = p.dist[b];
   const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
-  const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
+  const bool scale_ok = (SR != LT_LOG) || is_finite(logz_plain);
+  // Renormalised pair (lt_lattice_backward_norm): alphas hold alpha~_t, logZ = off_T + r;
+  // beta~_t = beta_t - (off_T - off_t) follows the forward's shifts d_t = off_{t+1} - off_t and
+  // every posterior exponent becomes alpha~ + w + beta~ - (r + d_t).
+  const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+  const int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
+  const float logz_res = norm ? __int_as_float(an[p.T + 1]) : logz_plain;
 
   // padding frames: zero gradients (lattices.py:775-779)
   for (int t = nf; t < p.T; ++t) {
@@ -174,6 +180,8 @@ lattice_backward_generic(const BwdParams p) {
   cluster_sync_all();
 
   for (int t = nf - 1; t >= 0; --t) {
+    const float shift = norm ? (float)(an[t + 1] - an[t]) : 0.f;
+    const float logz = logz_res + shift;
     const float* blank = p.blank + (bt0 + t) * C;
     const float* lex = p.lexical + (bt0 + t) * (size_t)C * V;
     const float* alpha = p.alphas + (bt0 + t) * C;
@@ -185,7 +193,7 @@ lattice_backward_generic(const BwdParams p) {
       for (int d = tid; d < D; d += nth) {
         const int q = p_lo + d;
         const float bb = S::times(blank[q], beta[q]);
-        const float v = S::plus(bb, row_out[d]);
+        const float v = S::plus(bb, row_out[d]) - shift;
         if constexpr (SR == LT_LOG)
           gb[q] = scale_ok ? gscale * fast_exp(alpha[q] + bb - logz) : 0.f;
         else
@@ -227,7 +235,8 @@ lattice_backward_generic(const BwdParams p) {
         __syncthreads();
         for (int d = tid; d < D; d += nth) {
           const int q = p_lo + d;
-          const float v = S::plus(S::times(blank[q], beta[q]), row_out[d]);  // alignments.py:414-415
+          float v = S::plus(S::times(blank[q], beta[q]), row_out[d]);  // alignments.py:414-415
+          if (j == 0) v -= shift;            // nb_0 is beta_t: move it to the frame of off_t
           bcast_store_b(out, q, v, nrank);
         }
         cluster_sync_all();
@@ -239,7 +248,9 @@ lattice_backward_generic(const BwdParams p) {
     }
   }
   if (p.beta_final)
-    for (int d = tid; d < D; d += nth) p.beta_final[(size_t)b * C + p_lo + d] = beta[p_lo + d];
+    for (int d = tid; d < D; d += nth)
+      p.beta_final[(size_t)b * C + p_lo + d] =
+          norm ? (float)((double)beta[p_lo + d] + (double)(an[p.T] - an[0])) : beta[p_lo + d];
   cluster_sync_all();
 }
 

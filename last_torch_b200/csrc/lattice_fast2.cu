@@ -59,7 +59,7 @@ struct Fast2FwdParams {
   float* alphas;
   float* alpha_final;
   int16_t* backptr;
-  int32_t* alpha_norm;   // NORM only: [B, T+2] = off_0 .. off_T (log2 units), bits of r (fp32)
+  int32_t* alpha_norm;   // NORM only: [B, T+3] = off_0 .. off_T (log2 units), bits of r, unit 0
 };
 
 // ============================================================== forward (K1) ==
@@ -182,8 +182,8 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
         for (int c = lane; c < C; c += 32) m = fmaxf(m, cur[c]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) shift_slot[t & 1] = is_finite(m) ? floorf(m) : 0.f;
-        if (rank == 0 && lane == 0) p.alpha_norm[(size_t)b * (p.T + 2) + t] = off;
+        if (lane == 0) shift_slot[t & 1] = norm_shift(m);
+        if (rank == 0 && lane == 0) p.alpha_norm[(size_t)b * (p.T + 3) + t] = off;
       }
     }
 
@@ -366,10 +366,11 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
         // logZ = (off_T + r) ln 2, rounded once from double; the pair (off_T, r) is what the
         // backward kernel uses (dist[b] alone has lost r's low bits at |logZ| ~ 1e3)
         const float r = ms + __log2f(s);
-        int32_t* an = p.alpha_norm + (size_t)b * (p.T + 2);
+        int32_t* an = p.alpha_norm + (size_t)b * (p.T + 3);
         for (int t = nf + lane; t <= p.T; t += 32) an[t] = off;
         if (lane == 0) {
           an[p.T + 1] = __float_as_int(r);
+          an[p.T + 2] = 0;               // offsets are in log2 units
           p.dist[b] = (float)(((double)r + (double)off) * 0.6931471805599453);
         }
       } else {
@@ -462,7 +463,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   const float logz = active ? p.dist[b] : 0.f;
   // Log: everything on chip is in log2 units.  NORM: logZ = off_T + r, and the offsets cancel
   // against those of alpha~ / beta~ up to the per-frame shift d_t (see the file comment).
-  const int32_t* an = NORM ? p.alpha_norm + (size_t)(active ? b : 0) * (p.T + 2) : nullptr;
+  const int32_t* an = NORM ? p.alpha_norm + (size_t)(active ? b : 0) * (p.T + 3) : nullptr;
   const float logz2 = NORM ? __int_as_float(an[p.T + 1]) : logz * kLog2e;
   const float gscale = (active && p.grad_dist) ? p.grad_dist[b] : 1.f;
   const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
@@ -732,11 +733,6 @@ bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* 
 // One 256-thread CTA per (utterance, 32-column slice), at most 113 KB of shared memory so that
 // TWO CTAs share an SM (33 clusters of 8 are co-resident on a B200).
 constexpr int kSharedBudget = 113 * 1024;
-
-bool lattice_norm_supported(int semiring, const NGram& g, int k, unsigned flags) {
-  // alignment of `lexical` is the caller's business: torch allocations are 512-byte aligned
-  return semiring == LT_LOG && lattice_fast2_supported(g, k, flags, nullptr);
-}
 
 int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
                                  unsigned flags, cudaStream_t stream) {

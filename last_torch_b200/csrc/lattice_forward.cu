@@ -151,6 +151,14 @@ lattice_forward_generic(const FwdParams p) {
   float* cur = alpha0;
   float* nxt = alpha1;
   const size_t bt0 = (size_t)b * p.T;
+  // Renormalised recursion state (lt_lattice_forward_norm, Log only): alpha_t = alpha~_t + off_t
+  // with an exact integer offset (natural-log units here) that follows floor(max_c alpha~_t);
+  // every CTA derives the shift from its own identical replica.
+  const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+  int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
+  __shared__ float shift_s;
+  int off = 0;
+  float shift = 0.f;
 
   for (int t = 0; t < nf; ++t) {
     const float* blank = p.blank + (bt0 + t) * C;
@@ -158,6 +166,20 @@ lattice_forward_generic(const FwdParams p) {
     if (p.alphas) {
       float* out = p.alphas + (bt0 + t) * C;
       for (int d = tid; d < D; d += nth) out[q_lo + d] = cur[q_lo + d];
+    }
+    if (norm) {
+      if (tid < 32) {
+        float m = neg_inf();
+        for (int c = tid; c < C; c += 32) m = fmaxf(m, cur[c]);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (tid == 0) {
+          shift_s = norm_shift(m);
+          if (rank == 0) an[t] = off;
+        }
+      }
+      __syncthreads();
+      shift = shift_s;
+      off += (int)shift;
     }
     if constexpr (!FLD) {
       reduce_into_slice<SR>(g, lex, cur, q_lo, q_hi, pm, ps, p.ppad);
@@ -172,7 +194,7 @@ lattice_forward_generic(const FwdParams p) {
           if (p.backptr)
             p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)__float_as_int(ps[d]);
         } else {
-          v = S::plus(a, r);
+          v = S::plus(a, r) - shift;
         }
         bcast_store(nxt, q, v, nrank);
       }
@@ -225,7 +247,7 @@ lattice_forward_generic(const FwdParams p) {
       for (int d = tid; d < D; d += nth) {
         const int q = q_lo + d;
         float v;
-        if constexpr (SR == LT_LOG) { v = msafe(am[d]) + fast_log(as[d]); }
+        if constexpr (SR == LT_LOG) { v = msafe(am[d]) + fast_log(as[d]) - shift; }
         else { v = am[d]; }
         if constexpr (SR == LT_MAXTROPICAL) {
           if (p.termptr) p.termptr[(bt0 + t) * C + q] = (uint8_t)__float_as_int(as[d]);
@@ -245,7 +267,9 @@ lattice_forward_generic(const FwdParams p) {
     }
   }
   if (p.alpha_final)
-    for (int d = tid; d < D; d += nth) p.alpha_final[(size_t)b * C + q_lo + d] = cur[q_lo + d];
+    for (int d = tid; d < D; d += nth)
+      p.alpha_final[(size_t)b * C + q_lo + d] =
+          norm ? (float)((double)cur[q_lo + d] + (double)off) : cur[q_lo + d];
 
   // dist = (+)_c alpha_T[c]  (lattices.py:496), by CTA 0 of the cluster.
   if (rank == 0) {
@@ -270,7 +294,15 @@ lattice_forward_generic(const FwdParams p) {
         if (tid < st) pm[tid] += pm[tid + st];
         __syncthreads();
       }
-      if (tid == 0) p.dist[b] = ms + fast_log(pm[0]);
+      if (tid == 0) {
+        const float r = ms + fast_log(pm[0]);
+        p.dist[b] = norm ? (float)((double)r + (double)off) : r;
+        if (norm) {
+          for (int t = nf; t <= p.T; ++t) an[t] = off;
+          an[p.T + 1] = __float_as_int(r);
+          an[p.T + 2] = 1;               // offsets are in natural-log units
+        }
+      }
     } else {
       for (int c = tid; c < C; c += nth) acc.add(cur[c], c);
       if constexpr (SR == LT_MAXTROPICAL) { pm[tid] = acc.m; ps[tid] = __int_as_float(acc.a); }

@@ -96,8 +96,10 @@ int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const B
 // TMA / cluster fast path (lattice_fast2.cu): bigram FrameDependent, V in {64..256}; two CTAs
 // of different utterances per SM.  lexical == nullptr skips the alignment test.
 bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical);
-// can the forward / backward pair keep alpha renormalised (FwdParams::alpha_norm)?
-bool lattice_norm_supported(int semiring, const NGram& g, int k, unsigned flags);
+// which kernel family keeps alpha renormalised for this lattice (FwdParams::alpha_norm):
+// 0 none, 1 the TMA fast path (log2 units), 2 the generic kernels (natural-log units).
+// lexical == nullptr assumes 16-byte aligned weights.
+int lattice_norm_family(int semiring, const NGram& g, int k, unsigned flags, const void* lexical);
 int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& base,
                                  unsigned flags, cudaStream_t stream);
 int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams& base,

@@ -191,14 +191,15 @@ int semiring_sum_backward_launch(int sr, const float* a, const float* out, const
   return LT_OK;
 }
 
-// alphas[b,t,c] += alpha_norm[b,t] * ln 2: turns the renormalised alpha~ of
+// alphas[b,t,c] += alpha_norm[b,t] (* ln 2 when the offsets are in log2 units): turns the renormalised alpha~ of
 // lt_lattice_forward_norm into the alphas RecognitionLattice._forward returns (lattices.py:496).
 __global__ void alphas_denormalize_kernel(float* __restrict__ alphas,
                                           const int32_t* __restrict__ alpha_norm, int T, int C,
                                           int64_t rows) {
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const int64_t b = r / T, t = r - b * T;
-    const double off = (double)alpha_norm[b * (T + 2) + t] * 0.6931471805599453;
+    const int32_t* an = alpha_norm + b * (T + 3);
+    const double off = (double)an[t] * (an[T + 2] == 0 ? 0.6931471805599453 : 1.0);
     float* row = alphas + r * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) row[c] = (float)((double)row[c] + off);
   }

@@ -367,7 +367,7 @@ __device__ __forceinline__ void ext_logaddexp(int ea, float fa, int eb, float fb
   const int base = oka ? (okb ? max(ea, eb) : ea) : (okb ? eb : 0);
   const float xa = fa + (float)(ea - base), xb = fb + (float)(eb - base);
   const float r = log_add_exp(xa, xb);
-  const float k = is_finite(r) ? floorf(r) : 0.f;
+  const float k = norm_shift(r);          // floor(r), 0 for -inf, clamped for absurd magnitudes
   e = base + (int)k;
   f = r - k;
 }

@@ -56,6 +56,8 @@ class RecognitionLattice(nn.Module, Generic[T]):
     # JointWeightFn + FullNGram: hand the arc posteriors to the joint network's backward as
     # split rows (ops.JointLatticeLoss); False keeps them in float32
     self.split_grad_handover = ops.SPLIT_GRAD_DEFAULT
+    # shortest_path: reproduce the label encoding of the reference as shipped (see there)
+    self.reference_compat = False
     # Range-check the reference labels (0 <= label <= vocab_size for the first num_labels
     # positions) and raise ValueError like the reference's one_hot (lattices.py:317-324) -- one
     # 4-byte device-to-host read per call.  False skips the read; the kernels then treat an
@@ -209,19 +211,22 @@ class RecognitionLattice(nn.Module, Generic[T]):
     return loss.reshape(batch_dims)
 
   def shortest_path(self, frames: torch.Tensor, num_frames: torch.Tensor,
-                    cache: Optional[T] = None, reference_compat: bool = False):
+                    cache: Optional[T] = None, reference_compat: Optional[bool] = None):
     """Highest scoring path (lattices.py:185-247).
 
     Returns (alignment_labels [batch_dims..., T * num_alignment_states],
     num_alignment_labels [batch_dims...], path_weights [batch_dims...]).
     Labels are the TRUE labels: 0 = blank, 1..vocab_size lexical.
 
-    reference_compat=True reproduces the label encoding of the reference as shipped
-    (lattices.py:242-244 takes argmax over the V-wide mask without the `1 +`): lexical
-    label y is reported as y - 1, so label 1 is indistinguishable from blank.  The reference's
-    second defect (D5: for B > 1 every utterance's path lands in batch element 0's mask) is NOT
-    reproduced; for a single utterance and FrameDependent the output then equals the
-    reference's (tests/lattices_test.py:238-242).
+    reference_compat=True (default: self.reference_compat) reproduces the labels the reference
+    prints as shipped, for code and tests that depend on them:
+      * lattices.py:242-244 takes argmax over the V-wide mask without the `1 +`:
+        lexical label y is reported as y - 1, so label 1 is indistinguishable from blank;
+      * FrameDependent with one batch dimension: lattices.py:875-879 hands batch element 0's
+        mask to every utterance, so row 0 holds, per frame, the most frequent label
+        (first on ties) over the paths of ALL utterances and every other row is zero
+        (tests/lattices_test.py:238-242 pins exactly this).
+    path_weights and num_alignment_labels are unaffected.
     """
     batch_dims = self._check_frames(frames, num_frames)
     if cache is None:
@@ -238,11 +243,29 @@ class RecognitionLattice(nn.Module, Generic[T]):
             blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), v, n, k,
             self.kernel_flags)
     num_alignment_states = self.alignment.num_states()
+    if reference_compat is None:
+      reference_compat = self.reference_compat
     if reference_compat:
-      labels = torch.clamp(labels - 1, min=0)
+      labels = self._reference_labels(labels, num_frames.to(dev).reshape(-1), v, len(batch_dims))
     alignment_labels = labels.to(torch.int64).reshape(*batch_dims, -1)
     num_alignment_labels = num_alignment_states * num_frames.to(dev)
     return alignment_labels, num_alignment_labels, path_weights.reshape(batch_dims)
+
+  def _reference_labels(self, labels, num_frames, v, num_batch_dims):
+    """labels [B, T, N] true labels -> what the reference as shipped prints (D4, D5)."""
+    if isinstance(self.alignment, alignments.FrameDependent) and num_batch_dims == 1:
+      b, t, _ = labels.shape
+      real = torch.arange(t, device=labels.device)[None, :] < num_frames[:, None]
+      lab = labels[..., 0].long()
+      taken = real & (lab > 0)
+      counts = torch.zeros([t, v], dtype=torch.int64, device=labels.device)
+      tt = torch.arange(t, device=labels.device)[None, :].expand(b, t)
+      counts.index_put_((tt[taken], lab[taken] - 1), torch.ones_like(lab[taken]), accumulate=True)
+      row0 = torch.where(counts.sum(-1) > 0, counts.argmax(-1), torch.zeros_like(counts[:, 0]))
+      out = torch.zeros_like(labels)
+      out[0, :, 0] = row0.to(labels.dtype)
+      return out
+    return torch.clamp(labels - 1, min=0)
 
   # -- "private" methods that the reference's tests call directly -------------------
 

@@ -108,16 +108,15 @@ def _lattice_forward_raw(sr, V, n, k, blank, lexical, num_frames, flags, want_le
   `stream` when one is given (the caller orders it against the current stream).
 
   norm=True asks for the renormalised recursion state where a kernel supports it
-  (lt_lattice_forward_norm): the 7th result is then the alpha_norm buffer [B, T+2] and `alphas`
+  (lt_lattice_forward_norm): the 7th result is then the alpha_norm buffer [B, T+3] and `alphas`
   holds alpha~ (only lt_lattice_backward_norm / lt_alphas_denormalize understand the pair);
   otherwise the 7th result is None."""
   B, T, C = blank.shape
   dev = blank.device
   alpha_norm = None
   if (norm and USE_NORM and T > 0 and B > 0 and
-      N.lib().lt_lattice_norm_supported(sr, V, n, k, flags) and
-      lexical.data_ptr() % 16 == 0):
-    alpha_norm = torch.empty([B, T + 2], dtype=torch.int32, device=dev)
+      N.lib().lt_lattice_norm_supported(sr, V, n, k, flags)):
+    alpha_norm = torch.empty([B, T + 3], dtype=torch.int32, device=dev)
   dist = torch.empty([B], dtype=torch.float32, device=dev)
   alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev)
   alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)

@@ -227,8 +227,8 @@ class SharedEmbCacher(WeightFnCacher[torch.Tensor]):
     super().__init__(*args, **kwargs)
     self.num_context_states = num_context_states
     self.embedding_size = embedding_size
-    self.device = device if device else 'cpu'
-    self.embedding = nn.Embedding(num_context_states, embedding_size, device=self.device)
+    self.device = device        # None: torch's current default device
+    self.embedding = nn.Embedding(num_context_states, embedding_size, device=device)
 
   def forward(self) -> torch.Tensor:
     return self.embedding.weight
@@ -312,7 +312,7 @@ class TableWeightFn(WeightFn[type(None)]):
     *batch_dims, input_vocab_size, num_context_states, _ = self.table.shape
     if tuple(frame.shape[:-1]) != tuple(batch_dims):
       raise ValueError(f'frame should have batch_dims={tuple(batch_dims)} but '
-                       f'got ({tuple(frame.shape[:-1])})')
+                       f'got ({frame.shape[:-1]})')
     index = frame[..., 0].to(torch.int64)
     table = self.table.float()
     idx = index.reshape(*index.shape, 1, 1, 1).expand(*index.shape, 1, *table.shape[-2:])

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box session: smoke, GPU tests, parity table, reference suite, bench, sanitizer.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh [steps...]
+mkdir -p gpurun_out
+STEPS=${@:-smoke tests parity reftests bench sanitize}
+for s in $STEPS; do
+  case $s in
+    smoke)    timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    tests)    timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 --timeout 600 -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1; echo "tests rc=$?"; tail -n 3 gpurun_out/gpu_tests.log ;;
+    parity)   timeout 900 python tools/parity_table.py gpurun_out/r02_parity_errors.json > gpurun_out/parity.log 2>&1; echo "parity rc=$?"; tail -n 5 gpurun_out/parity.log ;;
+    reftests) timeout 900 python tools/run_reference_tests.py -q -rfE > gpurun_out/reference_tests.log 2>&1; echo "reftests rc=$?"; tail -n 3 gpurun_out/reference_tests.log ;;
+    bench)    timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; head -c 600 gpurun_out/bench.json ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "benchref rc=$?" ;;
+    sanitize) bash tools/sanitize.sh gpurun_out/sanitizer; echo "sanitize done" ;;
+  esac
+done
