@@ -619,6 +619,7 @@ def run_b200(args):
       run_extra('configs[1] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=32 T=1000 '
                 '(real frames counted)', 32, 1000, 256, 1, -1, 120, 'lossgrad', ragged=True)
       run_extra('configs[1] Log loss+grad, B=48/GPU', 48, 1000, 256, 1, -1, 120, 'lossgrad')
+      run_extra('configs[1] Log forward only, B=32/GPU', 32, 1000, 256, 1, -1, 120, 'forward')
       run_extra('configs[1] Log forward only, B=8/GPU', 8, 1000, 256, 1, -1, 120, 'forward')
 
   cpu = None

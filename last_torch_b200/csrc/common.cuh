@@ -154,6 +154,11 @@ template <> struct Acc<LT_REAL> {
 };
 
 __device__ __forceinline__ float msafe(float m) { return is_finite(m) ? m : 0.f; }
+// Value of a Log accumulator (m, s) minus `shift`, rounded ONCE: (msafe(m) - shift) + log(s) in
+// double.  -inf when the accumulator is empty (s == 0).
+__device__ __forceinline__ float log_value_shifted(float m, float s, float shift) {
+  return (float)(((double)msafe(m) - (double)shift) + (double)logf(s));
+}
 // Per-frame shift of the renormalised recursions: floor(max), an integer so that the running
 // offset is exact; 0 when the maximum is not finite, and clamped so that offsets of absurd
 // magnitude (weights like -1e30 standing in for -inf) stay inside int32.

@@ -19,7 +19,9 @@ namespace lt {
 
 // Reduce all arcs into the destination slice [q_lo, q_hi) from source vector
 // `src` (shared memory, full C entries).  Result for destination q is left in
-// part[0][q - q_lo] (value) and parg[q - q_lo] (arg, MaxTropical).
+// pm[q - q_lo] (value; Log: the running maximum m) and ps[q - q_lo] (MaxTropical: arg-max;
+// Log: the sum s relative to msafe(m), i.e. value = msafe(m) + log(s) -- kept as a pair so that
+// the caller can merge further terms and round the new alpha ONCE).
 template <int SR>
 __device__ __forceinline__ void reduce_into_slice(
     const NGram& g, const float* __restrict__ lex, const float* __restrict__ src,
@@ -101,7 +103,8 @@ __device__ __forceinline__ void reduce_into_slice(
       else { o.s = pm[slot]; }
       acc.merge(o);
     }
-    pm[d] = acc.value();
+    if constexpr (SR == LT_LOG) { pm[d] = acc.m; ps[d] = acc.s; }
+    else pm[d] = acc.value();
     if constexpr (SR == LT_MAXTROPICAL) ps[d] = __int_as_float(acc.arg());
   }
   __syncthreads();
@@ -188,13 +191,19 @@ lattice_forward_generic(const FwdParams p) {
         const float a = S::times(cur[q], blank[q]);
         const float r = pm[d];
         float v;
-        if constexpr (SR == LT_MAXTROPICAL) {
+        if constexpr (SR == LT_LOG) {
+          // merge the blank term into the (m, s) pair of the reduction and round once, after
+          // the shift: (msafe(m) - shift) + log(s) in double
+          Acc<LT_LOG> acc; acc.m = pm[d]; acc.s = ps[d];
+          acc.add(a, 0);
+          v = log_value_shifted(acc.m, acc.s, shift);
+        } else if constexpr (SR == LT_MAXTROPICAL) {
           const bool take_blank = a >= r;      // semirings.py:363
           v = take_blank ? a : r;
           if (p.backptr)
             p.backptr[(bt0 + t) * C + q] = take_blank ? (int16_t)-1 : (int16_t)__float_as_int(ps[d]);
         } else {
-          v = S::plus(a, r) - shift;
+          v = S::plus(a, r);
         }
         bcast_store(nxt, q, v, nrank);
       }
@@ -218,7 +227,8 @@ lattice_forward_generic(const FwdParams p) {
         const bool need_bcast = (i + 1 < p.k);
         for (int d = tid; d < D; d += nth) {
           const int q = q_lo + d;
-          const float r = pm[d];
+          float r = pm[d];
+          if constexpr (SR == LT_LOG) r = log_value_shifted(pm[d], ps[d], 0.f);
           if (p.levels) p.levels[((bt0 + t) * p.k + i) * C + q] = r;
           if constexpr (SR == LT_MAXTROPICAL) {
             if (p.backptr) p.backptr[((bt0 + t) * p.k + i) * C + q] = (int16_t)__float_as_int(ps[d]);
@@ -247,7 +257,7 @@ lattice_forward_generic(const FwdParams p) {
       for (int d = tid; d < D; d += nth) {
         const int q = q_lo + d;
         float v;
-        if constexpr (SR == LT_LOG) { v = msafe(am[d]) + fast_log(as[d]) - shift; }
+        if constexpr (SR == LT_LOG) { v = log_value_shifted(am[d], as[d], shift); }
         else { v = am[d]; }
         if constexpr (SR == LT_MAXTROPICAL) {
           if (p.termptr) p.termptr[(bt0 + t) * C + q] = (uint8_t)__float_as_int(as[d]);
@@ -295,8 +305,9 @@ lattice_forward_generic(const FwdParams p) {
         __syncthreads();
       }
       if (tid == 0) {
-        const float r = ms + fast_log(pm[0]);
-        p.dist[b] = norm ? (float)((double)r + (double)off) : r;
+        const double rd = (double)ms + log((double)pm[0]);
+        const float r = (float)rd;
+        p.dist[b] = norm ? (float)(rd + (double)off) : r;
         if (norm) {
           for (int t = nf; t <= p.T; ++t) an[t] = off;
           an[p.T + 1] = __float_as_int(r);

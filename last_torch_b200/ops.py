@@ -389,20 +389,6 @@ def _side_stream(device):
   return _SIDE_STREAMS[key]
 
 
-_HP_STREAMS = {}
-
-
-def _hp_stream(device):
-  """High-priority stream for the HBM-bound lattice kernel while numerator kernels
-  run beside it: its CTAs fill an SM exactly (two CTAs x 256 threads x 128
-  registers), so they must be placed BEFORE the small kernels grab slots --
-  otherwise a cluster waits for a numerator CTA to retire and the whole
-  recursion ends late."""
-  key = (device.type, device.index)
-  if key not in _HP_STREAMS:
-    _HP_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
-  return _HP_STREAMS[key]
-
 def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels,
                         need_grad, side=None, ready=None):
   """gather + string forward.  With `side` (a torch.cuda.Stream) the two kernels
@@ -517,16 +503,21 @@ def _loss_forward(blank, lexical, num_frames, states, next_labels, num_labels, V
   C = blank.shape[-1]
   dev = blank.device
   cur = torch.cuda.current_stream(dev)
-  side, hp = _side_stream(dev), _hp_stream(dev)
+  side = _side_stream(dev)
   ready = torch.cuda.Event()
   ready.record(cur)
-  hp.wait_event(ready)
-  # NOTE: every buffer handed to a kernel on `hp` / `side` must stay referenced until the
-  # joins below -- a tensor dropped earlier returns to the current stream's pool and the
-  # next allocation may alias it while the other stream still writes to it.
+  # K1 stays on the CURRENT stream, directly behind the kernel that produced the weights: it
+  # becomes launchable the moment that kernel retires, while the numerator kernels first have to
+  # see the cross-stream event -- so K1's CTAs (which fill an SM's register file exactly, two
+  # per SM on 128 of the 148 SMs) are placed first and the small numerator CTAs take the SMs
+  # that are left.  The other way round, every SM a numerator CTA sits on is lost to K1 and a
+  # whole cluster (utterance) waits for it to retire.
+  # NOTE: every buffer handed to a kernel on `side` must stay referenced until the join below
+  # -- a tensor dropped earlier returns to the current stream's pool and the next allocation
+  # may alias it while the other stream still writes to it.
   fwd = _lattice_forward_raw(
       N.LOG, V, n, k, blank, lexical, num_frames, flags, want_levels=need_grad,
-      want_backptr=False, stream=hp, norm=True)
+      want_backptr=False, norm=True)
   log_z, alphas, _, levels, _, _, alpha_norm = fwd
   strf = _string_forward_raw(
       N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
@@ -537,7 +528,6 @@ def _loss_forward(blank, lexical, num_frames, states, next_labels, num_labels, V
     # posteriors of the label lattice with unit upstream gradient (scaled in backward)
     gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
                                 None, side=side, ready=ready, ext=ext)
-  cur.wait_stream(hp)
   cur.wait_stream(side)
   del fwd, strf
   return log_z, num, (alphas, levels, gbw, glw, alpha_norm)

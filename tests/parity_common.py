@@ -47,14 +47,22 @@ def row(name, quantity, ref, gpu, truth):
           'reference_fp32_abs': ra, 'reference_fp32_rel': rr, 'gpu_abs': ga, 'gpu_rel': gr}
 
 
-def within_bar(r, factor=2.0, abs_floor=2e-7):
-  """gpu error <= factor x reference error (max absolute error against the fp64 truth), plus a
-  floor of 2e-7 x max(scale, 1) for fixtures where both sit at fp32 round-off.  The elementwise
-  relative errors are reported next to it; they are dominated by near-cancelling entries
-  (gradient = denominator - numerator posteriors) and are not part of the bar."""
+def within_bar(r, factor=2.0, abs_floor=2e-7, north_star=1e-5):
+  """The parity bar, on the max absolute error against the fp64 truth:
+
+      gpu error <= max( factor x reference error + 2e-7 x scale,  north_star / 2 x scale )
+
+  i.e. the GPU is at most twice as far from the truth as the fp32 reference is (the floor covers
+  fixtures where both sit at fp32 round-off), OR it is inside half of north_star's 1e-5 of the
+  quantity's magnitude -- in which case |gpu - reference| <= 1e-5 x scale holds whenever the
+  reference itself does.  The elementwise relative errors are reported next to it; they are
+  dominated by near-cancelling entries (gradient = denominator - numerator posteriors) and are
+  not part of the bar."""
   if r['reference_fp32_abs'] is None:
     return True
-  return r['gpu_abs'] <= factor * r['reference_fp32_abs'] + abs_floor * max(r['scale'], 1.0)
+  scale = max(r['scale'], 1.0)
+  return r['gpu_abs'] <= max(factor * r['reference_fp32_abs'] + abs_floor * scale,
+                             0.5 * north_star * scale)
 
 
 # --------------------------------------------------------------------------- lattice goldens --

@@ -264,7 +264,9 @@ def test_joint_lattice_golden(fname, split):
     ref = g['grad_' + name]
     scale = float(np.abs(ref).max())
     err = float(np.abs(a.cpu().numpy() - ref).max())
-    assert err <= 1e-4 * scale + 1e-6, (name, err / scale)
+    # + 5e-6: grad_b_blank of the FrameLabelDependent fixture is 0 up to round-off (the
+    # reference's own value there is 1.7e-6 of noise)
+    assert err <= 1e-4 * scale + 5e-6, (name, err / scale)
 
 
 def test_joint_lattice_full_size_properties():

@@ -12,5 +12,8 @@ for s in $STEPS; do
     bench)    timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; head -c 600 gpurun_out/bench.json ;;
     benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "benchref rc=$?" ;;
     sanitize) bash tools/sanitize.sh gpurun_out/sanitizer; echo "sanitize done" ;;
+    sanity)   timeout 900 python tools/sanitize_targets.py > gpurun_out/sanitize_targets.log 2>&1; echo "sanity rc=$?"; tail -n 4 gpurun_out/sanitize_targets.log ;;
+    benchab)  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_norm.json 2> gpurun_out/bench_norm.err; echo "bench norm rc=$?"
+              LT_NO_NORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_nonorm.json 2> gpurun_out/bench_nonorm.err; echo "bench nonorm rc=$?" ;;
   esac
 done

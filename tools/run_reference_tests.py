@@ -49,6 +49,11 @@ if USE_CUDA:
     return _orig_array(self.detach().cpu(), dtype) if dtype is not None else \
         _orig_array(self.detach().cpu())
   torch.Tensor.__array__ = _array
+  _orig_numpy = torch.Tensor.numpy
+
+  def _numpy(self, *args, **kwargs):          # the tests call .detach().numpy() on results
+    return _orig_numpy(self.cpu() if self.is_cuda else self, *args, **kwargs)
+  torch.Tensor.numpy = _numpy
 
 import last_torch  # noqa: E402  (the alias)
 assert 'last_torch_b200' in last_torch.RecognitionLattice.__module__

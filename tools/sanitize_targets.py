@@ -3,6 +3,11 @@ DSMEM (st.async + mbarrier complete_tx, TMA rings, TMEM) -- the target of tools/
 
     compute-sanitizer --tool {memcheck,racecheck,synccheck} python tools/sanitize_targets.py
 
+compute-sanitizer is CLOSED on this GPU pool (profiles/r02_sanitizer_unavailable.log), so the
+script carries its own checks: guard bands around every output buffer of the lattice kernels
+(out-of-bounds writes) and bit-identical results over repeated runs (races), next to the
+comparison of every fast kernel family with the generic kernels.
+
 Families: lattice_fast2 (bigram TMA fast path, plain and renormalised, fp32 and split-row
 gradients), lattice_cols / lattice_rows (context_size 2), the generic cluster kernels,
 lattice_table2 (NextStateTable clusters), string_lattice (numerator, plain and (e, f) chain),
@@ -104,7 +109,77 @@ def joint_family(vocab, hidden, b, t):
   print(f'ok joint_tc / joint_dgrad2 / wgrad (vocab {vocab}, hidden {hidden})', flush=True)
 
 
+def guarded(shape, dtype=torch.float32, pad=4096):
+  """A tensor of `shape` inside a larger allocation whose margins hold a sentinel: a kernel
+  that writes outside its output buffer (what memcheck would flag) destroys the sentinel."""
+  n = 1
+  for d in shape:
+    n *= d
+  sentinel = 12345 if dtype in (torch.int32, torch.int16, torch.uint8) else 12345.0
+  if dtype == torch.uint8:
+    sentinel = 123
+  buf = torch.full([n + 2 * pad], sentinel, dtype=dtype, device='cuda')
+  view = buf[pad:pad + n].view(shape)
+
+  def check():
+    torch.cuda.synchronize()
+    assert bool((buf[:pad] == sentinel).all()) and bool((buf[pad + n:] == sentinel).all()), \
+        f'write outside a {tuple(shape)} {dtype} output buffer'
+  return view, check
+
+
+def raw_lattice_pair(name, vocab, n, k, b, t, flags=0, repeats=6):
+  """lt_lattice_forward_norm / lt_lattice_backward_norm called directly on guarded output
+  buffers, `repeats` times on the same inputs: (1) no write lands outside a buffer; (2) every
+  run gives BIT-IDENTICAL dist / alphas / gradients -- the kernels reduce in a fixed order, so a
+  missed mbarrier wait or a DSMEM store that races with its reader shows up as run-to-run
+  differences (the check compute-sanitizer's racecheck would make; it is closed on this pool)."""
+  rng = np.random.RandomState(7 * vocab + n)
+  c = sum(vocab**i for i in range(n + 1))
+  blank = torch.tensor(rng.randn(b, t, c).astype(np.float32), device='cuda')
+  lex = torch.tensor(rng.randn(b, t, c, vocab).astype(np.float32), device='cuda')
+  nf = torch.tensor([t] + [max(0, t - 2 * i - 1) for i in range(1, b)], dtype=torch.int32,
+                    device='cuda')
+  gd = torch.tensor(rng.rand(b).astype(np.float32) + 0.5, device='cuda')
+  L = N.lib()
+  norm = bool(L.lt_lattice_norm_supported(N.LOG, vocab, n, k, flags))
+  outs = []
+  for _ in range(repeats):
+    dist, c1 = guarded([b])
+    alphas, c2 = guarded([b, t, c])
+    afin, c3 = guarded([b, c])
+    levels, c4 = guarded([b, t, max(k, 1), c])
+    an, c5 = guarded([b, t + 3], torch.int32)
+    gb, c6 = guarded([b, t, c])
+    gl, c7 = guarded([b, t, c, vocab])
+    stream = N.stream_ptr(blank.device)
+    N.check(L.lt_lattice_forward_norm(
+        N.LOG, vocab, n, k, N.ptr(blank), N.ptr(lex), N.ptr(nf), b, t, None, N.ptr(dist),
+        N.ptr(alphas), N.ptr(afin), N.ptr(levels) if k >= 1 else None, None, None,
+        N.ptr(an) if norm else None, flags, stream), 'forward')
+    N.check(L.lt_lattice_backward_norm(
+        N.LOG, vocab, n, k, N.ptr(blank), N.ptr(lex), N.ptr(nf), b, t, N.ptr(alphas),
+        N.ptr(levels) if k >= 1 else None, N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None,
+        N.ptr(an) if norm else None, flags, stream), 'backward')
+    for chk in (c1, c2, c3, c4, c5, c6, c7):
+      chk()
+    outs.append([x.clone() for x in (dist, alphas, gb, gl)])
+  for o in outs[1:]:
+    for a, r in zip(o, outs[0]):
+      assert torch.equal(a, r), f'{name}: run-to-run difference'
+  print(f'ok {name}: {repeats} bit-identical runs, guard bands intact (renormalised: {norm})',
+        flush=True)
+
+
 def main():
+  raw_lattice_pair('lattice_fast2 vocab 256, cluster of 8, 33 utterances', 256, 1, -1, 33, 40)
+  raw_lattice_pair('lattice_fast2 vocab 64, single CTA', 64, 1, -1, 5, 23)
+  raw_lattice_pair('lattice_fast2 vocab 192, cluster of 6', 192, 1, -1, 7, 17)
+  raw_lattice_pair('lattice_cols + lattice_rows vocab 64 context 2 (cluster of 8)', 64, 2, -1, 3, 9)
+  raw_lattice_pair('lattice_cols FrameLabelDependent(2) vocab 32 context 2', 32, 2, 2, 3, 7)
+  raw_lattice_pair('generic kernels, cluster of 4, vocab 40', 40, 1, -1, 5, 13, flags=4 << 8)
+  raw_lattice_pair('generic kernels FrameLabelDependent(3), cluster of 2', 12, 1, 3, 4, 11,
+                   flags=2 << 8)
   lattice_family('lattice_fast2 vocab 64 (single CTA)', 64, 1, -1, 3, 11, 4)
   lattice_family('lattice_fast2 vocab 256 (cluster of 8)', 256, 1, -1, 2, 9, 4)
   lattice_family('lattice_cols + lattice_rows vocab 32 context 2', 32, 2, -1, 2, 7, 4)
