@@ -189,6 +189,28 @@ template <> struct Acc<LT_LOG> {
     s = s * sc + acc;
     m = mn;
   }
+  // The same with the terms given in DOUBLE (exact sums alpha + w of two floats): the running
+  // maximum stays a float (it is only a shift), every exponent x - ms is formed in double and
+  // rounded once, so a term near the maximum carries no rounding error of the sum alpha + w
+  // (which is ulp(|alpha + w|) ~ 2e-6 at |w| ~ 30 when formed in float).
+  __device__ void add_d(double x) {
+    const float xf = (float)x;
+    float mn = fmaxf(m, xf);
+    float ms = msafe(mn);
+    float sc = (m == neg_inf()) ? 0.f : fast_exp(msafe(m) - ms);
+    s = s * sc + fast_exp((float)(x - (double)ms));
+    m = mn;
+  }
+  template <int N> __device__ void add_chunk_d(const double (&x)[N], float cm) {
+    float mn = fmaxf(m, cm);
+    float ms = msafe(mn);
+    float sc = (m == neg_inf()) ? 0.f : fast_exp(msafe(m) - ms);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc += fast_exp((float)(x[i] - (double)ms));
+    s = s * sc + acc;
+    m = mn;
+  }
   __device__ void merge(const Acc& o) {
     float mn = fmaxf(m, o.m);
     float ms = msafe(mn);

@@ -52,7 +52,7 @@ __device__ __forceinline__ void rows_backward(
     const NGram& g, const float* __restrict__ lex, float* __restrict__ glex,
     const float* __restrict__ nb, const float* __restrict__ src_alpha,
     float logz, float gscale, bool scale_ok, int p_lo, int p_hi, bool accumulate,
-    float* row_out) {
+    double* row_out) {
   constexpr int RPW = 32 / LPR;              // rows per warp pass
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -69,28 +69,34 @@ __device__ __forceinline__ void rows_backward(
     const int ds = g.pstride ? 1 : 0;   // n == 0: every arc leads to state 0
     const float a = src_alpha[pc];
     if constexpr (SR == LT_LOG) {
-      float x[8];
+      // The sums w + beta'[next] are exact in double; the row maximum is only a shift (float),
+      // and every exponent (w + beta') - ms is rounded ONCE, after the subtraction: an arc near
+      // the maximum carries no rounding error of the sum (ulp(|w + beta'|) ~ 2e-6 at |w| ~ 30
+      // when formed in float).  These kernels are latency-bound; B200 has full-rate-ish FP64.
+      double x[8];
       float m = neg_inf();
       if (single) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int y = l + i * LPR;
-          x[i] = (y < V) ? ldg_stream(row + y) + dst[y * ds] : neg_inf();
-          m = fmaxf(m, x[i]);
+          x[i] = (y < V) ? (double)ldg_stream(row + y) + (double)dst[y * ds] : (double)neg_inf();
+          m = fmaxf(m, (float)x[i]);
         }
       } else {
-        for (int y = l; y < V; y += LPR) m = fmaxf(m, ldg_stream(row + y) + dst[y * ds]);
+        for (int y = l; y < V; y += LPR)
+          m = fmaxf(m, (float)((double)ldg_stream(row + y) + (double)dst[y * ds]));
       }
       m = group_max<LPR>(m);
       const float ms = msafe(m);
       // per-row posterior scale; 0 when the lattice is unreachable (logZ = -inf)
-      const float rs = scale_ok ? gscale * fast_exp(a + ms - logz) : 0.f;
+      const float rs = scale_ok
+          ? gscale * fast_exp((float)((double)a + (double)ms - (double)logz)) : 0.f;
       float s = 0.f;
       if (single) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int y = l + i * LPR;
-          const float e = fast_exp(x[i] - ms);
+          const float e = fast_exp((float)(x[i] - (double)ms));
           s += e;
           if (active && y < V) {
             const float gv = e * rs;
@@ -99,7 +105,8 @@ __device__ __forceinline__ void rows_backward(
         }
       } else {
         for (int y = l; y < V; y += LPR) {
-          const float e = fast_exp(ldg_stream(row + y) + dst[y * ds] - ms);
+          const float e = fast_exp(
+              (float)((double)ldg_stream(row + y) + (double)dst[y * ds] - (double)ms));
           s += e;
           if (active) {
             const float gv = e * rs;
@@ -108,7 +115,7 @@ __device__ __forceinline__ void rows_backward(
         }
       }
       s = group_sum<LPR>(s);
-      if (active && l == 0) row_out[p - p_lo] = ms + fast_log(s);
+      if (active && l == 0) row_out[p - p_lo] = (double)ms + (double)fast_log(s);
     } else {  // Real
       float s = 0.f;
       const float ga = gscale * a;
@@ -121,9 +128,18 @@ __device__ __forceinline__ void rows_backward(
         }
       }
       s = group_sum<LPR>(s);
-      if (active && l == 0) row_out[p - p_lo] = s;
+      if (active && l == 0) row_out[p - p_lo] = (double)s;
     }
   }
+}
+
+// log(exp(a) + exp(b)) - shift for exact double arguments, rounded once (the non-finite-max rule
+// of semirings.py:250-251).
+__device__ __forceinline__ float logaddexp_shifted_d(double a, double b, float shift) {
+  const double c = a > b ? a : b;
+  const double cs = (c == c && c - c == 0.0) ? c : 0.0;          // finite ? c : 0
+  const float z = fast_exp((float)(a - cs)) + fast_exp((float)(b - cs));
+  return (float)((cs - (double)shift) + (double)fast_log(z));
 }
 
 template <int SR, bool FLD, int LPR>
@@ -142,7 +158,7 @@ lattice_backward_generic(const BwdParams p) {
   float* buf0 = smem;
   float* buf1 = buf0 + Cp;
   float* buf2 = buf1 + Cp;                      // FLD only
-  float* row_out = buf2 + (FLD ? Cp : 0);       // [dslice]
+  double* row_out = reinterpret_cast<double*>(buf2 + (FLD ? Cp : 0));   // [dslice], 8-byte aligned
 
   const int p_lo = min(C, (int)rank * p.dslice);
   const int p_hi = min(C, p_lo + p.dslice);
@@ -192,12 +208,16 @@ lattice_backward_generic(const BwdParams p) {
       __syncthreads();
       for (int d = tid; d < D; d += nth) {
         const int q = p_lo + d;
-        const float bb = S::times(blank[q], beta[q]);
-        const float v = S::plus(bb, row_out[d]) - shift;
-        if constexpr (SR == LT_LOG)
-          gb[q] = scale_ok ? gscale * fast_exp(alpha[q] + bb - logz) : 0.f;
-        else
+        float v;
+        if constexpr (SR == LT_LOG) {
+          const double bb = (double)blank[q] + (double)beta[q];
+          v = logaddexp_shifted_d(bb, row_out[d], shift);
+          gb[q] = scale_ok
+              ? gscale * fast_exp((float)((double)alpha[q] + bb - (double)logz)) : 0.f;
+        } else {
+          v = blank[q] * beta[q] + (float)row_out[d];
           gb[q] = gscale * alpha[q] * beta[q];
+        }
         bcast_store_b(nxt, q, v, nrank);
       }
       cluster_sync_all();
@@ -214,9 +234,10 @@ lattice_backward_generic(const BwdParams p) {
         float acc = 0.f;
         if constexpr (SR == LT_LOG) {
           if (scale_ok) {
-            const float base = blank[q] + beta[q] - logz;
-            acc = fast_exp(alpha[q] + base);
-            for (int i = 0; i < k; ++i) acc += fast_exp(lev[(size_t)i * C + q] + base);
+            const double base = (double)blank[q] + (double)beta[q] - (double)logz;
+            acc = fast_exp((float)((double)alpha[q] + base));
+            for (int i = 0; i < k; ++i)
+              acc += fast_exp((float)((double)lev[(size_t)i * C + q] + base));
             acc *= gscale;
           }
         } else {
@@ -235,8 +256,12 @@ lattice_backward_generic(const BwdParams p) {
         __syncthreads();
         for (int d = tid; d < D; d += nth) {
           const int q = p_lo + d;
-          float v = S::plus(S::times(blank[q], beta[q]), row_out[d]);  // alignments.py:414-415
-          if (j == 0) v -= shift;            // nb_0 is beta_t: move it to the frame of off_t
+          float v;                                 // alignments.py:414-415
+          if constexpr (SR == LT_LOG)              // nb_0 is beta_t: move it to the frame of off_t
+            v = logaddexp_shifted_d((double)blank[q] + (double)beta[q], row_out[d],
+                                    j == 0 ? shift : 0.f);
+          else
+            v = blank[q] * beta[q] + (float)row_out[d];
           bcast_store_b(out, q, v, nrank);
         }
         cluster_sync_all();
@@ -302,7 +327,7 @@ int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const B
   const long long work = (long long)p.dslice * g.V;
   const int block = work >= 8192 ? 512 : (work >= 1024 ? 256 : 128);
   const int Cp = (g.C + 3) & ~3;
-  size_t smem = sizeof(float) * ((size_t)Cp * (fld ? 3 : 2) + (size_t)p.dslice);
+  size_t smem = sizeof(float) * ((size_t)Cp * (fld ? 3 : 2) + 2 * (size_t)p.dslice);   // row_out: double
   if (smem > 227 * 1024) {
     set_error("lt_lattice_backward: %d context states need %zu bytes of shared memory per CTA "
               "(limit 232448)", g.C, smem);

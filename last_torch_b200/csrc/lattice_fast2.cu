@@ -90,14 +90,14 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
   // shared-memory carve-up: [group][stage] tiles, then per-group small state
   float* tiles = reinterpret_cast<float*>(smem2) + (size_t)grp * NS * (kStageBytes / 4);
   float* small = reinterpret_cast<float*>(smem2 + (size_t)G * NS * kStageBytes);
-  constexpr int kSmallFloats = 2 * CP + 4 * kPart + 2 * 16 + 4;   // alpha x2, pmax x2, psum x2, bars, shift
+  constexpr int kSmallFloats = 2 * CP + 4 * kPart + 2 * 16 + 16;  // alpha x2, pmax x2, psum x2, bars, wmax x2
   small += (size_t)grp * kSmallFloats;
   float* alpha_buf = small;
   float* part_m = alpha_buf + 2 * CP;           // [2][warps][32]
   float* part_s = part_m + 2 * kPart;           // [2][warps][32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + 2 * kPart);   // NS full + 2 exchange
   uint64_t* xbar = bars + NS;
-  float* shift_slot = reinterpret_cast<float*>(bars + 16);   // NORM: d_t, written by warp 1
+  float* wmax = reinterpret_cast<float*>(bars + 16);   // NORM: [2][8] per-warp maxima of alpha~_t
 
   const int cg = gt & 7;                        // column group: columns 4cg .. 4cg+3
   const int rg = gt >> 3;                       // row group: rows rg*RPT .. +RPT-1
@@ -174,22 +174,24 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
       }
     }
     if (p.alphas && (is_fin || is_q0)) p.alphas[(bt0 + t) * C + q] = from_dom<SR>(cur[q]);
-    if constexpr (NORM) {
-      // d_t = floor(max_c alpha~_t[c]): every CTA derives it from its own (identical) replica,
-      // so no exchange is needed; an integer keeps `off` exact and the subtraction below exact.
-      if (warp == 1) {
-        float m = neg_inf();
-        for (int c = lane; c < C; c += 32) m = fmaxf(m, cur[c]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) shift_slot[t & 1] = norm_shift(m);
-        if (rank == 0 && lane == 0) p.alpha_norm[(size_t)b * (p.T + 3) + t] = off;
-      }
-    }
-
     float a[RPT];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) a[i] = cur[r0 + i];
+    if constexpr (NORM) {
+      // d_t = floor(max_{c < V} alpha~_t[c]): every CTA derives it from its own (identical)
+      // replica, so no exchange is needed; an integer keeps `off` exact and the subtraction
+      // below exact.  The maximum is taken over the values every thread has just loaded (the
+      // row groups of a warp cover 32 states, the 8 warps states 0 .. V-1; the shift need not
+      // see state V) and merged through the shared-memory hand-over that sync #1 orders anyway:
+      // no extra pass over alpha and nothing added to the frame's dependency chain.
+      float am = a[0];
+#pragma unroll
+      for (int i = 1; i < RPT; ++i) am = fmaxf(am, a[i]);
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 8));
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 16));
+      if (lane == 0) wmax[(t & 1) * 8 + warp] = am;
+      if (is_q0) p.alpha_norm[(size_t)b * (p.T + 3) + t] = off;
+    }
 
     float pm[4], ps[4];
     if constexpr (SR == LT_LOG) {
@@ -252,7 +254,15 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
     }
     group_sync(grp);   // #1: partial maxima visible; every thread holds its tile slice in registers
     float shift = 0.f;
-    if constexpr (NORM) { shift = shift_slot[t & 1]; off += (int)shift; }
+    if constexpr (NORM) {
+      if (warp < 2) {                         // finalisers (warp 0) and the state-0 / logZ warp
+        const float4 w0 = *reinterpret_cast<const float4*>(wmax + (t & 1) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wmax + (t & 1) * 8 + 4);
+        shift = norm_shift(fmaxf(fmaxf(fmaxf(w0.x, w0.y), fmaxf(w0.z, w0.w)),
+                                 fmaxf(fmaxf(w1.x, w1.y), fmaxf(w1.z, w1.w))));
+        off += (int)shift;
+      }
+    }
 
     if (gt == 0 && t + NS < nf) {               // the stage is free: refill it NS frames ahead
       const uint32_t bar = smem_u32(&bars[stage]);
@@ -752,7 +762,7 @@ int lattice_forward_fast2_launch(int semiring, const NGram& g, const FwdParams& 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return LT_ERR_CUDA; }
   const size_t stage = (size_t)V * kCols * 4;
   const int CP = (C + 3) & ~3;
-  const size_t small = sizeof(float) * (2 * CP + 4 * kGroupWarps * kCols + 2 * 16 + 4);
+  const size_t small = sizeof(float) * (2 * CP + 4 * kGroupWarps * kCols + 2 * 16 + 16);
   int stages = (int)((kSharedBudget - small - 256) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("fast forward: not enough shared memory"); return LT_ERR_UNSUPPORTED; }

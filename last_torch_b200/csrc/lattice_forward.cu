@@ -50,7 +50,8 @@ __device__ __forceinline__ void reduce_into_slice(
       } else if (qa < lowV) {
         if (kg == 0) {
           const int p = qa / g.V;
-          acc.add(S::times(src[p], ldg_stream(lex + qa)), 0);
+          if constexpr (SR == LT_LOG) acc.add_d((double)src[p] + (double)ldg_stream(lex + qa));
+          else acc.add(S::times(src[p], ldg_stream(lex + qa)), 0);
         }
       } else {
         const int j = q - g.A;
@@ -64,22 +65,30 @@ __device__ __forceinline__ void reduce_into_slice(
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             x[i] = ldg_stream(col + (size_t)(kk + i) * g.N);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            x[i] = S::times(src[p0 + (kk + i) * g.pstride], x[i]);
           if constexpr (SR == LT_LOG) {
-            float cm = x[0];
+            double xd[8];
+            float cm = neg_inf();
 #pragma unroll
-            for (int i = 1; i < 8; ++i) cm = fmaxf(cm, x[i]);
-            acc.add_chunk(x, cm);
+            for (int i = 0; i < 8; ++i) {
+              xd[i] = (double)src[p0 + (kk + i) * g.pstride] + (double)x[i];
+              cm = fmaxf(cm, (float)xd[i]);
+            }
+            acc.add_chunk_d(xd, cm);
           } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              x[i] = S::times(src[p0 + (kk + i) * g.pstride], x[i]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc.add(x[i], kk + i);
           }
         }
-        for (; kk < k_hi; ++kk)
-          acc.add(S::times(src[p0 + kk * g.pstride],
-                           ldg_stream(col + (size_t)kk * g.N)), kk);
+        for (; kk < k_hi; ++kk) {
+          if constexpr (SR == LT_LOG)
+            acc.add_d((double)src[p0 + kk * g.pstride] + (double)ldg_stream(col + (size_t)kk * g.N));
+          else
+            acc.add(S::times(src[p0 + kk * g.pstride],
+                             ldg_stream(col + (size_t)kk * g.N)), kk);
+        }
       }
       const int slot = kg * (nchunk << 5) + d;
       if constexpr (SR == LT_LOG) { pm[slot] = acc.m; ps[slot] = acc.s; }
@@ -195,7 +204,7 @@ lattice_forward_generic(const FwdParams p) {
           // merge the blank term into the (m, s) pair of the reduction and round once, after
           // the shift: (msafe(m) - shift) + log(s) in double
           Acc<LT_LOG> acc; acc.m = pm[d]; acc.s = ps[d];
-          acc.add(a, 0);
+          acc.add_d((double)cur[q] + (double)blank[q]);
           v = log_value_shifted(acc.m, acc.s, shift);
         } else if constexpr (SR == LT_MAXTROPICAL) {
           const bool take_blank = a >= r;      // semirings.py:363

@@ -351,8 +351,31 @@ def joint_lattice_case(name, vocab, hidden, emb, feat, batch, t_max, num_frames,
         f'{np.abs(out["grad_w_vocab"]).max():.3e}')
 
 
+def rnn_cacher_case(name, vocab, ctx, rnn_size, emb_size, seed):
+  """Reference SharedRNNCacher.forward (weight_fns.py:265-294) with an injected, seeded LSTMCell
+  (as shipped it builds a fresh random cell per call when none is given)."""
+  torch.manual_seed(seed)
+  cell = torch.nn.LSTMCell(emb_size, rnn_size)
+  cacher = last_torch.weight_fns.SharedRNNCacher(
+      vocab_size=vocab, context_size=ctx, rnn_size=rnn_size, rnn_embedding_size=emb_size,
+      rnn_cell=cell)
+  with torch.no_grad():
+    cache = cacher()
+  out = dict(vocab=vocab, context_size=ctx, rnn_size=rnn_size, emb_size=emb_size,
+             embedding=cacher.embedding.weight.detach().numpy(),
+             weight_ih=cell.weight_ih.detach().numpy(), weight_hh=cell.weight_hh.detach().numpy(),
+             bias_ih=cell.bias_ih.detach().numpy(), bias_hh=cell.bias_hh.detach().numpy(),
+             cache=cache.numpy())
+  np.savez_compressed(os.path.join(OUT, f'rnncacher_{name}.npz'), **out)
+  print(f'{name}: rnn cacher ok cache{tuple(cache.shape)}')
+
+
 def main():
   torch.set_num_threads(4)
+  if os.environ.get('LT_GOLDEN_ONLY') == 'rnncacher':
+    rnn_cacher_case('bigram_v5', vocab=5, ctx=1, rnn_size=12, emb_size=7, seed=50)
+    rnn_cacher_case('trigram_v3', vocab=3, ctx=2, rnn_size=8, emb_size=6, seed=51)
+    return
   lattice_case('fd_bigram_v3', vocab=3, ctx=1, k=None, batch=4, t_max=6,
                num_frames=[6, 4, 1, 0],
                labels=[[1, 3, 2], [2, 2, 0], [3, 0, 0], [1, 2, 3]],
@@ -410,6 +433,8 @@ def main():
   joint_lattice_case('trigram_v3_fld2', vocab=3, hidden=32, emb=12, feat=20, batch=3, t_max=5,
                      num_frames=[5, 4, 2], labels=[[1, 3, 2, 2, 1], [2, 2, 0, 0, 0], [3, 1, 0, 0, 0]],
                      num_labels=[5, 2, 2], seed=42, ctx=2, k=2)
+  rnn_cacher_case('bigram_v5', vocab=5, ctx=1, rnn_size=12, emb_size=7, seed=50)
+  rnn_cacher_case('trigram_v3', vocab=3, ctx=2, rnn_size=8, emb_size=6, seed=51)
 
 
 if __name__ == '__main__':

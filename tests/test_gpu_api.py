@@ -665,3 +665,44 @@ def test_split_row_handover_is_invisible_to_autograd():
     scale = float(b.abs().max()) + 1e-12
     assert float((a - b).abs().max()) / scale < 2e-5
   npt.assert_allclose(seen[0].cpu() * 2, out[True][5].cpu(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('fname', golden_files('rnncacher_'))
+def test_shared_rnn_cacher_golden_on_gpu(fname):
+  """SharedRNNCacher on the GPU against the reference's own forward
+  (weight_fns.py:265-294) run with an injected LSTMCell (tests/golden/make_golden.py), then
+  through RecognitionLattice.forward with JointWeightFn: the loss back-propagates into the
+  LSTM cell and the label embedding (the reference rebuilds a random cell per call, D7)."""
+  lt = _lt()
+  g = np.load(os.path.join(GOLDEN_DIR, fname))
+  v, n = int(g['vocab']), int(g['context_size'])
+  rnn_size, emb = int(g['rnn_size']), int(g['emb_size'])
+  cell = torch.nn.LSTMCell(emb, rnn_size, device='cuda')
+  with torch.no_grad():
+    cell.weight_ih.copy_(T(g['weight_ih'])); cell.weight_hh.copy_(T(g['weight_hh']))
+    cell.bias_ih.copy_(T(g['bias_ih'])); cell.bias_hh.copy_(T(g['bias_hh']))
+  context = lt.contexts.FullNGram(vocab_size=v, context_size=n)
+
+  def make_cacher(_):
+    cacher = lt.weight_fns.SharedRNNCacher(vocab_size=v, context_size=n, rnn_size=rnn_size,
+                                           rnn_embedding_size=emb, rnn_cell=cell, device='cuda')
+    with torch.no_grad():
+      cacher.embedding.weight.copy_(T(g['embedding']))
+    return cacher
+
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=make_cacher,
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=16, device='cuda'))
+  cache = lattice.build_cache()
+  assert cache.is_cuda and tuple(cache.shape) == (context.num_states(), rnn_size)
+  npt.assert_allclose(cache.detach().cpu(), g['cache'], rtol=1e-5, atol=1e-6)
+  torch.manual_seed(0)
+  x = torch.randn([2, 7, 5], device='cuda')
+  loss = lattice(frames=x, num_frames=T([7, 4]), labels=T([[1, 2, 1], [3, 0, 0]]),
+                 num_labels=T([3, 1]))
+  loss.sum().backward()
+  assert bool(torch.isfinite(loss).all())
+  for p in list(cell.parameters()) + [lattice.weight_fn_cacher.embedding.weight]:
+    assert p.grad is not None and float(p.grad.abs().max()) > 0

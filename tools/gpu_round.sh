@@ -12,6 +12,11 @@ for s in $STEPS; do
     bench)    timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; head -c 600 gpurun_out/bench.json ;;
     benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "benchref rc=$?" ;;
     sanitize) bash tools/sanitize.sh gpurun_out/sanitizer; echo "sanitize done" ;;
+    prof)     CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-extras"
+              $CMD > gpurun_out/prof_plain.log 2>&1 && \
+              ncu --set full --clock-control none --import-source on \
+                  -k regex:"fast2|joint_forward_tc|joint_dgrad2|joint_wgrad_tc" -c 10 \
+                  -f -o gpurun_out/r02_prof $CMD > gpurun_out/prof_ncu.log 2>&1; echo "prof rc=$?"; tail -n 3 gpurun_out/prof_ncu.log ;;
     sanity)   timeout 900 python tools/sanitize_targets.py > gpurun_out/sanitize_targets.log 2>&1; echo "sanity rc=$?"; tail -n 4 gpurun_out/sanitize_targets.log ;;
     benchab)  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_norm.json 2> gpurun_out/bench_norm.err; echo "bench norm rc=$?"
               LT_NO_NORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_nonorm.json 2> gpurun_out/bench_nonorm.err; echo "bench nonorm rc=$?" ;;

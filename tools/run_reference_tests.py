@@ -128,6 +128,8 @@ def main():
     env['LT_REFTEST_DEVICE'] = 'cpu'
   if not os.path.isdir(DEST):
     raise SystemExit('run with --prepare first (in the build container)')
+  with open(os.path.join(DEST, 'conftest.py'), 'w') as f:      # the harness is always current
+    f.write(CONFTEST)
   cmd = [sys.executable, '-m', 'pytest', DEST, '-q', '-p', 'no:cacheprovider',
          '-o', 'python_files=*_test.py', '--rootdir', DEST] + args
   return subprocess.call(cmd, env=env, cwd=DEST)
