@@ -15,7 +15,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'liblast_lattice.so')
+# LT_LIBRARY selects another build of the same sources (A/B experiments with compile-time switches)
+LIB_PATH = os.environ.get('LT_LIBRARY') or os.path.join(_HERE, '_C', 'liblast_lattice.so')
 
 REAL, LOG, MAXTROPICAL = 0, 1, 2
 FRAME_DEPENDENT = -1

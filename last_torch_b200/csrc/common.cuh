@@ -7,6 +7,15 @@
 
 #include "../../include/last_lattice.h"
 
+// mbarrier.try_wait suspend-time hint (ns): the waiting warp is parked by the hardware and woken
+// when the phase completes instead of re-polling the barrier.  Every poll is a shared-memory
+// access on the L1 data pipe -- the pipe the tensor core's operand reads and the producers'
+// stores already saturate in the joint kernels (ncu, profiles/r02: 236 M polls = a quarter of all
+// issued instructions of the forward kernel before the hint).
+#ifndef LT_MBAR_HINT
+#define LT_MBAR_HINT ", 0x989680"
+#endif
+
 namespace lt {
 
 // ---------------------------------------------------------------------------

@@ -65,7 +65,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
       "{\n"
       ".reg .pred p;\n"
       "LTD_WAIT%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1" LT_MBAR_HINT ";\n"
       "@p bra LTD_DONE%=;\n"
       "bra LTD_WAIT%=;\n"
       "LTD_DONE%=:\n"
@@ -112,7 +112,7 @@ __device__ __forceinline__ void mbar_wait_parity_cluster(uint32_t bar, uint32_t 
       "{\n"
       ".reg .pred p;\n"
       "LTDC_WAIT%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1" LT_MBAR_HINT ";\n"
       "@p bra LTDC_DONE%=;\n"
       "bra LTDC_WAIT%=;\n"
       "LTDC_DONE%=:\n"

@@ -31,7 +31,7 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
       "{\n"
       ".reg .pred p;\n"
       "LTJ_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1" LT_MBAR_HINT ";\n"
       "@p bra LTJ_DONE;\n"
       "bra LTJ_WAIT;\n"
       "LTJ_DONE:\n"

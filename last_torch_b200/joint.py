@@ -96,3 +96,22 @@ def joint_all_frames(fn, cache, frames):
       fn.joint_projection_to_vocab.bias)
   c, v = proj_ctx.shape[0], fn.vocab_size
   return blank.reshape(*batch_shape, c), lexical.reshape(*batch_shape, c, v)
+
+
+def joint_string_frames(fn, cache, frames, states):
+  """fn: weight_fns.JointWeightFn; cache [C,E]; frames [B,T,D]; states [B,U1] ->
+  (blank [B,T,U1], lexical [B,T,U1,V]): the vocabulary projection on the context states of each
+  utterance's label string only (lattices.py:300-313)."""
+  b, t, _ = frames.shape
+  proj_ctx, proj_frame = joint_projections(fn, cache, frames)              # [C,H], [B*T,H]
+  proj_frame = proj_frame.reshape(b, t, -1)
+  idx = states.to(torch.int64)
+  blanks, lexicals = [], []
+  for i in range(b):
+    bl, lx = _JointProjection.apply(
+        proj_ctx.index_select(0, idx[i]), proj_frame[i], fn.joint_projection_to_blank.weight,
+        fn.joint_projection_to_blank.bias.reshape(()), fn.joint_projection_to_vocab.weight,
+        fn.joint_projection_to_vocab.bias)
+    blanks.append(bl)
+    lexicals.append(lx)
+  return torch.stack(blanks), torch.stack(lexicals)

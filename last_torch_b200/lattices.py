@@ -56,6 +56,10 @@ class RecognitionLattice(nn.Module, Generic[T]):
     # JointWeightFn + FullNGram: hand the arc posteriors to the joint network's backward as
     # split rows (ops.JointLatticeLoss); False keeps them in float32
     self.split_grad_handover = ops.SPLIT_GRAD_DEFAULT
+    # Numerator from the weight function evaluated on the U+1 states of the label string only
+    # (lattices.py:300-313) instead of gathered out of the dense [B,T,C,V] weights.  None =
+    # automatic: when the loss needs no denominator (LocallyNormalizedWeightFn).
+    self.gathered_numerator = None
     # shortest_path: reproduce the label encoding of the reference as shipped (see there)
     self.reference_compat = False
     # Range-check the reference labels (0 <= label <= vocab_size for the first num_labels
@@ -278,6 +282,11 @@ class RecognitionLattice(nn.Module, Generic[T]):
     self._check_labels(labels, num_labels, batch_dims)
     sr = semirings.kernel_id(semiring)
     v, n, k = self._geometry()
+    gathered = self.gathered_numerator
+    if gathered is None:
+      gathered = isinstance(self.weight_fn, weight_fns.LocallyNormalizedWeightFn)
+    if gathered and len(batch_dims) == 1 and frames.is_cuda:
+      return self._string_forward_gathered(cache, frames, num_frames, labels, num_labels, sr, k)
     blank, lexical = self._arc_weights(cache, frames, batch_dims)
     dev = blank.device
     states, next_labels = self._string_indices(labels, num_labels, dev)
@@ -285,6 +294,22 @@ class RecognitionLattice(nn.Module, Generic[T]):
         blank, lexical, ops._as_i32(num_frames.reshape(-1), dev), states, next_labels,
         ops._as_i32(num_labels.reshape(-1), dev), sr, v, k)
     return dist.reshape(batch_dims)
+
+  def _string_forward_gathered(self, cache, frames, num_frames, labels, num_labels, sr, k):
+    """_string_forward with the reference's own evaluation order (lattices.py:300-342): the
+    weight function sees only the context states along the label string, [B,T,U+1,V] instead of
+    [B,T,C,V] -- (U+1)/C of the joint network's work and memory (121 / 257 at configs[3], 121 /
+    4161 for a trigram context).  With LocallyNormalizedWeightFn the loss is this alone
+    (lattices.py:178-179), so the dense weights are never materialised."""
+    dev = frames.device
+    states, next_labels = self._string_indices(labels, num_labels, dev)
+    bw, lw_all = self.weight_fn.string_frames(cache, frames, states)        # [B,T,U1], [B,T,U1,V]
+    b, t, u1 = bw.shape
+    pick = (next_labels.to(torch.int64) - 1)[:, None, :, None].expand(b, t, u1, 1)
+    lw = torch.gather(lw_all, 3, pick).squeeze(3)
+    return ops.StringChainForward.apply(
+        bw.contiguous().float(), lw.contiguous().float(), ops._as_i32(num_frames.reshape(-1), dev),
+        ops._as_i32(num_labels.reshape(-1), dev), sr, k)
 
   def _forward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor,
                semiring: semirings.Semiring[torch.Tensor],

@@ -465,6 +465,50 @@ def _string_scatter(V, C, gbw, glw, states, next_labels, scale, gb, gl, utt_scal
         N.ptr(utt_scale), N.ptr(gb), N.ptr(gl), N.stream_ptr(dev)), 'lt_string_scatter_add')
 
 
+class StringChainForward(torch.autograd.Function):
+  """Shortest distance on the T x (U+1) label lattice from the ALREADY GATHERED per-position
+  weights blank_w / lexical_w [B,T,U1] (shortest_distance_step_scan, lattices.py:347-377, with
+  alignment.string_forward): the numerator when the weight function was only evaluated on the
+  U+1 states of the label string (lattices.py:300-313) instead of on all context states."""
+
+  @staticmethod
+  def forward(ctx, bw, lw, num_frames, num_labels, sr, k):
+    bw = N.require_cuda(bw, 'blank_w')
+    lw = N.require_cuda(lw, 'lexical_w')
+    B, T, U1 = bw.shape
+    dev = bw.device
+    need_grad = any(ctx.needs_input_grad[:2])
+    dist = torch.empty([B], dtype=torch.float32, device=dev)
+    use_ext = bool(USE_NORM and B > 0 and T > 0 and N.lib().lt_string_norm_supported(sr, k, U1))
+    alphas = (torch.empty([B, T, U1], dtype=torch.float32, device=dev)
+              if (need_grad and sr != N.MAXTROPICAL) or use_ext else None)
+    backptr = (torch.empty([B, T, U1], dtype=torch.uint8, device=dev)
+               if need_grad and sr == N.MAXTROPICAL else None)
+    alpha_exp = dist_norm = None
+    if use_ext:
+      alpha_exp = torch.empty([B, T, U1], dtype=torch.int32, device=dev)
+      dist_norm = torch.empty([B, 2], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_string_forward_norm(
+          sr, k, N.ptr(bw), N.ptr(lw), N.ptr(num_frames), N.ptr(num_labels), B, T, U1,
+          N.ptr(dist), N.ptr(alphas), N.ptr(backptr), N.ptr(alpha_exp), N.ptr(dist_norm),
+          N.stream_ptr(dev)), 'lt_string_forward')
+    ctx.geom = (sr, k)
+    ctx.save_for_backward(bw, lw, num_frames, num_labels, alphas, backptr, dist, alpha_exp,
+                          dist_norm)
+    return dist
+
+  @staticmethod
+  def backward(ctx, g_dist):
+    sr, k = ctx.geom
+    bw, lw, num_frames, num_labels, alphas, backptr, dist, alpha_exp, dist_norm = \
+        ctx.saved_tensors
+    g_dist = N.require_cuda(g_dist, 'grad_dist')
+    gbw, glw = _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist,
+                                g_dist, ext=(alpha_exp, dist_norm))
+    return gbw, glw, None, None, None, None
+
+
 class StringForward(torch.autograd.Function):
   """RecognitionLattice._string_forward on dense weights (lattices.py:250-377)."""
 

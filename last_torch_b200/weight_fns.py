@@ -52,6 +52,18 @@ class WeightFn(nn.Module, Generic[T], abc.ABC):
             torch.stack([o[1] for o in outs], dim=nb))
 
 
+  def string_frames(self, cache: T, frames: torch.Tensor,
+                    states: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """Arc weights of all frames on the context states of a label string ONLY
+    (lattices.py:300-313, weight_step_scan :830-845): frames [B, T, feature_size], states
+    [B, U1] -> (blank [B, T, U1], lexical [B, T, U1, V]).  Default: one `forward` call per
+    string position with the state broadcast over the frames (what the reference does);
+    subclasses override it with batched evaluations."""
+    b, t = frames.shape[:2]
+    outs = [self(cache, frames, states[:, u, None].expand(b, t)) for u in range(states.shape[1])]
+    return torch.stack([o[0] for o in outs], dim=2), torch.stack([o[1] for o in outs], dim=2)
+
+
 class WeightFnCacher(nn.Module, Generic[T], abc.ABC):
   """Interface (weight_fns.py:86-96)."""
 
@@ -135,6 +147,9 @@ class LocallyNormalizedWeightFn(WeightFn[T]):
   def all_frames(self, cache, frames):
     return self.normalize(*self.weight_fn.all_frames(cache, frames))
 
+  def string_frames(self, cache, frames, states):
+    return self.normalize(*self.weight_fn.string_frames(cache, frames, states))
+
 
 class JointWeightFn(WeightFn[torch.Tensor]):
   r"""tanh(W_c emb[c] + W_f frame) -> Linear(H, 1), Linear(H, V)
@@ -216,6 +231,14 @@ class JointWeightFn(WeightFn[torch.Tensor]):
     self._check_lazy(cache, frames)
     from . import joint as joint_ops   # CUDA (tcgen05) vocabulary projection
     return joint_ops.joint_all_frames(self, cache, frames)
+
+  def string_frames(self, cache, frames, states):
+    """The joint network on the U+1 states of every utterance's label string: per utterance one
+    kernel call with proj_ctx gathered at its states (C := U+1, N := T), i.e. (U+1) / C of the
+    work and memory of all_frames."""
+    self._check_lazy(cache, frames)
+    from . import joint as joint_ops
+    return joint_ops.joint_string_frames(self, cache, frames, states)
 
 
 class SharedEmbCacher(WeightFnCacher[torch.Tensor]):
@@ -322,6 +345,20 @@ class TableWeightFn(WeightFn[type(None)]):
       sidx = state.reshape(*state.shape, 1, 1).expand(*state.shape, 1, weights.shape[-1])
       weights = torch.gather(weights, len(batch_dims), sidx).squeeze(len(batch_dims))
     return weights[..., 0], weights[..., 1:]
+
+  def string_frames(self, cache, frames, states):
+    del cache
+    *batch_dims, input_vocab_size, num_context_states, width = self.table.shape
+    if tuple(frames.shape[:-2]) != tuple(batch_dims) or len(batch_dims) != 1:
+      raise ValueError(f'frame should have batch_dims={tuple(batch_dims)} but '
+                       f'got ({tuple(frames.shape[:-2])})')
+    b, t = frames.shape[:2]
+    u1 = states.shape[1]
+    index = frames[..., 0].to(torch.int64)                                  # [B, T]
+    table = self.table.float()
+    bi = torch.arange(b, device=table.device)[:, None, None]
+    w = table[bi, index[:, :, None], states.to(torch.int64)[:, None, :]]    # [B, T, U1, 1+V]
+    return w[..., 0].contiguous(), w[..., 1:].contiguous()
 
   def all_frames(self, cache, frames):
     del cache

@@ -706,3 +706,82 @@ def test_shared_rnn_cacher_golden_on_gpu(fname):
   assert bool(torch.isfinite(loss).all())
   for p in list(cell.parameters()) + [lattice.weight_fn_cacher.embedding.weight]:
     assert p.grad is not None and float(p.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize('normalize', ['hat', 'log_softmax'])
+@pytest.mark.parametrize('vocab,hidden,ctx', [(128, 128, 1), (6, 16, 2)])
+def test_locally_normalized_loss_uses_the_state_gathered_weights(normalize, vocab, hidden, ctx):
+  """lattices.py:178-179 + :300-313: with LocallyNormalizedWeightFn the loss is -numerator and the
+  weight function only has to be evaluated on the U+1 context states of each label string
+  (WeightFn.string_frames -> [B,T,U+1,V]); same loss and parameter gradients as gathering out
+  of the dense [B,T,C,V] weights (gathered_numerator = False), tensor-core and CUDA-core joint
+  kernels, bigram and trigram contexts."""
+  lt = _lt()
+  torch.manual_seed(vocab + ctx)
+  norm = lt.weight_fns.hat_normalize if normalize == 'hat' else lt.weight_fns.log_softmax_normalize
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=vocab, context_size=ctx),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.LocallyNormalizedWeightFn(
+          lt.weight_fns.JointWeightFn(vocab_size=c.shape()[1], hidden_size=hidden, device='cuda',
+                                      embedding_size=24, feature_size=16), norm))
+  b, t, u = 3, 21, 7
+  x = torch.randn([b, t, 16], device='cuda', requires_grad=True)
+  args = dict(num_frames=T([21, 13, 8]),
+              labels=torch.randint(1, vocab + 1, [b, u], device='cuda'), num_labels=T([7, 4, 2]))
+  out = {}
+  for gathered in (True, False):
+    lattice.gathered_numerator = gathered
+    lattice.zero_grad()
+    x.grad = None
+    torch.cuda.reset_peak_memory_stats()
+    loss = lattice(frames=x, **args)
+    loss.sum().backward()
+    out[gathered] = (loss.detach().clone(),
+                     [p.grad.clone() for p in lattice.parameters()] + [x.grad.clone()])
+  lattice.gathered_numerator = None      # automatic = gathered for a locally normalised fn
+  auto = lattice(frames=x, **args)
+  npt.assert_array_equal(auto.detach().cpu(), out[True][0].cpu())
+  assert bool(torch.isfinite(out[True][0]).all()) and bool((out[True][0] > 0).all())
+  npt.assert_allclose(out[True][0].cpu(), out[False][0].cpu(), rtol=2e-5)
+  for a, r in zip(out[True][1], out[False][1]):
+    scale = float(r.abs().max()) + 1e-12
+    assert float((a - r).abs().max()) / scale < 5e-5, tuple(r.shape)
+
+
+def test_table_weight_fn_string_frames_matches_dense_gather():
+  """WeightFn.string_frames of TableWeightFn (and the per-position default of the base class)
+  against gathering the string's arcs out of all_frames, and _string_forward through it for the
+  three semirings."""
+  lt = _lt()
+  torch.manual_seed(2)
+  b, t, vocab, u = 3, 9, 5, 4
+  c = 1 + vocab + vocab * vocab
+  table = torch.randn([b, t, c, 1 + vocab], device='cuda')
+  fn = lt.weight_fns.TableWeightFn(table)
+  frames = torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None].expand(b, t, 1)
+  states = torch.randint(0, c, [b, u + 1], device='cuda')
+  bl, lx = fn.string_frames(None, frames, states)
+  db, dl = fn.all_frames(None, frames)
+  bi = torch.arange(b, device='cuda')[:, None, None]
+  ti = torch.arange(t, device='cuda')[None, :, None]
+  npt.assert_array_equal(bl.cpu(), db[bi, ti, states[:, None, :]].cpu())
+  npt.assert_array_equal(lx.cpu(), dl[bi, ti, states[:, None, :]].cpu())
+  b2, l2 = lt.weight_fns.WeightFn.string_frames(fn, None, frames, states)   # base-class default
+  npt.assert_array_equal(b2.cpu(), bl.cpu())
+  npt.assert_array_equal(l2.cpu(), lx.cpu())
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=vocab, context_size=2),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_factory=lambda _: fn, weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+  labels = torch.randint(1, vocab + 1, [b, u], device='cuda')
+  for name in ['Log', 'MaxTropical', 'Real']:
+    res = []
+    for gathered in (True, False):
+      lattice.gathered_numerator = gathered
+      res.append(lattice._string_forward(cache=None, frames=frames, num_frames=T([9, 6, 2]),
+                                         labels=labels, num_labels=T([4, 2, 1]),
+                                         semiring=getattr(lt.semirings, name)))
+    npt.assert_allclose(res[0].cpu(), res[1].cpu(), rtol=1e-6, err_msg=name)

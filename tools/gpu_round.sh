@@ -17,6 +17,9 @@ for s in $STEPS; do
               ncu --set full --clock-control none --import-source on \
                   -k regex:"fast2|joint_forward_tc|joint_dgrad2|joint_wgrad_tc" -c 10 \
                   -f -o gpurun_out/r02_prof $CMD > gpurun_out/prof_ncu.log 2>&1; echo "prof rc=$?"; tail -n 3 gpurun_out/prof_ncu.log ;;
+    benchlib) # A/B of two builds of the library: default vs $LT_AB_LIB (path relative to the repo root)
+              timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_A.json 2> gpurun_out/bench_A.err; echo "bench A rc=$?"
+              LT_LIBRARY=$PWD/$LT_AB_LIB timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_B.json 2> gpurun_out/bench_B.err; echo "bench B rc=$?" ;;
     sanity)   timeout 900 python tools/sanitize_targets.py > gpurun_out/sanitize_targets.log 2>&1; echo "sanity rc=$?"; tail -n 4 gpurun_out/sanitize_targets.log ;;
     benchab)  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_norm.json 2> gpurun_out/bench_norm.err; echo "bench norm rc=$?"
               LT_NO_NORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-extras --no-cpu > gpurun_out/bench_nonorm.json 2> gpurun_out/bench_nonorm.err; echo "bench nonorm rc=$?" ;;
