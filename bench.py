@@ -535,7 +535,7 @@ def run_b200(args):
       return loss_h
 
     e_steps, e_warm = max(1, args.steps), max(1, args.warmup)
-    ms_e2e, e_launches, e_kernels, _ = timed(e2e_step, e_steps, e_warm)
+    ms_e2e, e_launches, e_kernels, e_clocks = timed(e2e_step, e_steps, e_warm, sample_clocks=True)
     kms = {k: statistics.mean(v) for k, v in e_kernels.items()}
     kms['lt_h2d'] = statistics.mean(state['h2d_ms']) if state['h2d_ms'] else None
     if world > 1:
@@ -543,7 +543,7 @@ def run_b200(args):
     e2e = {'value': units / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e_steps,
            'warmup': e_warm, 'gpu_launches_per_step': e_launches / e_steps,
-           'kernels_ms': kms,
+           'kernels_ms': kms, 'clocks': e_clocks,
            'h2d': ('double-buffered on a copy stream: the copy of step i+1 is issued before step '
                    'i\'s kernels; lt_h2d is its duration on that stream (overlapped), '
                    'nccl_all_reduce the flat loss + parameter-gradient all-reduce'),
@@ -618,6 +618,9 @@ def run_b200(args):
                 'B=32 T=1000', 32, 1000, 256, 1, 2, 120, 'lossgrad')
       run_extra('configs[1] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=32 T=1000 '
                 '(real frames counted)', 32, 1000, 256, 1, -1, 120, 'lossgrad', ragged=True)
+      run_extra('configs[4] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=96/GPU (utterances '
+                'are handed to clusters longest first)', 96, 1000, 256, 1, -1, 120, 'lossgrad',
+                ragged=True)
       run_extra('configs[1] Log loss+grad, B=48/GPU', 48, 1000, 256, 1, -1, 120, 'lossgrad')
       run_extra('configs[1] Log forward only, B=32/GPU', 32, 1000, 256, 1, -1, 120, 'forward')
       run_extra('configs[1] Log forward only, B=8/GPU', 8, 1000, 256, 1, -1, 120, 'forward')

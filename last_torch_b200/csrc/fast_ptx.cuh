@@ -28,7 +28,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "LT_WAIT_LOOP%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1" LT_MBAR_HINT ";\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra LT_WAIT_DONE%=;\n"
       "bra LT_WAIT_LOOP%=;\n"
       "LT_WAIT_DONE%=:\n"

@@ -45,6 +45,29 @@ constexpr int kGroupThreads = 256;
 constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kCols = 32;                       // destination columns (fwd) / source rows (bwd) per CTA
 
+// Which utterance a cluster works on.  The block scheduler hands out clusters in blockIdx order
+// as slots free up -- a greedy work queue -- so with more utterances than co-resident clusters
+// (33 on a B200) the ORDER decides how well a ragged batch packs: longest first (LPT) keeps the
+// tail short.  Every CTA ranks the utterances by length itself (rank(i) = number of utterances
+// that are longer, or as long with a smaller index: O(B^2 / 256) compares per thread, a few
+// microseconds once per kernel) and takes the one whose rank equals its cluster index; all CTAs
+// of a cluster see the same num_frames and agree without communicating.
+__device__ __forceinline__ int utterance_of_cluster(int cluster_id, const int32_t* num_frames,
+                                                    int B, int T, int* slot) {
+  if (B <= 32 || B > 4096) return cluster_id;          // one wave / ranking not worth its cost
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int ni = max(0, min(num_frames[i], T));
+    int rank = 0;
+    for (int j = 0; j < B; ++j) {
+      const int nj = max(0, min(num_frames[j], T));
+      rank += (nj > ni || (nj == ni && j < i)) ? 1 : 0;
+    }
+    if (rank == cluster_id) *slot = i;
+  }
+  __syncthreads();
+  return *slot;
+}
+
 __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
@@ -84,7 +107,8 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
   const int lane = gt & 31, warp = gt >> 5;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x / CL;
-  const int b = cluster_id * G + grp;
+  __shared__ int b_slot;
+  const int b = utterance_of_cluster(cluster_id, p.num_frames, p.B, p.T, &b_slot);
   const bool active = b < p.B;
 
   // shared-memory carve-up: [group][stage] tiles, then per-group small state
@@ -454,7 +478,8 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   const uint32_t rank = cluster_ctarank();
   const bool last_rank = rank == CL - 1;
   const int cluster_id = blockIdx.x / CL;
-  const int b = cluster_id * G + grp;
+  __shared__ int b_slot;
+  const int b = utterance_of_cluster(cluster_id, p.num_frames, p.B, p.T, &b_slot);
   const bool active = b < p.B;
 
   float* tiles = reinterpret_cast<float*>(smem2) + (size_t)grp * NS * (kStageBytes / 4);

@@ -56,12 +56,23 @@ class WeightFn(nn.Module, Generic[T], abc.ABC):
                     states: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     """Arc weights of all frames on the context states of a label string ONLY
     (lattices.py:300-313, weight_step_scan :830-845): frames [B, T, feature_size], states
-    [B, U1] -> (blank [B, T, U1], lexical [B, T, U1, V]).  Default: one `forward` call per
-    string position with the state broadcast over the frames (what the reference does);
+    [B, U1] -> (blank [B, T, U1], lexical [B, T, U1, V]).  Default: what the reference does --
+    for every string position one `forward(cache, frame, state)` vectorised over the frames with
+    torch.vmap (falling back to a loop over frames for weight functions vmap cannot trace);
     subclasses override it with batched evaluations."""
-    b, t = frames.shape[:2]
-    outs = [self(cache, frames, states[:, u, None].expand(b, t)) for u in range(states.shape[1])]
-    return torch.stack([o[0] for o in outs], dim=2), torch.stack([o[1] for o in outs], dim=2)
+    t = frames.shape[1]
+    blanks, lexicals = [], []
+    for u in range(states.shape[1]):
+      state = states[:, u]
+      try:
+        bl, lx = torch.vmap(lambda fr: self(cache, fr, state), in_dims=1, out_dims=1)(frames)
+      except Exception:      # data-dependent control flow, custom autograd functions, ...
+        outs = [self(cache, frames[:, i], state) for i in range(t)]
+        bl = torch.stack([o[0] for o in outs], dim=1)
+        lx = torch.stack([o[1] for o in outs], dim=1)
+      blanks.append(bl)
+      lexicals.append(lx)
+    return torch.stack(blanks, dim=2), torch.stack(lexicals, dim=2)
 
 
 class WeightFnCacher(nn.Module, Generic[T], abc.ABC):
