@@ -647,10 +647,17 @@ def run_b200(args):
 
 def main():
   args = parse_args()
+  # stdout carries exactly ONE line, the JSON result: everything else that native libraries
+  # write to file descriptor 1 (NCCL's version banner, for one) is sent to stderr instead.
+  sys.stdout.flush()
+  real_stdout = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+  sys.stdout = real_stdout
   if args.impl == 'reference':
     run_reference(args)
   else:
     run_b200(args)
+  real_stdout.flush()
 
 
 if __name__ == '__main__':

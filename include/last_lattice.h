@@ -48,6 +48,12 @@ extern "C" {
 /* flags for lt_lattice_forward / lt_lattice_backward */
 #define LT_FLAG_FORCE_GENERIC 1u     /* never take the TMA/cluster fast path   */
 #define LT_FLAG_CLUSTER_SHIFT 8      /* bits 8..11: force cluster size (1,2,4,8) */
+#define LT_FLAG_LEVEL_WEIGHTS 32u    /* FrameLabelDependent(k) with one set of weights per alignment
+                                        state (lattices.py:447-453, zero-valued masks added per
+                                        state): blank is [B,T,k+1,C], lexical [B,T,k+1,C,V] (level i
+                                        = blank[i] / lexical[i] of alignments.py:362-376; lexical[k]
+                                        is unused) and the gradients have the same layout.  Generic
+                                        kernels only (implies LT_FLAG_FORCE_GENERIC).               */
 #define LT_FLAG_GRAD_SPLIT 16u       /* lt_lattice_backward: write grad_lexical as "split rows"
                                         (see lt_joint_backward); only when
                                         lt_lattice_backward_split_supported() returns 1 */
@@ -166,6 +172,17 @@ int lt_viterbi_backtrace(int vocab_size, int context_size, int max_expansions,
                          int B, int T, int32_t* labels, int32_t* path_states,
                          const float* grad_dist, float* grad_blank,
                          float* grad_lexical, void* stream);
+
+/* Scheduling aid for callers that run the numerator kernels on a side stream beside K1: one
+ * thread that sleeps for `nanoseconds` (<= 1 ms) on `stream`.  K1's CTAs fill the register file
+ * of an SM exactly (two per SM on 128 of the 148 SMs) and its clusters of 8 must be co-resident;
+ * 33 clusters fit on a B200.  When K1 and the small numerator kernels become launchable at the
+ * same moment (both wait for the kernel that produced the weights) and numerator CTAs are placed
+ * first, each one takes an SM away from K1, a whole cluster -- an utterance -- cannot be placed
+ * and starts only when the numerator retires: K1 then lasts up to twice as long (measured 2.25
+ * and 2.73 ms against 1.5 ms).  Delaying the side stream by a few tens of microseconds lets the
+ * block scheduler place K1 first; the numerator then runs on the SMs that are left. */
+int lt_stream_delay(unsigned nanoseconds, void* stream);
 
 /* ---- K3: numerator on the T x (U+1) label lattice (lattices.py:250-377) ----
  * gather: weight_step_scan + gather_weight (lattices.py:300-342, :830-845)

@@ -23,6 +23,7 @@ FRAME_DEPENDENT = -1
 FLAG_FORCE_GENERIC = 1
 FLAG_CLUSTER_SHIFT = 8
 FLAG_GRAD_SPLIT = 16
+FLAG_LEVEL_WEIGHTS = 32
 
 _c_int = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -56,6 +57,7 @@ SIGNATURES = {
     'lt_walk_states': [_c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr],
     'lt_walk_states_checked': [_c_int, _c_int, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr,
                                _ptr],
+    'lt_stream_delay': [_c_uint, _ptr],
     'lt_string_gather': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr],
     'lt_string_scatter_add': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,

@@ -178,6 +178,13 @@ int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size, int 
   p.backptr = semiring == LT_MAXTROPICAL ? backptr : nullptr;
   p.termptr = (semiring == LT_MAXTROPICAL && max_expansions >= 1) ? termptr : nullptr;
   p.alpha_norm = alpha_norm;
+  p.wlevels = 1;
+  if (flags & LT_FLAG_LEVEL_WEIGHTS) {
+    LT_CHECK_ARG(max_expansions >= 1,
+                 "lt_lattice_forward: LT_FLAG_LEVEL_WEIGHTS needs FrameLabelDependent");
+    p.wlevels = max_expansions + 1;
+    flags |= LT_FLAG_FORCE_GENERIC;
+  }
   const bool fast2 = T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical);
   if (alpha_norm && (T == 0 || !lattice_norm_family(semiring, g, max_expansions, flags, lexical))) {
     set_error("lt_lattice_forward_norm: this lattice has no renormalised kernel "
@@ -227,6 +234,13 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
   p.alphas = alphas; p.levels = levels; p.dist = dist; p.grad_dist = grad_dist;
   p.grad_blank = grad_blank; p.grad_lexical = grad_lexical; p.beta_final = beta_final;
   p.alpha_norm = alpha_norm;
+  p.wlevels = 1;
+  if (flags & LT_FLAG_LEVEL_WEIGHTS) {
+    LT_CHECK_ARG(max_expansions >= 1,
+                 "lt_lattice_backward: LT_FLAG_LEVEL_WEIGHTS needs FrameLabelDependent");
+    p.wlevels = max_expansions + 1;
+    flags |= LT_FLAG_FORCE_GENERIC;
+  }
   const bool fast2 = lattice_fast2_supported(g, max_expansions, flags, lexical) &&
                      reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0;
   if (alpha_norm) {
@@ -308,6 +322,10 @@ int lt_walk_states_checked(int vocab_size, int context_size, const int32_t* labe
   LT_CHECK_ARG(states && next_labels && (U == 0 || labels), "lt_walk_states: NULL pointer");
   return walk_states_launch(g, labels, num_labels, B, U, states, next_labels, bad_labels,
                             (cudaStream_t)stream);
+}
+
+int lt_stream_delay(unsigned nanoseconds, void* stream) {
+  return stream_delay_launch(nanoseconds, (cudaStream_t)stream);
 }
 
 int lt_string_gather(int vocab_size, int num_states, const float* blank, const float* lexical,

@@ -178,14 +178,19 @@ lattice_backward_generic(const BwdParams p) {
   const int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
   const float logz_res = norm ? __int_as_float(an[p.T + 1]) : logz_plain;
 
+  const int LW = p.wlevels > 1 ? p.wlevels : 1;             // weight / gradient sets per frame
+  const size_t lvb = LW > 1 ? (size_t)C : 0;
+  const size_t lvl = LW > 1 ? (size_t)C * V : 0;
   // padding frames: zero gradients (lattices.py:775-779)
   for (int t = nf; t < p.T; ++t) {
-    float* gb = p.grad_blank + (bt0 + t) * C;
-    float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
-    for (int d = tid; d < D; d += nth) gb[p_lo + d] = 0.f;
-    const size_t n = (size_t)D * V;
-    float* base = gl + (size_t)p_lo * V;
-    for (size_t i = tid; i < n; i += nth) base[i] = 0.f;
+    for (int lv = 0; lv < LW; ++lv) {
+      float* gb = p.grad_blank + ((bt0 + t) * LW + lv) * C;
+      float* gl = p.grad_lexical + ((bt0 + t) * LW + lv) * (size_t)C * V;
+      for (int d = tid; d < D; d += nth) gb[p_lo + d] = 0.f;
+      const size_t n = (size_t)D * V;
+      float* base = gl + (size_t)p_lo * V;
+      for (size_t i = tid; i < n; i += nth) base[i] = 0.f;
+    }
   }
 
   float* beta = buf0;      // beta_{t+1}
@@ -198,11 +203,11 @@ lattice_backward_generic(const BwdParams p) {
   for (int t = nf - 1; t >= 0; --t) {
     const float shift = norm ? (float)(an[t + 1] - an[t]) : 0.f;
     const float logz = logz_res + shift;
-    const float* blank = p.blank + (bt0 + t) * C;
-    const float* lex = p.lexical + (bt0 + t) * (size_t)C * V;
+    const float* blank = p.blank + (bt0 + t) * C * LW;
+    const float* lex = p.lexical + (bt0 + t) * (size_t)C * V * LW;
     const float* alpha = p.alphas + (bt0 + t) * C;
-    float* gb = p.grad_blank + (bt0 + t) * C;
-    float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V;
+    float* gb = p.grad_blank + (bt0 + t) * C * LW;
+    float* gl = p.grad_lexical + (bt0 + t) * (size_t)C * V * LW;
     if constexpr (!FLD) {
       rows_backward<SR, LPR>(g, lex, gl, beta, alpha, logz, gscale, scale_ok, p_lo, p_hi, false, row_out);
       __syncthreads();
@@ -227,41 +232,46 @@ lattice_backward_generic(const BwdParams p) {
       const float* lev = p.levels + (bt0 + t) * (size_t)k * C;   // last_1..last_k
       // nb_k = blank (x) beta'  (alignments.py:405), computed redundantly by every CTA
       float* nb = nxt;
-      for (int c = tid; c < C; c += nth) nb[c] = S::times(blank[c], beta[c]);
+      for (int c = tid; c < C; c += nth) nb[c] = S::times(blank[k * lvb + c], beta[c]);
       // blank marginals (alignments.py:398-403)
       for (int d = tid; d < D; d += nth) {
         const int q = p_lo + d;
         float acc = 0.f;
         if constexpr (SR == LT_LOG) {
           if (scale_ok) {
-            const double base = (double)blank[q] + (double)beta[q] - (double)logz;
-            acc = fast_exp((float)((double)alpha[q] + base));
-            for (int i = 0; i < k; ++i)
-              acc += fast_exp((float)((double)lev[(size_t)i * C + q] + base));
-            acc *= gscale;
+            // level i: exp(lexical_alphas[i] + blank[i] + beta' - logZ)  (alignments.py:398-403)
+            for (int i = 0; i <= k; ++i) {
+              const double src = i == 0 ? (double)alpha[q] : (double)lev[(size_t)(i - 1) * C + q];
+              const float e = gscale * fast_exp((float)(
+                  src + (double)blank[i * lvb + q] + (double)beta[q] - (double)logz));
+              if (LW > 1) gb[i * lvb + q] = e; else acc += e;
+            }
+          } else if (LW > 1) {
+            for (int i = 0; i <= k; ++i) gb[i * lvb + q] = 0.f;
           }
         } else {
-          acc = alpha[q];
-          for (int i = 0; i < k; ++i) acc += lev[(size_t)i * C + q];
-          acc *= gscale * beta[q];
+          for (int i = 0; i <= k; ++i) {
+            const float e = gscale * beta[q] * (i == 0 ? alpha[q] : lev[(size_t)(i - 1) * C + q]);
+            if (LW > 1) gb[i * lvb + q] = e; else acc += e;
+          }
         }
-        gb[q] = acc;
+        if (LW == 1) gb[q] = acc;
       }
       __syncthreads();
       float* out = spare;
       for (int j = k - 1; j >= 0; --j) {
         const float* src_alpha = (j == 0) ? alpha : lev + (size_t)(j - 1) * C;
-        rows_backward<SR, LPR>(g, lex, gl, nb, src_alpha, logz, gscale, scale_ok, p_lo, p_hi,
-                               j != k - 1, row_out);
+        rows_backward<SR, LPR>(g, lex + j * lvl, gl + j * lvl, nb, src_alpha, logz, gscale,
+                               scale_ok, p_lo, p_hi, LW == 1 && j != k - 1, row_out);
         __syncthreads();
         for (int d = tid; d < D; d += nth) {
           const int q = p_lo + d;
           float v;                                 // alignments.py:414-415
           if constexpr (SR == LT_LOG)              // nb_0 is beta_t: move it to the frame of off_t
-            v = logaddexp_shifted_d((double)blank[q] + (double)beta[q], row_out[d],
+            v = logaddexp_shifted_d((double)blank[j * lvb + q] + (double)beta[q], row_out[d],
                                     j == 0 ? shift : 0.f);
           else
-            v = blank[q] * beta[q] + (float)row_out[d];
+            v = blank[j * lvb + q] * beta[q] + (float)row_out[d];
           bcast_store_b(out, q, v, nrank);
         }
         cluster_sync_all();

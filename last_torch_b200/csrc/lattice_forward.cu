@@ -172,9 +172,12 @@ lattice_forward_generic(const FwdParams p) {
   int off = 0;
   float shift = 0.f;
 
+  const int LW = p.wlevels > 1 ? p.wlevels : 1;             // weight sets per frame
+  const size_t lvb = LW > 1 ? (size_t)C : 0;                  // stride between the sets
+  const size_t lvl = LW > 1 ? (size_t)C * g.V : 0;
   for (int t = 0; t < nf; ++t) {
-    const float* blank = p.blank + (bt0 + t) * C;
-    const float* lex = p.lexical + (bt0 + t) * (size_t)C * g.V;
+    const float* blank = p.blank + (bt0 + t) * C * LW;        // level 0
+    const float* lex = p.lexical + (bt0 + t) * (size_t)C * g.V * LW;
     if (p.alphas) {
       float* out = p.alphas + (bt0 + t) * C;
       for (int d = tid; d < D; d += nth) out[q_lo + d] = cur[q_lo + d];
@@ -232,7 +235,7 @@ lattice_forward_generic(const FwdParams p) {
       const float* src = cur;
       float* lv = last0;
       for (int i = 0; i < p.k; ++i) {
-        reduce_into_slice<SR>(g, lex, src, q_lo, q_hi, pm, ps, p.ppad);
+        reduce_into_slice<SR>(g, lex + i * lvl, src, q_lo, q_hi, pm, ps, p.ppad);
         const bool need_bcast = (i + 1 < p.k);
         for (int d = tid; d < D; d += nth) {
           const int q = q_lo + d;
@@ -242,7 +245,7 @@ lattice_forward_generic(const FwdParams p) {
           if constexpr (SR == LT_MAXTROPICAL) {
             if (p.backptr) p.backptr[((bt0 + t) * p.k + i) * C + q] = (int16_t)__float_as_int(ps[d]);
           }
-          const float term = S::times(r, blank[q]);
+          const float term = S::times(r, blank[(i + 1) * lvb + q]);
           if constexpr (SR == LT_LOG) {
             Acc<LT_LOG> acc; acc.m = am[d]; acc.s = as[d];
             // am holds the running max, as the running sum relative to msafe(am)

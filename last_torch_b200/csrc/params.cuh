@@ -24,6 +24,7 @@ struct FwdParams {
   int16_t* backptr;
   uint8_t* termptr;
   int32_t* alpha_norm;   // renormalised recursion state (lt_lattice_forward_norm) or nullptr
+  int wlevels;           // LT_FLAG_LEVEL_WEIGHTS: k + 1 sets of weights per frame, else 1
 };
 
 struct BwdParams {
@@ -43,6 +44,7 @@ struct BwdParams {
   float* grad_lexical;
   float* beta_final;
   const int32_t* alpha_norm;
+  int wlevels;           // LT_FLAG_LEVEL_WEIGHTS: weights AND gradients are [.., k + 1, C(, V)]
 };
 
 struct StrParams {
@@ -124,6 +126,7 @@ int string_scatter_launch(int V, int C, const float* gbw, const float* glw,
 int walk_states_launch(const NGram& g, const int32_t* labels, const int32_t* num_labels, int B,
                        int U, int32_t* states, int32_t* next_labels, int32_t* bad,
                        cudaStream_t stream);
+int stream_delay_launch(unsigned ns, cudaStream_t stream);
 int string_forward_launch(int semiring, const StrParams& p, cudaStream_t stream);
 int string_backward_launch(int semiring, const StrParams& p, cudaStream_t stream);
 int alphas_denormalize_launch(float* alphas, const int32_t* alpha_norm, int B, int T, int C,

@@ -147,6 +147,25 @@ int walk_states_launch(const NGram& g, const int32_t* labels, const int32_t* num
   return LT_OK;
 }
 
+// One thread that sleeps: put at the head of a side stream so that the kernels behind it start
+// a few tens of microseconds after a kernel on another stream that became launchable at the same
+// moment (see lt_stream_delay in include/last_lattice.h).
+__global__ void stream_delay_kernel(unsigned ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
+int stream_delay_launch(unsigned ns, cudaStream_t stream) {
+  if (ns == 0) return LT_OK;
+  stream_delay_kernel<<<1, 1, 0, stream>>>(ns > 1000000u ? 1000000u : ns);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+
 // ------------------------------------------------------------------ forward --
 
 // last_i[u] = alpha[u-i] (x) lex[u-i] (x) ... (x) lex[u-1], associated in the

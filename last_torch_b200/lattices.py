@@ -337,11 +337,23 @@ class RecognitionLattice(nn.Module, Generic[T]):
     blank, lexical = self._arc_weights(cache, frames, batch_dims)
     c = blank.shape[-1]
     t = blank.shape[1]
+    if (blank_mask is not None or lexical_mask is not None) and num_align != 1:
+      # lattices.py:447-453: one set of weights per alignment state, blank[i] + blank_mask[i] /
+      # lexical[i] + lexical_mask[i]; the generic kernels take them as [B,T,k+1,C(,V)]
+      if self._is_table():
+        raise NotImplementedError('per-alignment-state masks need a contexts.FullNGram context')
+      full_b, full_l = (*batch_dims, t, c), (*batch_dims, t, c, v)
+      bl = [blank if blank_mask is None else
+            blank + torch.broadcast_to(blank_mask[i], full_b).reshape(-1, t, c)
+            for i in range(num_align)]
+      lx = [lexical if lexical_mask is None else
+            lexical + torch.broadcast_to(lexical_mask[i], full_l).reshape(-1, t, c, v)
+            for i in range(num_align)]
+      dist, alphas = ops.LatticeForwardLevels.apply(
+          torch.stack(bl, dim=2).contiguous(), torch.stack(lx, dim=2).contiguous(),
+          ops._as_i32(num_frames.reshape(-1), blank.device), sr, v, n, k, self.kernel_flags)
+      return dist.reshape(batch_dims), alphas.reshape(*batch_dims, t, c)
     if blank_mask is not None or lexical_mask is not None:
-      if num_align != 1:
-        raise NotImplementedError(
-            'per-alignment-state masks are only supported for FrameDependent: the kernels '
-            'use alignment-state-invariant weights (lattices.py:447-449)')
       if blank_mask is not None:
         blank = blank + torch.broadcast_to(blank_mask[0], (*batch_dims, t, c)).reshape(-1, t, c)
       if lexical_mask is not None:

@@ -207,6 +207,98 @@ class LatticeForward(torch.autograd.Function):
     return gb, gl, None, None, None, None, None, None
 
 
+class LatticeForwardLevels(torch.autograd.Function):
+  """LatticeForward for FrameLabelDependent(k) with ONE SET OF WEIGHTS PER ALIGNMENT STATE
+  (lattices.py:447-453: per-state masks added to the weights): blank [B,T,k+1,C], lexical
+  [B,T,k+1,C,V] (LT_FLAG_LEVEL_WEIGHTS).  Gradients have the same layout: Log / Real from the
+  beta recursion, MaxTropical from the back-trace (one arc per taken expansion plus the closing
+  blank arc of every frame)."""
+
+  @staticmethod
+  def forward(ctx, blank, lexical, num_frames, sr, V, n, k, flags):
+    blank = N.require_cuda(blank, 'blank')
+    lexical = N.require_cuda(lexical, 'lexical')
+    B, T, L, C = blank.shape
+    if L != k + 1 or tuple(lexical.shape) != (B, T, L, C, V):
+      raise ValueError(f'per-state weights must be [B,T,{k + 1},C] / [B,T,{k + 1},C,V]; got '
+                       f'{tuple(blank.shape)} and {tuple(lexical.shape)}')
+    dev = blank.device
+    flags = flags | N.FLAG_LEVEL_WEIGHTS
+    dist = torch.empty([B], dtype=torch.float32, device=dev)
+    alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev)
+    alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)
+    need_grad = any(ctx.needs_input_grad[:2])
+    levels = torch.empty([B, T, k, C], dtype=torch.float32, device=dev) if need_grad else None
+    backptr = termptr = None
+    if sr == N.MAXTROPICAL:
+      backptr = torch.empty([B, T, k, C], dtype=torch.int16, device=dev)
+      termptr = torch.empty([B, T, C], dtype=torch.uint8, device=dev)
+    alpha_norm = None
+    if (USE_NORM and T > 0 and B > 0 and
+        N.lib().lt_lattice_norm_supported(sr, V, n, k, flags | N.FLAG_FORCE_GENERIC)):
+      alpha_norm = torch.empty([B, T + 3], dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_lattice_forward_norm(
+          sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, None,
+          N.ptr(dist), N.ptr(alphas), N.ptr(alpha_final), N.ptr(levels), N.ptr(backptr),
+          N.ptr(termptr), N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_forward')
+    ctx.geom = (sr, V, n, k, flags)
+    ctx.save_for_backward(blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr,
+                          termptr, alpha_norm)
+    out_alphas = _denormalized(alphas, alpha_norm)
+    ctx.mark_non_differentiable(out_alphas)
+    return dist, out_alphas
+
+  @staticmethod
+  def backward(ctx, g_dist, _g_alphas):
+    sr, V, n, k, flags = ctx.geom
+    (blank, lexical, num_frames, dist, alphas, alpha_final, levels, backptr, termptr,
+     alpha_norm) = ctx.saved_tensors
+    B, T, L, C = blank.shape
+    dev = blank.device
+    g_dist = N.require_cuda(g_dist, 'grad_dist').contiguous()
+    with torch.cuda.device(dev):
+      if sr != N.MAXTROPICAL:
+        gb = torch.empty_like(blank)
+        gl = torch.empty_like(lexical)
+        N.check(N.lib().lt_lattice_backward_norm(
+            sr, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+            N.ptr(levels), N.ptr(dist), N.ptr(g_dist), N.ptr(gb), N.ptr(gl), None,
+            N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_backward')
+        return gb, gl, None, None, None, None, None, None
+      labels = torch.empty([B, T, k + 1], dtype=torch.int32, device=dev)
+      states = torch.empty([B, T + 1], dtype=torch.int32, device=dev)
+      N.check(N.lib().lt_viterbi_backtrace(
+          V, n, k, N.ptr(backptr), N.ptr(termptr), N.ptr(alpha_final), N.ptr(num_frames), B, T,
+          N.ptr(labels), N.ptr(states), None, None, None, N.stream_ptr(dev)),
+          'lt_viterbi_backtrace')
+    # one-hot gradients per alignment state from the path (index arithmetic on [B,T,k+1] ints):
+    # expansion i of frame t leaves context state s_i with label y_i > 0; the frame closes with
+    # the blank arc of state e = number of expansions taken.
+    from . import contexts as _contexts
+    context = _contexts.FullNGram(vocab_size=V, context_size=n)
+    gb = torch.zeros_like(blank)
+    gl = torch.zeros_like(lexical)
+    real = torch.arange(T, device=dev)[None, :] < num_frames[:, None]
+    bi = torch.arange(B, device=dev)[:, None].expand(B, T)
+    ti = torch.arange(T, device=dev)[None, :].expand(B, T)
+    g = g_dist[:, None].expand(B, T)
+    s = states[:, :T].long()
+    alive = real
+    for i in range(k + 1):
+      y = labels[:, :, i].long() if i < k else torch.zeros_like(s)
+      take = alive & (y > 0)
+      close = alive & ~take                     # the blank arc of alignment state i
+      gb.index_put_((bi[close], ti[close], torch.full_like(s[close], i), s[close]), g[close],
+                    accumulate=True)
+      if i < k:
+        gl.index_put_((bi[take], ti[take], torch.full_like(s[take], i), s[take], y[take] - 1),
+                      g[take], accumulate=True)
+        s = torch.where(take, context.next_state(s, y), s)
+      alive = take
+    return gb, gl, None, None, None, None, None, None
+
+
 def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
   """MaxTropical forward + back-trace; returns (labels [B,T,k+1] int32 with true
   1-based labels, path_states [B,T+1], path_weights [B])."""
@@ -389,8 +481,12 @@ def _side_stream(device):
   return _SIDE_STREAMS[key]
 
 
+# Head start (ns) K1 gets over the numerator kernels on the side stream (lt_stream_delay)
+NUMERATOR_STAGGER_NS = int(os.environ.get('LT_NUMERATOR_STAGGER_NS', '40000'))
+
+
 def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels,
-                        need_grad, side=None, ready=None):
+                        need_grad, side=None, ready=None, stagger_ns=0):
   """gather + string forward.  With `side` (a torch.cuda.Stream) the two kernels
   are enqueued there, after the event `ready` (or, without one, after everything
   already on the current stream); the caller joins with
@@ -421,6 +517,8 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
         side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):           # stream(None) is a no-op
       L = N.lib()
+      if side is not None and stagger_ns:
+        N.check(L.lt_stream_delay(stagger_ns, N.stream_ptr(dev)), 'lt_stream_delay')
       N.check(L.lt_string_gather(V, C, N.ptr(blank), N.ptr(lexical), N.ptr(states),
                                  N.ptr(next_labels), B, T, U1, N.ptr(bw), N.ptr(lw),
                                  N.stream_ptr(dev)), 'lt_string_gather')
@@ -565,7 +663,7 @@ def _loss_forward(blank, lexical, num_frames, states, next_labels, num_labels, V
   log_z, alphas, _, levels, _, _, alpha_norm = fwd
   strf = _string_forward_raw(
       N.LOG, k, V, C, blank, lexical, num_frames, states, next_labels, num_labels, need_grad,
-      side=side, ready=ready)
+      side=side, ready=ready, stagger_ns=NUMERATOR_STAGGER_NS)
   num, bw, lw, s_alphas, _, ext = strf
   gbw = glw = None
   if need_grad:

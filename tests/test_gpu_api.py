@@ -785,3 +785,77 @@ def test_table_weight_fn_string_frames_matches_dense_gather():
                                          labels=labels, num_labels=T([4, 2, 1]),
                                          semiring=getattr(lt.semirings, name)))
     npt.assert_allclose(res[0].cpu(), res[1].cpu(), rtol=1e-6, err_msg=name)
+
+
+@pytest.mark.parametrize('ctx,vocab,k', [(1, 4, 2), (2, 3, 3)])
+@pytest.mark.parametrize('name', ['Log', 'MaxTropical', 'Real'])
+def test_frame_label_dependent_per_state_masks(name, ctx, vocab, k):
+  """lattices.py:447-453: blank_mask / lexical_mask hold ONE mask per alignment state of
+  FrameLabelDependent and are added to that state's weights.  (1) zero masks: same distance, and
+  the mask gradients summed over the states equal the gradient w.r.t. the shared weights;
+  (2) non-zero masks: distance and mask gradients against the per-frame host recursion
+  (alignment.forward, alignments.py:362-376, driven frame by frame like lattices.py:856-892)."""
+  lt = _lt()
+  torch.manual_seed(7 + ctx)
+  semiring = getattr(lt.semirings, name)
+  context = lt.contexts.FullNGram(vocab_size=vocab, context_size=ctx)
+  c = context.num_states()
+  b, t, n_align = 3, 6, k + 1
+  raw = torch.randn([b, t, c, 1 + vocab], device='cuda')
+  table = (torch.exp(raw * 0.25) / (1 + vocab) if name == 'Real' else raw).requires_grad_()
+  alignment = lt.alignments.FrameLabelDependent(max_expansions=k)
+  lattice = lt.RecognitionLattice(
+      context=context, alignment=alignment,
+      weight_fn_factory=lambda _: lt.weight_fns.TableWeightFn(table),
+      weight_fn_cacher_factory=lambda _: lt.weight_fns.NullCacher())
+  frames = torch.arange(t, device='cuda', dtype=torch.float32)[None, :, None].expand(b, t, 1)
+  nf = T([6, 4, 0])
+  w = torch.tensor([1.0, -0.5, 2.0], device='cuda')
+
+  def masks(scale):
+    g = torch.Generator(device='cuda').manual_seed(3)
+    bm = [(scale * torch.randn([b, t, c], device='cuda', generator=g)).requires_grad_()
+          for _ in range(n_align)]
+    lm = [(scale * torch.randn([b, t, 1, vocab], device='cuda', generator=g)).requires_grad_()
+          for _ in range(n_align)]                     # broadcast over context states
+    return bm, lm
+
+  # (1) zero masks
+  bm, lm = masks(0.0)
+  dist, _ = lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=semiring,
+                             blank_mask=bm, lexical_mask=lm)
+  plain, _ = lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=semiring)
+  npt.assert_allclose(dist.detach().cpu(), plain.detach().cpu(), rtol=1e-6)
+  grads = torch.autograd.grad((dist * w).sum(), bm + lm)
+  (gt,) = torch.autograd.grad((plain * w).sum(), table)
+  tol = dict(rtol=0, atol=0) if name == 'MaxTropical' else dict(rtol=1e-4, atol=1e-6)
+  npt.assert_allclose(sum(grads[:n_align]).cpu(), gt[..., 0].cpu(), **tol)
+  npt.assert_allclose(sum(grads[n_align:]).cpu(), gt[..., 1:].sum(2, keepdim=True).cpu(), **tol)
+  assert float(grads[2 * n_align - 1].abs().max()) == 0.0    # lexical[k] is never used
+
+  # (2) non-zero masks against the per-frame host recursion
+  bm, lm = masks(0.0 if name == 'Real' else 0.7)
+  if name == 'Real':
+    bm = [(0.01 * (i + 1) * torch.ones([b, t, c], device='cuda')).requires_grad_()
+          for i in range(n_align)]
+  dist, _ = lattice._forward(cache=None, frames=frames, num_frames=nf, semiring=semiring,
+                             blank_mask=bm, lexical_mask=lm)
+  got = torch.autograd.grad((dist * w).sum(), bm + lm)
+  start = torch.zeros([b, c], device='cuda')
+  alpha = semiring.zeros([b, c]).to('cuda').clone()
+  alpha[:, 0] = semiring.ones([b]).to('cuda')
+  for i in range(t):
+    blank_i, lex_i = table[:, i, :, 0], table[:, i, :, 1:]
+    nxt = alignment.forward(alpha=alpha, blank=[blank_i + m[:, i] for m in bm],
+                            lexical=[lex_i + m[:, i] for m in lm], context=context,
+                            semiring=semiring)
+    alpha = torch.where((i >= nf)[:, None], alpha, nxt)
+  ref = semiring.sum(alpha, dim=-1)
+  npt.assert_allclose(dist.detach().cpu(), ref.detach().cpu(), rtol=2e-5, atol=1e-6)
+  want = torch.autograd.grad((ref * w).sum(), bm + lm, allow_unused=True)
+  for a, r in zip(got, want):
+    r = torch.zeros_like(a) if r is None else r
+    if name == 'MaxTropical':
+      npt.assert_array_equal(a.cpu(), r.cpu())
+    else:
+      npt.assert_allclose(a.cpu(), r.cpu(), rtol=2e-4, atol=2e-6)
