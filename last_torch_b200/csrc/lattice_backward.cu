@@ -257,6 +257,10 @@ lattice_backward_generic(const BwdParams p) {
         }
         if (LW == 1) gb[q] = acc;
       }
+      if (LW > 1) {       // lexical[k] is never used (alignments.py:417): its gradient is zero
+        float* base = gl + k * lvl + (size_t)p_lo * V;
+        for (size_t i = tid; i < (size_t)D * V; i += nth) base[i] = 0.f;
+      }
       __syncthreads();
       float* out = spare;
       for (int j = k - 1; j >= 0; --j) {
