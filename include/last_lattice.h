@@ -66,9 +66,8 @@ unsigned long long lt_launch_count(void);
  * of the same name and can be changed at run time: LT_JOINT_SIMT, LT_JOINT_DGRAD_V1,
  * LT_JOINT_WGRAD_SIMT (CUDA-core / first-generation joint kernels), LT_JOINT_DGRAD_PAIR,
  * LT_JOINT_DGRAD_MULTICAST (measured-slower variants of the split-row dgrad), LT_TABLE_V1,
- * LT_TABLE_CLUSTER (NextStateTable kernel selection), LT_COLS_NO_RESIDENT (context_size >= 2
- * FrameLabelDependent forward: stream the frame once per level instead of keeping it resident in
- * a cluster of 16).  lt_get_option returns -1 for an unknown name. */
+ * LT_TABLE_CLUSTER (NextStateTable kernel selection).  lt_get_option returns -1 for an unknown
+ * name. */
 int lt_set_option(const char* name, int value);
 int lt_get_option(const char* name);
 /* Number of SMs, compute capability of the current device. */

@@ -38,7 +38,6 @@ enum Option {
   OPT_JOINT_DGRAD_MULTICAST,  // LT_JOINT_DGRAD_MULTICAST: TMA-multicast split-row dgrad
   OPT_TABLE_V1,               // LT_TABLE_V1: one-CTA NextStateTable kernels
   OPT_TABLE_CLUSTER,          // LT_TABLE_CLUSTER: force the NextStateTable cluster size
-  OPT_COLS_NO_RESIDENT,       // LT_COLS_NO_RESIDENT: k-fold streaming instead of resident frames
   OPT_COUNT
 };
 int option(Option o);

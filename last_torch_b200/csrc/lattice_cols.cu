@@ -19,13 +19,7 @@
 //     replica per CTA in two buffers that alternate per level; new values are all-gathered
 //     with st.async + mbarrier complete_tx (no cluster barrier in the loop);
 //   * two CTAs per SM (<= 113 KB of shared memory, 288 threads each), so the exchange
-//     latency of one utterance hides behind the arithmetic of another;
-//   * RES (FrameLabelDependent(k >= 2) on big contexts, e.g. configs[2]): a NON-PORTABLE cluster
-//     of 16 CTAs per utterance, one CTA per SM, each holding its WHOLE slice of a frame
-//     ([K rows x N/16 columns] = 66.5 KB at vocab 64, context_size 2) resident in shared memory
-//     for all k levels, double-buffered against the TMA load of the next frame: the frame
-//     crosses L2 -> SM once instead of k times (the k-fold re-streaming ran into the ~7 TB/s
-//     L2 -> SM wall at 0.5 of the HBM roofline).
+//     latency of one utterance hides behind the arithmetic of another.
 // The A = sum_{i<n} V^i low-order states have at most one incoming arc each and are
 // handled by spare lanes of rank 0.
 //
@@ -168,10 +162,9 @@ __device__ __forceinline__ float finish_dest(const ColsParams& p, size_t bt, int
   }
 }
 
-template <int SR, int CPT, bool FLD, bool RES>
-__global__ void __launch_bounds__(kColsThreads, RES ? 1 : 2)
+template <int SR, int CPT, bool FLD>
+__global__ void __launch_bounds__(kColsThreads, 2)
 lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams p) {
-  static_assert(!RES || FLD, "the resident-frame variant exists for FrameLabelDependent only");
   using S = Sr<SR>;
   extern __shared__ __align__(128) unsigned char csmem[];
   const NGram& g = p.g;
@@ -184,11 +177,9 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   const int LOW0 = K * kSrcStride;        // first low-order slot
   const uint32_t stage_bytes = (uint32_t)R * NCOL * 4;
   const int nlev = FLD ? p.k : 1;
-  // RES: a ring "stage" is a whole frame slice = nchunks row chunks of stage_bytes
-  const uint32_t ring_bytes = RES ? stage_bytes * (uint32_t)nchunks : stage_bytes;
 
   float* tiles = reinterpret_cast<float*>(csmem);
-  float* buf = reinterpret_cast<float*>(csmem + (size_t)NS * ring_bytes);    // [2][SB]
+  float* buf = reinterpret_cast<float*>(csmem + (size_t)NS * stage_bytes);    // [2][SB]
   float* dpart = buf + 2 * SB;                                                // [2 * 8] dist partials
   uint64_t* full = reinterpret_cast<uint64_t*>(dpart + 16);
   uint64_t* empty = full + NS;
@@ -238,23 +229,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
 
   if (warp == kConsumers / 32) {
     // ------------------------------------------------------------ producer warp
-    if (RES && lane == 0) {
-      // one whole frame slice per ring stage, loaded ONCE per frame (all k levels read it)
-      const int nbox = NCOL / kBoxCols;
-      const uint64_t drop = l2_policy_evict_first();
-      for (int t = 0; t < nf; ++t) {
-        const int fs = t % NS;
-        if (t >= NS) mbar_wait(smem_u32(&empty[fs]), (uint32_t)((t / NS - 1) & 1));
-        const uint32_t bar = smem_u32(&full[fs]);
-        mbar_arrive_expect_tx(bar, ring_bytes);
-        for (int c = 0; c < nchunks; ++c)
-          for (int bx = 0; bx < nbox; ++bx)
-            tma_load_3d_hint(smem_u32(tiles) + fs * ring_bytes + c * stage_bytes +
-                                 bx * (R * kBoxCols * 4),
-                             &tmap, (int)rank * NCOL + bx * kBoxCols, c * R, (int)(bt0 + t), bar,
-                             drop);
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       const long long total = total_levels * nchunks;
       const int nbox = NCOL / kBoxCols;
       // FrameLabelDependent streams a frame once per level: keep it in L2 until the last one
@@ -356,14 +331,9 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
 #pragma unroll
       for (int c = 0; c < CPT; ++c) acc[c].init();
       const float* srow = src + li;
-      if constexpr (RES) {
-        if (level == 0) mbar_wait(smem_u32(&full[t % NS]), (uint32_t)((t / NS) & 1));
-      }
       for (int ch = 0; ch < nchunks; ++ch) {
-        if constexpr (!RES) mbar_wait(smem_u32(&full[stage]), use & 1);
-        const float* tile = RES
-            ? tiles + (size_t)(t % NS) * (ring_bytes / 4) + (size_t)ch * (stage_bytes / 4) + box_off
-            : tiles + (size_t)stage * (stage_bytes / 4) + box_off;
+        mbar_wait(smem_u32(&full[stage]), use & 1);
+        const float* tile = tiles + (size_t)stage * (stage_bytes / 4) + box_off;
         const int kk0 = ch * R;
         const int rows = min(R, K - kk0);
         const float* sp = srow + kk0 * kSrcStride;
@@ -418,17 +388,9 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
             for (int c = 0; c < CPT; ++c) acc[c].add(Dom<SR>::times(sv, w[c]), kk0 + r);
           }
         }
-        if constexpr (!RES) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));
-          if (++stage == NS) { stage = 0; ++use; }
-        }
-      }
-      if constexpr (RES) {
-        if (level + 1 == nlev) {             // last level: the frame slice may be overwritten
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&empty[t % NS]));
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));
+        if (++stage == NS) { stage = 0; ++use; }
       }
 
       // ---- epilogue: every new value goes to the one CTA that reads it as a source
@@ -543,8 +505,6 @@ template <typename KernelT>
 static int launch_cols(KernelT kernel, int grid, size_t smem, int cluster, cudaStream_t stream,
                        const CUtensorMap& tmap, const ColsParams& p) {
   LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cluster > 8)
-    LT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kColsThreads);
@@ -584,26 +544,6 @@ static bool cols_geometry(const NGram& g, int* cl, int* cpt) {
   return false;
 }
 
-// Resident-frame variant (FrameLabelDependent(k >= 2)): a non-portable cluster of 16, one CTA per
-// SM, two whole frame slices in shared memory.  R / nchunks: row chunks of one slice.
-static bool cols_geometry_res(const NGram& g, int k, int* cpt, int* R, int* nchunks, size_t* smem) {
-  if (k < 2 || g.n < 2 || g.V % 4 != 0) return false;
-  if (g.A > kLowPerThread * kConsumers) return false;
-  const int cl = 16;
-  if (g.N % cl != 0) return false;
-  const int ncol = g.N / cl;
-  if (ncol % kBoxCols != 0 || ncol % g.V != 0 || ncol / g.V > kSrcStride) return false;
-  const int per = ncol / kConsumers;
-  if (per != 1 && per != 2) return false;
-  const int nch = (g.K + kMaxR - 1) / kMaxR;
-  const int rows = (g.K + nch - 1) / nch;
-  const size_t frame = (size_t)nch * rows * ncol * 4;
-  const size_t total = 2 * frame + cols_fixed_bytes(g, ncol);
-  if (total > 227 * 1024) return false;
-  *cpt = per; *R = rows; *nchunks = nch; *smem = total;
-  return true;
-}
-
 }  // namespace
 
 bool lattice_cols_supported(const NGram& g, int k, unsigned flags, const void* lexical) {
@@ -623,30 +563,21 @@ int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdPa
   if (!cols_geometry(g, &cl, &cpt)) { set_error("cols path: unsupported geometry"); return LT_ERR_UNSUPPORTED; }
   EncodeTiledFn encode = get_encode_fn3();
   if (!encode) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return LT_ERR_CUDA; }
-  int R = 0, nchunks = 0, stages = 0;
-  size_t smem = 0;
-  bool res = !option(OPT_COLS_NO_RESIDENT) && cols_geometry_res(g, k, &cpt, &R, &nchunks, &smem);
-  if (res) {
-    cl = 16;
-    stages = 2;
-  } else {
-    const int ncol = g.N / cl;
-    const size_t budget = 112 * 1024;
-    const size_t fixed = cols_fixed_bytes(g, ncol);
-    // rows per stage: as few chunks as possible with stages of <= 32 KB and >= 2 stages
-    int rmax = (int)(32 * 1024 / ((size_t)ncol * 4));
-    if (rmax > kMaxR) rmax = kMaxR;
-    while (rmax > 1 && fixed + 2 * (size_t)rmax * ncol * 4 > budget) --rmax;
-    if (rmax < 1) { set_error("cols path: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-    nchunks = (g.K + rmax - 1) / rmax;
-    R = (g.K + nchunks - 1) / nchunks;
-    const size_t stage = (size_t)R * ncol * 4;
-    stages = (int)((budget - fixed) / stage);
-    if (stages > 8) stages = 8;
-    if (stages < 2) { set_error("cols path: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
-    smem = stage * stages + fixed;
-  }
   const int ncol = g.N / cl;
+  const size_t budget = 112 * 1024;
+  const size_t fixed = cols_fixed_bytes(g, ncol);
+  // rows per stage: as few chunks as possible with stages of <= 32 KB and >= 2 stages
+  int rmax = (int)(32 * 1024 / ((size_t)ncol * 4));
+  if (rmax > kMaxR) rmax = kMaxR;
+  while (rmax > 1 && fixed + 2 * (size_t)rmax * ncol * 4 > budget) --rmax;
+  if (rmax < 1) { set_error("cols path: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
+  const int nchunks = (g.K + rmax - 1) / rmax;
+  const int R = (g.K + nchunks - 1) / nchunks;
+  const size_t stage = (size_t)R * ncol * 4;
+  int stages = (int)((budget - fixed) / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("cols path: not enough shared memory"); return LT_ERR_UNSUPPORTED; }
+  const size_t smem = stage * stages + fixed;
 
   CUtensorMap tmap;
   cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)g.K, (cuuint64_t)base.B * base.T};
@@ -670,10 +601,8 @@ int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdPa
   const int grid = base.B * cl;
   const bool fld = k >= 1;
 #define LT_COLS3(SR, CPTV)                                                                        \
-  if (res)                                                                                        \
-    return launch_cols(lattice_forward_cols<SR, CPTV, true, true>, grid, smem, cl, stream, tmap, p); \
-  return fld ? launch_cols(lattice_forward_cols<SR, CPTV, true, false>, grid, smem, cl, stream, tmap, p) \
-             : launch_cols(lattice_forward_cols<SR, CPTV, false, false>, grid, smem, cl, stream, tmap, p);
+  return fld ? launch_cols(lattice_forward_cols<SR, CPTV, true>, grid, smem, cl, stream, tmap, p) \
+             : launch_cols(lattice_forward_cols<SR, CPTV, false>, grid, smem, cl, stream, tmap, p);
 #define LT_COLS2(SR)                  \
   switch (cpt) {                      \
     case 1: LT_COLS3(SR, 1)           \

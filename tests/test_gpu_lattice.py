@@ -559,44 +559,3 @@ def test_backward_split_row_emission(vocab, semiring):
   err = (rec - gl0).abs()
   assert bool((err <= gl0.abs() * 2.0 ** -16 + 1e-37).all()), float(err.max())
   assert float(rec[1, 6:].abs().max()) == 0.0 and float(rec[2].abs().max()) == 0.0
-
-
-@pytest.mark.parametrize('k', [2, 3])
-def test_resident_frame_cols_kernel_matches_streaming(k):
-  """configs[2] width (vocab 64, context_size 2, 4161 states), FrameLabelDependent(k): the
-  resident-frame kernel (non-portable cluster of 16, the frame slice stays in shared memory for
-  all k levels) against the k-fold streaming kernel (LT_COLS_NO_RESIDENT) -- MaxTropical
-  distances, alphas and back-traced paths bit for bit, Log / Real values to fp32 round-off --
-  with ragged and empty utterances and more utterances than co-resident clusters."""
-  lt = _lt()
-  from last_torch_b200 import _native as N
-  b, t, vocab, ctx = 11, 9, 64, 2
-  c = 1 + vocab + vocab * vocab
-  g = torch.Generator(device='cuda').manual_seed(k)
-  table = torch.randn([b, t, c, 1 + vocab], device='cuda', generator=g)
-  nf = cuda(np.array([9, 4, 0, 7, 9, 1, 2, 9, 5, 3, 8]))
-  frames = frames_for(b, t)
-  res = {}
-  for streaming in (0, 1):
-    with N.option('LT_COLS_NO_RESIDENT', streaming):
-      out = {}
-      for name in ['MaxTropical', 'Log', 'Real']:
-        tab = table if name != 'Real' else torch.exp(table * 0.25) / (1 + vocab)
-        lattice = make_lattice(vocab, ctx, k, tab)
-        dist, alphas = lattice._forward(cache=None, frames=frames, num_frames=nf,
-                                        semiring=getattr(lt.semirings, name))
-        out[name] = (dist.cpu().numpy(), alphas.cpu().numpy())
-      labels, _, weights = make_lattice(vocab, ctx, k, table).shortest_path(
-          frames=frames, num_frames=nf, cache=None)
-      out['path'] = (labels.cpu().numpy(), weights.cpu().numpy())
-      res[streaming] = out
-  npt.assert_array_equal(res[0]['MaxTropical'][0], res[1]['MaxTropical'][0])
-  npt.assert_array_equal(res[0]['MaxTropical'][1], res[1]['MaxTropical'][1])
-  npt.assert_array_equal(res[0]['path'][0], res[1]['path'][0])
-  npt.assert_array_equal(res[0]['path'][1], res[1]['path'][1])
-  for name in ['Log', 'Real']:
-    npt.assert_allclose(res[0][name][0], res[1][name][0], rtol=2e-6, err_msg=name)
-    fin = np.isfinite(res[1][name][1])
-    npt.assert_array_equal(np.isfinite(res[0][name][1]), fin)
-    npt.assert_allclose(res[0][name][1][fin], res[1][name][1][fin], rtol=2e-6, atol=2e-6,
-                        err_msg=name)
