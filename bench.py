@@ -625,6 +625,38 @@ def run_b200(args):
       run_extra('configs[1] Log forward only, B=32/GPU', 32, 1000, 256, 1, -1, 120, 'forward')
       run_extra('configs[1] Log forward only, B=8/GPU', 8, 1000, 256, 1, -1, 120, 'forward')
 
+    if world == 1:
+      # north_star (4): JointWeightFn fused into the recursion vs joint kernel -> HBM -> K1, at the
+      # shape where recomputing the logits is cheapest (vocab 64, hidden 128): Viterbi decoding
+      try:
+        fv, fh = 64, 128
+        torch.manual_seed(99)
+        flat = last_torch.RecognitionLattice(
+            context=last_torch.contexts.FullNGram(vocab_size=fv, context_size=1),
+            alignment=last_torch.alignments.FrameDependent(),
+            weight_fn_cacher_factory=lambda c: last_torch.weight_fns.SharedEmbCacher(
+                num_context_states=c.shape()[0], embedding_size=fh, device=str(dev)),
+            weight_fn_factory=lambda c: last_torch.weight_fns.JointWeightFn(
+                vocab_size=c.shape()[1], hidden_size=fh, device=str(dev), embedding_size=fh,
+                feature_size=fh))
+        fx = torch.randn([32, 1000, fh], device=dev, generator=gen)
+        fnf = torch.full([32], 1000, dtype=torch.int32, device=dev)
+        ent = {'config': ('north_star (4): JointWeightFn fused into the forward recursion vs joint '
+                          'kernel -> HBM -> K1; bigram vocab 64, hidden 128, B=32 T=1000, '
+                          'MaxTropical shortest_path (Viterbi decoding)'),
+               'logits_gb_unfused': 32 * 1000 * 65 * 65 * 4 / 1e9}
+        for fused in (False, True):
+          flat.fused_inference = fused
+          ms, _, kk, _ = timed(lambda: flat.shortest_path(frames=fx, num_frames=fnf), x_steps, x_warm)
+          key = 'fused' if fused else 'unfused'
+          ent[key + '_ms'] = ms
+          ent[key + '_kernels_ms'] = {k: statistics.mean(tt) for k, tt in kk.items()}
+        extras.append(ent)
+        del flat, fx
+        torch.cuda.empty_cache()
+      except Exception as e:
+        extras.append({'config': 'north_star (4) fused inference', 'error': repr(e)[:300]})
+
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu:
     val, threads, desc, _, _ = cpu_bounded_run(args, with_joint=False, seconds=args.cpu_seconds)

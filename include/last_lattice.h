@@ -398,6 +398,26 @@ int lt_joint_split_rows(const float* rows, void* out, int64_t M, int V, void* st
  * workspace may be NULL, which selects the CUDA-core kernels. */
 int64_t lt_joint_backward_workspace_bytes(int64_t N, int C, int H, int V);
 
+/* ---- north_star (4): JointWeightFn FUSED into the forward recursion ----------------------------
+ * lt_joint_forward followed by lt_lattice_forward in ONE kernel: the logits of a frame are produced
+ * on chip (fp32 FMAs on the CUDA cores), consumed by the semiring update and never written to HBM;
+ * device memory is O(B*T*C) instead of O(B*T*C*V).  Inference direction only (no gradient): Log
+ * shortest distance, and MaxTropical distance + back-pointers (lt_viterbi_backtrace with
+ * context_size 1, LT_FRAME_DEPENDENT) -- what RecognitionLattice.shortest_path needs.
+ * Bigram FullNGram, FrameDependent, vocab_size <= 64, H in {32, 64, 128}
+ * (lt_joint_lattice_fused_supported); proj_frame is [B, T, H].  Measured against the unfused pair
+ * in DESIGN.md section 6: the recompute on CUDA cores makes it SLOWER than materialising the
+ * logits with the tensor-core kernel; it is the memory-saving path and the measured answer to
+ * "does fusion pay at the shape where recompute is cheapest". */
+int lt_joint_lattice_fused_supported(int semiring, int vocab_size, int context_size,
+                                     int max_expansions, int H);
+int lt_joint_lattice_forward_fused(int semiring, int vocab_size, const float* proj_ctx,
+                                   const float* proj_frame, const float* w_blank,
+                                   const float* b_blank, const float* w_vocab,
+                                   const float* b_vocab, const int32_t* num_frames, int B,
+                                   int T, int H, float* dist, float* alphas,
+                                   float* alpha_final, int16_t* backptr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

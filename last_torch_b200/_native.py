@@ -76,6 +76,9 @@ SIGNATURES = {
     'lt_joint_workspace_bytes': [_c_i64, _c_int, _c_int, _c_int],
     'lt_joint_forward': [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _c_int,
                          _ptr, _ptr, _ptr, _ptr],
+    'lt_joint_lattice_fused_supported': [_c_int, _c_int, _c_int, _c_int, _c_int],
+    'lt_joint_lattice_forward_fused': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                       _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr],
     'lt_joint_split_rows': [_ptr, _ptr, _c_i64, _c_int, _ptr],
     'lt_set_option': [ctypes.c_char_p, _c_int],
     'lt_get_option': [ctypes.c_char_p],
@@ -142,6 +145,7 @@ _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count', 
             'lt_get_option',
             'lt_joint_backward_split_supported', 'lt_lattice_backward_split_supported',
             'lt_lattice_norm_supported', 'lt_string_norm_supported',
+            'lt_joint_lattice_fused_supported',
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 
 

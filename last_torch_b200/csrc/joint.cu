@@ -246,3 +246,31 @@ extern "C" int lt_joint_split_rows(const float* rows, void* out, int64_t M, int 
                "lt_joint_split_rows: NULL or misaligned pointer");
   return joint_split_rows_launch(rows, out, M, V, (cudaStream_t)stream);
 }
+
+// ---- north_star (4): JointWeightFn fused into the recursion (joint_lattice_fused.cu) ----------
+extern "C" int lt_joint_lattice_fused_supported(int semiring, int vocab_size, int context_size,
+                                                int max_expansions, int H) {
+  return joint_lattice_fused_supported(semiring, vocab_size, context_size, max_expansions, H) ? 1 : 0;
+}
+
+extern "C" int lt_joint_lattice_forward_fused(int semiring, int vocab_size, const float* proj_ctx,
+                                              const float* proj_frame, const float* w_blank,
+                                              const float* b_blank, const float* w_vocab,
+                                              const float* b_vocab, const int32_t* num_frames,
+                                              int B, int T, int H, float* dist, float* alphas,
+                                              float* alpha_final, int16_t* backptr, void* stream) {
+  LT_CHECK_ARG(joint_lattice_fused_supported(semiring, vocab_size, 1, LT_FRAME_DEPENDENT, H),
+               "lt_joint_lattice_forward_fused: needs Log / MaxTropical, vocab_size <= 64 and "
+               "H in {32, 64, 128} (got semiring %d, V=%d, H=%d)", semiring, vocab_size, H);
+  LT_CHECK_ARG(B >= 0 && T >= 0, "lt_joint_lattice_forward_fused: bad sizes B=%d T=%d", B, T);
+  if (B == 0) return LT_OK;
+  LT_CHECK_ARG(proj_ctx && w_blank && b_blank && w_vocab && b_vocab && num_frames && dist &&
+                   (T == 0 || proj_frame),
+               "lt_joint_lattice_forward_fused: NULL pointer");
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  LT_CHECK_ARG(al16(w_vocab) && al16(w_blank),
+               "lt_joint_lattice_forward_fused: w_vocab / w_blank must be 16-byte aligned");
+  return joint_lattice_forward_fused_launch(semiring, vocab_size, H, proj_ctx, proj_frame, w_blank,
+                                            b_blank, w_vocab, b_vocab, num_frames, B, T, dist,
+                                            alphas, alpha_final, backptr, (cudaStream_t)stream);
+}

@@ -177,6 +177,14 @@ bool joint_wgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, co
 int joint_wgrad_tc_launch(const float* ec, const float* ef, const float* gb, const float* gl,
                           int split, int64_t N, int C, int H, int V, float* gwb, float* gbb,
                           float* gwv, float* gbv, cudaStream_t stream);
+// JointWeightFn fused into the forward recursion (joint_lattice_fused.cu): inference direction
+bool joint_lattice_fused_supported(int semiring, int V, int n, int k, int H);
+int joint_lattice_forward_fused_launch(int semiring, int V, int H, const float* pc, const float* pf,
+                                       const float* w_blank, const float* b_blank,
+                                       const float* w_vocab, const float* b_vocab,
+                                       const int32_t* num_frames, int B, int T, float* dist,
+                                       float* alphas, float* alpha_final, int16_t* backptr,
+                                       cudaStream_t stream);
 int pick_cluster_size(const NGram& g, int B, unsigned flags, int sm_count);
 
 }  // namespace lt

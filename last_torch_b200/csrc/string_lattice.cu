@@ -404,13 +404,16 @@ __device__ __forceinline__ void ext_logaddexp(int ea, float fa, int eb, float fb
   f = r - k;
 }
 
-template <int SR, bool EXT>
-__global__ void __launch_bounds__(1024)
+// MAXT: block-size bound.  Label strings are short (U+1 <= 256 covers ASR utterances), and the
+// kernels keep kChunk frames of weights in registers: bounding the block at 256 threads gives
+// the compiler 255 registers per thread instead of 64 (the 1024-thread build spills).
+template <int SR, bool EXT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 string_forward_fd_fast(const StrParams p) {
   using S = Sr<SR>;
   static_assert(!EXT || SR == LT_LOG, "the (e, f) representation is a Log-semiring feature");
-  __shared__ float mv[2][1024 + 1];
-  __shared__ int me[EXT ? 2 : 1][EXT ? 1024 + 1 : 1];
+  __shared__ float mv[2][MAXT + 1];
+  __shared__ int me[EXT ? 2 : 1][EXT ? MAXT + 1 : 1];
   const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
   const bool act = u < U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
@@ -486,13 +489,13 @@ string_forward_fd_fast(const StrParams p) {
   }
 }
 
-template <int SR, bool EXT>   // LT_LOG or LT_REAL
-__global__ void __launch_bounds__(1024)
+template <int SR, bool EXT, int MAXT>   // LT_LOG or LT_REAL
+__global__ void __launch_bounds__(MAXT)
 string_backward_fd_fast(const StrParams p) {
   using S = Sr<SR>;
   static_assert(!EXT || SR == LT_LOG, "the (e, f) representation is a Log-semiring feature");
-  __shared__ float sh[2][1024 + 1];
-  __shared__ int she[EXT ? 2 : 1][EXT ? 1024 + 1 : 1];
+  __shared__ float sh[2][MAXT + 1];
+  __shared__ int she[EXT ? 2 : 1][EXT ? MAXT + 1 : 1];
   const int b = blockIdx.x, U1 = p.U1, u = threadIdx.x;
   const bool act = u < U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
@@ -576,14 +579,17 @@ string_backward_fd_fast(const StrParams p) {
 template <int SR>
 static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
   if (p.k < 1 && p.U1 <= 1024) {
+    const bool small = p.U1 <= 256;
     if constexpr (SR == LT_LOG) {
       if (p.alpha_exp) {
-        string_forward_fd_fast<SR, true><<<p.B, block_for(p.U1), 0, stream>>>(p);
+        if (small) string_forward_fd_fast<SR, true, 256><<<p.B, block_for(p.U1), 0, stream>>>(p);
+        else string_forward_fd_fast<SR, true, 1024><<<p.B, block_for(p.U1), 0, stream>>>(p);
         LT_LAUNCHED();
         return LT_OK;
       }
     }
-    string_forward_fd_fast<SR, false><<<p.B, block_for(p.U1), 0, stream>>>(p);
+    if (small) string_forward_fd_fast<SR, false, 256><<<p.B, block_for(p.U1), 0, stream>>>(p);
+    else string_forward_fd_fast<SR, false, 1024><<<p.B, block_for(p.U1), 0, stream>>>(p);
     LT_LAUNCHED();
     return LT_OK;
   }
@@ -606,14 +612,17 @@ template <int SR>
 static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
   if constexpr (SR != LT_MAXTROPICAL) {
     if (p.k < 1 && p.U1 <= 1024) {
+      const bool small = p.U1 <= 256;
       if constexpr (SR == LT_LOG) {
         if (p.alpha_exp_in) {
-          string_backward_fd_fast<SR, true><<<p.B, block_for(p.U1), 0, stream>>>(p);
+          if (small) string_backward_fd_fast<SR, true, 256><<<p.B, block_for(p.U1), 0, stream>>>(p);
+          else string_backward_fd_fast<SR, true, 1024><<<p.B, block_for(p.U1), 0, stream>>>(p);
           LT_LAUNCHED();
           return LT_OK;
         }
       }
-      string_backward_fd_fast<SR, false><<<p.B, block_for(p.U1), 0, stream>>>(p);
+      if (small) string_backward_fd_fast<SR, false, 256><<<p.B, block_for(p.U1), 0, stream>>>(p);
+      else string_backward_fd_fast<SR, false, 1024><<<p.B, block_for(p.U1), 0, stream>>>(p);
       LT_LAUNCHED();
       return LT_OK;
     }

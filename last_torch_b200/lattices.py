@@ -60,6 +60,12 @@ class RecognitionLattice(nn.Module, Generic[T]):
     # (lattices.py:300-313) instead of gathered out of the dense [B,T,C,V] weights.  None =
     # automatic: when the loss needs no denominator (LocallyNormalizedWeightFn).
     self.gathered_numerator = None
+    # Inference without materialising the arc weights: JointWeightFn fused into the forward
+    # recursion (ops.joint_lattice_forward_fused; bigram, vocab <= 64, hidden in {32, 64, 128}).
+    # Off by default: it saves the O(B*T*C*V) logits but is slower than the tensor-core joint
+    # kernel + K1.  Used by shortest_path and by _forward when no
+    # gradient is required.
+    self.fused_inference = False
     # shortest_path: reproduce the label encoding of the reference as shipped (see there)
     self.reference_compat = False
     # Range-check the reference labels (0 <= label <= vocab_size for the first num_labels
@@ -236,6 +242,16 @@ class RecognitionLattice(nn.Module, Generic[T]):
     if cache is None:
       cache = self.weight_fn_cacher()
     v, n, k = self._geometry()
+    if self._fused_applicable(N.MAXTROPICAL, frames, cache):
+      path_weights, _, labels, _ = self._fused_forward(
+          N.MAXTROPICAL, cache, frames, num_frames, batch_dims, False, True)
+      dev = frames.device
+      if reference_compat is None:
+        reference_compat = self.reference_compat
+      if reference_compat:
+        labels = self._reference_labels(labels, num_frames.to(dev).reshape(-1), v, len(batch_dims))
+      return (labels.to(torch.int64).reshape(*batch_dims, -1),
+              self.alignment.num_states() * num_frames.to(dev), path_weights.reshape(batch_dims))
     with torch.no_grad():
       blank, lexical = self._arc_weights(cache, frames, batch_dims)
       dev = blank.device
@@ -254,6 +270,30 @@ class RecognitionLattice(nn.Module, Generic[T]):
     alignment_labels = labels.to(torch.int64).reshape(*batch_dims, -1)
     num_alignment_labels = num_alignment_states * num_frames.to(dev)
     return alignment_labels, num_alignment_labels, path_weights.reshape(batch_dims)
+
+  def _fused_applicable(self, sr, frames, cache) -> bool:
+    if not self.fused_inference or self._is_table() or not frames.is_cuda:
+      return False
+    if type(self.weight_fn) is not weight_fns.JointWeightFn:
+      return False
+    if not isinstance(self.context, contexts.FullNGram):
+      return False
+    k = self.alignment.kernel_max_expansions()
+    return bool(N.lib().lt_joint_lattice_fused_supported(
+        sr, self.context.vocab_size, self.context.context_size, k, self.weight_fn.hidden_size))
+
+  def _fused_forward(self, sr, cache, frames, num_frames, batch_dims, want_alphas, want_path):
+    from . import joint
+    fn = self.weight_fn
+    fn._check_lazy(cache, frames)
+    t = frames.shape[-2]
+    with torch.no_grad():
+      proj_ctx, proj_frame = joint.joint_projections(fn, cache, frames)
+      return ops.joint_lattice_forward_fused(
+          sr, self.context.vocab_size, proj_ctx, proj_frame.reshape(-1, t, proj_frame.shape[-1]),
+          fn.joint_projection_to_blank.weight, fn.joint_projection_to_blank.bias,
+          fn.joint_projection_to_vocab.weight, fn.joint_projection_to_vocab.bias,
+          ops._as_i32(num_frames.reshape(-1), frames.device), want_alphas, want_path)
 
   def _reference_labels(self, labels, num_frames, v, num_batch_dims):
     """labels [B, T, N] true labels -> what the reference as shipped prints (D4, D5)."""
@@ -334,6 +374,13 @@ class RecognitionLattice(nn.Module, Generic[T]):
                        f'but is {len(lexical_mask)}')
     sr = semirings.kernel_id(semiring)
     v, n, k = self._geometry()
+    if (blank_mask is None and lexical_mask is None and sr != N.REAL and
+        not (torch.is_grad_enabled() and (frames.requires_grad or any(
+            p.requires_grad for p in self.parameters()))) and
+        self._fused_applicable(sr, frames, cache)):
+      dist, alphas, _, _ = self._fused_forward(sr, cache, frames, num_frames, batch_dims, True,
+                                               False)
+      return dist.reshape(batch_dims), alphas.reshape(*batch_dims, frames.shape[-2], -1)
     blank, lexical = self._arc_weights(cache, frames, batch_dims)
     c = blank.shape[-1]
     t = blank.shape[1]

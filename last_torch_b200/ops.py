@@ -299,6 +299,42 @@ class LatticeForwardLevels(torch.autograd.Function):
     return gb, gl, None, None, None, None, None, None
 
 
+def joint_lattice_forward_fused(sr, V, proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab,
+                                num_frames, want_alphas=True, want_path=False):
+  """JointWeightFn fused into the forward recursion (lt_joint_lattice_forward_fused): no
+  [B,T,C,V] tensor exists.  proj_ctx [C,H], proj_frame [B,T,H].  Returns (dist [B], alphas
+  [B,T,C] or None, labels [B,T,1] / path_states [B,T+1] when want_path (MaxTropical))."""
+  proj_ctx = N.require_cuda(proj_ctx, 'proj_ctx')
+  proj_frame = N.require_cuda(proj_frame, 'proj_frame')
+  w_blank = N.require_cuda(w_blank.reshape(-1), 'w_blank')
+  b_blank = N.require_cuda(b_blank.reshape(-1), 'b_blank')
+  w_vocab = N.require_cuda(w_vocab, 'w_vocab')
+  b_vocab = N.require_cuda(b_vocab, 'b_vocab')
+  B, T, H = proj_frame.shape
+  C = proj_ctx.shape[0]
+  dev = proj_frame.device
+  dist = torch.empty([B], dtype=torch.float32, device=dev)
+  alphas = torch.empty([B, T, C], dtype=torch.float32, device=dev) if want_alphas else None
+  backptr = alpha_final = None
+  if want_path:
+    backptr = torch.empty([B, T, 1, C], dtype=torch.int16, device=dev)
+    alpha_final = torch.empty([B, C], dtype=torch.float32, device=dev)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_joint_lattice_forward_fused(
+        sr, V, N.ptr(proj_ctx), N.ptr(proj_frame), N.ptr(w_blank), N.ptr(b_blank), N.ptr(w_vocab),
+        N.ptr(b_vocab), N.ptr(num_frames), B, T, H, N.ptr(dist), N.ptr(alphas),
+        N.ptr(alpha_final), N.ptr(backptr), N.stream_ptr(dev)), 'lt_joint_lattice_forward_fused')
+    labels = states = None
+    if want_path:
+      labels = torch.empty([B, T, 1], dtype=torch.int32, device=dev)
+      states = torch.empty([B, T + 1], dtype=torch.int32, device=dev)
+      N.check(N.lib().lt_viterbi_backtrace(
+          V, 1, N.FRAME_DEPENDENT, N.ptr(backptr), None, N.ptr(alpha_final), N.ptr(num_frames),
+          B, T, N.ptr(labels), N.ptr(states), None, None, None, N.stream_ptr(dev)),
+          'lt_viterbi_backtrace')
+  return dist, alphas, labels, states
+
+
 def viterbi_path(blank, lexical, num_frames, V, n, k, flags=0):
   """MaxTropical forward + back-trace; returns (labels [B,T,k+1] int32 with true
   1-based labels, path_states [B,T+1], path_weights [B])."""

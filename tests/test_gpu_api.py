@@ -859,3 +859,54 @@ def test_frame_label_dependent_per_state_masks(name, ctx, vocab, k):
       npt.assert_array_equal(a.cpu(), r.cpu())
     else:
       npt.assert_allclose(a.cpu(), r.cpu(), rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize('vocab,hidden', [(64, 128), (32, 64), (5, 32)])
+def test_fused_joint_lattice_inference_matches_the_unfused_path(vocab, hidden):
+  """north_star (4): JointWeightFn fused into the forward recursion (no [B,T,C,V] logits in
+  memory) against the unfused path (tensor-core / CUDA-core joint kernel -> HBM -> K1): Log
+  distances and alphas to 2e-5 of their scale, MaxTropical distances to 1e-5 (the unfused
+  logits carry the bf16x3 rounding, the fused ones are fp32 FMAs), Viterbi labels identical
+  wherever the two best paths differ by more than that."""
+  lt = _lt()
+  torch.manual_seed(vocab)
+  lattice = lt.RecognitionLattice(
+      context=lt.contexts.FullNGram(vocab_size=vocab, context_size=1),
+      alignment=lt.alignments.FrameDependent(),
+      weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+          num_context_states=c.shape()[0], embedding_size=24, device='cuda'),
+      weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+          vocab_size=c.shape()[1], hidden_size=hidden, device='cuda', embedding_size=24,
+          feature_size=16))
+  with torch.no_grad():      # larger weights: well separated paths
+    lattice.weight_fn.joint_projection_to_vocab.weight.mul_(6.0)
+    lattice.weight_fn.joint_projection_to_blank.weight.mul_(6.0)
+  b, t = 4, 37
+  x = torch.randn([b, t, 16], device='cuda')
+  nf = T([37, 20, 1, 0])
+  res = {}
+  for fused in (False, True):
+    lattice.fused_inference = fused
+    with torch.no_grad():
+      log_z, alphas = lattice._forward(cache=lattice.build_cache(), frames=x, num_frames=nf,
+                                       semiring=lt.semirings.Log)
+      vd, _ = lattice._forward(cache=lattice.build_cache(), frames=x, num_frames=nf,
+                               semiring=lt.semirings.MaxTropical)
+    labels, num, weights = lattice.shortest_path(frames=x, num_frames=nf)
+    res[fused] = (log_z.cpu().numpy(), alphas.cpu().numpy(), vd.cpu().numpy(),
+                  labels.cpu().numpy(), num.cpu().numpy(), weights.cpu().numpy())
+  u, f = res[False], res[True]
+  scale = np.abs(u[0]).max() + 1.0
+  npt.assert_allclose(f[0], u[0], rtol=0, atol=2e-5 * scale)
+  fin = np.isfinite(u[1])
+  npt.assert_array_equal(np.isfinite(f[1]), fin)
+  npt.assert_allclose(f[1][fin], u[1][fin], rtol=0, atol=2e-5 * scale)
+  npt.assert_allclose(f[2], u[2], rtol=0, atol=1e-5 * scale)
+  npt.assert_allclose(f[5], f[2], rtol=1e-6)
+  npt.assert_array_equal(f[4], u[4])
+  npt.assert_array_equal(f[3], u[3])
+  assert f[3].min() >= 0 and f[3].max() <= vocab and (f[3] > 0).any()
+  # a training call still takes the differentiable path
+  loss = lattice(frames=x[:2], num_frames=nf[:2], labels=T([[1, 2], [3, 0]]), num_labels=T([2, 1]))
+  loss.sum().backward()
+  assert lattice.weight_fn.joint_projection_to_vocab.weight.grad is not None
