@@ -130,9 +130,13 @@ joint_lattice_forward_fused_kernel(const FusedParams p) {
     if (p.alphas)
       for (int c = tid; c < C; c += nth) p.alphas[(bt0 + t) * C + c] = cur[c];
     __syncthreads();
-    for (int i = tid; i < C * H; i += nth) {
-      const int c = i / H, h = i - c * H;
-      jt[c * JS + h] = tanh_from_exp(ec[i], ef[h]);
+    for (int i = tid; i < C * (H / 4); i += nth) {            // H is a power of two
+      const int c = i / (H / 4), h4 = (i - c * (H / 4)) * 4;
+      const float4 a = *reinterpret_cast<const float4*>(ec + c * H + h4);
+      const float4 f = *reinterpret_cast<const float4*>(ef + h4);
+      *reinterpret_cast<float4*>(jt + c * JS + h4) =
+          make_float4(tanh_from_exp(a.x, f.x), tanh_from_exp(a.y, f.y), tanh_from_exp(a.z, f.z),
+                      tanh_from_exp(a.w, f.w));
     }
     __syncthreads();
 
@@ -141,7 +145,37 @@ joint_lattice_forward_fused_kernel(const FusedParams p) {
     // multiply by zero weights and store nothing)
     typename FusedAcc<SR>::type acc; acc.init();
     {
-      for (int s = 0; s < C; ++s) {
+      auto consume = [&](int s, float d) {
+        const float logit = d + bias;
+        if (j < V) acc.add(S::times(cur[s], logit), s);       // arc s --(j+1)--> state 1 + j
+        else if (j == V && hq == 0) bl[s] = logit;            // blank weight of state s
+      };
+      // four source rows per step: 8 independent FMA chains and 4 shuffle pairs in flight
+      int s = 0;
+      for (; s + 4 <= C; s += 4) {
+        float d[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { d[r][0] = 0.f; d[r][1] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < HQ / 4; ++i) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(jt + (s + r) * JS + hq * 4 + i * 16);
+            d[r][0] = fmaf(x.x, w[4 * i], d[r][0]); d[r][1] = fmaf(x.y, w[4 * i + 1], d[r][1]);
+            d[r][0] = fmaf(x.z, w[4 * i + 2], d[r][0]); d[r][1] = fmaf(x.w, w[4 * i + 3], d[r][1]);
+          }
+        }
+        float e[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] = d[r][0] + d[r][1];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] += __shfl_xor_sync(0xffffffffu, e[r], 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] += __shfl_xor_sync(0xffffffffu, e[r], 2);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) consume(s + r, e[r]);
+      }
+      for (; s < C; ++s) {
         const float* row = jt + s * JS + hq * 4;
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -150,12 +184,10 @@ joint_lattice_forward_fused_kernel(const FusedParams p) {
           d0 = fmaf(x.x, w[4 * i], d0); d1 = fmaf(x.y, w[4 * i + 1], d1);
           d0 = fmaf(x.z, w[4 * i + 2], d0); d1 = fmaf(x.w, w[4 * i + 3], d1);
         }
-        float d = d0 + d1;
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        const float logit = d + bias;
-        if (j < V) acc.add(S::times(cur[s], logit), s);       // arc s --(j+1)--> state 1 + j
-        else if (j == V && hq == 0) bl[s] = logit;            // blank weight of state s
+        float dd = d0 + d1;
+        dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+        dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+        consume(s, dd);
       }
     }
     __syncthreads();
