@@ -65,7 +65,8 @@ unsigned long long lt_launch_count(void);
 /* Debug / test switches, process-wide.  Each is initialised once from the environment variable
  * of the same name and can be changed at run time: LT_JOINT_SIMT, LT_JOINT_DGRAD_V1,
  * LT_JOINT_WGRAD_SIMT (CUDA-core / first-generation joint kernels), LT_JOINT_DGRAD_PAIR,
- * LT_JOINT_DGRAD_MULTICAST (measured-slower variants of the split-row dgrad), LT_TABLE_V1,
+ * LT_JOINT_DGRAD_MULTICAST (measured-slower variants of the split-row dgrad), LT_JOINT_FWD_SS
+ * (forward projection with the tanh operand staged in shared instead of tensor memory), LT_TABLE_V1,
  * LT_TABLE_CLUSTER (NextStateTable kernel selection).  lt_get_option returns -1 for an unknown
  * name. */
 int lt_set_option(const char* name, int value);

@@ -38,6 +38,8 @@ enum Option {
   OPT_JOINT_DGRAD_MULTICAST,  // LT_JOINT_DGRAD_MULTICAST: TMA-multicast split-row dgrad
   OPT_TABLE_V1,               // LT_TABLE_V1: one-CTA NextStateTable kernels
   OPT_TABLE_CLUSTER,          // LT_TABLE_CLUSTER: force the NextStateTable cluster size
+  OPT_JOINT_FWD_SS,           // LT_JOINT_FWD_SS: forward with the tanh operand in shared memory
+  OPT_JOINT_FWD_CLUSTER,      // LT_JOINT_FWD_CLUSTER=1: no W_vocab multicast (one CTA per cluster)
   OPT_COUNT
 };
 int option(Option o);

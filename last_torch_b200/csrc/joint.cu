@@ -161,6 +161,10 @@ extern "C" int lt_joint_forward(const float* proj_ctx, const float* proj_frame,
   LT_CHECK_ARG(proj_ctx && proj_frame && w_blank && b_blank && w_vocab && b_vocab && blank && lexical,
                "lt_joint_forward: NULL pointer");
   if (workspace && reinterpret_cast<uintptr_t>(workspace) % 128 == 0 &&
+      joint_forward_ts_supported(N, C, H, V, lexical))
+    return joint_forward_ts_launch(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, N, C,
+                                   H, V, blank, lexical, workspace, (cudaStream_t)stream);
+  if (workspace && reinterpret_cast<uintptr_t>(workspace) % 128 == 0 &&
       joint_tc_supported(N, C, H, V, proj_ctx, proj_frame, lexical))
     return joint_forward_tc_launch(proj_ctx, proj_frame, w_blank, b_blank, w_vocab, b_vocab, N, C,
                                    H, V, blank, lexical, workspace, (cudaStream_t)stream);

@@ -1184,6 +1184,18 @@ int64_t joint_split_bytes(int H, int V) { return (((int64_t)V * H * 4 + 255) / 2
 int64_t joint_table_bytes(int64_t N, int C, int H) {
   return (((N + C) * (int64_t)H * 4 + 255) / 256) * 256;
 }
+int joint_split_weights_launch(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int n,
+                               cudaStream_t stream) {
+  split_weights_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, hi, lo, n);
+  LT_LAUNCHED();
+  return LT_OK;
+}
+int joint_exp_table_launch(const float* x, float* out, long long n, cudaStream_t stream) {
+  joint_exp_table_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 4096), 256, 0, stream>>>(
+      x, out, n);
+  LT_LAUNCHED();
+  return LT_OK;
+}
 // e^(2 pc) -> ec [C,H], e^(2 pf) -> ef [N,H]
 int joint_exp_tables_launch(const float* pc, const float* pf, int64_t N, int C, int H,
                                    float* ec, float* ef, cudaStream_t stream) {

@@ -1,6 +1,7 @@
 // Kernel parameter blocks and launcher prototypes shared by capi.cu and the
 // kernel translation units.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 struct CUtensorMap_st;
@@ -146,6 +147,14 @@ bool joint_tc_supported(int64_t N, int C, int H, int V, const void* pc, const vo
 int joint_forward_tc_launch(const float* pc, const float* pf, const float* wb, const float* bb,
                             const float* wv, const float* bv, int64_t N, int C, int H, int V,
                             float* blank, float* lexical, void* workspace, cudaStream_t stream);
+// the same with the tanh operand in tensor memory (joint_fwd_ts.cu)
+bool joint_forward_ts_supported(int64_t N, int C, int H, int V, const void* lexical);
+int joint_forward_ts_launch(const float* pc, const float* pf, const float* wb, const float* bb,
+                            const float* wv, const float* bv, int64_t N, int C, int H, int V,
+                            float* blank, float* lexical, void* workspace, cudaStream_t stream);
+int joint_split_weights_launch(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int n,
+                               cudaStream_t stream);
+int joint_exp_table_launch(const float* x, float* out, long long n, cudaStream_t stream);
 bool joint_dgrad_tc_supported(int64_t N, int C, int H, int V, const void* gl, const void* pc,
                               const void* pf);
 int64_t joint_backward_workspace_bytes(int64_t N, int C, int H, int V);

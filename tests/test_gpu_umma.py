@@ -44,6 +44,59 @@ def test_umma_probe_matches_fp32_matmul(n, k):
   assert err3 < err1 / 50
 
 
+@pytest.mark.parametrize('n,k', [(256, 64), (256, 512), (128, 128), (64, 192), (32, 64)])
+def test_umma_probe_operand_in_tensor_memory(n, k):
+  """The same product with the A operand written to TMEM by tcgen05.st (row = lane, two K
+  elements per 32-bit column) and only B in shared memory."""
+  N.lib()
+  handle = ctypes.CDLL(N.LIB_PATH)
+  fn = handle.ltx_umma_probe_ts
+  fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 + [ctypes.c_void_p]
+  fn.restype = ctypes.c_int
+  g = torch.Generator(device='cuda').manual_seed(n * 1000 + k + 1)
+  a = torch.randn([128, k], device='cuda', generator=g)
+  b = torch.randn([n, k], device='cuda', generator=g)
+  d = torch.empty([128, n], device='cuda')
+  rc = fn(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, torch.cuda.current_stream().cuda_stream)
+  assert rc == 0, handle.lt_last_error()
+  torch.cuda.synchronize()
+  ref = a.double() @ b.double().T
+  err = float((d.double() - ref).abs().max()) / float(ref.abs().max())
+  assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 300), (65, 64, 128, 9), (130, 128, 192, 31),
+                                     (7, 192, 1024, 77), (257, 256, 512, 2501), (64, 64, 64, 1),
+                                     (33, 256, 128, 130)])
+def test_joint_forward_operand_in_tensor_memory_equals_shared_memory_form(c, v, h, n):
+  """lt_joint_forward with the tanh operand in tensor memory (default for V % 64 == 0,
+  H <= 1024) against the shared-memory-operand kernel: same bf16x3 products, so the two agree to
+  fp32 accumulation order."""
+  from last_torch_b200.joint import joint_forward_raw
+  g = torch.Generator(device='cuda').manual_seed(c * 31 + n)
+  pc = torch.randn([c, h], device='cuda', generator=g)
+  pf = torch.randn([n, h], device='cuda', generator=g)
+  wb = torch.randn([1, h], device='cuda', generator=g) * 0.3
+  bb = torch.full([], -0.5, device='cuda')
+  wv = torch.randn([v, h], device='cuda', generator=g) * 0.3
+  bv = torch.randn([v], device='cuda', generator=g)
+  b_ts, l_ts = joint_forward_raw(pc, pf, wb, bb, wv, bv)
+  with N.option('LT_JOINT_FWD_CLUSTER', 1):                # no multicast: one CTA per cluster
+    b_1, l_1 = joint_forward_raw(pc, pf, wb, bb, wv, bv)
+  assert torch.equal(l_1, l_ts) and torch.equal(b_1, b_ts)
+  with N.option('LT_JOINT_FWD_SS', 1):
+    b_ss, l_ss = joint_forward_raw(pc, pf, wb, bb, wv, bv)
+  j = torch.tanh(pc.double()[None] + pf.double()[:, None])
+  rl = j @ wv.double().T + bv.double()
+  rb = j @ wb.double()[0] + bb.double()
+  scale = float(rl.abs().max())
+  assert float((l_ts.double() - rl).abs().max()) / scale < 1e-5
+  assert float((l_ss.double() - rl).abs().max()) / scale < 1e-5
+  assert float((l_ts - l_ss).abs().max()) / scale < 2e-6
+  assert float((b_ts.double() - rb).abs().max()) / float(rb.abs().max()) < 1e-5
+  assert float((b_ts - b_ss).abs().max()) / float(rb.abs().max()) < 2e-6
+
+
 @pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 70), (65, 64, 128, 9), (33, 32, 64, 5),
                                      (130, 128, 192, 31)])
 def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
