@@ -616,6 +616,8 @@ def run_b200(args):
                 32, 500, 64, 2, 2, 60, 'lossgrad')
       run_extra('bigram vocab 256 FrameLabelDependent(2) Log loss+grad at configs[1] geometry, '
                 'B=32 T=1000', 32, 1000, 256, 1, 2, 120, 'lossgrad')
+      run_extra('bigram vocab 256 FrameLabelDependent(2) MaxTropical shortest distance + '
+                'Viterbi at configs[1] geometry, B=32 T=1000', 32, 1000, 256, 1, 2, 120, 'viterbi')
       run_extra('configs[1] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=32 T=1000 '
                 '(real frames counted)', 32, 1000, 256, 1, -1, 120, 'lossgrad', ragged=True)
       run_extra('configs[4] ragged: num_frames ~ U{T/2..T}, Log loss+grad, B=96/GPU (utterances '

@@ -242,8 +242,9 @@ int lt_string_backward(int semiring, int max_expansions, const float* blank_w,
  * chain rounds have magnitude O(1) whatever the numerator's magnitude (1e3 at T = 1000).
  *   alphas [B,T,U1] then holds the fractions, alpha_exp [B,T,U1] int32 the integer parts;
  *   dist_norm [B,2] int32 = (integer part, bits of the fp32 fraction) of dist[b].
- * Only when lt_string_norm_supported() returns 1 (Log, FrameDependent, U1 <= 1024); NULL for both
- * selects the plain kernels. */
+ * Only when lt_string_norm_supported() returns 1 (Log: register kernels for FrameDependent with
+ * U1 <= 1024, a double-precision chain for FrameLabelDependent and longer label strings); NULL
+ * for both selects the plain fp32 kernels. */
 int lt_string_norm_supported(int semiring, int max_expansions, int U1);
 int lt_string_forward_norm(int semiring, int max_expansions, const float* blank_w,
                            const float* lexical_w, const int32_t* num_frames,

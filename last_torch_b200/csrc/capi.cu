@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 static const char* const kOptionNames[OPT_COUNT] = {
     "LT_JOINT_SIMT", "LT_JOINT_DGRAD_V1", "LT_JOINT_WGRAD_SIMT", "LT_JOINT_DGRAD_PAIR",
     "LT_JOINT_DGRAD_MULTICAST", "LT_TABLE_V1", "LT_TABLE_CLUSTER", "LT_JOINT_FWD_SS",
-    "LT_JOINT_FWD_CLUSTER"};
+    "LT_JOINT_FWD_CLUSTER", "LT_FLD_GENERIC"};
 static int g_options[OPT_COUNT];
 static std::once_flag g_options_once;
 
@@ -141,6 +141,7 @@ namespace lt {
 int lattice_norm_family(int semiring, const NGram& g, int k, unsigned flags, const void* lexical) {
   if (semiring != LT_LOG) return 0;
   if (lattice_fast2_supported(g, k, flags, lexical)) return 1;
+  if (lattice_fast2_fld_supported(g, k, flags, lexical)) return 1;
   // the thread-per-column forward (context_size >= 2) has no renormalised variant
   const void* probe = lexical ? lexical : reinterpret_cast<const void*>(uintptr_t(256));
   if (lattice_cols_supported(g, k, flags, probe)) return 0;
@@ -187,12 +188,14 @@ int lt_lattice_forward_norm(int semiring, int vocab_size, int context_size, int 
     flags |= LT_FLAG_FORCE_GENERIC;
   }
   const bool fast2 = T > 0 && lattice_fast2_supported(g, max_expansions, flags, lexical);
+  const bool fld2 = T > 0 && lattice_fast2_fld_supported(g, max_expansions, flags, lexical);
   if (alpha_norm && (T == 0 || !lattice_norm_family(semiring, g, max_expansions, flags, lexical))) {
     set_error("lt_lattice_forward_norm: this lattice has no renormalised kernel "
               "(lt_lattice_norm_supported, T > 0)");
     return LT_ERR_UNSUPPORTED;
   }
   if (fast2) return lattice_forward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
+  if (fld2) return lattice_forward_fld2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (T > 0 && lattice_cols_supported(g, max_expansions, flags, lexical))
     return lattice_forward_cols_launch(semiring, g, max_expansions, p, (cudaStream_t)stream);
   return lattice_forward_generic_launch(semiring, g, max_expansions, p, flags, sms,
@@ -242,8 +245,10 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
     p.wlevels = max_expansions + 1;
     flags |= LT_FLAG_FORCE_GENERIC;
   }
-  const bool fast2 = lattice_fast2_supported(g, max_expansions, flags, lexical) &&
-                     reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0;
+  const bool fld2 = lattice_fast2_fld_supported(g, max_expansions, flags, lexical) &&
+                    reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0;
+  const bool fast2 = fld2 || (lattice_fast2_supported(g, max_expansions, flags, lexical) &&
+                              reinterpret_cast<uintptr_t>(grad_lexical) % 16 == 0);
   if (alpha_norm) {
     // the pair must stay inside one kernel family: the offsets' unit differs between them
     const int family = lattice_norm_family(semiring, g, max_expansions, flags, lexical);
@@ -261,6 +266,7 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
                                              (cudaStream_t)stream);
     }
   }
+  if (fld2) return lattice_backward_fld2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (fast2) return lattice_backward_fast2_launch(semiring, g, p, flags, (cudaStream_t)stream);
   if (flags & LT_FLAG_GRAD_SPLIT) {
     set_error("lt_lattice_backward: LT_FLAG_GRAD_SPLIT needs the TMA fast path "
@@ -380,8 +386,9 @@ int lt_lattice_backward_split_supported(int semiring, int vocab_size, int contex
   if (check_common("lt_lattice_backward_split_supported", semiring, vocab_size, context_size,
                    max_expansions, 1, 1, &g))
     return 0;
-  return lattice_fast2_supported(g, max_expansions, flags & ~LT_FLAG_GRAD_SPLIT,
-                                 reinterpret_cast<const void*>(uintptr_t(256))) ? 1 : 0;
+  const void* probe = reinterpret_cast<const void*>(uintptr_t(256));
+  return (lattice_fast2_supported(g, max_expansions, flags & ~LT_FLAG_GRAD_SPLIT, probe) ||
+          lattice_fast2_fld_supported(g, max_expansions, flags & ~LT_FLAG_GRAD_SPLIT, probe)) ? 1 : 0;
 }
 
 static int check_string(const char* fn, int semiring, int k, int B, int T, int U1) {

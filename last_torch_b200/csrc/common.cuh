@@ -40,6 +40,7 @@ enum Option {
   OPT_TABLE_CLUSTER,          // LT_TABLE_CLUSTER: force the NextStateTable cluster size
   OPT_JOINT_FWD_SS,           // LT_JOINT_FWD_SS: forward with the tanh operand in shared memory
   OPT_JOINT_FWD_CLUSTER,      // LT_JOINT_FWD_CLUSTER=1: no W_vocab multicast (one CTA per cluster)
+  OPT_FLD_GENERIC,            // LT_FLD_GENERIC: FrameLabelDependent on bigram contexts uses the generic kernels
   OPT_COUNT
 };
 int option(Option o);

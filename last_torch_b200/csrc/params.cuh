@@ -71,9 +71,10 @@ struct StrParams {
   const int32_t* alpha_exp_in;   // backward in
   const int32_t* dist_norm_in;
 };
-// (e, f) kernels exist for: Log, FrameDependent, U1 <= 1024
+// (e, f) kernels exist for the Log semiring: register kernels for FrameDependent with
+// U1 <= 1024, a double-precision chain otherwise (five double arrays of U1 in shared memory)
 inline bool string_norm_supported(int semiring, int k, int U1) {
-  return semiring == LT_LOG && k < 1 && U1 >= 1 && U1 <= 1024;
+  return semiring == LT_LOG && U1 >= 1 && (size_t)U1 * 5 * sizeof(double) <= 200 * 1024;
 }
 
 struct VitParams {
@@ -99,6 +100,12 @@ int lattice_backward_generic_launch(int semiring, const NGram& g, int k, const B
 // TMA / cluster fast path (lattice_fast2.cu): bigram FrameDependent, V in {64..256}; two CTAs
 // of different utterances per SM.  lexical == nullptr skips the alignment test.
 bool lattice_fast2_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+// FrameLabelDependent(k <= 3) on the same bigram shapes (lattice_fast2_fld.cu)
+bool lattice_fast2_fld_supported(const NGram& g, int k, unsigned flags, const void* lexical);
+int lattice_forward_fld2_launch(int semiring, const NGram& g, const FwdParams& base,
+                                unsigned flags, cudaStream_t stream);
+int lattice_backward_fld2_launch(int semiring, const NGram& g, const BwdParams& base,
+                                 unsigned flags, cudaStream_t stream);
 // which kernel family keeps alpha renormalised for this lattice (FwdParams::alpha_norm):
 // 0 none, 1 the TMA fast path (log2 units), 2 the generic kernels (natural-log units).
 // lexical == nullptr assumes 16-byte aligned weights.

@@ -329,6 +329,156 @@ __global__ void string_backward_kernel(const StrParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Log chain in DOUBLE with the (integer part, fraction) storage of lt_string_forward_norm, for
+// the shapes the register kernels below do not cover (FrameLabelDependent, U + 1 > 1024).  The
+// label lattice is B x T x (U + 1) values behind a T-long dependency chain -- latency, not
+// throughput -- so fp64 exp / log cost nothing that matters, and every stored quantity keeps
+// ~1e-7 of a unit at |alpha| ~ 1e3 (alpha = e + f, e an exact integer, f in [0, 1)).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double dneg_inf() { return __longlong_as_double(0xfff0000000000000ll); }
+__device__ __forceinline__ double dlogaddexp(double a, double b) {
+  const double c = fmax(a, b);
+  if (!(c > dneg_inf())) return c;                  // both are the semiring zero
+  return c + log(exp(a - c) + exp(b - c));
+}
+__device__ __forceinline__ void ext_split(double v, int32_t& e, float& f) {
+  if (!(v > dneg_inf())) { e = 0; f = neg_inf(); return; }
+  double k = floor(v);
+  k = fmin(fmax(k, -16777216.0), 16777216.0);
+  e = (int32_t)k;
+  f = (float)(v - k);
+}
+__device__ __forceinline__ double ext_join(int32_t e, float f) {
+  return f > neg_inf() ? (double)e + (double)f : dneg_inf();
+}
+// last_i[u] = alpha[u-i] + lex[u-i] + ... + lex[u-1]  (alignments.py:429-430)
+__device__ __forceinline__ double chain_last_d(const double* alpha, const float* lx, int u, int i) {
+  if (u < i) return dneg_inf();
+  double v = alpha[u - i];
+  for (int j = i; j >= 1; --j) v += (double)lx[u - j];
+  return v;
+}
+
+template <bool FLD>
+__global__ void string_forward_ext_kernel(const StrParams p) {
+  extern __shared__ double dsm[];
+  const int b = blockIdx.x, U1 = p.U1;
+  double* a0 = dsm;
+  double* a1 = dsm + U1;
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) a0[u] = (u == 0) ? 0.0 : dneg_inf();
+  __syncthreads();
+  double* cur = a0; double* nxt = a1;
+  for (int t = 0; t < p.T; ++t) {
+    const size_t off = ((size_t)b * p.T + t) * U1;
+    for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+      int32_t e; float f;
+      ext_split(cur[u], e, f);
+      if (p.alphas) p.alphas[off + u] = f;
+      p.alpha_exp[off + u] = e;
+    }
+    if (t >= nf) continue;       // uniform per block
+    const float* bl = p.blank_w + off;
+    const float* lx = p.lexical_w + off;
+    for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+      if constexpr (!FLD) {
+        const double a = cur[u] + (double)bl[u];
+        const double l = (u > 0) ? cur[u - 1] + (double)lx[u - 1] : dneg_inf();
+        nxt[u] = dlogaddexp(a, l);
+      } else {
+        double acc = dneg_inf();
+        const double bu = (double)bl[u];
+        for (int i = 0; i <= p.k; ++i) acc = dlogaddexp(acc, chain_last_d(cur, lx, u, i) + bu);
+        nxt[u] = acc;
+      }
+    }
+    __syncthreads();
+    double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (threadIdx.x == 0) {
+    const int nl = p.num_labels[b];
+    const double v = (nl >= 0 && nl < U1) ? cur[nl] : dneg_inf();   // lattices.py:375-377
+    int32_t e; float f;
+    ext_split(v, e, f);
+    p.dist[b] = (float)v;
+    p.dist_norm[2 * b] = e;
+    p.dist_norm[2 * b + 1] = __float_as_int(f);
+  }
+}
+
+template <bool FLD>
+__global__ void string_backward_ext_kernel(const StrParams p) {
+  extern __shared__ double dsm[];
+  const int b = blockIdx.x, U1 = p.U1;
+  double* b0 = dsm;
+  double* b1 = dsm + U1;
+  double* n0 = dsm + 2 * U1;    // FLD level buffers
+  double* n1 = dsm + 3 * U1;
+  double* ad = dsm + 4 * U1;    // alpha_t
+  const int nf = max(0, min(p.num_frames[b], p.T));
+  const int nl = p.num_labels[b];
+  const float zf = __int_as_float(p.dist_norm_in[2 * b + 1]);
+  const double z = ext_join(p.dist_norm_in[2 * b], zf);
+  const double g = p.grad_dist ? (double)p.grad_dist[b] : 1.0;
+  const bool reachable = (nl >= 0 && nl < U1) && is_finite(zf);
+  const size_t base = (size_t)b * p.T * U1;
+  for (size_t i = (size_t)(reachable ? nf : 0) * U1 + threadIdx.x; i < (size_t)p.T * U1;
+       i += blockDim.x) {
+    p.grad_blank_w[base + i] = 0.f;
+    p.grad_lexical_w[base + i] = 0.f;
+  }
+  if (!reachable) return;
+  for (int u = threadIdx.x; u < U1; u += blockDim.x) b0[u] = (u == nl) ? 0.0 : dneg_inf();
+  __syncthreads();
+  double* beta = b0; double* nxt = b1;
+  for (int t = nf - 1; t >= 0; --t) {
+    const size_t off = base + (size_t)t * U1;
+    const float* bl = p.blank_w + off;
+    const float* lx = p.lexical_w + off;
+    for (int u = threadIdx.x; u < U1; u += blockDim.x)
+      ad[u] = ext_join(p.alpha_exp_in[off + u], p.alphas_in[off + u]);
+    __syncthreads();
+    if constexpr (!FLD) {
+      for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+        const double bn = (u + 1 < U1) ? beta[u + 1] : dneg_inf();
+        const double bb = (double)bl[u] + beta[u];
+        const double lb = (double)lx[u] + bn;
+        p.grad_blank_w[off + u] = (float)(g * exp(ad[u] + bb - z));
+        p.grad_lexical_w[off + u] = (float)(g * exp(ad[u] + lb - z));
+        nxt[u] = dlogaddexp(bb, lb);
+      }
+      __syncthreads();
+    } else {
+      const int k = p.k;
+      double* nb = n0; double* out = n1;
+      for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+        const double bb = (double)bl[u] + beta[u];
+        nb[u] = bb;
+        double acc = 0.0;
+        for (int i = 0; i <= k; ++i) acc += exp(chain_last_d(ad, lx, u, i) + bb - z);
+        p.grad_blank_w[off + u] = (float)(g * acc);
+      }
+      __syncthreads();
+      for (int j = k - 1; j >= 0; --j) {
+        for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+          const double bn = (u + 1 < U1) ? nb[u + 1] : dneg_inf();
+          const double lb = (double)lx[u] + bn;
+          const float gv = (float)(g * exp(chain_last_d(ad, lx, u, j) + lb - z));
+          if (j == k - 1) p.grad_lexical_w[off + u] = gv;
+          else p.grad_lexical_w[off + u] += gv;
+          out[u] = dlogaddexp((double)bl[u] + beta[u], lb);
+        }
+        __syncthreads();
+        double* tmp = nb; nb = out; out = tmp;
+      }
+      for (int u = threadIdx.x; u < U1; u += blockDim.x) nxt[u] = nb[u];
+      __syncthreads();
+    }
+    double* tmp = beta; beta = nxt; nxt = tmp;
+  }
+}
+
 // ------------------------------------------------------------------- launch --
 static int block_for(int U1) {
   int b = 32;
@@ -594,6 +744,22 @@ static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
     return LT_OK;
   }
   const int block = block_for(p.U1);
+  if constexpr (SR == LT_LOG) {
+    if (p.alpha_exp) {                      // double chain, (e, f) storage
+      const size_t dsmem = sizeof(double) * 2 * p.U1;
+      if (p.k >= 1) {
+        LT_CUDA(cudaFuncSetAttribute(string_forward_ext_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+        string_forward_ext_kernel<true><<<p.B, block, dsmem, stream>>>(p);
+      } else {
+        LT_CUDA(cudaFuncSetAttribute(string_forward_ext_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+        string_forward_ext_kernel<false><<<p.B, block, dsmem, stream>>>(p);
+      }
+      LT_LAUNCHED();
+      return LT_OK;
+    }
+  }
   const size_t smem = sizeof(float) * 2 * p.U1;
   if (p.k >= 1) {
     LT_CUDA(cudaFuncSetAttribute(string_forward_kernel<SR, true>,
@@ -628,6 +794,22 @@ static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
     }
   }
   const int block = block_for(p.U1);
+  if constexpr (SR == LT_LOG) {
+    if (p.alpha_exp_in) {
+      const size_t dsmem = sizeof(double) * 5 * p.U1;
+      if (p.k >= 1) {
+        LT_CUDA(cudaFuncSetAttribute(string_backward_ext_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+        string_backward_ext_kernel<true><<<p.B, block, dsmem, stream>>>(p);
+      } else {
+        LT_CUDA(cudaFuncSetAttribute(string_backward_ext_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+        string_backward_ext_kernel<false><<<p.B, block, dsmem, stream>>>(p);
+      }
+      LT_LAUNCHED();
+      return LT_OK;
+    }
+  }
   const size_t smem = sizeof(float) * 4 * p.U1;
   if (p.k >= 1) {
     LT_CUDA(cudaFuncSetAttribute(string_backward_kernel<SR, true>,

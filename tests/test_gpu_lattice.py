@@ -518,13 +518,14 @@ def test_full_size_properties_config1_and_2():
   assert bool((dist <= vd + nf.float() * np.log(1 + vocab) + 1e-2).all())
 
 
+@pytest.mark.parametrize('k', [-1, 2])
 @pytest.mark.parametrize('vocab', [64, 128, 192, 256])
 @pytest.mark.parametrize('semiring', ['log', 'real'])
-def test_backward_split_row_emission(vocab, semiring):
-  """lt_lattice_backward with LT_FLAG_GRAD_SPLIT: every row of grad_lexical holds
-  [V bf16 hi | V bf16 lo] in its V*4 bytes and hi + lo is the fp32 gradient to 2^-17 -- with an
-  odd batch, ragged and empty utterances (zero rows on padding frames) and a non-unit upstream
-  gradient; grad_blank is unchanged."""
+def test_backward_split_row_emission(vocab, semiring, k):
+  """lt_lattice_backward with LT_FLAG_GRAD_SPLIT (FrameDependent and FrameLabelDependent(2) fast
+  paths): every row of grad_lexical holds [V bf16 hi | V bf16 lo] in its V*4 bytes and hi + lo
+  is the fp32 gradient to 2^-17 -- with an odd batch, ragged and empty utterances (zero rows on
+  padding frames) and a non-unit upstream gradient; grad_blank is unchanged."""
   _lt()
   from last_torch_b200 import ops, _native as N
   sr = N.LOG if semiring == 'log' else N.REAL
@@ -537,16 +538,17 @@ def test_backward_split_row_emission(vocab, semiring):
   nf = torch.tensor([t, 6, 0], dtype=torch.int32, device='cuda')
   assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, -1, 0) == 1
   assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 2, -1, 0) == 0
-  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, 2, 0) == 0
-  out = ops._lattice_forward_raw(sr, vocab, 1, -1, blank, lex, nf, 0, False, False)
-  dist, alphas = out[0], out[1]
+  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, 2, 0) == 1
+  assert N.lib().lt_lattice_backward_split_supported(sr, vocab, 1, 4, 0) == 0
+  out = ops._lattice_forward_raw(sr, vocab, 1, k, blank, lex, nf, 0, True, False)
+  dist, alphas, levels = out[0], out[1], out[3]
   gd = torch.tensor([1.0, -0.5, 2.0], device='cuda')
 
   def bwd(flags):
     gb = torch.full_like(blank, 7.0)
     gl = torch.full_like(lex, 7.0)
     N.check(N.lib().lt_lattice_backward(
-        sr, vocab, 1, -1, N.ptr(blank), N.ptr(lex), N.ptr(nf), b, t, N.ptr(alphas), None,
+        sr, vocab, 1, k, N.ptr(blank), N.ptr(lex), N.ptr(nf), b, t, N.ptr(alphas), N.ptr(levels),
         N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, flags, N.stream_ptr(blank.device)),
         'lt_lattice_backward')
     return gb, gl
@@ -559,3 +561,141 @@ def test_backward_split_row_emission(vocab, semiring):
   err = (rec - gl0).abs()
   assert bool((err <= gl0.abs() * 2.0 ** -16 + 1e-37).all()), float(err.max())
   assert float(rec[1, 6:].abs().max()) == 0.0 and float(rec[2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('k', [1, 2, 3])
+@pytest.mark.parametrize('vocab', [64, 192, 256])
+def test_fast_path_frame_label_dependent(vocab, k):
+  """FrameLabelDependent(k) on the bigram fast path (lattice_fast2_fld.cu: the frame's k levels
+  against the resident tile): Log loss + gradients and Real values against the oracle, MaxTropical
+  distance + bit-exact Viterbi path, and everything against the generic kernels
+  (LT_FLD_GENERIC); odd batch, ragged lengths, -inf arcs."""
+  from last_torch_b200 import _native as N
+  lt = _lt()
+  b, t, ctx, u = 3, 9, 1, 5
+  rng = np.random.RandomState(vocab * 10 + k)
+  c = 1 + vocab
+  table_np = (rng.randn(b, t, c, 1 + vocab) * 2.0).astype(np.float32)
+  drop = rng.rand(b, t, c, 1 + vocab) < 0.05
+  drop[..., 0] = False
+  table_np[drop] = -np.inf
+  nf = np.array([9, 4, 7])
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = np.array([5, 2, 3])
+  octx = O.FullNGram(vocab, ctx)
+  tab64 = table_np.astype(np.float64)
+  blank, lex = np.ascontiguousarray(tab64[..., 0]), np.ascontiguousarray(tab64[..., 1:])
+  with np.errstate(all='ignore'):
+    o_loss, o_gb, o_gl = O.lattice_loss_and_grads(blank, lex, nf, labels, nl, octx, k, False)
+    o_vd, o_vgb, o_vgl, o_labels = O.viterbi(table_np[..., 0].copy(), table_np[..., 1:].copy(),
+                                             nf, octx, k, False)
+    o_dist, o_alphas = O.lattice_forward(blank, lex, nf, octx, O.LOG, k, False)
+
+  def run(generic):
+    with N.option('LT_FLD_GENERIC', generic):
+      table = cuda(table_np).requires_grad_()
+      lattice = make_lattice(vocab, ctx, k, table)
+      loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                     num_labels=cuda(nl), cache=None)
+      (gt,) = torch.autograd.grad(
+          torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss)).sum(), table)
+      dist, alphas = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                                      semiring=lt.semirings.Log)
+      vd, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                               semiring=lt.semirings.MaxTropical)
+      (gv,) = torch.autograd.grad(vd.sum(), table)
+      path, num, weights = lattice.shortest_path(frames=frames_for(b, t), num_frames=cuda(nf),
+                                                 cache=None)
+      return [x.detach().cpu().numpy() for x in (loss, gt, dist, alphas, vd, gv, path, weights)]
+
+  fast, gen = run(0), run(1)
+  loss, gt, dist, alphas, vd, gv, path, weights = fast
+  fin = np.isfinite(o_loss)
+  npt.assert_array_equal(np.isfinite(loss), fin)
+  npt.assert_allclose(loss[fin], o_loss[fin], rtol=1e-5, atol=1e-5)
+  assert np.all(np.isfinite(gt)) and np.all(gt[drop] == 0)
+  npt.assert_allclose(gt[fin][..., 0], o_gb[fin], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(gt[fin][..., 1:], o_gl[fin], rtol=1e-4, atol=1e-5)
+  npt.assert_allclose(dist, o_dist, rtol=1e-5, atol=1e-5)
+  afin = np.isfinite(o_alphas)
+  npt.assert_array_equal(np.isfinite(alphas), afin)
+  npt.assert_allclose(alphas[afin], o_alphas[afin], rtol=1e-5, atol=2e-4)
+  npt.assert_allclose(vd, o_vd, rtol=1e-6)
+  npt.assert_array_equal(gv[..., 0], o_vgb)
+  npt.assert_array_equal(gv[..., 1:], o_vgl)
+  npt.assert_array_equal(path, o_labels)
+  npt.assert_allclose(weights, o_vd, rtol=1e-6)
+  # the generic kernels on the same inputs
+  npt.assert_allclose(loss[fin], gen[0][fin], rtol=2e-6, atol=2e-6)
+  npt.assert_allclose(gt, gen[1], rtol=1e-4, atol=2e-6)
+  npt.assert_array_equal(gv, gen[5])
+  npt.assert_array_equal(path, gen[6])
+  # Real semiring on probabilities: values against the oracle, gradient against the generic kernels
+  prob = (np.exp(np.clip(table_np, -40, 5) * 0.25) / (1 + vocab)).astype(np.float32)
+  p64 = prob.astype(np.float64)
+  o_rd, o_ra = O.lattice_forward(np.ascontiguousarray(p64[..., 0]),
+                                 np.ascontiguousarray(p64[..., 1:]), nf, octx, O.REAL, k, False)
+  grads = []
+  for generic in (0, 1):
+    with N.option('LT_FLD_GENERIC', generic):
+      ptab = cuda(prob).requires_grad_()
+      rd, ra = make_lattice(vocab, ctx, k, ptab)._forward(
+          cache=None, frames=frames_for(b, t), num_frames=cuda(nf), semiring=lt.semirings.Real)
+      npt.assert_allclose(rd.detach().cpu(), o_rd, rtol=1e-5)
+      npt.assert_allclose(ra.cpu(), o_ra, rtol=2e-5, atol=1e-30)
+      grads.append(torch.autograd.grad(rd.sum(), ptab)[0].cpu().numpy())
+  npt.assert_allclose(grads[0], grads[1], rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize('k', [1, 2])
+def test_fast_path_frame_label_dependent_ties(k):
+  """All-equal weights: blank terms with fewer expansions win, the lowest source row wins
+  inside a level's reduction (semirings.py:363, :382) -- bit-exact against the oracle."""
+  b, t, vocab, ctx = 2, 5, 64, 1
+  c = 1 + vocab
+  tab = np.zeros([b, t, c, 1 + vocab], np.float32)
+  tab[1, :, :, 0] = -1.0
+  tab[1, :, :, 1:] = 0.25       # utterance 1: expanding pays, every label ties
+  nf = np.array([5, 3])
+  o_vd, o_gb, o_gl, o_labels = O.viterbi(tab[..., 0].copy(), tab[..., 1:].copy(), nf,
+                                         O.FullNGram(vocab, ctx), k, False)
+  table = cuda(tab).requires_grad_()
+  lattice = make_lattice(vocab, ctx, k, table)
+  dist, _ = lattice._forward(cache=None, frames=frames_for(b, t), num_frames=cuda(nf),
+                             semiring=_lt().semirings.MaxTropical)
+  npt.assert_array_equal(dist.detach().cpu(), o_vd)
+  (gd,) = torch.autograd.grad(dist.sum(), table)
+  npt.assert_array_equal(gd.cpu().numpy()[..., 0], o_gb)
+  npt.assert_array_equal(gd.cpu().numpy()[..., 1:], o_gl)
+  path, _, _ = lattice.shortest_path(frames=frames_for(b, t), num_frames=cuda(nf), cache=None)
+  npt.assert_array_equal(path.cpu(), o_labels)
+
+
+def test_fast_path_frame_label_dependent_t300_against_the_double_oracle():
+  """FrameLabelDependent(2), bigram vocab 256, T = 300, ragged: Log loss and ALL gradient entries
+  against the double build of the C oracle (renormalised recursion, double-precision numerator
+  chain: 1e-6 on the loss, 5e-5 relative + 1e-6 absolute on the gradients)."""
+  from oracle import c_oracle
+  b, t, v, k, u = 3, 300, 256, 2, 40
+  rng = np.random.RandomState(21)
+  gen = torch.Generator().manual_seed(212)
+  table = torch.randn([b, t, v + 1, 1 + v], generator=gen)
+  nf = np.array([300, 177, 251])
+  labels = rng.randint(1, v + 1, size=(b, u))
+  nl = np.array([40, 13, 0])
+  tab = table.numpy()
+  loss64, gb64, gl64, _, _ = c_oracle.lattice_loss_and_grads(
+      np.ascontiguousarray(tab[..., 0]), np.ascontiguousarray(tab[..., 1:]), nf, labels, nl, v, 1,
+      k, real='f64')
+  leaf = table.cuda().requires_grad_()
+  lattice = make_lattice(v, 1, k, leaf)
+  loss = lattice(frames=frames_for(b, t), num_frames=cuda(nf), labels=cuda(labels),
+                 num_labels=cuda(nl), cache=None)
+  (gt,) = torch.autograd.grad(loss.sum(), leaf)
+  npt.assert_allclose(loss.detach().cpu().numpy(), loss64, rtol=1e-6)
+  gt = gt.cpu().numpy()
+  # entries on the label string are differences of two O(1) posteriors (denominator minus
+  # numerator): their error is a few fp32 ulps of ONE, whatever is left after the cancellation
+  for got, want in ((gt[..., 0], gb64), (gt[..., 1:], gl64)):
+    assert np.abs(got - want).max() < 1e-5
+    npt.assert_allclose(got, want, rtol=5e-5, atol=1e-6)
