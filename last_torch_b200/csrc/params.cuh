@@ -72,9 +72,9 @@ struct StrParams {
   const int32_t* dist_norm_in;
 };
 // (e, f) kernels exist for the Log semiring: register kernels for FrameDependent with
-// U1 <= 1024, a double-precision chain otherwise (five double arrays of U1 in shared memory)
+// U1 <= 1024, a double-precision chain otherwise (48 bytes of shared memory per label state)
 inline bool string_norm_supported(int semiring, int k, int U1) {
-  return semiring == LT_LOG && U1 >= 1 && (size_t)U1 * 5 * sizeof(double) <= 200 * 1024;
+  return semiring == LT_LOG && U1 >= 1 && (size_t)U1 * 48 <= 200 * 1024;
 }
 
 struct VitParams {

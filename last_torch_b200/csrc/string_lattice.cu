@@ -330,17 +330,22 @@ __global__ void string_backward_kernel(const StrParams p) {
 }
 
 // ---------------------------------------------------------------------------
-// Log chain in DOUBLE with the (integer part, fraction) storage of lt_string_forward_norm, for
-// the shapes the register kernels below do not cover (FrameLabelDependent, U + 1 > 1024).  The
-// label lattice is B x T x (U + 1) values behind a T-long dependency chain -- latency, not
-// throughput -- so fp64 exp / log cost nothing that matters, and every stored quantity keeps
-// ~1e-7 of a unit at |alpha| ~ 1e3 (alpha = e + f, e an exact integer, f in [0, 1)).
+// Log chain with a DOUBLE state and the (integer part, fraction) storage of
+// lt_string_forward_norm, for the shapes the register kernels below do not cover
+// (FrameLabelDependent, U + 1 > 1024).  The state and every sum alpha + w / w + beta are double,
+// so nothing is lost to the numerator's magnitude (|alpha| ~ 1e3 at T = 1000); the
+// transcendental part of a logaddexp only ever sees the O(1) DIFFERENCE of its arguments and is
+// evaluated in float with the accurate expf / log1pf (a few 1e-8 per step, unbiased; the bare
+// MUFU forms accumulate ~1e-5 over k + 1 terms x 300 frames).  One thread
+// per chain state, the frame's weights prefetched into registers one frame ahead, one
+// __syncthreads per frame (state and the frame's lexical weights are double-buffered).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double dneg_inf() { return __longlong_as_double(0xfff0000000000000ll); }
 __device__ __forceinline__ double dlogaddexp(double a, double b) {
   const double c = fmax(a, b);
   if (!(c > dneg_inf())) return c;                  // both are the semiring zero
-  return c + log(exp(a - c) + exp(b - c));
+  const float d = (float)(fmin(a, b) - c);          // <= 0, O(1) where it matters
+  return c + (double)log1pf(expf(d));
 }
 __device__ __forceinline__ void ext_split(double v, int32_t& e, float& f) {
   if (!(v > dneg_inf())) { e = 0; f = neg_inf(); return; }
@@ -360,41 +365,63 @@ __device__ __forceinline__ double chain_last_d(const double* alpha, const float*
   return v;
 }
 
+// shared memory: double a[2][U1]; float lxs[2][U1]
 template <bool FLD>
 __global__ void string_forward_ext_kernel(const StrParams p) {
   extern __shared__ double dsm[];
-  const int b = blockIdx.x, U1 = p.U1;
+  const int b = blockIdx.x, U1 = p.U1, nth = blockDim.x;
   double* a0 = dsm;
   double* a1 = dsm + U1;
+  float* l0 = reinterpret_cast<float*>(dsm + 2 * U1);
+  float* l1 = l0 + U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
-  for (int u = threadIdx.x; u < U1; u += blockDim.x) a0[u] = (u == 0) ? 0.0 : dneg_inf();
-  __syncthreads();
+  const size_t base = (size_t)b * p.T * U1;
+  const bool single = U1 <= nth;                    // one chain state per thread: prefetch
+  const int u1 = threadIdx.x;
+  for (int u = threadIdx.x; u < U1; u += nth) a0[u] = (u == 0) ? 0.0 : dneg_inf();
+  float pb = 0.f, pl = 0.f;
+  if (single && u1 < U1 && nf > 0) { pb = ldg_stream(p.blank_w + base + u1); pl = ldg_stream(p.lexical_w + base + u1); }
   double* cur = a0; double* nxt = a1;
-  for (int t = 0; t < p.T; ++t) {
-    const size_t off = ((size_t)b * p.T + t) * U1;
-    for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+  float* lc = l0; float* ln = l1;
+  for (int t = 0; t < nf; ++t) {
+    const size_t off = base + (size_t)t * U1;
+    const float wb = pb, wl = pl;
+    if (single) {
+      if (u1 < U1) {
+        lc[u1] = wl;
+        if (t + 1 < nf) { pb = ldg_stream(p.blank_w + off + U1 + u1); pl = ldg_stream(p.lexical_w + off + U1 + u1); }
+      }
+    } else {
+      for (int u = threadIdx.x; u < U1; u += nth) lc[u] = p.lexical_w[off + u];
+    }
+    __syncthreads();                                // alpha_t and lexical_t visible
+    for (int u = threadIdx.x; u < U1; u += nth) {
+      int32_t e; float f;
+      ext_split(cur[u], e, f);
+      if (p.alphas) p.alphas[off + u] = f;
+      p.alpha_exp[off + u] = e;
+      const double bu = (double)(single ? wb : p.blank_w[off + u]);
+      if constexpr (!FLD) {
+        const double l = (u > 0) ? cur[u - 1] + (double)lc[u - 1] : dneg_inf();
+        nxt[u] = dlogaddexp(cur[u] + bu, l);
+      } else {
+        double acc = cur[u];
+        for (int i = 1; i <= p.k; ++i) acc = dlogaddexp(acc, chain_last_d(cur, lc, u, i));
+        nxt[u] = acc + bu;
+      }
+    }
+    double* tmp = cur; cur = nxt; nxt = tmp;
+    float* lt = lc; lc = ln; ln = lt;
+  }
+  __syncthreads();
+  for (int t = nf; t < p.T; ++t) {                  // padding frames keep alpha
+    const size_t off = base + (size_t)t * U1;
+    for (int u = threadIdx.x; u < U1; u += nth) {
       int32_t e; float f;
       ext_split(cur[u], e, f);
       if (p.alphas) p.alphas[off + u] = f;
       p.alpha_exp[off + u] = e;
     }
-    if (t >= nf) continue;       // uniform per block
-    const float* bl = p.blank_w + off;
-    const float* lx = p.lexical_w + off;
-    for (int u = threadIdx.x; u < U1; u += blockDim.x) {
-      if constexpr (!FLD) {
-        const double a = cur[u] + (double)bl[u];
-        const double l = (u > 0) ? cur[u - 1] + (double)lx[u - 1] : dneg_inf();
-        nxt[u] = dlogaddexp(a, l);
-      } else {
-        double acc = dneg_inf();
-        const double bu = (double)bl[u];
-        for (int i = 0; i <= p.k; ++i) acc = dlogaddexp(acc, chain_last_d(cur, lx, u, i) + bu);
-        nxt[u] = acc;
-      }
-    }
-    __syncthreads();
-    double* tmp = cur; cur = nxt; nxt = tmp;
   }
   if (threadIdx.x == 0) {
     const int nl = p.num_labels[b];
@@ -407,72 +434,93 @@ __global__ void string_forward_ext_kernel(const StrParams p) {
   }
 }
 
+// shared memory: double beta[2][U1], nb[2][U1], ad[U1]; float lxs[U1], bls[U1]
 template <bool FLD>
 __global__ void string_backward_ext_kernel(const StrParams p) {
   extern __shared__ double dsm[];
-  const int b = blockIdx.x, U1 = p.U1;
+  const int b = blockIdx.x, U1 = p.U1, nth = blockDim.x;
   double* b0 = dsm;
   double* b1 = dsm + U1;
   double* n0 = dsm + 2 * U1;    // FLD level buffers
   double* n1 = dsm + 3 * U1;
   double* ad = dsm + 4 * U1;    // alpha_t
+  float* lxs = reinterpret_cast<float*>(dsm + 5 * U1);
+  float* bls = lxs + U1;
   const int nf = max(0, min(p.num_frames[b], p.T));
   const int nl = p.num_labels[b];
   const float zf = __int_as_float(p.dist_norm_in[2 * b + 1]);
   const double z = ext_join(p.dist_norm_in[2 * b], zf);
-  const double g = p.grad_dist ? (double)p.grad_dist[b] : 1.0;
+  const float g = p.grad_dist ? p.grad_dist[b] : 1.f;
   const bool reachable = (nl >= 0 && nl < U1) && is_finite(zf);
   const size_t base = (size_t)b * p.T * U1;
-  for (size_t i = (size_t)(reachable ? nf : 0) * U1 + threadIdx.x; i < (size_t)p.T * U1;
-       i += blockDim.x) {
+  for (size_t i = (size_t)(reachable ? nf : 0) * U1 + threadIdx.x; i < (size_t)p.T * U1; i += nth) {
     p.grad_blank_w[base + i] = 0.f;
     p.grad_lexical_w[base + i] = 0.f;
   }
   if (!reachable) return;
-  for (int u = threadIdx.x; u < U1; u += blockDim.x) b0[u] = (u == nl) ? 0.0 : dneg_inf();
-  __syncthreads();
+  const bool single = U1 <= nth;
+  const int u1 = threadIdx.x;
+  for (int u = threadIdx.x; u < U1; u += nth) b0[u] = (u == nl) ? 0.0 : dneg_inf();
+  float pb = 0.f, pl = 0.f, pa = 0.f;
+  int32_t pe = 0;
+  auto prefetch = [&](int t) {
+    const size_t o = base + (size_t)t * U1 + u1;
+    pb = ldg_stream(p.blank_w + o); pl = ldg_stream(p.lexical_w + o);
+    pa = p.alphas_in[o]; pe = p.alpha_exp_in[o];
+  };
+  if (single && u1 < U1 && nf > 0) prefetch(nf - 1);
   double* beta = b0; double* nxt = b1;
+  // posterior = exp(exponent): the exponent is formed in double, the exponential in float
+  auto post = [&](double x) { return g * expf((float)x); };
   for (int t = nf - 1; t >= 0; --t) {
     const size_t off = base + (size_t)t * U1;
-    const float* bl = p.blank_w + off;
-    const float* lx = p.lexical_w + off;
-    for (int u = threadIdx.x; u < U1; u += blockDim.x)
-      ad[u] = ext_join(p.alpha_exp_in[off + u], p.alphas_in[off + u]);
-    __syncthreads();
+    if (single) {
+      if (u1 < U1) {
+        ad[u1] = ext_join(pe, pa); lxs[u1] = pl; bls[u1] = pb;
+        if (t > 0) prefetch(t - 1);
+      }
+    } else {
+      for (int u = threadIdx.x; u < U1; u += nth) {
+        ad[u] = ext_join(p.alpha_exp_in[off + u], p.alphas_in[off + u]);
+        lxs[u] = p.lexical_w[off + u];
+        bls[u] = p.blank_w[off + u];
+      }
+    }
+    __syncthreads();                                // beta_{t+1}, alpha_t, weights visible
     if constexpr (!FLD) {
-      for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+      for (int u = threadIdx.x; u < U1; u += nth) {
         const double bn = (u + 1 < U1) ? beta[u + 1] : dneg_inf();
-        const double bb = (double)bl[u] + beta[u];
-        const double lb = (double)lx[u] + bn;
-        p.grad_blank_w[off + u] = (float)(g * exp(ad[u] + bb - z));
-        p.grad_lexical_w[off + u] = (float)(g * exp(ad[u] + lb - z));
+        const double bb = (double)bls[u] + beta[u];
+        const double lb = (double)lxs[u] + bn;
+        p.grad_blank_w[off + u] = post(ad[u] + bb - z);
+        p.grad_lexical_w[off + u] = post(ad[u] + lb - z);
         nxt[u] = dlogaddexp(bb, lb);
       }
       __syncthreads();
     } else {
       const int k = p.k;
       double* nb = n0; double* out = n1;
-      for (int u = threadIdx.x; u < U1; u += blockDim.x) {
-        const double bb = (double)bl[u] + beta[u];
+      for (int u = threadIdx.x; u < U1; u += nth) {
+        const double bb = (double)bls[u] + beta[u];
         nb[u] = bb;
-        double acc = 0.0;
-        for (int i = 0; i <= k; ++i) acc += exp(chain_last_d(ad, lx, u, i) + bb - z);
-        p.grad_blank_w[off + u] = (float)(g * acc);
+        float acc = 0.f;
+        for (int i = 0; i <= k; ++i) acc += post(chain_last_d(ad, lxs, u, i) + bb - z);
+        p.grad_blank_w[off + u] = acc;
       }
       __syncthreads();
       for (int j = k - 1; j >= 0; --j) {
-        for (int u = threadIdx.x; u < U1; u += blockDim.x) {
+        for (int u = threadIdx.x; u < U1; u += nth) {
           const double bn = (u + 1 < U1) ? nb[u + 1] : dneg_inf();
-          const double lb = (double)lx[u] + bn;
-          const float gv = (float)(g * exp(chain_last_d(ad, lx, u, j) + lb - z));
+          const double lb = (double)lxs[u] + bn;
+          const float gv = post(chain_last_d(ad, lxs, u, j) + lb - z);
           if (j == k - 1) p.grad_lexical_w[off + u] = gv;
           else p.grad_lexical_w[off + u] += gv;
-          out[u] = dlogaddexp((double)bl[u] + beta[u], lb);
+          out[u] = dlogaddexp((double)bls[u] + beta[u], lb);
         }
         __syncthreads();
         double* tmp = nb; nb = out; out = tmp;
       }
-      for (int u = threadIdx.x; u < U1; u += blockDim.x) nxt[u] = nb[u];
+      for (int u = threadIdx.x; u < U1; u += nth) nxt[u] = nb[u];
       __syncthreads();
     }
     double* tmp = beta; beta = nxt; nxt = tmp;
@@ -746,7 +794,7 @@ static int string_fwd_sr(const StrParams& p, cudaStream_t stream) {
   const int block = block_for(p.U1);
   if constexpr (SR == LT_LOG) {
     if (p.alpha_exp) {                      // double chain, (e, f) storage
-      const size_t dsmem = sizeof(double) * 2 * p.U1;
+      const size_t dsmem = (sizeof(double) * 2 + sizeof(float) * 2) * p.U1;
       if (p.k >= 1) {
         LT_CUDA(cudaFuncSetAttribute(string_forward_ext_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
@@ -796,7 +844,7 @@ static int string_bwd_sr(const StrParams& p, cudaStream_t stream) {
   const int block = block_for(p.U1);
   if constexpr (SR == LT_LOG) {
     if (p.alpha_exp_in) {
-      const size_t dsmem = sizeof(double) * 5 * p.U1;
+      const size_t dsmem = (sizeof(double) * 5 + sizeof(float) * 2) * p.U1;
       if (p.k >= 1) {
         LT_CUDA(cudaFuncSetAttribute(string_backward_ext_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
