@@ -55,7 +55,7 @@ for kk, name in [(k, f'FrameLabelDependent({k})'), (-1, 'FrameDependent')]:
       ref = ref or {}
       ref[(kk, 'mt')] = out
     print(msg, flush=True)
-    dist, _, alpha_final, _, backptr, termptr = out
+    dist, _, alpha_final, _, backptr, termptr = out[:6]
     labels = torch.empty([B, T, max(kk, 0) + 1], dtype=torch.int32, device='cuda')
     states = torch.empty([B, T + 1], dtype=torch.int32, device='cuda')
 
