@@ -596,6 +596,10 @@ def run_b200(args):
         add(name, lambda: ops._lattice_forward_raw(N.LOG, v, nn, k, bl, lx, xx['nf_d'], 0, False,
                                                    False, norm=True),
             b, t, v, nn, 1.0, frames_done, note)
+      elif mode == 'entropy':
+        bl, lx = xx['blank'].detach(), xx['lexical'].detach()
+        add(name, lambda: ops.lattice_expectation(bl, lx, xx['nf_d'], v, nn, k), b, t, v, nn, 2.0,
+            frames_done, note)
       else:     # MaxTropical shortest distance + Viterbi back-trace
         bl, lx = xx['blank'].detach(), xx['lexical'].detach()
         add(name, lambda: ops.viterbi_path(bl, lx, xx['nf_d'], v, nn, k), b, t, v, nn, 1.0,
@@ -626,6 +630,9 @@ def run_b200(args):
       run_extra('configs[1] Log loss+grad, B=48/GPU', 48, 1000, 256, 1, -1, 120, 'lossgrad')
       run_extra('configs[1] Log forward only, B=32/GPU', 32, 1000, 256, 1, -1, 120, 'forward')
       run_extra('configs[1] Log forward only, B=8/GPU', 8, 1000, 256, 1, -1, 120, 'forward')
+      run_extra('configs[1] geometry, path entropy (expectation semiring by forward-backward, no '
+                'posterior tensor: 2 passes over W), B=32 T=1000', 32, 1000, 256, 1, -1, 120,
+                'entropy')
 
     if world == 1:
       # north_star (4): JointWeightFn fused into the recursion vs joint kernel -> HBM -> K1, at the

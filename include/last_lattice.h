@@ -153,6 +153,27 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size,
                              float* grad_blank, float* grad_lexical,
                              float* beta_final, const int32_t* alpha_norm,
                              unsigned flags, void* stream);
+/* Expected value of an additive arc function under the lattice's path distribution -- what the
+ * first-order expectation semiring (semirings.py:404-484, Expectation / LogLogExpectation) computes
+ * when it is run through the forward recursion, evaluated here by forward-backward in one pass
+ * over the weights and WITHOUT materialising the arc posteriors:
+ *     expect[b] = sum over arcs a of  posterior_b(a) * value(a)
+ * value_blank [B,T,C] / value_lexical [B,T,C,V]; both NULL: value(a) = the arc's own weight, so
+ * that  entropy[b] = logZ[b] - expect[b]  (semirings_test.py:305-324) costs two reads of the
+ * weights and no write.  `alphas`, `dist` (and `alpha_norm`, or NULL) come from
+ * lt_lattice_forward(_norm) on the same weights.  expect_part [B, V/32] doubles: the partial sums
+ * of the V/32 CTAs of an utterance's cluster (sum them; fixed order, bit-reproducible).
+ * Log semiring, lattices with lt_lattice_expectation_supported() == 1 (the bigram TMA fast path);
+ * LT_ERR_UNSUPPORTED otherwise (compose lt_lattice_backward's posteriors with the values). */
+int lt_lattice_expectation_supported(int vocab_size, int context_size, int max_expansions,
+                                     unsigned flags);
+int lt_lattice_expectation(int vocab_size, int context_size, int max_expansions,
+                           const float* blank, const float* lexical, const int32_t* num_frames,
+                           int B, int T, const float* alphas, const float* dist,
+                           const int32_t* alpha_norm, const float* value_blank,
+                           const float* value_lexical, double* expect_part, unsigned flags,
+                           void* stream);
+
 /* alphas[b,t,c] += alpha_norm[b,t] * (unit) in place (the alphas RecognitionLattice._forward
  * returns, lattices.py:496). */
 int lt_alphas_denormalize(float* alphas, const int32_t* alpha_norm, int B, int T, int C,

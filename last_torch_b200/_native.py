@@ -47,6 +47,9 @@ SIGNATURES = {
     'lt_lattice_backward_norm': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_alphas_denormalize': [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr],
+    'lt_lattice_expectation_supported': [_c_int, _c_int, _c_int, _c_uint],
+    'lt_lattice_expectation': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr,
+                               _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_string_norm_supported': [_c_int, _c_int, _c_int],
     'lt_string_forward_norm': [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int,
                                _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
@@ -145,6 +148,7 @@ _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count', 
             'lt_get_option',
             'lt_joint_backward_split_supported', 'lt_lattice_backward_split_supported',
             'lt_lattice_norm_supported', 'lt_string_norm_supported',
+            'lt_lattice_expectation_supported',
             'lt_joint_lattice_fused_supported',
             'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
 

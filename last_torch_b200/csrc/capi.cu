@@ -279,6 +279,49 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
                                          (cudaStream_t)stream);
 }
 
+int lt_lattice_expectation_supported(int vocab_size, int context_size, int max_expansions,
+                                     unsigned flags) {
+  NGram g;
+  if (vocab_size < 1 || context_size < 0 || !make_ngram(vocab_size, context_size, &g)) return 0;
+  return lattice_fast2_supported(g, max_expansions, flags,
+                                 reinterpret_cast<const void*>(uintptr_t(256))) ? 1 : 0;
+}
+
+int lt_lattice_expectation(int vocab_size, int context_size, int max_expansions,
+                           const float* blank, const float* lexical, const int32_t* num_frames,
+                           int B, int T, const float* alphas, const float* dist,
+                           const int32_t* alpha_norm, const float* value_blank,
+                           const float* value_lexical, double* expect_part, unsigned flags,
+                           void* stream) {
+  NGram g;
+  int rc = check_common("lt_lattice_expectation", LT_LOG, vocab_size, context_size, max_expansions,
+                        B, T, &g);
+  if (rc) return rc;
+  LT_CHECK_ARG(num_frames && dist && expect_part, "lt_lattice_expectation: NULL pointer");
+  LT_CHECK_ARG((value_blank == nullptr) == (value_lexical == nullptr),
+               "lt_lattice_expectation: value_blank and value_lexical go together");
+  if (B == 0) return LT_OK;
+  if ((rc = check_arch())) return rc;
+  const int cl = vocab_size / 32;
+  LT_CUDA(cudaMemsetAsync(expect_part, 0, sizeof(double) * (size_t)B * (cl > 0 ? cl : 1),
+                          (cudaStream_t)stream));
+  if (T == 0) return LT_OK;
+  LT_CHECK_ARG(blank && lexical && alphas, "lt_lattice_expectation: NULL weights / alphas");
+  if (!lattice_fast2_supported(g, max_expansions, flags, lexical) ||
+      (value_lexical && reinterpret_cast<uintptr_t>(value_lexical) % 16 != 0)) {
+    set_error("lt_lattice_expectation: no fused kernel for this lattice "
+              "(lt_lattice_expectation_supported); use the arc posteriors of lt_lattice_backward");
+    return LT_ERR_UNSUPPORTED;
+  }
+  BwdParams p = {};
+  p.g = g; p.k = max_expansions; p.B = B; p.T = T;
+  p.blank = blank; p.lexical = lexical; p.num_frames = num_frames;
+  p.alphas = alphas; p.dist = dist; p.alpha_norm = alpha_norm; p.wlevels = 1;
+  p.value_blank = value_blank; p.value_lexical = value_lexical; p.expect_part = expect_part;
+  return lattice_backward_fast2_launch(LT_LOG, g, p, flags & ~LT_FLAG_GRAD_SPLIT,
+                                       (cudaStream_t)stream);
+}
+
 int lt_alphas_denormalize(float* alphas, const int32_t* alpha_norm, int B, int T, int C,
                           void* stream) {
   LT_CHECK_ARG(B >= 0 && T >= 0 && C >= 0, "lt_alphas_denormalize: bad sizes B=%d T=%d C=%d", B, T, C);

@@ -75,6 +75,11 @@ struct Fast2BwdParams {
   int split;             // LT_FLAG_GRAD_SPLIT: rows of [V bf16 hi | V bf16 lo] instead of fp32
   const int32_t* alpha_norm;   // NORM only: written by the NORM forward kernel
   const float* levels;   // FrameLabelDependent only: [B, T, k, C]
+  // EXPECT (lt_lattice_expectation): no gradients are written; every CTA sums
+  // posterior(arc) * value(arc) over its arcs into expect_part[b * CL + rank]
+  const float* value_blank;     // [B, T, C] or nullptr: the arc's own weight
+  const float* value_lexical;   // [B, T, C, V] or nullptr
+  double* expect_part;
 };
 
 // Four consecutive gradients of one row.  fp32: one 16-byte store.  Split rows: the same 16

@@ -378,10 +378,14 @@ lattice_forward_fast2(const __grid_constant__ CUtensorMap tmap, const Fast2FwdPa
 }
 
 // ============================================================= backward (K2) ==
-template <int SR, int V, bool SPLIT, bool NORM>
+// posterior mass e of an arc times its value v; pruned arcs (e == 0) may carry v = -inf
+__device__ __forceinline__ float pv(float e, float v) { return e > 0.f ? e * v : 0.f; }
+
+template <int SR, int V, bool SPLIT, bool NORM, bool EXPECT = false>
 __global__ void __launch_bounds__(kGroupThreads, 2)
 lattice_backward_fast2(const Fast2BwdParams p) {
   static_assert(!NORM || SR == LT_LOG, "renormalisation is a Log-semiring feature");
+  static_assert(!EXPECT || (SR == LT_LOG && !SPLIT), "expectations: Log semiring, no gradient");
   constexpr int G = 1;
   using S = Sr<SR>;
   constexpr int CL = V / kCols;
@@ -451,8 +455,9 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   if (gt == 0)
     for (int it = 0; it < NS && it < nf; ++it) issue(it);
 
+  double eacc = 0.0;                            // EXPECT: this thread's sum of posterior * value
   // padding frames: zero gradients (lattices.py:775-779)
-  if (active) {
+  if (active && !EXPECT) {
     for (int t = nf; t < p.T; ++t) {
       float4* gl = reinterpret_cast<float4*>(p.grad_lexical + (bt0 + t) * (size_t)C * V +
                                              (size_t)rank * kRows * V);
@@ -534,15 +539,24 @@ lattice_backward_fast2(const Fast2BwdParams p) {
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
         const float ms = msafe(m);
         const float rs = scale_ok ? gscale * ex2(alpha_p + ms - zref) : 0.f;
-        float s = 0.f;
+        float s = 0.f, fa = 0.f;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           float4 e;
           e.x = ex2(x[i].x - ms); e.y = ex2(x[i].y - ms);
           e.z = ex2(x[i].z - ms); e.w = ex2(x[i].w - ms);
           s += (e.x + e.y) + (e.z + e.w);
-          store_grad4(grow, (sl + 8 * i) * 4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          if constexpr (EXPECT) {
+            const int c4 = (sl + 8 * i) * 4;
+            const float4 vv = p.value_lexical
+                ? ldg_stream4(p.value_lexical + (bt0 + t) * (size_t)C * V + (size_t)prow * V + c4)
+                : *reinterpret_cast<const float4*>(trow + c4);
+            fa += (pv(e.x, vv.x) + pv(e.y, vv.y)) + (pv(e.z, vv.z) + pv(e.w, vv.w));
+          } else {
+            store_grad4(grow, (sl + 8 * i) * 4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          }
         }
+        if constexpr (EXPECT) { if (rs > 0.f) eacc += (double)(fa * rs); }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -565,7 +579,10 @@ lattice_backward_fast2(const Fast2BwdParams p) {
       if (owner) {
         const float bp = beta[3 + prow];
         const float bb = arc<SR>(c_blank, bp);
-        if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
+        if constexpr (EXPECT) {
+          const float post = scale_ok ? ex2(alpha_p + bb - zref) : 0.f;
+          eacc += (double)pv(post, p.value_blank ? p.value_blank[(bt0 + t) * C + prow] : c_blank);
+        } else if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
         else gb[prow] = gscale * c_alpha * bp;
         xchg_store(nxt, 3 + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum,
                    &xbar[(it + 1) & 1], CL);
@@ -587,7 +604,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float ms = msafe(m);
         const float rs = scale_ok ? gscale * ex2(alpha_p + ms - zref) : 0.f;
-        float s = 0.f;
+        float s = 0.f, fa = 0.f;
         for (int c4 = lane * 4; c4 < V; c4 += 128) {
           const float4 w = *reinterpret_cast<const float4*>(trow + c4);
           const float4 bn = *reinterpret_cast<const float4*>(bnext + c4);
@@ -595,8 +612,15 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           e.x = ex2(arc<SR>(w.x, bn.x) - ms); e.y = ex2(arc<SR>(w.y, bn.y) - ms);
           e.z = ex2(arc<SR>(w.z, bn.z) - ms); e.w = ex2(arc<SR>(w.w, bn.w) - ms);
           s += (e.x + e.y) + (e.z + e.w);
-          store_grad4(grow, c4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          if constexpr (EXPECT) {
+            const float4 vv = p.value_lexical
+                ? ldg_stream4(p.value_lexical + (bt0 + t) * (size_t)C * V + (size_t)V * V + c4) : w;
+            fa += (pv(e.x, vv.x) + pv(e.y, vv.y)) + (pv(e.z, vv.z) + pv(e.w, vv.w));
+          } else {
+            store_grad4(grow, c4, V, split, make_float4(e.x * rs, e.y * rs, e.z * rs, e.w * rs));
+          }
         }
+        if constexpr (EXPECT) { if (rs > 0.f) eacc += (double)(fa * rs); }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         rowsum = ms + __log2f(s);
       } else {
@@ -614,7 +638,10 @@ lattice_backward_fast2(const Fast2BwdParams p) {
       if (lane == 0) {
         const float bp = beta[3 + V];
         const float bb = arc<SR>(c_tblank, bp);
-        if constexpr (SR == LT_LOG) gb[V] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
+        if constexpr (EXPECT) {
+          const float post = scale_ok ? ex2(alpha_p + bb - zref) : 0.f;
+          eacc += (double)pv(post, p.value_blank ? p.value_blank[(bt0 + t) * C + V] : c_tblank);
+        } else if constexpr (SR == LT_LOG) gb[V] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
         else gb[V] = gscale * c_talpha * bp;
         xchg_store(nxt, 3 + V, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum,
                    &xbar[(it + 1) & 1], CL);
@@ -623,6 +650,17 @@ lattice_backward_fast2(const Fast2BwdParams p) {
   }
   float* beta = beta_buf + (nf & 1) * BP;
   if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
+  if constexpr (EXPECT) {
+    __shared__ double esum[kGroupWarps];
+    for (int o = 16; o > 0; o >>= 1) eacc += __shfl_xor_sync(0xffffffffu, eacc, o);
+    if (lane == 0) esum[warp] = eacc;
+    __syncthreads();
+    if (gt == 0 && active) {
+      double tot = 0.0;
+      for (int w = 0; w < kGroupWarps; ++w) tot += esum[w];
+      p.expect_part[(size_t)b * CL + rank] = tot;
+    }
+  }
   if (active && p.beta_final) {
     // NORM: beta_0 = beta~_0 + (off_T - off_0)
     const double boff = NORM ? (double)(an[p.T] - an[0]) : 0.0;
@@ -723,6 +761,23 @@ int lattice_backward_fast2_launch(int semiring, const NGram& g, const BwdParams&
     case 128: LT_BWD2V(SR, 128, NORM)      \
     case 192: LT_BWD2V(SR, 192, NORM)      \
     default: LT_BWD2V(SR, 256, NORM)       \
+  }
+  if (base.expect_part) {       // lt_lattice_expectation: Log only (checked by the caller)
+    p.value_blank = base.value_blank; p.value_lexical = base.value_lexical;
+    p.expect_part = base.expect_part;
+#define LT_EXP2(VV, NORM) \
+  return launch_fast2(lattice_backward_fast2<LT_LOG, VV, false, NORM, true>, grid, kGroupThreads, smem, CL, stream, p);
+#define LT_EXP2V(NORM)                     \
+  switch (V) {                             \
+    case 64: LT_EXP2(64, NORM)             \
+    case 128: LT_EXP2(128, NORM)           \
+    case 192: LT_EXP2(192, NORM)           \
+    default: LT_EXP2(256, NORM)            \
+  }
+    if (p.alpha_norm) { LT_EXP2V(true) }
+    LT_EXP2V(false)
+#undef LT_EXP2V
+#undef LT_EXP2
   }
   if (semiring == LT_LOG && p.alpha_norm) { LT_BWD2(LT_LOG, true) }
   if (semiring == LT_LOG) { LT_BWD2(LT_LOG, false) }

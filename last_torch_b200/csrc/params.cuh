@@ -46,6 +46,10 @@ struct BwdParams {
   float* beta_final;
   const int32_t* alpha_norm;
   int wlevels;           // LT_FLAG_LEVEL_WEIGHTS: weights AND gradients are [.., k + 1, C(, V)]
+  // lt_lattice_expectation (fast path only): sum of posterior * value instead of gradients
+  const float* value_blank;
+  const float* value_lexical;
+  double* expect_part;   // [B, cluster size]
 };
 
 struct StrParams {

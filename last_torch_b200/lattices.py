@@ -416,6 +416,41 @@ class RecognitionLattice(nn.Module, Generic[T]):
           self.kernel_flags)
     return dist.reshape(batch_dims), alphas.reshape(*batch_dims, t, c)
 
+  def expectation(self, frames: torch.Tensor, num_frames: torch.Tensor,
+                  value_blank: Optional[torch.Tensor] = None,
+                  value_lexical: Optional[torch.Tensor] = None, cache: Optional[T] = None):
+    """(log_z, E) with E[b] = the expected total value of a lattice path under the Log-semiring
+    path distribution, for an additive arc value function value_blank [batch_dims..., T, C] /
+    value_lexical [batch_dims..., T, C, V] -- what running the recursion in the expectation
+    semiring (semirings.Expectation / LogLogExpectation, semirings.py:404-484) yields; the
+    reference cannot do that (`torch.where` on tuples in lattices.py:804-806).
+    Without values the arc weights themselves are used (E = expected path weight).
+    No gradients.  E is float64."""
+    batch_dims = self._check_frames(frames, num_frames)
+    if self._is_table():
+      raise NotImplementedError('expectation needs a contexts.FullNGram context')
+    if cache is None:
+      cache = self.build_cache()
+    with torch.no_grad():
+      blank, lexical = self._arc_weights(cache, frames, batch_dims)
+      v, n, k = self._geometry()
+      t, c = blank.shape[1], blank.shape[2]
+      if value_blank is not None:
+        value_blank = torch.broadcast_to(value_blank, (*batch_dims, t, c)).reshape(-1, t, c)
+      if value_lexical is not None:
+        value_lexical = torch.broadcast_to(value_lexical, (*batch_dims, t, c, v)).reshape(-1, t, c, v)
+      log_z, expect = ops.lattice_expectation(
+          blank, lexical, ops._as_i32(num_frames.reshape(-1), blank.device), v, n, k, value_blank,
+          value_lexical, self.kernel_flags)
+    return log_z.reshape(batch_dims), expect.reshape(batch_dims)
+
+  def entropy(self, frames: torch.Tensor, num_frames: torch.Tensor, cache: Optional[T] = None):
+    """Entropy (nats) of the lattice's distribution over alignment paths,
+    H = log Z - E[path weight]: the textbook use of the expectation semiring
+    (semirings_test.py:305-324), in two passes over the arc weights."""
+    log_z, expect = self.expectation(frames, num_frames, cache=cache)
+    return (log_z.double() - expect).float()
+
   def _forward_backward(self, cache: T, frames: torch.Tensor, num_frames: torch.Tensor):
     """Log-semiring shortest distance whose gradient is computed by the
     backward algorithm (lattices.py:498-642).  Returns (log_z, alphas)."""

@@ -6,6 +6,7 @@ arithmetic step below is a hand-written sm_100a kernel.
 
 from __future__ import annotations
 
+import math
 import os
 
 import torch
@@ -146,6 +147,62 @@ def _denormalized(alphas, alpha_norm):
     N.check(N.lib().lt_alphas_denormalize(N.ptr(out), N.ptr(alpha_norm), B, T, C,
                                           N.stream_ptr(out.device)), 'lt_alphas_denormalize')
   return out
+
+
+def lattice_expectation(blank, lexical, num_frames, V, n, k, value_blank=None, value_lexical=None,
+                        flags=0):
+  """(log_z [B], expect [B]), both float64: expect[b] = sum over arcs of posterior_b(arc) * value(arc)
+  under the Log-semiring path distribution of the lattice -- the first-order expectation semiring
+  (semirings.py:404-484) evaluated by forward-backward.  Without values the arc's own weight is
+  used: entropy = log_z - expect.  No gradients flow (inputs are detached).
+
+  On the bigram TMA fast path this is K1 + ONE more pass over the weights with no [B,T,C,V]
+  posterior tensor (lt_lattice_expectation); other lattices compose lt_lattice_backward's
+  posteriors with the values."""
+  blank, lexical = blank.detach(), lexical.detach()
+  B, T, C = blank.shape
+  dev = blank.device
+  if (value_blank is None) != (value_lexical is None):
+    raise ValueError('value_blank and value_lexical go together')
+  if value_blank is not None:
+    value_blank = N.require_cuda(value_blank.detach().float().contiguous(), 'value_blank')
+    value_lexical = N.require_cuda(value_lexical.detach().float().contiguous(), 'value_lexical')
+    if value_blank.shape != blank.shape or value_lexical.shape != lexical.shape:
+      raise ValueError(f'values must have the shapes of the weights {tuple(blank.shape)} / '
+                       f'{tuple(lexical.shape)}; got {tuple(value_blank.shape)} / '
+                       f'{tuple(value_lexical.shape)}')
+  dist, alphas, _, levels, _, _, alpha_norm = _lattice_forward_raw(
+      N.LOG, V, n, k, blank, lexical, num_frames, flags, True, False, norm=True)
+  if B == 0 or T == 0:
+    return dist.double(), torch.zeros([B], dtype=torch.float64, device=dev)
+  log_z = dist.double()
+  if alpha_norm is not None:
+    # logZ = offset + residual: exact in float64 (dist alone is rounded to fp32 at |logZ| ~ 1e3)
+    off = alpha_norm[:, T].double()
+    res = alpha_norm[:, T + 1].contiguous().view(torch.float32).double()
+    unit = torch.where(alpha_norm[:, T + 2] == 0, math.log(2.0), 1.0)
+    log_z = torch.where(torch.isfinite(dist), (off + res) * unit, log_z)
+  if N.lib().lt_lattice_expectation_supported(V, n, k, flags) and lexical.data_ptr() % 16 == 0:
+    part = torch.empty([B, max(V // 32, 1)], dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+      N.check(N.lib().lt_lattice_expectation(
+          V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+          N.ptr(dist), N.ptr(alpha_norm), N.ptr(value_blank), N.ptr(value_lexical), N.ptr(part),
+          flags, N.stream_ptr(dev)), 'lt_lattice_expectation')
+    return log_z, part.sum(-1)
+  gb = torch.empty_like(blank)
+  gl = torch.empty_like(lexical)
+  with torch.cuda.device(dev):
+    N.check(N.lib().lt_lattice_backward_norm(
+        N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
+        N.ptr(levels), N.ptr(dist), None, N.ptr(gb), N.ptr(gl), None, N.ptr(alpha_norm), flags,
+        N.stream_ptr(dev)), 'lt_lattice_backward')
+  vb = blank if value_blank is None else value_blank
+  vl = lexical if value_lexical is None else value_lexical
+  zero = torch.zeros([], device=dev)
+  expect = (torch.where(gb > 0, gb * vb, zero).double().sum((1, 2)) +
+            torch.where(gl > 0, gl * vl, zero).double().sum((1, 2, 3)))
+  return log_z, expect
 
 
 def _check_weights(blank, lexical, V, C):
