@@ -312,11 +312,13 @@ def ncu_traffic(kernel):
   ent = doc.get('kernels', {}).get(kernel)
   if not ent:
     return None, f'{kernel} not in profiles/r02_ncu_traffic.json'
-  src = os.path.join(ROOT, ent['source'])
-  with open(src, 'rb') as f:
-    digest = hashlib.sha256(f.read()).hexdigest()
-  if digest != ent['source_sha256']:
-    return None, (f'{ent["source"]} changed since the capture '
+  sources = ent['source'] if isinstance(ent['source'], list) else [ent['source']]
+  h = hashlib.sha256()
+  for src in sources:
+    with open(os.path.join(ROOT, src), 'rb') as f:
+      h.update(f.read())
+  if h.hexdigest() != ent['source_sha256']:
+    return None, (f'{", ".join(sources)} changed since the capture '
                   f'({doc.get("capture", "profiles/")}): re-profile')
   return float(ent['dram_bytes_per_launch']), doc.get('capture', 'profiles/r02_ncu_traffic.json')
 

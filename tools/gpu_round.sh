@@ -15,7 +15,7 @@ for s in $STEPS; do
     prof)     CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-extras"
               $CMD > gpurun_out/prof_plain.log 2>&1 && \
               ncu --set full --clock-control none --import-source on \
-                  -k regex:"fast2|joint_forward_tc|joint_dgrad2|joint_wgrad_tc" -c 10 \
+                  -k regex:"fast2|joint_forward_t|joint_dgrad2|joint_wgrad_tc" -c 10 \
                   -f -o gpurun_out/r02_prof $CMD > gpurun_out/prof_ncu.log 2>&1; echo "prof rc=$?"; tail -n 3 gpurun_out/prof_ncu.log ;;
     benchlib) # A/B of two builds of the library: default vs $LT_AB_LIB (path relative to the repo root)
               timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_A.json 2> gpurun_out/bench_A.err; echo "bench A rc=$?"

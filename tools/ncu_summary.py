@@ -4,7 +4,8 @@ import csv
 import sys
 
 WANT = [
-    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+    'gpu__time_duration.sum', 'sm__cycles_elapsed.avg.per_second', 'dram__bytes_read.sum',
+    'dram__bytes_write.sum', 'lts__t_sectors_srcunit_tex.sum',
     'lts__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
     'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__grid_size',
     'launch__block_size', 'launch__cluster_dim_x', 'launch__occupancy_limit_shared_mem',

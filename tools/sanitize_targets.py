@@ -9,7 +9,8 @@ script carries its own checks: guard bands around every output buffer of the lat
 comparison of every fast kernel family with the generic kernels.
 
 Families: lattice_fast2 (bigram TMA fast path, plain and renormalised, fp32 and split-row
-gradients), lattice_cols / lattice_rows (context_size 2), the generic cluster kernels,
+gradients, expectation variant), lattice_fast2_fld (FrameLabelDependent on the same path),
+joint_fwd_ts (tensor-memory operand, multicast pairs), lattice_cols / lattice_rows (context_size 2), the generic cluster kernels,
 lattice_table2 (NextStateTable clusters), string_lattice (numerator, plain and (e, f) chain),
 viterbi back-trace, joint_tc forward / wgrad and joint_dgrad2 (tcgen05).  Results are checked
 against the generic kernels so that a sanitizer-induced slowdown cannot hide a wrong answer."""
@@ -171,8 +172,62 @@ def raw_lattice_pair(name, vocab, n, k, b, t, flags=0, repeats=6):
         flush=True)
 
 
+def raw_joint_forward(name, c, vocab, hidden, n, repeats=6):
+  """lt_joint_forward (tanh operand in tensor memory, W_vocab multicast in CTA pairs) on guarded
+  outputs: bit-identical runs (TMEM stages, two TMA rings, multicast commits -- a missed wait
+  changes a tile), equal to the shared-memory-operand kernel."""
+  from last_torch_b200.joint import joint_forward_raw
+  g = torch.Generator(device='cuda').manual_seed(c + n)
+  pc = torch.randn([c, hidden], device='cuda', generator=g)
+  pf = torch.randn([n, hidden], device='cuda', generator=g)
+  wb = torch.randn([1, hidden], device='cuda', generator=g) * 0.3
+  bb = torch.full([], 0.5, device='cuda')
+  wv = torch.randn([vocab, hidden], device='cuda', generator=g) * 0.3
+  bv = torch.randn([vocab], device='cuda', generator=g)
+  L = N.lib()
+  outs = []
+  for _ in range(repeats):
+    blank, c1 = guarded([n, c])
+    lex, c2 = guarded([n, c, vocab])
+    ws = torch.empty([int(L.lt_joint_workspace_bytes(n, c, hidden, vocab))], dtype=torch.uint8,
+                     device='cuda')
+    N.check(L.lt_joint_forward(N.ptr(pc), N.ptr(pf), N.ptr(wb.reshape(-1)), N.ptr(bb.reshape(-1)),
+                               N.ptr(wv), N.ptr(bv), n, c, hidden, vocab, N.ptr(blank), N.ptr(lex),
+                               N.ptr(ws), N.stream_ptr(pc.device)), 'lt_joint_forward')
+    c1(); c2()
+    outs.append((blank.clone(), lex.clone()))
+  for o in outs[1:]:
+    assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]), f'{name}: run-to-run'
+  with N.option('LT_JOINT_FWD_SS', 1):
+    sb, sl = joint_forward_raw(pc, pf, wb, bb, wv, bv)
+  assert torch.equal(sl, outs[0][1]), f'{name}: differs from the shared-memory-operand kernel'
+  assert float((sb - outs[0][0]).abs().max()) < 1e-5
+  print(f'ok {name}: {repeats} bit-identical runs, guard bands intact', flush=True)
+
+
+def expectation_family(vocab, b, t, repeats=4):
+  """lt_lattice_expectation (K2 with posterior x value summed on the fly): bit-identical runs and
+  equal to posteriors x values through the generic kernels."""
+  from last_torch_b200 import ops
+  rng = np.random.RandomState(vocab)
+  blank = torch.tensor(rng.randn(b, t, vocab + 1).astype(np.float32), device='cuda')
+  lex = torch.tensor(rng.randn(b, t, vocab + 1, vocab).astype(np.float32), device='cuda')
+  nf = torch.tensor([t] + [max(0, t - 3 * i) for i in range(1, b)], dtype=torch.int32,
+                    device='cuda')
+  outs = [ops.lattice_expectation(blank, lex, nf, vocab, 1, -1) for _ in range(repeats)]
+  for z, e in outs[1:]:
+    assert torch.equal(z, outs[0][0]) and torch.equal(e, outs[0][1])
+  z2, e2 = ops.lattice_expectation(blank, lex, nf, vocab, 1, -1, flags=1)
+  assert float((outs[0][1] - e2).abs().max()) <= 2e-5 * float(e2.abs().max())
+  print(f'ok lattice expectation vocab {vocab}: {repeats} bit-identical runs', flush=True)
+
+
 def main():
   raw_lattice_pair('lattice_fast2 vocab 256, cluster of 8, 33 utterances', 256, 1, -1, 33, 40)
+  raw_lattice_pair('lattice_fast2_fld FrameLabelDependent(2) vocab 256, 33 utterances', 256, 1, 2,
+                   33, 24)
+  raw_lattice_pair('lattice_fast2_fld FrameLabelDependent(3) vocab 192', 192, 1, 3, 5, 15)
+  raw_lattice_pair('lattice_fast2_fld FrameLabelDependent(1) vocab 64, single CTA', 64, 1, 1, 4, 19)
   raw_lattice_pair('lattice_fast2 vocab 64, single CTA', 64, 1, -1, 5, 23)
   raw_lattice_pair('lattice_fast2 vocab 192, cluster of 6', 192, 1, -1, 7, 17)
   raw_lattice_pair('lattice_cols + lattice_rows vocab 64 context 2 (cluster of 8)', 64, 2, -1, 3, 9)
@@ -186,6 +241,12 @@ def main():
   lattice_family('lattice_cols FrameLabelDependent(2) vocab 16 context 2', 16, 2, 2, 2, 6, 5)
   lattice_family('generic cluster kernels vocab 33', 33, 1, -1, 3, 9, 4)
   table_family()
+  lattice_family('lattice_fast2_fld FrameLabelDependent(2) vocab 128', 128, 1, 2, 3, 9, 4)
+  expectation_family(256, 5, 21)
+  expectation_family(64, 3, 9)
+  raw_joint_forward('joint_fwd_ts vocab 256 hidden 512, 257 states, 1300 frames (multicast pairs)',
+                    257, 256, 512, 1300)
+  raw_joint_forward('joint_fwd_ts vocab 64 hidden 128, 70 states (left-over tiles)', 70, 64, 128, 333)
   joint_family(128, 128, 2, 12)
   joint_family(256, 256, 2, 9)
   print('all sanitizer targets ran', flush=True)
