@@ -16,4 +16,5 @@ if [ -f gpurun_out/r02_prof.ncu-rep ]; then
   python tools/ncu_summary.py profiles/${R}_ncu_summary.csv /tmp/${R}_raw.csv
   python tools/ncu_traffic.py /tmp/${R}_raw.csv "${1:-r02 final capture} (gpurun_out/r02_prof.ncu-rep, ncu --set full --clock-control none of bench.py --steps 1 --warmup 1 --no-cpu --no-extras)"
 fi
+[ -f gpurun_out/r02_launch_list.csv ] && cp gpurun_out/r02_launch_list.csv profiles/${R}_launch_list.csv
 ls -la profiles | grep ${R}_

@@ -1,6 +1,7 @@
 #!/bin/bash
 # One GPU-box session: smoke, GPU tests, parity table, reference suite, bench, sanitizer.
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh [steps...]
+# (`prof` and `launches` each run ncu once, after the same command has run plain: one per session)
 mkdir -p gpurun_out
 STEPS=${@:-smoke tests parity reftests bench sanitize}
 for s in $STEPS; do
@@ -17,6 +18,10 @@ for s in $STEPS; do
               ncu --set full --clock-control none --import-source on \
                   -k regex:"fast2|joint_forward_t|joint_dgrad2|joint_wgrad_tc" -c 10 \
                   -f -o gpurun_out/r02_prof $CMD > gpurun_out/prof_ncu.log 2>&1; echo "prof rc=$?"; tail -n 3 gpurun_out/prof_ncu.log ;;
+    launches) CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-extras"
+              $CMD > gpurun_out/launches_plain.log 2>&1 && \
+              ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+                  --log-file gpurun_out/r02_launch_list.csv $CMD > gpurun_out/launches_ncu.log 2>&1; echo "launches rc=$?" ;;
     benchlib) # A/B of two builds of the library: default vs $LT_AB_LIB (path relative to the repo root)
               timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_A.json 2> gpurun_out/bench_A.err; echo "bench A rc=$?"
               LT_LIBRARY=$PWD/$LT_AB_LIB timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu > gpurun_out/bench_B.json 2> gpurun_out/bench_B.err; echo "bench B rc=$?" ;;
