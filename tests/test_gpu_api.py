@@ -910,3 +910,17 @@ def test_fused_joint_lattice_inference_matches_the_unfused_path(vocab, hidden):
   loss = lattice(frames=x[:2], num_frames=nf[:2], labels=T([[1, 2], [3, 0]]), num_labels=T([2, 1]))
   loss.sum().backward()
   assert lattice.weight_fn.joint_projection_to_vocab.weight.grad is not None
+
+
+def test_example_training_loop_reduces_the_loss():
+  """examples/train_step.py end to end (one GPU): the loss goes down, Viterbi and entropy run."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, os.path.join(root, 'examples', 'train_step.py')],
+                     capture_output=True, text=True, timeout=600,
+                     env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE')})
+  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+  losses = [float(line.split()[-1]) for line in r.stdout.splitlines() if line.startswith('step')]
+  assert len(losses) == 4 and losses[-1] < losses[0], r.stdout
+  assert 'entropy' in r.stdout
