@@ -1,4 +1,4 @@
-"""A complete training loop on the GNAT loss: synthetic utterances, SGD on the JointWeightFn /
+"""A complete training loop on the GNAT loss: synthetic utterances, Adam on the JointWeightFn /
 SharedEmbCacher parameters, optional data parallelism.
 
     python examples/train_step.py                       # one GPU
@@ -39,7 +39,7 @@ def main():
           vocab_size=c.shape()[1], hidden_size=hidden, device=dev, embedding_size=hidden,
           feature_size=feat))
   params = list(lattice.parameters())
-  opt = torch.optim.SGD(params, lr=2e-3)
+  opt = torch.optim.Adam(params, lr=1e-3)
 
   g = torch.Generator(device=dev).manual_seed(1)        # the same GLOBAL batch on every rank
   frames = torch.randn([batch, frames_t, feat], device=dev, generator=g)

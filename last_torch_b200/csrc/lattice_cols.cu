@@ -368,6 +368,32 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
           }
 #pragma unroll
           for (int c = 0; c < CPT; ++c) acc[c].add_chunk(x[c], cm[c]);
+        } else if constexpr (SR == LT_MAXTROPICAL) {
+          // (max, first arg-max row): the row index inside the chunk is an immediate of the
+          // unrolled loop (one select per candidate, no index arithmetic); it is rebased to the
+          // frame's row numbering once per chunk.  Rows ascend, strict '>' keeps the first.
+          float bm[CPT];
+          int br[CPT];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) { bm[c] = acc[c].m; br[c] = -1; }
+#pragma unroll
+          for (int r = 0; r < kMaxR; ++r) {
+            if (r < rows) {
+              float w[CPT];
+              load_w(r, w);
+              const float sv = sp[r * kSrcStride];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) {
+                const float v = sv + w[c];
+                const bool better = v > bm[c];
+                bm[c] = better ? v : bm[c];
+                br[c] = better ? r : br[c];
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CPT; ++c)
+            if (br[c] >= 0) { acc[c].m = bm[c]; acc[c].a = kk0 + br[c]; }
         } else {
           int r = 0;
           for (; r + 4 <= rows; r += 4) {
