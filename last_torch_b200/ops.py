@@ -623,7 +623,7 @@ def _string_forward_raw(sr, k, V, C, blank, lexical, num_frames, states, next_la
 
 
 def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dist, g_dist,
-                     side=None, ready=None, out=None, ext=(None, None)):
+                     side=None, ready=None, out=None, ext=(None, None), no_wait=False):
   """Numerator posteriors on the label lattice: (grad_blank_w, grad_lexical_w).
   `ext` = (alpha_exp, dist_norm) of a lt_string_forward_norm run, or (None, None)."""
   alpha_exp, dist_norm = ext
@@ -631,7 +631,7 @@ def _string_backward(sr, k, bw, lw, num_frames, num_labels, alphas, backptr, dis
   dev = bw.device
   gbw, glw = out if out is not None else (torch.empty_like(bw), torch.empty_like(lw))
   with torch.cuda.device(dev):
-    if side is not None:
+    if side is not None and not no_wait:      # no_wait: `side` already follows the producers
       if ready is not None:
         side.wait_event(ready)
       else:
@@ -760,10 +760,23 @@ def _loss_forward(blank, lexical, num_frames, states, next_labels, num_labels, V
   num, bw, lw, s_alphas, _, ext = strf
   gbw = glw = None
   if need_grad:
-    # posteriors of the label lattice with unit upstream gradient (scaled in backward)
+    # The loss only needs the numerator's VALUE: the current stream joins after K3 forward, and
+    # K3 backward (the unscaled numerator posteriors, unit upstream gradient) runs on the side
+    # stream behind it, under whatever the current stream does next -- normally K2 -- and is
+    # joined by _loss_backward before the scatter.  For FrameDependent it fits under K1 either
+    # way; the FrameLabelDependent chain (double state, k + 1 terms per step) does not.
+    # record_stream: these buffers are in use on `side` beyond this function, the allocator must
+    # not hand them back to the current stream's pool before the side stream is done with them.
+    num_ready = torch.cuda.Event()
+    num_ready.record(side)
+    cur.wait_event(num_ready)
     gbw, glw = _string_backward(N.LOG, k, bw, lw, num_frames, num_labels, s_alphas, None, num,
-                                None, side=side, ready=ready, ext=ext)
-  cur.wait_stream(side)
+                                None, side=side, ext=ext, no_wait=True)
+    for x in (bw, lw, s_alphas, num, gbw, glw, num_frames, num_labels) + tuple(ext):
+      if x is not None:
+        x.record_stream(side)
+  else:
+    cur.wait_stream(side)
   del fwd, strf
   return log_z, num, (alphas, levels, gbw, glw, alpha_norm)
 
@@ -786,6 +799,7 @@ def _loss_backward(blank, lexical, num_frames, log_z, saved, states, next_labels
         N.LOG, V, n, k, N.ptr(blank), N.ptr(lexical), N.ptr(num_frames), B, T, N.ptr(alphas),
         N.ptr(levels), N.ptr(log_z), N.ptr(g_den), N.ptr(gb), N.ptr(gl), None,
         N.ptr(alpha_norm), flags, N.stream_ptr(dev)), 'lt_lattice_backward')
+  torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))   # K3 backward (_loss_forward)
   _string_scatter(V, C, gbw, glw, states, next_labels, 1.0, gb, gl, utt_scale=g_numr,
                   split=split)
   return gb, gl
