@@ -281,6 +281,17 @@ int lt_string_backward_norm(int semiring, int max_expansions, const float* blank
                             const int32_t* alpha_exp, const int32_t* dist_norm,
                             void* stream);
 
+/* ---- the bias-free input projections of JointWeightFn (weight_fns.py:208-211) -----------
+ * y[M,N] = x[M,K] . w[N,K]^T  (nn.Linear(K, N, bias=False)), fp32 FMAs.  The input gradient is
+ * the same call on (gy, w^T); the weight gradient gw[N,K] = gy[M,N]^T . x[M,K] is a two-pass
+ * reduction in a fixed order (bit-reproducible) through a caller-provided workspace of
+ * lt_linear_wgrad_workspace_bytes(M, K, N) bytes. */
+int lt_linear_forward(const float* x, const float* w, float* y, int64_t M, int K, int N,
+                      void* stream);
+int64_t lt_linear_wgrad_workspace_bytes(int64_t M, int K, int N);
+int lt_linear_wgrad(const float* gy, const float* x, float* gw, int64_t M, int K, int N,
+                    void* workspace, void* stream);
+
 /* ---- semiring (+) on arbitrary tensors (semirings.py:202-220, :330-348) ----
  * plus: elementwise on n elements (inputs already broadcast & contiguous).
  * sum: a viewed as [outer, reduce, inner] -> out [outer, inner];

@@ -47,6 +47,9 @@ SIGNATURES = {
     'lt_lattice_backward_norm': [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_alphas_denormalize': [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr],
+    'lt_linear_forward': [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr],
+    'lt_linear_wgrad_workspace_bytes': [_c_i64, _c_int, _c_int],
+    'lt_linear_wgrad': [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr, _ptr],
     'lt_lattice_expectation_supported': [_c_int, _c_int, _c_int, _c_uint],
     'lt_lattice_expectation': [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr,
                                _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
@@ -135,7 +138,8 @@ def lib():
       fn.restype = (ctypes.c_char_p if name == 'lt_last_error' else
                     ctypes.c_ulonglong if name == 'lt_launch_count' else
                     ctypes.c_int64 if name in ('lt_joint_workspace_bytes',
-                                                'lt_joint_backward_workspace_bytes') else _c_int)
+                                                'lt_joint_backward_workspace_bytes',
+                                                'lt_linear_wgrad_workspace_bytes') else _c_int)
     _lib = _TimedLib(handle)
   return _lib
 
@@ -150,7 +154,8 @@ _UNTIMED = ('lt_last_error', 'lt_version', 'lt_device_info', 'lt_launch_count', 
             'lt_lattice_norm_supported', 'lt_string_norm_supported',
             'lt_lattice_expectation_supported',
             'lt_joint_lattice_fused_supported',
-            'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes')
+            'lt_joint_workspace_bytes', 'lt_joint_backward_workspace_bytes',
+            'lt_linear_wgrad_workspace_bytes')
 
 
 # NVTX range per C-ABI call (nsys / ncu --nvtx show the entry point around its kernels); the

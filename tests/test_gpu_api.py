@@ -924,3 +924,58 @@ def test_example_training_loop_reduces_the_loss():
   losses = [float(line.split()[-1]) for line in r.stdout.splitlines() if line.startswith('step')]
   assert len(losses) == 4 and losses[-1] < losses[0], r.stdout
   assert 'entropy' in r.stdout
+
+
+@pytest.mark.parametrize('m,k,n', [(32000, 80, 512), (257, 512, 512), (130, 33, 70), (1, 5, 3),
+                                   (4097, 128, 129)])
+def test_input_projection_kernels_match_torch(m, k, n):
+  """lt_linear_forward / lt_linear_wgrad (the bias-free input projections of JointWeightFn,
+  weight_fns.py:208-211) against torch in float64: values, both gradients, odd shapes."""
+  from last_torch_b200.joint import _Linear
+  g = torch.Generator(device='cuda').manual_seed(m + k + n)
+  x = torch.randn([m, k], device='cuda', generator=g, requires_grad=True)
+  w = (torch.randn([n, k], device='cuda', generator=g) / k ** 0.5).requires_grad_()
+  gy = torch.randn([m, n], device='cuda', generator=g)
+  y = _Linear.apply(x, w)
+  gx, gw = torch.autograd.grad(y, [x, w], gy)
+  xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+  yd = xd @ wd.T
+  gxd, gwd = torch.autograd.grad(yd, [xd, wd], gy.double())
+  for got, want in ((y, yd), (gx, gxd), (gw, gwd)):
+    scale = float(want.abs().max()) + 1e-30
+    assert float((got.double() - want).abs().max()) <= 2e-6 * scale
+  # the weight gradient is reduced in a fixed order: bit-identical from run to run
+  (gw2,) = torch.autograd.grad(_Linear.apply(x, w), [w], gy)
+  assert torch.equal(gw, gw2)
+
+
+def test_own_input_projection_kernels_through_the_lattice(monkeypatch):
+  """LT_OWN_LINEAR: RecognitionLattice.forward + backward with the input projections on
+  lt_linear_forward / lt_linear_wgrad instead of the library GEMM -- same loss and gradients."""
+  lt = _lt()
+  from last_torch_b200 import joint
+
+  def run(own):
+    monkeypatch.setattr(joint, 'OWN_LINEAR', own)
+    torch.manual_seed(21)
+    lattice = lt.RecognitionLattice(
+        context=lt.contexts.FullNGram(vocab_size=64, context_size=1),
+        alignment=lt.alignments.FrameDependent(),
+        weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+            num_context_states=c.shape()[0], embedding_size=40, device='cuda'),
+        weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+            vocab_size=c.shape()[1], hidden_size=128, device='cuda', embedding_size=40,
+            feature_size=24))
+    g = torch.Generator(device='cuda').manual_seed(4)
+    x = torch.randn([3, 17, 24], device='cuda', generator=g)
+    loss = lattice(frames=x, num_frames=T([17, 9, 12]), labels=T([[3, 9, 60], [7, 7, 0], [1, 0, 0]]),
+                   num_labels=T([3, 2, 1]))
+    grads = torch.autograd.grad(loss.sum(), list(lattice.parameters()))
+    return loss.detach(), grads
+
+  l0, g0 = run(False)
+  l1, g1 = run(True)
+  npt.assert_allclose(l1.cpu(), l0.cpu(), rtol=2e-6)
+  for a, b in zip(g1, g0):
+    scale = float(b.abs().max()) + 1e-30
+    assert float((a - b).abs().max()) <= 2e-5 * scale
