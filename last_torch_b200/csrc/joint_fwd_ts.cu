@@ -336,8 +336,10 @@ joint_forward_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
       for (uint32_t it = 0; it < (uint32_t)p.rounds; ++it) {
         const uint32_t u0 = 2 * it, u1 = u0 + 1;
         const uint32_t a0 = u0 % 3, a1 = u1 % 3;
+        // a0 has been free since the tile before last; a1 is the accumulator the epilogue is
+        // draining right now (the previous tile's first half): wait for it only after this
+        // tile's first chunk has been issued for a0
         bar_wait(smem_u32(&tempty[a0]), ((u0 / 3) & 1) ^ 1);
-        bar_wait(smem_u32(&tempty[a1]), ((u1 / 3) & 1) ^ 1);
         umma::fence_after_thread_sync();
         const uint32_t d0 = tmem + a0 * 128, d1 = tmem + a1 * 128;
         for (int kc = 0; kc < nchunks; ++kc, ++g) {
@@ -348,20 +350,43 @@ joint_forward_ts_kernel(const __grid_constant__ CUtensorMap map_hi,
           const uint32_t bh = smem_u32(base) + sb * kBStageBytes;
           const uint32_t bl = bh + 256 * 128;
           const uint32_t half = (uint32_t)Vh * 128;
+          if (kc == 0) {
+            // first chunk: all of a0, then (once the epilogue has let go of it) all of a1
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ah = tmem + kACol + sa * 64 + k * 8, al = ah + 32;
-            const uint64_t dbh0 = umma::make_smem_desc_sw128(bh + k * 32);
-            const uint64_t dbl0 = umma::make_smem_desc_sw128(bl + k * 32);
-            const uint64_t dbh1 = umma::make_smem_desc_sw128(bh + half + k * 32);
-            const uint64_t dbl1 = umma::make_smem_desc_sw128(bl + half + k * 32);
-            const uint32_t acc = (kc | k) > 0;
-            umma::mma_bf16_ts(d0, ah, dbh0, idesc, acc);
-            umma::mma_bf16_ts(d0, ah, dbl0, idesc, 1);
-            umma::mma_bf16_ts(d0, al, dbh0, idesc, 1);
-            umma::mma_bf16_ts(d1, ah, dbh1, idesc, acc);
-            umma::mma_bf16_ts(d1, ah, dbl1, idesc, 1);
-            umma::mma_bf16_ts(d1, al, dbh1, idesc, 1);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = tmem + kACol + sa * 64 + k * 8, al = ah + 32;
+              const uint64_t dbh0 = umma::make_smem_desc_sw128(bh + k * 32);
+              const uint64_t dbl0 = umma::make_smem_desc_sw128(bl + k * 32);
+              umma::mma_bf16_ts(d0, ah, dbh0, idesc, k > 0);
+              umma::mma_bf16_ts(d0, ah, dbl0, idesc, 1);
+              umma::mma_bf16_ts(d0, al, dbh0, idesc, 1);
+            }
+            bar_wait(smem_u32(&tempty[a1]), ((u1 / 3) & 1) ^ 1);
+            umma::fence_after_thread_sync();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = tmem + kACol + sa * 64 + k * 8, al = ah + 32;
+              const uint64_t dbh1 = umma::make_smem_desc_sw128(bh + half + k * 32);
+              const uint64_t dbl1 = umma::make_smem_desc_sw128(bl + half + k * 32);
+              umma::mma_bf16_ts(d1, ah, dbh1, idesc, k > 0);
+              umma::mma_bf16_ts(d1, ah, dbl1, idesc, 1);
+              umma::mma_bf16_ts(d1, al, dbh1, idesc, 1);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = tmem + kACol + sa * 64 + k * 8, al = ah + 32;
+              const uint64_t dbh0 = umma::make_smem_desc_sw128(bh + k * 32);
+              const uint64_t dbl0 = umma::make_smem_desc_sw128(bl + k * 32);
+              const uint64_t dbh1 = umma::make_smem_desc_sw128(bh + half + k * 32);
+              const uint64_t dbl1 = umma::make_smem_desc_sw128(bl + half + k * 32);
+              umma::mma_bf16_ts(d0, ah, dbh0, idesc, 1);
+              umma::mma_bf16_ts(d0, ah, dbl0, idesc, 1);
+              umma::mma_bf16_ts(d0, al, dbh0, idesc, 1);
+              umma::mma_bf16_ts(d1, ah, dbh1, idesc, 1);
+              umma::mma_bf16_ts(d1, ah, dbl1, idesc, 1);
+              umma::mma_bf16_ts(d1, al, dbh1, idesc, 1);
+            }
           }
           if (CS > 1) umma::commit_mc(smem_u32(&empty_b[sb]), all_mask);
           else umma::commit(smem_u32(&empty_b[sb]));
