@@ -263,9 +263,13 @@ lattice_backward_rows(const RowsParams p) {
 //     grad_lex[p,y] (+)= g * exp(src_j[p] + lex[p,y] + nb_{j+1}[next] - logZ),  src_0 = alpha, src_j = last_j
 //     nb_j[p] = blank[p] (x) beta'[p] (+) rowsum_j[p]          (all-gathered, one exchange per pass)
 //   beta_t = nb_0;  grad_blank[q] = g * sum_{i<=k} exp(src_i[q] + blank[q] + beta'[q] - logZ)
-// Three state vectors rotate (beta', and a ping-pong pair for the nb_j); the frame is streamed
-// k times through the same ring (the re-reads hit L2); passes after the first accumulate into
-// grad_lexical.  Exchange e uses barrier e & 1, phase (e >> 1) & 1.
+// Three state vectors (beta', and a pair for the nb_j); the frame is streamed k times through the
+// same ring (the re-reads hit L2).  Exchange e uses barrier e & 1, phase (e >> 1) & 1.
+// k = 2 (RECOMP): the first pass only produces nb_1 and the second one writes the gradient ONCE,
+// recomputing the level-1 posterior of every arc from nb_2 (still in its buffer: beta_t is
+// gathered into beta's own buffer, whose entries a CTA only reads for its own rows) -- one more
+// exponential per arc instead of writing, re-reading and re-writing [B,T,C,V] through HBM.
+// k > 2: passes after the first accumulate into grad_lexical.
 template <int SR, int CHL>
 __global__ void __launch_bounds__(kRThreads, 2)
 lattice_backward_rows_fld(const RowsParams p) {
@@ -358,7 +362,8 @@ lattice_backward_rows_fld(const RowsParams p) {
       if (++q.ch == nchunks) { q.ch = 0; if (--q.j < 0) { q.j = K - 1; ++q.it; } }
       return q;
     };
-    float n_src[2] = {0.f, 0.f}, n_blank[2] = {0.f, 0.f};
+    const bool recomp = K == 2;
+    float n_src[2] = {0.f, 0.f}, n_blank[2] = {0.f, 0.f}, n_lv1[2] = {0.f, 0.f};
     auto prefetch = [&](const Pos& q) {
       if (!owner || q.it >= nf) return;
       const size_t bt = bt0 + (nf - 1 - q.it);
@@ -366,7 +371,11 @@ lattice_backward_rows_fld(const RowsParams p) {
 #pragma unroll
       for (int ps = 0; ps < 2; ++ps) {
         const int row = row0 + q.ch * kRChunk + ps * 32;
-        if (row < p_hi) { n_src[ps] = srcv[row]; n_blank[ps] = ldg_stream(p.blank + bt * C + row); }
+        if (row < p_hi) {
+          n_src[ps] = srcv[row];
+          n_blank[ps] = ldg_stream(p.blank + bt * C + row);
+          if (recomp && q.j == 0) n_lv1[ps] = p.levels[(bt * K) * C + row];
+        }
       }
     };
     Pos pos = {0, K - 1, 0};
@@ -412,9 +421,13 @@ lattice_backward_rows_fld(const RowsParams p) {
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[e & 1]), expect);
         float* grow = p.grad_lexical + (bt * (size_t)C + row0) * V + sl * 4;
         int prow = row0, wrel = wr0;
-        const bool accumulate = j != K - 1;
+        const bool accumulate = !recomp && j != K - 1;
+        const bool store = !recomp || j == 0;        // RECOMP: the gradient is written in pass 0
+        const bool redo1 = recomp && j == 0;         // ... including the level-1 posteriors
+        if (redo1) dst = bp;                         // beta_t goes straight into beta's buffer
         for (int ch = 0; ch < nchunks; ++ch) {
           const float c_src[2] = {n_src[0], n_src[1]}, c_blank[2] = {n_blank[0], n_blank[1]};
+          const float c_lv1[2] = {n_lv1[0], n_lv1[1]};
           pos = advance(pos);
           prefetch(pos);
           mbar_wait(smem_u32(&full[stage]), use & 1);
@@ -437,6 +450,8 @@ lattice_backward_rows_fld(const RowsParams p) {
             }
             const float src_raw = __shfl_sync(0xffffffffu, c_src[ps], lane & ~7);
             const float src_p = to_dom<SR>(src_raw);
+            const float lv1_p = to_dom<SR>(__shfl_sync(0xffffffffu, c_lv1[ps], lane & ~7));
+            const float* bbwin = f1 + kRPad + win + sl * 4;      // nb_K window (RECOMP)
             float rowsum;
             if constexpr (SR == LT_LOG) {
               float m = neg_inf();
@@ -454,11 +469,21 @@ lattice_backward_rows_fld(const RowsParams p) {
                 ev.x = ex2(x[i].x - ms); ev.y = ex2(x[i].y - ms);
                 ev.z = ex2(x[i].z - ms); ev.w = ex2(x[i].w - ms);
                 s += (ev.x + ev.y) + (ev.z + ev.w);
-                if (live) {
+                if (live && store) {
                   float4 gv = make_float4(ev.x * rs, ev.y * rs, ev.z * rs, ev.w * rs);
                   if (accumulate) {
                     const float4 old = *reinterpret_cast<const float4*>(grow + 32 * i);
                     gv.x += old.x; gv.y += old.y; gv.z += old.z; gv.w += old.w;
+                  }
+                  if (redo1 && scale_ok) {
+                    // level 1: exp(last_1[p] + w + nb_2[q] - logZ), the arc's weight re-read
+                    const float4 w = *reinterpret_cast<const float4*>(trow + 32 * i);
+                    const float4 b2 = *reinterpret_cast<const float4*>(bbwin + 32 * i);
+                    const float o = lv1_p - logz2;
+                    gv.x = fmaf(gscale, ex2(arc<SR>(w.x, b2.x) + o), gv.x);
+                    gv.y = fmaf(gscale, ex2(arc<SR>(w.y, b2.y) + o), gv.y);
+                    gv.z = fmaf(gscale, ex2(arc<SR>(w.z, b2.z) + o), gv.z);
+                    gv.w = fmaf(gscale, ex2(arc<SR>(w.w, b2.w) + o), gv.w);
                   }
                   stg_stream4(grow + 32 * i, gv);
                 }
@@ -474,11 +499,17 @@ lattice_backward_rows_fld(const RowsParams p) {
               for (int i = 0; i < CHL; ++i) {
                 const float4 bn = *reinterpret_cast<const float4*>(bwin + 32 * i);
                 s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
-                if (live) {
+                if (live && store) {
                   float4 gv = make_float4(ga * bn.x, ga * bn.y, ga * bn.z, ga * bn.w);
                   if (accumulate) {
                     const float4 old = *reinterpret_cast<const float4*>(grow + 32 * i);
                     gv.x += old.x; gv.y += old.y; gv.z += old.z; gv.w += old.w;
+                  }
+                  if (redo1) {
+                    const float4 b2 = *reinterpret_cast<const float4*>(bbwin + 32 * i);
+                    const float g1 = gscale * lv1_p;
+                    gv.x = fmaf(g1, b2.x, gv.x); gv.y = fmaf(g1, b2.y, gv.y);
+                    gv.z = fmaf(g1, b2.z, gv.z); gv.w = fmaf(g1, b2.w, gv.w);
                   }
                   stg_stream4(grow + 32 * i, gv);
                 }
@@ -505,10 +536,13 @@ lattice_backward_rows_fld(const RowsParams p) {
         ++e;
       }
       // beta_t now (being) gathered in dst; the old beta' and the other vector become scratch
-      float* old = bp;
-      bp = dst;
-      f1 = old;
-      f2 = src;
+      // (RECOMP: dst is beta's own buffer, nothing rotates)
+      if (!recomp) {
+        float* old = bp;
+        bp = dst;
+        f1 = old;
+        f2 = src;
+      }
     }
     if (e > 0) mbar_wait(smem_u32(&xbar[(e - 1) & 1]), (uint32_t)(((e - 1) >> 1) & 1));
     if (p.beta_final)
