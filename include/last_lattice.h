@@ -132,8 +132,10 @@ int lt_lattice_backward(int semiring, int vocab_size, int context_size,
  *              Written by the forward, read by the backward of the same lattice.
  *   alphas     [B,T,C] then holds alpha~_t (natural-log units); the TRUE alpha_t is
  *              alphas[b,t,c] + alpha_norm[b,t] * (u ? 1 : ln 2)  (lt_alphas_denormalize).
- * Only when lt_lattice_norm_supported() returns 1 (Log semiring; the TMA fast path and the generic
- * kernels, i.e. every FullNGram lattice except the context_size >= 2 thread-per-column path);
+ * Only when lt_lattice_norm_supported() returns 1 (Log semiring; the bigram TMA fast path, the
+ * context_size >= 2 thread-per-column forward where its 8-lanes-per-row backward also applies, and
+ * the generic kernels: every FullNGram lattice except thread-per-column shapes whose vocabulary
+ * the row backward does not cover);
  * alpha_norm == NULL selects the plain kernels (identical to lt_lattice_forward / _backward).
  */
 int lt_lattice_norm_supported(int semiring, int vocab_size, int context_size,

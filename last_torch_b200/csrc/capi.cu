@@ -142,9 +142,11 @@ int lattice_norm_family(int semiring, const NGram& g, int k, unsigned flags, con
   if (semiring != LT_LOG) return 0;
   if (lattice_fast2_supported(g, k, flags, lexical)) return 1;
   if (lattice_fast2_fld_supported(g, k, flags, lexical)) return 1;
-  // the thread-per-column forward (context_size >= 2) has no renormalised variant
+  // context_size >= 2: the thread-per-column forward and the 8-lanes-per-row backward share the
+  // fast path's convention (log2 units); a forward without its backward stays plain
   const void* probe = lexical ? lexical : reinterpret_cast<const void*>(uintptr_t(256));
-  if (lattice_cols_supported(g, k, flags, probe)) return 0;
+  if (lattice_cols_supported(g, k, flags, probe))
+    return lattice_rows_supported(g, k, flags, probe, probe) ? 1 : 0;
   return 2;
 }
 }  // namespace lt
@@ -252,7 +254,9 @@ int lt_lattice_backward_norm(int semiring, int vocab_size, int context_size, int
   if (alpha_norm) {
     // the pair must stay inside one kernel family: the offsets' unit differs between them
     const int family = lattice_norm_family(semiring, g, max_expansions, flags, lexical);
-    if (family == 0 || (family == 1 && !fast2)) {
+    const bool rows = !fast2 && !(flags & LT_FLAG_GRAD_SPLIT) &&
+                      lattice_rows_supported(g, max_expansions, flags, lexical, grad_lexical);
+    if (family == 0 || (family == 1 && !fast2 && !rows)) {
       set_error("lt_lattice_backward_norm: `alphas` / `alpha_norm` are renormalised but this "
                 "call cannot take the kernel family that wrote them (16-byte aligned gradients?)");
       return LT_ERR_UNSUPPORTED;

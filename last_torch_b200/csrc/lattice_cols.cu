@@ -23,6 +23,17 @@
 // The A = sum_{i<n} V^i low-order states have at most one incoming arc each and are
 // handled by spare lanes of rank 0.
 //
+// Renormalised state (Log, `alpha_norm` given; same contract as lattice_fast2.cu):
+// alpha_t = alpha~_t + off_t with exact integer offsets in log2 units, off_{t+1} = off_t + D_t,
+// the shift applied where alpha_{t+1} is published.  No CTA holds all of alpha, so the maximum
+// the shift follows is exchanged: at the first level of a frame every warp sends the maximum of
+// the alpha~_t entries it owns to every CTA with the level's own st.async exchange (64 floats per
+// CTA, nothing on the dependency chain) and every warp reduces the 8 CL values after the next
+// wait.  FrameLabelDependent has the maximum of alpha~_t in hand before the frame's last level:
+// D_t = floor(max alpha~_t).  FrameDependent (one level per frame) sees it one frame late and uses
+// D_t = floor(max alpha~_{t-1} / 2): the halved feedback is a damped recursion whose fixed point
+// is max alpha~ = two frames of growth (the undamped one would ring).
+//
 // Reference semantics: lattices.py:436-462, alignments.py:294-297 (FrameDependent),
 // alignments.py:362-376 (FrameLabelDependent), contexts.py:207-230; MaxTropical ties:
 // semirings.py:363 (blank >= lexical), :382 (first arg-max = lowest row block / fewest
@@ -127,6 +138,7 @@ struct ColsParams {
   float* levels;
   int16_t* backptr;
   uint8_t* termptr;
+  int32_t* alpha_norm;   // Log only: [B, T+3] offsets of the renormalised state (fast2.cuh), or nullptr
 };
 
 // Epilogue of one destination for one level (shared by column and low-order destinations).
@@ -181,7 +193,8 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   float* tiles = reinterpret_cast<float*>(csmem);
   float* buf = reinterpret_cast<float*>(csmem + (size_t)NS * stage_bytes);    // [2][SB]
   float* dpart = buf + 2 * SB;                                                // [2 * 8] dist partials
-  uint64_t* full = reinterpret_cast<uint64_t*>(dpart + 16);
+  float* wmx = dpart + 16;                                                    // [2][8 ranks][8 warps] maxima
+  uint64_t* full = reinterpret_cast<uint64_t*>(wmx + 128);
   uint64_t* empty = full + NS;
   uint64_t* xbar = empty + NS;
 
@@ -226,6 +239,9 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   cluster_sync_all();
 
   const long long total_levels = (long long)nf * nlev;
+  const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+  int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
+  int off = 0;                            // off_t (consumers)
 
   if (warp == kConsumers / 32) {
     // ------------------------------------------------------------ producer warp
@@ -305,6 +321,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
 
     int stage = 0;
     uint32_t use = 0;
+    float pend = 0.f;                     // D_t, applied where alpha_{t+1} is published
     for (long long lev = 0; lev < total_levels; ++lev) {
       const int t = (int)(lev / nlev);
       const int level = (int)(lev - (long long)t * nlev);
@@ -312,7 +329,31 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
       const float* src = buf + (lev & 1) * SB;
       const uint32_t dpar = (uint32_t)((lev + 1) & 1);
       if (lev > 0) mbar_wait(smem_u32(&xbar[lev & 1]), (uint32_t)(((lev - 1) >> 1) & 1));
-      if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[dpar]), expect);
+      if (tid == 0)
+        mbar_arrive_expect_tx(smem_u32(&xbar[dpar]), expect + ((norm && level == 0) ? CL * 32u : 0u));
+      if (norm) {
+        if (lev > 0 && (nlev == 1 || level == 1)) {
+          // the warp maxima of alpha~ sent during the previous (first) level have landed
+          const float* wm = wmx + (lev & 1) * 64;
+          float m = lane < (int)CL * 8 ? wm[lane] : neg_inf();
+          if (lane + 32 < (int)CL * 8) m = fmaxf(m, wm[lane + 32]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          pend = norm_shift(nlev == 1 ? 0.5f * m : m);
+        }
+        if (level == 0) {
+          if (rank == 0 && tid == 0) an[t] = off;
+          float m = neg_inf();
+#pragma unroll
+          for (int d = 0; d < ND; ++d)
+            if (dq[d] >= 0) m = fmaxf(m, areg[d]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          if (lane < (int)CL)
+            st_async_f32(map_shared_rank(smem_u32(wmx + dpar * 64 + rank * 8 + warp), lane), m,
+                         map_shared_rank(smem_u32(&xbar[dpar]), lane));
+        }
+      }
       if (level == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) cbl[d] = nbl[d];
@@ -434,10 +475,12 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
           r = S::zero();                                                   // state 0: no incoming arc
           if (q >= g.off) r = Dom<SR>::times(src[LOW0 + (q - g.off) / V], clx[d >= CPT ? d - CPT : 0]);
         }
-        const float v = finish_dest<SR, FLD>(p, bt, q, level, r, arg, areg[d], cbl[d], term[d]);
+        float v = finish_dest<SR, FLD>(p, bt, q, level, r, arg, areg[d], cbl[d], term[d]);
+        if (norm && level + 1 == nlev) v -= pend;           // alpha~_{t+1}: -inf stays -inf
         if (!FLD || level + 1 == nlev) areg[d] = v;
         st_async_f32(raddr[d] + boff, v, rbar[d] + xoff);
       }
+      if (norm && level + 1 == nlev) off += (int)pend;
     }
 
     if (total_levels > 0)
@@ -452,7 +495,9 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
       if (q < 0) continue;
       if (p.alphas)
         for (int t = nf; t < p.T; ++t) p.alphas[(bt0 + t) * C + q] = Dom<SR>::out(areg[d]);
-      if (p.alpha_final) p.alpha_final[(size_t)b * C + q] = Dom<SR>::out(areg[d]);
+      if (p.alpha_final)
+        p.alpha_final[(size_t)b * C + q] =
+            norm ? (float)(((double)areg[d] + (double)off) * 0.6931471805599453) : Dom<SR>::out(areg[d]);
       DAcc<SR> one; one.init(); one.add(areg[d], q);
       part.merge(one);
     }
@@ -469,6 +514,8 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
       }
       part.merge(other);
     }
+    if (norm && rank == 0)
+      for (int t = nf + tid; t <= p.T; t += kConsumers) an[t] = off;
     // warp partials -> rank 0's dpart[rank * ... ] is too small for 8 warps x 8 ranks; reduce
     // inside the CTA through the (now idle) state buffer first
     float* red = buf;                    // nobody reads the state buffers any more
@@ -506,7 +553,15 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
       else { other.s = dpart[2 * r]; }
       tot.merge(other);
     }
-    p.dist[b] = Dom<SR>::out(tot.value());
+    if (norm) {
+      // logZ = (off_T + r) ln 2, rounded once from double; the backward reads the pair
+      const float r = tot.value();
+      an[p.T + 1] = __float_as_int(r);
+      an[p.T + 2] = 0;                   // offsets are in log2 units
+      p.dist[b] = (float)(((double)r + (double)off) * 0.6931471805599453);
+    } else {
+      p.dist[b] = Dom<SR>::out(tot.value());
+    }
   }
 }
 
@@ -551,7 +606,7 @@ static int launch_cols(KernelT kernel, int grid, size_t smem, int cluster, cudaS
 // cluster size / columns per thread for a geometry, or false if the path does not apply
 static size_t cols_fixed_bytes(const NGram& g, int ncol) {
   const int sbuf = (g.K * kSrcStride + g.Alow + 3) & ~3;
-  return sizeof(float) * (2 * (size_t)sbuf + 16) + 8 * (2 * 8 + 2) + 256;
+  return sizeof(float) * (2 * (size_t)sbuf + 16 + 128) + 8 * (2 * 8 + 2) + 256;
 }
 
 static bool cols_geometry(const NGram& g, int* cl, int* cpt) {
@@ -624,6 +679,7 @@ int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdPa
   p.alpha_init = base.alpha_init; p.dist = base.dist; p.alphas = base.alphas;
   p.alpha_final = base.alpha_final; p.levels = base.levels; p.backptr = base.backptr;
   p.termptr = base.termptr;
+  p.alpha_norm = semiring == LT_LOG ? base.alpha_norm : nullptr;
   const int grid = base.B * cl;
   const bool fld = k >= 1;
 #define LT_COLS3(SR, CPTV)                                                                        \

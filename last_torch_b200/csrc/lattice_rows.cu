@@ -15,7 +15,11 @@
 //   * beta lives in shared memory as a full replica per CTA (every CTA's windows wrap over all
 //     N full-order states), double-buffered, all-gathered with st.async + mbarrier
 //     complete_tx: no cluster barrier in the loop; two CTAs of 288 threads per SM.
-// Log arithmetic in log2 units as in lattice_fast2.cu.
+// Log arithmetic in log2 units as in lattice_fast2.cu.  With the renormalised pair of the
+// thread-per-column forward (`alpha_norm`: alphas hold alpha~_t, logZ = off_T + r) beta is kept as
+// beta~_t = beta_t - (off_T - off_t): it follows the forward's own shifts d_t = off_{t+1} - off_t
+// (subtracted where beta_t is published) and every posterior exponent becomes
+// alpha~ + w + beta~ - (r + d_t), all O(10) instead of O(logZ).
 //
 // Reference semantics: alignments.py:300-318, lattices.py:775-779, contexts.py:232-256.
 #include <cuda.h>
@@ -54,6 +58,7 @@ struct RowsParams {
   float* grad_blank;
   float* grad_lexical;
   float* beta_final;
+  const int32_t* alpha_norm;                  // Log: offsets written by the renormalised forward, or nullptr
 };
 
 template <int SR, int CHL>      // CHL = V / 32 float4 chunks per lane
@@ -121,7 +126,10 @@ lattice_backward_rows(const RowsParams p) {
     const int sub = lane >> 3, sl = lane & 7;       // row within the warp pass, lane within the row
     const int rloc = warp * 4 + sub;                // 0 .. 31: row inside a 32-row pass
     const float logz = p.dist[b];
-    const float logz2 = (SR == LT_LOG) ? logz * kLog2e : logz;
+    const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+    const int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
+    const float lz_res = norm ? __int_as_float(an[p.T + 1]) : ((SR == LT_LOG) ? logz * kLog2e : logz);
+    int an_hi = norm ? an[nf] : 0, an_lo = (norm && nf > 0) ? an[nf - 1] : 0;
     const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
     const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
     const bool owner = sl == 0;
@@ -165,6 +173,11 @@ lattice_backward_rows(const RowsParams p) {
       const int t = nf - 1 - it;
       float* beta = beta_buf + (it & 1) * BP;          // beta_{t+1}; entry q at beta[kRPad + q]
       float* nxt = beta_buf + ((it + 1) & 1) * BP;
+      // d_t = off_{t+1} - off_t; the offset of the next frame is fetched a frame ahead
+      const float dsh = (float)(an_hi - an_lo);
+      const float logz2 = lz_res + dsh;
+      an_hi = an_lo;
+      if (norm && t > 0) an_lo = an[t - 1];
       if (it > 0) mbar_wait(smem_u32(&xbar[it & 1]), ((it - 1) >> 1) & 1);
       if (tid == 0) mbar_arrive_expect_tx(smem_u32(&xbar[(it + 1) & 1]), expect);
       float* gb = p.grad_blank + (bt0 + t) * C;
@@ -237,7 +250,7 @@ lattice_backward_rows(const RowsParams p) {
             const float bb = arc<SR>(c_blank[ps], bp);
             if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
             else gb[prow] = gscale * alpha_raw * bp;
-            xchg_store(nxt, kRPad + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
+            xchg_store(nxt, kRPad + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - dsh : bb + rowsum,
                        &xbar[(it + 1) & 1], CL);
           }
         }
@@ -250,7 +263,9 @@ lattice_backward_rows(const RowsParams p) {
     if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
     if (p.beta_final)
       for (int i = tid; i < nrows; i += kRConsumers)
-        p.beta_final[(size_t)b * C + p_lo + i] = from_dom<SR>(beta[kRPad + p_lo + i]);
+        p.beta_final[(size_t)b * C + p_lo + i] =
+            norm ? (float)(((double)beta[kRPad + p_lo + i] + (double)an[p.T]) * 0.6931471805599453)
+                 : from_dom<SR>(beta[kRPad + p_lo + i]);
   }
   __syncthreads();
   cluster_sync_all();
@@ -337,7 +352,10 @@ lattice_backward_rows_fld(const RowsParams p) {
     const int sub = lane >> 3, sl = lane & 7;
     const int rloc = warp * 4 + sub;
     const float logz = p.dist[b];
-    const float logz2 = (SR == LT_LOG) ? logz * kLog2e : logz;
+    const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+    const int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
+    const float lz_res = norm ? __int_as_float(an[p.T + 1]) : ((SR == LT_LOG) ? logz * kLog2e : logz);
+    int an_hi = norm ? an[nf] : 0, an_lo = (norm && nf > 0) ? an[nf - 1] : 0;
     const float gscale = p.grad_dist ? p.grad_dist[b] : 1.f;
     const bool scale_ok = (SR != LT_LOG) || is_finite(logz);
     const bool owner = sl == 0;
@@ -391,6 +409,10 @@ lattice_backward_rows_fld(const RowsParams p) {
     for (int it = 0; it < nf; ++it) {
       const int t = nf - 1 - it;
       const size_t bt = bt0 + t;
+      const float dsh = (float)(an_hi - an_lo);        // d_t = off_{t+1} - off_t
+      const float logz2 = lz_res + dsh;
+      an_hi = an_lo;
+      if (norm && t > 0) an_lo = an[t - 1];
       if (e > 0) mbar_wait(smem_u32(&xbar[(e - 1) & 1]), (uint32_t)(((e - 1) >> 1) & 1));
       // nb_K = blank (x) beta' for ALL states (every CTA keeps a full replica)
       {
@@ -521,7 +543,9 @@ lattice_backward_rows_fld(const RowsParams p) {
             }
             if (owner && live) {
               const float bb = arc<SR>(c_blank[ps], bp[kRPad + prow]);       // blank (x) beta'
-              xchg_store(dst, kRPad + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) : bb + rowsum,
+              // beta~_t = nb_0 - d_t: the shift is applied to the last pass only
+              xchg_store(dst, kRPad + prow,
+                         SR == LT_LOG ? log2_add_exp2(bb, rowsum) - (j == 0 ? dsh : 0.f) : bb + rowsum,
                          &xbar[e & 1], CL);
             }
           }
@@ -547,7 +571,9 @@ lattice_backward_rows_fld(const RowsParams p) {
     if (e > 0) mbar_wait(smem_u32(&xbar[(e - 1) & 1]), (uint32_t)(((e - 1) >> 1) & 1));
     if (p.beta_final)
       for (int i = tid; i < nrows; i += kRConsumers)
-        p.beta_final[(size_t)b * C + p_lo + i] = from_dom<SR>(bp[kRPad + p_lo + i]);
+        p.beta_final[(size_t)b * C + p_lo + i] =
+            norm ? (float)(((double)bp[kRPad + p_lo + i] + (double)an[p.T]) * 0.6931471805599453)
+                 : from_dom<SR>(bp[kRPad + p_lo + i]);
   }
   __syncthreads();
   cluster_sync_all();
@@ -612,6 +638,7 @@ int lattice_backward_rows_launch(int semiring, const NGram& g, const BwdParams& 
   p.blank = base.blank; p.lexical = base.lexical; p.num_frames = base.num_frames;
   p.alphas = base.alphas; p.dist = base.dist; p.grad_dist = base.grad_dist;
   p.grad_blank = base.grad_blank; p.grad_lexical = base.grad_lexical; p.beta_final = base.beta_final;
+  p.alpha_norm = semiring == LT_LOG ? base.alpha_norm : nullptr;
   const int grid = base.B * cl;
   (void)sm_count;
 #define LT_ROWS1(SR, N)                                                                     \

@@ -337,3 +337,34 @@ def joint_lattice_truth_large(g):
       'w_frame': g_pf.reshape(-1, h).T @ frames.reshape(b * t, -1),
   }
   return loss, grads
+
+
+# ------------------------------------------------------------- context_size 2, long utterances --
+
+def trigram_rows(k, vocab=32, t=200, b=2, u=30, tag=''):
+  """Rows (grad_blank, grad_lexical) of a FullNGram(vocab, 2) lattice at T = t against the double
+  build of the C oracle, and the relative error of the loss; k = -1: FrameDependent."""
+  import torch
+  from oracle import c_oracle
+  n = 2
+  c = 1 + vocab + vocab * vocab
+  rng = np.random.RandomState(5)
+  gen = torch.Generator().manual_seed(vocab)
+  table = torch.randn([b, t, c, 1 + vocab], generator=gen)
+  nf = np.array([t] + [int(x) for x in rng.randint(t // 2, t + 1, size=b - 1)])
+  labels = rng.randint(1, vocab + 1, size=(b, u))
+  nl = rng.randint(0, u + 1, size=b)
+  tab = table.numpy()
+  loss64, gb64, gl64, _, _ = c_oracle.lattice_loss_and_grads(
+      np.ascontiguousarray(tab[..., 0]), np.ascontiguousarray(tab[..., 1:]), nf, labels, nl, vocab,
+      n, k, real='f64')
+  leaf = table.cuda().requires_grad_()
+  lattice = table_lattice(vocab, n, k, leaf)
+  loss = lattice(frames=frames_for(b, t), num_frames=_cuda(nf), labels=_cuda(labels),
+                 num_labels=_cuda(nl), cache=None)
+  (gt,) = torch.autograd.grad(loss.sum(), leaf)
+  gt = gt.cpu().numpy()
+  name = f'trigram_v{vocab}_t{t}_' + ('fd' if k < 0 else f'fld{k}') + tag
+  loss_rel = float(np.abs(loss.detach().cpu().numpy() - loss64).max() / np.abs(loss64).max())
+  return [row(name, 'grad_blank', None, gt[..., 0], gb64),
+          row(name, 'grad_lexical', None, gt[..., 1:], gl64)], loss_rel

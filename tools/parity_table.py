@@ -34,6 +34,8 @@ def headline_rows(tag):
     sums = np.concatenate([gpu['grad_frame_sums'][b, :nf[b]] for b in range(len(nf))])
     rows.append({'case': f[:-4] + tag, 'quantity': 'max |sum of the gradient of a real frame| (= 0)',
                  'gpu_abs': float(np.abs(sums).max())})
+  for k in (-1, 2, 3):          # context_size 2 (thread-per-column / row kernels), T = 200
+    rows += P.trigram_rows(k, tag=tag)[0]
   return rows
 
 

@@ -38,18 +38,20 @@ def timeit(fn, reps=5):
 for k, name in [(-1, 'FrameDependent'), (2, 'FrameLabelDependent(2)')]:
   ref = None
   for flags in [0, 1]:
-    out = ops._lattice_forward_raw(N.LOG, V, n, k, blank, lex, nf, flags, k >= 1, False)
-    dist, alphas, _, levels, _, _ = out[:6]
-    fms = timeit(lambda: ops._lattice_forward_raw(N.LOG, V, n, k, blank, lex, nf, flags, k >= 1, False))
+    # renormalised state where the kernels support it (LT_NO_NORM=1: the plain recursion)
+    out = ops._lattice_forward_raw(N.LOG, V, n, k, blank, lex, nf, flags, k >= 1, False, norm=True)
+    dist, alphas, _, levels, _, _, an = out[:7]
+    fms = timeit(lambda: ops._lattice_forward_raw(N.LOG, V, n, k, blank, lex, nf, flags, k >= 1,
+                                                  False, norm=True))
 
     def bwd():
-      N.check(N.lib().lt_lattice_backward(
+      N.check(N.lib().lt_lattice_backward_norm(
           N.LOG, V, n, k, N.ptr(blank), N.ptr(lex), N.ptr(nf), B, T, N.ptr(alphas), N.ptr(levels),
-          N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, flags, N.stream_ptr(blank.device)),
-          'bwd')
+          N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, N.ptr(an), flags,
+          N.stream_ptr(blank.device)), 'bwd')
     bwd()
     bms = timeit(bwd)
-    msg = (f'{name:24s} flags={flags}: forward {fms:8.3f} ms ({W / fms * 1e3:6.0f} GB/s)  '
+    msg = (f'{name:24s} flags={flags} norm={int(an is not None)}: forward {fms:8.3f} ms ({W / fms * 1e3:6.0f} GB/s)  '
            f'backward {bms:8.3f} ms ({2 * W / bms * 1e3:6.0f} GB/s)  frame-sum '
            f'{float(gl[0, T // 2].sum() + gb[0, T // 2].sum()):.5f}')
     if ref is not None:
