@@ -295,7 +295,12 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return v;
 }
 // tanh(a + b) from the factors ea = e^(2a), eb = e^(2b) (joint exponential tables):
-//   tanh = 1 - 2 / (1 + ea * eb): ONE MUFU op (the reciprocal) and three FMA-pipe ops.
+//   tanh = 1 - 2 / (1 + ea * eb): ONE MUFU op (the reciprocal) and two FMA-pipe ops.
+// The product may overflow to +inf (1 / inf = 0: tanh -> 1) or flush to 0 (tanh -> -1) -- that IS
+// the saturated tanh -- so the tables only keep each FACTOR finite and non-zero: exponents clamped
+// to +-126 in log2 units, exact for projections up to |x| = 43.6 each (fp32 tanh has saturated at
+// |a + b| > 9.1; round 1 clamped to +-63 to keep the product normal, which was wrong by up to
+// 0.05 when one projection exceeded 21.8 and the other cancelled it to within 9).
 __device__ __forceinline__ float rcp_1p(float e) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));

@@ -215,7 +215,7 @@ __global__ void joint_exp_table4_kernel(const float* __restrict__ x, float* __re
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i / H), h = (int)(i % H);
     double a = (double)x[i] * 2.8853900817779268;
-    a = a < -63.0 ? -63.0 : (a > 63.0 ? 63.0 : a);
+    a = a < -126.0 ? -126.0 : (a > 126.0 ? 126.0 : a);
     out[((size_t)(h >> 2) * C + c) * 4 + (h & 3)] = (float)exp2(a);
   }
 }

@@ -94,7 +94,7 @@ joint_lattice_forward_fused_kernel(const FusedParams p) {
 
   for (int i = tid; i < C * H; i += nth) {
     float a = p.pc[i] * 2.8853900817779268f;      // e^(2x) = 2^(2 log2(e) x), clamped like the
-    a = fminf(fmaxf(a, -63.f), 63.f);             // tensor-core kernels' tables (joint_tc.cu)
+    a = fminf(fmaxf(a, -126.f), 126.f);             // tensor-core kernels' tables (joint_tc.cu)
     ec[i] = exp2f(a);
   }
   for (int c = tid; c < C; c += nth) {
@@ -124,7 +124,7 @@ joint_lattice_forward_fused_kernel(const FusedParams p) {
     const float* pft = p.pf + (bt0 + t) * H;
     for (int h = tid; h < H; h += nth) {
       float a = pft[h] * 2.8853900817779268f;
-      a = fminf(fmaxf(a, -63.f), 63.f);
+      a = fminf(fmaxf(a, -126.f), 126.f);
       ef[h] = exp2f(a);
     }
     if (p.alphas)

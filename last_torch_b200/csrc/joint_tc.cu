@@ -274,18 +274,19 @@ __device__ __forceinline__ void store_block_coalesced(const float (&v)[32], floa
 }
 
 // Exponential tables of the two projections: out = e^(2x) = 2^(2 log2(e) x), exponent clamped
-// to +-63 so that the product of two entries is always a normal fp32 number.  tanh(pc + pf) then
-// costs one reciprocal: 1 - 2 / (1 + E_c E_f).  Evaluated in double precision (the table is
-// O((C + N) H), the joint is O(N C H)): each entry is correctly rounded, so the product carries
-// ~1.5 ulp -- no worse than rounding the fp32 argument 2 log2(e) (pc + pf) of an ex2.  The clamp
-// only matters for |x| > 21.8, where fp32 tanh has long saturated (|x| > 9.1) unless the OTHER
-// projection cancels it to within 9: both beyond 12.7 with opposite signs.
+// to +-126 so that every entry is a normal, non-zero fp32 number.  tanh(pc + pf) then costs one
+// reciprocal: 1 - 2 / (1 + E_c E_f); the product may overflow or flush to zero, which IS the
+// saturated tanh (common.cuh).  Evaluated in double precision (the table is O((C + N) H), the
+// joint is O(N C H)): each entry is correctly rounded, so the product carries ~1.5 ulp -- no worse
+// than rounding the fp32 argument 2 log2(e) (pc + pf) of an ex2.  The clamp only matters for
+// |x| > 43.6, where fp32 tanh has long saturated (|x| > 9.1) unless the OTHER projection cancels
+// it to within 9: both beyond 34 with opposite signs.
 __global__ void joint_exp_table_kernel(const float* __restrict__ x, float* __restrict__ out,
                                        long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     double a = (double)x[i] * 2.8853900817779268;
-    a = a < -63.0 ? -63.0 : (a > 63.0 ? 63.0 : a);
+    a = a < -126.0 ? -126.0 : (a > 126.0 ? 126.0 : a);
     out[i] = (float)exp2(a);
   }
 }

@@ -127,6 +127,40 @@ def test_joint_forward_tcgen05_matches_fp32(c, v, h, n):
   assert err_b < 1e-5, err_b
 
 
+@pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 40), (65, 64, 128, 9)])
+def test_joint_forward_large_preactivations(c, v, h, n):
+  """Pre-activations of +-20 .. 40 that partly cancel (context projection against frame
+  projection): tanh(pc + pf) must come out of the exponential tables exactly, not from factors
+  clamped so that their product stays normal (the tables clamp at 2^+-126 per factor and let the
+  product overflow / flush inside 1 / (1 + E_c E_f); exact up to |x| = 43.6)."""
+  import last_torch_b200 as lt
+  torch.manual_seed(3 * c + v)
+  fn = lt.weight_fns.JointWeightFn(vocab_size=v, hidden_size=h, device='cuda', embedding_size=48,
+                                   feature_size=40)
+  cache = torch.randn([c, 48], device='cuda')
+  frames = torch.randn([n, 1, 40], device='cuda')
+  with torch.no_grad():
+    # scale both projections so that their entries reach +-38: a few per cent of the (state, frame,
+    # hidden unit) triples then pair a factor beyond 21.8 with a sum inside the unsaturated range
+    pcx = fn.context_projection(cache)
+    pfx = fn.blank_projection(frames[:, 0])
+    fn.context_projection.weight.mul_(38.0 / float(pcx.abs().max()))
+    fn.blank_projection.weight.mul_(38.0 / float(pfx.abs().max()))
+    kb, kl = fn.all_frames(cache, frames)
+    pcx = fn.context_projection(cache).double()
+    pfx = fn.blank_projection(frames[:, 0]).double()
+    assert float(pcx.abs().max()) > 30 and float(pfx.abs().max()) > 30
+    s = pcx[None] + pfx[:, None]
+    # the case the clamp of round 1 got wrong must be present: one factor beyond 21.8, sum small
+    assert int(((pcx[None].abs() > 22) & (s.abs() < 9)).sum()) > 0
+    joint = torch.tanh(s)
+    rl = joint @ fn.joint_projection_to_vocab.weight.double().T + fn.joint_projection_to_vocab.bias.double()
+    rb = joint @ fn.joint_projection_to_blank.weight.double()[0] + fn.joint_projection_to_blank.bias.double()
+  scale = float(rl.abs().max())
+  assert float((kl[:, 0].double() - rl).abs().max()) / scale < 1e-5
+  assert float((kb[:, 0].double() - rb).abs().max()) / max(float(rb.abs().max()), 1e-6) < 1e-5
+
+
 @pytest.mark.parametrize('c,v,h,n', [(257, 256, 512, 40), (65, 64, 128, 9), (130, 128, 256, 17),
                                      (257, 256, 512, 300), (33, 64, 128, 261), (17, 192, 384, 130)])
 def test_joint_backward_tcgen05_matches_autograd(c, v, h, n):
