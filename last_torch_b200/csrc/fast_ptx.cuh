@@ -78,6 +78,17 @@ __device__ __forceinline__ void xchg_store(float* base, int idx, float v, uint64
   for (uint32_t r = 0; r < nrank; ++r)
     st_async_f32(map_shared_rank(a, r), v, map_shared_rank(bb, r));
 }
+// The same all-gather issued by the 8 lanes of a row group (lane `sl` of the group sends to rank
+// `sl`): one shuffle and one store per lane instead of a loop of `nrank` stores on the owner lane.
+// Every lane of the warp must call it (the shuffle is warp-wide); `v` is taken from the group's
+// lane 0, `go` (uniform inside a group) masks groups that have nothing to send.
+__device__ __forceinline__ void xchg_store_group8(float* base, int idx, float v, uint64_t* bar,
+                                                  uint32_t nrank, int lane, bool go) {
+  const float vv = __shfl_sync(0xffffffffu, v, lane & ~7);
+  const uint32_t r = lane & 7;
+  if (go && r < nrank)
+    st_async_f32(map_shared_rank(smem_u32(base + idx), r), vv, map_shared_rank(smem_u32(bar), r));
+}
 
 // The Log-semiring fast kernels keep alpha / beta in LOG2 units on chip:
 //   y = fma(w, log2(e), alpha2)  is one FFMA whose rounding error is the fp32

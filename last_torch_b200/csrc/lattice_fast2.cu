@@ -576,6 +576,7 @@ lattice_backward_fast2(const Fast2BwdParams p) {
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         rowsum = s;
       }
+      float bnew = 0.f;
       if (owner) {
         const float bp = beta[3 + prow];
         const float bb = arc<SR>(c_blank, bp);
@@ -584,9 +585,10 @@ lattice_backward_fast2(const Fast2BwdParams p) {
           eacc += (double)pv(post, p.value_blank ? p.value_blank[(bt0 + t) * C + prow] : c_blank);
         } else if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - zref) : 0.f;
         else gb[prow] = gscale * c_alpha * bp;
-        xchg_store(nxt, 3 + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum,
-                   &xbar[(it + 1) & 1], CL);
+        bnew = SR == LT_LOG ? log2_add_exp2(bb, rowsum) - shift : bb + rowsum;
       }
+      // lane sl of the row group sends the row's new beta to rank sl
+      xchg_store_group8(nxt, 3 + prow, bnew, &xbar[(it + 1) & 1], CL, lane, true);
     }
     if (last_rank && warp == 0) {          // tail row: source state V, all 32 lanes
       const float* trow = tile + (size_t)kRows * V;

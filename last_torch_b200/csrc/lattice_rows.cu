@@ -245,14 +245,16 @@ lattice_backward_rows(const RowsParams p) {
             s += __shfl_xor_sync(0xffffffffu, s, 4);
             rowsum = s;
           }
+          float bnew = 0.f;
           if (owner && live) {
             const float bp = beta[kRPad + prow];
             const float bb = arc<SR>(c_blank[ps], bp);
             if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz2) : 0.f;
             else gb[prow] = gscale * alpha_raw * bp;
-            xchg_store(nxt, kRPad + prow, SR == LT_LOG ? log2_add_exp2(bb, rowsum) - dsh : bb + rowsum,
-                       &xbar[(it + 1) & 1], CL);
+            bnew = SR == LT_LOG ? log2_add_exp2(bb, rowsum) - dsh : bb + rowsum;
           }
+          // lane sl of the row group sends the row's new beta to rank sl
+          xchg_store_group8(nxt, kRPad + prow, bnew, &xbar[(it + 1) & 1], CL, lane, live);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_r(smem_u32(&empty[stage]));
@@ -541,13 +543,13 @@ lattice_backward_rows_fld(const RowsParams p) {
               s += __shfl_xor_sync(0xffffffffu, s, 4);
               rowsum = s;
             }
+            float bnew = 0.f;
             if (owner && live) {
               const float bb = arc<SR>(c_blank[ps], bp[kRPad + prow]);       // blank (x) beta'
               // beta~_t = nb_0 - d_t: the shift is applied to the last pass only
-              xchg_store(dst, kRPad + prow,
-                         SR == LT_LOG ? log2_add_exp2(bb, rowsum) - (j == 0 ? dsh : 0.f) : bb + rowsum,
-                         &xbar[e & 1], CL);
+              bnew = SR == LT_LOG ? log2_add_exp2(bb, rowsum) - (j == 0 ? dsh : 0.f) : bb + rowsum;
             }
+            xchg_store_group8(dst, kRPad + prow, bnew, &xbar[e & 1], CL, lane, live);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_r(smem_u32(&empty[stage]));
