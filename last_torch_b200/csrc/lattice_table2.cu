@@ -540,14 +540,16 @@ table_backward2_kernel(const TableParams p, const int R, const int NS) {
           rowv = s;
         }
       }
+      float bnew = 0.f;
       if (sl == 0 && live) {
         const float bp = beta[prow];
         const float bb = arc<SR>(k_own, bp);
         if constexpr (SR == LT_LOG) gb[prow] = scale_ok ? gscale * ex2(alpha_p + bb - logz_d) : 0.f;
         else gb[prow] = gscale * a_own * bp;
-        xchg_store(nxt, prow, SR == LT_LOG ? log2_add_exp2(bb, rowv) : bb + rowv,
-                   &xbar[(it + 1) & 1], CL);
+        bnew = SR == LT_LOG ? log2_add_exp2(bb, rowv) : bb + rowv;
       }
+      // lane sl of the row group sends the row's new beta to rank sl (cluster size <= 8)
+      xchg_store_group8(nxt, prow, bnew, &xbar[(it + 1) & 1], CL, lane, live);
     }
   }
   if (nf > 0) mbar_wait(smem_u32(&xbar[nf & 1]), ((nf - 1) >> 1) & 1);
