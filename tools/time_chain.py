@@ -48,8 +48,20 @@ for B, ragged in CASES:
         N.ptr(dist), N.ptr(gd), N.ptr(gb), N.ptr(gl), None, N.ptr(an), 0,
         N.stream_ptr(blank.device)), 'bwd')
   k = timeit(bwd)
+  # alternating K1, K2 (as in a training step, nothing else running): per-kernel CUDA events
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * 10)]
+  for i in range(10):
+    ev[3 * i].record()
+    ops._lattice_forward_raw(N.LOG, V, 1, -1, blank, lex, nf, 0, False, False, norm=True)
+    ev[3 * i + 1].record()
+    bwd()
+    ev[3 * i + 2].record()
+  torch.cuda.synchronize()
+  fa = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(2, 10)) / 8
+  ka = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(2, 10)) / 8
   real = float(nf.sum()) * C
   print(f'B={B:3d} ragged={int(ragged)}: forward {f:6.3f} ms  backward {k:6.3f} ms  '
-        f'{real / (f + k) / 1e6:7.1f} G real frames*states/s (K1+K2)  dist[0]={float(dist[0]):.4f}',
+        f'{real / (f + k) / 1e6:7.1f} G real frames*states/s (K1+K2)  alternating: {fa:6.3f} / {ka:6.3f} ms  '
+        f'dist[0]={float(dist[0]):.4f}',
         flush=True)
   del blank, lex, gb, gl
