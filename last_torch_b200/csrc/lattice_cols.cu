@@ -30,9 +30,10 @@
 // the alpha~_t entries it owns to every CTA with the level's own st.async exchange (64 floats per
 // CTA, nothing on the dependency chain) and every warp reduces the 8 CL values after the next
 // wait.  FrameLabelDependent has the maximum of alpha~_t in hand before the frame's last level:
-// D_t = floor(max alpha~_t).  FrameDependent (one level per frame) sees it one frame late and uses
-// D_t = floor(max alpha~_{t-1} / 2): the halved feedback is a damped recursion whose fixed point
-// is max alpha~ = two frames of growth (the undamped one would ring).
+// D_t = floor(max alpha~_t).  FrameDependent (one level per frame) sees it one frame late and
+// predicts: the shift cancels the growth last observed in full and half of the level it expects
+// (see the loop), which keeps max |alpha~| within about one frame of growth; plain feedback of the
+// late maximum would ring, half of it settles at two frames of growth.
 //
 // Reference semantics: lattices.py:436-462, alignments.py:294-297 (FrameDependent),
 // alignments.py:362-376 (FrameLabelDependent), contexts.py:207-230; MaxTropical ties:
@@ -174,7 +175,7 @@ __device__ __forceinline__ float finish_dest(const ColsParams& p, size_t bt, int
   }
 }
 
-template <int SR, int CPT, bool FLD>
+template <int SR, int CPT, bool FLD, bool NORM>
 __global__ void __launch_bounds__(kColsThreads, 2)
 lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams p) {
   using S = Sr<SR>;
@@ -239,7 +240,8 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
   cluster_sync_all();
 
   const long long total_levels = (long long)nf * nlev;
-  const bool norm = SR == LT_LOG && p.alpha_norm != nullptr;
+  static_assert(!NORM || SR == LT_LOG, "renormalisation is a Log-semiring feature");
+  constexpr bool norm = NORM;             // compile-time: the plain kernels carry none of it
   int32_t* an = norm ? p.alpha_norm + (size_t)b * (p.T + 3) : nullptr;
   int off = 0;                            // off_t (consumers)
 
@@ -322,6 +324,7 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
     int stage = 0;
     uint32_t use = 0;
     float pend = 0.f;                     // D_t, applied where alpha_{t+1} is published
+    [[maybe_unused]] float m_prev = 0.f, d_prev = 0.f, d_prev2 = 0.f;   // M_{t-2}, D_{t-1}, D_{t-2} (FrameDependent)
     for (long long lev = 0; lev < total_levels; ++lev) {
       const int t = (int)(lev / nlev);
       const int level = (int)(lev - (long long)t * nlev);
@@ -339,7 +342,22 @@ lattice_forward_cols(const __grid_constant__ CUtensorMap tmap, const ColsParams 
           if (lane + 32 < (int)CL * 8) m = fmaxf(m, wm[lane + 32]);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          pend = norm_shift(nlev == 1 ? 0.5f * m : m);
+          if constexpr (FLD) {
+            pend = norm_shift(m);                       // m = max alpha~_t: no lag (k >= 2), or ...
+            if (nlev == 1) pend = norm_shift(0.5f * m); // ... k = 1: one frame late, damped
+          } else {
+            // m = M_{t-1}, one frame late.  M_{t+1} = M_t + G_t - D_t with G the growth of the
+            // maximum; predict M_t = M_{t-1} + G^ - D_{t-1} and G_t = G^ from the last observed
+            // growth G^ = M_{t-1} - M_{t-2} + D_{t-2}, cancel the growth fully and the predicted
+            // level by half (the half damps the prediction error instead of echoing it)
+            float raw = 0.5f * m;
+            if (t >= 3 && is_finite(m) && is_finite(m_prev)) {
+              const float ghat = m - m_prev + d_prev2;
+              raw = fmaf(0.5f, m - d_prev + ghat, ghat);
+            }
+            pend = norm_shift(raw);
+            m_prev = m; d_prev2 = d_prev; d_prev = pend;
+          }
         }
         if (level == 0) {
           if (rank == 0 && tid == 0) an[t] = off;
@@ -682,17 +700,20 @@ int lattice_forward_cols_launch(int semiring, const NGram& g, int k, const FwdPa
   p.alpha_norm = semiring == LT_LOG ? base.alpha_norm : nullptr;
   const int grid = base.B * cl;
   const bool fld = k >= 1;
-#define LT_COLS3(SR, CPTV)                                                                        \
-  return fld ? launch_cols(lattice_forward_cols<SR, CPTV, true>, grid, smem, cl, stream, tmap, p) \
-             : launch_cols(lattice_forward_cols<SR, CPTV, false>, grid, smem, cl, stream, tmap, p);
-#define LT_COLS2(SR)                  \
-  switch (cpt) {                      \
-    case 1: LT_COLS3(SR, 1)           \
-    default: LT_COLS3(SR, 2)          \
+#define LT_COLS3(SR, CPTV, NORM)                                                             \
+  return fld ? launch_cols(lattice_forward_cols<SR, CPTV, true, NORM>, grid, smem, cl, stream, \
+                           tmap, p)                                                            \
+             : launch_cols(lattice_forward_cols<SR, CPTV, false, NORM>, grid, smem, cl, stream, \
+                           tmap, p);
+#define LT_COLS2(SR, NORM)               \
+  switch (cpt) {                         \
+    case 1: LT_COLS3(SR, 1, NORM)        \
+    default: LT_COLS3(SR, 2, NORM)       \
   }
-  if (semiring == LT_LOG) { LT_COLS2(LT_LOG) }
-  if (semiring == LT_MAXTROPICAL) { LT_COLS2(LT_MAXTROPICAL) }
-  LT_COLS2(LT_REAL)
+  if (semiring == LT_LOG && p.alpha_norm) { LT_COLS2(LT_LOG, true) }
+  if (semiring == LT_LOG) { LT_COLS2(LT_LOG, false) }
+  if (semiring == LT_MAXTROPICAL) { LT_COLS2(LT_MAXTROPICAL, false) }
+  LT_COLS2(LT_REAL, false)
 #undef LT_COLS2
 #undef LT_COLS3
 }

@@ -341,7 +341,7 @@ def joint_lattice_truth_large(g):
 
 # ------------------------------------------------------------- context_size 2, long utterances --
 
-def trigram_rows(k, vocab=32, t=200, b=2, u=30, tag=''):
+def trigram_rows(k, vocab=32, t=200, b=2, u=30, tag='', scale=1.0):
   """Rows (grad_blank, grad_lexical) of a FullNGram(vocab, 2) lattice at T = t against the double
   build of the C oracle, and the relative error of the loss; k = -1: FrameDependent."""
   import torch
@@ -350,7 +350,7 @@ def trigram_rows(k, vocab=32, t=200, b=2, u=30, tag=''):
   c = 1 + vocab + vocab * vocab
   rng = np.random.RandomState(5)
   gen = torch.Generator().manual_seed(vocab)
-  table = torch.randn([b, t, c, 1 + vocab], generator=gen)
+  table = torch.randn([b, t, c, 1 + vocab], generator=gen) * scale
   nf = np.array([t] + [int(x) for x in rng.randint(t // 2, t + 1, size=b - 1)])
   labels = rng.randint(1, vocab + 1, size=(b, u))
   nl = rng.randint(0, u + 1, size=b)

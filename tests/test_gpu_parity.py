@@ -198,3 +198,17 @@ def test_trigram_v32_t200_against_the_double_oracle(k):
   assert loss_rel < 1e-6
   for r in rows:
     assert r['gpu_abs'] < 2e-5, r
+
+
+@pytest.mark.parametrize('k', [-1, 2])
+def test_trigram_v32_t200_wide_weights_against_the_double_oracle(k):
+  """The same lattices with weights ~ N(0, 8^2): alpha grows by ~45 log2 units per frame, which is
+  what the one-frame-late, predicted shift of the FrameDependent kernel has to follow without
+  ringing (lattice_cols.cu: measured 1.0e-5 absolute; half-weight feedback of the late maximum
+  gave 2.6e-5).  FrameLabelDependent(2) shifts once per frame, so its level vectors sit up to two
+  such steps above the shifted alpha and fp32 resolves their sums to ~7e-5 (gradients up to 2)."""
+  rows, loss_rel = P.trigram_rows(k, scale=8.0)
+  _show([dict(r, reference_fp32_abs=float('nan'), reference_fp32_rel=float('nan')) for r in rows])
+  assert loss_rel < 1e-6
+  for r in rows:
+    assert r['gpu_abs'] < (2e-5 if k < 0 else 1.5e-4), r
