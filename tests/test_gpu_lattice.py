@@ -140,6 +140,8 @@ ORACLE_CASES = [
     (15, 2, 5, 64, 2, -1, 5, 2.0),       # configs[2] width, cluster of 8, FrameDependent
     (16, 3, 8, 8, 3, 2, 6, 1.0),         # thread-per-column path, 4-gram states (n=3), cluster of 2
     (17, 3, 9, 32, 2, -1, 5, 1.5),       # cols forward + 8-lanes-per-row backward, C = 1057
+    (18, 2, 40, 32, 2, 1, 8, 1.0),       # same kernels, FLD(1): one level per frame, late shift
+    (19, 2, 60, 32, 2, -1, 9, 6.0),      # same kernels, wide weights over 60 frames
 ]
 
 
