@@ -284,15 +284,23 @@ int lt_string_backward_norm(int semiring, int max_expansions, const float* blank
                             void* stream);
 
 /* ---- the bias-free input projections of JointWeightFn (weight_fns.py:208-211) -----------
- * y[M,N] = x[M,K] . w[N,K]^T  (nn.Linear(K, N, bias=False)), fp32 FMAs.  The input gradient is
- * the same call on (gy, w^T); the weight gradient gw[N,K] = gy[M,N]^T . x[M,K] is a two-pass
- * reduction in a fixed order (bit-reproducible) through a caller-provided workspace of
- * lt_linear_wgrad_workspace_bytes(M, K, N) bytes. */
+ * y[M,N] = x[M,K] . w[N,K]^T  (nn.Linear(K, N, bias=False)).  The input gradient is the same
+ * call on (gy, w^T); the weight gradient gw[N,K] = gy[M,N]^T . x[M,K] is a two-pass reduction in
+ * a fixed order (bit-reproducible) through a caller-provided workspace of
+ * lt_linear_wgrad_workspace_bytes(M, K, N) bytes.  Large 64-aligned products run on tcgen05
+ * tensor cores (bf16x3 operand split, ~2^-17 relative, fp32 accumulation in tensor memory; forward:
+ * M >= 128, K % 64 == 0, N % 16 == 0; weight gradient: M >= 1024, N % 128 == 0, K % 64 == 0;
+ * 16-byte aligned buffers), everything else on fp32 FMAs. */
 int lt_linear_forward(const float* x, const float* w, float* y, int64_t M, int K, int N,
                       void* stream);
 int64_t lt_linear_wgrad_workspace_bytes(int64_t M, int K, int N);
 int lt_linear_wgrad(const float* gy, const float* x, float* gw, int64_t M, int K, int N,
                     void* workspace, void* stream);
+/* 1 when both calls above run on tcgen05 tensor cores for this shape (bf16x3 operand split, fp32
+ * accumulation; K % 64 == 0, N % 128 == 0) AND the product is large enough (M >= 4096) for that
+ * to beat an fp32 FMA GEMM -- the host side then routes the projection here instead of to the
+ * library sgemm behind nn.Linear (LT_LINEAR_SIMT=1 keeps the CUDA-core kernels). */
+int lt_linear_tensor_core(int64_t M, int K, int N);
 
 /* ---- semiring (+) on arbitrary tensors (semirings.py:202-220, :330-348) ----
  * plus: elementwise on n elements (inputs already broadcast & contiguous).

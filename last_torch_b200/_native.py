@@ -48,6 +48,7 @@ SIGNATURES = {
                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_uint, _ptr],
     'lt_alphas_denormalize': [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr],
     'lt_linear_forward': [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr],
+    'lt_linear_tensor_core': [_c_i64, _c_int, _c_int],
     'lt_linear_wgrad_workspace_bytes': [_c_i64, _c_int, _c_int],
     'lt_linear_wgrad': [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr, _ptr],
     'lt_lattice_expectation_supported': [_c_int, _c_int, _c_int, _c_uint],

@@ -33,7 +33,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 static const char* const kOptionNames[OPT_COUNT] = {
     "LT_JOINT_SIMT", "LT_JOINT_DGRAD_V1", "LT_JOINT_WGRAD_SIMT", "LT_JOINT_DGRAD_PAIR",
     "LT_JOINT_DGRAD_MULTICAST", "LT_TABLE_V1", "LT_TABLE_CLUSTER", "LT_JOINT_FWD_SS",
-    "LT_JOINT_FWD_CLUSTER", "LT_FLD_GENERIC"};
+    "LT_JOINT_FWD_CLUSTER", "LT_FLD_GENERIC", "LT_LINEAR_SIMT"};
 static int g_options[OPT_COUNT];
 static std::once_flag g_options_once;
 

@@ -41,6 +41,7 @@ enum Option {
   OPT_JOINT_FWD_SS,           // LT_JOINT_FWD_SS: forward with the tanh operand in shared memory
   OPT_JOINT_FWD_CLUSTER,      // LT_JOINT_FWD_CLUSTER=1: no W_vocab multicast (one CTA per cluster)
   OPT_FLD_GENERIC,            // LT_FLD_GENERIC: FrameLabelDependent on bigram contexts uses the generic kernels
+  OPT_LINEAR_SIMT,            // LT_LINEAR_SIMT: lt_linear_* on CUDA cores even where the tcgen05 kernels apply
   OPT_COUNT
 };
 int option(Option o);

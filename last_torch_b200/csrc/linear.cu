@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "params.cuh"
+#include "umma.cuh"
 
 namespace lt {
 namespace {
@@ -165,6 +166,256 @@ __global__ void linear_wgrad_reduce_kernel(const float* __restrict__ part, float
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core variants (tcgen05, bf16x3 operand split, fp32 accumulation in tensor memory) for
+// the shapes of a production-sized joint network (D = E = H = 512 at the headline: 16.8 GFLOP
+// per projection, where the fp32 FMA kernels -- the library's or the ones above -- need 0.35 ms).
+// Same building blocks as the joint kernels (umma.cuh): operands are split into bf16 hi / lo
+// while they are staged into the SWIZZLE_128B shared-memory layout, three MMAs per product
+// (hi*hi, hi*lo, lo*hi: 2^-17 relative), one 128 x <=256 fp32 accumulator per CTA, two CTAs per SM
+// so that one stages while the other multiplies.
+__device__ __forceinline__ void lin_mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void lin_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LTL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LTL_DONE;\n"
+      "bra LTL_WAIT;\n"
+      "LTL_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// rows [0, nrows) x 64 K-elements of a row-major fp32 matrix -> bf16 hi / lo tiles, K-major
+// SWIZZLE_128B; rows at or beyond `valid` are written as zeros.  Four 32-byte pieces per thread
+// are in flight at a time.
+__device__ __forceinline__ void lin_fill_kmajor(const float* __restrict__ src, int64_t ld, int nrows,
+                                                int64_t valid, unsigned char* hi, unsigned char* lo,
+                                                int tid, int nthreads) {
+  for (int idx0 = tid; idx0 < nrows * 8; idx0 += 4 * nthreads) {
+    float4 v[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = idx0 + j * nthreads;
+      const int row = idx >> 3, chunk = idx & 7;
+      if (idx < nrows * 8 && row < valid) {
+        const float4* q = reinterpret_cast<const float4*>(src + (int64_t)row * ld + chunk * 8);
+        v[j][0] = q[0]; v[j][1] = q[1];
+      } else {
+        v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = idx0 + j * nthreads;
+      if (idx >= nrows * 8) break;
+      const int row = idx >> 3, chunk = idx & 7;
+      const float x[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w,
+                          v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+      uint4 h, l;
+      umma::split_pack8(x, h, l);
+      const uint32_t off = umma::swizzled_offset(row, chunk);
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  }
+}
+
+// y[m0 .. m0+128, n0 .. n0+nt] = x[.., K] . w[n0 .., K]^T ; K % 64 == 0, nt % 16 == 0, nt <= 256
+__global__ void __launch_bounds__(128, 2)
+linear_forward_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                         float* __restrict__ y, int64_t M, int K, int N) {
+  extern __shared__ __align__(1024) unsigned char lsm_raw[];
+  unsigned char* sm = lsm_raw + ((1024u - (smem_u32(lsm_raw) & 1023u)) & 1023u);
+  unsigned char* a_hi = sm;                          // 128 x 128 B
+  unsigned char* a_lo = a_hi + 128 * 128;
+  unsigned char* b_hi = a_lo + 128 * 128;            // 256 x 128 B
+  unsigned char* b_lo = b_hi + 256 * 128;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  const int n0 = blockIdx.y * 256;
+  const int nt = min(256, N - n0);
+  if (tid == 0) {
+    lin_mbar_init(smem_u32(&mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_base), 256);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = umma::make_idesc_bf16(128, nt);
+  const int nchunks = K / 64;
+  for (int kc = 0; kc < nchunks; ++kc) {
+    lin_fill_kmajor(x + m0 * K + kc * 64, K, 128, M - m0, a_hi, a_lo, tid, 128);
+    lin_fill_kmajor(w + (int64_t)n0 * K + kc * 64, K, nt, nt, b_hi, b_lo, tid, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_thread_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {           // 4 x (K = 16 bf16 = 32 bytes) per 128-byte row
+        const uint64_t dah = umma::make_smem_desc_sw128(smem_u32(a_hi) + k * 32);
+        const uint64_t dal = umma::make_smem_desc_sw128(smem_u32(a_lo) + k * 32);
+        const uint64_t dbh = umma::make_smem_desc_sw128(smem_u32(b_hi) + k * 32);
+        const uint64_t dbl = umma::make_smem_desc_sw128(smem_u32(b_lo) + k * 32);
+        umma::mma_bf16(tmem, dah, dbh, idesc, (kc | k) > 0);
+        umma::mma_bf16(tmem, dah, dbl, idesc, 1);
+        umma::mma_bf16(tmem, dal, dbh, idesc, 1);
+      }
+      umma::commit(smem_u32(&mbar));          // arrives when the MMAs above have completed
+    }
+    lin_mbar_wait(smem_u32(&mbar), kc & 1);   // the operand tiles may be overwritten after this
+  }
+  umma::fence_after_thread_sync();
+  // epilogue: warp w owns TMEM lanes (= rows) 32w .. 32w+31, 32 columns at a time
+  const int64_t row = m0 + warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < nt; c0 += 32) {
+    float v[32];
+    umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    if (row < M) {
+      float* dst = y + row * N + n0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (c0 + i < nt)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+// Weight gradient: part[s][n0 .. n0+128, k0 .. k0+kt] = sum over the rows m of split s of
+// gy[m, n0 ..]^T x[m, k0 ..]: both operands are contiguous along the OUTPUT dimensions (MN-major),
+// the reduction runs over M in chunks of 32 rows.  kt % 64 == 0, kt <= 256.
+__global__ void __launch_bounds__(128, 2)
+linear_wgrad_tc_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                       float* __restrict__ part, int64_t M, int K, int N, int64_t rows_per_split) {
+  extern __shared__ __align__(1024) unsigned char wsm_raw[];
+  unsigned char* sm = wsm_raw + ((1024u - (smem_u32(wsm_raw) & 1023u)) & 1023u);
+  unsigned char* a_hi = sm;                        // [128 x 32] bf16 = 8 KB
+  unsigned char* a_lo = a_hi + 128 * 32 * 2;
+  unsigned char* b_hi = a_lo + 128 * 32 * 2;      // [256 x 32] bf16 = 16 KB
+  unsigned char* b_lo = b_hi + 256 * 32 * 2;
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n0 = blockIdx.x * 128, k0 = blockIdx.y * 256;
+  const int kt = min(256, K - k0);
+  const int64_t mb = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t me = mb + rows_per_split < M ? mb + rows_per_split : M;
+  if (tid == 0) {
+    lin_mbar_init(smem_u32(&mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc(smem_u32(&tmem_base), 256);
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = umma::make_idesc_bf16_mn(128, kt);
+  const uint32_t a_sbo = (128 / 64) * 1024, b_sbo = (uint32_t)(kt / 64) * 1024, lbo = 1024;
+  int it = 0;
+  for (int64_t m = mb; m < me; m += 32, ++it) {
+    // A: gy rows m .. m+31 (the reduction index), 128 contiguous output features each
+    for (int idx = tid; idx < 32 * 16; idx += 128) {
+      const int r = idx >> 4, mn = (idx & 15) * 8;
+      float v[8];
+      if (m + r < me) {
+        const float4* q = reinterpret_cast<const float4*>(gy + (m + r) * N + n0 + mn);
+        const float4 q0 = q[0], q1 = q[1];
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+        v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      uint4 h, l;
+      umma::split_pack8(v, h, l);
+      const uint32_t off = umma::mn_major_chunk_offset(128, mn, r);
+      *reinterpret_cast<uint4*>(a_hi + off) = h;
+      *reinterpret_cast<uint4*>(a_lo + off) = l;
+    }
+    // B: x rows m .. m+31, kt contiguous input features each
+    for (int idx = tid; idx < 32 * (kt / 8); idx += 128) {
+      const int r = idx / (kt / 8), mn = (idx % (kt / 8)) * 8;
+      float v[8];
+      if (m + r < me) {
+        const float4* q = reinterpret_cast<const float4*>(x + (m + r) * K + k0 + mn);
+        const float4 q0 = q[0], q1 = q[1];
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+        v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      uint4 h, l;
+      umma::split_pack8(v, h, l);
+      const uint32_t off = umma::mn_major_chunk_offset(kt, mn, r);
+      *reinterpret_cast<uint4*>(b_hi + off) = h;
+      *reinterpret_cast<uint4*>(b_lo + off) = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_thread_sync();
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {            // K = 16 per instruction = 2 atoms deep
+        const uint32_t aoff = 2 * ks * a_sbo, boff = 2 * ks * b_sbo;
+        const uint64_t dah = umma::make_smem_desc_mn_sw128(smem_u32(a_hi) + aoff, lbo, a_sbo);
+        const uint64_t dal = umma::make_smem_desc_mn_sw128(smem_u32(a_lo) + aoff, lbo, a_sbo);
+        const uint64_t dbh = umma::make_smem_desc_mn_sw128(smem_u32(b_hi) + boff, lbo, b_sbo);
+        const uint64_t dbl = umma::make_smem_desc_mn_sw128(smem_u32(b_lo) + boff, lbo, b_sbo);
+        umma::mma_bf16(tmem, dah, dbh, idesc, (it | ks) > 0);
+        umma::mma_bf16(tmem, dah, dbl, idesc, 1);
+        umma::mma_bf16(tmem, dal, dbh, idesc, 1);
+      }
+      umma::commit(smem_u32(&mbar));
+    }
+    lin_mbar_wait(smem_u32(&mbar), it & 1);
+  }
+  umma::fence_after_thread_sync();
+  float* out = part + (size_t)blockIdx.z * N * K;
+  const int row = n0 + warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < kt; c0 += 32) {
+    float v[32];
+    if (it > 0) {
+      umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;     // a split without rows
+    }
+    if (row < N) {
+      float* dst = out + (size_t)row * K + k0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (c0 + i < kt)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+bool linear_tc_forward_ok(const void* x, const void* w, const void* y, int64_t M, int K, int N) {
+  return M >= 128 && K % 64 == 0 && N % 16 == 0 &&
+         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) |
+           reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+}
+// gw [N, K] = gy[M, N]^T x[M, K]
+bool linear_tc_wgrad_ok(const void* gy, const void* x, int64_t M, int K, int N) {
+  return M >= 1024 && N % 128 == 0 && K % 64 == 0 &&
+         ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+}
+
 int wgrad_slabs(int64_t M) {
   int64_t blocks = (M + kLinKC - 1) / kLinKC;
   return (int)(blocks < 64 ? (blocks < 1 ? 1 : blocks) : 64);
@@ -181,10 +432,30 @@ extern "C" int lt_linear_forward(const float* x, const float* w, float* y, int64
                (long long)M, K, N);
   if (M == 0) return LT_OK;
   LT_CHECK_ARG(x && w && y, "lt_linear_forward: NULL pointer");
+  if (!option(OPT_LINEAR_SIMT) && linear_tc_forward_ok(x, w, y, M, K, N)) {
+    const size_t smem = 2 * 128 * 128 + 2 * 256 * 128 + 1024;
+    LT_CUDA(cudaFuncSetAttribute(linear_forward_tc_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 tgrid((unsigned)((M + 127) / 128), (unsigned)((N + 255) / 256));
+    linear_forward_tc_kernel<<<tgrid, 128, smem, (cudaStream_t)stream>>>(x, w, y, M, K, N);
+    LT_LAUNCHED();
+    return LT_OK;
+  }
   dim3 grid((unsigned)((M + kLinTile - 1) / kLinTile), (unsigned)((N + kLinTile - 1) / kLinTile));
   linear_forward_kernel<<<grid, kLinThreads, 0, (cudaStream_t)stream>>>(x, w, y, M, K, N);
   LT_LAUNCHED();
   return LT_OK;
+}
+
+// 1 when lt_linear_forward / lt_linear_wgrad take the tcgen05 kernels for [M, K] x [N, K]
+// (16-byte aligned buffers assumed) AND the product is large enough for them to beat an fp32 FMA
+// GEMM: measured 0.123 vs 0.33 ms (forward) and 0.24 vs 0.38 ms (weight gradient) at
+// 32000 x 512 x 512, but 0.040 vs 0.015 ms at 257 x 512 x 512.
+extern "C" int lt_linear_tensor_core(int64_t M, int K, int N) {
+  const void* aligned = reinterpret_cast<const void*>(uintptr_t(256));
+  if (option(OPT_LINEAR_SIMT) || M < 4096) return 0;
+  return (linear_tc_forward_ok(aligned, aligned, aligned, M, K, N) &&
+          linear_tc_wgrad_ok(aligned, aligned, M, K, N)) ? 1 : 0;
 }
 
 extern "C" int64_t lt_linear_wgrad_workspace_bytes(int64_t M, int K, int N) {
@@ -200,10 +471,32 @@ extern "C" int lt_linear_wgrad(const float* gy, const float* x, float* gw, int64
     LT_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)N * K, (cudaStream_t)stream));
     return LT_OK;
   }
+  float* part = reinterpret_cast<float*>(workspace);
+  if (!option(OPT_LINEAR_SIMT) && linear_tc_wgrad_ok(gy, x, M, K, N)) {
+    // as many splits of the reduction as fill the chip twice over, at most the workspace's
+    // slabs; every split is a multiple of 32 rows
+    const int tiles = (N / 128) * ((K + 255) / 256);
+    int S = (2 * 148 + tiles - 1) / tiles;
+    const int smax = wgrad_slabs(M);
+    S = S < 1 ? 1 : (S > smax ? smax : S);
+    int64_t rows = (M + S - 1) / S;
+    rows = (rows + 31) / 32 * 32;
+    S = (int)((M + rows - 1) / rows);
+    const size_t smem = 2 * 128 * 64 + 2 * 256 * 64 + 1024;
+    LT_CUDA(cudaFuncSetAttribute(linear_wgrad_tc_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 tgrid((unsigned)(N / 128), (unsigned)((K + 255) / 256), (unsigned)S);
+    linear_wgrad_tc_kernel<<<tgrid, 128, smem, (cudaStream_t)stream>>>(gy, x, part, M, K, N, rows);
+    LT_LAUNCHED();
+    const int64_t nk = (int64_t)N * K;
+    linear_wgrad_reduce_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        part, gw, S, nk);
+    LT_LAUNCHED();
+    return LT_OK;
+  }
   const int S = wgrad_slabs(M);
   dim3 grid((unsigned)S, (unsigned)((N + kLinTile - 1) / kLinTile),
             (unsigned)((K + kLinKC - 1) / kLinKC));
-  float* part = reinterpret_cast<float*>(workspace);
   linear_wgrad_partial_kernel<<<grid, kLinThreads, 0, (cudaStream_t)stream>>>(gy, x, part, M, K, N);
   LT_LAUNCHED();
   const int64_t nk = (int64_t)N * K;

@@ -126,6 +126,10 @@ class _Linear(torch.autograd.Function):
 # 0.074 / 0.136 ms for the library sgemm behind nn.Linear -- so the library call stays the default
 # and the library's own kernels are the opt-in path (LT_OWN_LINEAR=1) for a build without cuBLAS.
 OWN_LINEAR = os.environ.get('LT_OWN_LINEAR', '0') == '1'
+# LT_NO_TC_LINEAR=1: nn.Linear also for projections the tcgen05 kernels would take
+# (lt_linear_tensor_core: M >= 4096, K % 64 == 0, N % 128 == 0; 0.12 + 0.24 ms against the library
+# sgemm's 0.33 + 0.38 ms at 32000 x 512 x 512)
+NO_TC_LINEAR = os.environ.get('LT_NO_TC_LINEAR', '0') == '1'
 
 
 def joint_projections(fn, cache, frames):
@@ -135,7 +139,18 @@ def joint_projections(fn, cache, frames):
   if OWN_LINEAR:
     return (_Linear.apply(cache, fn.context_projection.weight),
             _Linear.apply(flat, fn.blank_projection.weight))
-  return fn.context_projection(cache), fn.blank_projection(flat)
+
+  def project(layer, x):
+    # a production-sized frame projection ([B T, D] x [H, D], 16.8 GFLOP at the headline shape)
+    # runs on the library's tcgen05 kernels; small products stay with nn.Linear's sgemm
+    w = layer.weight
+    if (not NO_TC_LINEAR and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
+        and N.lib().lt_linear_tensor_core(x.shape[0], x.shape[1], w.shape[0])
+        and x.data_ptr() % 16 == 0):
+      return _Linear.apply(x, w)
+    return layer(x)
+
+  return project(fn.context_projection, cache), project(fn.blank_projection, flat)
 
 
 def joint_all_frames(fn, cache, frames):

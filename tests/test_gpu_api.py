@@ -927,10 +927,13 @@ def test_example_training_loop_reduces_the_loss():
 
 
 @pytest.mark.parametrize('m,k,n', [(32000, 80, 512), (257, 512, 512), (130, 33, 70), (1, 5, 3),
-                                   (4097, 128, 129)])
+                                   (4097, 128, 129), (32000, 512, 512), (5001, 192, 256),
+                                   (1500, 64, 128), (2049, 320, 384)])
 def test_input_projection_kernels_match_torch(m, k, n):
   """lt_linear_forward / lt_linear_wgrad (the bias-free input projections of JointWeightFn,
-  weight_fns.py:208-211) against torch in float64: values, both gradients, odd shapes."""
+  weight_fns.py:208-211) against torch in float64: values, both gradients, odd shapes.  Shapes
+  with 64-multiples take the tcgen05 kernels (bf16x3 split: 1e-5 of the scale), the others the
+  fp32 FMA kernels (2e-6)."""
   from last_torch_b200.joint import _Linear
   g = torch.Generator(device='cuda').manual_seed(m + k + n)
   x = torch.randn([m, k], device='cuda', generator=g, requires_grad=True)
@@ -941,9 +944,10 @@ def test_input_projection_kernels_match_torch(m, k, n):
   xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
   yd = xd @ wd.T
   gxd, gwd = torch.autograd.grad(yd, [xd, wd], gy.double())
+  tol = 1e-5 if (k % 64 == 0 or n % 64 == 0) and m >= 128 else 2e-6
   for got, want in ((y, yd), (gx, gxd), (gw, gwd)):
     scale = float(want.abs().max()) + 1e-30
-    assert float((got.double() - want).abs().max()) <= 2e-6 * scale
+    assert float((got.double() - want).abs().max()) <= tol * scale
   # the weight gradient is reduced in a fixed order: bit-identical from run to run
   (gw2,) = torch.autograd.grad(_Linear.apply(x, w), [w], gy)
   assert torch.equal(gw, gw2)
@@ -976,6 +980,46 @@ def test_own_input_projection_kernels_through_the_lattice(monkeypatch):
   l0, g0 = run(False)
   l1, g1 = run(True)
   npt.assert_allclose(l1.cpu(), l0.cpu(), rtol=2e-6)
+  for a, b in zip(g1, g0):
+    scale = float(b.abs().max()) + 1e-30
+    assert float((a - b).abs().max()) <= 2e-5 * scale
+
+
+def test_tensor_core_frame_projection_through_the_lattice(monkeypatch):
+  """A frame projection large enough for the tcgen05 kernels (B T = 4400 frames, feature size 64,
+  hidden size 128: lt_linear_tensor_core) against nn.Linear's sgemm through
+  RecognitionLattice.forward + backward: same loss, same gradients to the bf16x3 split's 1e-5."""
+  lt = _lt()
+  from last_torch_b200 import joint
+  from last_torch_b200 import _native as N
+  assert N.lib().lt_linear_tensor_core(4400, 64, 128) == 1
+  assert N.lib().lt_linear_tensor_core(300, 64, 128) == 0          # too small to pay
+  assert N.lib().lt_linear_tensor_core(4400, 80, 128) == 0         # K % 64
+
+  def run(no_tc):
+    monkeypatch.setattr(joint, 'NO_TC_LINEAR', no_tc)
+    torch.manual_seed(33)
+    lattice = lt.RecognitionLattice(
+        context=lt.contexts.FullNGram(vocab_size=64, context_size=1),
+        alignment=lt.alignments.FrameDependent(),
+        weight_fn_cacher_factory=lambda c: lt.weight_fns.SharedEmbCacher(
+            num_context_states=c.shape()[0], embedding_size=40, device='cuda'),
+        weight_fn_factory=lambda c: lt.weight_fns.JointWeightFn(
+            vocab_size=c.shape()[1], hidden_size=128, device='cuda', embedding_size=40,
+            feature_size=64))
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn([4, 1100, 64], device='cuda', generator=g)
+    labels = torch.randint(1, 65, [4, 30], device='cuda', generator=g)
+    before = N.lib().lt_launch_count()
+    loss = lattice(frames=x, num_frames=T([1100, 800, 1100, 640]), labels=labels,
+                   num_labels=T([30, 12, 0, 25]))
+    grads = torch.autograd.grad(loss.sum(), list(lattice.parameters()))
+    return loss.detach(), grads, N.lib().lt_launch_count() - before
+
+  l0, g0, n0 = run(True)
+  l1, g1, n1 = run(False)
+  assert n1 == n0 + 3            # lt_linear_forward + lt_linear_wgrad (partials, reduction)
+  npt.assert_allclose(l1.cpu(), l0.cpu(), rtol=1e-5)
   for a, b in zip(g1, g0):
     scale = float(b.abs().max()) + 1e-30
     assert float((a - b).abs().max()) <= 2e-5 * scale

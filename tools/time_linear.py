@@ -11,7 +11,7 @@ def t(fn, n=20):
   for _ in range(n): fn()
   e.record(); torch.cuda.synchronize()
   return s.elapsed_time(e) / n
-for m, k, n in [(32000, 80, 512), (257, 512, 512)]:
+for m, k, n in [(32000, 80, 512), (257, 512, 512), (32000, 512, 512)]:
   x = torch.randn([m, k], device='cuda'); w = torch.randn([n, k], device='cuda'); gy = torch.randn([m, n], device='cuda')
   gw = torch.empty_like(w)
   ws = torch.empty([int(N.lib().lt_linear_wgrad_workspace_bytes(m, k, n))], dtype=torch.uint8, device='cuda')
