@@ -132,6 +132,17 @@ OWN_LINEAR = os.environ.get('LT_OWN_LINEAR', '0') == '1'
 NO_TC_LINEAR = os.environ.get('LT_NO_TC_LINEAR', '0') == '1'
 
 
+_TC_LINEAR_SHAPES = {}
+
+
+def _tensor_core_linear(m, k, n):
+  """lt_linear_tensor_core(m, k, n), asked once per shape (a host-side query, no kernel)."""
+  key = (int(m), int(k), int(n))
+  if key not in _TC_LINEAR_SHAPES:
+    _TC_LINEAR_SHAPES[key] = bool(N.lib().lt_linear_tensor_core(*key))
+  return _TC_LINEAR_SHAPES[key]
+
+
 def joint_projections(fn, cache, frames):
   """The two bias-free input projections in front of the joint kernel: proj_ctx [C,H],
   proj_frame [N,H] (weight_fns.py:208-211)."""
@@ -145,8 +156,7 @@ def joint_projections(fn, cache, frames):
     # runs on the library's tcgen05 kernels; small products stay with nn.Linear's sgemm
     w = layer.weight
     if (not NO_TC_LINEAR and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32
-        and N.lib().lt_linear_tensor_core(x.shape[0], x.shape[1], w.shape[0])
-        and x.data_ptr() % 16 == 0):
+        and _tensor_core_linear(x.shape[0], x.shape[1], w.shape[0]) and x.data_ptr() % 16 == 0):
       return _Linear.apply(x, w)
     return layer(x)
 
