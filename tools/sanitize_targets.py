@@ -205,6 +205,38 @@ def raw_joint_forward(name, c, vocab, hidden, n, repeats=6):
   print(f'ok {name}: {repeats} bit-identical runs, guard bands intact', flush=True)
 
 
+def raw_linear(name, m, k, n, repeats=6):
+  """lt_linear_forward / lt_linear_wgrad on the tcgen05 path (operand tiles staged and split in
+  shared memory, one mbarrier per CTA, split-K partials reduced in a fixed order): guarded outputs,
+  bit-identical runs, equal to the CUDA-core kernels to the operand split's 1e-5."""
+  g = torch.Generator(device='cuda').manual_seed(m + k + n)
+  x = torch.randn([m, k], device='cuda', generator=g)
+  w = torch.randn([n, k], device='cuda', generator=g) / k ** 0.5
+  gy = torch.randn([m, n], device='cuda', generator=g)
+  L = N.lib()
+  ws = torch.empty([int(L.lt_linear_wgrad_workspace_bytes(m, k, n))], dtype=torch.uint8,
+                   device='cuda')
+
+  def once():
+    y, c1 = guarded([m, n])
+    gw, c2 = guarded([n, k])
+    N.check(L.lt_linear_forward(N.ptr(x), N.ptr(w), N.ptr(y), m, k, n, N.stream_ptr(x.device)),
+            'lt_linear_forward')
+    N.check(L.lt_linear_wgrad(N.ptr(gy), N.ptr(x), N.ptr(gw), m, k, n, N.ptr(ws),
+                              N.stream_ptr(x.device)), 'lt_linear_wgrad')
+    c1(); c2()
+    return y.clone(), gw.clone()
+
+  outs = [once() for _ in range(repeats)]
+  for o in outs[1:]:
+    assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]), f'{name}: run-to-run'
+  with N.option('LT_LINEAR_SIMT', 1):
+    y0, gw0 = once()
+  for a, b in zip(outs[0], (y0, gw0)):
+    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), name
+  print(f'ok {name}: {repeats} bit-identical runs, guard bands intact', flush=True)
+
+
 def expectation_family(vocab, b, t, repeats=4):
   """lt_lattice_expectation (K2 with posterior x value summed on the fly): bit-identical runs and
   equal to posteriors x values through the generic kernels."""
@@ -223,6 +255,8 @@ def expectation_family(vocab, b, t, repeats=4):
 
 
 def main():
+  raw_linear('lt_linear tcgen05 5001 x 192 -> 256 (ragged last row tile, 26 splits)', 5001, 192, 256)
+  raw_linear('lt_linear tcgen05 32000 x 512 -> 512', 32000, 512, 512, repeats=3)
   raw_lattice_pair('lattice_fast2 vocab 256, cluster of 8, 33 utterances', 256, 1, -1, 33, 40)
   raw_lattice_pair('lattice_fast2_fld FrameLabelDependent(2) vocab 256, 33 utterances', 256, 1, 2,
                    33, 24)
