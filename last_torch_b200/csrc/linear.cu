@@ -175,6 +175,8 @@ __global__ void linear_wgrad_reduce_kernel(const float* __restrict__ part, float
 // while they are staged into the SWIZZLE_128B shared-memory layout, three MMAs per product
 // (hi*hi, hi*lo, lo*hi: 2^-17 relative), one 128 x <=256 fp32 accumulator per CTA, two CTAs per SM
 // so that one stages while the other multiplies.
+constexpr int kLinTcThreads = 256;   // warps 0-3 and 4-7 share the TMEM lane quadrants in the epilogue
+
 __device__ __forceinline__ void lin_mbar_init(uint32_t bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
 }
@@ -226,7 +228,7 @@ __device__ __forceinline__ void lin_fill_kmajor(const float* __restrict__ src, i
 }
 
 // y[m0 .. m0+128, n0 .. n0+nt] = x[.., K] . w[n0 .., K]^T ; K % 64 == 0, nt % 16 == 0, nt <= 256
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kLinTcThreads, 2)
 linear_forward_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                          float* __restrict__ y, int64_t M, int K, int N) {
   extern __shared__ __align__(1024) unsigned char lsm_raw[];
@@ -253,8 +255,8 @@ linear_forward_tc_kernel(const float* __restrict__ x, const float* __restrict__ 
   const uint32_t idesc = umma::make_idesc_bf16(128, nt);
   const int nchunks = K / 64;
   for (int kc = 0; kc < nchunks; ++kc) {
-    lin_fill_kmajor(x + m0 * K + kc * 64, K, 128, M - m0, a_hi, a_lo, tid, 128);
-    lin_fill_kmajor(w + (int64_t)n0 * K + kc * 64, K, nt, nt, b_hi, b_lo, tid, 128);
+    lin_fill_kmajor(x + m0 * K + kc * 64, K, 128, M - m0, a_hi, a_lo, tid, kLinTcThreads);
+    lin_fill_kmajor(w + (int64_t)n0 * K + kc * 64, K, nt, nt, b_hi, b_lo, tid, kLinTcThreads);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> async proxy
     __syncthreads();
     if (tid == 0) {
@@ -274,11 +276,13 @@ linear_forward_tc_kernel(const float* __restrict__ x, const float* __restrict__ 
     lin_mbar_wait(smem_u32(&mbar), kc & 1);   // the operand tiles may be overwritten after this
   }
   umma::fence_after_thread_sync();
-  // epilogue: warp w owns TMEM lanes (= rows) 32w .. 32w+31, 32 columns at a time
-  const int64_t row = m0 + warp * 32 + (tid & 31);
-  for (int c0 = 0; c0 < nt; c0 += 32) {
+  // epilogue: warp w (and w + 4 for the other half of the columns) owns TMEM lanes (= rows)
+  // 32 (w % 4) .. + 31, 32 columns at a time
+  const int q = warp & 3, half = warp >> 2;
+  const int64_t row = m0 + q * 32 + (tid & 31);
+  for (int c0 = half * 32; c0 < nt; c0 += 64) {
     float v[32];
-    umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
     if (row < M) {
       float* dst = y + row * N + n0 + c0;
 #pragma unroll
@@ -295,7 +299,7 @@ linear_forward_tc_kernel(const float* __restrict__ x, const float* __restrict__ 
 // Weight gradient: part[s][n0 .. n0+128, k0 .. k0+kt] = sum over the rows m of split s of
 // gy[m, n0 ..]^T x[m, k0 ..]: both operands are contiguous along the OUTPUT dimensions (MN-major),
 // the reduction runs over M in chunks of 32 rows.  kt % 64 == 0, kt <= 256.
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kLinTcThreads, 2)
 linear_wgrad_tc_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                        float* __restrict__ part, int64_t M, int K, int N, int64_t rows_per_split) {
   extern __shared__ __align__(1024) unsigned char wsm_raw[];
@@ -325,7 +329,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ gy, const float* __restrict__ x
   int it = 0;
   for (int64_t m = mb; m < me; m += 32, ++it) {
     // A: gy rows m .. m+31 (the reduction index), 128 contiguous output features each
-    for (int idx = tid; idx < 32 * 16; idx += 128) {
+    for (int idx = tid; idx < 32 * 16; idx += kLinTcThreads) {
       const int r = idx >> 4, mn = (idx & 15) * 8;
       float v[8];
       if (m + r < me) {
@@ -344,7 +348,7 @@ linear_wgrad_tc_kernel(const float* __restrict__ gy, const float* __restrict__ x
       *reinterpret_cast<uint4*>(a_lo + off) = l;
     }
     // B: x rows m .. m+31, kt contiguous input features each
-    for (int idx = tid; idx < 32 * (kt / 8); idx += 128) {
+    for (int idx = tid; idx < 32 * (kt / 8); idx += kLinTcThreads) {
       const int r = idx / (kt / 8), mn = (idx % (kt / 8)) * 8;
       float v[8];
       if (m + r < me) {
@@ -383,11 +387,12 @@ linear_wgrad_tc_kernel(const float* __restrict__ gy, const float* __restrict__ x
   }
   umma::fence_after_thread_sync();
   float* out = part + (size_t)blockIdx.z * N * K;
-  const int row = n0 + warp * 32 + (tid & 31);
-  for (int c0 = 0; c0 < kt; c0 += 32) {
+  const int q = warp & 3, half = warp >> 2;
+  const int row = n0 + q * 32 + (tid & 31);
+  for (int c0 = half * 32; c0 < kt; c0 += 64) {
     float v[32];
     if (it > 0) {
-      umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;     // a split without rows
@@ -437,7 +442,7 @@ extern "C" int lt_linear_forward(const float* x, const float* w, float* y, int64
     LT_CUDA(cudaFuncSetAttribute(linear_forward_tc_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 tgrid((unsigned)((M + 127) / 128), (unsigned)((N + 255) / 256));
-    linear_forward_tc_kernel<<<tgrid, 128, smem, (cudaStream_t)stream>>>(x, w, y, M, K, N);
+    linear_forward_tc_kernel<<<tgrid, kLinTcThreads, smem, (cudaStream_t)stream>>>(x, w, y, M, K, N);
     LT_LAUNCHED();
     return LT_OK;
   }
@@ -449,7 +454,7 @@ extern "C" int lt_linear_forward(const float* x, const float* w, float* y, int64
 
 // 1 when lt_linear_forward / lt_linear_wgrad take the tcgen05 kernels for [M, K] x [N, K]
 // (16-byte aligned buffers assumed) AND the product is large enough for them to beat an fp32 FMA
-// GEMM: measured 0.123 vs 0.33 ms (forward) and 0.24 vs 0.38 ms (weight gradient) at
+// GEMM: measured 0.109 vs 0.33 ms (forward) and 0.147 vs 0.38 ms (weight gradient) at
 // 32000 x 512 x 512, but 0.040 vs 0.015 ms at 257 x 512 x 512.
 extern "C" int lt_linear_tensor_core(int64_t M, int K, int N) {
   const void* aligned = reinterpret_cast<const void*>(uintptr_t(256));
@@ -486,7 +491,7 @@ extern "C" int lt_linear_wgrad(const float* gy, const float* x, float* gw, int64
     LT_CUDA(cudaFuncSetAttribute(linear_wgrad_tc_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 tgrid((unsigned)(N / 128), (unsigned)((K + 255) / 256), (unsigned)S);
-    linear_wgrad_tc_kernel<<<tgrid, 128, smem, (cudaStream_t)stream>>>(gy, x, part, M, K, N, rows);
+    linear_wgrad_tc_kernel<<<tgrid, kLinTcThreads, smem, (cudaStream_t)stream>>>(gy, x, part, M, K, N, rows);
     LT_LAUNCHED();
     const int64_t nk = (int64_t)N * K;
     linear_wgrad_reduce_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

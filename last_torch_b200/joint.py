@@ -127,7 +127,7 @@ class _Linear(torch.autograd.Function):
 # and the library's own kernels are the opt-in path (LT_OWN_LINEAR=1) for a build without cuBLAS.
 OWN_LINEAR = os.environ.get('LT_OWN_LINEAR', '0') == '1'
 # LT_NO_TC_LINEAR=1: nn.Linear also for projections the tcgen05 kernels would take
-# (lt_linear_tensor_core: M >= 4096, K % 64 == 0, N % 128 == 0; 0.12 + 0.24 ms against the library
+# (lt_linear_tensor_core: M >= 4096, K % 64 == 0, N % 128 == 0; 0.11 + 0.15 ms against the library
 # sgemm's 0.33 + 0.38 ms at 32000 x 512 x 512)
 NO_TC_LINEAR = os.environ.get('LT_NO_TC_LINEAR', '0') == '1'
 

@@ -16,7 +16,7 @@ for s in $STEPS; do
     prof)     CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-extras"
               $CMD > gpurun_out/prof_plain.log 2>&1 && \
               ncu --set full --clock-control none --import-source on \
-                  -k regex:"fast2|joint_forward_t|joint_dgrad2|joint_wgrad_tc" -c 10 \
+                  -k regex:"fast2|joint_forward_t|joint_dgrad2|joint_wgrad_tc|linear_.*_tc" -c 12 \
                   -f -o gpurun_out/r02_prof $CMD > gpurun_out/prof_ncu.log 2>&1; echo "prof rc=$?"; tail -n 3 gpurun_out/prof_ncu.log ;;
     launches) CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-extras"
               $CMD > gpurun_out/launches_plain.log 2>&1 && \
